@@ -1,0 +1,60 @@
+// Host-side launchers of the ddh kernels.  All launches are asynchronous on `st`.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace ddh {
+
+// scalar constants of the elementwise stages
+struct OdoConsts {
+  float lidar_max_x, lidar_max_y;
+};
+struct DdimCoef {
+  float sqrt_ac_t, sqrt_1m_ac_t, sqrt_ac_prev, sqrt_1m_ac_prev;
+};
+
+// ---- kernels_simt.cu -------------------------------------------------------------
+void launch_simt_gemm(const GemmParams& p, int n_total, cudaStream_t st);
+void launch_simt_conv(const GemmParams& p, int B, cudaStream_t st);
+
+void launch_bev_to_nhwc(const void* src, int src_dtype, void* dst, int dst_dtype, int B, int C,
+                        int HW, cudaStream_t st);
+void launch_cast_f32_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t st);
+void launch_cast_bf16_f32(const __nv_bfloat16* src, float* dst, size_t n, cudaStream_t st);
+
+void launch_init_img(const float* anchors, const float* noise, float* img, int B, int AP,
+                     float sqrt_ac, float sqrt_1m_ac, cudaStream_t st);
+void launch_embed(const float* img, float* pts, float* emb32, __nv_bfloat16* emb16, int M, int P,
+                  const float* dim_t_dev, cudaStream_t st);
+void launch_plan(const float* q0, const float* attw_w, const float* attw_b, const float* pts,
+                 int* upix, int* nuniq, int* ent_slot, float* ent_w, int B, int A, int P, int H,
+                 int W, int rcap, OdoConsts oc, cudaStream_t st);
+void launch_combine(const float* V, const int* ent_slot, const float* ent_w, float* s32,
+                    __nv_bfloat16* s16, int B, int A, int P, int rcap, cudaStream_t st);
+void launch_attn_core(const float* qh, const float* kv, float* o32, __nv_bfloat16* o16, int B,
+                      int A, int Na, int heads, cudaStream_t st);
+void launch_reg_finish(const float* r2, const float* w4, const float* b4, float* pts, float* img,
+                       float* modes, int M, int P, int do_ddim, DdimCoef dc, cudaStream_t st);
+void launch_select(const float* scores, const float* modes, float* traj, long long* mode_idx,
+                   int B, int A, int P, cudaStream_t st);
+
+// pack-time helpers
+void launch_transpose_f32(const float* src, float* dst, int rows, int cols, cudaStream_t st);
+void launch_pack_conv_f32(const float* w, float* dst, int Cout, int Cin, cudaStream_t st);
+void launch_pack_conv_bf16(const float* w, __nv_bfloat16* dst, int Cout, int Cin,
+                           cudaStream_t st);
+void launch_matvec(const float* W, const float* x, const float* b, float* y, int n_out, int k,
+                   int act_in_mish, cudaStream_t st);
+void launch_time_sinemb(float* emb, int dim, int timestep, cudaStream_t st);
+
+// ---- kernels_tc.cu (tcgen05 / TMEM / TMA engine) ----------------------------------
+// W is described by a TMA tensor map over a bf16 [N_total][K] matrix (box 64 x 256,
+// 128-byte swizzle).  A is bf16 [M][lda] (dense) or gathered from the NHWC bf16 BEV map.
+void launch_tc_gemm(const GemmParams& p, const CUtensorMap& wmap, int n_total, cudaStream_t st);
+void launch_tc_conv(const GemmParams& p, const CUtensorMap& wmap, int B, cudaStream_t st);
+int tc_engine_init();   // sets max dynamic smem attributes; returns cudaError_t as int
+
+}  // namespace ddh

@@ -1,0 +1,791 @@
+// CUDA-core (fp32) kernels of the ddh planning head: the fp32-precision GEMM/conv engine
+// and every non-GEMM stage (layout conversion, sine embedding, BEV sampling plan, bilinear
+// combine, agent attention core, regression tail + DDIM, mode selection).
+//
+// Reference lines are cited per kernel (paths relative to
+// navsim/agents/diffusiondrive/ of seulbinHwang/DiffusionDrive).
+#include <math.h>
+
+#include "kernels.h"
+
+namespace ddh {
+
+// ===================================================================================
+// fp32 GEMM engine:  C[m, n0:n0+256] = A[m,:] . Wt[:, n0:n0+256]  (+ fused row epilogue)
+// Tile 64 rows x 256 cols x 16 k, 256 threads, 8x8 outputs per thread.
+// CONV = true gathers A rows from the NHWC fp32 BEV map (value_proj conv evaluated at the
+// sampled pixels only, modules/blocks.py:68-76,114).
+// ===================================================================================
+constexpr int SG_BM = 64, SG_BK = 16, SG_THREADS = 256;
+constexpr int SG_AS_LD = SG_BM + 4;
+constexpr int SG_SMEM_BYTES = (SG_BK * SG_AS_LD + SG_BK * D + SG_BM * D) * 4 + SG_BM * 4;
+
+template <bool CONV>
+__global__ void __launch_bounds__(SG_THREADS, 2) simt_gemm_kernel(const GemmParams p) {
+  extern __shared__ __align__(16) float smem[];
+  float* As = smem;                         // [BK][AS_LD]  (k-major: As[k][row])
+  float* Ws = As + SG_BK * SG_AS_LD;        // [BK][256]
+  float* Cs = Ws + SG_BK * D;               // [BM][256]
+  int* s_pix = reinterpret_cast<int*>(Cs + SG_BM * D);  // [BM] (conv only)
+
+  const int tid = threadIdx.x;
+  const int tx = tid & 31, ty = tid >> 5;
+  const int n0 = CONV ? 0 : blockIdx.y * D;
+  int row0, rows_valid;
+  long long out_row0;
+  int scene = 0;
+  if (CONV) {
+    scene = blockIdx.y;
+    const int nu = p.nuniq[scene];
+    row0 = blockIdx.x * SG_BM;
+    if (row0 >= nu) return;
+    rows_valid = min(SG_BM, nu - row0);
+    out_row0 = (long long)scene * p.rcap + row0;
+    if (tid < SG_BM) s_pix[tid] = (tid < rows_valid) ? p.upix[(long long)scene * p.rcap + row0 + tid] : -1;
+    __syncthreads();
+  } else {
+    row0 = blockIdx.x * SG_BM;
+    rows_valid = min(SG_BM, p.M - row0);
+    out_row0 = row0;
+  }
+
+  // A-tile load mapping: thread -> (row = tid/4, 4 consecutive k at (tid%4)*4)
+  const int a_row = tid >> 2, a_kq = (tid & 3) * 4;
+  const float* Af = reinterpret_cast<const float*>(p.A);
+  const float* bev = reinterpret_cast<const float*>(p.bev);
+  int a_y = 0, a_x = 0;
+  bool a_valid = a_row < rows_valid;
+  if (CONV && a_valid) {
+    const int pix = s_pix[a_row];
+    a_y = pix / p.W_;
+    a_x = pix - a_y * p.W_;
+  }
+  const float* Wt = reinterpret_cast<const float*>(p.W) + n0;
+
+  auto load_a = [&](int k0) -> float4 {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a_valid) {
+      if (CONV) {
+        const int tap = k0 / p.C, c0 = k0 - tap * p.C;
+        const int yy = a_y + tap / 3 - 1, xx = a_x + tap % 3 - 1;
+        if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W_) {
+          const float* src = bev + (((long long)scene * p.H + yy) * p.W_ + xx) * p.C + c0 + a_kq;
+          v = *reinterpret_cast<const float4*>(src);
+        }
+      } else {
+        v = *reinterpret_cast<const float4*>(Af + (long long)(row0 + a_row) * p.lda + k0 + a_kq);
+      }
+    }
+    return v;
+  };
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  const int nk = p.K / SG_BK;
+  float4 a_reg = load_a(0);
+  float4 w_reg[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = tid + i * SG_THREADS;  // float4 index in [BK][64]
+    const int k = idx >> 6, c4 = idx & 63;
+    w_reg[i] = *reinterpret_cast<const float4*>(Wt + (long long)k * p.ldw + c4 * 4);
+  }
+
+  for (int kc = 0; kc < nk; ++kc) {
+    // registers -> smem
+    As[(a_kq + 0) * SG_AS_LD + a_row] = a_reg.x;
+    As[(a_kq + 1) * SG_AS_LD + a_row] = a_reg.y;
+    As[(a_kq + 2) * SG_AS_LD + a_row] = a_reg.z;
+    As[(a_kq + 3) * SG_AS_LD + a_row] = a_reg.w;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + i * SG_THREADS;
+      *reinterpret_cast<float4*>(Ws + idx * 4) = w_reg[i];
+    }
+    __syncthreads();
+    if (kc + 1 < nk) {  // prefetch next tile into registers
+      const int k0 = (kc + 1) * SG_BK;
+      a_reg = load_a(k0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int idx = tid + i * SG_THREADS;
+        const int k = idx >> 6, c4 = idx & 63;
+        w_reg[i] = *reinterpret_cast<const float4*>(Wt + (long long)(k0 + k) * p.ldw + c4 * 4);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < SG_BK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(As + k * SG_AS_LD + ty * 8);
+      const float4 a1 = *reinterpret_cast<const float4*>(As + k * SG_AS_LD + ty * 8 + 4);
+      const float4 w0 = *reinterpret_cast<const float4*>(Ws + k * D + tx * 4);
+      const float4 w1 = *reinterpret_cast<const float4*>(Ws + k * D + 128 + tx * 4);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  // stage the tile, then one warp per row runs the shared epilogue
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float* c = Cs + (ty * 8 + i) * D;
+    *reinterpret_cast<float4*>(c + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    *reinterpret_cast<float4*>(c + 128 + tx * 4) =
+        make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+  }
+  __syncthreads();
+  for (int r = ty; r < rows_valid; r += SG_THREADS / 32) {
+    float v[8];
+    load8(Cs + r * D, tx, v);
+    row_epilogue(p.epi, v, out_row0 + r, n0, tx);
+  }
+}
+
+void launch_simt_gemm(const GemmParams& p, int n_total, cudaStream_t st) {
+  static bool once = false;
+  if (!once) {
+    cudaFuncSetAttribute(simt_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         SG_SMEM_BYTES);
+    cudaFuncSetAttribute(simt_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         SG_SMEM_BYTES);
+    once = true;
+  }
+  dim3 grid((p.M + SG_BM - 1) / SG_BM, n_total / D);
+  simt_gemm_kernel<false><<<grid, SG_THREADS, SG_SMEM_BYTES, st>>>(p);
+}
+
+void launch_simt_conv(const GemmParams& p, int B, cudaStream_t st) {
+  static bool once = false;
+  if (!once) {
+    cudaFuncSetAttribute(simt_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         SG_SMEM_BYTES);
+    cudaFuncSetAttribute(simt_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         SG_SMEM_BYTES);
+    once = true;
+  }
+  dim3 grid((p.rcap + SG_BM - 1) / SG_BM, B);
+  simt_gemm_kernel<true><<<grid, SG_THREADS, SG_SMEM_BYTES, st>>>(p);
+}
+
+// ===================================================================================
+// BEV layout conversion  [B][C][HW] (NCHW)  ->  [B][HW][C] (NHWC), optional dtype change.
+// The reference hands the head NCHW fp32 (transfuser_model_v2.py:138-140); the gather of
+// the on-demand value_proj wants all channels of one pixel contiguous.
+// One CTA moves a 64-pixel x 256-channel tile through shared memory: coalesced 256-byte
+// reads along HW, coalesced 128-byte writes along C.  HBM-bound: 4 B read + 2|4 B written
+// per element.
+// ===================================================================================
+template <typename TI>
+__device__ __forceinline__ float4 ld4(const TI* p);
+template <>
+__device__ __forceinline__ float4 ld4<float>(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+template <>
+__device__ __forceinline__ float4 ld4<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+  const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+  return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+}
+
+constexpr int TP_PX = 64;
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) bev_to_nhwc_kernel(const TI* __restrict__ src,
+                                                          TO* __restrict__ dst, int C, int HW) {
+  // tile[px][c], padded so that the transposing stores are conflict free
+  constexpr int LDW = (sizeof(TO) == 2) ? 129 : 257;  // 32-bit words per pixel row
+  extern __shared__ __align__(16) uint32_t tile_u32[];
+  TO* tile = reinterpret_cast<TO*>(tile_u32);
+  constexpr int LDE = LDW * 4 / sizeof(TO);  // elements per pixel row
+  const int b = blockIdx.y;
+  const int px0 = blockIdx.x * TP_PX;
+  const int tid = threadIdx.x;
+  const int px4 = tid & 15;      // which group of 4 pixels
+  const int cl = tid >> 4;       // 0..15
+  const TI* s = src + (size_t)b * C * HW + px0 + px4 * 4;
+  float4 v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int c = i * 16 + cl;
+    v[i] = ld4<TI>(s + (size_t)c * HW);
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int c = i * 16 + cl;
+    tile[(px4 * 4 + 0) * LDE + c] = (TO)v[i].x;
+    tile[(px4 * 4 + 1) * LDE + c] = (TO)v[i].y;
+    tile[(px4 * 4 + 2) * LDE + c] = (TO)v[i].z;
+    tile[(px4 * 4 + 3) * LDE + c] = (TO)v[i].w;
+  }
+  __syncthreads();
+  // write: one warp per pixel row, 32-bit words, consecutive lanes consecutive words
+  const int lane = tid & 31, warp = tid >> 5;
+  constexpr int WORDS = 256 * sizeof(TO) / 4;  // 128 (bf16) or 256 (f32)
+  uint32_t* d = reinterpret_cast<uint32_t*>(dst + ((size_t)b * HW + px0) * C);
+  for (int px = warp; px < TP_PX; px += 8) {
+#pragma unroll
+    for (int w = lane; w < WORDS; w += 32) d[(size_t)px * WORDS + w] = tile_u32[px * LDW + w];
+  }
+}
+
+template <typename TI, typename TO>
+static void bev_launch(const void* src, void* dst, int B, int C, int HW, cudaStream_t st) {
+  constexpr int LDW = (sizeof(TO) == 2) ? 129 : 257;
+  const int smem = TP_PX * LDW * 4;
+  static bool once = false;
+  if (!once) {
+    cudaFuncSetAttribute(bev_to_nhwc_kernel<TI, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         smem);
+    once = true;
+  }
+  dim3 grid(HW / TP_PX, B);
+  bev_to_nhwc_kernel<TI, TO><<<grid, 256, smem, st>>>(reinterpret_cast<const TI*>(src),
+                                                     reinterpret_cast<TO*>(dst), C, HW);
+}
+
+void launch_bev_to_nhwc(const void* src, int src_dtype, void* dst, int dst_dtype, int B, int C,
+                        int HW, cudaStream_t st) {
+  if (src_dtype == 0 && dst_dtype == 0) bev_launch<float, float>(src, dst, B, C, HW, st);
+  else if (src_dtype == 0 && dst_dtype == 1) bev_launch<float, __nv_bfloat16>(src, dst, B, C, HW, st);
+  else if (src_dtype == 1 && dst_dtype == 1)
+    bev_launch<__nv_bfloat16, __nv_bfloat16>(src, dst, B, C, HW, st);
+  else bev_launch<__nv_bfloat16, float>(src, dst, B, C, HW, st);
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d,
+                                     size_t n4) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(s) + i);
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a);
+    u.y = *reinterpret_cast<uint32_t*>(&b);
+    reinterpret_cast<uint2*>(d)[i] = u;
+  }
+}
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ s, float* __restrict__ d,
+                                     size_t n4) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) reinterpret_cast<float4*>(d)[i] = ld4<__nv_bfloat16>(s + i * 4);
+}
+void launch_cast_f32_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t st) {
+  const size_t n4 = n / 4;
+  const int blocks = (int)min((size_t)148 * 16, (n4 + 255) / 256);
+  cast_f32_bf16_kernel<<<blocks > 0 ? blocks : 1, 256, 0, st>>>(src, dst, n4);
+}
+void launch_cast_bf16_f32(const __nv_bfloat16* src, float* dst, size_t n, cudaStream_t st) {
+  const size_t n4 = n / 4;
+  const int blocks = (int)min((size_t)148 * 16, (n4 + 255) / 256);
+  cast_bf16_f32_kernel<<<blocks > 0 ? blocks : 1, 256, 0, st>>>(src, dst, n4);
+}
+
+// ===================================================================================
+// Odometry (de)normalisation, transfuser_model_v2.py:480-500.  Intrinsics keep the
+// reference's operation order (no FMA contraction) so fp32 results track torch's.
+// ===================================================================================
+__device__ __forceinline__ float norm_x(float x) {   // 2*(x+1.2)/56.9 - 1
+  return __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fadd_rn(x, 1.2f)), 56.9f), 1.0f);
+}
+__device__ __forceinline__ float norm_y(float y) {   // 2*(y+20)/46 - 1
+  return __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fadd_rn(y, 20.0f)), 46.0f), 1.0f);
+}
+__device__ __forceinline__ float denorm_x(float v) { // (v+1)/2*56.9 - 1.2
+  return __fsub_rn(__fmul_rn(__fdiv_rn(__fadd_rn(v, 1.0f), 2.0f), 56.9f), 1.2f);
+}
+__device__ __forceinline__ float denorm_y(float v) { // (v+1)/2*46 - 20
+  return __fsub_rn(__fmul_rn(__fdiv_rn(__fadd_rn(v, 1.0f), 2.0f), 46.0f), 20.0f);
+}
+
+// img = sqrt(ac[t]) * norm_odo(plan_anchor) + sqrt(1-ac[t]) * noise     (:591-597)
+__global__ void init_img_kernel(const float* __restrict__ anchors, const float* __restrict__ noise,
+                                float* __restrict__ img, int B, int AP, float sa, float sb) {
+  const size_t n = (size_t)B * AP * 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % ((size_t)AP * 2));
+    const float a = anchors[j];
+    const float nv = (j & 1) ? norm_y(a) : norm_x(a);
+    img[i] = __fadd_rn(__fmul_rn(sa, nv), __fmul_rn(sb, noise[i]));
+  }
+}
+void launch_init_img(const float* anchors, const float* noise, float* img, int B, int AP,
+                     float sqrt_ac, float sqrt_1m_ac, cudaStream_t st) {
+  const size_t n = (size_t)B * AP * 2;
+  const int blocks = (int)min((size_t)148 * 8, (n + 255) / 256);
+  init_img_kernel<<<blocks, 256, 0, st>>>(anchors, noise, img, B, AP, sqrt_ac, sqrt_1m_ac);
+}
+
+// ===================================================================================
+// clamp + denorm_odo (:601-602) and gen_sineembed_for_position(hidden_dim=64)
+// (modules/blocks.py:22-40, call :605-607): per pose 64 features = [embed(y) | embed(x)],
+// embed(v)[i] = sin|cos(v * 2pi / dim_t[i]) (even i: sin, odd i: cos), flattened over the
+// P poses -> 64*P features per anchor row.  Accurate sinf/cosf: arguments reach ~360 rad.
+// 64 threads per row, 4 rows per CTA.
+// ===================================================================================
+__global__ void __launch_bounds__(256) embed_kernel(const float* __restrict__ img,
+                                                    float* __restrict__ pts,
+                                                    float* __restrict__ emb32,
+                                                    __nv_bfloat16* __restrict__ emb16, int M, int P,
+                                                    const float* __restrict__ dim_t) {
+  const int m = blockIdx.x * 4 + (threadIdx.x >> 6);
+  if (m >= M) return;
+  const int j = threadIdx.x & 63;
+  const int half = j >> 5, i = j & 31;
+  const float dt = dim_t[i];
+  const float two_pi = 6.283185307179586f;
+  for (int p = 0; p < P; ++p) {
+    const float ix = img[((size_t)m * P + p) * 2 + 0];
+    const float iy = img[((size_t)m * P + p) * 2 + 1];
+    const float x = denorm_x(fminf(fmaxf(ix, -1.0f), 1.0f));
+    const float y = denorm_y(fminf(fmaxf(iy, -1.0f), 1.0f));
+    if (j == 0) {
+      pts[((size_t)m * P + p) * 2 + 0] = x;
+      pts[((size_t)m * P + p) * 2 + 1] = y;
+    }
+    const float v = half ? x : y;  // output order is (pos_y, pos_x), blocks.py:39
+    const float arg = __fdiv_rn(__fmul_rn(v, two_pi), dt);
+    const float e = (i & 1) ? cosf(arg) : sinf(arg);
+    const size_t o = (size_t)m * (64 * P) + p * 64 + j;
+    if (emb32) emb32[o] = e;
+    if (emb16) emb16[o] = __float2bfloat16_rn(e);
+  }
+}
+void launch_embed(const float* img, float* pts, float* emb32, __nv_bfloat16* emb16, int M, int P,
+                  const float* dim_t_dev, cudaStream_t st) {
+  embed_kernel<<<(M + 3) / 4, 256, 0, st>>>(img, pts, emb32, emb16, M, P, dim_t_dev);
+}
+
+// ===================================================================================
+// BEV sampling plan, one CTA per scene (GridSampleCrossBEVAttention.forward,
+// modules/blocks.py:98-125):
+//   aw      = softmax_p(Linear(D->P)(q))                                    (:110-112)
+//   grid    = (y / lidar_max_x, x / lidar_max_y)                            (:101-108)
+//   ix, iy  = ((g+1)*size-1)/2, 4 bilinear corners, zero padding            (:117-122)
+// Output: the sorted list of UNIQUE in-bounds corner pixels of the scene (the only pixels at
+// which value_proj has to be evaluated), and per (anchor, pose, corner) the slot of its pixel
+// in that list with the combined weight bilinear * aw.
+// ===================================================================================
+struct Corners {
+  int pix[4];
+  float w[4];
+};
+__device__ __forceinline__ Corners corners_of(float px, float py, int H, int W, OdoConsts oc) {
+  Corners c;
+  const float gx = __fdiv_rn(py, oc.lidar_max_x);
+  const float gy = __fdiv_rn(px, oc.lidar_max_y);
+  const float ix = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.0f), (float)W), 1.0f), 2.0f);
+  const float iy = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.0f), (float)H), 1.0f), 2.0f);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { c.pix[k] = -1; c.w[k] = 0.f; }
+  if (!(ix > -2.0f && ix < (float)(W + 1) && iy > -2.0f && iy < (float)(H + 1))) return c;
+  const float fx0 = floorf(ix), fy0 = floorf(iy);
+  const int x0 = (int)fx0, y0 = (int)fy0;
+  const float wx1 = __fsub_rn(ix, fx0), wx0 = __fsub_rn(__fadd_rn(fx0, 1.0f), ix);
+  const float wy1 = __fsub_rn(iy, fy0), wy0 = __fsub_rn(__fadd_rn(fy0, 1.0f), iy);
+  const int xs[4] = {x0, x0 + 1, x0, x0 + 1};
+  const int ys[4] = {y0, y0, y0 + 1, y0 + 1};
+  const float ws[4] = {__fmul_rn(wx0, wy0), __fmul_rn(wx1, wy0), __fmul_rn(wx0, wy1),
+                       __fmul_rn(wx1, wy1)};  // nw, ne, sw, se
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (xs[k] >= 0 && xs[k] < W && ys[k] >= 0 && ys[k] < H) {
+      c.pix[k] = ys[k] * W + xs[k];
+      c.w[k] = ws[k];
+    }
+  }
+  return c;
+}
+
+__global__ void __launch_bounds__(256) plan_kernel(const float* __restrict__ q0,
+                                                   const float* __restrict__ attw_w,
+                                                   const float* __restrict__ attw_b,
+                                                   const float* __restrict__ pts,
+                                                   int* __restrict__ upix, int* __restrict__ nuniq,
+                                                   int* __restrict__ ent_slot,
+                                                   float* __restrict__ ent_w, int A, int P, int H,
+                                                   int W, int rcap, OdoConsts oc) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int HW = H * W;
+  unsigned short* table = reinterpret_cast<unsigned short*>(smraw);        // [HW]
+  float* aw = reinterpret_cast<float*>(smraw + ((HW * 2 + 15) / 16) * 16);  // [A*P]
+  __shared__ int warp_tot[8];
+  __shared__ int total_s;
+  const int scene = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  for (int i = tid; i < HW; i += 256) table[i] = 0;
+  // ---- attention weights: P (=8) logits per anchor, softmax over the poses
+  for (int a = warp; a < A; a += 8) {
+    const float* q = q0 + ((size_t)scene * A + a) * D;
+    float qv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) qv[i] = q[lane + 32 * i];
+    float logit[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s = fmaf(qv[i], attw_w[o * D + lane + 32 * i], s);
+      logit[o] = warp_sum(s) + attw_b[o];
+    }
+    float mx = logit[0];
+#pragma unroll
+    for (int o = 1; o < 8; ++o) mx = fmaxf(mx, logit[o]);
+    float e[8], den = 0.f;
+#pragma unroll
+    for (int o = 0; o < 8; ++o) { e[o] = expf(logit[o] - mx); den += e[o]; }
+    if (lane < 8) {
+      float mine = e[0];
+#pragma unroll
+      for (int o = 1; o < 8; ++o) if (lane == o) mine = e[o];
+      aw[a * P + lane] = mine / den;
+    }
+  }
+  __syncthreads();
+  // ---- mark needed pixels
+  const int AP = A * P;
+  for (int e = tid; e < AP; e += 256) {
+    const float px = pts[((size_t)scene * AP + e) * 2 + 0];
+    const float py = pts[((size_t)scene * AP + e) * 2 + 1];
+    const Corners c = corners_of(px, py, H, W, oc);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (c.pix[k] >= 0) table[c.pix[k]] = 1;
+  }
+  __syncthreads();
+  // ---- ordered compaction (pixel order == memory order of the NHWC map)
+  const int ipt = (HW + 255) / 256;
+  const int beg = tid * ipt, end = min(HW, beg + ipt);
+  int cnt = 0;
+  for (int i = beg; i < end; ++i) cnt += table[i] ? 1 : 0;
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  int base = incl - cnt;
+  for (int w = 0; w < warp; ++w) base += warp_tot[w];
+  if (tid == 255) total_s = base + cnt;
+  for (int i = beg; i < end; ++i) {
+    if (table[i]) {
+      upix[(size_t)scene * rcap + base] = i;
+      table[i] = (unsigned short)(base + 1);
+      ++base;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) nuniq[scene] = total_s;
+  // ---- entries
+  for (int e = tid; e < AP; e += 256) {
+    const float px = pts[((size_t)scene * AP + e) * 2 + 0];
+    const float py = pts[((size_t)scene * AP + e) * 2 + 1];
+    const Corners c = corners_of(px, py, H, W, oc);
+    const float a_w = aw[e];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const size_t o = ((size_t)scene * AP + e) * 4 + k;
+      if (c.pix[k] >= 0) {
+        ent_slot[o] = (int)table[c.pix[k]] - 1;
+        ent_w[o] = c.w[k] * a_w;
+      } else {
+        ent_slot[o] = -1;
+        ent_w[o] = 0.f;
+      }
+    }
+  }
+}
+void launch_plan(const float* q0, const float* attw_w, const float* attw_b, const float* pts,
+                 int* upix, int* nuniq, int* ent_slot, float* ent_w, int B, int A, int P, int H,
+                 int W, int rcap, OdoConsts oc, cudaStream_t st) {
+  const int smem = ((H * W * 2 + 15) / 16) * 16 + A * P * 4;
+  static int cur = 0;
+  if (smem > cur) {
+    cudaFuncSetAttribute(plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cur = smem;
+  }
+  plan_kernel<<<B, 256, smem, st>>>(q0, attw_w, attw_b, pts, upix, nuniq, ent_slot, ent_w, A, P,
+                                     H, W, rcap, oc);
+}
+
+// ===================================================================================
+// Bilinear + attention-weighted combine (modules/blocks.py:117-126):
+//   S[a, c] = sum_{p, corner} (bilinear * aw)[a,p,corner] * value[pixel(a,p,corner), c]
+// One CTA per scene, one thread per channel; value rows were produced at the unique pixels.
+// ===================================================================================
+__global__ void __launch_bounds__(256) combine_kernel(const float* __restrict__ V,
+                                                      const int* __restrict__ ent_slot,
+                                                      const float* __restrict__ ent_w,
+                                                      float* __restrict__ s32,
+                                                      __nv_bfloat16* __restrict__ s16, int A, int P,
+                                                      int rcap) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int scene = blockIdx.x, c = threadIdx.x;
+  const int n_ent = A * P * 4;
+  int* sl = reinterpret_cast<int*>(smraw);
+  float* sw = reinterpret_cast<float*>(smraw + (size_t)n_ent * 4);
+  for (int i = c; i < n_ent; i += 256) {
+    sl[i] = ent_slot[(size_t)scene * n_ent + i];
+    sw[i] = ent_w[(size_t)scene * n_ent + i];
+  }
+  __syncthreads();
+  const float* Vs = V + (size_t)scene * rcap * D + c;
+  const int per = P * 4;
+  for (int a = 0; a < A; ++a) {
+    float acc = 0.f;
+#pragma unroll 8
+    for (int j = 0; j < per; ++j) {
+      const int s = sl[a * per + j];
+      if (s >= 0) acc = fmaf(sw[a * per + j], Vs[(size_t)s * D], acc);
+    }
+    const size_t o = ((size_t)scene * A + a) * D + c;
+    if (s32) s32[o] = acc;
+    if (s16) s16[o] = __float2bfloat16_rn(acc);
+  }
+}
+void launch_combine(const float* V, const int* ent_slot, const float* ent_w, float* s32,
+                    __nv_bfloat16* s16, int B, int A, int P, int rcap, cudaStream_t st) {
+  const int smem = A * P * 4 * 8;
+  static int cur = 0;
+  if (smem > cur && smem > 48 * 1024) {
+    cudaFuncSetAttribute(combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cur = smem;
+  }
+  combine_kernel<<<B, 256, smem, st>>>(V, ent_slot, ent_w, s32, s16, A, P, rcap);
+}
+
+// ===================================================================================
+// Agent cross-attention core (nn.MultiheadAttention, transfuser_model_v2.py:316-321,355-357)
+// after the Q projection and the hoisted K|V projection: per scene and head,
+// softmax(q*scale . K^T) . V with head_dim 32 and Na <= 32 keys.
+// One warp per (scene, head): lane j keeps key j in registers for the scores, lane c keeps
+// channel c of every value row for the output.  No shared memory.
+// ===================================================================================
+__global__ void __launch_bounds__(256) attn_core_kernel(const float* __restrict__ qh,
+                                                        const float* __restrict__ kv,
+                                                        float* __restrict__ o32,
+                                                        __nv_bfloat16* __restrict__ o16, int A,
+                                                        int Na, int heads) {
+  const int scene = blockIdx.x;
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (h >= heads) return;
+  const float scale = 0.17677669529663687f;  // 1/sqrt(32)
+  float kreg[32], vreg[32];
+  {
+    const float* kp = kv + ((size_t)scene * Na + min(lane, Na - 1)) * (2 * D) + h * 32;
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) {
+      const float4 t = *reinterpret_cast<const float4*>(kp + c4 * 4);
+      kreg[c4 * 4 + 0] = t.x; kreg[c4 * 4 + 1] = t.y; kreg[c4 * 4 + 2] = t.z; kreg[c4 * 4 + 3] = t.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      vreg[j] = (j < Na) ? kv[((size_t)scene * Na + j) * (2 * D) + D + h * 32 + lane] : 0.f;
+  }
+  for (int a = 0; a < A; ++a) {
+    const size_t row = (size_t)scene * A + a;
+    const float q = qh[row * D + h * 32 + lane] * scale;
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) s = fmaf(__shfl_sync(0xffffffffu, q, c), kreg[c], s);
+    if (lane >= Na) s = -INFINITY;
+    float mx = s;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float e = (lane < Na) ? expf(s - mx) : 0.f;
+    const float p = e / warp_sum(e);
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc = fmaf(__shfl_sync(0xffffffffu, p, j), vreg[j], acc);
+    if (o32) o32[row * D + h * 32 + lane] = acc;
+    if (o16) o16[row * D + h * 32 + lane] = __float2bfloat16_rn(acc);
+  }
+}
+void launch_attn_core(const float* qh, const float* kv, float* o32, __nv_bfloat16* o16, int B,
+                      int A, int Na, int heads, cudaStream_t st) {
+  attn_core_kernel<<<B, 256, 0, st>>>(qh, kv, o32, o16, A, Na, heads);
+}
+
+// ===================================================================================
+// Regression tail of DiffMotionPlanningRefinementModule + layer/step bookkeeping:
+//   reg = Linear(D->3P)(r2)                         (transfuser_model_v2.py:225-231,253-254)
+//   reg[..., :2] += points ; reg[..., 2] = tanh(.)*pi                        (:378-380)
+//   next layer's points = reg[..., :2]                                       (:424)
+//   after the last layer of a non-final step: x0 = norm_odo(reg[..., :2]);
+//   img = DDIM step(x0, t, img), prediction_type "sample", clip_sample, eta 0 (:632-636)
+// One warp per anchor row.
+// ===================================================================================
+__global__ void __launch_bounds__(256) reg_finish_kernel(const float* __restrict__ r2,
+                                                         const float* __restrict__ w4,
+                                                         const float* __restrict__ b4,
+                                                         float* __restrict__ pts,
+                                                         float* __restrict__ img,
+                                                         float* __restrict__ modes, int M, int P,
+                                                         int do_ddim, DdimCoef dc) {
+  const int m = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (m >= M) return;
+  const int lane = threadIdx.x & 31;
+  float r[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = r2[(size_t)m * D + lane + 32 * i];
+  const int n_out = 3 * P;  // 24
+  float mine = 0.f;
+  for (int o = 0; o < n_out; ++o) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s = fmaf(r[i], w4[(size_t)o * D + lane + 32 * i], s);
+    s = warp_sum(s) + b4[o];
+    if (lane == o) mine = s;
+  }
+  if (lane < n_out) {
+    const int p = lane / 3, comp = lane - p * 3;
+    float out;
+    if (comp < 2) {
+      const size_t pi = ((size_t)m * P + p) * 2 + comp;
+      out = __fadd_rn(mine, pts[pi]);
+      pts[pi] = out;
+      if (do_ddim) {
+        const float x0 = comp ? norm_y(out) : norm_x(out);
+        const float sample = img[pi];
+        const float eps = __fdiv_rn(__fsub_rn(sample, __fmul_rn(dc.sqrt_ac_t, x0)), dc.sqrt_1m_ac_t);
+        const float x0c = fminf(fmaxf(x0, -1.0f), 1.0f);
+        img[pi] = __fadd_rn(__fmul_rn(dc.sqrt_ac_prev, x0c), __fmul_rn(dc.sqrt_1m_ac_prev, eps));
+      }
+    } else {
+      out = __fmul_rn(tanhf(mine), 3.14159265358979323846f);
+    }
+    modes[((size_t)m * P + p) * 3 + comp] = out;
+  }
+}
+void launch_reg_finish(const float* r2, const float* w4, const float* b4, float* pts, float* img,
+                       float* modes, int M, int P, int do_ddim, DdimCoef dc, cudaStream_t st) {
+  reg_finish_kernel<<<(M + 7) / 8, 256, 0, st>>>(r2, w4, b4, pts, img, modes, M, P, do_ddim, dc);
+}
+
+// mode = argmax(cls) (first maximum wins), trajectory = reg[b, mode]          (:637-640)
+__global__ void select_kernel(const float* __restrict__ scores, const float* __restrict__ modes,
+                              float* __restrict__ traj, long long* __restrict__ mode_idx, int B,
+                              int A, int P) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int best = 0;
+  float bv = scores[(size_t)b * A];
+  for (int a = 1; a < A; ++a) {
+    const float v = scores[(size_t)b * A + a];
+    if (v > bv) { bv = v; best = a; }
+  }
+  if (mode_idx) mode_idx[b] = best;
+  if (traj)
+    for (int i = 0; i < P * 3; ++i) traj[(size_t)b * P * 3 + i] = modes[((size_t)b * A + best) * P * 3 + i];
+}
+void launch_select(const float* scores, const float* modes, float* traj, long long* mode_idx,
+                   int B, int A, int P, cudaStream_t st) {
+  select_kernel<<<(B + 127) / 128, 128, 0, st>>>(scores, modes, traj, mode_idx, B, A, P);
+}
+
+// ===================================================================================
+// Pack-time helpers (run once per ddh_pack_weights).
+// ===================================================================================
+__global__ void transpose_f32_kernel(const float* __restrict__ s, float* __restrict__ d, int rows,
+                                     int cols) {
+  __shared__ float t[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    t[i][threadIdx.x] = (r < rows && c < cols) ? s[(size_t)r * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) d[(size_t)c * rows + r] = t[threadIdx.x][i];
+  }
+}
+void launch_transpose_f32(const float* src, float* dst, int rows, int cols, cudaStream_t st) {
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  transpose_f32_kernel<<<grid, block, 0, st>>>(src, dst, rows, cols);
+}
+
+// conv weight [Cout][Cin][3][3]  ->  Wt[(tap*Cin + c)][Cout]  (fp32, k-major for the SIMT engine)
+__global__ void pack_conv_f32_kernel(const float* __restrict__ w, float* __restrict__ d, int Cout,
+                                     int Cin) {
+  const size_t n = (size_t)Cout * Cin * 9;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int o = (int)(i % Cout);
+    const size_t k = i / Cout;
+    const int c = (int)(k % Cin), tap = (int)(k / Cin);
+    d[i] = w[((size_t)o * Cin + c) * 9 + tap];
+  }
+}
+// conv weight -> W[Cout][(tap*Cin + c)] bf16 (K contiguous, the tensor engine's B operand)
+__global__ void pack_conv_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ d,
+                                      int Cout, int Cin) {
+  const size_t n = (size_t)Cout * Cin * 9;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const size_t k = i % ((size_t)Cin * 9);
+    const int o = (int)(i / ((size_t)Cin * 9));
+    const int c = (int)(k % Cin), tap = (int)(k / Cin);
+    d[i] = __float2bfloat16_rn(w[((size_t)o * Cin + c) * 9 + tap]);
+  }
+}
+void launch_pack_conv_f32(const float* w, float* dst, int Cout, int Cin, cudaStream_t st) {
+  pack_conv_f32_kernel<<<592, 256, 0, st>>>(w, dst, Cout, Cin);
+}
+void launch_pack_conv_bf16(const float* w, __nv_bfloat16* dst, int Cout, int Cin,
+                           cudaStream_t st) {
+  pack_conv_bf16_kernel<<<592, 256, 0, st>>>(w, dst, Cout, Cin);
+}
+
+// y[o] = sum_k W[o][k] * act(x[k]) + b[o]   (torch Linear layout), one warp per output
+__global__ void matvec_kernel(const float* __restrict__ W, const float* __restrict__ x,
+                              const float* __restrict__ b, float* __restrict__ y, int n_out, int k,
+                              int act_in_mish) {
+  const int o = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (o >= n_out) return;
+  const int lane = threadIdx.x & 31;
+  float s = 0.f;
+  for (int i = lane; i < k; i += 32) {
+    float xv = x[i];
+    if (act_in_mish) xv = mishf(xv);
+    s = fmaf(W[(size_t)o * k + i], xv, s);
+  }
+  s = warp_sum(s);
+  if (lane == 0) y[o] = s + (b ? b[o] : 0.f);
+}
+void launch_matvec(const float* W, const float* x, const float* b, float* y, int n_out, int k,
+                   int act_in_mish, cudaStream_t st) {
+  matvec_kernel<<<(n_out + 7) / 8, 256, 0, st>>>(W, x, b, y, n_out, k, act_in_mish);
+}
+
+// SinusoidalPosEmb(dim) of one integer timestep (modules/conditional_unet1d.py:53-66)
+__global__ void time_sinemb_kernel(float* emb, int dim, int timestep, float c) {
+  const int i = threadIdx.x;
+  const int half = dim / 2;
+  if (i >= half) return;
+  const float f = expf(__fmul_rn((float)i, c));
+  const float a = __fmul_rn((float)timestep, f);
+  emb[i] = sinf(a);
+  emb[half + i] = cosf(a);
+}
+void launch_time_sinemb(float* emb, int dim, int timestep, cudaStream_t st) {
+  // python: emb = math.log(10000) / (half_dim - 1) in double, then cast by torch to fp32
+  const float c = (float)(-(log(10000.0) / (double)(dim / 2 - 1)));
+  time_sinemb_kernel<<<1, dim / 2, 0, st>>>(emb, dim, timestep, c);
+}
+
+}  // namespace ddh

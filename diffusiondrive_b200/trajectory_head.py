@@ -1,0 +1,358 @@
+"""Drop-in ``TrajectoryHead`` whose inference path runs in the ddh CUDA extension.
+
+Mirrors the reference module of seulbinHwang/DiffusionDrive
+(navsim/agents/diffusiondrive/transfuser_model_v2.py:428-641):
+
+* same constructor arguments (:431-432) and the same parameter names/shapes, so a
+  reference ``state_dict`` (checkpoint with the ``agent.`` prefix stripped,
+  transfuser_agent.py:68-77) loads unchanged;
+* same ``forward`` signature (:502-509) and the same ``"trajectory"`` entry in the
+  returned dict (:641), plus three additive keys: ``"trajectory_modes"`` (B,A,8,3)
+  = ``poses_reg`` (:630), ``"trajectory_scores"`` (B,A) = ``poses_cls`` logits (:631)
+  and ``"mode_idx"`` (B,) int64 (:637).
+
+The module tree below only HOLDS the parameters; all arithmetic of ``forward_test``
+(:578-641) happens behind the C ABI in include/ddh.h.  There is no PyTorch or CPU
+fallback for inference.  Training (``forward_train``, :520-576) is outside the
+accelerated path and raises.
+"""
+from __future__ import annotations
+
+import copy
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .config import HeadConfig, NUM_TRAIN_TIMESTEPS
+
+
+# ------------------------------------------------------------------ parameter holders
+class _BevAttentionParams(nn.Module):
+    """Parameters of GridSampleCrossBEVAttention (modules/blocks.py:51-86)."""
+
+    def __init__(self, d_model: int, num_points: int, in_bev_dims: int = 256):
+        super().__init__()
+        self.attention_weights = nn.Linear(d_model, num_points)
+        self.output_proj = nn.Linear(d_model, d_model)
+        self.value_proj = nn.Sequential(
+            nn.Conv2d(in_bev_dims, 256, kernel_size=(3, 3), stride=(1, 1), padding=1, bias=True),
+            nn.ReLU(inplace=True))
+        nn.init.constant_(self.attention_weights.weight, 0)     # blocks.py:82-83
+        nn.init.constant_(self.attention_weights.bias, 0)
+        nn.init.xavier_uniform_(self.output_proj.weight)        # blocks.py:85-86
+        nn.init.constant_(self.output_proj.bias, 0)
+
+
+class _ModulationParams(nn.Module):
+    """ModulationLayer (transfuser_model_v2.py:259-269)."""
+
+    def __init__(self, d_model: int, cond_dims: int):
+        super().__init__()
+        self.scale_shift_mlp = nn.Sequential(nn.Mish(), nn.Linear(cond_dims, d_model * 2))
+
+
+class _RefinementParams(nn.Module):
+    """DiffMotionPlanningRefinementModule (transfuser_model_v2.py:208-242)."""
+
+    def __init__(self, d_model: int, num_poses: int):
+        super().__init__()
+        self.plan_cls_branch = nn.Sequential(
+            nn.Linear(d_model, d_model), nn.ReLU(inplace=True), nn.LayerNorm(d_model),
+            nn.Linear(d_model, d_model), nn.ReLU(inplace=True), nn.LayerNorm(d_model),
+            nn.Linear(d_model, 1))
+        self.plan_reg_branch = nn.Sequential(
+            nn.Linear(d_model, d_model), nn.ReLU(),
+            nn.Linear(d_model, d_model), nn.ReLU(),
+            nn.Linear(d_model, num_poses * 3))
+        nn.init.constant_(self.plan_cls_branch[-1].bias, float(-np.log((1 - 0.01) / 0.01)))
+
+
+class _DecoderLayerParams(nn.Module):
+    """CustomTransformerDecoderLayer (transfuser_model_v2.py:297-341)."""
+
+    def __init__(self, num_poses: int, d_model: int, d_ffn: int, num_heads: int, dropout: float):
+        super().__init__()
+        self.cross_bev_attention = _BevAttentionParams(d_model, num_poses)
+        self.cross_agent_attention = nn.MultiheadAttention(d_model, num_heads, dropout=dropout,
+                                                           batch_first=True)
+        self.cross_ego_attention = nn.MultiheadAttention(d_model, num_heads, dropout=dropout,
+                                                         batch_first=True)
+        self.ffn = nn.Sequential(nn.Linear(d_model, d_ffn), nn.ReLU(), nn.Linear(d_ffn, d_model))
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+        self.norm3 = nn.LayerNorm(d_model)
+        self.time_modulation = _ModulationParams(d_model, 256)
+        self.task_decoder = _RefinementParams(d_model, num_poses)
+
+
+class _DecoderParams(nn.Module):
+    """CustomTransformerDecoder (transfuser_model_v2.py:390-402): deep copies of one layer."""
+
+    def __init__(self, layer: nn.Module, num_layers: int):
+        super().__init__()
+        self.layers = nn.ModuleList([copy.deepcopy(layer) for _ in range(num_layers)])
+        self.num_layers = num_layers
+
+
+def ddim_alphas_cumprod() -> torch.Tensor:
+    """alphas_cumprod of ``DDIMScheduler(1000, beta_schedule="scaled_linear")`` as diffusers
+    computes it (fp32 linspace in sqrt space, squared, fp32 cumprod); see the ctor call at
+    transfuser_model_v2.py:447-451."""
+    betas = torch.linspace(1e-4 ** 0.5, 0.02 ** 0.5, NUM_TRAIN_TIMESTEPS, dtype=torch.float32) ** 2
+    return torch.cumprod(1.0 - betas, dim=0)
+
+
+# ------------------------------------------------------------------ the head
+class TrajectoryHead(nn.Module):
+    """Trajectory prediction head (truncated-diffusion planner), CUDA inference path."""
+
+    def __init__(self, num_poses: int, d_ffn: int, d_model: int, plan_anchor_path: Optional[str],
+                 config=None, *, plan_anchor: Optional[np.ndarray] = None,
+                 precision: str = "fp32"):
+        super().__init__()
+        config = config if config is not None else HeadConfig()
+        self._config = config
+        self._num_poses = num_poses
+        self._d_model = d_model
+        self._d_ffn = d_ffn
+        self.ego_fut_mode = 20
+        self._num_layers = int(getattr(config, "num_decoder_layers", 2))   # literal 2 at :476
+        self._step_num = int(getattr(config, "step_num", 2))               # literal 2 at :581
+        self._trunc_timestep = int(getattr(config, "trunc_timestep", 8))   # literal 8 at :594
+        self._num_heads = int(getattr(config, "tf_num_head", 8))
+        self._lidar_max_x = float(getattr(config, "lidar_max_x", 32.0))
+        self._lidar_max_y = float(getattr(config, "lidar_max_y", 32.0))
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self.precision = precision
+
+        if plan_anchor is None:
+            plan_anchor = np.load(plan_anchor_path)                        # :453
+        self.plan_anchor = nn.Parameter(torch.tensor(plan_anchor, dtype=torch.float32),
+                                        requires_grad=False)               # :455-458
+        self.plan_anchor_encoder = nn.Sequential(
+            nn.Linear(512, d_model), nn.ReLU(inplace=True), nn.LayerNorm(d_model),
+            nn.Linear(d_model, d_model))                                   # :459-462
+        self.time_mlp = nn.Sequential(
+            nn.Identity(),                   # slot of SinusoidalPosEmb (no parameters), :464
+            nn.Linear(d_model, d_model * 4), nn.Mish(), nn.Linear(d_model * 4, d_model))
+        layer = _DecoderLayerParams(num_poses, d_model, d_ffn, self._num_heads,
+                                    float(getattr(config, "tf_dropout", 0.0)))
+        self.diff_decoder = _DecoderParams(layer, self._num_layers)        # :470-476
+
+        self._lib = None
+        self._handle = None
+        self._handle_key = None
+        self._packed_sig = None
+        self._keepalive = None
+        self.frozen = False     # True: skip the per-call "did the weights change" check
+        self.register_load_state_dict_post_hook(lambda *_: self._invalidate())
+
+    # -------------------------------------------------------------- ABI plumbing
+    def _invalidate(self):
+        self._packed_sig = None
+
+    def __del__(self):
+        try:
+            if self._handle is not None and self._lib is not None:
+                self._lib.ddh_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+    def _ensure_handle(self, num_agents: int, bev_c: int, bev_h: int, bev_w: int):
+        key = (num_agents, bev_c, bev_h, bev_w, self.plan_anchor.shape[0])
+        if self._handle is not None and key == self._handle_key:
+            return
+        lib = self._lib = _lib.load()
+        if self._handle is not None:
+            lib.ddh_destroy(self._handle)
+            self._handle = None
+        shp = _lib.Shape(
+            num_anchors=self.plan_anchor.shape[0], num_poses=self._num_poses,
+            d_model=self._d_model, d_ffn=self._d_ffn, num_heads=self._num_heads,
+            num_agents=num_agents, bev_channels=bev_c, bev_h=bev_h, bev_w=bev_w,
+            num_layers=self._num_layers, num_steps=self._step_num,
+            trunc_timestep=self._trunc_timestep, lidar_max_x=self._lidar_max_x,
+            lidar_max_y=self._lidar_max_y)
+        hp = C.c_void_p()
+        rc = lib.ddh_create(C.byref(shp), C.byref(hp))
+        _lib.check(lib, None, rc, "ddh_create")
+        self._handle = hp
+        self._handle_key = key
+        self._packed_sig = None
+        ac = ddim_alphas_cumprod().contiguous()
+        rc = lib.ddh_set_alphas_cumprod(hp, C.cast(ac.data_ptr(), C.POINTER(C.c_float)),
+                                        ac.numel())
+        _lib.check(lib, hp, rc, "ddh_set_alphas_cumprod")
+
+    def _signature(self):
+        return (self.precision,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def _ensure_packed(self, device: torch.device):
+        if self._packed_sig is not None and self.frozen:
+            return
+        sig = self._signature()
+        if sig == self._packed_sig:
+            return
+        lib, h = self._lib, self._handle
+        keep = []
+
+        def ptr(t: torch.Tensor) -> int:
+            if t.device != device or t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.detach().to(device=device, dtype=torch.float32).contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        sd = dict(self.named_parameters())
+        L = self._num_layers
+        lw = (_lib.LayerWeights * L)()
+        names = {
+            "bev_attw": "cross_bev_attention.attention_weights",
+            "bev_out": "cross_bev_attention.output_proj",
+            "bev_conv": "cross_bev_attention.value_proj.0",
+            "agent_out": "cross_agent_attention.out_proj",
+            "ego_out": "cross_ego_attention.out_proj",
+            "ffn0": "ffn.0", "ffn2": "ffn.2",
+            "norm1": "norm1", "norm2": "norm2", "norm3": "norm3",
+            "film": "time_modulation.scale_shift_mlp.1",
+            "cls0": "task_decoder.plan_cls_branch.0", "cls_ln2": "task_decoder.plan_cls_branch.2",
+            "cls3": "task_decoder.plan_cls_branch.3", "cls_ln5": "task_decoder.plan_cls_branch.5",
+            "cls6": "task_decoder.plan_cls_branch.6",
+            "reg0": "task_decoder.plan_reg_branch.0", "reg2": "task_decoder.plan_reg_branch.2",
+            "reg4": "task_decoder.plan_reg_branch.4",
+        }
+        for l in range(L):
+            pre = f"diff_decoder.layers.{l}."
+            for short, full in names.items():
+                setattr(lw[l], short + "_w", ptr(sd[pre + full + ".weight"]))
+                setattr(lw[l], short + "_b", ptr(sd[pre + full + ".bias"]))
+            for short, full in (("agent_in", "cross_agent_attention"),
+                                ("ego_in", "cross_ego_attention")):
+                setattr(lw[l], short + "_w", ptr(sd[pre + full + ".in_proj_weight"]))
+                setattr(lw[l], short + "_b", ptr(sd[pre + full + ".in_proj_bias"]))
+        wp = _lib.WeightPtrs()
+        wp.plan_anchor = ptr(self.plan_anchor)
+        for short, full in (("enc0", "plan_anchor_encoder.0"), ("enc_ln", "plan_anchor_encoder.2"),
+                            ("enc3", "plan_anchor_encoder.3"), ("time1", "time_mlp.1"),
+                            ("time3", "time_mlp.3")):
+            setattr(wp, short + "_w", ptr(sd[full + ".weight"]))
+            setattr(wp, short + "_b", ptr(sd[full + ".bias"]))
+        wp.layers = C.cast(lw, C.POINTER(_lib.LayerWeights))
+        prec = _lib.PREC_BF16 if self.precision == "bf16" else _lib.PREC_FP32
+        stream = torch.cuda.current_stream(device).cuda_stream
+        rc = lib.ddh_pack_weights(h, C.byref(wp), prec, C.c_void_p(stream))
+        _lib.check(lib, h, rc, "ddh_pack_weights")
+        torch.cuda.current_stream(device).synchronize()   # sources may be temporaries
+        self._keepalive = None
+        self._packed_sig = sig
+
+    def reserve(self, batch: int, num_agents: int = 30, bev_c: int = 256, bev_h: int = 64,
+                bev_w: int = 64) -> None:
+        """Pre-allocate the workspace for ``batch`` scenes (avoids a sync on the first call)."""
+        dev = self.plan_anchor.device
+        with torch.cuda.device(dev):
+            self._ensure_handle(num_agents, bev_c, bev_h, bev_w)
+            self._ensure_packed(dev)
+            _lib.check(self._lib, self._handle, self._lib.ddh_reserve(self._handle, batch),
+                       "ddh_reserve")
+
+    # -------------------------------------------------------------- reference interface
+    def forward(self, ego_query, agents_query, bev_feature, bev_spatial_shape=None,
+                status_encoding=None, targets=None, global_img=None, *,
+                noise: Optional[torch.Tensor] = None,
+                bev_layout: str = "NCHW") -> Dict[str, torch.Tensor]:
+        """Same contract as the reference ``forward`` (:502-518).
+
+        ``status_encoding``, ``bev_spatial_shape`` and ``global_img`` are dead inputs of the
+        reference path and are ignored.  ``noise`` (B,A,P,2) replaces the ``torch.randn`` of
+        :593; when omitted it is drawn the same way.  ``bev_layout="NHWC"`` accepts the map as
+        (B,H,W,C), the layout the producer holds one line before the permute (:136-140).
+        """
+        if self.training:
+            raise NotImplementedError(
+                "diffusiondrive_b200.TrajectoryHead accelerates the inference path "
+                "(forward_test); forward_train (transfuser_model_v2.py:520-576) is out of scope. "
+                "Call .eval() first.")
+        return self.forward_test(ego_query, agents_query, bev_feature, bev_spatial_shape,
+                                 status_encoding, global_img, noise=noise, bev_layout=bev_layout)
+
+    @torch.no_grad()
+    def forward_test(self, ego_query, agents_query, bev_feature, bev_spatial_shape=None,
+                     status_encoding=None, global_img=None, *, noise=None, bev_layout="NCHW"):
+        dev = self.plan_anchor.device
+        if dev.type != "cuda":
+            raise RuntimeError("TrajectoryHead parameters must live on a CUDA device "
+                               "(module.cuda()); there is no CPU fallback")
+        B = ego_query.shape[0]
+        A, P = self.plan_anchor.shape[0], self._num_poses
+        Na = agents_query.shape[1]
+        if bev_layout == "NCHW":
+            _, Cc, H, W = bev_feature.shape
+        elif bev_layout == "NHWC":
+            _, H, W, Cc = bev_feature.shape
+        else:
+            raise ValueError("bev_layout must be 'NCHW' or 'NHWC'")
+        if bev_feature.dtype not in (torch.float32, torch.bfloat16):
+            raise TypeError("bev_feature must be float32 or bfloat16")
+        host_call = ego_query.device.type == "cpu"
+        in_dev = ego_query.device
+        if noise is None:
+            noise = torch.randn((B, A, P, 2), device=in_dev)                   # :593
+        for name, t in (("agents_query", agents_query), ("bev_feature", bev_feature),
+                        ("noise", noise)):
+            if t.device != in_dev:
+                raise RuntimeError(f"{name} is on {t.device}, ego_query on {in_dev}")
+        if not host_call and in_dev != dev:
+            raise RuntimeError(f"inputs on {in_dev} but parameters on {dev}")
+
+        ego = ego_query.to(torch.float32).contiguous()
+        agents = agents_query.to(torch.float32).contiguous()
+        bev = bev_feature.contiguous()
+        noise = noise.to(torch.float32).contiguous()
+        out_dev = in_dev
+        traj = torch.empty((B, P, 3), dtype=torch.float32, device=out_dev)
+        modes = torch.empty((B, A, P, 3), dtype=torch.float32, device=out_dev)
+        scores = torch.empty((B, A), dtype=torch.float32, device=out_dev)
+        idx = torch.empty((B,), dtype=torch.int64, device=out_dev)
+
+        with torch.cuda.device(dev):
+            self._ensure_handle(Na, Cc, H, W)
+            self._ensure_packed(dev)
+            lib, h = self._lib, self._handle
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            fn = lib.ddh_forward_host if host_call else lib.ddh_forward
+            rc = fn(h, ego.data_ptr(), agents.data_ptr(), bev.data_ptr(),
+                    _lib.BF16 if bev.dtype == torch.bfloat16 else _lib.F32,
+                    _lib.NHWC if bev_layout == "NHWC" else _lib.NCHW,
+                    noise.data_ptr(), traj.data_ptr(), modes.data_ptr(), scores.data_ptr(),
+                    idx.data_ptr(), B, stream)
+            _lib.check(lib, h, rc, "ddh_forward_host" if host_call else "ddh_forward")
+        return {"trajectory": traj, "trajectory_modes": modes, "trajectory_scores": scores,
+                "mode_idx": idx}
+
+    # -------------------------------------------------------------- test hooks
+    def debug_tap(self, name: str, dtype=np.float32) -> np.ndarray:
+        """Copy a named internal buffer of the last forward to the host (tests only)."""
+        lib, h = self._lib, self._handle
+        buf = np.empty(1 << 20, dtype=np.uint8)
+        n = lib.ddh_debug_copy(h, name.encode(), buf.ctypes.data_as(C.c_void_p), 0)
+        if n < 0:
+            _lib.check(lib, h, int(n), "ddh_debug_copy")
+        # first call with max_bytes=0 only validates the name; size by doubling
+        size = 1 << 20
+        while True:
+            buf = np.empty(size, dtype=np.uint8)
+            n = lib.ddh_debug_copy(h, name.encode(), buf.ctypes.data_as(C.c_void_p), size)
+            if n < 0:
+                _lib.check(lib, h, int(n), "ddh_debug_copy")
+            if n < size:
+                return buf[:n].view(dtype).copy()
+            size *= 4
+
+    def last_launch_count(self) -> int:
+        return int(self._lib.ddh_last_launch_count(self._handle)) if self._handle else 0

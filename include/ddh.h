@@ -1,0 +1,199 @@
+/*
+ * ddh.h — C ABI of the B200-native DiffusionDrive planning head ("ddh").
+ *
+ * The reference (seulbinHwang/DiffusionDrive) is pure Python and has no FFI layer
+ * of its own; the boundary this library replaces is the Python method
+ *
+ *   TrajectoryHead.forward_test(ego_query, agents_query, bev_feature,
+ *                               bev_spatial_shape, status_encoding, global_img)
+ *   navsim/agents/diffusiondrive/transfuser_model_v2.py:578-641
+ *
+ * reached through TrajectoryHead.forward (:502-518), called by
+ * V2TransfuserModel.forward (:150-156).  Each entry point below cites the
+ * reference lines whose work it takes over.  The Python binding a maintainer
+ * adds on the reference side is shown in INTEGRATION.md; the one shipped in this
+ * repo is diffusiondrive_b200/_lib.py (ctypes).
+ *
+ * Conventions
+ *   - plain C: no C++ types, no torch types, pointers + sizes only;
+ *   - every function returning int returns DDH_OK (0) or a negative ddh_status;
+ *     the text of the last failure is available from ddh_last_error();
+ *   - all tensors are dense row-major ("contiguous" in torch terms);
+ *   - the caller owns every buffer it passes in; the library borrows device
+ *     pointers for the duration of one call and never frees them;
+ *   - the library owns packed weights, workspace and TMA tensor maps, all
+ *     released by ddh_destroy();
+ *   - ddh_forward() is asynchronous on the given CUDA stream and never
+ *     synchronises the host (workspace growth on a larger batch is the one
+ *     exception: call ddh_reserve() first to avoid it);
+ *   - one in-flight call per handle; different handles are independent;
+ *     cudaSetDevice() is the caller's job;
+ *   - there is no CPU fallback: without a CUDA device every compute entry
+ *     point fails with DDH_ERR_CUDA.
+ */
+#ifndef DDH_H_
+#define DDH_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DDH_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define DDH_API __attribute__((visibility("default")))
+#else
+#define DDH_API
+#endif
+
+typedef enum ddh_status {
+  DDH_OK = 0,
+  DDH_ERR_BAD_ARG = -1,      /* null pointer, bad enum, B <= 0 ...                 */
+  DDH_ERR_UNSUPPORTED = -2,  /* shape outside what the kernels are built for       */
+  DDH_ERR_NOT_PACKED = -3,   /* ddh_forward before ddh_pack_weights                */
+  DDH_ERR_CUDA = -4,         /* CUDA runtime / driver error (text in last_error)   */
+  DDH_ERR_ALIGNMENT = -5,    /* a pointer is not aligned as documented             */
+  DDH_ERR_NOMEM = -6
+} ddh_status;
+
+/* arithmetic of the GEMM-shaped stages (everything between them is fp32) */
+typedef enum ddh_precision {
+  DDH_PREC_FP32 = 0,  /* CUDA-core fp32 FMA everywhere: <= 1e-4 m vs the reference  */
+  DDH_PREC_BF16 = 1   /* bf16 operands on tcgen05 tensor cores, fp32 accumulate     */
+} ddh_precision;
+
+typedef enum ddh_dtype { DDH_F32 = 0, DDH_BF16 = 1 } ddh_dtype;
+
+/* layout of bev_feature: the reference hands the head NCHW
+ * (transfuser_model_v2.py:138-140); one line earlier it holds NHWC (:136-137). */
+typedef enum ddh_layout { DDH_NCHW = 0, DDH_NHWC = 1 } ddh_layout;
+
+/* Shape of the path.  Defaults of the reference in brackets. */
+typedef struct ddh_shape {
+  int32_t num_anchors;     /* A  [20]  plan_anchor.shape[0], :453-458                */
+  int32_t num_poses;       /* P  [8]   must be 8                                     */
+  int32_t d_model;         /* D  [256] must be 256                                   */
+  int32_t d_ffn;           /* F  [1024] multiple of 256                              */
+  int32_t num_heads;       /*    [8]   head_dim must be 32                           */
+  int32_t num_agents;      /* Na [30]  <= 32                                         */
+  int32_t bev_channels;    /* C  [256] must be 256 (in_bev_dims, :314)               */
+  int32_t bev_h;           /* H  [64]                                                */
+  int32_t bev_w;           /* W  [64]  H*W <= 65535                                  */
+  int32_t num_layers;      /* L  [2]   decoder depth, literal at :476                */
+  int32_t num_steps;       /* S  [2]   step_num, literal at :581                     */
+  int32_t trunc_timestep;  /*    [8]   literal at :594                               */
+  float lidar_max_x;       /*    [32]  transfuser_config.py:29-32                    */
+  float lidar_max_y;       /*    [32]                                                */
+} ddh_shape;
+
+/* Device pointers to the fp32 parameters of one CustomTransformerDecoderLayer
+ * (transfuser_model_v2.py:297-341), in torch's native layouts. */
+typedef struct ddh_layer_weights {
+  /* cross_bev_attention (modules/blocks.py:49-78) */
+  const float *bev_attw_w, *bev_attw_b;   /* attention_weights  [P,D], [P]           */
+  const float *bev_out_w, *bev_out_b;     /* output_proj        [D,D], [D]           */
+  const float *bev_conv_w, *bev_conv_b;   /* value_proj.0       [256,C,3,3], [256]   */
+  /* cross_agent_attention / cross_ego_attention (nn.MultiheadAttention) */
+  const float *agent_in_w, *agent_in_b;   /* in_proj q|k|v      [3D,D], [3D]         */
+  const float *agent_out_w, *agent_out_b; /* out_proj           [D,D], [D]           */
+  const float *ego_in_w, *ego_in_b;
+  const float *ego_out_w, *ego_out_b;
+  const float *ffn0_w, *ffn0_b;           /* ffn.0              [F,D], [F]           */
+  const float *ffn2_w, *ffn2_b;           /* ffn.2              [D,F], [D]           */
+  const float *norm1_w, *norm1_b, *norm2_w, *norm2_b, *norm3_w, *norm3_b; /* [D]     */
+  const float *film_w, *film_b;           /* time_modulation.scale_shift_mlp.1 [2D,D]*/
+  /* task_decoder (DiffMotionPlanningRefinementModule, :208-256) */
+  const float *cls0_w, *cls0_b, *cls_ln2_w, *cls_ln2_b;
+  const float *cls3_w, *cls3_b, *cls_ln5_w, *cls_ln5_b;
+  const float *cls6_w, *cls6_b;           /* [1,D], [1]                              */
+  const float *reg0_w, *reg0_b, *reg2_w, *reg2_b;
+  const float *reg4_w, *reg4_b;           /* [3P,D], [3P]                            */
+} ddh_layer_weights;
+
+/* Device pointers to all fp32 parameters of TrajectoryHead (:455-476). */
+typedef struct ddh_weight_ptrs {
+  const float *plan_anchor;                /* [A,P,2] metres                         */
+  const float *enc0_w, *enc0_b;            /* plan_anchor_encoder.0 [D,512]          */
+  const float *enc_ln_w, *enc_ln_b;        /* plan_anchor_encoder.2 [D]              */
+  const float *enc3_w, *enc3_b;            /* plan_anchor_encoder.3 [D,D]            */
+  const float *time1_w, *time1_b;          /* time_mlp.1 [4D,D]                      */
+  const float *time3_w, *time3_b;          /* time_mlp.3 [D,4D]                      */
+  const ddh_layer_weights *layers;         /* HOST array of num_layers entries       */
+} ddh_weight_ptrs;
+
+typedef struct ddh_handle ddh_handle;
+
+/* Library / ABI version (DDH_ABI_VERSION of the build). */
+DDH_API int ddh_abi_version(void);
+
+/* Build-time facts: "sm_100a", kernel families present. Static string. */
+DDH_API const char *ddh_build_info(void);
+
+/* Replaces TrajectoryHead.__init__ shape bookkeeping (:431-478). No device work. */
+DDH_API int ddh_create(const ddh_shape *shape, ddh_handle **out);
+DDH_API void ddh_destroy(ddh_handle *h);
+
+/* Text of the last error on this handle (h may be NULL for create-time errors). */
+DDH_API const char *ddh_last_error(const ddh_handle *h);
+
+/* Override the DDIM alphas_cumprod table (n >= 21 floats, host pointer).  By default the
+ * library computes DDIMScheduler(1000, "scaled_linear") itself (diffusers, :447-451);
+ * a Python caller passes torch's own table so the constants are bit-identical. */
+DDH_API int ddh_set_alphas_cumprod(ddh_handle *h, const float *table_host, int n);
+/* Copy the table in use to the caller (host), for tests. */
+DDH_API int ddh_get_alphas_cumprod(const ddh_handle *h, float *table_host, int n);
+
+/* Copy + repack the parameters into the layouts the kernels read, fold what is
+ * weight-only (time_mlp + FiLM vectors :463-468,:276-294; ego out_proj o v_proj :322-327)
+ * and build the TMA tensor maps.  Must be called again after any change of the
+ * source parameters (load_state_dict, .to(), ...).  Asynchronous on `stream`. */
+DDH_API int ddh_pack_weights(ddh_handle *h, const ddh_weight_ptrs *w, int precision, void *stream);
+
+/* Workspace the library will hold for a batch of B scenes, in bytes. */
+DDH_API size_t ddh_workspace_bytes(const ddh_handle *h, int B);
+/* Pre-allocate for up to B scenes (synchronises; optional). */
+DDH_API int ddh_reserve(ddh_handle *h, int B);
+
+/* TrajectoryHead.forward_test (:578-641) for B scenes, device buffers.
+ *   ego     [B,1,D] f32          agents [B,Na,D] f32
+ *   bev     [B,C,H,W] (NCHW) or [B,H,W,C] (NHWC), f32 or bf16, 16-byte aligned
+ *   noise   [B,A,P,2] f32        host-generated N(0,1), replaces torch.randn (:593)
+ * outputs (any may be NULL):
+ *   out_traj     [B,P,3] f32     "trajectory" (:641)
+ *   out_modes    [B,A,P,3] f32   poses_reg of the last step (:630)
+ *   out_scores   [B,A] f32       poses_cls logits of the last step (:631)
+ *   out_mode_idx [B] int64       argmax (:637)
+ */
+DDH_API int ddh_forward(ddh_handle *h, const float *ego, const float *agents, const void *bev,
+                int bev_dtype, int bev_layout, const float *noise, float *out_traj,
+                float *out_modes, float *out_scores, int64_t *out_mode_idx, int B,
+                void *stream);
+
+/* Same call with HOST buffers (pinned memory recommended): copies the inputs to the
+ * device, runs ddh_forward, copies the outputs back and synchronises `stream`.
+ * This is the end-to-end path a CPU-resident caller (abstract_agent.py:65-86) uses. */
+DDH_API int ddh_forward_host(ddh_handle *h, const float *ego, const float *agents, const void *bev,
+                     int bev_dtype, int bev_layout, const float *noise, float *out_traj,
+                     float *out_modes, float *out_scores, int64_t *out_mode_idx, int B,
+                     void *stream);
+
+/* Number of kernel launches issued by the last ddh_forward on this handle. */
+DDH_API int ddh_last_launch_count(const ddh_handle *h);
+
+/* Test hook: copy a named internal buffer of the last forward to the host (synchronises).
+ * Returns the number of bytes copied (>= 0) or a negative ddh_status.  Names are listed in
+ * DESIGN.md ("debug taps"); sizes depend on B. */
+DDH_API long long ddh_debug_copy(ddh_handle *h, const char *name, void *host_dst, size_t max_bytes);
+
+/* Test hook: C[M,N] = A[M,K] * W[N,K]^T + bias on the GEMM engine of the given
+ * precision (device pointers, f32 in/out), to validate the tensor-core tiles in isolation. */
+DDH_API int ddh_test_gemm(ddh_handle *h, const float *A, const float *W, const float *bias, float *C,
+                  int M, int N, int K, int precision, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDH_H_ */

@@ -126,21 +126,29 @@ def cross_bev_attention(sd: SD, pre: str, queries, traj_points, bev_feature,
 
 
 def decoder_layer(sd: SD, pre: str, traj_feature, points, bev_feature, agents_query,
-                  ego_query, time_embed, heads: int, lmx: float, lmy: float
+                  ego_query, time_embed, heads: int, lmx: float, lmy: float,
+                  trace: Optional[dict] = None, tkey: str = ""
                   ) -> Tuple[torch.Tensor, torch.Tensor]:
-    """CustomTransformerDecoderLayer.forward, transfuser_model_v2.py:343-382."""
+    """CustomTransformerDecoderLayer.forward, transfuser_model_v2.py:343-382.
+    ``trace`` (tests only) records the intermediate activations under ``tkey``."""
+    def rec(name, t):
+        if trace is not None:
+            trace[tkey + name] = t.detach().clone()
     f = cross_bev_attention(sd, pre + "cross_bev_attention.", traj_feature, points,
                             bev_feature, lmx, lmy)                                     # :353-354
+    rec("x1", f)
     f = f + _mha(sd, pre + "cross_agent_attention", f, agents_query, heads)            # :355-357
     f = _ln(sd, pre + "norm1", f)                                                      # :358
     f = f + _mha(sd, pre + "cross_ego_attention", f, ego_query, heads)                 # :363-364
     f = _ln(sd, pre + "norm2", f)                                                      # :365
+    rec("x2", f)
     f = _ln(sd, pre + "norm3",
             _lin(sd, pre + "ffn.2", F.relu(_lin(sd, pre + "ffn.0", f))))               # :368
     # ModulationLayer.forward :276-294
     ss = _lin(sd, pre + "time_modulation.scale_shift_mlp.1", F.mish(time_embed))
     scale, shift = ss.chunk(2, dim=-1)
     f = f * (1 + scale) + shift
+    rec("x3", f)
     # DiffMotionPlanningRefinementModule.forward :244-256
     bs, modes, _ = f.shape
     c = f
@@ -160,7 +168,7 @@ def decoder_layer(sd: SD, pre: str, traj_feature, points, bev_feature, agents_qu
 
 
 def diff_decoder(sd: SD, num_layers: int, traj_feature, points, bev_feature, agents_query,
-                 ego_query, time_embed, heads, lmx, lmy):
+                 ego_query, time_embed, heads, lmx, lmy, trace=None, tkey=""):
     """CustomTransformerDecoder.forward, transfuser_model_v2.py:404-425: every layer sees
     the SAME traj_feature; only the points chain."""
     regs: List[torch.Tensor] = []
@@ -168,7 +176,11 @@ def diff_decoder(sd: SD, num_layers: int, traj_feature, points, bev_feature, age
     pts = points
     for l in range(num_layers):
         reg, cls = decoder_layer(sd, f"diff_decoder.layers.{l}.", traj_feature, pts, bev_feature,
-                                 agents_query, ego_query, time_embed, heads, lmx, lmy)
+                                 agents_query, ego_query, time_embed, heads, lmx, lmy,
+                                 trace, f"{tkey}l{l}.")
+        if trace is not None:
+            trace[f"{tkey}l{l}.reg"] = reg.detach().clone()
+            trace[f"{tkey}l{l}.cls"] = cls.detach().clone()
         regs.append(reg)
         clss.append(cls)
         pts = reg[..., :2].clone().detach()                                            # :424
@@ -181,7 +193,8 @@ def forward_test(sd: SD, ego_query: torch.Tensor, agents_query: torch.Tensor,
                  bev_feature: torch.Tensor, noise: torch.Tensor, *, num_layers: int = 2,
                  step_num: int = 2, trunc_timestep: int = 8, heads: int = 8,
                  lidar_max_x: float = 32.0, lidar_max_y: float = 32.0,
-                 dtype: Optional[torch.dtype] = None) -> Dict[str, torch.Tensor]:
+                 dtype: Optional[torch.dtype] = None,
+                 trace: Optional[dict] = None) -> Dict[str, torch.Tensor]:
     """TrajectoryHead.forward_test, transfuser_model_v2.py:578-641, with the noise of
     :593 injected.  Returns the reference's ``trajectory`` plus the locals
     ``poses_reg`` / ``poses_cls`` of the last denoise step (:630-631) as
@@ -208,7 +221,7 @@ def forward_test(sd: SD, ego_query: torch.Tensor, agents_query: torch.Tensor,
     modes = img.shape[1]
     d_model = sd["plan_anchor_encoder.3.weight"].shape[0]
     poses_reg = poses_cls = None
-    for k in roll:                                                                     # :600
+    for si, k in enumerate(roll):                                                      # :600
         x_boxes = torch.clamp(img, min=-1, max=1)                                      # :601
         pts = denorm_odo(x_boxes)                                                      # :602
         emb = gen_sineembed_for_position(pts, hidden_dim=64).flatten(-2)               # :605-607
@@ -219,8 +232,13 @@ def forward_test(sd: SD, ego_query: torch.Tensor, agents_query: torch.Tensor,
         ts = torch.tensor([int(k)], dtype=torch.long).expand(bs)                       # :611-621
         te = sinusoidal_pos_emb(ts, d_model).to(work_dtype)                            # :622 (463-468)
         te = _lin(sd, "time_mlp.3", F.mish(_lin(sd, "time_mlp.1", te))).view(bs, 1, -1)  # :623
+        if trace is not None:
+            trace[f"s{si}.img"] = img.clone()
+            trace[f"s{si}.pts"] = pts.clone()
+            trace[f"s{si}.q0"] = f.clone()
         regs, clss = diff_decoder(sd, num_layers, f, pts, bev_feature, agents_query,
-                                  ego_query, te, heads, lidar_max_x, lidar_max_y)      # :626-629
+                                  ego_query, te, heads, lidar_max_x, lidar_max_y,
+                                  trace, f"s{si}.")                                    # :626-629
         poses_reg, poses_cls = regs[-1], clss[-1]                                      # :630-631
         x_start = norm_odo(poses_reg[..., :2])                                         # :632-633
         img = sched.step(model_output=x_start, timestep=k, sample=img).prev_sample     # :634-636
