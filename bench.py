@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native DiffusionDrive planning head.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun)
+    python bench.py --impl reference --steps K --warmup W    (CPU arm: the oracle port)
+
+A "step" is one pass of TrajectoryHead.forward_test (2-step DDIM, 2 decoder layers, 20
+anchors x 8 poses) over one batch of synthetic scenes: 4096 scenes per GPU, bf16 tensor-core
+engine, fp32 NCHW bev_feature already resident in HBM (the layout/bf16 conversion runs INSIDE
+the timed region).  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "scenes/sec (2-step DDIM head)"
+UNIT = "scenes/s"
+A, P, D, NA, C_BEV, H, W = 20, 8, 256, 30, 256, 64, 64
+# algorithmic work of the on-demand value_proj conv
+K_CONV = 9 * C_BEV
+FLOP_PER_CONV_ROW = 2.0 * K_CONV * 256
+CONTRACT_ROWS_PER_SCENE_CALL = A * P * 4          # 640 corner rows, no dedup
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {"bf16_tflops_sustained": p.get("bf16_tflops_sustained", 1415.4),
+                "bf16_tflops": p.get("bf16_tflops", 1678.2), "hbm_gbs": p.get("hbm_gbs", 6551.0),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_tflops_sustained": 1400.0, "bf16_tflops": 1590.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_oracle_rate(batch: int, reps: int, warm: int):
+    """scenes/s of the oracle port (as-written reference algorithm, torch CPU ops)."""
+    import torch
+    from diffusiondrive_b200 import synth
+    from oracle import head_oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = synth.make_state_dict()
+    ft = synth.make_features(batch)
+    nz = synth.make_noise(batch)
+    times = []
+    for i in range(warm + reps):
+        t0 = time.perf_counter()
+        head_oracle.forward_test(sd, ft["ego_query"], ft["agents_query"], ft["bev_feature"], nz)
+        dt = time.perf_counter() - t0
+        if i >= warm:
+            times.append(dt)
+    return batch / (sum(times) / len(times)), sum(times) / len(times), torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = args.ref_batch
+    rate, sec, threads = cpu_oracle_rate(batch, args.steps, args.warmup)
+    sample = (f"{batch} scenes per step of the same synthetic workload (seed-identical weights, "
+              f"features, noise), fp32, torch CPU ops, {threads} threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "TrajectoryHead.forward_test, 20 anchors x 8 poses, 2 DDIM steps, "
+                               "2 decoder layers, BEV 256x64x64", "scenes_per_step": batch,
+                   "note": "CPU arm = oracle port of the reference algorithm as written "
+                           "(the reference is pure Python/PyTorch and cannot travel to this box)"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from diffusiondrive_b200 import HeadConfig, TrajectoryHead, synth
+    from diffusiondrive_b200.parallel import gather_scenes
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    B = args.batch
+    precision = args.precision
+
+    sd = synth.make_state_dict()
+    head = TrajectoryHead(P, 1024, D, None, HeadConfig(), plan_anchor=sd["plan_anchor"].numpy(),
+                          precision=precision)
+    head.load_state_dict(sd)
+    head = head.to(dev).eval()
+
+    # ---- synthetic scenes, generated on the device (seed 3000 + rank); the first scenes of
+    # rank 0 are the seeded parity set so that every bench run re-checks parity
+    g = torch.Generator(device=dev).manual_seed(synth.SEED_THROUGHPUT + rank)
+    ego = torch.randn(B, 1, D, device=dev, generator=g)
+    agents = torch.randn(B, NA, D, device=dev, generator=g)
+    bev = torch.randn(B, C_BEV, H, W, device=dev, generator=g)
+    noise = torch.randn(B, A, P, 2, device=dev, generator=g)
+    parity = None
+    n_par = min(B, 256)
+    gold_path = os.path.join(ROOT, "tests", "golden", "default_b256.npz")
+    if rank == 0 and os.path.exists(gold_path):
+        ft = synth.make_features(n_par)
+        ego[:n_par] = ft["ego_query"].to(dev)
+        agents[:n_par] = ft["agents_query"].to(dev)
+        bev[:n_par] = ft["bev_feature"].to(dev)
+        noise[:n_par] = synth.make_noise(n_par).to(dev)
+        del ft
+
+    head.reserve(B)
+    head.frozen = False
+    total = B * world
+
+    def step():
+        out = head(ego, agents, bev, noise=noise)
+        if world > 1:
+            return gather_scenes(out["trajectory"], total), out
+        return out["trajectory"], out
+
+    for _ in range(max(args.warmup, 3)):
+        traj, out = step()
+    torch.cuda.synchronize()
+    head.frozen = True
+    launches_per_step = head.last_launch_count()
+    if rank == 0 and os.path.exists(gold_path):
+        z = np.load(gold_path)
+        modes = out["trajectory_modes"][:n_par].float().cpu().numpy()
+        idx = out["mode_idx"][:n_par].cpu().numpy()
+        dxy = float(np.abs(modes[..., :2] - z["trajectory_modes"][:n_par, ..., :2]).max())
+        agree = idx == z["mode_idx"][:n_par]
+        s = np.sort(z["trajectory_scores"][:n_par], axis=1)
+        big = (s[:, -1] - s[:, -2]) > 0.05
+        parity = {"scenes": n_par, "max_dxy_m": dxy, "tolerance_m": 2e-2 if precision == "bf16" else 1e-4,
+                  "mode_agreement": float(agree.mean()),
+                  "mode_agreement_margin_gt_0.05": float(agree[big].mean()) if big.any() else None,
+                  "against": "live-reference golden (tests/golden/default_b256.npz)"}
+
+    # ---- timed region: barrier + sync, K steps between CUDA events, max over ranks
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    elapsed_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = total / (ms_per_step * 1e-3)
+
+    # ---- per-stage device times (one profiled forward, outside the timed region)
+    head.set_profiling(True)
+    head(ego, agents, bev, noise=noise)
+    prof = head.stage_profile()
+    conv_rows = head.debug_tap("conv_rows", np.int32)
+    head.set_profiling(False)
+    peaks = _peaks()
+    n_conv = max(prof["conv"]["spans"], 1)
+    conv_ms = prof["conv"]["ms"] / n_conv
+    rows_unique = float(conv_rows.sum()) / n_conv
+    stage_total = sum(v["ms"] for v in prof.values())
+    roofline = None
+    if precision == "bf16" and conv_ms > 0:
+        flops_unique = rows_unique * FLOP_PER_CONV_ROW
+        flops_contract = B * CONTRACT_ROWS_PER_SCENE_CALL * FLOP_PER_CONV_ROW
+        achieved = flops_unique / (conv_ms * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "conv_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                with open(tpath) as fh:
+                    traffic = json.load(fh).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        roofline = {
+            "kernel": "tc_gemm_kernel<2,true> (on-demand value_proj conv, tcgen05)",
+            "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"],
+            "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"],
+            "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside the step)",
+            "traffic": traffic,
+            "flops_per_launch": flops_unique,
+            "flops_per_launch_basis": "unique sampled pixels (exact dedup) x 2*2304*256",
+            "achieved_contract_no_dedup": flops_contract / (conv_ms * 1e-3) / 1e12,
+            "launch_ms": conv_ms, "launches_per_step": n_conv,
+            "share_of_step": prof["conv"]["ms"] / stage_total if stage_total else None,
+            "unique_rows_per_scene_call": rows_unique / B,
+        }
+    # secondary, HBM-bound stage: the NCHW fp32 -> NHWC bf16 layout pass
+    bev_ms = prof["bev_layout"]["ms"]
+    hbm = None
+    if bev_ms > 0:
+        out_b = 2 if precision == "bf16" else 4
+        bytes_alg = B * C_BEV * H * W * (4 + out_b)
+        hbm = {"kernel": "bev_to_nhwc_kernel", "bound": "hbm", "achieved": bytes_alg / (bev_ms * 1e-3) / 1e9,
+               "peak": peaks["hbm_gbs"], "unit": "GB/s",
+               "frac": bytes_alg / (bev_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "launch_ms": bev_ms,
+               "share_of_step": bev_ms / stage_total if stage_total else None}
+
+    # ---- end to end through the host-buffer entry point (pinned host memory, H2D + D2H timed)
+    e2e = None
+    Be = min(B, args.e2e_batch)
+    try:
+        h_ego = ego[:Be].cpu().pin_memory()
+        h_agents = agents[:Be].cpu().pin_memory()
+        h_bev = bev[:Be].cpu().pin_memory()
+        h_noise = noise[:Be].cpu().pin_memory()
+        for _ in range(2):
+            o = head(h_ego, h_agents, h_bev, noise=h_noise)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        k_e2e = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(k_e2e):
+            o = head(h_ego, h_agents, h_bev, noise=h_noise)
+            _ = float(o["trajectory"][0, 0, 0])        # result is read on the host
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / k_e2e
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        h2d = sum(x.numel() * x.element_size() for x in (h_ego, h_agents, h_bev, h_noise))
+        d2h = sum(x.numel() * x.element_size() for x in o.values())
+        e2e = {"value": Be * world / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "scenes_per_step_per_gpu": Be, "ms_per_step": ms,
+               "steps": k_e2e,
+               "path": "TrajectoryHead.forward with CPU (pinned) tensors -> ddh_forward_host: "
+                       "H2D of fp32 NCHW inputs, forward, D2H of trajectory/modes/scores/idx"}
+        del h_ego, h_agents, h_bev, h_noise
+    except Exception as ex:          # keep the bench line even if pinning fails on a small host
+        e2e = {"value": None, "unit": UNIT, "error": repr(ex)}
+
+    # ---- batch-1 latency (device-resident single scene), p50 over single calls
+    lat = None
+    try:
+        e1s = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+               for _ in range(args.latency_iters)]
+        one = (ego[:1].clone(), agents[:1].clone(), bev[:1].clone())
+        n1 = noise[:1].clone()
+        for _ in range(10):
+            head(*one, noise=n1)
+        torch.cuda.synchronize()
+        wall = []
+        for a, b in e1s:
+            t0 = time.perf_counter()
+            a.record()
+            head(*one, noise=n1)
+            b.record()
+            b.synchronize()
+            wall.append((time.perf_counter() - t0) * 1e6)
+        dts = sorted(a.elapsed_time(b) * 1e3 for a, b in e1s)
+        lat = {"p50_us": dts[len(dts) // 2], "p90_us": dts[int(len(dts) * 0.9)],
+               "wall_p50_us": sorted(wall)[len(wall) // 2], "iters": len(dts),
+               "precision": precision, "launches": head.last_launch_count()}
+    except Exception as ex:
+        lat = {"error": repr(ex)}
+
+    # ---- CPU baseline (oracle port) on this box's host cores, rank 0 at N = 1 only
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, sec, threads = cpu_oracle_rate(args.ref_batch, 3, 1)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{args.ref_batch} scenes x 3 timed forwards (+1 warm-up) of the oracle "
+                         f"port, fp32, {threads} torch threads, {sec * 1e3:.0f} ms per forward"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": precision, "data": "synthetic",
+            "config": {
+                "workload": "TrajectoryHead bf16 throughput, batch 4096 per GPU (BASELINE configs[2]); "
+                            "20 anchors x 8 poses, 2 DDIM steps, 2 decoder layers, BEV 256x64x64, "
+                            "30 agents" if precision == "bf16" and B == 4096 else
+                            f"TrajectoryHead {precision}, batch {B} per GPU",
+                "scenes_per_gpu": B, "global_batch": total, "precision": precision,
+                "bev_input": "fp32 NCHW resident in HBM; NHWC/bf16 layout pass inside the timed region",
+                "parallelism": f"scene-sharded x{world}, one all-gather of trajectories per step"
+                               if world > 1 else "single GPU",
+                "l2": f"inputs per step ({B * C_BEV * H * W * 4 / 2**30:.1f} GiB per GPU) exceed the 126 MB L2; no flush needed",
+                "weights": "random init (seed 0), synthetic arc anchors",
+            },
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches_per_step": launches_per_step,
+            "roofline": roofline, "roofline_hbm_stage": hbm, "cpu_baseline": cpu,
+            "latency_b1": lat, "parity": parity,
+            "stage_ms": {k: round(v["ms"], 4) for k, v in prof.items()},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="scenes per GPU per step")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--e2e-batch", type=int, default=1024)
+    ap.add_argument("--ref-batch", type=int, default=16)
+    ap.add_argument("--latency-iters", type=int, default=200)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -110,9 +110,30 @@ struct ddh_handle {
 
   std::map<std::string, std::pair<const void*, size_t>> taps;
   int launches = 0;
+  // optional per-stage device timing (ddh_set_profiling)
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<std::pair<int, int>> ev_spans;   // (stage id, index of the begin event)
+  int ev_used = 0;
+  int* conv_rows = nullptr;                    // [S*L] unique value_proj rows per conv launch
 };
 
 namespace {
+
+const char* const kStageNames[] = {"bev_layout", "hoist_kv_ego", "embed_encode", "plan", "conv",
+                                   "combine", "gemm_chain", "attn_core", "reg_finish", "select",
+                                   "init"};
+constexpr int kNumStages = sizeof(kStageNames) / sizeof(kStageNames[0]);
+enum { ST_BEV = 0, ST_HOIST, ST_EMBED, ST_PLAN, ST_CONV, ST_COMBINE, ST_GEMM, ST_ATTN, ST_REG,
+       ST_SELECT, ST_INIT };
+
+struct ProfSpan {
+  ddh_handle* h;
+  cudaStream_t st;
+  bool on;
+  ProfSpan(ddh_handle* h_, int stage, cudaStream_t st_);
+  ~ProfSpan();
+};
 
 int fail(ddh_handle* h, int code, const std::string& msg) {
   if (h) h->err = msg; else g_create_error = msg;
@@ -125,6 +146,21 @@ int fail(ddh_handle* h, int code, const std::string& msg) {
     if (e__ != cudaSuccess)                                                          \
       return fail(h, DDH_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
   } while (0)
+
+ProfSpan::ProfSpan(ddh_handle* h_, int stage, cudaStream_t st_) : h(h_), st(st_), on(h_->profiling) {
+  if (!on) return;
+  while ((int)h->ev_pool.size() < h->ev_used + 2) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    h->ev_pool.push_back(e);
+  }
+  h->ev_spans.push_back({stage, h->ev_used});
+  cudaEventRecord(h->ev_pool[h->ev_used], st);
+  h->ev_used += 2;
+}
+ProfSpan::~ProfSpan() {
+  if (on) cudaEventRecord(h->ev_pool[h->ev_spans.back().second + 1], st);
+}
 
 template <typename T>
 int dev_alloc(ddh_handle* h, std::vector<void*>& owner, T** out, size_t count) {
@@ -277,6 +313,7 @@ int ensure_ws(ddh_handle* h, int B) {
   WS(h->egov, (size_t)L * B * D);
   WS(h->upix, (size_t)B * h->rcap);
   WS(h->nuniq, B);
+  WS(h->conv_rows, s.num_layers * s.num_steps);
   WS(h->ent_slot, M * s.num_poses * 4);
   WS(h->ent_w, M * s.num_poses * 4);
   WS(h->V, (size_t)B * h->rcap * D);
@@ -314,6 +351,7 @@ void register_taps(ddh_handle* h, int B) {
   t["egov"] = {h->egov, (size_t)s.num_layers * B * D * 4};
   t["upix"] = {h->upix, (size_t)B * h->rcap * 4};
   t["nuniq"] = {h->nuniq, (size_t)B * 4};
+  t["conv_rows"] = {h->conv_rows, (size_t)s.num_layers * s.num_steps * 4};
   t["ent_slot"] = {h->ent_slot, M * s.num_poses * 4 * 4};
   t["ent_w"] = {h->ent_w, M * s.num_poses * 4 * 4};
   t["V"] = {h->V, (size_t)B * h->rcap * D * 4};
@@ -388,6 +426,7 @@ void ddh_destroy(ddh_handle* h) {
   free_all(h->owned_w);
   free_all(h->owned_ws);
   free_all(h->owned_host);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   delete h;
 }
 
@@ -543,8 +582,12 @@ int ddh_forward(ddh_handle* h, const float* ego, const float* agents, const void
   const int M = B * A, F = s.d_ffn, HW = s.bev_h * s.bev_w;
   const int want_dtype = bf ? DDH_BF16 : DDH_F32;
 
+  h->ev_used = 0;
+  h->ev_spans.clear();
+  CU_TRY(h, cudaMemsetAsync(h->conv_rows, 0, (size_t)L * S * 4, st));
   // ---- BEV map -> NHWC in the engine's operand type
   const void* bevn = bev;
+  { ProfSpan ps(h, ST_BEV, st);
   if (bev_layout == DDH_NCHW) {
     launch_bev_to_nhwc(bev, bev_dtype, h->bev_nhwc, want_dtype, B, s.bev_channels, HW, st);
     h->launches++;
@@ -558,8 +601,10 @@ int ddh_forward(ddh_handle* h, const float* ego, const float* agents, const void
     h->launches++;
     bevn = h->bev_nhwc;
   }
+  }
 
   // ---- hoisted per (scene, layer): agent K|V and the collapsed ego vector
+  { ProfSpan ps(h, ST_HOIST, st);
   if (bf) {
     launch_cast_f32_bf16(agents, h->agents16, (size_t)B * Na * D, st);
     launch_cast_f32_bf16(ego, h->ego16, (size_t)B * D, st);
@@ -575,11 +620,13 @@ int ddh_forward(ddh_handle* h, const float* ego, const float* agents, const void
     e2.ldo32 = D;
     run_gemm(h, h->layers[l].ego, ego, h->ego16, D, B, e2, st);
   }
+  }
 
   // ---- truncated noising of the anchors (:591-597)
   const float ac_tr = h->ac[s.trunc_timestep];
+  { ProfSpan ps(h, ST_INIT, st);
   launch_init_img(h->anchors, noise, h->img, B, A * P, sqrtf(ac_tr), sqrtf(1.0f - ac_tr), st);
-  h->launches++;
+  h->launches++; }
 
   float* modes = out_modes ? out_modes : h->modes_buf;
   float* scores = out_scores ? out_scores : h->scores_buf;
@@ -587,9 +634,10 @@ int ddh_forward(ddh_handle* h, const float* ego, const float* agents, const void
 
   for (int si = 0; si < S; ++si) {
     // clamp, denorm, sine embedding, plan_anchor_encoder (:601-609)
-    launch_embed(h->img, h->pts, h->emb32, h->emb16, M, P, h->dim_t, st);
-    h->launches++;
     {
+      ProfSpan ps(h, ST_EMBED, st);
+      launch_embed(h->img, h->pts, h->emb32, h->emb16, M, P, h->dim_t, st);
+      h->launches++;
       RowEpi e;
       e.relu = 1; e.ln1_g = h->enc_ln_g; e.ln1_b = h->enc_ln_b;
       e.out_f32 = h->e1_32; e.ldo32 = D; e.out_bf16 = h->e1_16; e.ldo16 = D;
@@ -602,9 +650,11 @@ int ddh_forward(ddh_handle* h, const float* ego, const float* agents, const void
       const PackedLayer& pl = h->layers[l];
       const bool last_layer = (l == L - 1), last_step = (si == S - 1);
       // -- cross_bev_attention (modules/blocks.py:88-129)
+      { ProfSpan ps(h, ST_PLAN, st);
       launch_plan(h->q0_32, pl.attw_w, pl.attw_b, h->pts, h->upix, h->nuniq, h->ent_slot,
-                  h->ent_w, B, A, P, s.bev_h, s.bev_w, h->rcap, oc, st);
+                  h->ent_w, h->conv_rows + si * L + l, B, A, P, s.bev_h, s.bev_w, h->rcap, oc, st); }
       {
+        ProfSpan ps(h, ST_CONV, st);
         GemmParams gp;
         gp.K = pl.conv.K;
         gp.bev = bevn; gp.upix = h->upix; gp.nuniq = h->nuniq; gp.rcap = h->rcap;
@@ -614,9 +664,11 @@ int ddh_forward(ddh_handle* h, const float* ego, const float* agents, const void
         if (bf) launch_tc_conv(gp, pl.conv.map, B, st);
         else { gp.W = pl.conv.wt32; gp.ldw = D; launch_simt_conv(gp, B, st); }
       }
-      launch_combine(h->V, h->ent_slot, h->ent_w, h->s32, h->s16, B, A, P, h->rcap, st);
+      { ProfSpan ps(h, ST_COMBINE, st);
+      launch_combine(h->V, h->ent_slot, h->ent_w, h->s32, h->s16, B, A, P, h->rcap, st); }
       h->launches += 3;
       {
+        ProfSpan ps(h, ST_GEMM, st);
         RowEpi e;   // output_proj + residual (:127-129)
         e.res = h->q0_32; e.ldres = D;
         e.out_f32 = h->x1_32; e.ldo32 = D; e.out_bf16 = h->x1_16; e.ldo16 = D;
@@ -624,13 +676,16 @@ int ddh_forward(ddh_handle* h, const float* ego, const float* agents, const void
       }
       // -- cross_agent_attention + norm1, cross_ego_attention + norm2 (:355-365)
       {
+        ProfSpan ps(h, ST_GEMM, st);
         RowEpi e;
         e.out_f32 = h->qh32; e.ldo32 = D;
         run_gemm(h, pl.q, h->x1_32, h->x1_16, D, M, e, st);
       }
+      { ProfSpan ps(h, ST_ATTN, st);
       launch_attn_core(h->qh32, h->kv32 + (size_t)l * B * Na * 2 * D, h->o32, h->o16, B, A, Na,
-                       s.num_heads, st);
+                       s.num_heads, st); }
       h->launches++;
+      ProfSpan* chain = new ProfSpan(h, ST_GEMM, st);
       {
         RowEpi e;
         e.res = h->x1_32; e.ldres = D;
@@ -673,6 +728,7 @@ int ddh_forward(ddh_handle* h, const float* ego, const float* agents, const void
         e2.out_f32 = h->r2_32; e2.ldo32 = D;
         run_gemm(h, pl.reg2, h->r1_32, h->r1_16, D, M, e2, st);
       }
+      delete chain;
       DdimCoef dc{0.f, 1.f, 1.f, 0.f};
       const int do_ddim = (last_layer && !last_step) ? 1 : 0;
       if (do_ddim) {
@@ -681,11 +737,13 @@ int ddh_forward(ddh_handle* h, const float* ego, const float* agents, const void
         dc.sqrt_ac_t = sqrtf(ac_t); dc.sqrt_1m_ac_t = sqrtf(1.0f - ac_t);
         dc.sqrt_ac_prev = sqrtf(ac_p); dc.sqrt_1m_ac_prev = sqrtf(1.0f - ac_p);
       }
-      launch_reg_finish(h->r2_32, pl.reg4_w, pl.reg4_b, h->pts, h->img, modes, M, P, do_ddim, dc, st);
+      { ProfSpan ps(h, ST_REG, st);
+      launch_reg_finish(h->r2_32, pl.reg4_w, pl.reg4_b, h->pts, h->img, modes, M, P, do_ddim, dc, st); }
       h->launches++;
     }
   }
-  launch_select(scores, modes, out_traj, reinterpret_cast<long long*>(out_mode_idx), B, A, P, st);
+  { ProfSpan ps(h, ST_SELECT, st);
+  launch_select(scores, modes, out_traj, reinterpret_cast<long long*>(out_mode_idx), B, A, P, st); }
   h->launches++;
   CU_TRY(h, cudaGetLastError());
   return DDH_OK;
@@ -736,6 +794,34 @@ int ddh_forward_host(ddh_handle* h, const float* ego, const float* agents, const
 }
 
 int ddh_last_launch_count(const ddh_handle* h) { return h ? h->launches : 0; }
+
+int ddh_set_profiling(ddh_handle* h, int on) {
+  if (!h) return DDH_ERR_BAD_ARG;
+  h->profiling = on != 0;
+  return DDH_OK;
+}
+
+int ddh_get_profile(ddh_handle* h, const char* stage, float* total_ms, int* spans) {
+  if (!h || !stage || !total_ms || !spans) return DDH_ERR_BAD_ARG;
+  int id = -1;
+  for (int i = 0; i < kNumStages; ++i) if (!strcmp(stage, kStageNames[i])) id = i;
+  if (id < 0) return fail(h, DDH_ERR_BAD_ARG, std::string("ddh_get_profile: unknown stage ") + stage);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return fail(h, DDH_ERR_CUDA, std::string("ddh_get_profile: ") + cudaGetErrorString(e));
+  float tot = 0.f;
+  int n = 0;
+  for (auto& sp : h->ev_spans) {
+    if (sp.first != id) continue;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev_pool[sp.second], h->ev_pool[sp.second + 1]) == cudaSuccess) {
+      tot += ms;
+      ++n;
+    }
+  }
+  *total_ms = tot;
+  *spans = n;
+  return DDH_OK;
+}
 
 long long ddh_debug_copy(ddh_handle* h, const char* name, void* host_dst, size_t max_bytes) {
   if (!h || !name || !host_dst) return DDH_ERR_BAD_ARG;

@@ -415,8 +415,9 @@ __global__ void __launch_bounds__(256) plan_kernel(const float* __restrict__ q0,
                                                    const float* __restrict__ pts,
                                                    int* __restrict__ upix, int* __restrict__ nuniq,
                                                    int* __restrict__ ent_slot,
-                                                   float* __restrict__ ent_w, int A, int P, int H,
-                                                   int W, int rcap, OdoConsts oc) {
+                                                   float* __restrict__ ent_w,
+                                                   int* __restrict__ rows_total, int A, int P,
+                                                   int H, int W, int rcap, OdoConsts oc) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int HW = H * W;
   unsigned short* table = reinterpret_cast<unsigned short*>(smraw);        // [HW]
@@ -489,7 +490,10 @@ __global__ void __launch_bounds__(256) plan_kernel(const float* __restrict__ q0,
     }
   }
   __syncthreads();
-  if (tid == 0) nuniq[scene] = total_s;
+  if (tid == 0) {
+    nuniq[scene] = total_s;
+    if (rows_total) atomicAdd(rows_total, total_s);
+  }
   // ---- entries
   for (int e = tid; e < AP; e += 256) {
     const float px = pts[((size_t)scene * AP + e) * 2 + 0];
@@ -510,16 +514,16 @@ __global__ void __launch_bounds__(256) plan_kernel(const float* __restrict__ q0,
   }
 }
 void launch_plan(const float* q0, const float* attw_w, const float* attw_b, const float* pts,
-                 int* upix, int* nuniq, int* ent_slot, float* ent_w, int B, int A, int P, int H,
-                 int W, int rcap, OdoConsts oc, cudaStream_t st) {
+                 int* upix, int* nuniq, int* ent_slot, float* ent_w, int* rows_total, int B, int A,
+                 int P, int H, int W, int rcap, OdoConsts oc, cudaStream_t st) {
   const int smem = ((H * W * 2 + 15) / 16) * 16 + A * P * 4;
   static int cur = 0;
   if (smem > cur) {
     cudaFuncSetAttribute(plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cur = smem;
   }
-  plan_kernel<<<B, 256, smem, st>>>(q0, attw_w, attw_b, pts, upix, nuniq, ent_slot, ent_w, A, P,
-                                     H, W, rcap, oc);
+  plan_kernel<<<B, 256, smem, st>>>(q0, attw_w, attw_b, pts, upix, nuniq, ent_slot, ent_w,
+                                     rows_total, A, P, H, W, rcap, oc);
 }
 
 // ===================================================================================

@@ -354,5 +354,23 @@ class TrajectoryHead(nn.Module):
                 return buf[:n].view(dtype).copy()
             size *= 4
 
+    STAGES = ("bev_layout", "hoist_kv_ego", "init", "embed_encode", "plan", "conv", "combine",
+              "gemm_chain", "attn_core", "reg_finish", "select")
+
+    def set_profiling(self, on: bool) -> None:
+        """Bracket every stage of the next forwards with CUDA events (bench.py roofline leg)."""
+        _lib.check(self._lib, self._handle, self._lib.ddh_set_profiling(self._handle, int(on)),
+                   "ddh_set_profiling")
+
+    def stage_profile(self) -> Dict[str, Dict[str, float]]:
+        """Per-stage device time of the last forward: {stage: {"ms": total, "spans": n}}."""
+        out = {}
+        for s in self.STAGES:
+            ms, n = C.c_float(), C.c_int()
+            rc = self._lib.ddh_get_profile(self._handle, s.encode(), C.byref(ms), C.byref(n))
+            _lib.check(self._lib, self._handle, rc, "ddh_get_profile")
+            out[s] = {"ms": float(ms.value), "spans": int(n.value)}
+        return out
+
     def last_launch_count(self) -> int:
         return int(self._lib.ddh_last_launch_count(self._handle)) if self._handle else 0

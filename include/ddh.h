@@ -183,6 +183,14 @@ DDH_API int ddh_forward_host(ddh_handle *h, const float *ego, const float *agent
 /* Number of kernel launches issued by the last ddh_forward on this handle. */
 DDH_API int ddh_last_launch_count(const ddh_handle *h);
 
+/* Optional per-stage device timing: when on, ddh_forward brackets each stage with CUDA events
+ * on the caller's stream.  ddh_get_profile synchronises and returns the summed duration and
+ * the number of timed spans of one stage of the LAST forward.  Stages: "bev_layout",
+ * "hoist_kv_ego", "init", "embed_encode", "plan", "conv", "combine", "gemm_chain",
+ * "attn_core", "reg_finish", "select". */
+DDH_API int ddh_set_profiling(ddh_handle *h, int on);
+DDH_API int ddh_get_profile(ddh_handle *h, const char *stage, float *total_ms, int *spans);
+
 /* Test hook: copy a named internal buffer of the last forward to the host (synchronises).
  * Returns the number of bytes copied (>= 0) or a negative ddh_status.  Names are listed in
  * DESIGN.md ("debug taps"); sizes depend on B. */
