@@ -172,6 +172,11 @@ struct GemmParams {
   const int* nuniq = nullptr; // [B]
   int rcap = 0;
   int H = 0, W_ = 0, C = 0;
+  // fused bilinear/attention combine (tensor-engine conv only)
+  const int* ent_slot = nullptr;   // [B][A*ent_per_anchor] slot of the corner pixel or -1
+  const float* ent_w = nullptr;    // [B][A*ent_per_anchor] bilinear * attention weight
+  int n_anchor = 0;
+  int ent_per_anchor = 0;          // P * 4
 };
 
 }  // namespace ddh

@@ -316,7 +316,7 @@ int ensure_ws(ddh_handle* h, int B) {
   WS(h->conv_rows, s.num_layers * s.num_steps);
   WS(h->ent_slot, M * s.num_poses * 4);
   WS(h->ent_w, M * s.num_poses * 4);
-  WS(h->V, (size_t)B * h->rcap * D);
+  if (!bf) WS(h->V, (size_t)B * h->rcap * D);
   WS(h->x1_32, M * D);
   WS(h->qh32, M * D);
   WS(h->r2_32, M * D);
@@ -469,6 +469,8 @@ int ddh_pack_weights(ddh_handle* h, const ddh_weight_ptrs* w, int precision, voi
   if (precision != h->precision) { free_all(h->owned_ws); h->cap_B = 0; }
   h->packed = false;
   h->precision = precision;
+  if (precision == DDH_PREC_BF16 && tc_conv_smem_bytes(s.num_anchors, s.num_poses * 4) > 227 * 1024)
+    return fail(h, DDH_ERR_UNSUPPORTED, "ddh_pack_weights: too many anchors for the bf16 conv kernel's shared memory");
   if (precision == DDH_PREC_BF16 && !h->tc_ready) {
     int e = tc_engine_init();
     if (e) return fail(h, DDH_ERR_CUDA, std::string("tc_engine_init: ") + cudaGetErrorString((cudaError_t)e));
@@ -660,13 +662,22 @@ int ddh_forward(ddh_handle* h, const float* ego, const float* agents, const void
         gp.bev = bevn; gp.upix = h->upix; gp.nuniq = h->nuniq; gp.rcap = h->rcap;
         gp.H = s.bev_h; gp.W_ = s.bev_w; gp.C = s.bev_channels;
         gp.epi.bias = pl.conv.bias; gp.epi.relu = 1;
-        gp.epi.out_f32 = h->V; gp.epi.ldo32 = D;
-        if (bf) launch_tc_conv(gp, pl.conv.map, B, st);
-        else { gp.W = pl.conv.wt32; gp.ldw = D; launch_simt_conv(gp, B, st); }
+        if (bf) {   // combine fused into the conv epilogue: V never leaves the SM
+          gp.ent_slot = h->ent_slot; gp.ent_w = h->ent_w; gp.n_anchor = A; gp.ent_per_anchor = P * 4;
+          gp.epi.out_f32 = h->s32; gp.epi.ldo32 = D; gp.epi.out_bf16 = h->s16; gp.epi.ldo16 = D;
+          launch_tc_conv(gp, pl.conv.map, B, st);
+          h->launches += 2;
+        } else {
+          gp.epi.out_f32 = h->V; gp.epi.ldo32 = D;
+          gp.W = pl.conv.wt32; gp.ldw = D;
+          launch_simt_conv(gp, B, st);
+        }
       }
-      { ProfSpan ps(h, ST_COMBINE, st);
-      launch_combine(h->V, h->ent_slot, h->ent_w, h->s32, h->s16, B, A, P, h->rcap, st); }
-      h->launches += 3;
+      if (!bf) {
+        ProfSpan ps(h, ST_COMBINE, st);
+        launch_combine(h->V, h->ent_slot, h->ent_w, h->s32, h->s16, B, A, P, h->rcap, st);
+        h->launches += 3;
+      }
       {
         ProfSpan ps(h, ST_GEMM, st);
         RowEpi e;   // output_proj + residual (:127-129)

@@ -55,6 +55,7 @@ void launch_time_sinemb(float* emb, int dim, int timestep, cudaStream_t st);
 // 128-byte swizzle).  A is bf16 [M][lda] (dense) or gathered from the NHWC bf16 BEV map.
 void launch_tc_gemm(const GemmParams& p, const CUtensorMap& wmap, int n_total, cudaStream_t st);
 void launch_tc_conv(const GemmParams& p, const CUtensorMap& wmap, int B, cudaStream_t st);
+int tc_conv_smem_bytes(int A, int ent_per_anchor);
 int tc_engine_init();   // sets max dynamic smem attributes; returns cudaError_t as int
 
 }  // namespace ddh

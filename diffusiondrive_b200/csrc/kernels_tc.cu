@@ -23,20 +23,19 @@ constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;                        // 64 bf16 = 128 B = one swizzle span
 constexpr int TC_A_TILE = TC_BM * TC_BK * 2;     // 16 KiB
 constexpr int TC_B_TILE = D * TC_BK * 2;         // 32 KiB
-constexpr int TC_CS_LD = D + 4;                  // padded fp32 staging row
-constexpr int TC_LAG = 2;                        // cp.async groups kept in flight
+constexpr int TC_BAR_BYTES = 256;
 
-template <int NT>
-struct TcCfg {
-  static constexpr int kStages = (NT == 1) ? 4 : 3;
-  static constexpr int kStageBytes = NT * TC_A_TILE + TC_B_TILE;
-  static constexpr int kPipeBytes = kStages * kStageBytes;
-  static constexpr int kStagingBytes = 4 * 32 * TC_CS_LD * 4;
-  static constexpr int kBarBytes = 256;
-  static constexpr int kSmemBytes =
-      (kPipeBytes > kStagingBytes ? kPipeBytes : kStagingBytes) + kBarBytes + 1024;
-  static constexpr int kTmemCols = NT * D;       // 256 or 512 (power of two)
-};
+// dense GEMM: 1 row tile, 2 stages, 2 CTAs per SM (one CTA's epilogue overlaps the other's
+// main loop); conv: 2 row tiles share each weight tile, 3 stages, 1 CTA per SM.
+constexpr int G_NS = 2;
+constexpr int G_STAGE = TC_A_TILE + TC_B_TILE;                 // 48 KiB
+constexpr int G_SMEM = G_NS * G_STAGE + TC_BAR_BYTES + 1024;
+constexpr int C_NT = 2;
+constexpr int C_NS = 3;
+constexpr int C_STAGE = C_NT * TC_A_TILE + TC_B_TILE;          // 64 KiB
+constexpr int C_PIPE = C_NS * C_STAGE;                         // 192 KiB
+constexpr int C_VS_LD = 128 + 4;                               // fp32 staging row (half of N)
+static_assert(C_NT * TC_BM * C_VS_LD * 4 <= C_PIPE, "combine staging must fit in the pipeline");
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -78,9 +77,14 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32
                : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+// The mbarrier receives one arrival from this thread once all its prior cp.async have landed
+// (.noinc: the arrival counts against the barrier's expected count).  Same producer/consumer
+// protocol as CUTLASS's SM100 cp.async + UMMA mainloop.
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
                                             int c0, int c1) {
@@ -143,6 +147,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+      "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
+      "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+      "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 
 // Shared-memory matrix descriptor: K-major operand, 128-byte swizzle, bf16.
 // Rows are 128 B apart, 8-row groups 1024 B apart (SBO = 64 in 16-byte units); LBO is unused
@@ -161,57 +180,73 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16_m128_n256() {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
 }
 
-// ------------------------------------------------------------------ the kernel
-template <int NT, bool CONV>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// ------------------------------------------------------------------ shared roles
+struct TcBars {
+  uint32_t base;
+  int ns;
+  __device__ __forceinline__ uint32_t full(int s) const { return base + s * 8; }
+  __device__ __forceinline__ uint32_t empty(int s) const { return base + (ns + s) * 8; }
+  __device__ __forceinline__ uint32_t accum() const { return base + 2 * ns * 8; }
+  __device__ __forceinline__ uint32_t passgo() const { return base + (2 * ns + 1) * 8; }
+};
+
+// One k-chunk of MMAs: NT_ACTIVE row tiles x (64/16) instructions, then release the stage.
+template <int NT>
+__device__ __forceinline__ void mma_chunk(uint32_t a_stage, uint32_t b_stage, uint32_t tmem_base,
+                                          int nt_active, bool first, uint32_t idesc,
+                                          uint32_t empty_bar) {
+  for (int t = 0; t < nt_active; ++t) {
+#pragma unroll
+    for (int k4 = 0; k4 < TC_BK / 16; ++k4) {
+      const uint64_t adesc = umma_desc_sw128(a_stage + t * TC_A_TILE + k4 * 32);
+      const uint64_t bdesc = umma_desc_sw128(b_stage + k4 * 32);
+      umma_bf16(tmem_base + t * D, adesc, bdesc, idesc, (first && k4 == 0) ? 0u : 1u);
+    }
+  }
+  umma_commit(empty_bar);
+}
+
+// ===================================================================================
+// Dense rows GEMM + fused row epilogue (the Linear layers of the decoder chain).
+// Epilogue: thread r of the 128 epilogue threads owns output row r (TMEM lane r) and walks
+// its 256 columns in 8 blocks of 32 straight out of TMEM; LayerNorm statistics are
+// thread-local sums, intermediate rows are written back to TMEM (tcgen05.st) between passes,
+// nothing is staged in shared memory.
+// ===================================================================================
+__device__ __forceinline__ void ldg_row32(const float* p, float (&o)[32]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p) + q);
+    o[4 * q + 0] = t.x; o[4 * q + 1] = t.y; o[4 * q + 2] = t.z; o[4 * q + 3] = t.w;
+  }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
 tc_gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap) {
-  using Cfg = TcCfg<NT>;
-  constexpr int NS = Cfg::kStages;
+  constexpr int NS = G_NS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
   uint8_t* sm = smem_raw + pad;
   const uint32_t sm_addr = raw_addr + pad;
-  constexpr int kPipeOrStage =
-      Cfg::kPipeBytes > Cfg::kStagingBytes ? Cfg::kPipeBytes : Cfg::kStagingBytes;
-  const uint32_t bar_addr = sm_addr + kPipeOrStage;  // full[NS], empty[NS], accum, tmem slot
+  const TcBars bars{sm_addr + NS * G_STAGE, NS};
   volatile uint32_t* tmem_slot =
-      reinterpret_cast<volatile uint32_t*>(sm + kPipeOrStage + (2 * NS + 1) * 8);
-
+      reinterpret_cast<volatile uint32_t*>(sm + NS * G_STAGE + (2 * NS + 2) * 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  // ---- tile coordinates
-  int n0 = 0, row0, rows_valid, scene = 0;
-  long long out_row0;
-  if (CONV) {
-    scene = blockIdx.y;
-    const int nu = p.nuniq[scene];
-    row0 = blockIdx.x * (NT * TC_BM);
-    if (row0 >= nu) return;
-    rows_valid = min(NT * TC_BM, nu - row0);
-    out_row0 = (long long)scene * p.rcap + row0;
-  } else {
-    row0 = blockIdx.x * (NT * TC_BM);
-    rows_valid = min(NT * TC_BM, p.M - row0);
-    n0 = blockIdx.y * D;
-    out_row0 = row0;
-  }
-  const int nt_active = (rows_valid + TC_BM - 1) / TC_BM;
+  const int row0 = blockIdx.x * TC_BM;
+  const int rows_valid = min(TC_BM, p.M - row0);
+  const int n0 = blockIdx.y * D;
   const int KC = p.K / TC_BK;
-
-  auto full_bar = [&](int s) { return bar_addr + s * 8; };
-  auto empty_bar = [&](int s) { return bar_addr + (NS + s) * 8; };
-  const uint32_t accum_bar = bar_addr + 2 * NS * 8;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NS; ++s) {
-      mbar_init(full_bar(s), 128 + 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(bars.full(s), 128 + 1);
+      mbar_init(bars.empty(s), 1);
     }
-    mbar_init(accum_bar, 1);
+    mbar_init(bars.accum(), 1);
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc<Cfg::kTmemCols>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  if (warp == 5) tmem_alloc<D>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
   if (warp == 4 && lane == 0) tma_prefetch_desc(&wmap);
   tc_fence_before();
   __syncthreads();
@@ -219,168 +254,445 @@ tc_gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap) {
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
-    // ======================= A producers ==========================================
+    // ---------------- A producers: 8 rows x one 16-byte chunk per thread and k-chunk
     const int tid = threadIdx.x;
-    const int j = tid & 7;        // 16-byte chunk of the 128-byte row
-    const int rb = tid >> 3;      // 0..15
-    constexpr int RPT = NT * 8;   // rows per thread
-    int info[RPT];                // CONV: (y << 16) | x, or -1 ; dense: 1 / -1
-#pragma unroll
-    for (int i = 0; i < RPT; ++i) {
-      const int r = rb + 16 * i;
-      if (r < rows_valid) {
-        if (CONV) {
-          const int pix = p.upix[(long long)scene * p.rcap + row0 + r];
-          const int y = pix / p.W_;
-          info[i] = (y << 16) | (pix - y * p.W_);
-        } else {
-          info[i] = 1;
-        }
-      } else {
-        info[i] = -1;
-      }
-    }
+    const int j = tid & 7, rb = tid >> 3;
     const __nv_bfloat16* Ab = reinterpret_cast<const __nv_bfloat16*>(p.A);
-    const __nv_bfloat16* bev = reinterpret_cast<const __nv_bfloat16*>(p.bev);
-    const int cchunks = CONV ? (p.C / TC_BK) : 1;
-
-    auto signal = [&](int kc_done) {
-      fence_proxy_async();
-      mbar_arrive(full_bar(kc_done % NS));
-    };
-
+    const __nv_bfloat16* src[8];
+    uint32_t dst_off[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = rb + 16 * i;
+      src[i] = (r < rows_valid) ? (Ab + (long long)(row0 + r) * p.lda + j * 8) : nullptr;
+      dst_off[i] = r * 128 + ((j ^ (r & 7)) << 4);
+    }
     for (int kc = 0; kc < KC; ++kc) {
       const int s = kc % NS;
-      mbar_wait(empty_bar(s), ((kc / NS) & 1) ^ 1);
-      const uint32_t a_stage = sm_addr + s * Cfg::kStageBytes;
-      int dy = 0, dx = 0, c0 = 0;
-      if (CONV) {
-        const int tap = kc / cchunks;
-        c0 = (kc - tap * cchunks) * TC_BK;
-        dy = tap / 3 - 1;
-        dx = tap % 3 - 1;
-      }
+      mbar_wait(bars.empty(s), ((kc / NS) & 1) ^ 1);
+      const uint32_t a_stage = sm_addr + s * G_STAGE;
 #pragma unroll
-      for (int i = 0; i < RPT; ++i) {
-        const int r = rb + 16 * i;
-        const int t = r >> 7, rt = r & 127;
-        if (t < nt_active) {
-          const void* src = CONV ? (const void*)bev : (const void*)Ab;
-          uint32_t nbytes = 0;
-          if (info[i] >= 0) {
-            if (CONV) {
-              const int yy = (info[i] >> 16) + dy, xx = (info[i] & 0xffff) + dx;
-              if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W_) {
-                src = bev + (((long long)scene * p.H + yy) * p.W_ + xx) * p.C + c0 + j * 8;
-                nbytes = 16;
-              }
-            } else {
-              src = Ab + (long long)(row0 + r) * p.lda + kc * TC_BK + j * 8;
-              nbytes = 16;
-            }
-          }
-          const uint32_t dst = a_stage + t * TC_A_TILE + rt * 128 + ((j ^ (rt & 7)) << 4);
-          cp_async16(dst, src, nbytes);
-        }
+      for (int i = 0; i < 8; ++i) {
+        const bool ok = src[i] != nullptr;
+        cp_async16(a_stage + dst_off[i], ok ? (const void*)(src[i] + kc * TC_BK) : (const void*)Ab,
+                   ok ? 16u : 0u);
       }
-      cp_async_commit();
-      if (kc >= TC_LAG) {
-        cp_async_wait<TC_LAG>();
-        signal(kc - TC_LAG);
-      }
+      cp_async_mbar_arrive_noinc(bars.full(s));
     }
-    // drain the last TC_LAG groups in order
-    cp_async_wait<0>();
-    for (int kc = (KC > TC_LAG ? KC - TC_LAG : 0); kc < KC; ++kc) signal(kc);
 
-    // ======================= epilogue ==============================================
-    mbar_wait(accum_bar, 0);
+    // ---------------- epilogue: thread-per-row out of TMEM
+    const RowEpi& e = p.epi;
+    const int r = warp * 32 + lane;
+    const bool valid = r < rows_valid;
+    const long long m = row0 + r;
+    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+    mbar_wait(bars.accum(), 0);
     tc_fence_after();
-    float* Cs = reinterpret_cast<float*>(sm) + warp * 32 * TC_CS_LD;
-    for (int t = 0; t < nt_active; ++t) {
-#pragma unroll 1
-      for (int c0 = 0; c0 < D; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + t * D + c0, v);
-        tmem_ld_wait();
-        float* dst = Cs + lane * TC_CS_LD + c0;
+
+    float dsum = 0.f;
+    auto finalize = [&](int b, float (&v)[32]) {
+      const int c0 = n0 + b * 32;
+      if (e.film) {
+        float sc[32], sh[32];
+        ldg_row32(e.film + c0, sc);
+        ldg_row32(e.film + D + c0, sh);
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<float4*>(dst + q * 4) =
-              make_float4(__uint_as_float(v[q * 4 + 0]), __uint_as_float(v[q * 4 + 1]),
-                          __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
+        for (int i = 0; i < 32; ++i) v[i] = v[i] * (1.0f + sc[i]) + sh[i];
       }
-      __syncwarp();
-      for (int rr = 0; rr < 32; ++rr) {
-        const int r = t * TC_BM + warp * 32 + rr;
-        if (r < rows_valid) {
-          float v[8];
-          load8(Cs + rr * TC_CS_LD, lane, v);
-          row_epilogue(p.epi, v, out_row0 + r, n0, lane);
+      if (e.dot_w) {
+        float w[32];
+        ldg_row32(e.dot_w + c0, w);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) dsum = fmaf(v[i], w[i], dsum);
+      }
+      if (valid) {
+        if (e.out_f32) {
+          float4* o = reinterpret_cast<float4*>(e.out_f32 + m * e.ldo32 + c0);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+        if (e.out_bf16) {
+          uint4* o = reinterpret_cast<uint4*>(e.out_bf16 + m * e.ldo16 + c0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * q + 0], v[8 * q + 1]);
+            __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]);
+            __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * q + 6], v[8 * q + 7]);
+            uint4 u;
+            u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+            u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+            o[q] = u;
+          }
         }
       }
-      __syncwarp();
+    };
+    auto ld_block = [&](int b, float (&v)[32]) {
+      uint32_t u[32];
+      tmem_ld32(trow + b * 32, u);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(u[i]);
+    };
+    auto st_block = [&](int b, const float (&v)[32]) {
+      uint32_t u[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) u[i] = __float_as_uint(v[i]);
+      tmem_st32(trow + b * 32, u);
+    };
+
+    // pass 1: bias, ReLU, residual (+ statistics of LN1)
+    float s1 = 0.f, q1 = 0.f, c1 = 0.f;
+#pragma unroll 1
+    for (int b = 0; b < 8; ++b) {
+      float v[32];
+      ld_block(b, v);
+      if (e.bias) {
+        float t[32];
+        ldg_row32(e.bias + n0 + b * 32, t);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += t[i];
+      }
+      if (e.relu) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+      }
+      if (e.res && valid) {
+        float t[32];
+        ldg_row32(e.res + m * e.ldres + n0 + b * 32, t);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += t[i];
+      }
+      if (e.ln1_g) {
+        if (b == 0) c1 = v[0];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float d = v[i] - c1;
+          s1 += d;
+          q1 = fmaf(d, d, q1);
+        }
+        st_block(b, v);
+      } else {
+        finalize(b, v);
+      }
     }
+    if (e.ln1_g) {
+      tmem_st_wait();
+      const float ms = s1 * (1.0f / D);
+      const float mean = c1 + ms;
+      const float rstd = 1.0f / sqrtf(fmaxf(q1 * (1.0f / D) - ms * ms, 0.f) + LN_EPS);
+      float s2 = 0.f, q2 = 0.f, c2 = 0.f;
+#pragma unroll 1
+      for (int b = 0; b < 8; ++b) {
+        float v[32], g[32], bb[32];
+        ld_block(b, v);
+        ldg_row32(e.ln1_g + b * 32, g);
+        ldg_row32(e.ln1_b + b * 32, bb);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = (v[i] - mean) * rstd * g[i] + bb[i];
+        if (e.rowvec && valid) {
+          float t[32];
+          ldg_row32(e.rowvec + (m / e.rows_per_group) * D + b * 32, t);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += t[i];
+        }
+        if (e.ln2_g) {
+          if (b == 0) c2 = v[0];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float d = v[i] - c2;
+            s2 += d;
+            q2 = fmaf(d, d, q2);
+          }
+          st_block(b, v);
+        } else {
+          finalize(b, v);
+        }
+      }
+      if (e.ln2_g) {
+        tmem_st_wait();
+        const float ms2 = s2 * (1.0f / D);
+        const float mean2 = c2 + ms2;
+        const float rstd2 = 1.0f / sqrtf(fmaxf(q2 * (1.0f / D) - ms2 * ms2, 0.f) + LN_EPS);
+#pragma unroll 1
+        for (int b = 0; b < 8; ++b) {
+          float v[32], g[32], bb[32];
+          ld_block(b, v);
+          ldg_row32(e.ln2_g + b * 32, g);
+          ldg_row32(e.ln2_b + b * 32, bb);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = (v[i] - mean2) * rstd2 * g[i] + bb[i];
+          finalize(b, v);
+        }
+      }
+    }
+    if (e.dot_w && valid) e.dot_out[m] = dsum + e.dot_b[0];
   } else if (warp == 4) {
-    // ======================= TMA producer (weights) ================================
     if (lane == 0) {
       for (int kc = 0; kc < KC; ++kc) {
         const int s = kc % NS;
-        mbar_wait(empty_bar(s), ((kc / NS) & 1) ^ 1);
-        mbar_arrive_expect_tx(full_bar(s), TC_B_TILE);
-        tma_load_2d(sm_addr + s * Cfg::kStageBytes + NT * TC_A_TILE, &wmap, full_bar(s),
-                    kc * TC_BK, n0);
+        mbar_wait(bars.empty(s), ((kc / NS) & 1) ^ 1);
+        mbar_arrive_expect_tx(bars.full(s), TC_B_TILE);
+        tma_load_2d(sm_addr + s * G_STAGE + TC_A_TILE, &wmap, bars.full(s), kc * TC_BK, n0);
       }
     }
     __syncwarp();
   } else {
-    // ======================= MMA issuer ============================================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16_m128_n256();
       for (int kc = 0; kc < KC; ++kc) {
         const int s = kc % NS;
-        mbar_wait(full_bar(s), (kc / NS) & 1);
+        mbar_wait(bars.full(s), (kc / NS) & 1);
         tc_fence_after();
-        const uint32_t a_stage = sm_addr + s * Cfg::kStageBytes;
-        const uint32_t b_stage = a_stage + NT * TC_A_TILE;
-        for (int t = 0; t < nt_active; ++t) {
-#pragma unroll
-          for (int k4 = 0; k4 < TC_BK / 16; ++k4) {
-            const uint64_t adesc = umma_desc_sw128(a_stage + t * TC_A_TILE + k4 * 32);
-            const uint64_t bdesc = umma_desc_sw128(b_stage + k4 * 32);
-            umma_bf16(tmem_base + t * D, adesc, bdesc, idesc, (kc | k4) ? 1u : 0u);
-          }
-        }
-        umma_commit(empty_bar(s));
+        const uint32_t a_stage = sm_addr + s * G_STAGE;
+        mma_chunk<1>(a_stage, a_stage + TC_A_TILE, tmem_base, 1, kc == 0, idesc, bars.empty(s));
       }
-      umma_commit(accum_bar);
+      umma_commit(bars.accum());
     }
     __syncwarp();
   }
-
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  if (warp == 5) tmem_dealloc<D>(tmem_base);
+}
+
+// ===================================================================================
+// On-demand value_proj conv + bilinear/attention combine, one CTA per scene
+// (GridSampleCrossBEVAttention, modules/blocks.py:110-126):
+//   V[r, :] = ReLU(conv3x3(bev)[pixel r] + bias)   for the scene's unique sampled pixels r
+//   S[a, :] = sum_{p,corner} w[a,p,corner] * V[slot[a,p,corner], :]
+// Rows are processed 256 at a time ("pass": 2 row tiles sharing each weight tile).  A rows are
+// 3x3xC patches gathered from the NHWC bf16 map by cp.async (zero padded); V never leaves the
+// SM: the accumulators are drained from TMEM to a shared-memory staging area (aliasing the
+// idle pipeline buffers) half of N at a time and combined there.
+// ===================================================================================
+struct EntPair { int slot; float w; };
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_conv_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap) {
+  constexpr int NS = C_NS, NT = C_NT;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
+  uint8_t* sm = smem_raw + pad;
+  const uint32_t sm_addr = raw_addr + pad;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int scene = blockIdx.x;
+  const int nu = p.nuniq[scene];
+  const int A = p.n_anchor, n_ent = p.n_anchor * p.ent_per_anchor;
+  float* S32 = p.epi.out_f32;
+  __nv_bfloat16* S16 = p.epi.out_bf16;
+
+  if (nu == 0) {   // every sample point fell outside the grid: grid_sample returns zeros
+    for (int i = threadIdx.x; i < A * D; i += TC_THREADS) {
+      if (S32) S32[(size_t)scene * A * D + i] = 0.f;
+      if (S16) S16[(size_t)scene * A * D + i] = __float2bfloat16_rn(0.f);
+    }
+    return;
+  }
+  const int passes = (nu + NT * TC_BM - 1) / (NT * TC_BM);
+  const int ent_bytes = ((n_ent * 8 + 15) / 16) * 16;
+  EntPair* ent = reinterpret_cast<EntPair*>(sm + C_PIPE);
+  const TcBars bars{sm_addr + C_PIPE + ent_bytes, NS};
+  volatile uint32_t* tmem_slot =
+      reinterpret_cast<volatile uint32_t*>(sm + C_PIPE + ent_bytes + (2 * NS + 2) * 8);
+  constexpr int KC = 9 * (D / TC_BK);   // 36 k-chunks: (tap, 64-channel chunk)
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(bars.full(s), 128 + 1);
+      mbar_init(bars.empty(s), 1);
+    }
+    mbar_init(bars.accum(), 1);
+    mbar_init(bars.passgo(), 128);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc<NT * D>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  if (warp == 4 && lane == 0) tma_prefetch_desc(&wmap);
+  for (int i = threadIdx.x; i < n_ent; i += TC_THREADS) {
+    EntPair e;
+    e.slot = p.ent_slot[(size_t)scene * n_ent + i];
+    e.w = p.ent_w[(size_t)scene * n_ent + i];
+    ent[i] = e;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    const int tid = threadIdx.x;
+    const int j = tid & 7, rb = tid >> 3;
+    constexpr int RPT = NT * 8;
+    const __nv_bfloat16* bev = reinterpret_cast<const __nv_bfloat16*>(p.bev) +
+                               (size_t)scene * p.H * p.W_ * D;
+    const float* bias = p.epi.bias;
+    float* Vs = reinterpret_cast<float*>(sm);
+    int g = 0;
+    for (int pass = 0; pass < passes; ++pass) {
+      const int row_base = pass * NT * TC_BM;
+      const int rows_valid = min(NT * TC_BM, nu - row_base);
+      const int nt_active = (rows_valid + TC_BM - 1) / TC_BM;
+      // ---------------- A producers: gather 3x3xC patches
+      int yx[RPT];
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        const int r = rb + 16 * i;
+        if (r < rows_valid) {
+          const int pix = p.upix[(size_t)scene * p.rcap + row_base + r];
+          const int y = pix / p.W_;
+          yx[i] = (y << 16) | (pix - y * p.W_);
+        } else {
+          yx[i] = -1;
+        }
+      }
+      for (int kc = 0; kc < KC; ++kc, ++g) {
+        const int s = g % NS;
+        mbar_wait(bars.empty(s), ((g / NS) & 1) ^ 1);
+        const uint32_t a_stage = sm_addr + s * C_STAGE;
+        const int tap = kc >> 2, c0 = (kc & 3) * TC_BK + j * 8;
+        const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          const int r = rb + 16 * i;
+          const int t = r >> 7, rt = r & 127;
+          if (t < nt_active) {
+            const void* src = bev;
+            uint32_t nbytes = 0;
+            if (yx[i] >= 0) {
+              const int yy = (yx[i] >> 16) + dy, xx = (yx[i] & 0xffff) + dx;
+              if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W_) {
+                src = bev + (yy * p.W_ + xx) * D + c0;
+                nbytes = 16;
+              }
+            }
+            cp_async16(a_stage + t * TC_A_TILE + rt * 128 + ((j ^ (rt & 7)) << 4), src, nbytes);
+          }
+        }
+        cp_async_mbar_arrive_noinc(bars.full(s));
+      }
+      // ---------------- epilogue: drain TMEM -> smem, combine, half of N at a time
+      mbar_wait(bars.accum(), pass & 1);
+      tc_fence_after();
+      for (int half = 0; half < 2; ++half) {
+        for (int t = 0; t < nt_active; ++t) {
+          float* vrow = Vs + (size_t)(t * TC_BM + warp * 32 + lane) * C_VS_LD;
+#pragma unroll 1
+          for (int cb = 0; cb < 4; ++cb) {
+            uint32_t u[32];
+            const int col = half * 128 + cb * 32;
+            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + t * D + col, u);
+            tmem_ld_wait();
+            float bb[32];
+            ldg_row32(bias + col, bb);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float4 o;
+              o.x = fmaxf(__uint_as_float(u[4 * q + 0]) + bb[4 * q + 0], 0.f);
+              o.y = fmaxf(__uint_as_float(u[4 * q + 1]) + bb[4 * q + 1], 0.f);
+              o.z = fmaxf(__uint_as_float(u[4 * q + 2]) + bb[4 * q + 2], 0.f);
+              o.w = fmaxf(__uint_as_float(u[4 * q + 3]) + bb[4 * q + 3], 0.f);
+              *reinterpret_cast<float4*>(vrow + cb * 32 + 4 * q) = o;
+            }
+          }
+        }
+        named_bar_sync(1, 128);
+        for (int a = warp; a < A; a += 4) {
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          const EntPair* ea = ent + a * p.ent_per_anchor;
+#pragma unroll 4
+          for (int k = 0; k < p.ent_per_anchor; ++k) {
+            const EntPair e = ea[k];
+            const int rr = e.slot - row_base;
+            if (rr >= 0 && rr < rows_valid) {
+              const float4 v = *reinterpret_cast<const float4*>(Vs + (size_t)rr * C_VS_LD + lane * 4);
+              acc.x = fmaf(e.w, v.x, acc.x);
+              acc.y = fmaf(e.w, v.y, acc.y);
+              acc.z = fmaf(e.w, v.z, acc.z);
+              acc.w = fmaf(e.w, v.w, acc.w);
+            }
+          }
+          const size_t o = ((size_t)scene * A + a) * D + half * 128 + lane * 4;
+          if (pass > 0) {   // same thread wrote it in the previous pass: deterministic RMW
+            const float4 old = *reinterpret_cast<const float4*>(S32 + o);
+            acc.x += old.x; acc.y += old.y; acc.z += old.z; acc.w += old.w;
+          }
+          *reinterpret_cast<float4*>(S32 + o) = acc;
+          if (S16) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(acc.x, acc.y);
+            __nv_bfloat162 h1 = __floats2bfloat162_rn(acc.z, acc.w);
+            uint2 u2;
+            u2.x = *reinterpret_cast<uint32_t*>(&h0);
+            u2.y = *reinterpret_cast<uint32_t*>(&h1);
+            *reinterpret_cast<uint2*>(S16 + o) = u2;
+          }
+        }
+        named_bar_sync(1, 128);
+      }
+      // staging (generic proxy) is done: the weight TMA of the next pass may overwrite it
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(bars.passgo());
+    }
+  } else if (warp == 4) {
+    if (lane == 0) {
+      int g = 0;
+      for (int pass = 0; pass < passes; ++pass) {
+        if (pass > 0) mbar_wait(bars.passgo(), (pass - 1) & 1);
+        for (int kc = 0; kc < KC; ++kc, ++g) {
+          const int s = g % NS;
+          mbar_wait(bars.empty(s), ((g / NS) & 1) ^ 1);
+          mbar_arrive_expect_tx(bars.full(s), TC_B_TILE);
+          tma_load_2d(sm_addr + s * C_STAGE + NT * TC_A_TILE, &wmap, bars.full(s), kc * TC_BK, 0);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16_m128_n256();
+      int g = 0;
+      for (int pass = 0; pass < passes; ++pass) {
+        const int rows_valid = min(NT * TC_BM, nu - pass * NT * TC_BM);
+        const int nt_active = (rows_valid + TC_BM - 1) / TC_BM;
+        for (int kc = 0; kc < KC; ++kc, ++g) {
+          const int s = g % NS;
+          mbar_wait(bars.full(s), (g / NS) & 1);
+          tc_fence_after();
+          const uint32_t a_stage = sm_addr + s * C_STAGE;
+          mma_chunk<NT>(a_stage, a_stage + NT * TC_A_TILE, tmem_base, nt_active, kc == 0, idesc,
+                        bars.empty(s));
+        }
+        umma_commit(bars.accum());
+      }
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<NT * D>(tmem_base);
 }
 
 int tc_engine_init() {
   cudaError_t e;
-  e = cudaFuncSetAttribute(tc_gemm_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           TcCfg<1>::kSmemBytes);
+  e = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM);
   if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(tc_gemm_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           TcCfg<2>::kSmemBytes);
+  e = cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           227 * 1024);
   return (int)e;
 }
 
 void launch_tc_gemm(const GemmParams& p, const CUtensorMap& wmap, int n_total, cudaStream_t st) {
   dim3 grid((p.M + TC_BM - 1) / TC_BM, n_total / D);
-  tc_gemm_kernel<1, false><<<grid, TC_THREADS, TcCfg<1>::kSmemBytes, st>>>(p, wmap);
+  tc_gemm_kernel<<<grid, TC_THREADS, G_SMEM, st>>>(p, wmap);
+}
+
+int tc_conv_smem_bytes(int A, int ent_per_anchor) {
+  return C_PIPE + ((A * ent_per_anchor * 8 + 15) / 16) * 16 + TC_BAR_BYTES + 1024;
 }
 
 void launch_tc_conv(const GemmParams& p, const CUtensorMap& wmap, int B, cudaStream_t st) {
-  dim3 grid((p.rcap + 2 * TC_BM - 1) / (2 * TC_BM), B);
-  tc_gemm_kernel<2, true><<<grid, TC_THREADS, TcCfg<2>::kSmemBytes, st>>>(p, wmap);
+  tc_conv_kernel<<<B, TC_THREADS, tc_conv_smem_bytes(p.n_anchor, p.ent_per_anchor), st>>>(p, wmap);
 }
 
 }  // namespace ddh
