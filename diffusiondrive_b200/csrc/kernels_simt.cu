@@ -56,9 +56,9 @@ __global__ void __launch_bounds__(SG_THREADS, 2) simt_gemm_kernel(const GemmPara
   int a_y = 0, a_x = 0;
   bool a_valid = a_row < rows_valid;
   if (CONV && a_valid) {
-    const int pix = s_pix[a_row];
-    a_y = pix / p.W_;
-    a_x = pix - a_y * p.W_;
+    const int yx = s_pix[a_row];   // (y << 16) | x
+    a_y = yx >> 16;
+    a_x = yx & 0xffff;
   }
   const float* Wt = reinterpret_cast<const float*>(p.W) + n0;
 
@@ -374,8 +374,8 @@ void launch_embed(const float* img, float* pts, float* emb32, __nv_bfloat16* emb
 //   aw      = softmax_p(Linear(D->P)(q))                                    (:110-112)
 //   grid    = (y / lidar_max_x, x / lidar_max_y)                            (:101-108)
 //   ix, iy  = ((g+1)*size-1)/2, 4 bilinear corners, zero padding            (:117-122)
-// Output: the sorted list of UNIQUE in-bounds corner pixels of the scene (the only pixels at
-// which value_proj has to be evaluated), and per (anchor, pose, corner) the slot of its pixel
+// Output: the sorted list of UNIQUE in-bounds corner pixels of the scene, packed (y << 16) | x
+// (the only pixels at which value_proj has to be evaluated), and per (anchor, pose, corner) the slot of its pixel
 // in that list with the combined weight bilinear * aw.
 // ===================================================================================
 struct Corners {
@@ -484,7 +484,8 @@ __global__ void __launch_bounds__(256) plan_kernel(const float* __restrict__ q0,
   if (tid == 255) total_s = base + cnt;
   for (int i = beg; i < end; ++i) {
     if (table[i]) {
-      upix[(size_t)scene * rcap + base] = i;
+      const int yy = i / W;
+      upix[(size_t)scene * rcap + base] = (yy << 16) | (i - yy * W);   // packed (y, x)
       table[i] = (unsigned short)(base + 1);
       ++base;
     }

@@ -534,39 +534,38 @@ tc_conv_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap) {
       const int rows_valid = min(NT * TC_BM, nu - row_base);
       const int nt_active = (rows_valid + TC_BM - 1) / TC_BM;
       // ---------------- A producers: gather 3x3xC patches
-      int yx[RPT];
+      // Loop-invariant per thread: the swizzled destination (row r = rb + 16 i always has
+      // r & 7 == rb & 7, and consecutive i are 2048 B apart), the element offset of the row's
+      // centre pixel and a 9-bit mask of the taps that fall inside the map.
+      int rowoff[RPT];
+      uint32_t vmask[RPT];
 #pragma unroll
       for (int i = 0; i < RPT; ++i) {
         const int r = rb + 16 * i;
+        rowoff[i] = 0;
+        vmask[i] = 0;
         if (r < rows_valid) {
-          const int pix = p.upix[(size_t)scene * p.rcap + row_base + r];
-          const int y = pix / p.W_;
-          yx[i] = (y << 16) | (pix - y * p.W_);
-        } else {
-          yx[i] = -1;
+          const int yx = p.upix[(size_t)scene * p.rcap + row_base + r];   // (y << 16) | x
+          const int y = yx >> 16, x = yx & 0xffff;
+          rowoff[i] = (y * p.W_ + x) * D + j * 8;
+          const uint32_t xm = (x > 0 ? 1u : 0u) | 2u | (x + 1 < p.W_ ? 4u : 0u);
+          vmask[i] = (y > 0 ? xm : 0u) | (xm << 3) | (y + 1 < p.H ? (xm << 6) : 0u);
         }
       }
+      const uint32_t dst_base = rb * 128 + ((j ^ (rb & 7)) << 4);
       for (int kc = 0; kc < KC; ++kc, ++g) {
         const int s = g % NS;
         mbar_wait(bars.empty(s), ((g / NS) & 1) ^ 1);
-        const uint32_t a_stage = sm_addr + s * C_STAGE;
-        const int tap = kc >> 2, c0 = (kc & 3) * TC_BK + j * 8;
+        const uint32_t a_dst = sm_addr + s * C_STAGE + dst_base;
+        const int tap = kc >> 2;
         const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+        const int tapoff = (dy * p.W_ + dx) * D + (kc & 3) * TC_BK;
 #pragma unroll
         for (int i = 0; i < RPT; ++i) {
-          const int r = rb + 16 * i;
-          const int t = r >> 7, rt = r & 127;
-          if (t < nt_active) {
-            const void* src = bev;
-            uint32_t nbytes = 0;
-            if (yx[i] >= 0) {
-              const int yy = (yx[i] >> 16) + dy, xx = (yx[i] & 0xffff) + dx;
-              if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W_) {
-                src = bev + (yy * p.W_ + xx) * D + c0;
-                nbytes = 16;
-              }
-            }
-            cp_async16(a_stage + t * TC_A_TILE + rt * 128 + ((j ^ (rt & 7)) << 4), src, nbytes);
+          if (i < 8 * nt_active) {
+            const bool ok = (vmask[i] >> tap) & 1u;
+            const int off = ok ? rowoff[i] + tapoff : 0;
+            cp_async16(a_dst + i * 2048, bev + off, ok ? 16u : 0u);
           }
         }
         cp_async_mbar_arrive_noinc(bars.full(s));
