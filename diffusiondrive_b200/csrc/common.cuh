@@ -177,6 +177,7 @@ struct GemmParams {
   const float* ent_w = nullptr;    // [B][A*ent_per_anchor] bilinear * attention weight
   int n_anchor = 0;
   int ent_per_anchor = 0;          // P * 4
+  long long* dbg = nullptr;        // optional timeline (DDH_TIMELINE builds): CTA 0 clock64 stamps
 };
 
 }  // namespace ddh

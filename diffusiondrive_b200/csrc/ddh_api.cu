@@ -116,6 +116,12 @@ struct ddh_handle {
   std::vector<std::pair<int, int>> ev_spans;   // (stage id, index of the begin event)
   int ev_used = 0;
   int* conv_rows = nullptr;                    // [S*L] unique value_proj rows per conv launch
+  long long* dbg = nullptr;                    // timeline stamps (DDH_TIMELINE builds)
+  // scene-chunk concurrency (ddh_set_concurrency)
+  int chunks = 4;
+  int min_chunk_scenes = 512;
+  cudaStream_t aux_stream = nullptr;
+  std::vector<cudaEvent_t> sync_events;
 };
 
 namespace {
@@ -314,6 +320,7 @@ int ensure_ws(ddh_handle* h, int B) {
   WS(h->upix, (size_t)B * h->rcap);
   WS(h->nuniq, B);
   WS(h->conv_rows, s.num_layers * s.num_steps);
+  WS(h->dbg, 4 * 40 * 2);
   WS(h->ent_slot, M * s.num_poses * 4);
   WS(h->ent_w, M * s.num_poses * 4);
   if (!bf) WS(h->V, (size_t)B * h->rcap * D);
@@ -351,6 +358,7 @@ void register_taps(ddh_handle* h, int B) {
   t["egov"] = {h->egov, (size_t)s.num_layers * B * D * 4};
   t["upix"] = {h->upix, (size_t)B * h->rcap * 4};
   t["nuniq"] = {h->nuniq, (size_t)B * 4};
+  t["dbg"] = {h->dbg, (size_t)4 * 40 * 2 * 8};
   t["conv_rows"] = {h->conv_rows, (size_t)s.num_layers * s.num_steps * 4};
   t["ent_slot"] = {h->ent_slot, M * s.num_poses * 4 * 4};
   t["ent_w"] = {h->ent_w, M * s.num_poses * 4 * 4};
@@ -427,6 +435,8 @@ void ddh_destroy(ddh_handle* h) {
   free_all(h->owned_ws);
   free_all(h->owned_host);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->sync_events) cudaEventDestroy(e);
+  if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
   delete h;
 }
 
@@ -560,6 +570,252 @@ int ddh_pack_weights(ddh_handle* h, const ddh_weight_ptrs* w, int precision, voi
   return DDH_OK;
 }
 
+}  // extern "C" (reopened below)
+
+namespace {
+
+// Per-chunk view of the workspace and of the caller's buffers: every pointer advanced to
+// scene `s0`.  Layer-major buffers (kv32, egov) keep the full-batch layer stride `Btot`.
+struct View {
+  float *img, *pts, *emb32, *e1_32, *q0_32, *kv32, *egov, *ent_w, *V, *s32, *x1_32, *qh32, *o32,
+      *x2_32, *h32, *x3_32, *c1_32, *r1_32, *r2_32, *modes_buf, *scores_buf;
+  __nv_bfloat16 *emb16, *e1_16, *q0_16, *agents16, *ego16, *s16, *x1_16, *o16, *x2_16, *h16,
+      *x3_16, *c1_16, *r1_16;
+  int *upix, *nuniq, *ent_slot;
+  void* bev_nhwc;
+};
+template <typename T>
+T* adv(T* p, size_t n) { return p ? p + n : nullptr; }
+
+View make_view(const ddh_handle* h, int s0) {
+  const ddh_shape& s = h->shp;
+  const size_t A = s.num_anchors, P = s.num_poses, Na = s.num_agents, F = s.d_ffn, z = s0;
+  const size_t rows = z * A;
+  View v;
+  v.img = adv(h->img, rows * P * 2); v.pts = adv(h->pts, rows * P * 2);
+  v.emb32 = adv(h->emb32, rows * 64 * P); v.emb16 = adv(h->emb16, rows * 64 * P);
+  v.e1_32 = adv(h->e1_32, rows * D); v.e1_16 = adv(h->e1_16, rows * D);
+  v.q0_32 = adv(h->q0_32, rows * D); v.q0_16 = adv(h->q0_16, rows * D);
+  v.kv32 = adv(h->kv32, z * Na * 2 * D); v.egov = adv(h->egov, z * D);
+  v.agents16 = adv(h->agents16, z * Na * D); v.ego16 = adv(h->ego16, z * D);
+  v.upix = adv(h->upix, z * h->rcap); v.nuniq = adv(h->nuniq, z);
+  v.ent_slot = adv(h->ent_slot, rows * P * 4); v.ent_w = adv(h->ent_w, rows * P * 4);
+  v.V = adv(h->V, z * h->rcap * D);
+  v.s32 = adv(h->s32, rows * D); v.s16 = adv(h->s16, rows * D);
+  v.x1_32 = adv(h->x1_32, rows * D); v.x1_16 = adv(h->x1_16, rows * D);
+  v.qh32 = adv(h->qh32, rows * D);
+  v.o32 = adv(h->o32, rows * D); v.o16 = adv(h->o16, rows * D);
+  v.x2_32 = adv(h->x2_32, rows * D); v.x2_16 = adv(h->x2_16, rows * D);
+  v.h32 = adv(h->h32, rows * F); v.h16 = adv(h->h16, rows * F);
+  v.x3_32 = adv(h->x3_32, rows * D); v.x3_16 = adv(h->x3_16, rows * D);
+  v.c1_32 = adv(h->c1_32, rows * D); v.c1_16 = adv(h->c1_16, rows * D);
+  v.r1_32 = adv(h->r1_32, rows * D); v.r1_16 = adv(h->r1_16, rows * D);
+  v.r2_32 = adv(h->r2_32, rows * D);
+  v.modes_buf = adv(h->modes_buf, rows * P * 3); v.scores_buf = adv(h->scores_buf, rows);
+  const size_t bev_elt = h->precision == DDH_PREC_BF16 ? 2 : 4;
+  v.bev_nhwc = h->bev_nhwc ? (unsigned char*)h->bev_nhwc + z * s.bev_h * s.bev_w * s.bev_channels * bev_elt : nullptr;
+  return v;
+}
+
+// forward_test (:578-641) for the `B` scenes starting at scene `s0` of a call of `Btot` scenes,
+// all launches on `st`.  `layout_done` (optional) is recorded right after the BEV layout pass.
+int forward_range(ddh_handle* h, const float* ego, const float* agents, const void* bev,
+                  int bev_dtype, int bev_layout, const float* noise, float* out_traj,
+                  float* out_modes, float* out_scores, int64_t* out_mode_idx, int s0, int B,
+                  int Btot, cudaStream_t st, cudaEvent_t layout_done) {
+  const ddh_shape& s = h->shp;
+  const bool bf = h->precision == DDH_PREC_BF16;
+  const int A = s.num_anchors, P = s.num_poses, Na = s.num_agents, L = s.num_layers, S = s.num_steps;
+  const int M = B * A, F = s.d_ffn, HW = s.bev_h * s.bev_w;
+  const int want_dtype = bf ? DDH_BF16 : DDH_F32;
+  const View v = make_view(h, s0);
+  {
+    const size_t z = s0, bev_in_elt = bev_dtype == DDH_BF16 ? 2 : 4;
+    ego += z * D; agents += z * Na * D; noise += z * A * P * 2;
+    bev = (const unsigned char*)bev + z * HW * s.bev_channels * bev_in_elt;
+    out_traj = adv(out_traj, z * P * 3); out_modes = adv(out_modes, z * A * P * 3);
+    out_scores = adv(out_scores, z * A); out_mode_idx = adv(out_mode_idx, z);
+  }
+  // ---- BEV map -> NHWC in the engine's operand type
+  const void* bevn = bev;
+  { ProfSpan ps(h, ST_BEV, st);
+  if (bev_layout == DDH_NCHW) {
+    launch_bev_to_nhwc(bev, bev_dtype, v.bev_nhwc, want_dtype, B, s.bev_channels, HW, st);
+    h->launches++;
+    bevn = v.bev_nhwc;
+  } else if (bev_dtype != want_dtype) {
+    const size_t n = (size_t)B * HW * s.bev_channels;
+    if (bf) launch_cast_f32_bf16(reinterpret_cast<const float*>(bev),
+                                 reinterpret_cast<__nv_bfloat16*>(v.bev_nhwc), n, st);
+    else launch_cast_bf16_f32(reinterpret_cast<const __nv_bfloat16*>(bev),
+                              reinterpret_cast<float*>(v.bev_nhwc), n, st);
+    h->launches++;
+    bevn = v.bev_nhwc;
+  }
+  }
+
+  if (layout_done) CU_TRY(h, cudaEventRecord(layout_done, st));
+
+  // ---- hoisted per (scene, layer): agent K|V and the collapsed ego vector
+  { ProfSpan ps(h, ST_HOIST, st);
+  if (bf) {
+    launch_cast_f32_bf16(agents, v.agents16, (size_t)B * Na * D, st);
+    launch_cast_f32_bf16(ego, v.ego16, (size_t)B * D, st);
+    h->launches += 2;
+  }
+  for (int l = 0; l < L; ++l) {
+    RowEpi e;
+    e.out_f32 = v.kv32 + (size_t)l * Btot * Na * 2 * D;
+    e.ldo32 = 2 * D;
+    run_gemm(h, h->layers[l].kv, agents, v.agents16, D, B * Na, e, st);
+    RowEpi e2;
+    e2.out_f32 = v.egov + (size_t)l * Btot * D;
+    e2.ldo32 = D;
+    run_gemm(h, h->layers[l].ego, ego, v.ego16, D, B, e2, st);
+  }
+  }
+
+  // ---- truncated noising of the anchors (:591-597)
+  const float ac_tr = h->ac[s.trunc_timestep];
+  { ProfSpan ps(h, ST_INIT, st);
+  launch_init_img(h->anchors, noise, v.img, B, A * P, sqrtf(ac_tr), sqrtf(1.0f - ac_tr), st);
+  h->launches++; }
+
+  float* modes = out_modes ? out_modes : v.modes_buf;
+  float* scores = out_scores ? out_scores : v.scores_buf;
+  OdoConsts oc{s.lidar_max_x, s.lidar_max_y};
+
+  for (int si = 0; si < S; ++si) {
+    // clamp, denorm, sine embedding, plan_anchor_encoder (:601-609)
+    {
+      ProfSpan ps(h, ST_EMBED, st);
+      launch_embed(v.img, v.pts, v.emb32, v.emb16, M, P, h->dim_t, st);
+      h->launches++;
+      RowEpi e;
+      e.relu = 1; e.ln1_g = h->enc_ln_g; e.ln1_b = h->enc_ln_b;
+      e.out_f32 = v.e1_32; e.ldo32 = D; e.out_bf16 = v.e1_16; e.ldo16 = D;
+      run_gemm(h, h->enc0, v.emb32, v.emb16, 64 * P, M, e, st);
+      RowEpi e3;
+      e3.out_f32 = v.q0_32; e3.ldo32 = D; e3.out_bf16 = v.q0_16; e3.ldo16 = D;
+      run_gemm(h, h->enc3, v.e1_32, v.e1_16, D, M, e3, st);
+    }
+    for (int l = 0; l < L; ++l) {
+      const PackedLayer& pl = h->layers[l];
+      const bool last_layer = (l == L - 1), last_step = (si == S - 1);
+      // -- cross_bev_attention (modules/blocks.py:88-129)
+      { ProfSpan ps(h, ST_PLAN, st);
+      launch_plan(v.q0_32, pl.attw_w, pl.attw_b, v.pts, v.upix, v.nuniq, v.ent_slot,
+                  v.ent_w, h->conv_rows + si * L + l, B, A, P, s.bev_h, s.bev_w, h->rcap, oc, st); }
+      {
+        ProfSpan ps(h, ST_CONV, st);
+        GemmParams gp;
+        gp.K = pl.conv.K;
+        gp.bev = bevn; gp.upix = v.upix; gp.nuniq = v.nuniq; gp.rcap = h->rcap;
+        gp.H = s.bev_h; gp.W_ = s.bev_w; gp.C = s.bev_channels;
+        gp.epi.bias = pl.conv.bias; gp.epi.relu = 1;
+        if (bf) {   // combine fused into the conv epilogue: V never leaves the SM
+          gp.dbg = h->dbg;
+          gp.ent_slot = v.ent_slot; gp.ent_w = v.ent_w; gp.n_anchor = A; gp.ent_per_anchor = P * 4;
+          gp.epi.out_f32 = v.s32; gp.epi.ldo32 = D; gp.epi.out_bf16 = v.s16; gp.epi.ldo16 = D;
+          launch_tc_conv(gp, pl.conv.map, B, st);
+          h->launches += 2;
+        } else {
+          gp.epi.out_f32 = v.V; gp.epi.ldo32 = D;
+          gp.W = pl.conv.wt32; gp.ldw = D;
+          launch_simt_conv(gp, B, st);
+        }
+      }
+      if (!bf) {
+        ProfSpan ps(h, ST_COMBINE, st);
+        launch_combine(v.V, v.ent_slot, v.ent_w, v.s32, v.s16, B, A, P, h->rcap, st);
+        h->launches += 3;
+      }
+      {
+        ProfSpan ps(h, ST_GEMM, st);
+        RowEpi e;   // output_proj + residual (:127-129)
+        e.res = v.q0_32; e.ldres = D;
+        e.out_f32 = v.x1_32; e.ldo32 = D; e.out_bf16 = v.x1_16; e.ldo16 = D;
+        run_gemm(h, pl.bev_out, v.s32, v.s16, D, M, e, st);
+      }
+      // -- cross_agent_attention + norm1, cross_ego_attention + norm2 (:355-365)
+      {
+        ProfSpan ps(h, ST_GEMM, st);
+        RowEpi e;
+        e.out_f32 = v.qh32; e.ldo32 = D;
+        run_gemm(h, pl.q, v.x1_32, v.x1_16, D, M, e, st);
+      }
+      { ProfSpan ps(h, ST_ATTN, st);
+      launch_attn_core(v.qh32, v.kv32 + (size_t)l * Btot * Na * 2 * D, v.o32, v.o16, B, A, Na,
+                       s.num_heads, st); }
+      h->launches++;
+      ProfSpan* chain = new ProfSpan(h, ST_GEMM, st);
+      {
+        RowEpi e;
+        e.res = v.x1_32; e.ldres = D;
+        e.ln1_g = pl.norm1_g; e.ln1_b = pl.norm1_b;
+        e.rowvec = v.egov + (size_t)l * Btot * D; e.rows_per_group = A;
+        e.ln2_g = pl.norm2_g; e.ln2_b = pl.norm2_b;
+        e.out_f32 = v.x2_32; e.ldo32 = D; e.out_bf16 = v.x2_16; e.ldo16 = D;
+        run_gemm(h, pl.attn_out, v.o32, v.o16, D, M, e, st);
+      }
+      // -- FFN (no residual) + norm3 + time FiLM (:368-373)
+      {
+        RowEpi e;
+        e.relu = 1;
+        e.out_f32 = v.h32; e.ldo32 = F; e.out_bf16 = v.h16; e.ldo16 = F;
+        run_gemm(h, pl.ffn0, v.x2_32, v.x2_16, D, M, e, st);
+        RowEpi e2;
+        e2.ln1_g = pl.norm3_g; e2.ln1_b = pl.norm3_b;
+        e2.film = h->film + ((size_t)si * L + l) * 2 * D;
+        e2.out_f32 = v.x3_32; e2.ldo32 = D; e2.out_bf16 = v.x3_16; e2.ldo16 = D;
+        run_gemm(h, pl.ffn2, v.h32, v.h16, F, M, e2, st);
+      }
+      // -- task_decoder (:244-256, 376-380); cls only where it is read (:631)
+      if (last_layer && last_step) {
+        RowEpi e;
+        e.relu = 1; e.ln1_g = pl.cls_ln2_g; e.ln1_b = pl.cls_ln2_b;
+        e.out_f32 = v.c1_32; e.ldo32 = D; e.out_bf16 = v.c1_16; e.ldo16 = D;
+        run_gemm(h, pl.cls0, v.x3_32, v.x3_16, D, M, e, st);
+        RowEpi e2;
+        e2.relu = 1; e2.ln1_g = pl.cls_ln5_g; e2.ln1_b = pl.cls_ln5_b;
+        e2.dot_w = pl.cls6_w; e2.dot_b = pl.cls6_b; e2.dot_out = scores;
+        run_gemm(h, pl.cls3, v.c1_32, v.c1_16, D, M, e2, st);
+      }
+      {
+        RowEpi e;
+        e.relu = 1;
+        e.out_f32 = v.r1_32; e.ldo32 = D; e.out_bf16 = v.r1_16; e.ldo16 = D;
+        run_gemm(h, pl.reg0, v.x3_32, v.x3_16, D, M, e, st);
+        RowEpi e2;
+        e2.relu = 1;
+        e2.out_f32 = v.r2_32; e2.ldo32 = D;
+        run_gemm(h, pl.reg2, v.r1_32, v.r1_16, D, M, e2, st);
+      }
+      delete chain;
+      DdimCoef dc{0.f, 1.f, 1.f, 0.f};
+      const int do_ddim = (last_layer && !last_step) ? 1 : 0;
+      if (do_ddim) {
+        const int t = h->roll[si], prev = t - 1;   // set_timesteps(1000) => step ratio 1 (:584)
+        const float ac_t = h->ac[t], ac_p = prev >= 0 ? h->ac[prev] : 1.0f;
+        dc.sqrt_ac_t = sqrtf(ac_t); dc.sqrt_1m_ac_t = sqrtf(1.0f - ac_t);
+        dc.sqrt_ac_prev = sqrtf(ac_p); dc.sqrt_1m_ac_prev = sqrtf(1.0f - ac_p);
+      }
+      { ProfSpan ps(h, ST_REG, st);
+      launch_reg_finish(v.r2_32, pl.reg4_w, pl.reg4_b, v.pts, v.img, modes, M, P, do_ddim, dc, st); }
+      h->launches++;
+    }
+  }
+  { ProfSpan ps(h, ST_SELECT, st);
+  launch_select(scores, modes, out_traj, reinterpret_cast<long long*>(out_mode_idx), B, A, P, st); }
+  h->launches++;
+  CU_TRY(h, cudaGetLastError());
+  return DDH_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
 int ddh_forward(ddh_handle* h, const float* ego, const float* agents, const void* bev,
                 int bev_dtype, int bev_layout, const float* noise, float* out_traj,
                 float* out_modes, float* out_scores, int64_t* out_mode_idx, int B, void* stream) {
@@ -579,183 +835,45 @@ int ddh_forward(ddh_handle* h, const float* ego, const float* agents, const void
   h->launches = 0;
   register_taps(h, B);
   const ddh_shape& s = h->shp;
-  const bool bf = h->precision == DDH_PREC_BF16;
-  const int A = s.num_anchors, P = s.num_poses, Na = s.num_agents, L = s.num_layers, S = s.num_steps;
-  const int M = B * A, F = s.d_ffn, HW = s.bev_h * s.bev_w;
-  const int want_dtype = bf ? DDH_BF16 : DDH_F32;
-
   h->ev_used = 0;
   h->ev_spans.clear();
-  CU_TRY(h, cudaMemsetAsync(h->conv_rows, 0, (size_t)L * S * 4, st));
-  // ---- BEV map -> NHWC in the engine's operand type
-  const void* bevn = bev;
-  { ProfSpan ps(h, ST_BEV, st);
-  if (bev_layout == DDH_NCHW) {
-    launch_bev_to_nhwc(bev, bev_dtype, h->bev_nhwc, want_dtype, B, s.bev_channels, HW, st);
-    h->launches++;
-    bevn = h->bev_nhwc;
-  } else if (bev_dtype != want_dtype) {
-    const size_t n = (size_t)B * HW * s.bev_channels;
-    if (bf) launch_cast_f32_bf16(reinterpret_cast<const float*>(bev),
-                                 reinterpret_cast<__nv_bfloat16*>(h->bev_nhwc), n, st);
-    else launch_cast_bf16_f32(reinterpret_cast<const __nv_bfloat16*>(bev),
-                              reinterpret_cast<float*>(h->bev_nhwc), n, st);
-    h->launches++;
-    bevn = h->bev_nhwc;
-  }
-  }
+  CU_TRY(h, cudaMemsetAsync(h->conv_rows, 0, (size_t)s.num_layers * s.num_steps * 4, st));
 
-  // ---- hoisted per (scene, layer): agent K|V and the collapsed ego vector
-  { ProfSpan ps(h, ST_HOIST, st);
-  if (bf) {
-    launch_cast_f32_bf16(agents, h->agents16, (size_t)B * Na * D, st);
-    launch_cast_f32_bf16(ego, h->ego16, (size_t)B * D, st);
-    h->launches += 2;
-  }
-  for (int l = 0; l < L; ++l) {
-    RowEpi e;
-    e.out_f32 = h->kv32 + (size_t)l * B * Na * 2 * D;
-    e.ldo32 = 2 * D;
-    run_gemm(h, h->layers[l].kv, agents, h->agents16, D, B * Na, e, st);
-    RowEpi e2;
-    e2.out_f32 = h->egov + (size_t)l * B * D;
-    e2.ldo32 = D;
-    run_gemm(h, h->layers[l].ego, ego, h->ego16, D, B, e2, st);
-  }
-  }
-
-  // ---- truncated noising of the anchors (:591-597)
-  const float ac_tr = h->ac[s.trunc_timestep];
-  { ProfSpan ps(h, ST_INIT, st);
-  launch_init_img(h->anchors, noise, h->img, B, A * P, sqrtf(ac_tr), sqrtf(1.0f - ac_tr), st);
-  h->launches++; }
-
-  float* modes = out_modes ? out_modes : h->modes_buf;
-  float* scores = out_scores ? out_scores : h->scores_buf;
-  OdoConsts oc{s.lidar_max_x, s.lidar_max_y};
-
-  for (int si = 0; si < S; ++si) {
-    // clamp, denorm, sine embedding, plan_anchor_encoder (:601-609)
-    {
-      ProfSpan ps(h, ST_EMBED, st);
-      launch_embed(h->img, h->pts, h->emb32, h->emb16, M, P, h->dim_t, st);
-      h->launches++;
-      RowEpi e;
-      e.relu = 1; e.ln1_g = h->enc_ln_g; e.ln1_b = h->enc_ln_b;
-      e.out_f32 = h->e1_32; e.ldo32 = D; e.out_bf16 = h->e1_16; e.ldo16 = D;
-      run_gemm(h, h->enc0, h->emb32, h->emb16, 64 * P, M, e, st);
-      RowEpi e3;
-      e3.out_f32 = h->q0_32; e3.ldo32 = D; e3.out_bf16 = h->q0_16; e3.ldo16 = D;
-      run_gemm(h, h->enc3, h->e1_32, h->e1_16, D, M, e3, st);
+  // Scene chunks on two streams: scenes are independent, so chunk c+1's HBM-bound layout pass
+  // runs under chunk c's tensor-bound conv/GEMMs.  Chunk c starts once layout(c-1) is done.
+  int nchunk = 1;
+  if (!h->profiling && h->chunks > 1 && B >= h->chunks * h->min_chunk_scenes) nchunk = h->chunks;
+  if (nchunk == 1) {
+    rc = forward_range(h, ego, agents, bev, bev_dtype, bev_layout, noise, out_traj, out_modes,
+                       out_scores, out_mode_idx, 0, B, B, st, nullptr);
+    if (rc) return rc;
+  } else {
+    if (!h->aux_stream) CU_TRY(h, cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+    while ((int)h->sync_events.size() < nchunk + 2) {
+      cudaEvent_t e;
+      CU_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      h->sync_events.push_back(e);
     }
-    for (int l = 0; l < L; ++l) {
-      const PackedLayer& pl = h->layers[l];
-      const bool last_layer = (l == L - 1), last_step = (si == S - 1);
-      // -- cross_bev_attention (modules/blocks.py:88-129)
-      { ProfSpan ps(h, ST_PLAN, st);
-      launch_plan(h->q0_32, pl.attw_w, pl.attw_b, h->pts, h->upix, h->nuniq, h->ent_slot,
-                  h->ent_w, h->conv_rows + si * L + l, B, A, P, s.bev_h, s.bev_w, h->rcap, oc, st); }
-      {
-        ProfSpan ps(h, ST_CONV, st);
-        GemmParams gp;
-        gp.K = pl.conv.K;
-        gp.bev = bevn; gp.upix = h->upix; gp.nuniq = h->nuniq; gp.rcap = h->rcap;
-        gp.H = s.bev_h; gp.W_ = s.bev_w; gp.C = s.bev_channels;
-        gp.epi.bias = pl.conv.bias; gp.epi.relu = 1;
-        if (bf) {   // combine fused into the conv epilogue: V never leaves the SM
-          gp.ent_slot = h->ent_slot; gp.ent_w = h->ent_w; gp.n_anchor = A; gp.ent_per_anchor = P * 4;
-          gp.epi.out_f32 = h->s32; gp.epi.ldo32 = D; gp.epi.out_bf16 = h->s16; gp.epi.ldo16 = D;
-          launch_tc_conv(gp, pl.conv.map, B, st);
-          h->launches += 2;
-        } else {
-          gp.epi.out_f32 = h->V; gp.epi.ldo32 = D;
-          gp.W = pl.conv.wt32; gp.ldw = D;
-          launch_simt_conv(gp, B, st);
-        }
-      }
-      if (!bf) {
-        ProfSpan ps(h, ST_COMBINE, st);
-        launch_combine(h->V, h->ent_slot, h->ent_w, h->s32, h->s16, B, A, P, h->rcap, st);
-        h->launches += 3;
-      }
-      {
-        ProfSpan ps(h, ST_GEMM, st);
-        RowEpi e;   // output_proj + residual (:127-129)
-        e.res = h->q0_32; e.ldres = D;
-        e.out_f32 = h->x1_32; e.ldo32 = D; e.out_bf16 = h->x1_16; e.ldo16 = D;
-        run_gemm(h, pl.bev_out, h->s32, h->s16, D, M, e, st);
-      }
-      // -- cross_agent_attention + norm1, cross_ego_attention + norm2 (:355-365)
-      {
-        ProfSpan ps(h, ST_GEMM, st);
-        RowEpi e;
-        e.out_f32 = h->qh32; e.ldo32 = D;
-        run_gemm(h, pl.q, h->x1_32, h->x1_16, D, M, e, st);
-      }
-      { ProfSpan ps(h, ST_ATTN, st);
-      launch_attn_core(h->qh32, h->kv32 + (size_t)l * B * Na * 2 * D, h->o32, h->o16, B, A, Na,
-                       s.num_heads, st); }
-      h->launches++;
-      ProfSpan* chain = new ProfSpan(h, ST_GEMM, st);
-      {
-        RowEpi e;
-        e.res = h->x1_32; e.ldres = D;
-        e.ln1_g = pl.norm1_g; e.ln1_b = pl.norm1_b;
-        e.rowvec = h->egov + (size_t)l * B * D; e.rows_per_group = A;
-        e.ln2_g = pl.norm2_g; e.ln2_b = pl.norm2_b;
-        e.out_f32 = h->x2_32; e.ldo32 = D; e.out_bf16 = h->x2_16; e.ldo16 = D;
-        run_gemm(h, pl.attn_out, h->o32, h->o16, D, M, e, st);
-      }
-      // -- FFN (no residual) + norm3 + time FiLM (:368-373)
-      {
-        RowEpi e;
-        e.relu = 1;
-        e.out_f32 = h->h32; e.ldo32 = F; e.out_bf16 = h->h16; e.ldo16 = F;
-        run_gemm(h, pl.ffn0, h->x2_32, h->x2_16, D, M, e, st);
-        RowEpi e2;
-        e2.ln1_g = pl.norm3_g; e2.ln1_b = pl.norm3_b;
-        e2.film = h->film + ((size_t)si * L + l) * 2 * D;
-        e2.out_f32 = h->x3_32; e2.ldo32 = D; e2.out_bf16 = h->x3_16; e2.ldo16 = D;
-        run_gemm(h, pl.ffn2, h->h32, h->h16, F, M, e2, st);
-      }
-      // -- task_decoder (:244-256, 376-380); cls only where it is read (:631)
-      if (last_layer && last_step) {
-        RowEpi e;
-        e.relu = 1; e.ln1_g = pl.cls_ln2_g; e.ln1_b = pl.cls_ln2_b;
-        e.out_f32 = h->c1_32; e.ldo32 = D; e.out_bf16 = h->c1_16; e.ldo16 = D;
-        run_gemm(h, pl.cls0, h->x3_32, h->x3_16, D, M, e, st);
-        RowEpi e2;
-        e2.relu = 1; e2.ln1_g = pl.cls_ln5_g; e2.ln1_b = pl.cls_ln5_b;
-        e2.dot_w = pl.cls6_w; e2.dot_b = pl.cls6_b; e2.dot_out = scores;
-        run_gemm(h, pl.cls3, h->c1_32, h->c1_16, D, M, e2, st);
-      }
-      {
-        RowEpi e;
-        e.relu = 1;
-        e.out_f32 = h->r1_32; e.ldo32 = D; e.out_bf16 = h->r1_16; e.ldo16 = D;
-        run_gemm(h, pl.reg0, h->x3_32, h->x3_16, D, M, e, st);
-        RowEpi e2;
-        e2.relu = 1;
-        e2.out_f32 = h->r2_32; e2.ldo32 = D;
-        run_gemm(h, pl.reg2, h->r1_32, h->r1_16, D, M, e2, st);
-      }
-      delete chain;
-      DdimCoef dc{0.f, 1.f, 1.f, 0.f};
-      const int do_ddim = (last_layer && !last_step) ? 1 : 0;
-      if (do_ddim) {
-        const int t = h->roll[si], prev = t - 1;   // set_timesteps(1000) => step ratio 1 (:584)
-        const float ac_t = h->ac[t], ac_p = prev >= 0 ? h->ac[prev] : 1.0f;
-        dc.sqrt_ac_t = sqrtf(ac_t); dc.sqrt_1m_ac_t = sqrtf(1.0f - ac_t);
-        dc.sqrt_ac_prev = sqrtf(ac_p); dc.sqrt_1m_ac_prev = sqrtf(1.0f - ac_p);
-      }
-      { ProfSpan ps(h, ST_REG, st);
-      launch_reg_finish(h->r2_32, pl.reg4_w, pl.reg4_b, h->pts, h->img, modes, M, P, do_ddim, dc, st); }
-      h->launches++;
+    cudaEvent_t ev_fork = h->sync_events[nchunk], ev_join = h->sync_events[nchunk + 1];
+    CU_TRY(h, cudaEventRecord(ev_fork, st));
+    CU_TRY(h, cudaStreamWaitEvent(h->aux_stream, ev_fork, 0));
+    const int base = B / nchunk, rem = B % nchunk;
+    int lo = 0, launches = 0;
+    for (int c = 0; c < nchunk; ++c) {
+      const int n = base + (c < rem ? 1 : 0);
+      cudaStream_t sc = (c & 1) ? h->aux_stream : st;
+      if (c > 0) CU_TRY(h, cudaStreamWaitEvent(sc, h->sync_events[c - 1], 0));
+      h->launches = 0;
+      rc = forward_range(h, ego, agents, bev, bev_dtype, bev_layout, noise, out_traj, out_modes,
+                         out_scores, out_mode_idx, lo, n, B, sc, h->sync_events[c]);
+      if (rc) return rc;
+      launches += h->launches;
+      lo += n;
     }
+    h->launches = launches;
+    CU_TRY(h, cudaEventRecord(ev_join, h->aux_stream));
+    CU_TRY(h, cudaStreamWaitEvent(st, ev_join, 0));
   }
-  { ProfSpan ps(h, ST_SELECT, st);
-  launch_select(scores, modes, out_traj, reinterpret_cast<long long*>(out_mode_idx), B, A, P, st); }
-  h->launches++;
   CU_TRY(h, cudaGetLastError());
   return DDH_OK;
 }
@@ -805,6 +923,14 @@ int ddh_forward_host(ddh_handle* h, const float* ego, const float* agents, const
 }
 
 int ddh_last_launch_count(const ddh_handle* h) { return h ? h->launches : 0; }
+
+int ddh_set_concurrency(ddh_handle* h, int chunks, int min_chunk_scenes) {
+  if (!h || chunks < 1 || chunks > 64 || min_chunk_scenes < 1)
+    return fail(h, DDH_ERR_BAD_ARG, "ddh_set_concurrency: bad argument");
+  h->chunks = chunks;
+  h->min_chunk_scenes = min_chunk_scenes;
+  return DDH_OK;
+}
 
 int ddh_set_profiling(ddh_handle* h, int on) {
   if (!h) return DDH_ERR_BAD_ARG;

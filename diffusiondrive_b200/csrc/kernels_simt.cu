@@ -197,9 +197,9 @@ __device__ __forceinline__ float4 ld4<__nv_bfloat16>(const __nv_bfloat16* p) {
   return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
 }
 
-constexpr int TP_PX = 64;
-
-template <typename TI, typename TO>
+// PXT pixels per tile: 64 for fp32 output; 32 for bf16 output, whose 16.5 KB of shared memory
+// lets a layout CTA share an SM with the resident tensor-core CTAs (scene-chunk concurrency).
+template <typename TI, typename TO, int PXT>
 __global__ void __launch_bounds__(256) bev_to_nhwc_kernel(const TI* __restrict__ src,
                                                           TO* __restrict__ dst, int C, int HW) {
   // tile[px][c], padded so that the transposing stores are conflict free
@@ -207,21 +207,20 @@ __global__ void __launch_bounds__(256) bev_to_nhwc_kernel(const TI* __restrict__
   extern __shared__ __align__(16) uint32_t tile_u32[];
   TO* tile = reinterpret_cast<TO*>(tile_u32);
   constexpr int LDE = LDW * 4 / sizeof(TO);  // elements per pixel row
+  constexpr int G = PXT / 4;                 // groups of 4 pixels
+  constexpr int CL = 256 / G;                // channels covered per iteration
   const int b = blockIdx.y;
-  const int px0 = blockIdx.x * TP_PX;
+  const int px0 = blockIdx.x * PXT;
   const int tid = threadIdx.x;
-  const int px4 = tid & 15;      // which group of 4 pixels
-  const int cl = tid >> 4;       // 0..15
+  const int px4 = tid % G;
+  const int cl = tid / G;
   const TI* s = src + (size_t)b * C * HW + px0 + px4 * 4;
-  float4 v[16];
+  float4 v[256 / CL];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int c = i * 16 + cl;
-    v[i] = ld4<TI>(s + (size_t)c * HW);
-  }
+  for (int i = 0; i < 256 / CL; ++i) v[i] = ld4<TI>(s + (size_t)(i * CL + cl) * HW);
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int c = i * 16 + cl;
+  for (int i = 0; i < 256 / CL; ++i) {
+    const int c = i * CL + cl;
     tile[(px4 * 4 + 0) * LDE + c] = (TO)v[i].x;
     tile[(px4 * 4 + 1) * LDE + c] = (TO)v[i].y;
     tile[(px4 * 4 + 2) * LDE + c] = (TO)v[i].z;
@@ -232,7 +231,7 @@ __global__ void __launch_bounds__(256) bev_to_nhwc_kernel(const TI* __restrict__
   const int lane = tid & 31, warp = tid >> 5;
   constexpr int WORDS = 256 * sizeof(TO) / 4;  // 128 (bf16) or 256 (f32)
   uint32_t* d = reinterpret_cast<uint32_t*>(dst + ((size_t)b * HW + px0) * C);
-  for (int px = warp; px < TP_PX; px += 8) {
+  for (int px = warp; px < PXT; px += 8) {
 #pragma unroll
     for (int w = lane; w < WORDS; w += 32) d[(size_t)px * WORDS + w] = tile_u32[px * LDW + w];
   }
@@ -241,16 +240,17 @@ __global__ void __launch_bounds__(256) bev_to_nhwc_kernel(const TI* __restrict__
 template <typename TI, typename TO>
 static void bev_launch(const void* src, void* dst, int B, int C, int HW, cudaStream_t st) {
   constexpr int LDW = (sizeof(TO) == 2) ? 129 : 257;
-  const int smem = TP_PX * LDW * 4;
+  constexpr int PXT = (sizeof(TO) == 2) ? 32 : 64;
+  const int smem = PXT * LDW * 4;
   static bool once = false;
   if (!once) {
-    cudaFuncSetAttribute(bev_to_nhwc_kernel<TI, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         smem);
+    cudaFuncSetAttribute(bev_to_nhwc_kernel<TI, TO, PXT>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     once = true;
   }
-  dim3 grid(HW / TP_PX, B);
-  bev_to_nhwc_kernel<TI, TO><<<grid, 256, smem, st>>>(reinterpret_cast<const TI*>(src),
-                                                     reinterpret_cast<TO*>(dst), C, HW);
+  dim3 grid(HW / PXT, B);
+  bev_to_nhwc_kernel<TI, TO, PXT><<<grid, 256, smem, st>>>(reinterpret_cast<const TI*>(src),
+                                                          reinterpret_cast<TO*>(dst), C, HW);
 }
 
 void launch_bev_to_nhwc(const void* src, int src_dtype, void* dst, int dst_dtype, int B, int C,

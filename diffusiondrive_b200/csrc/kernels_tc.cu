@@ -280,6 +280,9 @@ tc_gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap) {
     }
 
     // ---------------- epilogue: thread-per-row out of TMEM
+    // Arithmetic is thread-per-row (row = TMEM lane); global traffic goes through a 32x32
+    // per-warp transpose in shared memory (aliasing the now idle pipeline buffers) so that
+    // every global instruction covers 8 rows x 64 contiguous bytes instead of 32 rows x 16 B.
     const RowEpi& e = p.epi;
     const int r = warp * 32 + lane;
     const bool valid = r < rows_valid;
@@ -287,6 +290,34 @@ tc_gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap) {
     const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
     mbar_wait(bars.accum(), 0);
     tc_fence_after();
+    constexpr int SLD = 36;                                   // fp32 staging row stride (words)
+    float* stg = reinterpret_cast<float*>(sm) + warp * (32 * SLD);
+    uint32_t* stg16 = reinterpret_cast<uint32_t*>(stg);       // bf16 staging, 20 words per row
+    const int cr = lane & 7, cc = lane >> 3;                  // coalesced side: row, 16B chunk
+
+    // rows [warp*32, +32) x cols [c0, c0+32) of an fp32 matrix -> this thread's row in t[]
+    auto load_rows = [&](auto rowptr, int c0, float (&t)[32]) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rr = cr + 8 * i;
+        const bool ok = warp * 32 + rr < rows_valid;
+        const float* g = rowptr((long long)row0 + warp * 32 + rr) + c0;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int ch = cc + 4 * hh;
+          float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok) v4 = __ldg(reinterpret_cast<const float4*>(g) + ch);
+          *reinterpret_cast<float4*>(stg + rr * SLD + ch * 4) = v4;
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 v4 = *reinterpret_cast<const float4*>(stg + lane * SLD + 4 * q);
+        t[4 * q + 0] = v4.x; t[4 * q + 1] = v4.y; t[4 * q + 2] = v4.z; t[4 * q + 3] = v4.w;
+      }
+      __syncwarp();
+    };
 
     float dsum = 0.f;
     auto finalize = [&](int b, float (&v)[32]) {
@@ -304,27 +335,49 @@ tc_gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) dsum = fmaf(v[i], w[i], dsum);
       }
-      if (valid) {
-        if (e.out_f32) {
-          float4* o = reinterpret_cast<float4*>(e.out_f32 + m * e.ldo32 + c0);
+      if (e.out_f32) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        }
-        if (e.out_bf16) {
-          uint4* o = reinterpret_cast<uint4*>(e.out_bf16 + m * e.ldo16 + c0);
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(stg + lane * SLD + 4 * q) =
+              make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        __syncwarp();
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * q + 0], v[8 * q + 1]);
-            __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]);
-            __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * q + 6], v[8 * q + 7]);
-            uint4 u;
-            u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-            u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-            o[q] = u;
+        for (int i = 0; i < 4; ++i) {
+          const int rr = cr + 8 * i;
+          if (warp * 32 + rr < rows_valid) {
+            float* g = e.out_f32 + ((long long)row0 + warp * 32 + rr) * e.ldo32 + c0;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const int ch = cc + 4 * hh;
+              reinterpret_cast<float4*>(g)[ch] =
+                  *reinterpret_cast<const float4*>(stg + rr * SLD + ch * 4);
+            }
           }
         }
+        __syncwarp();
+      }
+      if (e.out_bf16) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * q + 0], v[8 * q + 1]);
+          __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]);
+          __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * q + 6], v[8 * q + 7]);
+          uint4 u;
+          u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+          u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+          *reinterpret_cast<uint4*>(stg16 + lane * 20 + 4 * q) = u;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rr = cr + 8 * i;
+          if (warp * 32 + rr < rows_valid) {
+            __nv_bfloat16* g = e.out_bf16 + ((long long)row0 + warp * 32 + rr) * e.ldo16 + c0;
+            reinterpret_cast<uint4*>(g)[cc] = *reinterpret_cast<const uint4*>(stg16 + rr * 20 + cc * 4);
+          }
+        }
+        __syncwarp();
       }
     };
     auto ld_block = [&](int b, float (&v)[32]) {
@@ -357,9 +410,11 @@ tc_gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
       }
-      if (e.res && valid) {
+      if (e.res) {
         float t[32];
-        ldg_row32(e.res + m * e.ldres + n0 + b * 32, t);
+        const float* rbase = e.res;
+        const long long ldr = e.ldres;
+        load_rows([&](long long mm) { return rbase + mm * ldr; }, n0 + b * 32, t);
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] += t[i];
       }
@@ -390,9 +445,11 @@ tc_gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap) {
         ldg_row32(e.ln1_b + b * 32, bb);
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = (v[i] - mean) * rstd * g[i] + bb[i];
-        if (e.rowvec && valid) {
+        if (e.rowvec) {
           float t[32];
-          ldg_row32(e.rowvec + (m / e.rows_per_group) * D + b * 32, t);
+          const float* vbase = e.rowvec;
+          const int rpg = e.rows_per_group;
+          load_rows([&](long long mm) { return vbase + (mm / rpg) * D; }, b * 32, t);
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] += t[i];
         }
@@ -468,6 +525,15 @@ tc_gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap) {
 // ===================================================================================
 struct EntPair { int slot; float w; };
 
+#ifdef DDH_TIMELINE
+#define TL_STAMP(role, idx, which)                                                        \
+  do {                                                                                    \
+    if (p.dbg && blockIdx.x == 0 && (idx) < 40) p.dbg[((role)*40 + (idx)) * 2 + (which)] = clock64(); \
+  } while (0)
+#else
+#define TL_STAMP(role, idx, which) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_conv_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap) {
   constexpr int NS = C_NS, NT = C_NT;
@@ -493,11 +559,23 @@ tc_conv_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap) {
   const int passes = (nu + NT * TC_BM - 1) / (NT * TC_BM);
   const int ent_bytes = ((n_ent * 8 + 15) / 16) * 16;
   EntPair* ent = reinterpret_cast<EntPair*>(sm + C_PIPE);
-  const TcBars bars{sm_addr + C_PIPE + ent_bytes, NS};
+  float* bias_s = reinterpret_cast<float*>(sm + C_PIPE + ent_bytes);          // [256]
+  const TcBars bars{sm_addr + C_PIPE + ent_bytes + D * 4, NS};
   volatile uint32_t* tmem_slot =
-      reinterpret_cast<volatile uint32_t*>(sm + C_PIPE + ent_bytes + (2 * NS + 2) * 8);
+      reinterpret_cast<volatile uint32_t*>(sm + C_PIPE + ent_bytes + D * 4 + (2 * NS + 2) * 8);
   constexpr int KC = 9 * (D / TC_BK);   // 36 k-chunks: (tap, 64-channel chunk)
 
+  // Row coordinates of the first pass: 16 independent loads per producer thread, issued before
+  // anything else so their latency hides under the barrier / TMEM setup (index clamped, the
+  // validity is re-derived from nu).
+  constexpr int RPT = NT * 8;
+  int yx0[RPT];
+  if (warp < 4) {
+    const int rb0 = threadIdx.x >> 3;
+#pragma unroll
+    for (int i = 0; i < RPT; ++i)
+      yx0[i] = __ldg(p.upix + (size_t)scene * p.rcap + min(rb0 + 16 * i, nu - 1));
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < NS; ++s) {
       mbar_init(bars.full(s), 128 + 1);
@@ -509,11 +587,18 @@ tc_conv_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap) {
   }
   if (warp == 5) tmem_alloc<NT * D>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
   if (warp == 4 && lane == 0) tma_prefetch_desc(&wmap);
-  for (int i = threadIdx.x; i < n_ent; i += TC_THREADS) {
-    EntPair e;
-    e.slot = p.ent_slot[(size_t)scene * n_ent + i];
-    e.w = p.ent_w[(size_t)scene * n_ent + i];
-    ent[i] = e;
+  if (threadIdx.x >= 128 && threadIdx.x < 192)
+    reinterpret_cast<float4*>(bias_s)[threadIdx.x - 128] =
+        __ldg(reinterpret_cast<const float4*>(p.epi.bias) + (threadIdx.x - 128));
+  {
+    const int* es = p.ent_slot + (size_t)scene * n_ent;
+    const float* ew = p.ent_w + (size_t)scene * n_ent;
+    for (int i = threadIdx.x; i < n_ent; i += TC_THREADS) {
+      EntPair e;
+      e.slot = __ldg(es + i);
+      e.w = __ldg(ew + i);
+      ent[i] = e;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -523,11 +608,10 @@ tc_conv_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap) {
   if (warp < 4) {
     const int tid = threadIdx.x;
     const int j = tid & 7, rb = tid >> 3;
-    constexpr int RPT = NT * 8;
     const __nv_bfloat16* bev = reinterpret_cast<const __nv_bfloat16*>(p.bev) +
                                (size_t)scene * p.H * p.W_ * D;
-    const float* bias = p.epi.bias;
     float* Vs = reinterpret_cast<float*>(sm);
+    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
     int g = 0;
     for (int pass = 0; pass < passes; ++pass) {
       const int row_base = pass * NT * TC_BM;
@@ -539,13 +623,18 @@ tc_conv_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap) {
       // centre pixel and a 9-bit mask of the taps that fall inside the map.
       int rowoff[RPT];
       uint32_t vmask[RPT];
+      if (pass > 0) {
+#pragma unroll
+        for (int i = 0; i < RPT; ++i)
+          yx0[i] = __ldg(p.upix + (size_t)scene * p.rcap + min(row_base + rb + 16 * i, nu - 1));
+      }
 #pragma unroll
       for (int i = 0; i < RPT; ++i) {
         const int r = rb + 16 * i;
         rowoff[i] = 0;
         vmask[i] = 0;
         if (r < rows_valid) {
-          const int yx = p.upix[(size_t)scene * p.rcap + row_base + r];   // (y << 16) | x
+          const int yx = yx0[i];   // (y << 16) | x
           const int y = yx >> 16, x = yx & 0xffff;
           rowoff[i] = (y * p.W_ + x) * D + j * 8;
           const uint32_t xm = (x > 0 ? 1u : 0u) | 2u | (x + 1 < p.W_ ? 4u : 0u);
@@ -556,6 +645,7 @@ tc_conv_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap) {
       for (int kc = 0; kc < KC; ++kc, ++g) {
         const int s = g % NS;
         mbar_wait(bars.empty(s), ((g / NS) & 1) ^ 1);
+        if (tid == 0) TL_STAMP(0, g, 0);
         const uint32_t a_dst = sm_addr + s * C_STAGE + dst_base;
         const int tap = kc >> 2;
         const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
@@ -568,30 +658,58 @@ tc_conv_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap) {
             cp_async16(a_dst + i * 2048, bev + off, ok ? 16u : 0u);
           }
         }
+        if (kc == 0) {
+          // Accumulators start at the conv bias (every MMA accumulates), so the drain is only
+          // ReLU + store.  Done here, after the first chunk's copies are in flight and before
+          // this thread's arrival lets the first MMA start; bias comes from shared memory.
+#pragma unroll 1
+          for (int cb = 0; cb < D / 32; ++cb) {
+            uint32_t u[32];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const uint4 t4 = *reinterpret_cast<const uint4*>(bias_s + cb * 32 + 4 * q);
+              u[4 * q + 0] = t4.x; u[4 * q + 1] = t4.y; u[4 * q + 2] = t4.z; u[4 * q + 3] = t4.w;
+            }
+            for (int t = 0; t < nt_active; ++t) tmem_st32(trow + t * D + cb * 32, u);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+        }
         cp_async_mbar_arrive_noinc(bars.full(s));
+        if (tid == 0) TL_STAMP(0, g, 1);
       }
       // ---------------- epilogue: drain TMEM -> smem, combine, half of N at a time
+      if (tid == 0) TL_STAMP(3, pass * 4 + 0, 0);
       mbar_wait(bars.accum(), pass & 1);
+      if (tid == 0) TL_STAMP(3, pass * 4 + 0, 1);
       tc_fence_after();
       for (int half = 0; half < 2; ++half) {
         for (int t = 0; t < nt_active; ++t) {
           float* vrow = Vs + (size_t)(t * TC_BM + warp * 32 + lane) * C_VS_LD;
 #pragma unroll 1
-          for (int cb = 0; cb < 4; ++cb) {
-            uint32_t u[32];
+          for (int cb = 0; cb < 4; cb += 2) {
+            uint32_t u0[32], u1[32];
             const int col = half * 128 + cb * 32;
-            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + t * D + col, u);
+            tmem_ld32(trow + t * D + col, u0);
+            tmem_ld32(trow + t * D + col + 32, u1);
             tmem_ld_wait();
-            float bb[32];
-            ldg_row32(bias + col, bb);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               float4 o;
-              o.x = fmaxf(__uint_as_float(u[4 * q + 0]) + bb[4 * q + 0], 0.f);
-              o.y = fmaxf(__uint_as_float(u[4 * q + 1]) + bb[4 * q + 1], 0.f);
-              o.z = fmaxf(__uint_as_float(u[4 * q + 2]) + bb[4 * q + 2], 0.f);
-              o.w = fmaxf(__uint_as_float(u[4 * q + 3]) + bb[4 * q + 3], 0.f);
+              o.x = fmaxf(__uint_as_float(u0[4 * q + 0]), 0.f);
+              o.y = fmaxf(__uint_as_float(u0[4 * q + 1]), 0.f);
+              o.z = fmaxf(__uint_as_float(u0[4 * q + 2]), 0.f);
+              o.w = fmaxf(__uint_as_float(u0[4 * q + 3]), 0.f);
               *reinterpret_cast<float4*>(vrow + cb * 32 + 4 * q) = o;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float4 o;
+              o.x = fmaxf(__uint_as_float(u1[4 * q + 0]), 0.f);
+              o.y = fmaxf(__uint_as_float(u1[4 * q + 1]), 0.f);
+              o.z = fmaxf(__uint_as_float(u1[4 * q + 2]), 0.f);
+              o.w = fmaxf(__uint_as_float(u1[4 * q + 3]), 0.f);
+              *reinterpret_cast<float4*>(vrow + cb * 32 + 32 + 4 * q) = o;
             }
           }
         }
@@ -599,7 +717,7 @@ tc_conv_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap) {
         for (int a = warp; a < A; a += 4) {
           float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
           const EntPair* ea = ent + a * p.ent_per_anchor;
-#pragma unroll 4
+#pragma unroll 8
           for (int k = 0; k < p.ent_per_anchor; ++k) {
             const EntPair e = ea[k];
             const int rr = e.slot - row_base;
@@ -628,6 +746,7 @@ tc_conv_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap) {
         }
         named_bar_sync(1, 128);
       }
+      if (tid == 0) TL_STAMP(3, pass * 4 + 1, 0);
       // staging (generic proxy) is done: the weight TMA of the next pass may overwrite it
       fence_proxy_async();
       tc_fence_before();
@@ -641,8 +760,10 @@ tc_conv_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap) {
         for (int kc = 0; kc < KC; ++kc, ++g) {
           const int s = g % NS;
           mbar_wait(bars.empty(s), ((g / NS) & 1) ^ 1);
+          TL_STAMP(1, g, 0);
           mbar_arrive_expect_tx(bars.full(s), TC_B_TILE);
           tma_load_2d(sm_addr + s * C_STAGE + NT * TC_A_TILE, &wmap, bars.full(s), kc * TC_BK, 0);
+          TL_STAMP(1, g, 1);
         }
       }
     }
@@ -657,10 +778,12 @@ tc_conv_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap) {
         for (int kc = 0; kc < KC; ++kc, ++g) {
           const int s = g % NS;
           mbar_wait(bars.full(s), (g / NS) & 1);
+          TL_STAMP(2, g, 0);
           tc_fence_after();
           const uint32_t a_stage = sm_addr + s * C_STAGE;
-          mma_chunk<NT>(a_stage, a_stage + NT * TC_A_TILE, tmem_base, nt_active, kc == 0, idesc,
+          mma_chunk<NT>(a_stage, a_stage + NT * TC_A_TILE, tmem_base, nt_active, false, idesc,
                         bars.empty(s));
+          TL_STAMP(2, g, 1);
         }
         umma_commit(bars.accum());
       }
@@ -687,7 +810,7 @@ void launch_tc_gemm(const GemmParams& p, const CUtensorMap& wmap, int n_total, c
 }
 
 int tc_conv_smem_bytes(int A, int ent_per_anchor) {
-  return C_PIPE + ((A * ent_per_anchor * 8 + 15) / 16) * 16 + TC_BAR_BYTES + 1024;
+  return C_PIPE + ((A * ent_per_anchor * 8 + 15) / 16) * 16 + D * 4 + TC_BAR_BYTES + 1024;
 }
 
 void launch_tc_conv(const GemmParams& p, const CUtensorMap& wmap, int B, cudaStream_t st) {

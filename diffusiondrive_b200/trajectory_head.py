@@ -357,6 +357,12 @@ class TrajectoryHead(nn.Module):
     STAGES = ("bev_layout", "hoist_kv_ego", "init", "embed_encode", "plan", "conv", "combine",
               "gemm_chain", "attn_core", "reg_finish", "select")
 
+    def set_concurrency(self, chunks: int, min_chunk_scenes: int = 512) -> None:
+        """Scene-chunk concurrency of a forward (see ddh_set_concurrency in include/ddh.h)."""
+        _lib.check(self._lib, self._handle,
+                   self._lib.ddh_set_concurrency(self._handle, int(chunks), int(min_chunk_scenes)),
+                   "ddh_set_concurrency")
+
     def set_profiling(self, on: bool) -> None:
         """Bracket every stage of the next forwards with CUDA events (bench.py roofline leg)."""
         _lib.check(self._lib, self._handle, self._lib.ddh_set_profiling(self._handle, int(on)),

@@ -183,6 +183,14 @@ DDH_API int ddh_forward_host(ddh_handle *h, const float *ego, const float *agent
 /* Number of kernel launches issued by the last ddh_forward on this handle. */
 DDH_API int ddh_last_launch_count(const ddh_handle *h);
 
+/* Scene-chunk concurrency of ddh_forward: a call of B >= chunks*min_chunk_scenes scenes is cut
+ * into `chunks` contiguous scene blocks issued alternately on the caller's stream and one
+ * internal stream (fork/join with events, CUDA-graph capturable), so that one block's HBM-bound
+ * BEV layout pass overlaps another block's tensor-bound stages.  Results do not depend on the
+ * setting (scenes are independent).  Default: 4 chunks, at least 512 scenes each; chunks = 1
+ * issues everything on the caller's stream. */
+DDH_API int ddh_set_concurrency(ddh_handle *h, int chunks, int min_chunk_scenes);
+
 /* Optional per-stage device timing: when on, ddh_forward brackets each stage with CUDA events
  * on the caller's stream.  ddh_get_profile synchronises and returns the summed duration and
  * the number of timed spans of one stage of the LAST forward.  Stages: "bev_layout",
