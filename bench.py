@@ -260,7 +260,7 @@ def run_ours(args):
             except Exception:
                 traffic = None
         roofline = {
-            "kernel": "tc_gemm_kernel<2,true> (on-demand value_proj conv, tcgen05)",
+            "kernel": "tc_conv_kernel (on-demand value_proj conv + fused combine, tcgen05)",
             "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"],
             "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"],
             "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside the step)",

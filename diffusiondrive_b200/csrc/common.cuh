@@ -165,6 +165,7 @@ struct GemmParams {
   int K = 0;
   const void* W = nullptr;   // SIMT: Wt[K][ldw] fp32; tensor engine: via TMA map
   int ldw = 0;
+  int n_blocks = 1;          // 256-wide column blocks of the output (tensor engine)
   RowEpi epi;
   // conv gather
   const void* bev = nullptr;  // NHWC [B][H][W][C]

@@ -13,6 +13,7 @@
 #include <cuda.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -117,6 +118,7 @@ struct ddh_handle {
   int ev_used = 0;
   int* conv_rows = nullptr;                    // [S*L] unique value_proj rows per conv launch
   long long* dbg = nullptr;                    // timeline stamps (DDH_TIMELINE builds)
+  int tl_gemm = -1;                            // env DDH_TIMELINE_GEMM=<launch index>: stamp that dense GEMM
   // scene-chunk concurrency (ddh_set_concurrency)
   int chunks = 4;
   int min_chunk_scenes = 512;
@@ -272,6 +274,7 @@ int run_gemm(ddh_handle* h, const PackedLinear& L, const float* a32, const __nv_
     launch_simt_gemm(p, L.N, st);
   } else {
     p.A = a16;
+    p.dbg = (h->tl_gemm >= 0 && h->launches == h->tl_gemm) ? h->dbg : nullptr;
     launch_tc_gemm(p, L.map, L.N, st);
   }
   h->launches++;
@@ -423,6 +426,7 @@ int ddh_create(const ddh_shape* s, ddh_handle** out) {
 #undef REQUIRE
   ddh_handle* h = new ddh_handle();
   h->shp = *s;
+  if (const char* e = getenv("DDH_TIMELINE_GEMM")) h->tl_gemm = atoi(e);
   default_alphas_cumprod(h->ac);
   make_roll(s->num_steps, h->roll);
   *out = h;
@@ -714,7 +718,7 @@ int forward_range(ddh_handle* h, const float* ego, const float* agents, const vo
         gp.H = s.bev_h; gp.W_ = s.bev_w; gp.C = s.bev_channels;
         gp.epi.bias = pl.conv.bias; gp.epi.relu = 1;
         if (bf) {   // combine fused into the conv epilogue: V never leaves the SM
-          gp.dbg = h->dbg;
+          gp.dbg = h->tl_gemm < 0 ? h->dbg : nullptr;
           gp.ent_slot = v.ent_slot; gp.ent_w = v.ent_w; gp.n_anchor = A; gp.ent_per_anchor = P * 4;
           gp.epi.out_f32 = v.s32; gp.epi.ldo32 = D; gp.epi.out_bf16 = v.s16; gp.epi.ldo16 = D;
           launch_tc_conv(gp, pl.conv.map, B, st);

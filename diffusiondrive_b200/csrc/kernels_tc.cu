@@ -25,11 +25,21 @@ constexpr int TC_A_TILE = TC_BM * TC_BK * 2;     // 16 KiB
 constexpr int TC_B_TILE = D * TC_BK * 2;         // 32 KiB
 constexpr int TC_BAR_BYTES = 256;
 
-// dense GEMM: 1 row tile, 2 stages, 2 CTAs per SM (one CTA's epilogue overlaps the other's
-// main loop); conv: 2 row tiles share each weight tile, 3 stages, 1 CTA per SM.
-constexpr int G_NS = 2;
+// dense GEMM: persistent CTAs (one per SM) walking 128x256 tiles, 4 stages, two TMEM
+// accumulator buffers so the epilogue of tile i overlaps the main loop of tile i+1;
+// conv: 2 row tiles share each weight tile, 3 stages, 1 CTA per SM.
+constexpr int G_NS = 4;
 constexpr int G_STAGE = TC_A_TILE + TC_B_TILE;                 // 48 KiB
-constexpr int G_SMEM = G_NS * G_STAGE + TC_BAR_BYTES + 1024;
+constexpr int G_THREADS = 320;                                 // 4 epilogue + 4 producer + TMA + MMA warps
+constexpr int G_STG_BYTES = 4 * 32 * 36 * 4;                   // per-warp 32x32 transpose staging
+// per-column epilogue vectors staged in smem (L1 is only ~12 KB next to 216 KB of smem, so
+// "uniform" global loads of bias / LN / FiLM vectors would miss and serialise L2 round trips)
+constexpr int G_PAR_BIAS = 0;        // up to 1024 floats (N_total <= 1024)
+constexpr int G_PAR_LN1G = 1024, G_PAR_LN1B = 1280, G_PAR_LN2G = 1536, G_PAR_LN2B = 1792;
+constexpr int G_PAR_FILM = 2048;     // 512
+constexpr int G_PAR_DOTW = 2560;     // 256
+constexpr int G_PAR_FLOATS = 2816;
+constexpr int G_SMEM = G_NS * G_STAGE + G_STG_BYTES + G_PAR_FLOATS * 4 + TC_BAR_BYTES + 1024;
 constexpr int C_NT = 2;
 constexpr int C_NS = 3;
 constexpr int C_STAGE = C_NT * TC_A_TILE + TC_B_TILE;          // 64 KiB
@@ -180,6 +190,15 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16_m128_n256() {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+#ifdef DDH_TIMELINE
+#define TL_STAMP(role, idx, which)                                                        \
+  do {                                                                                    \
+    if (p.dbg && blockIdx.x == 0 && (idx) < 40) p.dbg[((role)*40 + (idx)) * 2 + (which)] = clock64(); \
+  } while (0)
+#else
+#define TL_STAMP(role, idx, which) do { } while (0)
+#endif
+
 // ------------------------------------------------------------------ shared roles
 struct TcBars {
   uint32_t base;
@@ -221,7 +240,15 @@ __device__ __forceinline__ void ldg_row32(const float* p, float (&o)[32]) {
   }
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__device__ __forceinline__ void lds_row32(const float* p, float (&o)[32]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 t = *(reinterpret_cast<const float4*>(p) + q);
+    o[4 * q + 0] = t.x; o[4 * q + 1] = t.y; o[4 * q + 2] = t.z; o[4 * q + 3] = t.w;
+  }
+}
+
+__global__ void __launch_bounds__(G_THREADS, 1)
 tc_gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap) {
   constexpr int NS = G_NS;
   extern __shared__ uint8_t smem_raw[];
@@ -229,288 +256,359 @@ tc_gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap) {
   const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
   uint8_t* sm = smem_raw + pad;
   const uint32_t sm_addr = raw_addr + pad;
-  const TcBars bars{sm_addr + NS * G_STAGE, NS};
-  volatile uint32_t* tmem_slot =
-      reinterpret_cast<volatile uint32_t*>(sm + NS * G_STAGE + (2 * NS + 2) * 8);
+  float* par = reinterpret_cast<float*>(sm + NS * G_STAGE + G_STG_BYTES);
+  constexpr int kBarOff = NS * G_STAGE + G_STG_BYTES + G_PAR_FLOATS * 4;
+  const uint32_t bar = sm_addr + kBarOff;
+  auto full_bar = [&](int s) { return bar + s * 8; };
+  auto empty_bar = [&](int s) { return bar + (NS + s) * 8; };
+  auto tfull_bar = [&](int b) { return bar + (2 * NS + b) * 8; };
+  auto tempty_bar = [&](int b) { return bar + (2 * NS + 2 + b) * 8; };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + kBarOff + (2 * NS + 4) * 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row0 = blockIdx.x * TC_BM;
-  const int rows_valid = min(TC_BM, p.M - row0);
-  const int n0 = blockIdx.y * D;
+  const int n_row_tiles = (p.M + TC_BM - 1) / TC_BM;
+  const int n_tiles = n_row_tiles * p.n_blocks;
   const int KC = p.K / TC_BK;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NS; ++s) {
-      mbar_init(bars.full(s), 128 + 1);
-      mbar_init(bars.empty(s), 1);
+      mbar_init(full_bar(s), 128 + 1);
+      mbar_init(empty_bar(s), 1);
     }
-    mbar_init(bars.accum(), 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 128);
+    }
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc<D>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
-  if (warp == 4 && lane == 0) tma_prefetch_desc(&wmap);
+  if (warp == 9) tmem_alloc<2 * D>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  if (warp == 8 && lane == 0) tma_prefetch_desc(&wmap);
+  {
+    const RowEpi& e = p.epi;
+    const int nb_tot = p.n_blocks * D;
+    for (int i = threadIdx.x; i < nb_tot; i += G_THREADS) par[G_PAR_BIAS + i] = e.bias ? __ldg(e.bias + i) : 0.f;
+    for (int i = threadIdx.x; i < D; i += G_THREADS) {
+      if (e.ln1_g) { par[G_PAR_LN1G + i] = __ldg(e.ln1_g + i); par[G_PAR_LN1B + i] = __ldg(e.ln1_b + i); }
+      if (e.ln2_g) { par[G_PAR_LN2G + i] = __ldg(e.ln2_g + i); par[G_PAR_LN2B + i] = __ldg(e.ln2_b + i); }
+      if (e.film) { par[G_PAR_FILM + i] = __ldg(e.film + i); par[G_PAR_FILM + D + i] = __ldg(e.film + D + i); }
+      if (e.dot_w) par[G_PAR_DOTW + i] = __ldg(e.dot_w + i);
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
-    // ---------------- A producers: 8 rows x one 16-byte chunk per thread and k-chunk
-    const int tid = threadIdx.x;
-    const int j = tid & 7, rb = tid >> 3;
-    const __nv_bfloat16* Ab = reinterpret_cast<const __nv_bfloat16*>(p.A);
-    const __nv_bfloat16* src[8];
-    uint32_t dst_off[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = rb + 16 * i;
-      src[i] = (r < rows_valid) ? (Ab + (long long)(row0 + r) * p.lda + j * 8) : nullptr;
-      dst_off[i] = r * 128 + ((j ^ (r & 7)) << 4);
-    }
-    for (int kc = 0; kc < KC; ++kc) {
-      const int s = kc % NS;
-      mbar_wait(bars.empty(s), ((kc / NS) & 1) ^ 1);
-      const uint32_t a_stage = sm_addr + s * G_STAGE;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const bool ok = src[i] != nullptr;
-        cp_async16(a_stage + dst_off[i], ok ? (const void*)(src[i] + kc * TC_BK) : (const void*)Ab,
-                   ok ? 16u : 0u);
-      }
-      cp_async_mbar_arrive_noinc(bars.full(s));
-    }
-
-    // ---------------- epilogue: thread-per-row out of TMEM
+    // ======================= epilogue warps (TMEM lane quarter = warp) =================
     // Arithmetic is thread-per-row (row = TMEM lane); global traffic goes through a 32x32
-    // per-warp transpose in shared memory (aliasing the now idle pipeline buffers) so that
-    // every global instruction covers 8 rows x 64 contiguous bytes instead of 32 rows x 16 B.
+    // per-warp transpose in shared memory so that every global instruction covers 8 rows x
+    // 64 contiguous bytes; residual / row-vector loads of block b+1 are in flight while
+    // block b is processed.
     const RowEpi& e = p.epi;
-    const int r = warp * 32 + lane;
-    const bool valid = r < rows_valid;
-    const long long m = row0 + r;
-    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
-    mbar_wait(bars.accum(), 0);
-    tc_fence_after();
-    constexpr int SLD = 36;                                   // fp32 staging row stride (words)
-    float* stg = reinterpret_cast<float*>(sm) + warp * (32 * SLD);
-    uint32_t* stg16 = reinterpret_cast<uint32_t*>(stg);       // bf16 staging, 20 words per row
-    const int cr = lane & 7, cc = lane >> 3;                  // coalesced side: row, 16B chunk
+    constexpr int SLD = 36;
+    float* stg = reinterpret_cast<float*>(sm + NS * G_STAGE) + warp * (32 * SLD);
+    uint32_t* stg16 = reinterpret_cast<uint32_t*>(stg);
+    const int cr = lane & 7, cc = lane >> 3;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int row0 = (tile / p.n_blocks) * TC_BM;
+      const int n0 = (tile % p.n_blocks) * D;
+      const int rows_valid = min(TC_BM, p.M - row0);
+      const int buf = it & 1;
+      const int r = warp * 32 + lane;
+      const bool valid = r < rows_valid;
+      const long long m = row0 + r;
+      const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * D;
 
-    // rows [warp*32, +32) x cols [c0, c0+32) of an fp32 matrix -> this thread's row in t[]
-    auto load_rows = [&](auto rowptr, int c0, float (&t)[32]) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int rr = cr + 8 * i;
-        const bool ok = warp * 32 + rr < rows_valid;
-        const float* g = rowptr((long long)row0 + warp * 32 + rr) + c0;
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          const int ch = cc + 4 * hh;
-          float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ok) v4 = __ldg(reinterpret_cast<const float4*>(g) + ch);
-          *reinterpret_cast<float4*>(stg + rr * SLD + ch * 4) = v4;
-        }
-      }
-      __syncwarp();
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 v4 = *reinterpret_cast<const float4*>(stg + lane * SLD + 4 * q);
-        t[4 * q + 0] = v4.x; t[4 * q + 1] = v4.y; t[4 * q + 2] = v4.z; t[4 * q + 3] = v4.w;
-      }
-      __syncwarp();
-    };
-
-    float dsum = 0.f;
-    auto finalize = [&](int b, float (&v)[32]) {
-      const int c0 = n0 + b * 32;
-      if (e.film) {
-        float sc[32], sh[32];
-        ldg_row32(e.film + c0, sc);
-        ldg_row32(e.film + D + c0, sh);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = v[i] * (1.0f + sc[i]) + sh[i];
-      }
-      if (e.dot_w) {
-        float w[32];
-        ldg_row32(e.dot_w + c0, w);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) dsum = fmaf(v[i], w[i], dsum);
-      }
-      if (e.out_f32) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<float4*>(stg + lane * SLD + 4 * q) =
-              make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        __syncwarp();
+      auto issue_rows = [&](auto rowptr, int c0, float4 (&pre)[8]) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int rr = cr + 8 * i;
-          if (warp * 32 + rr < rows_valid) {
-            float* g = e.out_f32 + ((long long)row0 + warp * 32 + rr) * e.ldo32 + c0;
+          const bool ok = warp * 32 + rr < rows_valid;
+          const float* g = rowptr((long long)row0 + warp * 32 + rr) + c0;
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              const int ch = cc + 4 * hh;
-              reinterpret_cast<float4*>(g)[ch] =
-                  *reinterpret_cast<const float4*>(stg + rr * SLD + ch * 4);
+          for (int hh = 0; hh < 2; ++hh) {
+            pre[i * 2 + hh] = ok ? __ldg(reinterpret_cast<const float4*>(g) + cc + 4 * hh)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      };
+      auto commit_rows = [&](const float4 (&pre)[8], float (&t)[32]) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh)
+            *reinterpret_cast<float4*>(stg + (cr + 8 * i) * SLD + (cc + 4 * hh) * 4) = pre[i * 2 + hh];
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 v4 = *reinterpret_cast<const float4*>(stg + lane * SLD + 4 * q);
+          t[4 * q + 0] = v4.x; t[4 * q + 1] = v4.y; t[4 * q + 2] = v4.z; t[4 * q + 3] = v4.w;
+        }
+        __syncwarp();
+      };
+
+      float dsum = 0.f;
+      auto finalize = [&](int b, float (&v)[32]) {
+        const int c0 = n0 + b * 32;
+        if (e.film) {
+          float sc[32], sh[32];
+          lds_row32(par + G_PAR_FILM + c0, sc);
+          lds_row32(par + G_PAR_FILM + D + c0, sh);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = v[i] * (1.0f + sc[i]) + sh[i];
+        }
+        if (e.dot_w) {
+          float w[32];
+          lds_row32(par + G_PAR_DOTW + c0, w);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) dsum = fmaf(v[i], w[i], dsum);
+        }
+        if (e.out_f32) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(stg + lane * SLD + 4 * q) =
+                make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = cr + 8 * i;
+            if (warp * 32 + rr < rows_valid) {
+              float* g = e.out_f32 + ((long long)row0 + warp * 32 + rr) * e.ldo32 + c0;
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                const int ch = cc + 4 * hh;
+                reinterpret_cast<float4*>(g)[ch] =
+                    *reinterpret_cast<const float4*>(stg + rr * SLD + ch * 4);
+              }
             }
           }
+          __syncwarp();
         }
-        __syncwarp();
-      }
-      if (e.out_bf16) {
+        if (e.out_bf16) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * q + 0], v[8 * q + 1]);
-          __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]);
-          __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * q + 6], v[8 * q + 7]);
-          uint4 u;
-          u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-          u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-          *reinterpret_cast<uint4*>(stg16 + lane * 20 + 4 * q) = u;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int rr = cr + 8 * i;
-          if (warp * 32 + rr < rows_valid) {
-            __nv_bfloat16* g = e.out_bf16 + ((long long)row0 + warp * 32 + rr) * e.ldo16 + c0;
-            reinterpret_cast<uint4*>(g)[cc] = *reinterpret_cast<const uint4*>(stg16 + rr * 20 + cc * 4);
+          for (int q = 0; q < 4; ++q) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * q + 0], v[8 * q + 1]);
+            __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]);
+            __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * q + 6], v[8 * q + 7]);
+            uint4 u;
+            u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+            u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(stg16 + lane * 20 + 4 * q) = u;
           }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = cr + 8 * i;
+            if (warp * 32 + rr < rows_valid) {
+              __nv_bfloat16* g = e.out_bf16 + ((long long)row0 + warp * 32 + rr) * e.ldo16 + c0;
+              reinterpret_cast<uint4*>(g)[cc] =
+                  *reinterpret_cast<const uint4*>(stg16 + rr * 20 + cc * 4);
+            }
+          }
+          __syncwarp();
         }
-        __syncwarp();
-      }
-    };
-    auto ld_block = [&](int b, float (&v)[32]) {
-      uint32_t u[32];
-      tmem_ld32(trow + b * 32, u);
-      tmem_ld_wait();
+      };
+      auto ld_block = [&](int b, float (&v)[32]) {
+        uint32_t u[32];
+        tmem_ld32(trow + b * 32, u);
+        tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(u[i]);
-    };
-    auto st_block = [&](int b, const float (&v)[32]) {
-      uint32_t u[32];
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(u[i]);
+      };
+      auto st_block = [&](int b, const float (&v)[32]) {
+        uint32_t u[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) u[i] = __float_as_uint(v[i]);
-      tmem_st32(trow + b * 32, u);
-    };
+        for (int i = 0; i < 32; ++i) u[i] = __float_as_uint(v[i]);
+        tmem_st32(trow + b * 32, u);
+      };
+      const float* rbase = e.res;
+      const long long ldr = e.ldres;
+      auto res_ptr = [&](long long mm) { return rbase + mm * ldr; };
+      const float* vbase = e.rowvec;
+      const int rpg = e.rows_per_group;
+      auto vec_ptr = [&](long long mm) { return vbase + (mm / rpg) * D; };
 
-    // pass 1: bias, ReLU, residual (+ statistics of LN1)
-    float s1 = 0.f, q1 = 0.f, c1 = 0.f;
-#pragma unroll 1
-    for (int b = 0; b < 8; ++b) {
-      float v[32];
-      ld_block(b, v);
-      if (e.bias) {
-        float t[32];
-        ldg_row32(e.bias + n0 + b * 32, t);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] += t[i];
-      }
-      if (e.relu) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-      }
-      if (e.res) {
-        float t[32];
-        const float* rbase = e.res;
-        const long long ldr = e.ldres;
-        load_rows([&](long long mm) { return rbase + mm * ldr; }, n0 + b * 32, t);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] += t[i];
-      }
-      if (e.ln1_g) {
-        if (b == 0) c1 = v[0];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float d = v[i] - c1;
-          s1 += d;
-          q1 = fmaf(d, d, q1);
-        }
-        st_block(b, v);
-      } else {
-        finalize(b, v);
-      }
-    }
-    if (e.ln1_g) {
-      tmem_st_wait();
-      const float ms = s1 * (1.0f / D);
-      const float mean = c1 + ms;
-      const float rstd = 1.0f / sqrtf(fmaxf(q1 * (1.0f / D) - ms * ms, 0.f) + LN_EPS);
-      float s2 = 0.f, q2 = 0.f, c2 = 0.f;
+      if (threadIdx.x == 0) TL_STAMP(0, it, 0);
+      mbar_wait(tfull_bar(buf), (it >> 1) & 1);
+      tc_fence_after();
+      if (threadIdx.x == 0) TL_STAMP(1, it, 0);
+
+      // pass 1: bias, ReLU, residual (+ statistics of LN1)
+      float s1 = 0.f, q1 = 0.f, c1 = 0.f;
+      float4 pre[8];
+      if (e.res) issue_rows(res_ptr, n0, pre);
 #pragma unroll 1
       for (int b = 0; b < 8; ++b) {
-        float v[32], g[32], bb[32];
+        float v[32];
+        if (threadIdx.x == 0 && it == 1) TL_STAMP(3, 8 + b * 4, 0);
         ld_block(b, v);
-        ldg_row32(e.ln1_g + b * 32, g);
-        ldg_row32(e.ln1_b + b * 32, bb);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = (v[i] - mean) * rstd * g[i] + bb[i];
-        if (e.rowvec) {
+        if (threadIdx.x == 0 && it == 1) TL_STAMP(3, 8 + b * 4, 1);
+        if (e.bias) {
           float t[32];
-          const float* vbase = e.rowvec;
-          const int rpg = e.rows_per_group;
-          load_rows([&](long long mm) { return vbase + (mm / rpg) * D; }, b * 32, t);
+          lds_row32(par + G_PAR_BIAS + n0 + b * 32, t);
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] += t[i];
         }
-        if (e.ln2_g) {
-          if (b == 0) c2 = v[0];
+        if (e.relu) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (e.res) {
+          float t[32];
+          if (threadIdx.x == 0 && it == 1) TL_STAMP(3, 9 + b * 4, 0);
+          commit_rows(pre, t);
+          if (threadIdx.x == 0 && it == 1) TL_STAMP(3, 9 + b * 4, 1);
+          if (b < 7) issue_rows(res_ptr, n0 + (b + 1) * 32, pre);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += t[i];
+        }
+        if (threadIdx.x == 0 && it == 1) TL_STAMP(3, 10 + b * 4, 0);
+        if (e.ln1_g) {
+          if (b == 0) c1 = v[0];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const float d = v[i] - c2;
-            s2 += d;
-            q2 = fmaf(d, d, q2);
+            const float d = v[i] - c1;
+            s1 += d;
+            q1 = fmaf(d, d, q1);
           }
           st_block(b, v);
         } else {
           finalize(b, v);
         }
+        if (threadIdx.x == 0 && it == 1) TL_STAMP(3, 10 + b * 4, 1);
       }
-      if (e.ln2_g) {
+      if (e.ln1_g) {
         tmem_st_wait();
-        const float ms2 = s2 * (1.0f / D);
-        const float mean2 = c2 + ms2;
-        const float rstd2 = 1.0f / sqrtf(fmaxf(q2 * (1.0f / D) - ms2 * ms2, 0.f) + LN_EPS);
+        const float ms = s1 * (1.0f / D);
+        const float mean = c1 + ms;
+        const float rstd = 1.0f / sqrtf(fmaxf(q1 * (1.0f / D) - ms * ms, 0.f) + LN_EPS);
+        float s2 = 0.f, q2 = 0.f, c2 = 0.f;
+        if (e.rowvec) issue_rows(vec_ptr, 0, pre);
 #pragma unroll 1
         for (int b = 0; b < 8; ++b) {
           float v[32], g[32], bb[32];
           ld_block(b, v);
-          ldg_row32(e.ln2_g + b * 32, g);
-          ldg_row32(e.ln2_b + b * 32, bb);
+          lds_row32(par + G_PAR_LN1G + b * 32, g);
+          lds_row32(par + G_PAR_LN1B + b * 32, bb);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = (v[i] - mean2) * rstd2 * g[i] + bb[i];
-          finalize(b, v);
+          for (int i = 0; i < 32; ++i) v[i] = (v[i] - mean) * rstd * g[i] + bb[i];
+          if (e.rowvec) {
+            float t[32];
+            commit_rows(pre, t);
+            if (b < 7) issue_rows(vec_ptr, (b + 1) * 32, pre);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += t[i];
+          }
+          if (e.ln2_g) {
+            if (b == 0) c2 = v[0];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float d = v[i] - c2;
+              s2 += d;
+              q2 = fmaf(d, d, q2);
+            }
+            st_block(b, v);
+          } else {
+            finalize(b, v);
+          }
+        }
+        if (e.ln2_g) {
+          tmem_st_wait();
+          const float ms2 = s2 * (1.0f / D);
+          const float mean2 = c2 + ms2;
+          const float rstd2 = 1.0f / sqrtf(fmaxf(q2 * (1.0f / D) - ms2 * ms2, 0.f) + LN_EPS);
+#pragma unroll 1
+          for (int b = 0; b < 8; ++b) {
+            float v[32], g[32], bb[32];
+            ld_block(b, v);
+            lds_row32(par + G_PAR_LN2G + b * 32, g);
+            lds_row32(par + G_PAR_LN2B + b * 32, bb);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = (v[i] - mean2) * rstd2 * g[i] + bb[i];
+            finalize(b, v);
+          }
         }
       }
+      if (e.dot_w && valid) e.dot_out[m] = dsum + e.dot_b[0];
+      // this accumulator buffer may be overwritten by the MMA warp
+      tc_fence_before();
+      mbar_arrive(tempty_bar(buf));
+      if (threadIdx.x == 0) TL_STAMP(1, it, 1);
     }
-    if (e.dot_w && valid) e.dot_out[m] = dsum + e.dot_b[0];
-  } else if (warp == 4) {
+  } else if (warp < 8) {
+    // ======================= A producers ===============================================
+    const int ptid = threadIdx.x - 128;
+    const int j = ptid & 7, rb = ptid >> 3;
+    const __nv_bfloat16* Ab = reinterpret_cast<const __nv_bfloat16*>(p.A);
+    const uint32_t dst_base = rb * 128 + ((j ^ (rb & 7)) << 4);
+    int g = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int row0 = (tile / p.n_blocks) * TC_BM;
+      const int rows_valid = min(TC_BM, p.M - row0);
+      const __nv_bfloat16* src[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = rb + 16 * i;
+        src[i] = (r < rows_valid) ? (Ab + (long long)(row0 + r) * p.lda + j * 8) : nullptr;
+      }
+      for (int kc = 0; kc < KC; ++kc, ++g) {
+        const int s = g % NS;
+        mbar_wait(empty_bar(s), ((g / NS) & 1) ^ 1);
+        const uint32_t a_dst = sm_addr + s * G_STAGE + dst_base;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const bool ok = src[i] != nullptr;
+          cp_async16(a_dst + i * 2048, ok ? (const void*)(src[i] + kc * TC_BK) : (const void*)Ab,
+                     ok ? 16u : 0u);
+        }
+        cp_async_mbar_arrive_noinc(full_bar(s));
+      }
+    }
+  } else if (warp == 8) {
+    // ======================= TMA producer (weights) ====================================
     if (lane == 0) {
-      for (int kc = 0; kc < KC; ++kc) {
-        const int s = kc % NS;
-        mbar_wait(bars.empty(s), ((kc / NS) & 1) ^ 1);
-        mbar_arrive_expect_tx(bars.full(s), TC_B_TILE);
-        tma_load_2d(sm_addr + s * G_STAGE + TC_A_TILE, &wmap, bars.full(s), kc * TC_BK, n0);
+      int g = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int n0 = (tile % p.n_blocks) * D;
+        for (int kc = 0; kc < KC; ++kc, ++g) {
+          const int s = g % NS;
+          mbar_wait(empty_bar(s), ((g / NS) & 1) ^ 1);
+          mbar_arrive_expect_tx(full_bar(s), TC_B_TILE);
+          tma_load_2d(sm_addr + s * G_STAGE + TC_A_TILE, &wmap, full_bar(s), kc * TC_BK, n0);
+        }
       }
     }
     __syncwarp();
   } else {
+    // ======================= MMA issuer ================================================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16_m128_n256();
-      for (int kc = 0; kc < KC; ++kc) {
-        const int s = kc % NS;
-        mbar_wait(bars.full(s), (kc / NS) & 1);
+      int g = 0, it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(tempty_bar(buf), ((it >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t a_stage = sm_addr + s * G_STAGE;
-        mma_chunk<1>(a_stage, a_stage + TC_A_TILE, tmem_base, 1, kc == 0, idesc, bars.empty(s));
+        TL_STAMP(2, it, 0);
+        for (int kc = 0; kc < KC; ++kc, ++g) {
+          const int s = g % NS;
+          mbar_wait(full_bar(s), (g / NS) & 1);
+          if (kc == 0) TL_STAMP(3, it, 0);
+          tc_fence_after();
+          const uint32_t a_stage = sm_addr + s * G_STAGE;
+          mma_chunk<1>(a_stage, a_stage + TC_A_TILE, tmem_base + buf * D, 1, kc == 0, idesc,
+                       empty_bar(s));
+        }
+        umma_commit(tfull_bar(buf));
+        TL_STAMP(2, it, 1);
       }
-      umma_commit(bars.accum());
     }
     __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc<D>(tmem_base);
+  if (warp == 9) tmem_dealloc<2 * D>(tmem_base);
 }
 
 // ===================================================================================
@@ -525,14 +623,7 @@ tc_gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap) {
 // ===================================================================================
 struct EntPair { int slot; float w; };
 
-#ifdef DDH_TIMELINE
-#define TL_STAMP(role, idx, which)                                                        \
-  do {                                                                                    \
-    if (p.dbg && blockIdx.x == 0 && (idx) < 40) p.dbg[((role)*40 + (idx)) * 2 + (which)] = clock64(); \
-  } while (0)
-#else
-#define TL_STAMP(role, idx, which) do { } while (0)
-#endif
+
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_conv_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap) {
@@ -804,9 +895,18 @@ int tc_engine_init() {
   return (int)e;
 }
 
-void launch_tc_gemm(const GemmParams& p, const CUtensorMap& wmap, int n_total, cudaStream_t st) {
-  dim3 grid((p.M + TC_BM - 1) / TC_BM, n_total / D);
-  tc_gemm_kernel<<<grid, TC_THREADS, G_SMEM, st>>>(p, wmap);
+void launch_tc_gemm(const GemmParams& p0, const CUtensorMap& wmap, int n_total, cudaStream_t st) {
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  GemmParams p = p0;
+  p.n_blocks = n_total / D;
+  const int n_tiles = ((p.M + TC_BM - 1) / TC_BM) * p.n_blocks;
+  tc_gemm_kernel<<<n_tiles < num_sms ? n_tiles : num_sms, G_THREADS, G_SMEM, st>>>(p, wmap);
 }
 
 int tc_conv_smem_bytes(int A, int ent_per_anchor) {
