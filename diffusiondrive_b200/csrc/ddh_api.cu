@@ -117,6 +117,10 @@ struct ddh_handle {
   std::vector<std::pair<int, int>> ev_spans;   // (stage id, index of the begin event)
   int ev_used = 0;
   int* conv_rows = nullptr;                    // [S*L] unique value_proj rows per conv launch
+  unsigned long long* need_rows = nullptr;     // [B] BEV rows (+halo) the coming conv call reads
+  unsigned long long* done_rows = nullptr;     // [B] BEV rows already converted to NHWC
+  int lazy_layout = 1;                         // convert BEV rows on demand (H <= 64, NCHW input)
+  bool profiling_eager = false;
   long long* dbg = nullptr;                    // timeline stamps (DDH_TIMELINE builds)
   int tl_gemm = -1;                            // env DDH_TIMELINE_GEMM=<launch index>: stamp that dense GEMM
   // scene-chunk concurrency (ddh_set_concurrency)
@@ -323,6 +327,8 @@ int ensure_ws(ddh_handle* h, int B) {
   WS(h->upix, (size_t)B * h->rcap);
   WS(h->nuniq, B);
   WS(h->conv_rows, s.num_layers * s.num_steps);
+  WS(h->need_rows, B);
+  WS(h->done_rows, B);
   WS(h->dbg, 4 * 40 * 2);
   WS(h->ent_slot, M * s.num_poses * 4);
   WS(h->ent_w, M * s.num_poses * 4);
@@ -362,6 +368,7 @@ void register_taps(ddh_handle* h, int B) {
   t["upix"] = {h->upix, (size_t)B * h->rcap * 4};
   t["nuniq"] = {h->nuniq, (size_t)B * 4};
   t["dbg"] = {h->dbg, (size_t)4 * 40 * 2 * 8};
+  t["done_rows"] = {h->done_rows, (size_t)B * 8};
   t["conv_rows"] = {h->conv_rows, (size_t)s.num_layers * s.num_steps * 4};
   t["ent_slot"] = {h->ent_slot, M * s.num_poses * 4 * 4};
   t["ent_w"] = {h->ent_w, M * s.num_poses * 4 * 4};
@@ -427,6 +434,7 @@ int ddh_create(const ddh_shape* s, ddh_handle** out) {
   ddh_handle* h = new ddh_handle();
   h->shp = *s;
   if (const char* e = getenv("DDH_TIMELINE_GEMM")) h->tl_gemm = atoi(e);
+  if (const char* e = getenv("DDH_LAZY_LAYOUT")) h->lazy_layout = atoi(e);
   default_alphas_cumprod(h->ac);
   make_roll(s->num_steps, h->roll);
   *out = h;
@@ -640,12 +648,20 @@ int forward_range(ddh_handle* h, const float* ego, const float* agents, const vo
     out_traj = adv(out_traj, z * P * 3); out_modes = adv(out_modes, z * A * P * 3);
     out_scores = adv(out_scores, z * A); out_mode_idx = adv(out_mode_idx, z);
   }
-  // ---- BEV map -> NHWC in the engine's operand type
+  // ---- BEV map -> NHWC in the engine's operand type.  NCHW input with H <= 64: rows are
+  // converted on demand before each conv call (only rows a conv will read); otherwise up front.
   const void* bevn = bev;
+  const bool lazy = bev_layout == DDH_NCHW && h->lazy_layout && s.bev_h <= 64 && !h->profiling_eager;
+  unsigned long long* need_rows = lazy ? h->need_rows + s0 : nullptr;
+  unsigned long long* done_rows = lazy ? h->done_rows + s0 : nullptr;
   { ProfSpan ps(h, ST_BEV, st);
   if (bev_layout == DDH_NCHW) {
-    launch_bev_to_nhwc(bev, bev_dtype, v.bev_nhwc, want_dtype, B, s.bev_channels, HW, st);
-    h->launches++;
+    if (lazy) {
+      CU_TRY(h, cudaMemsetAsync(done_rows, 0, (size_t)B * 8, st));
+    } else {
+      launch_bev_to_nhwc(bev, bev_dtype, v.bev_nhwc, want_dtype, B, s.bev_channels, HW, st);
+      h->launches++;
+    }
     bevn = v.bev_nhwc;
   } else if (bev_dtype != want_dtype) {
     const size_t n = (size_t)B * HW * s.bev_channels;
@@ -709,7 +725,14 @@ int forward_range(ddh_handle* h, const float* ego, const float* agents, const vo
       // -- cross_bev_attention (modules/blocks.py:88-129)
       { ProfSpan ps(h, ST_PLAN, st);
       launch_plan(v.q0_32, pl.attw_w, pl.attw_b, v.pts, v.upix, v.nuniq, v.ent_slot,
-                  v.ent_w, h->conv_rows + si * L + l, B, A, P, s.bev_h, s.bev_w, h->rcap, oc, st); }
+                  v.ent_w, h->conv_rows + si * L + l, need_rows, B, A, P, s.bev_h, s.bev_w,
+                  h->rcap, oc, st); }
+      if (lazy) {
+        ProfSpan ps(h, ST_BEV, st);
+        launch_bev_rows_to_nhwc(bev, bev_dtype, v.bev_nhwc, want_dtype, need_rows, done_rows, B,
+                                s.bev_channels, s.bev_h, s.bev_w, st);
+        h->launches++;
+      }
       {
         ProfSpan ps(h, ST_CONV, st);
         GemmParams gp;

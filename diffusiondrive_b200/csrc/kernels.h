@@ -30,8 +30,12 @@ void launch_init_img(const float* anchors, const float* noise, float* img, int B
 void launch_embed(const float* img, float* pts, float* emb32, __nv_bfloat16* emb16, int M, int P,
                   const float* dim_t_dev, cudaStream_t st);
 void launch_plan(const float* q0, const float* attw_w, const float* attw_b, const float* pts,
-                 int* upix, int* nuniq, int* ent_slot, float* ent_w, int* rows_total, int B, int A,
-                 int P, int H, int W, int rcap, OdoConsts oc, cudaStream_t st);
+                 int* upix, int* nuniq, int* ent_slot, float* ent_w, int* rows_total,
+                 unsigned long long* need_rows, int B, int A, int P, int H, int W, int rcap,
+                 OdoConsts oc, cudaStream_t st);
+void launch_bev_rows_to_nhwc(const void* src, int src_dtype, void* dst, int dst_dtype,
+                             const unsigned long long* need, unsigned long long* done, int B, int C,
+                             int H, int W, cudaStream_t st);
 void launch_combine(const float* V, const int* ent_slot, const float* ent_w, float* s32,
                     __nv_bfloat16* s16, int B, int A, int P, int rcap, cudaStream_t st);
 void launch_attn_core(const float* qh, const float* kv, float* o32, __nv_bfloat16* o16, int B,

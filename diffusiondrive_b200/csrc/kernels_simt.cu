@@ -253,6 +253,78 @@ static void bev_launch(const void* src, void* dst, int B, int C, int HW, cudaStr
                                                           reinterpret_cast<TO*>(dst), C, HW);
 }
 
+// On-demand variant: one CTA per scene converts only the BEV rows the coming conv call reads
+// (need_rows, written by plan_kernel) that have not been converted yet (done_rows), 32 pixels x
+// 256 channels per tile.  Trajectories only ever sample the forward part of the map, so ~45 %
+// of the rows are never touched.  H <= 64.
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) bev_rows_to_nhwc_kernel(
+    const TI* __restrict__ src, TO* __restrict__ dst, const unsigned long long* __restrict__ need_rows,
+    unsigned long long* __restrict__ done_rows, int C, int H, int W) {
+  constexpr int PXT = 32;
+  constexpr int LDW = (sizeof(TO) == 2) ? 129 : 257;
+  extern __shared__ __align__(16) uint32_t tile_u32[];
+  TO* tile = reinterpret_cast<TO*>(tile_u32);
+  constexpr int LDE = LDW * 4 / sizeof(TO);
+  constexpr int G = PXT / 4, CL = 256 / G;
+  const int b = blockIdx.x;
+  const unsigned long long done = done_rows[b];
+  unsigned long long todo = need_rows[b] & ~done;
+  if (!todo) return;
+  const int tid = threadIdx.x, px4 = tid % G, cl = tid / G;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int HW = H * W;
+  constexpr int WORDS = 256 * sizeof(TO) / 4;
+  unsigned long long rest = todo;
+  while (rest) {
+    const int y = __ffsll((long long)rest) - 1;
+    rest &= rest - 1;
+    for (int x0 = 0; x0 < W; x0 += PXT) {
+      const int px0 = y * W + x0;
+      const TI* s = src + (size_t)b * C * HW + px0 + px4 * 4;
+      float4 v[256 / CL];
+#pragma unroll
+      for (int i = 0; i < 256 / CL; ++i) v[i] = ld4<TI>(s + (size_t)(i * CL + cl) * HW);
+      __syncthreads();   // previous tile fully written out
+#pragma unroll
+      for (int i = 0; i < 256 / CL; ++i) {
+        const int c = i * CL + cl;
+        tile[(px4 * 4 + 0) * LDE + c] = (TO)v[i].x;
+        tile[(px4 * 4 + 1) * LDE + c] = (TO)v[i].y;
+        tile[(px4 * 4 + 2) * LDE + c] = (TO)v[i].z;
+        tile[(px4 * 4 + 3) * LDE + c] = (TO)v[i].w;
+      }
+      __syncthreads();
+      uint32_t* d = reinterpret_cast<uint32_t*>(dst + ((size_t)b * HW + px0) * C);
+      for (int px = warp; px < PXT; px += 8) {
+#pragma unroll
+        for (int w = lane; w < WORDS; w += 32) d[(size_t)px * WORDS + w] = tile_u32[px * LDW + w];
+      }
+    }
+  }
+  if (tid == 0) done_rows[b] = done | todo;
+}
+
+template <typename TI, typename TO>
+static void bev_rows_launch(const void* src, void* dst, const unsigned long long* need,
+                            unsigned long long* done, int B, int C, int H, int W, cudaStream_t st) {
+  constexpr int LDW = (sizeof(TO) == 2) ? 129 : 257;
+  const int smem = 32 * LDW * 4;
+  bev_rows_to_nhwc_kernel<TI, TO><<<B, 256, smem, st>>>(
+      reinterpret_cast<const TI*>(src), reinterpret_cast<TO*>(dst), need, done, C, H, W);
+}
+
+void launch_bev_rows_to_nhwc(const void* src, int src_dtype, void* dst, int dst_dtype,
+                             const unsigned long long* need, unsigned long long* done, int B, int C,
+                             int H, int W, cudaStream_t st) {
+  if (src_dtype == 0 && dst_dtype == 0) bev_rows_launch<float, float>(src, dst, need, done, B, C, H, W, st);
+  else if (src_dtype == 0 && dst_dtype == 1)
+    bev_rows_launch<float, __nv_bfloat16>(src, dst, need, done, B, C, H, W, st);
+  else if (src_dtype == 1 && dst_dtype == 1)
+    bev_rows_launch<__nv_bfloat16, __nv_bfloat16>(src, dst, need, done, B, C, H, W, st);
+  else bev_rows_launch<__nv_bfloat16, float>(src, dst, need, done, B, C, H, W, st);
+}
+
 void launch_bev_to_nhwc(const void* src, int src_dtype, void* dst, int dst_dtype, int B, int C,
                         int HW, cudaStream_t st) {
   if (src_dtype == 0 && dst_dtype == 0) bev_launch<float, float>(src, dst, B, C, HW, st);
@@ -416,15 +488,19 @@ __global__ void __launch_bounds__(256) plan_kernel(const float* __restrict__ q0,
                                                    int* __restrict__ upix, int* __restrict__ nuniq,
                                                    int* __restrict__ ent_slot,
                                                    float* __restrict__ ent_w,
-                                                   int* __restrict__ rows_total, int A, int P,
-                                                   int H, int W, int rcap, OdoConsts oc) {
+                                                   int* __restrict__ rows_total,
+                                                   unsigned long long* __restrict__ need_rows,
+                                                   int A, int P, int H, int W, int rcap,
+                                                   OdoConsts oc) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int HW = H * W;
   unsigned short* table = reinterpret_cast<unsigned short*>(smraw);        // [HW]
   float* aw = reinterpret_cast<float*>(smraw + ((HW * 2 + 15) / 16) * 16);  // [A*P]
   __shared__ int warp_tot[8];
   __shared__ int total_s;
+  __shared__ unsigned long long need_s;
   const int scene = blockIdx.x;
+  if (threadIdx.x == 0) need_s = 0ull;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   for (int i = tid; i < HW; i += 256) table[i] = 0;
@@ -482,18 +558,22 @@ __global__ void __launch_bounds__(256) plan_kernel(const float* __restrict__ q0,
   int base = incl - cnt;
   for (int w = 0; w < warp; ++w) base += warp_tot[w];
   if (tid == 255) total_s = base + cnt;
+  unsigned long long need = 0ull;   // rows y-1..y+1 of every unique pixel (H <= 64 only)
   for (int i = beg; i < end; ++i) {
     if (table[i]) {
       const int yy = i / W;
       upix[(size_t)scene * rcap + base] = (yy << 16) | (i - yy * W);   // packed (y, x)
       table[i] = (unsigned short)(base + 1);
       ++base;
+      need |= (yy > 0) ? (7ull << (yy - 1)) : 3ull;
     }
   }
+  if (need_rows && need) atomicOr(&need_s, need);
   __syncthreads();
   if (tid == 0) {
     nuniq[scene] = total_s;
     if (rows_total) atomicAdd(rows_total, total_s);
+    if (need_rows) need_rows[scene] = (H >= 64) ? need_s : (need_s & ((1ull << H) - 1ull));
   }
   // ---- entries
   for (int e = tid; e < AP; e += 256) {
@@ -515,8 +595,9 @@ __global__ void __launch_bounds__(256) plan_kernel(const float* __restrict__ q0,
   }
 }
 void launch_plan(const float* q0, const float* attw_w, const float* attw_b, const float* pts,
-                 int* upix, int* nuniq, int* ent_slot, float* ent_w, int* rows_total, int B, int A,
-                 int P, int H, int W, int rcap, OdoConsts oc, cudaStream_t st) {
+                 int* upix, int* nuniq, int* ent_slot, float* ent_w, int* rows_total,
+                 unsigned long long* need_rows, int B, int A, int P, int H, int W, int rcap,
+                 OdoConsts oc, cudaStream_t st) {
   const int smem = ((H * W * 2 + 15) / 16) * 16 + A * P * 4;
   static int cur = 0;
   if (smem > cur) {
@@ -524,7 +605,7 @@ void launch_plan(const float* q0, const float* attw_w, const float* attw_b, cons
     cur = smem;
   }
   plan_kernel<<<B, 256, smem, st>>>(q0, attw_w, attw_b, pts, upix, nuniq, ent_slot, ent_w,
-                                     rows_total, A, P, H, W, rcap, oc);
+                                     rows_total, need_rows, A, P, H, W, rcap, oc);
 }
 
 // ===================================================================================
