@@ -121,10 +121,11 @@ struct ddh_handle {
   unsigned long long* done_rows = nullptr;     // [B] BEV rows already converted to NHWC
   int lazy_layout = 1;                         // convert BEV rows on demand (H <= 64, NCHW input)
   bool profiling_eager = false;
+  bool debug_taps = false;                     // env DDH_DEBUG_TAPS=1: keep fp32 copies of x2/x3 in bf16 mode
   long long* dbg = nullptr;                    // timeline stamps (DDH_TIMELINE builds)
   int tl_gemm = -1;                            // env DDH_TIMELINE_GEMM=<launch index>: stamp that dense GEMM
   // scene-chunk concurrency (ddh_set_concurrency)
-  int chunks = 4;
+  int chunks = 1;
   int min_chunk_scenes = 512;
   cudaStream_t aux_stream = nullptr;
   std::vector<cudaEvent_t> sync_events;
@@ -435,6 +436,7 @@ int ddh_create(const ddh_shape* s, ddh_handle** out) {
   h->shp = *s;
   if (const char* e = getenv("DDH_TIMELINE_GEMM")) h->tl_gemm = atoi(e);
   if (const char* e = getenv("DDH_LAZY_LAYOUT")) h->lazy_layout = atoi(e);
+  if (const char* e = getenv("DDH_DEBUG_TAPS")) h->debug_taps = atoi(e) != 0;
   default_alphas_cumprod(h->ac);
   make_roll(s->num_steps, h->roll);
   *out = h;
@@ -782,7 +784,7 @@ int forward_range(ddh_handle* h, const float* ego, const float* agents, const vo
         e.ln1_g = pl.norm1_g; e.ln1_b = pl.norm1_b;
         e.rowvec = v.egov + (size_t)l * Btot * D; e.rows_per_group = A;
         e.ln2_g = pl.norm2_g; e.ln2_b = pl.norm2_b;
-        e.out_f32 = v.x2_32; e.ldo32 = D; e.out_bf16 = v.x2_16; e.ldo16 = D;
+        e.out_f32 = (bf && !h->debug_taps) ? nullptr : v.x2_32; e.ldo32 = D; e.out_bf16 = v.x2_16; e.ldo16 = D;
         run_gemm(h, pl.attn_out, v.o32, v.o16, D, M, e, st);
       }
       // -- FFN (no residual) + norm3 + time FiLM (:368-373)
@@ -794,7 +796,7 @@ int forward_range(ddh_handle* h, const float* ego, const float* agents, const vo
         RowEpi e2;
         e2.ln1_g = pl.norm3_g; e2.ln1_b = pl.norm3_b;
         e2.film = h->film + ((size_t)si * L + l) * 2 * D;
-        e2.out_f32 = v.x3_32; e2.ldo32 = D; e2.out_bf16 = v.x3_16; e2.ldo16 = D;
+        e2.out_f32 = (bf && !h->debug_taps) ? nullptr : v.x3_32; e2.ldo32 = D; e2.out_bf16 = v.x3_16; e2.ldo16 = D;
         run_gemm(h, pl.ffn2, v.h32, v.h16, F, M, e2, st);
       }
       // -- task_decoder (:244-256, 376-380); cls only where it is read (:631)

@@ -658,52 +658,115 @@ void launch_combine(const float* V, const int* ent_slot, const float* ent_w, flo
 // Agent cross-attention core (nn.MultiheadAttention, transfuser_model_v2.py:316-321,355-357)
 // after the Q projection and the hoisted K|V projection: per scene and head,
 // softmax(q*scale . K^T) . V with head_dim 32 and Na <= 32 keys.
-// One warp per (scene, head): lane j keeps key j in registers for the scores, lane c keeps
-// channel c of every value row for the output.  No shared memory.
+// One CTA per scene, one warp per head, one LANE per query: the scene's K|V rows sit in shared
+// memory and are read as warp-wide broadcasts, the query / score / output vectors live in
+// registers, so the inner loops are pure LDS.128 + FFMA (no shuffles).
 // ===================================================================================
-__global__ void __launch_bounds__(256) attn_core_kernel(const float* __restrict__ qh,
-                                                        const float* __restrict__ kv,
-                                                        float* __restrict__ o32,
-                                                        __nv_bfloat16* __restrict__ o16, int A,
-                                                        int Na, int heads) {
+__global__ void __launch_bounds__(256, 2) attn_core_kernel(const float* __restrict__ qh,
+                                                           const float* __restrict__ kv,
+                                                           float* __restrict__ o32,
+                                                           __nv_bfloat16* __restrict__ o16, int A,
+                                                           int Na, int heads) {
+  extern __shared__ __align__(16) float kv_s[];   // [Na][2*D]: K | V
   const int scene = blockIdx.x;
   const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
+    const float4* src = reinterpret_cast<const float4*>(kv + (size_t)scene * Na * 2 * D);
+    float4* dst = reinterpret_cast<float4*>(kv_s);
+    for (int i = threadIdx.x; i < Na * 2 * D / 4; i += 256) dst[i] = __ldg(src + i);
+  }
+  __syncthreads();
   if (h >= heads) return;
   const float scale = 0.17677669529663687f;  // 1/sqrt(32)
-  float kreg[32], vreg[32];
-  {
-    const float* kp = kv + ((size_t)scene * Na + min(lane, Na - 1)) * (2 * D) + h * 32;
+  for (int a0 = 0; a0 < A; a0 += 32) {
+    const int a = a0 + lane;
+    const bool act = a < A;
+    const size_t row = (size_t)scene * A + (act ? a : 0);
+    float q[32];
 #pragma unroll
     for (int c4 = 0; c4 < 8; ++c4) {
-      const float4 t = *reinterpret_cast<const float4*>(kp + c4 * 4);
-      kreg[c4 * 4 + 0] = t.x; kreg[c4 * 4 + 1] = t.y; kreg[c4 * 4 + 2] = t.z; kreg[c4 * 4 + 3] = t.w;
+      const float4 t = __ldg(reinterpret_cast<const float4*>(qh + row * D + h * 32) + c4);
+      q[4 * c4 + 0] = t.x * scale; q[4 * c4 + 1] = t.y * scale;
+      q[4 * c4 + 2] = t.z * scale; q[4 * c4 + 3] = t.w * scale;
     }
+    float s[32];
+    float mx = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      vreg[j] = (j < Na) ? kv[((size_t)scene * Na + j) * (2 * D) + D + h * 32 + lane] : 0.f;
-  }
-  for (int a = 0; a < A; ++a) {
-    const size_t row = (size_t)scene * A + a;
-    const float q = qh[row * D + h * 32 + lane] * scale;
-    float s = 0.f;
+    for (int j = 0; j < 32; ++j) {
+      s[j] = -INFINITY;
+      if (j < Na) {
+        const float4* kr = reinterpret_cast<const float4*>(kv_s + j * 2 * D + h * 32);
+        float acc = 0.f;
 #pragma unroll
-    for (int c = 0; c < 32; ++c) s = fmaf(__shfl_sync(0xffffffffu, q, c), kreg[c], s);
-    if (lane >= Na) s = -INFINITY;
-    float mx = s;
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 k4 = kr[c4];
+          acc = fmaf(q[4 * c4 + 0], k4.x, acc);
+          acc = fmaf(q[4 * c4 + 1], k4.y, acc);
+          acc = fmaf(q[4 * c4 + 2], k4.z, acc);
+          acc = fmaf(q[4 * c4 + 3], k4.w, acc);
+        }
+        s[j] = acc;
+        mx = fmaxf(mx, acc);
+      }
+    }
+    float den = 0.f;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    const float e = (lane < Na) ? expf(s - mx) : 0.f;
-    const float p = e / warp_sum(e);
-    float acc = 0.f;
+    for (int j = 0; j < 32; ++j) {
+      s[j] = (j < Na) ? expf(s[j] - mx) : 0.f;
+      den += s[j];
+    }
+    const float inv = 1.0f / den;
+    float o[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) acc = fmaf(__shfl_sync(0xffffffffu, p, j), vreg[j], acc);
-    if (o32) o32[row * D + h * 32 + lane] = acc;
-    if (o16) o16[row * D + h * 32 + lane] = __float2bfloat16_rn(acc);
+    for (int c = 0; c < 32; ++c) o[c] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j < Na) {
+        const float4* vr = reinterpret_cast<const float4*>(kv_s + j * 2 * D + D + h * 32);
+        const float pj = s[j] * inv;
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 v4 = vr[c4];
+          o[4 * c4 + 0] = fmaf(pj, v4.x, o[4 * c4 + 0]);
+          o[4 * c4 + 1] = fmaf(pj, v4.y, o[4 * c4 + 1]);
+          o[4 * c4 + 2] = fmaf(pj, v4.z, o[4 * c4 + 2]);
+          o[4 * c4 + 3] = fmaf(pj, v4.w, o[4 * c4 + 3]);
+        }
+      }
+    }
+    if (act) {
+      if (o32) {
+        float4* d = reinterpret_cast<float4*>(o32 + row * D + h * 32);
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4)
+          d[c4] = make_float4(o[4 * c4], o[4 * c4 + 1], o[4 * c4 + 2], o[4 * c4 + 3]);
+      }
+      if (o16) {
+        uint4* d = reinterpret_cast<uint4*>(o16 + row * D + h * 32);
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(o[8 * c8 + 0], o[8 * c8 + 1]);
+          __nv_bfloat162 h1 = __floats2bfloat162_rn(o[8 * c8 + 2], o[8 * c8 + 3]);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(o[8 * c8 + 4], o[8 * c8 + 5]);
+          __nv_bfloat162 h3 = __floats2bfloat162_rn(o[8 * c8 + 6], o[8 * c8 + 7]);
+          uint4 u;
+          u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+          u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+          d[c8] = u;
+        }
+      }
+    }
   }
 }
 void launch_attn_core(const float* qh, const float* kv, float* o32, __nv_bfloat16* o16, int B,
                       int A, int Na, int heads, cudaStream_t st) {
-  attn_core_kernel<<<B, 256, 0, st>>>(qh, kv, o32, o16, A, Na, heads);
+  const int smem = Na * 2 * D * 4;
+  static int cur = 0;
+  if (smem > cur) {
+    cudaFuncSetAttribute(attn_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cur = smem;
+  }
+  attn_core_kernel<<<B, 256, smem, st>>>(qh, kv, o32, o16, A, Na, heads);
 }
 
 // ===================================================================================

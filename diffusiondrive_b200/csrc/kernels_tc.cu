@@ -825,8 +825,9 @@ tc_conv_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap) {
             const float4 old = *reinterpret_cast<const float4*>(S32 + o);
             acc.x += old.x; acc.y += old.y; acc.z += old.z; acc.w += old.w;
           }
-          *reinterpret_cast<float4*>(S32 + o) = acc;
-          if (S16) {
+          if (pass + 1 < passes) {          // fp32 partial sums only between passes
+            *reinterpret_cast<float4*>(S32 + o) = acc;
+          } else if (S16) {                 // final value: the bf16 A operand of output_proj
             __nv_bfloat162 h0 = __floats2bfloat162_rn(acc.x, acc.y);
             __nv_bfloat162 h1 = __floats2bfloat162_rn(acc.z, acc.w);
             uint2 u2;

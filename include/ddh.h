@@ -187,8 +187,8 @@ DDH_API int ddh_last_launch_count(const ddh_handle *h);
  * into `chunks` contiguous scene blocks issued alternately on the caller's stream and one
  * internal stream (fork/join with events, CUDA-graph capturable), so that one block's HBM-bound
  * BEV layout pass overlaps another block's tensor-bound stages.  Results do not depend on the
- * setting (scenes are independent).  Default: 4 chunks, at least 512 scenes each; chunks = 1
- * issues everything on the caller's stream. */
+ * setting (scenes are independent).  Default: chunks = 1 (everything on the caller's stream);
+ * 2 chunks gain ~1 % at 4096 scenes on a B200. */
 DDH_API int ddh_set_concurrency(ddh_handle *h, int chunks, int min_chunk_scenes);
 
 /* Optional per-stage device timing: when on, ddh_forward brackets each stage with CUDA events

@@ -12,6 +12,8 @@ import time
 import numpy as np
 import torch
 
+os.environ.setdefault("DDH_DEBUG_TAPS", "1")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
