@@ -185,6 +185,8 @@ def run_ours(args):
         del ft
 
     head.reserve(B)
+    if args.chunks > 1:
+        head.set_concurrency(args.chunks, 256)
     head.frozen = False
     total = B * world
 
@@ -293,6 +295,8 @@ def run_ours(args):
     e2e = None
     Be = min(B, args.e2e_batch)
     try:
+        if args.quick:
+            raise RuntimeError("skipped (--quick)")
         h_ego = ego[:Be].cpu().pin_memory()
         h_agents = agents[:Be].cpu().pin_memory()
         h_bev = bev[:Be].cpu().pin_memory()
@@ -329,6 +333,8 @@ def run_ours(args):
     # ---- batch-1 latency (device-resident single scene), p50 over single calls
     lat = None
     try:
+        if args.quick:
+            raise RuntimeError("skipped (--quick)")
         e1s = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                for _ in range(args.latency_iters)]
         one = (ego[:1].clone(), agents[:1].clone(), bev[:1].clone())
@@ -353,7 +359,7 @@ def run_ours(args):
 
     # ---- CPU baseline (oracle port) on this box's host cores, rank 0 at N = 1 only
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.quick:
         rate, sec, threads = cpu_oracle_rate(args.ref_batch, 3, 1)
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{args.ref_batch} scenes x 3 timed forwards (+1 warm-up) of the oracle "
@@ -400,6 +406,9 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=16)
     ap.add_argument("--latency-iters", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true",
+                    help="timed region + stage profile only (for ncu launch lists)")
+    ap.add_argument("--chunks", type=int, default=1, help="scene-chunk concurrency of a forward")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

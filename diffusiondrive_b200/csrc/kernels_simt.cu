@@ -785,23 +785,50 @@ __global__ void __launch_bounds__(256) reg_finish_kernel(const float* __restrict
                                                          float* __restrict__ img,
                                                          float* __restrict__ modes, int M, int P,
                                                          int do_ddim, DdimCoef dc) {
-  const int m = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (m >= M) return;
-  const int lane = threadIdx.x & 31;
-  float r[8];
+  // 4 lanes per row (interleaved float4 columns), 8 rows per warp, 64 rows per CTA; the
+  // [24][256] head weights are read from shared memory as (4-address) broadcasts.
+  __shared__ __align__(16) float w_s[24 * D];
+  __shared__ float b_s[24];
+  for (int i = threadIdx.x; i < 24 * D / 4; i += 256)
+    reinterpret_cast<float4*>(w_s)[i] = __ldg(reinterpret_cast<const float4*>(w4) + i);
+  if (threadIdx.x < 24) b_s[threadIdx.x] = b4[threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int part = lane & 3;
+  const int m = blockIdx.x * 64 + warp * 8 + (lane >> 2);
+  const bool valid = m < M;
+  const float* row = r2 + (size_t)(valid ? m : 0) * D;
+  float acc[24];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) r[i] = r2[(size_t)m * D + lane + 32 * i];
-  const int n_out = 3 * P;  // 24
-  float mine = 0.f;
-  for (int o = 0; o < n_out; ++o) {
-    float s = 0.f;
+  for (int o = 0; o < 24; ++o) acc[o] = 0.f;
+#pragma unroll 4
+  for (int k = 0; k < 16; ++k) {
+    const int f = k * 4 + part;                       // float4 index within the row
+    const float4 r = __ldg(reinterpret_cast<const float4*>(row) + f);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s = fmaf(r[i], w4[(size_t)o * D + lane + 32 * i], s);
-    s = warp_sum(s) + b4[o];
-    if (lane == o) mine = s;
+    for (int o = 0; o < 24; ++o) {
+      const float4 w = reinterpret_cast<const float4*>(w_s + o * D)[f];
+      acc[o] = fmaf(r.x, w.x, acc[o]);
+      acc[o] = fmaf(r.y, w.y, acc[o]);
+      acc[o] = fmaf(r.z, w.z, acc[o]);
+      acc[o] = fmaf(r.w, w.w, acc[o]);
+    }
   }
-  if (lane < n_out) {
-    const int p = lane / 3, comp = lane - p * 3;
+#pragma unroll
+  for (int o = 0; o < 24; ++o) {
+    acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 1);
+    acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 2);
+  }
+  if (!valid) return;
+  // lane `part` finishes outputs part*6 .. part*6+5  (= poses 2*part, 2*part+1)
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    const int o = part * 6 + q;
+    float mine = 0.f;
+#pragma unroll
+    for (int oo = 0; oo < 24; ++oo) if (oo == o) mine = acc[oo];
+    mine += b_s[o];
+    const int p = o / 3, comp = o - p * 3;
     float out;
     if (comp < 2) {
       const size_t pi = ((size_t)m * P + p) * 2 + comp;
@@ -822,7 +849,7 @@ __global__ void __launch_bounds__(256) reg_finish_kernel(const float* __restrict
 }
 void launch_reg_finish(const float* r2, const float* w4, const float* b4, float* pts, float* img,
                        float* modes, int M, int P, int do_ddim, DdimCoef dc, cudaStream_t st) {
-  reg_finish_kernel<<<(M + 7) / 8, 256, 0, st>>>(r2, w4, b4, pts, img, modes, M, P, do_ddim, dc);
+  reg_finish_kernel<<<(M + 63) / 64, 256, 0, st>>>(r2, w4, b4, pts, img, modes, M, P, do_ddim, dc);
 }
 
 // mode = argmax(cls) (first maximum wins), trajectory = reg[b, mode]          (:637-640)

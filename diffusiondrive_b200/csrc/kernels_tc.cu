@@ -914,7 +914,16 @@ int tc_conv_smem_bytes(int A, int ent_per_anchor) {
   return C_PIPE + ((A * ent_per_anchor * 8 + 15) / 16) * 16 + D * 4 + TC_BAR_BYTES + 1024;
 }
 
-void launch_tc_conv(const GemmParams& p, const CUtensorMap& wmap, int B, cudaStream_t st) {
+void launch_tc_conv(const GemmParams& p0, const CUtensorMap& wmap, int B, cudaStream_t st) {
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  GemmParams p = p0;
+  p.M = num_sms;
   tc_conv_kernel<<<B, TC_THREADS, tc_conv_smem_bytes(p.n_anchor, p.ent_per_anchor), st>>>(p, wmap);
 }
 

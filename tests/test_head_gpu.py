@@ -202,6 +202,49 @@ def test_host_call_and_layouts_agree(precision):
             assert torch.equal(o3[k], dev[k]), k
 
 
+def test_execution_options_do_not_change_results():
+    """Scene-chunk concurrency (two streams) and stage profiling are pure scheduling choices;
+    on-demand vs eager BEV layout conversion reads the same pixels: results are bit-identical."""
+    B = 37
+    ft = synth.make_features(B)
+    nz = synth.make_noise(B).cuda()
+    args = (ft["ego_query"].cuda(), ft["agents_query"].cuda(), ft["bev_feature"].cuda())
+    for precision in ("fp32", "bf16"):
+        head, _ = _make_head(precision)
+        base = {k: v.clone() for k, v in head(*args, noise=nz).items()}
+        for chunks in (2, 3, 5):
+            head.set_concurrency(chunks, 1)
+            out = head(*args, noise=nz)
+            for k in base:
+                assert torch.equal(out[k], base[k]), (precision, chunks, k)
+        head.set_concurrency(1, 512)
+        head.set_profiling(True)
+        out = head(*args, noise=nz)
+        prof = head.stage_profile()
+        head.set_profiling(False)
+        for k in base:
+            assert torch.equal(out[k], base[k]), (precision, "profiling", k)
+        assert prof["conv"]["spans"] == 4 and prof["conv"]["ms"] > 0
+        assert sum(v["ms"] for v in prof.values()) > 0
+        # rows converted on demand: a strict subset of the map for forward-driving anchors
+        done = head.debug_tap("done_rows", np.uint64)[:B]
+        rows = np.array([bin(int(x)).count("1") for x in done])
+        assert (rows > 8).all() and (rows < 64).all()
+    os.environ["DDH_LAZY_LAYOUT"] = "0"
+    try:
+        for precision in ("fp32", "bf16"):
+            eager, _ = _make_head(precision)
+            lazy_ref, _ = _make_head(precision)
+            a = eager(*args, noise=nz)
+            os.environ["DDH_LAZY_LAYOUT"] = "1"
+            b = lazy_ref(*args, noise=nz)
+            os.environ["DDH_LAZY_LAYOUT"] = "0"
+            for k in a:
+                assert torch.equal(a[k], b[k]), (precision, "lazy-vs-eager", k)
+    finally:
+        os.environ.pop("DDH_LAZY_LAYOUT", None)
+
+
 def test_scene_independence_and_determinism_full_size():
     """Size-independent properties at BASELINE's full size (4096 scenes, bf16): a scene's plan
     does not depend on the batch it rides in nor on its position, and reruns are bit-identical."""
