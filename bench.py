@@ -47,7 +47,7 @@ def _peaks():
 
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -61,7 +61,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -73,7 +73,10 @@ class ClockSampler:
         self.thread = threading.Thread(target=pump, daemon=True)
         self.thread.start()
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Median SM clock / throttle reasons over the samples taken inside [t_begin, t_end]
+        (wall clock, time.time()); the sampler itself runs from before the warm-up."""
+        import datetime
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -86,16 +89,19 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-                for n, v in zip(names, r[3:7]):
+                ts = datetime.datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                if t_begin is not None and not (t_begin - 0.05 <= ts <= t_end + 0.05):
+                    continue
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for n, v in zip(names, r[4:8]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
             except Exception:
                 continue
         return {"sm_mhz": statistics.median(sm) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "sample_period_ms": 50}
 
 
 def cpu_oracle_rate(batch: int, reps: int, warm: int):
@@ -139,7 +145,7 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(args.real_stdout, line)
 
 
 def run_ours(args):
@@ -196,6 +202,8 @@ def run_ours(args):
             return gather_scenes(out["trajectory"], total), out
         return out["trajectory"], out
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         traj, out = step()
     torch.cuda.synchronize()
@@ -215,20 +223,20 @@ def run_ours(args):
                   "against": "live-reference golden (tests/golden/default_b256.npz)"}
 
     # ---- timed region: barrier + sync, K steps between CUDA events, max over ranks
-    sampler = ClockSampler(local_rank)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.time()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     torch.cuda.synchronize()
+    t_end = time.time()
     if world > 1:
         dist.barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_begin, t_end)
     elapsed_ms = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([elapsed_ms], device=dev)
@@ -388,16 +396,30 @@ def run_ours(args):
             "latency_b1": lat, "parity": parity,
             "stage_ms": {k: round(v["ms"], 4) for k, v in prof.items()},
         }
-        print(json.dumps(line), flush=True)
+        _emit(args.real_stdout, line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+def _claim_stdout() -> int:
+    """Keep stdout clean for the ONE JSON line: libraries (NCCL prints its version banner on
+    stdout) are sent to stderr; returns the fd of the real stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return real
+
+
+def _emit(real_stdout: int, line: dict) -> None:
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="scenes per GPU per step")
@@ -410,6 +432,7 @@ def main():
                     help="timed region + stage profile only (for ncu launch lists)")
     ap.add_argument("--chunks", type=int, default=1, help="scene-chunk concurrency of a forward")
     args = ap.parse_args()
+    args.real_stdout = _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
