@@ -361,7 +361,35 @@ def run_ours(args):
         dts = sorted(a.elapsed_time(b) * 1e3 for a, b in e1s)
         lat = {"p50_us": dts[len(dts) // 2], "p90_us": dts[int(len(dts) * 0.9)],
                "wall_p50_us": sorted(wall)[len(wall) // 2], "iters": len(dts),
-               "precision": precision, "launches": head.last_launch_count()}
+               "precision": precision, "launches": head.last_launch_count(),
+               "engine": "small-batch engine (kernels_lat.cu), stream launches"}
+        # the same call captured once into a CUDA graph and replayed (no host launch gaps)
+        try:
+            side = torch.cuda.Stream(device=dev)
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    head(*one, noise=n1)
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=side):
+                    gout = head(*one, noise=n1)
+            torch.cuda.synchronize()
+            for _ in range(5):
+                graph.replay()
+            torch.cuda.synchronize()
+            gd = []
+            for a, b in e1s:
+                a.record()
+                graph.replay()
+                b.record()
+                b.synchronize()
+                gd.append(a.elapsed_time(b) * 1e3)
+            gd.sort()
+            lat["graph_p50_us"] = gd[len(gd) // 2]
+            lat["graph_p90_us"] = gd[int(len(gd) * 0.9)]
+            del graph, gout
+        except Exception as gex:
+            lat["graph_error"] = repr(gex)
     except Exception as ex:
         lat = {"error": repr(ex)}
 

@@ -32,6 +32,7 @@ struct PackedLinear {
   float* wt32 = nullptr;          // [K][N] fp32 (SIMT engine)
   __nv_bfloat16* w16 = nullptr;   // [N][K] bf16 (tensor engine)
   CUtensorMap map;
+  CUtensorMap map64;              // conv only: 64-row box for the small-batch kernel
   float* bias = nullptr;          // [N]
   int N = 0, K = 0;
 };
@@ -109,6 +110,12 @@ struct ddh_handle {
   void* hs_bev = nullptr;
   long long* hs_idx = nullptr;
 
+  // small-batch latency engine (B <= kLatMaxB, bf16-packed weights): fp32 activations
+  int lat_enabled = 1;
+  std::vector<void*> owned_lat;
+  float *lt_emb = nullptr, *lt_e1 = nullptr, *lt_kv = nullptr, *lt_ego = nullptr, *lt_spart = nullptr,
+        *lt_x1 = nullptr, *lt_o = nullptr, *lt_y2 = nullptr, *lt_h = nullptr, *lt_y3 = nullptr,
+        *lt_r1 = nullptr, *lt_c1 = nullptr, *lt_r2 = nullptr, *lt_c2 = nullptr;
   std::map<std::string, std::pair<const void*, size_t>> taps;
   int launches = 0;
   // optional per-stage device timing (ddh_set_profiling)
@@ -215,7 +222,7 @@ void make_roll(int S, std::vector<int>& roll) {
   for (int i = 0; i < S; ++i) roll[S - 1 - i] = (int)nearbyint(i * ratio);
 }
 
-int make_wmap(ddh_handle* h, PackedLinear& L) {
+int make_wmap(ddh_handle* h, PackedLinear& L, int box_rows = 256) {
   if (!h->encode) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -226,9 +233,9 @@ int make_wmap(ddh_handle* h, PackedLinear& L) {
   }
   const cuuint64_t gdim[2] = {(cuuint64_t)L.K, (cuuint64_t)L.N};
   const cuuint64_t gstride[1] = {(cuuint64_t)L.K * 2};
-  const cuuint32_t box[2] = {64, 256};
+  const cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult r = h->encode(&L.map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, L.w16, gdim, gstride, box,
+  CUresult r = h->encode(box_rows == 256 ? &L.map : &L.map64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, L.w16, gdim, gstride, box,
                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -436,6 +443,7 @@ int ddh_create(const ddh_shape* s, ddh_handle** out) {
   h->shp = *s;
   if (const char* e = getenv("DDH_TIMELINE_GEMM")) h->tl_gemm = atoi(e);
   if (const char* e = getenv("DDH_LAZY_LAYOUT")) h->lazy_layout = atoi(e);
+  if (const char* e = getenv("DDH_LAT")) h->lat_enabled = atoi(e);
   if (const char* e = getenv("DDH_DEBUG_TAPS")) h->debug_taps = atoi(e) != 0;
   default_alphas_cumprod(h->ac);
   make_roll(s->num_steps, h->roll);
@@ -448,6 +456,7 @@ void ddh_destroy(ddh_handle* h) {
   free_all(h->owned_w);
   free_all(h->owned_ws);
   free_all(h->owned_host);
+  free_all(h->owned_lat);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   for (cudaEvent_t e : h->sync_events) cudaEventDestroy(e);
   if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
@@ -540,6 +549,7 @@ int ddh_pack_weights(ddh_handle* h, const ddh_weight_ptrs* w, int precision, voi
       TRY(dev_alloc(h, h->owned_w, &pl.conv.w16, (size_t)256 * pl.conv.K));
       launch_pack_conv_bf16(lw.bev_conv_w, pl.conv.w16, 256, s.bev_channels, st);
       TRY(make_wmap(h, pl.conv));
+      TRY(make_wmap(h, pl.conv, 64));
     }
     TRY(copy_vec(h, &pl.attw_w, lw.bev_attw_w, (size_t)P * D, st));
     TRY(copy_vec(h, &pl.attw_b, lw.bev_attw_b, P, st));
@@ -633,6 +643,163 @@ View make_view(const ddh_handle* h, int s0) {
 
 // forward_test (:578-641) for the `B` scenes starting at scene `s0` of a call of `Btot` scenes,
 // all launches on `st`.  `layout_done` (optional) is recorded right after the BEV layout pass.
+constexpr int kLatMaxB = 2;
+
+int ensure_lat_ws(ddh_handle* h) {
+  if (h->lt_emb) return DDH_OK;
+  const ddh_shape& s = h->shp;
+  const size_t M = (size_t)kLatMaxB * s.num_anchors, F = s.d_ffn, L = s.num_layers;
+  const size_t tiles = (h->rcap + 127) / 128;
+  auto& o = h->owned_lat;
+  int rc;
+#define LW(ptr, count) do { rc = dev_alloc(h, o, &(ptr), (size_t)(count)); if (rc) return rc; } while (0)
+  LW(h->lt_emb, M * 64 * s.num_poses); LW(h->lt_e1, M * D);
+  LW(h->lt_kv, L * kLatMaxB * s.num_agents * 2 * D); LW(h->lt_ego, L * kLatMaxB * D);
+  LW(h->lt_spart, tiles * M * D);
+  LW(h->lt_x1, M * D); LW(h->lt_o, M * D); LW(h->lt_y2, M * D); LW(h->lt_h, M * F);
+  LW(h->lt_y3, M * D); LW(h->lt_r1, M * D); LW(h->lt_c1, M * D); LW(h->lt_r2, M * D);
+  LW(h->lt_c2, M * D);
+#undef LW
+  return DDH_OK;
+}
+
+// forward_test for one or two scenes on the small-batch engine (kernels_lat.cu + lat_conv_kernel):
+// same algebra as forward_range, fp32 activations, LayerNorm applied by the consumer.
+int forward_small(ddh_handle* h, const float* ego, const float* agents, const void* bev,
+                  int bev_dtype, int bev_layout, const float* noise, float* out_traj,
+                  float* out_modes, float* out_scores, int64_t* out_mode_idx, int B,
+                  cudaStream_t st) {
+  int rc = ensure_lat_ws(h);
+  if (rc) return rc;
+  const ddh_shape& s = h->shp;
+  const int A = s.num_anchors, P = s.num_poses, Na = s.num_agents, L = s.num_layers, S = s.num_steps;
+  const int M = B * A, HW = s.bev_h * s.bev_w;
+  const void* bevn = bev;
+  const bool lazy = bev_layout == DDH_NCHW && h->lazy_layout && s.bev_h <= 64;
+  { ProfSpan ps(h, ST_BEV, st);
+  if (bev_layout == DDH_NCHW) {
+    if (lazy) {
+      CU_TRY(h, cudaMemsetAsync(h->done_rows, 0, (size_t)B * 8, st));
+    } else {
+      launch_bev_to_nhwc(bev, bev_dtype, h->bev_nhwc, DDH_BF16, B, s.bev_channels, HW, st);
+      h->launches++;
+    }
+    bevn = h->bev_nhwc;
+  } else if (bev_dtype != DDH_BF16) {
+    launch_cast_f32_bf16(reinterpret_cast<const float*>(bev),
+                         reinterpret_cast<__nv_bfloat16*>(h->bev_nhwc),
+                         (size_t)B * HW * s.bev_channels, st);
+    h->launches++;
+    bevn = h->bev_nhwc;
+  }
+  }
+  auto lin = [&](const PackedLinear& Lw, const float* Ain, int Mrows, float* out, int relu,
+                 const float* res) {
+    LatLinearArgs a;
+    a.A = Ain; a.M = Mrows; a.K = Lw.K; a.N = Lw.N; a.W = Lw.w16; a.bias = Lw.bias; a.relu = relu;
+    a.res = res; a.out = out; a.ldo = Lw.N;
+    return a;
+  };
+  { ProfSpan ps(h, ST_HOIST, st);
+  for (int l = 0; l < L; ++l) {
+    launch_lat_linear(lin(h->layers[l].kv, agents, B * Na, h->lt_kv + (size_t)l * kLatMaxB * Na * 2 * D, 0, nullptr), st);
+    launch_lat_linear(lin(h->layers[l].ego, ego, B, h->lt_ego + (size_t)l * kLatMaxB * D, 0, nullptr), st);
+    h->launches += 2;
+  }
+  }
+  const float ac_tr = h->ac[s.trunc_timestep];
+  { ProfSpan ps(h, ST_INIT, st);
+  launch_init_img(h->anchors, noise, h->img, B, A * P, sqrtf(ac_tr), sqrtf(1.0f - ac_tr), st);
+  h->launches++; }
+  float* modes = out_modes ? out_modes : h->modes_buf;
+  float* scores = out_scores ? out_scores : h->scores_buf;
+  OdoConsts oc{s.lidar_max_x, s.lidar_max_y};
+  const int part_stride = kLatMaxB * A * D;
+  for (int si = 0; si < S; ++si) {
+    { ProfSpan ps(h, ST_EMBED, st);
+    launch_embed(h->img, h->pts, h->lt_emb, nullptr, M, P, h->dim_t, st);
+    launch_lat_linear(lin(h->enc0, h->lt_emb, M, h->lt_e1, 1, nullptr), st);
+    LatLinearArgs a = lin(h->enc3, h->lt_e1, M, h->q0_32, 0, nullptr);
+    a.prologue = 1; a.ln1_g = h->enc_ln_g; a.ln1_b = h->enc_ln_b;
+    launch_lat_linear(a, st);
+    h->launches += 3; }
+    for (int l = 0; l < L; ++l) {
+      const PackedLayer& pl = h->layers[l];
+      const bool last_layer = (l == L - 1), last_step = (si == S - 1);
+      { ProfSpan ps(h, ST_PLAN, st);
+      launch_plan(h->q0_32, pl.attw_w, pl.attw_b, h->pts, h->upix, h->nuniq, h->ent_slot, h->ent_w,
+                  h->conv_rows + si * L + l, lazy ? h->need_rows : nullptr, h->done_rows, B, A, P,
+                  s.bev_h, s.bev_w, h->rcap, oc, st);
+      h->launches++; }
+      if (lazy) {
+        ProfSpan ps(h, ST_BEV, st);
+        launch_bev_rows_to_nhwc(bev, bev_dtype, h->bev_nhwc, DDH_BF16, h->need_rows, B,
+                                s.bev_channels, s.bev_h, s.bev_w, st);
+        h->launches++;
+      }
+      { ProfSpan ps(h, ST_CONV, st);
+      GemmParams gp;
+      gp.K = pl.conv.K;
+      gp.bev = bevn; gp.upix = h->upix; gp.nuniq = h->nuniq; gp.rcap = h->rcap;
+      gp.H = s.bev_h; gp.W_ = s.bev_w; gp.C = s.bev_channels;
+      gp.epi.bias = pl.conv.bias;
+      gp.ent_slot = h->ent_slot; gp.ent_w = h->ent_w; gp.n_anchor = A; gp.ent_per_anchor = P * 4;
+      launch_lat_conv(gp, pl.conv.map64, h->lt_spart, part_stride, B, st);
+      h->launches++; }
+      { ProfSpan ps(h, ST_GEMM, st);
+      LatLinearArgs a = lin(pl.bev_out, h->lt_spart, M, h->lt_x1, 0, h->q0_32);
+      a.prologue = 4; a.nuniq = h->nuniq; a.rows_per_group = A; a.part_stride = part_stride;
+      launch_lat_linear(a, st);
+      h->launches++; }
+      { ProfSpan ps(h, ST_ATTN, st);
+      launch_lat_qattn(h->lt_x1, pl.q.w16, pl.q.bias, h->lt_kv + (size_t)l * kLatMaxB * Na * 2 * D,
+                       h->lt_o, B, A, Na, s.num_heads, st);
+      h->launches++; }
+      { ProfSpan ps(h, ST_GEMM, st);
+      launch_lat_linear(lin(pl.attn_out, h->lt_o, M, h->lt_y2, 0, h->lt_x1), st);
+      LatLinearArgs a = lin(pl.ffn0, h->lt_y2, M, h->lt_h, 1, nullptr);
+      a.prologue = 2; a.ln1_g = pl.norm1_g; a.ln1_b = pl.norm1_b;
+      a.rowvec = h->lt_ego + (size_t)l * kLatMaxB * D; a.rows_per_group = A;
+      a.ln2_g = pl.norm2_g; a.ln2_b = pl.norm2_b;
+      launch_lat_linear(a, st);
+      launch_lat_linear(lin(pl.ffn2, h->lt_h, M, h->lt_y3, 0, nullptr), st);
+      LatLinearArgs r = lin(pl.reg0, h->lt_y3, M, h->lt_r1, 1, nullptr);
+      r.prologue = 3; r.ln1_g = pl.norm3_g; r.ln1_b = pl.norm3_b;
+      r.film = h->film + ((size_t)si * L + l) * 2 * D;
+      launch_lat_linear(r, st);
+      launch_lat_linear(lin(pl.reg2, h->lt_r1, M, h->lt_r2, 1, nullptr), st);
+      h->launches += 5;
+      if (last_layer && last_step) {
+        LatLinearArgs c = lin(pl.cls0, h->lt_y3, M, h->lt_c1, 1, nullptr);
+        c.prologue = 3; c.ln1_g = pl.norm3_g; c.ln1_b = pl.norm3_b; c.film = r.film;
+        launch_lat_linear(c, st);
+        LatLinearArgs c2 = lin(pl.cls3, h->lt_c1, M, h->lt_c2, 1, nullptr);
+        c2.prologue = 1; c2.ln1_g = pl.cls_ln2_g; c2.ln1_b = pl.cls_ln2_b;
+        launch_lat_linear(c2, st);
+        launch_lat_cls(h->lt_c2, pl.cls_ln5_g, pl.cls_ln5_b, pl.cls6_w, pl.cls6_b, scores, M, st);
+        h->launches += 3;
+      }
+      }
+      DdimCoef dc{0.f, 1.f, 1.f, 0.f};
+      const int do_ddim = (last_layer && !last_step) ? 1 : 0;
+      if (do_ddim) {
+        const int t = h->roll[si], prev = t - 1;
+        const float ac_t = h->ac[t], ac_p = prev >= 0 ? h->ac[prev] : 1.0f;
+        dc.sqrt_ac_t = sqrtf(ac_t); dc.sqrt_1m_ac_t = sqrtf(1.0f - ac_t);
+        dc.sqrt_ac_prev = sqrtf(ac_p); dc.sqrt_1m_ac_prev = sqrtf(1.0f - ac_p);
+      }
+      { ProfSpan ps(h, ST_REG, st);
+      launch_reg_finish(h->lt_r2, pl.reg4_w, pl.reg4_b, h->pts, h->img, modes, M, P, do_ddim, dc, st);
+      h->launches++; }
+    }
+  }
+  { ProfSpan ps(h, ST_SELECT, st);
+  launch_select(scores, modes, out_traj, reinterpret_cast<long long*>(out_mode_idx), B, A, P, st);
+  h->launches++; }
+  CU_TRY(h, cudaGetLastError());
+  return DDH_OK;
+}
+
 int forward_range(ddh_handle* h, const float* ego, const float* agents, const void* bev,
                   int bev_dtype, int bev_layout, const float* noise, float* out_traj,
                   float* out_modes, float* out_scores, int64_t* out_mode_idx, int s0, int B,
@@ -727,11 +894,11 @@ int forward_range(ddh_handle* h, const float* ego, const float* agents, const vo
       // -- cross_bev_attention (modules/blocks.py:88-129)
       { ProfSpan ps(h, ST_PLAN, st);
       launch_plan(v.q0_32, pl.attw_w, pl.attw_b, v.pts, v.upix, v.nuniq, v.ent_slot,
-                  v.ent_w, h->conv_rows + si * L + l, need_rows, B, A, P, s.bev_h, s.bev_w,
-                  h->rcap, oc, st); }
+                  v.ent_w, h->conv_rows + si * L + l, need_rows, done_rows, B, A, P, s.bev_h,
+                  s.bev_w, h->rcap, oc, st); }
       if (lazy) {
         ProfSpan ps(h, ST_BEV, st);
-        launch_bev_rows_to_nhwc(bev, bev_dtype, v.bev_nhwc, want_dtype, need_rows, done_rows, B,
+        launch_bev_rows_to_nhwc(bev, bev_dtype, v.bev_nhwc, want_dtype, need_rows, B,
                                 s.bev_channels, s.bev_h, s.bev_w, st);
         h->launches++;
       }
@@ -870,6 +1037,15 @@ int ddh_forward(ddh_handle* h, const float* ego, const float* agents, const void
 
   // Scene chunks on two streams: scenes are independent, so chunk c+1's HBM-bound layout pass
   // runs under chunk c's tensor-bound conv/GEMMs.  Chunk c starts once layout(c-1) is done.
+  if (h->lat_enabled && h->precision == DDH_PREC_BF16 && B <= kLatMaxB &&
+      (size_t)B * s.num_anchors * std::max(s.d_ffn, 64 * s.num_poses) * 4 <= 200 * 1024 &&
+      (size_t)B * s.num_agents * 256 * 4 <= 200 * 1024) {
+    rc = forward_small(h, ego, agents, bev, bev_dtype, bev_layout, noise, out_traj, out_modes,
+                       out_scores, out_mode_idx, B, st);
+    if (rc) return rc;
+    CU_TRY(h, cudaGetLastError());
+    return DDH_OK;
+  }
   int nchunk = 1;
   if (!h->profiling && h->chunks > 1 && B >= h->chunks * h->min_chunk_scenes) nchunk = h->chunks;
   if (nchunk == 1) {

@@ -31,11 +31,11 @@ void launch_embed(const float* img, float* pts, float* emb32, __nv_bfloat16* emb
                   const float* dim_t_dev, cudaStream_t st);
 void launch_plan(const float* q0, const float* attw_w, const float* attw_b, const float* pts,
                  int* upix, int* nuniq, int* ent_slot, float* ent_w, int* rows_total,
-                 unsigned long long* need_rows, int B, int A, int P, int H, int W, int rcap,
-                 OdoConsts oc, cudaStream_t st);
+                 unsigned long long* need_rows, unsigned long long* done_rows, int B, int A, int P,
+                 int H, int W, int rcap, OdoConsts oc, cudaStream_t st);
 void launch_bev_rows_to_nhwc(const void* src, int src_dtype, void* dst, int dst_dtype,
-                             const unsigned long long* need, unsigned long long* done, int B, int C,
-                             int H, int W, cudaStream_t st);
+                             const unsigned long long* todo, int B, int C, int H, int W,
+                             cudaStream_t st);
 void launch_combine(const float* V, const int* ent_slot, const float* ent_w, float* s32,
                     __nv_bfloat16* s16, int B, int A, int P, int rcap, cudaStream_t st);
 void launch_attn_core(const float* qh, const float* kv, float* o32, __nv_bfloat16* o16, int B,
@@ -53,6 +53,26 @@ void launch_pack_conv_bf16(const float* w, __nv_bfloat16* dst, int Cout, int Cin
 void launch_matvec(const float* W, const float* x, const float* b, float* y, int n_out, int k,
                    int act_in_mish, cudaStream_t st);
 void launch_time_sinemb(float* emb, int dim, int timestep, cudaStream_t st);
+
+// ---- kernels_lat.cu (small-batch latency engine: column-split fp32 x bf16 linears) ---------
+struct LatLinearArgs {
+  const float* A = nullptr; int M = 0, K = 0, N = 0;
+  const __nv_bfloat16* W = nullptr; const float* bias = nullptr; int relu = 0;
+  const float* res = nullptr; float* out = nullptr; int ldo = 0;
+  int prologue = 0;   // 0 none, 1 LN, 2 LN+ego+LN, 3 LN+FiLM, 4 sum of conv partials
+  const float *ln1_g = nullptr, *ln1_b = nullptr, *rowvec = nullptr; int rows_per_group = 1;
+  const float *ln2_g = nullptr, *ln2_b = nullptr, *film = nullptr;
+  const int* nuniq = nullptr; int part_stride = 0;
+};
+void launch_lat_linear(const LatLinearArgs& a, cudaStream_t st);
+void launch_lat_qattn(const float* x1, const __nv_bfloat16* wq, const float* bq, const float* kv,
+                      float* o, int B, int A, int Na, int heads, cudaStream_t st);
+void launch_lat_cls(const float* c2, const float* g, const float* b, const float* w6,
+                    const float* b6, float* scores, int M, cudaStream_t st);
+// tile/column-split tcgen05 conv for one or two scenes: grid (4 column quarters, row tiles, B);
+// writes per-tile partial sums S_part[tile][B*A][256] (fp32)
+void launch_lat_conv(const GemmParams& p, const CUtensorMap& wmap64, float* s_part,
+                     int part_stride, int B, cudaStream_t st);
 
 // ---- kernels_tc.cu (tcgen05 / TMEM / TMA engine) ----------------------------------
 // W is described by a TMA tensor map over a bf16 [N_total][K] matrix (box 64 x 256,

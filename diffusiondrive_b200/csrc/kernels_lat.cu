@@ -1,0 +1,315 @@
+// Small-batch ("latency") engine of the ddh planning head: one or two scenes per call.
+//
+// At batch 1 every GEMM of the decoder chain is 20 x 256 x 256: a 128-row tensor-core tile would
+// be 84 % padding and runs on ONE SM.  Here each Linear is split over its OUTPUT COLUMNS across
+// many CTAs (8 columns per CTA, one warp per column, lanes split K), activations stay fp32,
+// weights are the packed bf16 [N][K] matrices, and LayerNorm / FiLM / the ego add are applied by
+// the CONSUMER when it stages its input rows in shared memory ("normalise on load"), so that no
+// stage needs a full output row and every stage is a short, wide kernel.
+//
+// Stored tensors of one decoder layer (transfuser_model_v2.py:343-382), all [M, 256] fp32:
+//   x1  = S.Wbo + b + q0                               (S = sum of the conv's per-tile partials)
+//   o   = softmax(q.K^T).V,  q = x1.Wq + b             (lat_qattn_kernel, one CTA per scene x head)
+//   y2  = o.Wao + b + x1                               (pre-norm1)
+//   h   = relu(x2.W1 + b),  x2 = LN2(LN1(y2) + ego)    (prologue LN_EGO_LN)
+//   y3  = h.W2 + b                                     (pre-norm3)
+//   r1  = relu(x3.Wr0 + b), c1 = relu(x3.Wc0 + b),  x3 = FiLM(LN3(y3))   (prologue LN_FILM)
+//   r2  = relu(r1.Wr2 + b), c2 = relu(LN(c1).Wc3 + b)                    (prologue LN)
+//   reg = r2.Wr4 + b (reg_finish_kernel),  cls = LN(c2).w6 + b6 (lat_cls_kernel)
+#include "kernels.h"
+
+namespace ddh {
+
+enum LatPrologue { LP_NONE = 0, LP_LN = 1, LP_LN_EGO_LN = 2, LP_LN_FILM = 3, LP_SUM_PARTS = 4 };
+
+struct LatLinearParams {
+  const float* A = nullptr;        // [M][K] fp32  (LP_SUM_PARTS: [parts][M][K])
+  int M = 0, K = 0, N = 0;
+  const __nv_bfloat16* W = nullptr;  // [N][K] bf16 (torch Linear layout)
+  const float* bias = nullptr;
+  int relu = 0;
+  const float* res = nullptr;      // [M][N] added after bias / relu
+  float* out = nullptr;            // [M][ldo]
+  int ldo = 0;
+  int prologue = LP_NONE;
+  const float* ln1_g = nullptr; const float* ln1_b = nullptr;
+  const float* rowvec = nullptr; int rows_per_group = 1;   // LP_LN_EGO_LN
+  const float* ln2_g = nullptr; const float* ln2_b = nullptr;
+  const float* film = nullptr;                            // LP_LN_FILM: [2*D]
+  const int* nuniq = nullptr; int part_stride = 0;         // LP_SUM_PARTS: parts = ceil(nuniq/128)
+};
+
+__device__ __forceinline__ void lat_ln_row(float (&v)[8], const float* g, const float* b, int lane) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += v[i];
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; q += d * d; }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / D) + LN_EPS);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = lane * 4 + (i & 3) + 128 * (i >> 2);
+    v[i] = (v[i] - mean) * rstd * g[c] + b[c];
+  }
+}
+
+// out[m, n] = epi( pro(A)[m, :] . W[n, :] ),  8 columns per CTA, one warp per column.
+// Lane l owns k = 4*l + 128*i + {0..3}: 16-byte shared-memory reads with no bank conflicts and
+// 256-byte coalesced weight reads.
+template <int KMAX>
+__global__ void __launch_bounds__(256) lat_linear_kernel(const LatLinearParams p) {
+  extern __shared__ __align__(16) float As[];   // [M][K]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int M = p.M, K = p.K;
+  const int n = blockIdx.x * 8 + warp;
+  // ---- this warp's weight row: issued first so its latency hides under the input staging
+  constexpr int NI = KMAX / 128;
+  uint2 wraw[NI];
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    wraw[i] = make_uint2(0u, 0u);
+    if (i * 128 < K && n < p.N)
+      wraw[i] = __ldg(reinterpret_cast<const uint2*>(p.W + (size_t)n * K + i * 128 + lane * 4));
+  }
+  const float bias = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.f;
+  // ---- stage (and normalise) the input rows
+  if (p.prologue == LP_NONE) {
+    const float4* src = reinterpret_cast<const float4*>(p.A);
+    float4* dst = reinterpret_cast<float4*>(As);
+    for (int i = tid; i < M * K / 4; i += 256) dst[i] = __ldg(src + i);
+  } else {
+    // K == D for every normalised input; one warp per row, 8 values per lane
+    for (int m = warp; m < M; m += 8) {
+      float v[8];
+      if (p.prologue == LP_SUM_PARTS) {
+        const int parts = (p.nuniq[m / p.rows_per_group] + 127) / 128;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        for (int t = 0; t < parts; ++t) {
+          float u[8];
+          load8(p.A + (size_t)t * p.part_stride + (size_t)m * D, lane, u);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] += u[i];
+        }
+      } else {
+        load8(p.A + (size_t)m * D, lane, v);
+        lat_ln_row(v, p.ln1_g, p.ln1_b, lane);
+        if (p.prologue == LP_LN_EGO_LN) {
+          float u[8];
+          load8(p.rowvec + (size_t)(m / p.rows_per_group) * D, lane, u);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] += u[i];
+          lat_ln_row(v, p.ln2_g, p.ln2_b, lane);
+        } else if (p.prologue == LP_LN_FILM) {
+          float sc[8], sh[8];
+          load8(p.film, lane, sc);
+          load8(p.film + D, lane, sh);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = v[i] * (1.0f + sc[i]) + sh[i];
+        }
+      }
+      *reinterpret_cast<float4*>(As + m * D + lane * 4) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(As + m * D + 128 + lane * 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  }
+  __syncthreads();
+  if (n >= p.N) return;
+  float w[NI][4];
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&wraw[i].x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&wraw[i].y);
+    w[i][0] = __low2float(a); w[i][1] = __high2float(a);
+    w[i][2] = __low2float(b); w[i][3] = __high2float(b);
+  }
+  // four rows at a time: four independent shuffle reductions in flight
+  for (int m0 = 0; m0 < M; m0 += 4) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int m = min(m0 + r, M - 1);
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        if (i * 128 < K) {
+          const float4 a = *reinterpret_cast<const float4*>(As + (size_t)m * K + i * 128 + lane * 4);
+          s[r] = fmaf(a.x, w[i][0], s[r]);
+          s[r] = fmaf(a.y, w[i][1], s[r]);
+          s[r] = fmaf(a.z, w[i][2], s[r]);
+          s[r] = fmaf(a.w, w[i][3], s[r]);
+        }
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], off);
+    }
+    if (lane < 4 && m0 + lane < M) {
+      const int m = m0 + lane;
+      float v = (lane == 0) ? s[0] : (lane == 1) ? s[1] : (lane == 2) ? s[2] : s[3];
+      v += bias;
+      if (p.relu) v = fmaxf(v, 0.f);
+      if (p.res) v += p.res[(size_t)m * p.N + n];
+      p.out[(size_t)m * p.ldo + n] = v;
+    }
+  }
+}
+
+// q projection + attention core for one (scene, head): q_h = x1.Wq_h + b (32 columns), then
+// softmax(q*scale . K_h^T) . V_h over the hoisted K|V rows (nn.MultiheadAttention, :316-321).
+// 8 warps: warp w computes q columns 4w..4w+3 (lanes split K), then queries w, w+8, w+16.
+__global__ void __launch_bounds__(256) lat_qattn_kernel(const float* __restrict__ x1,
+                                                        const __nv_bfloat16* __restrict__ wq,
+                                                        const float* __restrict__ bq,
+                                                        const float* __restrict__ kv,
+                                                        float* __restrict__ o, int A, int Na) {
+  extern __shared__ __align__(16) float sm[];
+  float* As = sm;                       // [A][256]
+  float* qs = As + A * D;               // [A][32]
+  float* ks = qs + A * 32;              // [Na][33]
+  float* vs = ks + Na * 33;             // [Na][32]
+  const int scene = blockIdx.x, h = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  {
+    const float4* src = reinterpret_cast<const float4*>(x1 + (size_t)scene * A * D);
+    float4* dst = reinterpret_cast<float4*>(As);
+    for (int i = tid; i < A * D / 4; i += 256) dst[i] = __ldg(src + i);
+    for (int i = tid; i < Na * 32; i += 256) {
+      const int j = i >> 5, c = i & 31;
+      ks[j * 33 + c] = __ldg(kv + ((size_t)scene * Na + j) * 2 * D + h * 32 + c);
+      vs[j * 32 + c] = __ldg(kv + ((size_t)scene * Na + j) * 2 * D + D + h * 32 + c);
+    }
+  }
+  __syncthreads();
+  const float scale = 0.17677669529663687f;
+  {
+    // warp w -> q columns 4w..4w+3 of this head; 4 columns x 4 rows of dot products in flight
+    float w[4][2][4];
+    float bias[4];
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const int n = h * 32 + warp * 4 + cc;
+      bias[cc] = __ldg(bq + n);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const uint2 u = __ldg(reinterpret_cast<const uint2*>(wq + (size_t)n * D + i * 128 + lane * 4));
+        const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+        const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+        w[cc][i][0] = __low2float(a); w[cc][i][1] = __high2float(a);
+        w[cc][i][2] = __low2float(b); w[cc][i][3] = __high2float(b);
+      }
+    }
+    for (int m0 = 0; m0 < A; m0 += 4) {
+      float s[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int m = min(m0 + r, A - 1);
+        const float4 a0 = *reinterpret_cast<const float4*>(As + m * D + lane * 4);
+        const float4 a1 = *reinterpret_cast<const float4*>(As + m * D + 128 + lane * 4);
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          float t = a0.x * w[cc][0][0];
+          t = fmaf(a0.y, w[cc][0][1], t); t = fmaf(a0.z, w[cc][0][2], t); t = fmaf(a0.w, w[cc][0][3], t);
+          t = fmaf(a1.x, w[cc][1][0], t); t = fmaf(a1.y, w[cc][1][1], t);
+          t = fmaf(a1.z, w[cc][1][2], t); t = fmaf(a1.w, w[cc][1][3], t);
+          s[r][cc] = t;
+        }
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) s[r][cc] += __shfl_xor_sync(0xffffffffu, s[r][cc], off);
+      if (lane < 16) {
+        const int r = lane >> 2, cc = lane & 3;
+        float v = 0.f;
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+          for (int c2 = 0; c2 < 4; ++c2) if (rr == r && c2 == cc) v = s[rr][c2];
+        if (m0 + r < A) qs[(m0 + r) * 32 + warp * 4 + cc] = (v + bias[cc]) * scale;
+      }
+    }
+  }
+  __syncthreads();
+  for (int a = warp; a < A; a += 8) {
+    float s = -INFINITY;
+    if (lane < Na) {
+      s = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) s = fmaf(qs[a * 32 + c], ks[lane * 33 + c], s);
+    }
+    float mx = s;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    const float e = (lane < Na) ? expf(s - mx) : 0.f;
+    const float pj = e / warp_sum(e);
+    float acc = 0.f;
+    for (int j = 0; j < Na; ++j) acc = fmaf(__shfl_sync(0xffffffffu, pj, j), vs[j * 32 + lane], acc);
+    o[((size_t)scene * A + a) * D + h * 32 + lane] = acc;
+  }
+}
+
+// cls = LN(c2) . w6 + b6, one warp per row (plan_cls_branch tail, :221-224)
+__global__ void __launch_bounds__(256) lat_cls_kernel(const float* __restrict__ c2,
+                                                      const float* __restrict__ g,
+                                                      const float* __restrict__ b,
+                                                      const float* __restrict__ w6,
+                                                      const float* __restrict__ b6,
+                                                      float* __restrict__ scores, int M) {
+  const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (m >= M) return;
+  float v[8], w[8];
+  load8(c2 + (size_t)m * D, lane, v);
+  lat_ln_row(v, g, b, lane);
+  load8(w6, lane, w);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s = fmaf(v[i], w[i], s);
+  s = warp_sum(s);
+  if (lane == 0) scores[m] = s + b6[0];
+}
+
+// ---------------------------------------------------------------------------------- launchers
+void launch_lat_linear(const LatLinearArgs& a, cudaStream_t st) {
+  LatLinearParams p;
+  p.A = a.A; p.M = a.M; p.K = a.K; p.N = a.N; p.W = a.W; p.bias = a.bias; p.relu = a.relu;
+  p.res = a.res; p.out = a.out; p.ldo = a.ldo; p.prologue = a.prologue;
+  p.ln1_g = a.ln1_g; p.ln1_b = a.ln1_b; p.rowvec = a.rowvec; p.rows_per_group = a.rows_per_group;
+  p.ln2_g = a.ln2_g; p.ln2_b = a.ln2_b; p.film = a.film; p.nuniq = a.nuniq;
+  p.part_stride = a.part_stride;
+  const int smem = a.M * a.K * 4;
+  static bool once = false;
+  if (!once) {
+    cudaFuncSetAttribute(lat_linear_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(lat_linear_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(lat_linear_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    once = true;
+  }
+  const int grid = (a.N + 7) / 8;
+  if (a.K <= 256) lat_linear_kernel<256><<<grid, 256, smem, st>>>(p);
+  else if (a.K <= 512) lat_linear_kernel<512><<<grid, 256, smem, st>>>(p);
+  else lat_linear_kernel<1024><<<grid, 256, smem, st>>>(p);
+}
+
+void launch_lat_qattn(const float* x1, const __nv_bfloat16* wq, const float* bq, const float* kv,
+                      float* o, int B, int A, int Na, int heads, cudaStream_t st) {
+  const int smem = (A * D + A * 32 + Na * 33 + Na * 32) * 4;
+  static int cur = 0;
+  if (smem > cur && smem > 48 * 1024) {
+    cudaFuncSetAttribute(lat_qattn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cur = smem;
+  }
+  dim3 grid(B, heads);
+  lat_qattn_kernel<<<grid, 256, smem, st>>>(x1, wq, bq, kv, o, A, Na);
+}
+
+void launch_lat_cls(const float* c2, const float* g, const float* b, const float* w6,
+                    const float* b6, float* scores, int M, cudaStream_t st) {
+  lat_cls_kernel<<<(M + 7) / 8, 256, 0, st>>>(c2, g, b, w6, b6, scores, M);
+}
+
+}  // namespace ddh

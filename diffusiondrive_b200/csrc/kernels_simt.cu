@@ -253,14 +253,15 @@ static void bev_launch(const void* src, void* dst, int B, int C, int HW, cudaStr
                                                           reinterpret_cast<TO*>(dst), C, HW);
 }
 
-// On-demand variant: one CTA per scene converts only the BEV rows the coming conv call reads
-// (need_rows, written by plan_kernel) that have not been converted yet (done_rows), 32 pixels x
-// 256 channels per tile.  Trajectories only ever sample the forward part of the map, so ~45 %
+// On-demand variant: converts only the BEV rows the coming conv call reads and that are not
+// converted yet (todo mask written by plan_kernel, which also maintains the done mask), 32 pixels
+// x 256 channels per tile; one CTA per scene at large batch, rows dealt over gridDim.y CTAs at
+// small batch.  Trajectories only ever sample the forward part of the map, so ~45 %
 // of the rows are never touched.  H <= 64.
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) bev_rows_to_nhwc_kernel(
-    const TI* __restrict__ src, TO* __restrict__ dst, const unsigned long long* __restrict__ need_rows,
-    unsigned long long* __restrict__ done_rows, int C, int H, int W) {
+    const TI* __restrict__ src, TO* __restrict__ dst, const unsigned long long* __restrict__ todo_rows,
+    int C, int H, int W) {
   constexpr int PXT = 32;
   constexpr int LDW = (sizeof(TO) == 2) ? 129 : 257;
   extern __shared__ __align__(16) uint32_t tile_u32[];
@@ -268,17 +269,18 @@ __global__ void __launch_bounds__(256) bev_rows_to_nhwc_kernel(
   constexpr int LDE = LDW * 4 / sizeof(TO);
   constexpr int G = PXT / 4, CL = 256 / G;
   const int b = blockIdx.x;
-  const unsigned long long done = done_rows[b];
-  unsigned long long todo = need_rows[b] & ~done;
+  const unsigned long long todo = todo_rows[b];   // written by plan_kernel
   if (!todo) return;
   const int tid = threadIdx.x, px4 = tid % G, cl = tid / G;
   const int lane = tid & 31, warp = tid >> 5;
   const int HW = H * W;
   constexpr int WORDS = 256 * sizeof(TO) / 4;
   unsigned long long rest = todo;
+  int idx = 0;
   while (rest) {
     const int y = __ffsll((long long)rest) - 1;
     rest &= rest - 1;
+    if ((idx++ % (int)gridDim.y) != (int)blockIdx.y) continue;   // rows dealt round-robin over y
     for (int x0 = 0; x0 < W; x0 += PXT) {
       const int px0 = y * W + x0;
       const TI* s = src + (size_t)b * C * HW + px0 + px4 * 4;
@@ -302,27 +304,29 @@ __global__ void __launch_bounds__(256) bev_rows_to_nhwc_kernel(
       }
     }
   }
-  if (tid == 0) done_rows[b] = done | todo;
 }
 
 template <typename TI, typename TO>
-static void bev_rows_launch(const void* src, void* dst, const unsigned long long* need,
-                            unsigned long long* done, int B, int C, int H, int W, cudaStream_t st) {
+static void bev_rows_launch(const void* src, void* dst, const unsigned long long* todo, int B,
+                            int C, int H, int W, cudaStream_t st) {
   constexpr int LDW = (sizeof(TO) == 2) ? 129 : 257;
   const int smem = 32 * LDW * 4;
-  bev_rows_to_nhwc_kernel<TI, TO><<<B, 256, smem, st>>>(
-      reinterpret_cast<const TI*>(src), reinterpret_cast<TO*>(dst), need, done, C, H, W);
+  int ysplit = 592 / (B > 0 ? B : 1);     // small batches: spread one scene's rows over CTAs
+  ysplit = ysplit < 1 ? 1 : (ysplit > 32 ? 32 : ysplit);
+  dim3 grid(B, ysplit);
+  bev_rows_to_nhwc_kernel<TI, TO><<<grid, 256, smem, st>>>(
+      reinterpret_cast<const TI*>(src), reinterpret_cast<TO*>(dst), todo, C, H, W);
 }
 
 void launch_bev_rows_to_nhwc(const void* src, int src_dtype, void* dst, int dst_dtype,
-                             const unsigned long long* need, unsigned long long* done, int B, int C,
-                             int H, int W, cudaStream_t st) {
-  if (src_dtype == 0 && dst_dtype == 0) bev_rows_launch<float, float>(src, dst, need, done, B, C, H, W, st);
+                             const unsigned long long* todo, int B, int C, int H, int W,
+                             cudaStream_t st) {
+  if (src_dtype == 0 && dst_dtype == 0) bev_rows_launch<float, float>(src, dst, todo, B, C, H, W, st);
   else if (src_dtype == 0 && dst_dtype == 1)
-    bev_rows_launch<float, __nv_bfloat16>(src, dst, need, done, B, C, H, W, st);
+    bev_rows_launch<float, __nv_bfloat16>(src, dst, todo, B, C, H, W, st);
   else if (src_dtype == 1 && dst_dtype == 1)
-    bev_rows_launch<__nv_bfloat16, __nv_bfloat16>(src, dst, need, done, B, C, H, W, st);
-  else bev_rows_launch<__nv_bfloat16, float>(src, dst, need, done, B, C, H, W, st);
+    bev_rows_launch<__nv_bfloat16, __nv_bfloat16>(src, dst, todo, B, C, H, W, st);
+  else bev_rows_launch<__nv_bfloat16, float>(src, dst, todo, B, C, H, W, st);
 }
 
 void launch_bev_to_nhwc(const void* src, int src_dtype, void* dst, int dst_dtype, int B, int C,
@@ -490,6 +494,7 @@ __global__ void __launch_bounds__(256) plan_kernel(const float* __restrict__ q0,
                                                    float* __restrict__ ent_w,
                                                    int* __restrict__ rows_total,
                                                    unsigned long long* __restrict__ need_rows,
+                                                   unsigned long long* __restrict__ done_rows,
                                                    int A, int P, int H, int W, int rcap,
                                                    OdoConsts oc) {
   extern __shared__ __align__(16) unsigned char smraw[];
@@ -573,7 +578,12 @@ __global__ void __launch_bounds__(256) plan_kernel(const float* __restrict__ q0,
   if (tid == 0) {
     nuniq[scene] = total_s;
     if (rows_total) atomicAdd(rows_total, total_s);
-    if (need_rows) need_rows[scene] = (H >= 64) ? need_s : (need_s & ((1ull << H) - 1ull));
+    if (need_rows) {   // rows still to convert for the coming conv call; mark them converted
+      const unsigned long long need = (H >= 64) ? need_s : (need_s & ((1ull << H) - 1ull));
+      const unsigned long long done = done_rows[scene];
+      need_rows[scene] = need & ~done;
+      done_rows[scene] = done | need;
+    }
   }
   // ---- entries
   for (int e = tid; e < AP; e += 256) {
@@ -596,8 +606,8 @@ __global__ void __launch_bounds__(256) plan_kernel(const float* __restrict__ q0,
 }
 void launch_plan(const float* q0, const float* attw_w, const float* attw_b, const float* pts,
                  int* upix, int* nuniq, int* ent_slot, float* ent_w, int* rows_total,
-                 unsigned long long* need_rows, int B, int A, int P, int H, int W, int rcap,
-                 OdoConsts oc, cudaStream_t st) {
+                 unsigned long long* need_rows, unsigned long long* done_rows, int B, int A, int P,
+                 int H, int W, int rcap, OdoConsts oc, cudaStream_t st) {
   const int smem = ((H * W * 2 + 15) / 16) * 16 + A * P * 4;
   static int cur = 0;
   if (smem > cur) {
@@ -605,7 +615,7 @@ void launch_plan(const float* q0, const float* attw_w, const float* attw_b, cons
     cur = smem;
   }
   plan_kernel<<<B, 256, smem, st>>>(q0, attw_w, attw_b, pts, upix, nuniq, ent_slot, ent_w,
-                                     rows_total, need_rows, A, P, H, W, rcap, oc);
+                                     rows_total, need_rows, done_rows, A, P, H, W, rcap, oc);
 }
 
 // ===================================================================================

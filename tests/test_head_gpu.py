@@ -159,6 +159,29 @@ def test_bf16_b256_within_tolerance(golden_dir):
     assert rec["mode_agreement_margin_gt_0.05"] == 1.0
 
 
+def test_small_batch_engine_matches_reference(golden_dir):
+    """B <= 2 in bf16 mode runs the small-batch latency engine (column-split fp32 x bf16 linears,
+    tile/column-split tcgen05 conv): same tolerance as the tensor path, and it is the engine the
+    batch-1 latency number is measured on."""
+    ref = _load(golden_dir, "default_b256")
+    head, _ = _make_head("bf16")
+    for B in (1, 2):
+        out, _, _ = _run(head, B)
+        sub = {k: v[:B] for k, v in ref.items()}
+        rec = _report(f"bf16_small_batch_b{B}_vs_reference", out, sub)
+        assert rec["max_dxy_m"] <= TOL_BF16_M and rec["max_dheading_rad"] <= TOL_BF16_M
+        assert rec["mode_agreement"] == 1.0
+        assert head.last_launch_count() < 64
+    # the two engines agree with each other well inside the bf16 tolerance
+    os.environ["DDH_LAT"] = "0"
+    try:
+        head2, _ = _make_head("bf16")
+        out2, _, _ = _run(head2, 2)
+    finally:
+        os.environ.pop("DDH_LAT", None)
+    assert np.abs(out2["trajectory_modes"] - out["trajectory_modes"]).max() <= TOL_BF16_M
+
+
 # ------------------------------------------------------------------------------ stress shape
 @pytest.mark.parametrize("precision,tol", [("fp32", TOL_FP32_M), ("bf16", TOL_BF16_M)])
 def test_stress_config_matches_reference_golden(golden_dir, precision, tol):
