@@ -843,7 +843,11 @@ int forward_range(ddh_handle* h, const float* ego, const float* agents, const vo
   }
   }
 
-  if (layout_done) CU_TRY(h, cudaEventRecord(layout_done, st));
+  bool layout_event_pending = layout_done != nullptr;
+  if (layout_event_pending && !lazy) {
+    CU_TRY(h, cudaEventRecord(layout_done, st));
+    layout_event_pending = false;
+  }
 
   // ---- hoisted per (scene, layer): agent K|V and the collapsed ego vector
   { ProfSpan ps(h, ST_HOIST, st);
@@ -901,6 +905,10 @@ int forward_range(ddh_handle* h, const float* ego, const float* agents, const vo
         launch_bev_rows_to_nhwc(bev, bev_dtype, v.bev_nhwc, want_dtype, need_rows, B,
                                 s.bev_channels, s.bev_h, s.bev_w, st);
         h->launches++;
+        if (layout_event_pending) {   // the next chunk may start: its layout runs under our conv
+          CU_TRY(h, cudaEventRecord(layout_done, st));
+          layout_event_pending = false;
+        }
       }
       {
         ProfSpan ps(h, ST_CONV, st);
