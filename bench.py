@@ -299,6 +299,29 @@ def run_ours(args):
                "note": "BEV rows are converted on demand before each conv call; only rows a conv reads",
                "share_of_step": bev_ms / stage_total if stage_total else None}
 
+    # ---- the same timed loop with the map handed over as NHWC bf16 (what the producer holds one
+    # line before the reference's permute, transfuser_model_v2.py:136-140): no layout pass
+    nhwc = None
+    if precision == "bf16" and not args.quick:
+        try:
+            bev_n = bev.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+            for _ in range(3):
+                head(ego, agents, bev_n, noise=noise, bev_layout="NHWC")
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(args.steps):
+                head(ego, agents, bev_n, noise=noise, bev_layout="NHWC")
+            e1.record()
+            torch.cuda.synchronize()
+            ms_n = e0.elapsed_time(e1) / args.steps
+            nhwc = {"value": B * world / (ms_n * 1e-3) if world == 1 else None, "unit": UNIT,
+                    "ms_per_step": ms_n, "per_gpu_value": B / (ms_n * 1e-3),
+                    "note": "bev_feature resident as NHWC bf16 (SURVEY §8f row N1 hands it over this way); "
+                            "not the headline: the reference boundary is fp32 NCHW"}
+            del bev_n
+        except Exception as ex:
+            nhwc = {"error": repr(ex)}
+
     # ---- end to end through the host-buffer entry point (pinned host memory, H2D + D2H timed)
     e2e = None
     Be = min(B, args.e2e_batch)
@@ -421,7 +444,7 @@ def run_ours(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step,
             "roofline": roofline, "roofline_hbm_stage": hbm, "cpu_baseline": cpu,
-            "latency_b1": lat, "parity": parity,
+            "latency_b1": lat, "parity": parity, "nhwc_bf16_input": nhwc,
             "stage_ms": {k: round(v["ms"], 4) for k, v in prof.items()},
         }
         _emit(args.real_stdout, line)

@@ -320,6 +320,35 @@ def test_edge_cases_vs_oracle():
         assert torch.equal(out["mode_idx"].cpu(), ref["mode_idx"])
 
 
+def test_bf16_edge_cases_and_precision_switch():
+    """bf16 engines (tensor path and small-batch path) on few/many agents, odd batches and
+    out-of-grid anchors; switching precision on one module re-packs."""
+    from oracle import head_oracle
+    sd = synth.make_state_dict()
+    for scale, na, B in ((1.0, 5, 1), (1.0, 5, 3), (40.0, 30, 2), (40.0, 30, 4), (1.0, 32, 9), (1.0, 1, 1)):
+        sd2 = dict(sd)
+        sd2["plan_anchor"] = sd["plan_anchor"] * scale
+        head = TrajectoryHead(8, 1024, 256, None, HeadConfig(), plan_anchor=sd2["plan_anchor"].numpy(),
+                              precision="bf16")
+        head.load_state_dict(sd2)
+        head = head.cuda().eval()
+        ft = synth.make_features(B, num_agents=na)
+        nz = synth.make_noise(B)
+        args = (ft["ego_query"].cuda(), ft["agents_query"].cuda(), ft["bev_feature"].cuda())
+        out = head(*args, noise=nz.cuda())
+        ref = head_oracle.forward_test(sd2, ft["ego_query"], ft["agents_query"], ft["bev_feature"], nz)
+        d = (out["trajectory_modes"].cpu() - ref["trajectory_modes"]).abs().max().item()
+        assert d <= TOL_BF16_M, (scale, na, B, d)
+    head.precision = "fp32"
+    out32 = head(*args, noise=nz.cuda())
+    d = (out32["trajectory_modes"].cpu() - ref["trajectory_modes"]).abs().max().item()
+    assert d <= TOL_FP32_M
+    head.precision = "bf16"
+    again = head(*args, noise=nz.cuda())
+    for k in out:
+        assert torch.equal(again[k], out[k]), k
+
+
 def test_reload_state_dict_repacks():
     head, sd = _make_head("fp32")
     ft = synth.make_features(2)
