@@ -701,10 +701,16 @@ int forward_small(ddh_handle* h, const float* ego, const float* agents, const vo
     return a;
   };
   { ProfSpan ps(h, ST_HOIST, st);
+  LatLinearArgs sets[4];
+  int nset = 0;
   for (int l = 0; l < L; ++l) {
-    launch_lat_linear(lin(h->layers[l].kv, agents, B * Na, h->lt_kv + (size_t)l * kLatMaxB * Na * 2 * D, 0, nullptr), st);
-    launch_lat_linear(lin(h->layers[l].ego, ego, B, h->lt_ego + (size_t)l * kLatMaxB * D, 0, nullptr), st);
-    h->launches += 2;
+    sets[nset++] = lin(h->layers[l].kv, agents, B * Na, h->lt_kv + (size_t)l * kLatMaxB * Na * 2 * D, 0, nullptr);
+    sets[nset++] = lin(h->layers[l].ego, ego, B, h->lt_ego + (size_t)l * kLatMaxB * D, 0, nullptr);
+    if (nset == 4 || l == L - 1) {
+      launch_lat_linear_multi(sets, nset, st);
+      h->launches++;
+      nset = 0;
+    }
   }
   }
   const float ac_tr = h->ac[s.trunc_timestep];
@@ -763,21 +769,23 @@ int forward_small(ddh_handle* h, const float* ego, const float* agents, const vo
       a.ln2_g = pl.norm2_g; a.ln2_b = pl.norm2_b;
       launch_lat_linear(a, st);
       launch_lat_linear(lin(pl.ffn2, h->lt_h, M, h->lt_y3, 0, nullptr), st);
-      LatLinearArgs r = lin(pl.reg0, h->lt_y3, M, h->lt_r1, 1, nullptr);
-      r.prologue = 3; r.ln1_g = pl.norm3_g; r.ln1_b = pl.norm3_b;
-      r.film = h->film + ((size_t)si * L + l) * 2 * D;
-      launch_lat_linear(r, st);
-      launch_lat_linear(lin(pl.reg2, h->lt_r1, M, h->lt_r2, 1, nullptr), st);
+      const bool want_cls = last_layer && last_step;
+      LatLinearArgs duo[2];
+      duo[0] = lin(pl.reg0, h->lt_y3, M, h->lt_r1, 1, nullptr);
+      duo[0].prologue = 3; duo[0].ln1_g = pl.norm3_g; duo[0].ln1_b = pl.norm3_b;
+      duo[0].film = h->film + ((size_t)si * L + l) * 2 * D;
+      duo[1] = lin(pl.cls0, h->lt_y3, M, h->lt_c1, 1, nullptr);
+      duo[1].prologue = 3; duo[1].ln1_g = pl.norm3_g; duo[1].ln1_b = pl.norm3_b;
+      duo[1].film = duo[0].film;
+      launch_lat_linear_multi(duo, want_cls ? 2 : 1, st);
+      duo[0] = lin(pl.reg2, h->lt_r1, M, h->lt_r2, 1, nullptr);
+      duo[1] = lin(pl.cls3, h->lt_c1, M, h->lt_c2, 1, nullptr);
+      duo[1].prologue = 1; duo[1].ln1_g = pl.cls_ln2_g; duo[1].ln1_b = pl.cls_ln2_b;
+      launch_lat_linear_multi(duo, want_cls ? 2 : 1, st);
       h->launches += 5;
-      if (last_layer && last_step) {
-        LatLinearArgs c = lin(pl.cls0, h->lt_y3, M, h->lt_c1, 1, nullptr);
-        c.prologue = 3; c.ln1_g = pl.norm3_g; c.ln1_b = pl.norm3_b; c.film = r.film;
-        launch_lat_linear(c, st);
-        LatLinearArgs c2 = lin(pl.cls3, h->lt_c1, M, h->lt_c2, 1, nullptr);
-        c2.prologue = 1; c2.ln1_g = pl.cls_ln2_g; c2.ln1_b = pl.cls_ln2_b;
-        launch_lat_linear(c2, st);
+      if (want_cls) {
         launch_lat_cls(h->lt_c2, pl.cls_ln5_g, pl.cls_ln5_b, pl.cls6_w, pl.cls6_b, scores, M, st);
-        h->launches += 3;
+        h->launches += 1;
       }
       }
       DdimCoef dc{0.f, 1.f, 1.f, 0.f};
@@ -789,7 +797,7 @@ int forward_small(ddh_handle* h, const float* ego, const float* agents, const vo
         dc.sqrt_ac_prev = sqrtf(ac_p); dc.sqrt_1m_ac_prev = sqrtf(1.0f - ac_p);
       }
       { ProfSpan ps(h, ST_REG, st);
-      launch_reg_finish(h->lt_r2, pl.reg4_w, pl.reg4_b, h->pts, h->img, modes, M, P, do_ddim, dc, st);
+      launch_lat_reg_finish(h->lt_r2, pl.reg4_w, pl.reg4_b, h->pts, h->img, modes, M, P, do_ddim, dc, st);
       h->launches++; }
     }
   }

@@ -65,6 +65,9 @@ struct LatLinearArgs {
   const int* nuniq = nullptr; int part_stride = 0;
 };
 void launch_lat_linear(const LatLinearArgs& a, cudaStream_t st);
+void launch_lat_linear_multi(const LatLinearArgs* args, int n, cudaStream_t st);   // n <= 4
+void launch_lat_reg_finish(const float* r2, const float* w4, const float* b4, float* pts, float* img,
+                           float* modes, int M, int P, int do_ddim, DdimCoef dc, cudaStream_t st);
 void launch_lat_qattn(const float* x1, const __nv_bfloat16* wq, const float* bq, const float* kv,
                       float* o, int B, int A, int Na, int heads, cudaStream_t st);
 void launch_lat_cls(const float* c2, const float* g, const float* b, const float* w6,

@@ -58,8 +58,12 @@ __device__ __forceinline__ void lat_ln_row(float (&v)[8], const float* g, const 
 // out[m, n] = epi( pro(A)[m, :] . W[n, :] ),  8 columns per CTA, one warp per column.
 // Lane l owns k = 4*l + 128*i + {0..3}: 16-byte shared-memory reads with no bank conflicts and
 // 256-byte coalesced weight reads.
+struct LatLinearSets { LatLinearParams s[4]; };
+
 template <int KMAX>
-__global__ void __launch_bounds__(256) lat_linear_kernel(const LatLinearParams p) {
+__global__ void __launch_bounds__(256) lat_linear_kernel(const LatLinearSets sets) {
+  const LatLinearParams& p = sets.s[blockIdx.y];
+  if ((int)blockIdx.x * 8 >= p.N) return;
   extern __shared__ __align__(16) float As[];   // [M][K]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int M = p.M, K = p.K;
@@ -274,14 +278,27 @@ __global__ void __launch_bounds__(256) lat_cls_kernel(const float* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------- launchers
-void launch_lat_linear(const LatLinearArgs& a, cudaStream_t st) {
+static LatLinearParams to_params(const LatLinearArgs& a) {
   LatLinearParams p;
   p.A = a.A; p.M = a.M; p.K = a.K; p.N = a.N; p.W = a.W; p.bias = a.bias; p.relu = a.relu;
   p.res = a.res; p.out = a.out; p.ldo = a.ldo; p.prologue = a.prologue;
   p.ln1_g = a.ln1_g; p.ln1_b = a.ln1_b; p.rowvec = a.rowvec; p.rows_per_group = a.rows_per_group;
   p.ln2_g = a.ln2_g; p.ln2_b = a.ln2_b; p.film = a.film; p.nuniq = a.nuniq;
   p.part_stride = a.part_stride;
-  const int smem = a.M * a.K * 4;
+  return p;
+}
+
+// Up to 4 independent linears in ONE launch (grid.y = set): hoisted K|V and ego projections of
+// all layers, or the reg/cls branch pairs.
+void launch_lat_linear_multi(const LatLinearArgs* args, int n, cudaStream_t st) {
+  LatLinearSets sets;
+  int smem = 0, kmax = 0, nmax = 0;
+  for (int i = 0; i < n; ++i) {
+    sets.s[i] = to_params(args[i]);
+    smem = smem > args[i].M * args[i].K * 4 ? smem : args[i].M * args[i].K * 4;
+    kmax = kmax > args[i].K ? kmax : args[i].K;
+    nmax = nmax > args[i].N ? nmax : args[i].N;
+  }
   static bool once = false;
   if (!once) {
     cudaFuncSetAttribute(lat_linear_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -289,10 +306,79 @@ void launch_lat_linear(const LatLinearArgs& a, cudaStream_t st) {
     cudaFuncSetAttribute(lat_linear_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     once = true;
   }
-  const int grid = (a.N + 7) / 8;
-  if (a.K <= 256) lat_linear_kernel<256><<<grid, 256, smem, st>>>(p);
-  else if (a.K <= 512) lat_linear_kernel<512><<<grid, 256, smem, st>>>(p);
-  else lat_linear_kernel<1024><<<grid, 256, smem, st>>>(p);
+  dim3 grid((nmax + 7) / 8, n);
+  if (kmax <= 256) lat_linear_kernel<256><<<grid, 256, smem, st>>>(sets);
+  else if (kmax <= 512) lat_linear_kernel<512><<<grid, 256, smem, st>>>(sets);
+  else lat_linear_kernel<1024><<<grid, 256, smem, st>>>(sets);
+}
+
+void launch_lat_linear(const LatLinearArgs& a, cudaStream_t st) { launch_lat_linear_multi(&a, 1, st); }
+
+// Regression tail for a handful of rows: CTA = 4 rows, warp p = pose p (outputs 3p..3p+2), lanes
+// split K; no shared memory, no block barrier (see reg_finish_kernel for the arithmetic).
+__global__ void __launch_bounds__(256) lat_reg_finish_kernel(const float* __restrict__ r2,
+                                                             const float* __restrict__ w4,
+                                                             const float* __restrict__ b4,
+                                                             float* __restrict__ pts,
+                                                             float* __restrict__ img,
+                                                             float* __restrict__ modes, int M, int P,
+                                                             int do_ddim, DdimCoef dc) {
+  const int lane = threadIdx.x & 31, pose = threadIdx.x >> 5;
+  if (pose >= P) return;
+  const int m0 = blockIdx.x * 4;
+  float w[3][8], s[4][3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) load8(w4 + (size_t)(pose * 3 + c) * D, lane, w[c]);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    float a[8];
+    load8(r2 + (size_t)min(m0 + r, M - 1) * D, lane, a);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t = fmaf(a[i], w[c][i], t);
+      s[r][c] = t;
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) s[r][c] += __shfl_xor_sync(0xffffffffu, s[r][c], off);
+  if (lane < 12) {
+    const int r = lane / 3, comp = lane - r * 3, m = m0 + r;
+    float mine = 0.f;
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) if (rr == r && cc == comp) mine = s[rr][cc];
+    if (m < M) {
+      mine += b4[pose * 3 + comp];
+      float out;
+      if (comp < 2) {
+        const size_t pi = ((size_t)m * P + pose) * 2 + comp;
+        out = __fadd_rn(mine, pts[pi]);
+        pts[pi] = out;
+        if (do_ddim) {   // norm_odo + DDIM step, same operation order as reg_finish_kernel
+          const float x0 = comp ? __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fadd_rn(out, 20.0f)), 46.0f), 1.0f)
+                                : __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fadd_rn(out, 1.2f)), 56.9f), 1.0f);
+          const float sample = img[pi];
+          const float eps = __fdiv_rn(__fsub_rn(sample, __fmul_rn(dc.sqrt_ac_t, x0)), dc.sqrt_1m_ac_t);
+          const float x0c = fminf(fmaxf(x0, -1.0f), 1.0f);
+          img[pi] = __fadd_rn(__fmul_rn(dc.sqrt_ac_prev, x0c), __fmul_rn(dc.sqrt_1m_ac_prev, eps));
+        }
+      } else {
+        out = __fmul_rn(tanhf(mine), 3.14159265358979323846f);
+      }
+      modes[((size_t)m * P + pose) * 3 + comp] = out;
+    }
+  }
+}
+void launch_lat_reg_finish(const float* r2, const float* w4, const float* b4, float* pts, float* img,
+                           float* modes, int M, int P, int do_ddim, DdimCoef dc, cudaStream_t st) {
+  lat_reg_finish_kernel<<<(M + 3) / 4, 256, 0, st>>>(r2, w4, b4, pts, img, modes, M, P, do_ddim, dc);
 }
 
 void launch_lat_qattn(const float* x1, const __nv_bfloat16* wq, const float* bq, const float* kv,
