@@ -116,6 +116,8 @@ struct ddh_handle {
   float *lt_emb = nullptr, *lt_e1 = nullptr, *lt_kv = nullptr, *lt_ego = nullptr, *lt_spart = nullptr,
         *lt_x1 = nullptr, *lt_o = nullptr, *lt_y2 = nullptr, *lt_h = nullptr, *lt_y3 = nullptr,
         *lt_r1 = nullptr, *lt_c1 = nullptr, *lt_r2 = nullptr, *lt_c2 = nullptr;
+  unsigned int* lt_bar = nullptr;              // [S*L] grid-barrier counters of the cooperative layer kernel
+  int lat_coop = 0;                            // env DDH_LAT_COOP=1: decoder layer as one cooperative kernel (measured slower)
   std::map<std::string, std::pair<const void*, size_t>> taps;
   int launches = 0;
   // optional per-stage device timing (ddh_set_profiling)
@@ -444,6 +446,7 @@ int ddh_create(const ddh_shape* s, ddh_handle** out) {
   if (const char* e = getenv("DDH_TIMELINE_GEMM")) h->tl_gemm = atoi(e);
   if (const char* e = getenv("DDH_LAZY_LAYOUT")) h->lazy_layout = atoi(e);
   if (const char* e = getenv("DDH_LAT")) h->lat_enabled = atoi(e);
+  if (const char* e = getenv("DDH_LAT_COOP")) h->lat_coop = atoi(e);
   if (const char* e = getenv("DDH_DEBUG_TAPS")) h->debug_taps = atoi(e) != 0;
   default_alphas_cumprod(h->ac);
   make_roll(s->num_steps, h->roll);
@@ -659,6 +662,7 @@ int ensure_lat_ws(ddh_handle* h) {
   LW(h->lt_x1, M * D); LW(h->lt_o, M * D); LW(h->lt_y2, M * D); LW(h->lt_h, M * F);
   LW(h->lt_y3, M * D); LW(h->lt_r1, M * D); LW(h->lt_c1, M * D); LW(h->lt_r2, M * D);
   LW(h->lt_c2, M * D);
+  LW(h->lt_bar, (size_t)s.num_layers * s.num_steps);
 #undef LW
   return DDH_OK;
 }
@@ -721,6 +725,8 @@ int forward_small(ddh_handle* h, const float* ego, const float* agents, const vo
   float* scores = out_scores ? out_scores : h->scores_buf;
   OdoConsts oc{s.lidar_max_x, s.lidar_max_y};
   const int part_stride = kLatMaxB * A * D;
+  bool coop = h->lat_coop && !h->profiling && s.d_ffn <= 1024;
+  if (coop) CU_TRY(h, cudaMemsetAsync(h->lt_bar, 0, (size_t)L * S * 4, st));
   for (int si = 0; si < S; ++si) {
     { ProfSpan ps(h, ST_EMBED, st);
     launch_embed(h->img, h->pts, h->lt_emb, nullptr, M, P, h->dim_t, st);
@@ -752,9 +758,50 @@ int forward_small(ddh_handle* h, const float* ego, const float* agents, const vo
       gp.ent_slot = h->ent_slot; gp.ent_w = h->ent_w; gp.n_anchor = A; gp.ent_per_anchor = P * 4;
       launch_lat_conv(gp, pl.conv.map64, h->lt_spart, part_stride, B, st);
       h->launches++; }
+      DdimCoef dc{0.f, 1.f, 1.f, 0.f};
+      const int do_ddim = (last_layer && !last_step) ? 1 : 0;
+      if (do_ddim) {
+        const int t = h->roll[si], prev = t - 1;
+        const float ac_t = h->ac[t], ac_p = prev >= 0 ? h->ac[prev] : 1.0f;
+        dc.sqrt_ac_t = sqrtf(ac_t); dc.sqrt_1m_ac_t = sqrtf(1.0f - ac_t);
+        dc.sqrt_ac_prev = sqrtf(ac_p); dc.sqrt_1m_ac_prev = sqrtf(1.0f - ac_p);
+      }
+      if (coop) {   // the eight post-conv stages as one cooperative kernel
+        LatLayerArgs g;
+        g.bev_out = lin(pl.bev_out, h->lt_spart, M, h->lt_x1, 0, h->q0_32);
+        g.bev_out.prologue = 4; g.bev_out.nuniq = h->nuniq; g.bev_out.rows_per_group = A;
+        g.bev_out.part_stride = part_stride; g.bev_out.max_parts = (h->rcap + 127) / 128;
+        g.wq = pl.q.w16; g.bq = pl.q.bias; g.kv = h->lt_kv + (size_t)l * kLatMaxB * Na * 2 * D;
+        g.o = h->lt_o; g.A = A; g.Na = Na; g.B = B; g.heads = s.num_heads;
+        g.attn_out = lin(pl.attn_out, h->lt_o, M, h->lt_y2, 0, h->lt_x1);
+        g.ffn0 = lin(pl.ffn0, h->lt_y2, M, h->lt_h, 1, nullptr);
+        g.ffn0.prologue = 2; g.ffn0.ln1_g = pl.norm1_g; g.ffn0.ln1_b = pl.norm1_b;
+        g.ffn0.rowvec = h->lt_ego + (size_t)l * kLatMaxB * D; g.ffn0.rows_per_group = A;
+        g.ffn0.ln2_g = pl.norm2_g; g.ffn0.ln2_b = pl.norm2_b;
+        g.ffn2 = lin(pl.ffn2, h->lt_h, M, h->lt_y3, 0, nullptr);
+        g.reg0 = lin(pl.reg0, h->lt_y3, M, h->lt_r1, 1, nullptr);
+        g.reg0.prologue = 3; g.reg0.ln1_g = pl.norm3_g; g.reg0.ln1_b = pl.norm3_b;
+        g.reg0.film = h->film + ((size_t)si * L + l) * 2 * D;
+        g.cls0 = lin(pl.cls0, h->lt_y3, M, h->lt_c1, 1, nullptr);
+        g.cls0.prologue = 3; g.cls0.ln1_g = pl.norm3_g; g.cls0.ln1_b = pl.norm3_b; g.cls0.film = g.reg0.film;
+        g.reg2 = lin(pl.reg2, h->lt_r1, M, h->lt_r2, 1, nullptr);
+        g.cls3 = lin(pl.cls3, h->lt_c1, M, h->lt_c2, 1, nullptr);
+        g.cls3.prologue = 1; g.cls3.ln1_g = pl.cls_ln2_g; g.cls3.ln1_b = pl.cls_ln2_b;
+        g.w4 = pl.reg4_w; g.b4 = pl.reg4_b; g.pts = h->pts; g.img = h->img; g.modes = modes;
+        g.M = M; g.P = P; g.do_ddim = do_ddim; g.dc = dc;
+        g.want_cls = (last_layer && last_step) ? 1 : 0;
+        g.cls_g = pl.cls_ln5_g; g.cls_b = pl.cls_ln5_b; g.w6 = pl.cls6_w; g.b6 = pl.cls6_b;
+        g.scores = scores; g.bar = h->lt_bar + si * L + l; g.dbg = h->dbg;
+        if (launch_lat_layer(g, st) == 0) {
+          h->launches++;
+          continue;
+        }
+        coop = false;   // cooperative launch unavailable: fall through to per-stage launches
+      }
       { ProfSpan ps(h, ST_GEMM, st);
       LatLinearArgs a = lin(pl.bev_out, h->lt_spart, M, h->lt_x1, 0, h->q0_32);
       a.prologue = 4; a.nuniq = h->nuniq; a.rows_per_group = A; a.part_stride = part_stride;
+      a.max_parts = (h->rcap + 127) / 128;
       launch_lat_linear(a, st);
       h->launches++; }
       { ProfSpan ps(h, ST_ATTN, st);
@@ -787,14 +834,6 @@ int forward_small(ddh_handle* h, const float* ego, const float* agents, const vo
         launch_lat_cls(h->lt_c2, pl.cls_ln5_g, pl.cls_ln5_b, pl.cls6_w, pl.cls6_b, scores, M, st);
         h->launches += 1;
       }
-      }
-      DdimCoef dc{0.f, 1.f, 1.f, 0.f};
-      const int do_ddim = (last_layer && !last_step) ? 1 : 0;
-      if (do_ddim) {
-        const int t = h->roll[si], prev = t - 1;
-        const float ac_t = h->ac[t], ac_p = prev >= 0 ? h->ac[prev] : 1.0f;
-        dc.sqrt_ac_t = sqrtf(ac_t); dc.sqrt_1m_ac_t = sqrtf(1.0f - ac_t);
-        dc.sqrt_ac_prev = sqrtf(ac_p); dc.sqrt_1m_ac_prev = sqrtf(1.0f - ac_p);
       }
       { ProfSpan ps(h, ST_REG, st);
       launch_lat_reg_finish(h->lt_r2, pl.reg4_w, pl.reg4_b, h->pts, h->img, modes, M, P, do_ddim, dc, st);
@@ -1054,6 +1093,7 @@ int ddh_forward(ddh_handle* h, const float* ego, const float* agents, const void
   // Scene chunks on two streams: scenes are independent, so chunk c+1's HBM-bound layout pass
   // runs under chunk c's tensor-bound conv/GEMMs.  Chunk c starts once layout(c-1) is done.
   if (h->lat_enabled && h->precision == DDH_PREC_BF16 && B <= kLatMaxB &&
+      s.d_ffn <= 1024 &&
       (size_t)B * s.num_anchors * std::max(s.d_ffn, 64 * s.num_poses) * 4 <= 200 * 1024 &&
       (size_t)B * s.num_agents * 256 * 4 <= 200 * 1024) {
     rc = forward_small(h, ego, agents, bev, bev_dtype, bev_layout, noise, out_traj, out_modes,

@@ -62,7 +62,7 @@ struct LatLinearArgs {
   int prologue = 0;   // 0 none, 1 LN, 2 LN+ego+LN, 3 LN+FiLM, 4 sum of conv partials
   const float *ln1_g = nullptr, *ln1_b = nullptr, *rowvec = nullptr; int rows_per_group = 1;
   const float *ln2_g = nullptr, *ln2_b = nullptr, *film = nullptr;
-  const int* nuniq = nullptr; int part_stride = 0;
+  const int* nuniq = nullptr; int part_stride = 0; int max_parts = 1;
 };
 void launch_lat_linear(const LatLinearArgs& a, cudaStream_t st);
 void launch_lat_linear_multi(const LatLinearArgs* args, int n, cudaStream_t st);   // n <= 4
@@ -72,6 +72,18 @@ void launch_lat_qattn(const float* x1, const __nv_bfloat16* wq, const float* bq,
                       float* o, int B, int A, int Na, int heads, cudaStream_t st);
 void launch_lat_cls(const float* c2, const float* g, const float* b, const float* w6,
                     const float* b6, float* scores, int M, cudaStream_t st);
+// one decoder layer after the conv as one cooperative kernel (grid barriers between stages);
+// returns 0 on success, non-zero if cooperative launch is unavailable / failed
+struct LatLayerArgs {
+  LatLinearArgs bev_out, attn_out, ffn0, ffn2, reg0, cls0, reg2, cls3;
+  const __nv_bfloat16* wq = nullptr; const float* bq = nullptr; const float* kv = nullptr;
+  float* o = nullptr; int A = 0, Na = 0, B = 0, heads = 0;
+  const float* w4 = nullptr; const float* b4 = nullptr; float* pts = nullptr; float* img = nullptr;
+  float* modes = nullptr; int M = 0, P = 0, do_ddim = 0; DdimCoef dc{0.f, 1.f, 1.f, 0.f};
+  int want_cls = 0; const float *cls_g = nullptr, *cls_b = nullptr, *w6 = nullptr, *b6 = nullptr;
+  float* scores = nullptr; unsigned int* bar = nullptr; long long* dbg = nullptr;
+};
+int launch_lat_layer(const LatLayerArgs& a, cudaStream_t st);
 // tile/column-split tcgen05 conv for one or two scenes: grid (4 column quarters, row tiles, B);
 // writes per-tile partial sums S_part[tile][B*A][256] (fp32)
 void launch_lat_conv(const GemmParams& p, const CUtensorMap& wmap64, float* s_part,
