@@ -23,6 +23,7 @@
 
 #include "../../include/ddh.h"
 #include "kernels.h"
+#include "kernels_res.h"
 
 using namespace ddh;
 
@@ -118,6 +119,12 @@ struct ddh_handle {
         *lt_r1 = nullptr, *lt_c1 = nullptr, *lt_r2 = nullptr, *lt_c2 = nullptr;
   unsigned int* lt_bar = nullptr;              // [S*L] grid-barrier counters of the cooperative layer kernel
   int lat_coop = 0;                            // env DDH_LAT_COOP=1: decoder layer as one cooperative kernel (measured slower)
+  // resident engine (kernels_res.cu): the whole forward of <= RES_MAX_B scenes in one launch
+  int res_enabled = 1;                         // env DDH_RES=0 disables it
+  bool res_ok = false;
+  std::vector<void*> owned_res;
+  ResConsts* res_consts = nullptr;             // device copy
+  ResConsts res_host;                          // host mirror (workspace pointers for the debug taps)
   std::map<std::string, std::pair<const void*, size_t>> taps;
   int launches = 0;
   // optional per-stage device timing (ddh_set_profiling)
@@ -224,7 +231,8 @@ void make_roll(int S, std::vector<int>& roll) {
   for (int i = 0; i < S; ++i) roll[S - 1 - i] = (int)nearbyint(i * ratio);
 }
 
-int make_wmap(ddh_handle* h, PackedLinear& L, int box_rows = 256) {
+// TMA tensor map over a bf16 [N][K] matrix: box {64 k, box_rows}, 128-byte swizzle.
+int encode_wmap(ddh_handle* h, CUtensorMap* out, void* w16, int N, int K, int box_rows) {
   if (!h->encode) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -233,16 +241,20 @@ int make_wmap(ddh_handle* h, PackedLinear& L, int box_rows = 256) {
       return fail(h, DDH_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     h->encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
-  const cuuint64_t gdim[2] = {(cuuint64_t)L.K, (cuuint64_t)L.N};
-  const cuuint64_t gstride[1] = {(cuuint64_t)L.K * 2};
+  const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)N};
+  const cuuint64_t gstride[1] = {(cuuint64_t)K * 2};
   const cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult r = h->encode(box_rows == 256 ? &L.map : &L.map64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, L.w16, gdim, gstride, box,
-                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+  CUresult r = h->encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w16, gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(h, DDH_ERR_CUDA, "cuTensorMapEncodeTiled failed, CUresult " + std::to_string((int)r));
   return DDH_OK;
+}
+
+int make_wmap(ddh_handle* h, PackedLinear& L, int box_rows = 256) {
+  return encode_wmap(h, box_rows == 256 ? &L.map : &L.map64, L.w16, L.N, L.K, box_rows);
 }
 
 int copy_vec(ddh_handle* h, float** dst, const float* src, size_t n, cudaStream_t st) {
@@ -339,7 +351,7 @@ int ensure_ws(ddh_handle* h, int B) {
   WS(h->conv_rows, s.num_layers * s.num_steps);
   WS(h->need_rows, B);
   WS(h->done_rows, B);
-  WS(h->dbg, 4 * 40 * 2);
+  WS(h->dbg, 1024);
   WS(h->ent_slot, M * s.num_poses * 4);
   WS(h->ent_w, M * s.num_poses * 4);
   if (!bf) WS(h->V, (size_t)B * h->rcap * D);
@@ -377,7 +389,7 @@ void register_taps(ddh_handle* h, int B) {
   t["egov"] = {h->egov, (size_t)s.num_layers * B * D * 4};
   t["upix"] = {h->upix, (size_t)B * h->rcap * 4};
   t["nuniq"] = {h->nuniq, (size_t)B * 4};
-  t["dbg"] = {h->dbg, (size_t)4 * 40 * 2 * 8};
+  t["dbg"] = {h->dbg, (size_t)1024 * 8};
   t["done_rows"] = {h->done_rows, (size_t)B * 8};
   t["conv_rows"] = {h->conv_rows, (size_t)s.num_layers * s.num_steps * 4};
   t["ent_slot"] = {h->ent_slot, M * s.num_poses * 4 * 4};
@@ -394,6 +406,128 @@ void register_taps(ddh_handle* h, int B) {
   t["scores"] = {h->scores_buf, M * 4};
   if (h->precision == DDH_PREC_BF16) t["bev_nhwc"] = {h->bev_nhwc, (size_t)B * s.bev_h * s.bev_w * s.bev_channels * 2};
   else t["bev_nhwc"] = {h->bev_nhwc, (size_t)B * s.bev_h * s.bev_w * s.bev_channels * 4};
+}
+
+// Resident engine (kernels_res.cu): tensor maps with per-CTA slice boxes, the weight item order,
+// constants and exchange buffers.  Leaves h->res_ok false when the shape is outside the engine's
+// limits or a 16-CTA cluster cannot be scheduled (the other engines then serve small batches).
+int build_res(ddh_handle* h, cudaStream_t st) {
+  h->res_ok = false;
+  free_all(h->owned_res);
+  h->res_consts = nullptr;
+  const ddh_shape& s = h->shp;
+  const int A = s.num_anchors, P = s.num_poses, Na = s.num_agents, F = s.d_ffn, L = s.num_layers,
+            S = s.num_steps, H = s.bev_h, W = s.bev_w;
+  if (!h->res_enabled || h->precision != DDH_PREC_BF16) return DDH_OK;
+  if (A > 32 || A * P > 256 || P != 8 || Na > 31 || F > 1024 || F % 128 || s.num_heads != 8 ||
+      H * W > 4096 || H > 64 || W % 32 || L > RES_MAX_L || S > RES_MAX_S || s.bev_channels != 256)
+    return DDH_OK;
+  if (res_engine_init() != 0) return DDH_OK;
+  auto& o = h->owned_res;
+  int rc;
+#define TRY(x) do { rc = (x); if (rc) return rc; } while (0)
+  ResMaps* maps_dev = nullptr;
+  TRY(dev_alloc(h, o, &maps_dev, 1));
+  TRY(dev_alloc(h, o, &h->res_consts, 1));
+  std::vector<ResMaps> maps_host(1);
+  ResMaps& M = maps_host[0];
+  ResConsts& C = h->res_host;
+  memset(&C, 0, sizeof C);
+  const int NC = D / RES_CL;
+  TRY(encode_wmap(h, &M.enc0, h->enc0.w16, D, 64 * P, NC));
+  TRY(encode_wmap(h, &M.enc3, h->enc3.w16, D, D, NC));
+  for (int l = 0; l < L; ++l) {
+    PackedLayer& pl = h->layers[l];
+    // [Wkv ; Wego] stacked: one streamed item per layer for the hoisted K|V and ego projections
+    __nv_bfloat16* kvego;
+    float* b_kvego;
+    TRY(dev_alloc(h, o, &kvego, (size_t)3 * D * D));
+    TRY(dev_alloc(h, o, &b_kvego, (size_t)3 * D));
+    CU_TRY(h, cudaMemcpyAsync(kvego, pl.kv.w16, (size_t)2 * D * D * 2, cudaMemcpyDeviceToDevice, st));
+    CU_TRY(h, cudaMemcpyAsync(kvego + (size_t)2 * D * D, pl.ego.w16, (size_t)D * D * 2, cudaMemcpyDeviceToDevice, st));
+    CU_TRY(h, cudaMemcpyAsync(b_kvego, pl.kv.bias, (size_t)2 * D * 4, cudaMemcpyDeviceToDevice, st));
+    CU_TRY(h, cudaMemcpyAsync(b_kvego + 2 * D, pl.ego.bias, (size_t)D * 4, cudaMemcpyDeviceToDevice, st));
+    TRY(encode_wmap(h, &M.layer[l][RM_KVEGO], kvego, 3 * D, D, 3 * D / RES_CL));
+    TRY(encode_wmap(h, &M.layer[l][RM_BEV_OUT], pl.bev_out.w16, D, D, NC));
+    TRY(encode_wmap(h, &M.layer[l][RM_Q], pl.q.w16, D, D, 32));
+    TRY(encode_wmap(h, &M.layer[l][RM_ATTN_OUT], pl.attn_out.w16, D, D, NC));
+    TRY(encode_wmap(h, &M.layer[l][RM_FFN0], pl.ffn0.w16, F, D, F / RES_CL));
+    TRY(encode_wmap(h, &M.layer[l][RM_FFN2], pl.ffn2.w16, D, F, NC));
+    TRY(encode_wmap(h, &M.layer[l][RM_REG0], pl.reg0.w16, D, D, NC));
+    TRY(encode_wmap(h, &M.layer[l][RM_REG2], pl.reg2.w16, D, D, NC));
+    TRY(encode_wmap(h, &M.layer[l][RM_CLS0], pl.cls0.w16, D, D, NC));
+    TRY(encode_wmap(h, &M.layer[l][RM_CLS3], pl.cls3.w16, D, D, NC));
+    TRY(encode_wmap(h, &M.layer[l][RM_CONV], pl.conv.w16, D, pl.conv.K, D / (RES_CL / 2)));
+    ResLayerC& lc = C.layer[l];
+    lc.b_kvego = b_kvego; lc.b_bev_out = pl.bev_out.bias; lc.b_q = pl.q.bias;
+    lc.b_attn_out = pl.attn_out.bias; lc.b_ffn0 = pl.ffn0.bias; lc.b_ffn2 = pl.ffn2.bias;
+    lc.b_reg0 = pl.reg0.bias; lc.b_reg2 = pl.reg2.bias; lc.b_cls0 = pl.cls0.bias;
+    lc.b_cls3 = pl.cls3.bias; lc.b_conv = pl.conv.bias;
+    lc.attw_w = pl.attw_w; lc.attw_b = pl.attw_b;
+    lc.norm1_g = pl.norm1_g; lc.norm1_b = pl.norm1_b; lc.norm2_g = pl.norm2_g; lc.norm2_b = pl.norm2_b;
+    lc.norm3_g = pl.norm3_g; lc.norm3_b = pl.norm3_b;
+    lc.cls_ln2_g = pl.cls_ln2_g; lc.cls_ln2_b = pl.cls_ln2_b;
+    lc.cls_ln5_g = pl.cls_ln5_g; lc.cls_ln5_b = pl.cls_ln5_b;
+    lc.cls6_w = pl.cls6_w; lc.cls6_b = pl.cls6_b; lc.reg4_w = pl.reg4_w; lc.reg4_b = pl.reg4_b;
+    lc.conv_map = &maps_dev->layer[l][RM_CONV];
+  }
+  C.b_enc0 = h->enc0.bias; C.b_enc3 = h->enc3.bias; C.enc_ln_g = h->enc_ln_g; C.enc_ln_b = h->enc_ln_b;
+  C.anchors = h->anchors; C.dim_t = h->dim_t; C.film = h->film;
+  C.A = A; C.P = P; C.Na = Na; C.F = F; C.L = L; C.S = S; C.H = H; C.W = W; C.heads = s.num_heads;
+  C.rcap = (int)std::min((size_t)A * P * 4, (size_t)H * W);
+  C.tiles_max = (C.rcap + 127) / 128;
+  C.oc = OdoConsts{s.lidar_max_x, s.lidar_max_y};
+  const float ac_tr = h->ac[s.trunc_timestep];
+  C.sa_tr = sqrtf(ac_tr); C.sb_tr = sqrtf(1.0f - ac_tr);
+  for (int si = 0; si < S; ++si) {
+    const int t = h->roll[si], prev = t - 1;
+    const float ac_t = h->ac[t], ac_p = prev >= 0 ? h->ac[prev] : 1.0f;
+    C.dc[si] = DdimCoef{sqrtf(ac_t), sqrtf(1.0f - ac_t), sqrtf(ac_p), sqrtf(1.0f - ac_p)};
+  }
+  // weight items in the order the kernel's stages consume them
+  int n = 0;
+  auto item = [&](const CUtensorMap* m, int rows, int K, int n_total) {
+    C.items[n].map = m; C.items[n].rows = (unsigned short)rows;
+    C.items[n].kchunks = (unsigned short)(K / 64); C.items[n].n_total = n_total;
+    ++n;
+  };
+  for (int l = 0; l < L; ++l) item(&maps_dev->layer[l][RM_KVEGO], 3 * D / RES_CL, D, 3 * D);
+  for (int si = 0; si < S; ++si) {
+    item(&maps_dev->enc0, NC, 64 * P, D);
+    item(&maps_dev->enc3, NC, D, D);
+    for (int l = 0; l < L; ++l) {
+      const bool want_cls = (si == S - 1) && (l == L - 1);
+      item(&maps_dev->layer[l][RM_BEV_OUT], NC, D, D);
+      item(&maps_dev->layer[l][RM_Q], 32, D, D);
+      item(&maps_dev->layer[l][RM_ATTN_OUT], NC, D, D);
+      item(&maps_dev->layer[l][RM_FFN0], F / RES_CL, D, F);
+      item(&maps_dev->layer[l][RM_FFN2], NC, F, D);
+      item(&maps_dev->layer[l][RM_REG0], NC, D, D);
+      if (want_cls) item(&maps_dev->layer[l][RM_CLS0], NC, D, D);
+      item(&maps_dev->layer[l][RM_REG2], NC, D, D);
+      if (want_cls) item(&maps_dev->layer[l][RM_CLS3], NC, D, D);
+    }
+  }
+  C.n_items = n;
+  // exchange buffers
+  const size_t MB = (size_t)RES_MAX_B * A;
+  TRY(dev_alloc(h, o, &C.emb16, MB * 64 * P)); TRY(dev_alloc(h, o, &C.o16, MB * D));
+  TRY(dev_alloc(h, o, &C.h16, MB * F)); TRY(dev_alloc(h, o, &C.r1_16, MB * D));
+  TRY(dev_alloc(h, o, &C.e1, MB * D)); TRY(dev_alloc(h, o, &C.q0, MB * D));
+  TRY(dev_alloc(h, o, &C.spart, MB * D * C.tiles_max));
+  TRY(dev_alloc(h, o, &C.x1, MB * D)); TRY(dev_alloc(h, o, &C.y2, MB * D));
+  TRY(dev_alloc(h, o, &C.y3, MB * D)); TRY(dev_alloc(h, o, &C.c1, MB * D));
+  TRY(dev_alloc(h, o, &C.r2, MB * D)); TRY(dev_alloc(h, o, &C.c2, MB * D));
+  TRY(dev_alloc(h, o, &C.regraw, MB * 3 * P));
+  TRY(dev_alloc(h, o, &C.kv, (size_t)RES_MAX_B * L * Na * 2 * D));
+  TRY(dev_alloc(h, o, &C.egov, (size_t)RES_MAX_B * L * D));
+  TRY(dev_alloc(h, o, &C.bev_nhwc, (size_t)RES_MAX_B * H * W * D));
+#undef TRY
+  CU_TRY(h, cudaMemcpyAsync(maps_dev, &M, sizeof(ResMaps), cudaMemcpyHostToDevice, st));
+  CU_TRY(h, cudaMemcpyAsync(h->res_consts, &C, sizeof(ResConsts), cudaMemcpyHostToDevice, st));
+  CU_TRY(h, cudaStreamSynchronize(st));   // maps_host is a local
+  h->res_ok = true;
+  return DDH_OK;
 }
 
 }  // namespace
@@ -447,6 +581,7 @@ int ddh_create(const ddh_shape* s, ddh_handle** out) {
   if (const char* e = getenv("DDH_LAZY_LAYOUT")) h->lazy_layout = atoi(e);
   if (const char* e = getenv("DDH_LAT")) h->lat_enabled = atoi(e);
   if (const char* e = getenv("DDH_LAT_COOP")) h->lat_coop = atoi(e);
+  if (const char* e = getenv("DDH_RES")) h->res_enabled = atoi(e);
   if (const char* e = getenv("DDH_DEBUG_TAPS")) h->debug_taps = atoi(e) != 0;
   default_alphas_cumprod(h->ac);
   make_roll(s->num_steps, h->roll);
@@ -460,6 +595,7 @@ void ddh_destroy(ddh_handle* h) {
   free_all(h->owned_ws);
   free_all(h->owned_host);
   free_all(h->owned_lat);
+  free_all(h->owned_res);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   for (cudaEvent_t e : h->sync_events) cudaEventDestroy(e);
   if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
@@ -593,6 +729,8 @@ int ddh_pack_weights(ddh_handle* h, const ddh_weight_ptrs* w, int precision, voi
   }
 #undef TRY
   CU_TRY(h, cudaGetLastError());
+  rc = build_res(h, st);
+  if (rc) return rc;
   h->packed = true;
   return DDH_OK;
 }
@@ -1090,6 +1228,41 @@ int ddh_forward(ddh_handle* h, const float* ego, const float* agents, const void
   h->ev_spans.clear();
   CU_TRY(h, cudaMemsetAsync(h->conv_rows, 0, (size_t)s.num_layers * s.num_steps * 4, st));
 
+  // <= RES_MAX_B scenes: the whole forward as ONE launch on one 16-CTA cluster per scene
+  if (h->res_ok && !h->profiling && h->precision == DDH_PREC_BF16 && B <= RES_MAX_B) {
+    ResCall call;
+    call.ego = ego; call.agents = agents; call.bev = bev; call.bev_dtype = bev_dtype == DDH_BF16 ? 1 : 0;
+    call.bev_nhwc_bf16 = (bev_layout == DDH_NHWC) ? 1 : 0;
+    h->launches = 0;
+    if (bev_layout == DDH_NHWC && bev_dtype != DDH_BF16) {   // NHWC fp32: one cast pass in front
+      launch_cast_f32_bf16(reinterpret_cast<const float*>(bev), h->res_host.bev_nhwc,
+                           (size_t)B * s.bev_h * s.bev_w * s.bev_channels, st);
+      call.bev = h->res_host.bev_nhwc;
+      call.bev_dtype = 1;
+      h->launches++;
+    }
+    call.noise = noise; call.out_traj = out_traj;
+    call.out_modes = out_modes ? out_modes : h->modes_buf;
+    call.out_scores = out_scores ? out_scores : h->scores_buf;
+    call.out_mode_idx = reinterpret_cast<long long*>(out_mode_idx);
+    call.dbg = h->debug_taps ? h->dbg : nullptr;
+    const int e = launch_res_forward(h->res_consts, call, B, st);
+    if (e) return fail(h, DDH_ERR_CUDA, std::string("res_forward launch: ") + cudaGetErrorString((cudaError_t)e));
+    h->launches++;
+    const ResConsts& R = h->res_host;
+    const size_t MA = (size_t)B * s.num_anchors;
+    h->taps["res_q0"] = {R.q0, MA * D * 4}; h->taps["res_x1"] = {R.x1, MA * D * 4};
+    h->taps["res_y2"] = {R.y2, MA * D * 4}; h->taps["res_y3"] = {R.y3, MA * D * 4};
+    h->taps["res_r2"] = {R.r2, MA * D * 4}; h->taps["res_e1"] = {R.e1, MA * D * 4};
+    h->taps["res_spart"] = {R.spart, MA * D * 4 * R.tiles_max};
+    h->taps["res_kv"] = {R.kv, (size_t)B * s.num_layers * s.num_agents * 2 * D * 4};
+    h->taps["res_egov"] = {R.egov, (size_t)B * s.num_layers * D * 4};
+    h->taps["res_regraw"] = {R.regraw, MA * 3 * s.num_poses * 4};
+    h->taps["res_emb16"] = {R.emb16, MA * 64 * s.num_poses * 2};
+    h->taps["res_o16"] = {R.o16, MA * D * 2}; h->taps["res_h16"] = {R.h16, MA * s.d_ffn * 2};
+    CU_TRY(h, cudaGetLastError());
+    return DDH_OK;
+  }
   // Scene chunks on two streams: scenes are independent, so chunk c+1's HBM-bound layout pass
   // runs under chunk c's tensor-bound conv/GEMMs.  Chunk c starts once layout(c-1) is done.
   if (h->lat_enabled && h->precision == DDH_PREC_BF16 && B <= kLatMaxB &&

@@ -7,6 +7,7 @@
 #include <math.h>
 
 #include "kernels.h"
+#include "geom.cuh"
 
 namespace ddh {
 
@@ -372,19 +373,6 @@ void launch_cast_bf16_f32(const __nv_bfloat16* src, float* dst, size_t n, cudaSt
 // Odometry (de)normalisation, transfuser_model_v2.py:480-500.  Intrinsics keep the
 // reference's operation order (no FMA contraction) so fp32 results track torch's.
 // ===================================================================================
-__device__ __forceinline__ float norm_x(float x) {   // 2*(x+1.2)/56.9 - 1
-  return __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fadd_rn(x, 1.2f)), 56.9f), 1.0f);
-}
-__device__ __forceinline__ float norm_y(float y) {   // 2*(y+20)/46 - 1
-  return __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fadd_rn(y, 20.0f)), 46.0f), 1.0f);
-}
-__device__ __forceinline__ float denorm_x(float v) { // (v+1)/2*56.9 - 1.2
-  return __fsub_rn(__fmul_rn(__fdiv_rn(__fadd_rn(v, 1.0f), 2.0f), 56.9f), 1.2f);
-}
-__device__ __forceinline__ float denorm_y(float v) { // (v+1)/2*46 - 20
-  return __fsub_rn(__fmul_rn(__fdiv_rn(__fadd_rn(v, 1.0f), 2.0f), 46.0f), 20.0f);
-}
-
 // img = sqrt(ac[t]) * norm_odo(plan_anchor) + sqrt(1-ac[t]) * noise     (:591-597)
 __global__ void init_img_kernel(const float* __restrict__ anchors, const float* __restrict__ noise,
                                 float* __restrict__ img, int B, int AP, float sa, float sb) {
@@ -454,37 +442,6 @@ void launch_embed(const float* img, float* pts, float* emb32, __nv_bfloat16* emb
 // (the only pixels at which value_proj has to be evaluated), and per (anchor, pose, corner) the slot of its pixel
 // in that list with the combined weight bilinear * aw.
 // ===================================================================================
-struct Corners {
-  int pix[4];
-  float w[4];
-};
-__device__ __forceinline__ Corners corners_of(float px, float py, int H, int W, OdoConsts oc) {
-  Corners c;
-  const float gx = __fdiv_rn(py, oc.lidar_max_x);
-  const float gy = __fdiv_rn(px, oc.lidar_max_y);
-  const float ix = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.0f), (float)W), 1.0f), 2.0f);
-  const float iy = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.0f), (float)H), 1.0f), 2.0f);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) { c.pix[k] = -1; c.w[k] = 0.f; }
-  if (!(ix > -2.0f && ix < (float)(W + 1) && iy > -2.0f && iy < (float)(H + 1))) return c;
-  const float fx0 = floorf(ix), fy0 = floorf(iy);
-  const int x0 = (int)fx0, y0 = (int)fy0;
-  const float wx1 = __fsub_rn(ix, fx0), wx0 = __fsub_rn(__fadd_rn(fx0, 1.0f), ix);
-  const float wy1 = __fsub_rn(iy, fy0), wy0 = __fsub_rn(__fadd_rn(fy0, 1.0f), iy);
-  const int xs[4] = {x0, x0 + 1, x0, x0 + 1};
-  const int ys[4] = {y0, y0, y0 + 1, y0 + 1};
-  const float ws[4] = {__fmul_rn(wx0, wy0), __fmul_rn(wx1, wy0), __fmul_rn(wx0, wy1),
-                       __fmul_rn(wx1, wy1)};  // nw, ne, sw, se
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    if (xs[k] >= 0 && xs[k] < W && ys[k] >= 0 && ys[k] < H) {
-      c.pix[k] = ys[k] * W + xs[k];
-      c.w[k] = ws[k];
-    }
-  }
-  return c;
-}
-
 __global__ void __launch_bounds__(256) plan_kernel(const float* __restrict__ q0,
                                                    const float* __restrict__ attw_w,
                                                    const float* __restrict__ attw_b,
@@ -681,9 +638,18 @@ __global__ void __launch_bounds__(256, 2) attn_core_kernel(const float* __restri
   const int scene = blockIdx.x;
   const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
   {
+    // 8 independent 16-byte loads in flight per thread (a load-then-store loop would serialise
+    // one memory round trip per iteration: 15 of them for 60 KB of K|V)
     const float4* src = reinterpret_cast<const float4*>(kv + (size_t)scene * Na * 2 * D);
     float4* dst = reinterpret_cast<float4*>(kv_s);
-    for (int i = threadIdx.x; i < Na * 2 * D / 4; i += 256) dst[i] = __ldg(src + i);
+    const int n4 = Na * 2 * D / 4;
+    for (int base = threadIdx.x; base < n4; base += 256 * 8) {
+      float4 t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) if (base + u * 256 < n4) t[u] = __ldg(src + base + u * 256);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) if (base + u * 256 < n4) dst[base + u * 256] = t[u];
+    }
   }
   __syncthreads();
   if (h >= heads) return;
@@ -799,8 +765,13 @@ __global__ void __launch_bounds__(256) reg_finish_kernel(const float* __restrict
   // [24][256] head weights are read from shared memory as (4-address) broadcasts.
   __shared__ __align__(16) float w_s[24 * D];
   __shared__ float b_s[24];
-  for (int i = threadIdx.x; i < 24 * D / 4; i += 256)
-    reinterpret_cast<float4*>(w_s)[i] = __ldg(reinterpret_cast<const float4*>(w4) + i);
+  {
+    float4 t[6];   // 24*256/4 = 1536 float4 = 6 per thread, all in flight
+#pragma unroll
+    for (int u = 0; u < 6; ++u) t[u] = __ldg(reinterpret_cast<const float4*>(w4) + threadIdx.x + u * 256);
+#pragma unroll
+    for (int u = 0; u < 6; ++u) reinterpret_cast<float4*>(w_s)[threadIdx.x + u * 256] = t[u];
+  }
   if (threadIdx.x < 24) b_s[threadIdx.x] = b4[threadIdx.x];
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -220,7 +220,8 @@ def test_host_call_and_layouts_agree(precision):
     if precision == "bf16":
         o3 = head(ft["ego_query"].cuda(), ft["agents_query"].cuda(), nhwc.bfloat16(),
                   noise=nz.cuda(), bev_layout="NHWC")
-        assert head.last_launch_count() < n_dev           # no layout passes
+        # no layout passes (the resident engine runs the whole forward, layout included, as one launch)
+        assert head.last_launch_count() < n_dev or n_dev == 1
         for k in dev:
             assert torch.equal(o3[k], dev[k]), k
 
