@@ -24,6 +24,7 @@
 #include "../../include/ddh.h"
 #include "kernels.h"
 #include "kernels_res.h"
+#include "kernels_res2.h"
 
 using namespace ddh;
 
@@ -125,6 +126,12 @@ struct ddh_handle {
   std::vector<void*> owned_res;
   ResConsts* res_consts = nullptr;             // device copy
   ResConsts res_host;                          // host mirror (workspace pointers for the debug taps)
+  // anchor-resident engine (kernels_res2.cu): same one-launch contract, activations stay on-chip
+  int res_mode = 2;                            // env DDH_RES: 0 off, 1 first-generation engine, 2 anchor-resident
+  bool res2_ok = false;
+  std::vector<void*> owned_res2;
+  R2Consts* res2_consts = nullptr;
+  R2Consts res2_host;
   std::map<std::string, std::pair<const void*, size_t>> taps;
   int launches = 0;
   // optional per-stage device timing (ddh_set_profiling)
@@ -530,6 +537,128 @@ int build_res(ddh_handle* h, cudaStream_t st) {
   return DDH_OK;
 }
 
+// Anchor-resident engine (kernels_res2.cu): full-matrix tensor maps (box 64 k x 128 rows), the
+// static stage schedule its TMA / MMA threads walk, constants and the L2 exchange buffers.
+int build_res2(ddh_handle* h, cudaStream_t st) {
+  h->res2_ok = false;
+  free_all(h->owned_res2);
+  h->res2_consts = nullptr;
+  const ddh_shape& s = h->shp;
+  const int A = s.num_anchors, P = s.num_poses, Na = s.num_agents, F = s.d_ffn, L = s.num_layers,
+            S = s.num_steps, H = s.bev_h, W = s.bev_w;
+  if (h->res_mode != 2 || h->precision != DDH_PREC_BF16) return DDH_OK;
+  if (A > 32 || A * P > 256 || P != 8 || Na > 30 || F > 1024 || F % 256 || s.num_heads != 8 ||
+      H * W > 4096 || H > 64 || W % 32 || L > RES_MAX_L || S > RES_MAX_S || s.bev_channels != 256)
+    return DDH_OK;
+  if (res2_engine_init() != 0) return DDH_OK;
+  auto& o = h->owned_res2;
+  int rc;
+#define TRY(x) do { rc = (x); if (rc) return rc; } while (0)
+  ResMaps* maps_dev = nullptr;
+  TRY(dev_alloc(h, o, &maps_dev, 1));
+  TRY(dev_alloc(h, o, &h->res2_consts, 1));
+  std::vector<ResMaps> maps_host(1);
+  ResMaps& M = maps_host[0];
+  R2Consts& C = h->res2_host;
+  memset(&C, 0, sizeof C);
+  TRY(encode_wmap(h, &M.enc0, h->enc0.w16, D, 64 * P, 128));
+  TRY(encode_wmap(h, &M.enc3, h->enc3.w16, D, D, 128));
+  for (int l = 0; l < L; ++l) {
+    PackedLayer& pl = h->layers[l];
+    __nv_bfloat16* kvego;
+    float* b_kvego;
+    TRY(dev_alloc(h, o, &kvego, (size_t)3 * D * D));
+    TRY(dev_alloc(h, o, &b_kvego, (size_t)3 * D));
+    CU_TRY(h, cudaMemcpyAsync(kvego, pl.kv.w16, (size_t)2 * D * D * 2, cudaMemcpyDeviceToDevice, st));
+    CU_TRY(h, cudaMemcpyAsync(kvego + (size_t)2 * D * D, pl.ego.w16, (size_t)D * D * 2, cudaMemcpyDeviceToDevice, st));
+    CU_TRY(h, cudaMemcpyAsync(b_kvego, pl.kv.bias, (size_t)2 * D * 4, cudaMemcpyDeviceToDevice, st));
+    CU_TRY(h, cudaMemcpyAsync(b_kvego + 2 * D, pl.ego.bias, (size_t)D * 4, cudaMemcpyDeviceToDevice, st));
+    TRY(encode_wmap(h, &M.layer[l][RM_KVEGO], kvego, 3 * D, D, 3 * D / RES_CL));
+    TRY(encode_wmap(h, &M.layer[l][RM_BEV_OUT], pl.bev_out.w16, D, D, 128));
+    TRY(encode_wmap(h, &M.layer[l][RM_Q], pl.q.w16, D, D, 128));
+    TRY(encode_wmap(h, &M.layer[l][RM_ATTN_OUT], pl.attn_out.w16, D, D, 128));
+    TRY(encode_wmap(h, &M.layer[l][RM_FFN0], pl.ffn0.w16, F, D, 128));
+    TRY(encode_wmap(h, &M.layer[l][RM_FFN2], pl.ffn2.w16, D, F, 128));
+    TRY(encode_wmap(h, &M.layer[l][RM_REG0], pl.reg0.w16, D, D, 128));
+    TRY(encode_wmap(h, &M.layer[l][RM_REG2], pl.reg2.w16, D, D, 128));
+    TRY(encode_wmap(h, &M.layer[l][RM_CLS0], pl.cls0.w16, D, D, 128));
+    TRY(encode_wmap(h, &M.layer[l][RM_CLS3], pl.cls3.w16, D, D, 128));
+    TRY(encode_wmap(h, &M.layer[l][RM_CONV], pl.conv.w16, D, pl.conv.K, D / (RES_CL / 2)));
+    ResLayerC& lc = C.layer[l];
+    lc.b_kvego = b_kvego; lc.b_bev_out = pl.bev_out.bias; lc.b_q = pl.q.bias;
+    lc.b_attn_out = pl.attn_out.bias; lc.b_ffn0 = pl.ffn0.bias; lc.b_ffn2 = pl.ffn2.bias;
+    lc.b_reg0 = pl.reg0.bias; lc.b_reg2 = pl.reg2.bias; lc.b_cls0 = pl.cls0.bias;
+    lc.b_cls3 = pl.cls3.bias; lc.b_conv = pl.conv.bias;
+    lc.attw_w = pl.attw_w; lc.attw_b = pl.attw_b;
+    lc.norm1_g = pl.norm1_g; lc.norm1_b = pl.norm1_b; lc.norm2_g = pl.norm2_g; lc.norm2_b = pl.norm2_b;
+    lc.norm3_g = pl.norm3_g; lc.norm3_b = pl.norm3_b;
+    lc.cls_ln2_g = pl.cls_ln2_g; lc.cls_ln2_b = pl.cls_ln2_b;
+    lc.cls_ln5_g = pl.cls_ln5_g; lc.cls_ln5_b = pl.cls_ln5_b;
+    lc.cls6_w = pl.cls6_w; lc.cls6_b = pl.cls6_b; lc.reg4_w = pl.reg4_w; lc.reg4_b = pl.reg4_b;
+    lc.conv_map = &maps_dev->layer[l][RM_CONV];
+  }
+  C.b_enc0 = h->enc0.bias; C.b_enc3 = h->enc3.bias; C.enc_ln_g = h->enc_ln_g; C.enc_ln_b = h->enc_ln_b;
+  C.anchors = h->anchors; C.dim_t = h->dim_t; C.film = h->film;
+  C.A = A; C.P = P; C.Na = Na; C.F = F; C.L = L; C.S = S; C.H = H; C.W = W; C.heads = s.num_heads;
+  C.rcap = (int)std::min((size_t)A * P * 4, (size_t)H * W);
+  C.oc = OdoConsts{s.lidar_max_x, s.lidar_max_y};
+  const float ac_tr = h->ac[s.trunc_timestep];
+  C.sa_tr = sqrtf(ac_tr); C.sb_tr = sqrtf(1.0f - ac_tr);
+  for (int si = 0; si < S; ++si) {
+    const int t = h->roll[si], prev = t - 1;
+    const float ac_t = h->ac[t], ac_p = prev >= 0 ? h->ac[prev] : 1.0f;
+    C.dc[si] = DdimCoef{sqrtf(ac_t), sqrtf(1.0f - ac_t), sqrtf(ac_p), sqrtf(1.0f - ac_p)};
+  }
+  // the schedule, in the program order of the compute warps (kernels_res2.cu)
+  constexpr unsigned short ACC_LIN = 32;
+  int n = 0;
+  auto stage = [&](const CUtensorMap* m, int rows, int mtiles, int K, int acc_col, int flags, int bsel) {
+    R2Stage& g = C.stages[n++];
+    g.map = m; g.rows = (unsigned short)rows; g.mtiles = (unsigned char)mtiles;
+    g.kchunks = (unsigned char)(K / 64); g.acc_col = (unsigned short)acc_col;
+    g.flags = (unsigned char)flags; g.bsel = (unsigned char)bsel;
+  };
+  const int both = R2F_WAITB | R2F_COMMIT;
+  for (int l = 0; l < L; ++l)
+    stage(&maps_dev->layer[l][RM_KVEGO], 3 * D / RES_CL, 1, D, ACC_LIN + 32 * l,
+          R2F_N32 | R2F_RANKROWS | (l == 0 ? R2F_WAITB : 0) | (l == L - 1 ? R2F_COMMIT : 0), 0);
+  for (int si = 0; si < S; ++si) {
+    stage(&maps_dev->enc0, 128, 2, 64 * P, ACC_LIN, both, 0);
+    stage(&maps_dev->enc3, 128, 2, D, ACC_LIN, both, 0);
+    for (int l = 0; l < L; ++l) {
+      const bool want_cls = (si == S - 1) && (l == L - 1);
+      stage(&maps_dev->layer[l][RM_CONV], 0, 0, 0, 0, R2F_CONV, 0);
+      stage(&maps_dev->layer[l][RM_BEV_OUT], 128, 2, D, ACC_LIN, both, 0);
+      stage(&maps_dev->layer[l][RM_Q], 128, 2, D, ACC_LIN, both, 0);
+      stage(&maps_dev->layer[l][RM_ATTN_OUT], 128, 2, D, ACC_LIN, both, 0);
+      stage(&maps_dev->layer[l][RM_FFN0], 128, F / 128, D, ACC_LIN, both, 0);
+      stage(&maps_dev->layer[l][RM_FFN2], 128, 2, F, ACC_LIN, both, 0);
+      if (!want_cls) {
+        stage(&maps_dev->layer[l][RM_REG0], 128, 2, D, ACC_LIN, both, 0);
+        stage(&maps_dev->layer[l][RM_REG2], 128, 2, D, ACC_LIN, both, 0);
+      } else {
+        stage(&maps_dev->layer[l][RM_REG0], 128, 2, D, ACC_LIN, R2F_WAITB, 0);
+        stage(&maps_dev->layer[l][RM_CLS0], 128, 2, D, ACC_LIN + 32, R2F_COMMIT, 0);
+        stage(&maps_dev->layer[l][RM_REG2], 128, 2, D, ACC_LIN, R2F_WAITB, 0);
+        stage(&maps_dev->layer[l][RM_CLS3], 128, 2, D, ACC_LIN + 32, R2F_COMMIT, 1);
+      }
+    }
+  }
+  C.n_stages = n;
+  TRY(dev_alloc(h, o, &C.kv, (size_t)RES_MAX_B * L * Na * 2 * D));
+  TRY(dev_alloc(h, o, &C.egov, (size_t)RES_MAX_B * L * D));
+  TRY(dev_alloc(h, o, &C.bev_nhwc, (size_t)RES_MAX_B * H * W * D));
+  TRY(dev_alloc(h, o, &C.tap_q0, (size_t)RES_MAX_B * A * D));
+  TRY(dev_alloc(h, o, &C.tap_x1, (size_t)RES_MAX_B * A * D));
+  TRY(dev_alloc(h, o, &C.tap_regraw, (size_t)RES_MAX_B * A * 3 * P));
+#undef TRY
+  CU_TRY(h, cudaMemcpyAsync(maps_dev, &M, sizeof(ResMaps), cudaMemcpyHostToDevice, st));
+  CU_TRY(h, cudaMemcpyAsync(h->res2_consts, &C, sizeof(R2Consts), cudaMemcpyHostToDevice, st));
+  CU_TRY(h, cudaStreamSynchronize(st));   // maps_host is a local
+  h->res2_ok = true;
+  return DDH_OK;
+}
+
 }  // namespace
 
 // =====================================================================================
@@ -581,7 +710,8 @@ int ddh_create(const ddh_shape* s, ddh_handle** out) {
   if (const char* e = getenv("DDH_LAZY_LAYOUT")) h->lazy_layout = atoi(e);
   if (const char* e = getenv("DDH_LAT")) h->lat_enabled = atoi(e);
   if (const char* e = getenv("DDH_LAT_COOP")) h->lat_coop = atoi(e);
-  if (const char* e = getenv("DDH_RES")) h->res_enabled = atoi(e);
+  if (const char* e = getenv("DDH_RES")) { h->res_mode = atoi(e); h->res_enabled = (h->res_mode == 1); }
+  else h->res_enabled = 0;
   if (const char* e = getenv("DDH_DEBUG_TAPS")) h->debug_taps = atoi(e) != 0;
   default_alphas_cumprod(h->ac);
   make_roll(s->num_steps, h->roll);
@@ -596,6 +726,7 @@ void ddh_destroy(ddh_handle* h) {
   free_all(h->owned_host);
   free_all(h->owned_lat);
   free_all(h->owned_res);
+  free_all(h->owned_res2);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   for (cudaEvent_t e : h->sync_events) cudaEventDestroy(e);
   if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
@@ -730,6 +861,8 @@ int ddh_pack_weights(ddh_handle* h, const ddh_weight_ptrs* w, int precision, voi
 #undef TRY
   CU_TRY(h, cudaGetLastError());
   rc = build_res(h, st);
+  if (rc) return rc;
+  rc = build_res2(h, st);
   if (rc) return rc;
   h->packed = true;
   return DDH_OK;
@@ -1228,7 +1361,37 @@ int ddh_forward(ddh_handle* h, const float* ego, const float* agents, const void
   h->ev_spans.clear();
   CU_TRY(h, cudaMemsetAsync(h->conv_rows, 0, (size_t)s.num_layers * s.num_steps * 4, st));
 
-  // <= RES_MAX_B scenes: the whole forward as ONE launch on one 16-CTA cluster per scene
+  // <= RES_MAX_B scenes: the whole forward as ONE launch on one 16-CTA cluster per scene,
+  // activations resident on the SM that owns the anchor (kernels_res2.cu)
+  if (h->res2_ok && !h->profiling && h->precision == DDH_PREC_BF16 && B <= RES_MAX_B) {
+    ResCall call;
+    call.ego = ego; call.agents = agents; call.bev = bev; call.bev_dtype = bev_dtype == DDH_BF16 ? 1 : 0;
+    call.bev_nhwc_bf16 = (bev_layout == DDH_NHWC) ? 1 : 0;
+    h->launches = 0;
+    if (bev_layout == DDH_NHWC && bev_dtype != DDH_BF16) {   // NHWC fp32: one cast pass in front
+      launch_cast_f32_bf16(reinterpret_cast<const float*>(bev), h->res2_host.bev_nhwc,
+                           (size_t)B * s.bev_h * s.bev_w * s.bev_channels, st);
+      call.bev = h->res2_host.bev_nhwc;
+      call.bev_dtype = 1;
+      h->launches++;
+    }
+    call.noise = noise; call.out_traj = out_traj;
+    call.out_modes = out_modes ? out_modes : h->modes_buf;
+    call.out_scores = out_scores ? out_scores : h->scores_buf;
+    call.out_mode_idx = reinterpret_cast<long long*>(out_mode_idx);
+    call.dbg = h->debug_taps ? h->dbg : nullptr;
+    const int e = launch_res2_forward(h->res2_consts, call, B, st);
+    if (e) return fail(h, DDH_ERR_CUDA, std::string("res2_forward launch: ") + cudaGetErrorString((cudaError_t)e));
+    h->launches++;
+    const R2Consts& R = h->res2_host;
+    const size_t MA = (size_t)B * s.num_anchors;
+    h->taps["res_q0"] = {R.tap_q0, MA * D * 4}; h->taps["res_x1"] = {R.tap_x1, MA * D * 4};
+    h->taps["res_regraw"] = {R.tap_regraw, MA * 3 * s.num_poses * 4};
+    h->taps["res_kv"] = {R.kv, (size_t)B * s.num_layers * s.num_agents * 2 * D * 4};
+    h->taps["res_egov"] = {R.egov, (size_t)B * s.num_layers * D * 4};
+    CU_TRY(h, cudaGetLastError());
+    return DDH_OK;
+  }
   if (h->res_ok && !h->profiling && h->precision == DDH_PREC_BF16 && B <= RES_MAX_B) {
     ResCall call;
     call.ego = ego; call.agents = agents; call.bev = bev; call.bev_dtype = bev_dtype == DDH_BF16 ? 1 : 0;

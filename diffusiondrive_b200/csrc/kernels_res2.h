@@ -1,0 +1,50 @@
+// Anchor-resident engine of the ddh planning head (sm_100a), second generation of the
+// one-launch small-batch path: one 16-CTA thread-block cluster per scene runs the whole
+// TrajectoryHead.forward_test (transfuser_model_v2.py:578-641) in ONE kernel, and the decoder
+// chain of an anchor never leaves the SM that owns it.  See kernels_res2.cu for the design.
+#pragma once
+#include "kernels_res.h"
+
+namespace ddh {
+
+constexpr int R2_MAX_STAGES = 160;
+
+// One entry of the static schedule that the weight-ring TMA thread and the MMA thread walk in
+// lock-step with the compute warps' program order.
+enum : unsigned char {
+  R2F_WAITB = 1,      // MMA thread waits for the B operand(s) of this stage group first
+  R2F_COMMIT = 2,     // last entry of a stage group: commit the accumulators to the compute warps
+  R2F_CONV = 4,       // marker: the value_proj conv of a layer call runs here (map = conv weights)
+  R2F_N32 = 8,        // 32 activation rows (hoisted K|V|ego stage), standard operand layout
+  R2F_RANKROWS = 16,  // feature-split stage: this CTA streams rows [rank*rows, +rows)
+};
+struct R2Stage {
+  const CUtensorMap* map;   // bf16 [N_out][K] weight matrix, box {64, rows}, 128-byte swizzle
+  unsigned short rows;      // weight rows per ring slot (128; 48 for the hoisted stage)
+  unsigned short acc_col;   // TMEM column of tile 0
+  unsigned char mtiles;     // 128-row output tiles
+  unsigned char kchunks;    // K / 64
+  unsigned char flags;
+  unsigned char bsel;       // 0: main B operand, 1: second (cls branch)
+};
+
+struct alignas(16) R2Consts {
+  ResLayerC layer[RES_MAX_L];
+  const float *b_enc0, *b_enc3, *enc_ln_g, *enc_ln_b, *anchors, *dim_t, *film;   // film [S][L][2D]
+  int A, P, Na, F, L, S, H, W, heads, rcap, n_stages, pad0;
+  OdoConsts oc;
+  float sa_tr, sb_tr;              // sqrt(ac[t_trunc]), sqrt(1 - ac[t_trunc])
+  DdimCoef dc[RES_MAX_S];
+  // exchange through L2 (library-owned workspace, per scene)
+  float *kv, *egov;                 // [B][L][Na][2D], [B][L][D]
+  __nv_bfloat16* bev_nhwc;          // [B][H*W][256] working copy (NCHW callers)
+  // debug taps (written only when ResCall::dbg is set)
+  float *tap_q0, *tap_x1, *tap_regraw;
+  R2Stage stages[R2_MAX_STAGES];
+};
+
+int res2_smem_bytes();
+int res2_engine_init();   // 0 when a 16-CTA cluster of this kernel can be co-scheduled
+int launch_res2_forward(const R2Consts* consts_dev, const ResCall& call, int B, cudaStream_t st);
+
+}  // namespace ddh

@@ -21,6 +21,9 @@ from diffusiondrive_b200 import HeadConfig, TrajectoryHead, synth, _lib  # noqa:
 from oracle import head_oracle  # noqa: E402
 
 
+RES_MODE = int(os.environ.get("RES_MODE", "2"))
+
+
 def err(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
@@ -28,7 +31,7 @@ def err(a, b):
 
 
 def make_head(cfg, sd, res):
-    os.environ["DDH_RES"] = "1" if res else "0"
+    os.environ["DDH_RES"] = str(int(res))
     head = TrajectoryHead(8, 1024, 256, None, cfg, plan_anchor=sd["plan_anchor"].numpy(), precision="bf16")
     head.load_state_dict(sd)
     head = head.cuda().eval()
@@ -46,7 +49,7 @@ def run_stage(B=2):
     trace = {}
     ref = head_oracle.forward_test(sd, ft["ego_query"], ft["agents_query"], ft["bev_feature"], nz,
                                    num_layers=1, step_num=1, trace=trace)
-    head = make_head(cfg, sd, True)
+    head = make_head(cfg, sd, RES_MODE)
     out = head(ft["ego_query"].cuda(), ft["agents_query"].cuda(), ft["bev_feature"].cuda(), noise=nz.cuda())
     torch.cuda.synchronize()
     A = 20
@@ -70,7 +73,7 @@ def run_stage(B=2):
 def run_full():
     sd = synth.make_state_dict()
     cfg = HeadConfig()
-    heads = {"res": make_head(cfg, sd, True), "lat": make_head(cfg, sd, False)}
+    heads = {"res": make_head(cfg, sd, RES_MODE), "lat": make_head(cfg, sd, 0)}
     for B in (1, 2, 3, 8):
         ft = synth.make_features(B)
         nz = synth.make_noise(B)
@@ -96,9 +99,10 @@ def run_full():
 def run_time():
     sd = synth.make_state_dict()
     cfg = HeadConfig()
-    for name, res in (("res", True), ("lat", False)):
+    modes = (("res", RES_MODE),) if os.environ.get("ONLY_RES") else (("res", RES_MODE), ("res1", 1), ("lat", 0))
+    for name, res in modes:
         head = make_head(cfg, sd, res)
-        for B in (1, 2, 4, 8):
+        for B in ((1,) if os.environ.get("ONLY_RES") else (1, 2, 4, 8)):
             ft = synth.make_features(B)
             nz = synth.make_noise(B).cuda()
             ins = [ft["ego_query"].cuda(), ft["agents_query"].cuda(), ft["bev_feature"].cuda()]
@@ -114,7 +118,7 @@ def run_time():
             ts = sorted(a.elapsed_time(b) * 1e3 for a, b in evs)
             print(f"[time {name}] B={B} launches={head.last_launch_count()} p50 {ts[len(ts)//2]:.1f} us "
                   f"min {ts[0]:.1f} us", flush=True)
-            if B == 1 and res:
+            if B == 1 and res == RES_MODE:
                 dbg = head.debug_tap("dbg", np.int64)[:1000]
                 n = int((dbg > 0).sum())
                 if n > 2:
