@@ -547,22 +547,33 @@ int build_res2(ddh_handle* h, cudaStream_t st) {
   const int A = s.num_anchors, P = s.num_poses, Na = s.num_agents, F = s.d_ffn, L = s.num_layers,
             S = s.num_steps, H = s.bev_h, W = s.bev_w;
   if (h->res_mode != 2 || h->precision != DDH_PREC_BF16) return DDH_OK;
-  if (A > 32 || A * P > 256 || P != 8 || Na > 30 || F > 1024 || F % 256 || s.num_heads != 8 ||
+  if (A > 28 || A * P > 256 || P != 8 || Na > 30 || F > 1024 || F % 256 || s.num_heads != 8 ||
       H * W > 4096 || H > 64 || W % 32 || L > RES_MAX_L || S > RES_MAX_S || s.bev_channels != 256)
     return DDH_OK;
-  if (res2_engine_init() != 0) return DDH_OK;
+  if (const int why = res2_engine_init()) {
+    if (getenv("DDH_VERBOSE")) fprintf(stderr, "ddh: anchor-resident engine unavailable (init step %d)\n", why);
+    return DDH_OK;
+  }
   auto& o = h->owned_res2;
   int rc;
 #define TRY(x) do { rc = (x); if (rc) return rc; } while (0)
-  ResMaps* maps_dev = nullptr;
-  TRY(dev_alloc(h, o, &maps_dev, 1));
   TRY(dev_alloc(h, o, &h->res2_consts, 1));
-  std::vector<ResMaps> maps_host(1);
-  ResMaps& M = maps_host[0];
   R2Consts& C = h->res2_host;
   memset(&C, 0, sizeof C);
-  TRY(encode_wmap(h, &M.enc0, h->enc0.w16, D, 64 * P, 128));
-  TRY(encode_wmap(h, &M.enc3, h->enc3.w16, D, D, 128));
+  // weights re-packed as pre-swizzled shared-memory images (one bulk copy per 32 KiB fill)
+  auto pack = [&](const __nv_bfloat16* w, int N, int K, int rows, const void** out) -> int {
+    __nv_bfloat16* pk;
+    int r = dev_alloc(h, o, &pk, (size_t)N * K);
+    if (r) return r;
+    launch_pack_sw128(w, pk, N, K, rows, st);
+    *out = pk;
+    return DDH_OK;
+  };
+  const void *w_enc0, *w_enc3;
+  struct LayerW { const void *kvego, *bev_out, *q, *attn_out, *ffn0, *ffn2, *reg0, *reg2, *cls0, *cls3, *conv; };
+  std::vector<LayerW> lw(L);
+  TRY(pack(h->enc0.w16, D, 64 * P, 64, &w_enc0));
+  TRY(pack(h->enc3.w16, D, D, 64, &w_enc3));
   for (int l = 0; l < L; ++l) {
     PackedLayer& pl = h->layers[l];
     __nv_bfloat16* kvego;
@@ -573,17 +584,17 @@ int build_res2(ddh_handle* h, cudaStream_t st) {
     CU_TRY(h, cudaMemcpyAsync(kvego + (size_t)2 * D * D, pl.ego.w16, (size_t)D * D * 2, cudaMemcpyDeviceToDevice, st));
     CU_TRY(h, cudaMemcpyAsync(b_kvego, pl.kv.bias, (size_t)2 * D * 4, cudaMemcpyDeviceToDevice, st));
     CU_TRY(h, cudaMemcpyAsync(b_kvego + 2 * D, pl.ego.bias, (size_t)D * 4, cudaMemcpyDeviceToDevice, st));
-    TRY(encode_wmap(h, &M.layer[l][RM_KVEGO], kvego, 3 * D, D, 3 * D / RES_CL));
-    TRY(encode_wmap(h, &M.layer[l][RM_BEV_OUT], pl.bev_out.w16, D, D, 128));
-    TRY(encode_wmap(h, &M.layer[l][RM_Q], pl.q.w16, D, D, 128));
-    TRY(encode_wmap(h, &M.layer[l][RM_ATTN_OUT], pl.attn_out.w16, D, D, 128));
-    TRY(encode_wmap(h, &M.layer[l][RM_FFN0], pl.ffn0.w16, F, D, 128));
-    TRY(encode_wmap(h, &M.layer[l][RM_FFN2], pl.ffn2.w16, D, F, 128));
-    TRY(encode_wmap(h, &M.layer[l][RM_REG0], pl.reg0.w16, D, D, 128));
-    TRY(encode_wmap(h, &M.layer[l][RM_REG2], pl.reg2.w16, D, D, 128));
-    TRY(encode_wmap(h, &M.layer[l][RM_CLS0], pl.cls0.w16, D, D, 128));
-    TRY(encode_wmap(h, &M.layer[l][RM_CLS3], pl.cls3.w16, D, D, 128));
-    TRY(encode_wmap(h, &M.layer[l][RM_CONV], pl.conv.w16, D, pl.conv.K, D / (RES_CL / 2)));
+    TRY(pack(kvego, 3 * D, D, 3 * D / RES_CL, &lw[l].kvego));
+    TRY(pack(pl.bev_out.w16, D, D, 64, &lw[l].bev_out));
+    TRY(pack(pl.q.w16, D, D, 64, &lw[l].q));
+    TRY(pack(pl.attn_out.w16, D, D, 64, &lw[l].attn_out));
+    TRY(pack(pl.ffn0.w16, F, D, 64, &lw[l].ffn0));
+    TRY(pack(pl.ffn2.w16, D, F, 64, &lw[l].ffn2));
+    TRY(pack(pl.reg0.w16, D, D, 64, &lw[l].reg0));
+    TRY(pack(pl.reg2.w16, D, D, 64, &lw[l].reg2));
+    TRY(pack(pl.cls0.w16, D, D, 64, &lw[l].cls0));
+    TRY(pack(pl.cls3.w16, D, D, 64, &lw[l].cls3));
+    TRY(pack(pl.conv.w16, D, pl.conv.K, 64, &lw[l].conv));
     ResLayerC& lc = C.layer[l];
     lc.b_kvego = b_kvego; lc.b_bev_out = pl.bev_out.bias; lc.b_q = pl.q.bias;
     lc.b_attn_out = pl.attn_out.bias; lc.b_ffn0 = pl.ffn0.bias; lc.b_ffn2 = pl.ffn2.bias;
@@ -595,7 +606,7 @@ int build_res2(ddh_handle* h, cudaStream_t st) {
     lc.cls_ln2_g = pl.cls_ln2_g; lc.cls_ln2_b = pl.cls_ln2_b;
     lc.cls_ln5_g = pl.cls_ln5_g; lc.cls_ln5_b = pl.cls_ln5_b;
     lc.cls6_w = pl.cls6_w; lc.cls6_b = pl.cls6_b; lc.reg4_w = pl.reg4_w; lc.reg4_b = pl.reg4_b;
-    lc.conv_map = &maps_dev->layer[l][RM_CONV];
+    lc.conv_map = nullptr;
   }
   C.b_enc0 = h->enc0.bias; C.b_enc3 = h->enc3.bias; C.enc_ln_g = h->enc_ln_g; C.enc_ln_b = h->enc_ln_b;
   C.anchors = h->anchors; C.dim_t = h->dim_t; C.film = h->film;
@@ -609,38 +620,40 @@ int build_res2(ddh_handle* h, cudaStream_t st) {
     const float ac_t = h->ac[t], ac_p = prev >= 0 ? h->ac[prev] : 1.0f;
     C.dc[si] = DdimCoef{sqrtf(ac_t), sqrtf(1.0f - ac_t), sqrtf(ac_p), sqrtf(1.0f - ac_p)};
   }
-  // the schedule, in the program order of the compute warps (kernels_res2.cu)
-  constexpr unsigned short ACC_LIN = 32;
-  int n = 0;
-  auto stage = [&](const CUtensorMap* m, int rows, int mtiles, int K, int acc_col, int flags, int bsel) {
+  // the schedule, in the program order of the compute warps (kernels_res2.cu); chain stage k
+  // reads B operand buffer k & 1
+  constexpr unsigned short ACC_LIN = 256;   // linear tile t at ACC_LIN + 64 t (4 accumulators of 16 columns)
+  int n = 0, k = 0;
+  auto stage = [&](const void* m, int rows, int mtiles, int K, int acc_col, int flags, int bsel) {
     R2Stage& g = C.stages[n++];
-    g.map = m; g.rows = (unsigned short)rows; g.mtiles = (unsigned char)mtiles;
+    g.w = m; g.rows = (unsigned short)rows; g.mtiles = (unsigned char)mtiles;
     g.kchunks = (unsigned char)(K / 64); g.acc_col = (unsigned short)acc_col;
     g.flags = (unsigned char)flags; g.bsel = (unsigned char)bsel;
   };
   const int both = R2F_WAITB | R2F_COMMIT;
   for (int l = 0; l < L; ++l)
-    stage(&maps_dev->layer[l][RM_KVEGO], 3 * D / RES_CL, 1, D, ACC_LIN + 32 * l,
-          R2F_N32 | R2F_RANKROWS | (l == 0 ? R2F_WAITB : 0) | (l == L - 1 ? R2F_COMMIT : 0), 0);
+    stage(lw[l].kvego, 3 * D / RES_CL, 1, D, ACC_LIN + 32 * l,
+          R2F_N32 | R2F_RANK16 | (l == 0 ? R2F_WAITB : 0) | (l == L - 1 ? R2F_COMMIT : 0), 0);
+  const int fq = F / 4;   // hidden features per CTA
   for (int si = 0; si < S; ++si) {
-    stage(&maps_dev->enc0, 128, 2, 64 * P, ACC_LIN, both, 0);
-    stage(&maps_dev->enc3, 128, 2, D, ACC_LIN, both, 0);
+    stage(w_enc0, 64, 1, 64 * P, ACC_LIN, both, k++ & 1);
+    stage(w_enc3, 64, 1, D, ACC_LIN, both, k++ & 1);
     for (int l = 0; l < L; ++l) {
       const bool want_cls = (si == S - 1) && (l == L - 1);
-      stage(&maps_dev->layer[l][RM_CONV], 0, 0, 0, 0, R2F_CONV, 0);
-      stage(&maps_dev->layer[l][RM_BEV_OUT], 128, 2, D, ACC_LIN, both, 0);
-      stage(&maps_dev->layer[l][RM_Q], 128, 2, D, ACC_LIN, both, 0);
-      stage(&maps_dev->layer[l][RM_ATTN_OUT], 128, 2, D, ACC_LIN, both, 0);
-      stage(&maps_dev->layer[l][RM_FFN0], 128, F / 128, D, ACC_LIN, both, 0);
-      stage(&maps_dev->layer[l][RM_FFN2], 128, 2, F, ACC_LIN, both, 0);
+      stage(lw[l].conv, 0, 0, 0, 0, R2F_CONV, 0);
+      stage(lw[l].bev_out, 64, 1, D, ACC_LIN, both, k++ & 1);
+      stage(lw[l].q, 64, 1, D, ACC_LIN, both, k++ & 1);
+      stage(lw[l].attn_out, 64, 1, D, ACC_LIN, both, k++ & 1);
+      stage(lw[l].ffn0, 64, fq / 64, D, ACC_LIN, both, k++ & 1);
+      stage(lw[l].ffn2, 64, 1, F, ACC_LIN, both, k++ & 1);
       if (!want_cls) {
-        stage(&maps_dev->layer[l][RM_REG0], 128, 2, D, ACC_LIN, both, 0);
-        stage(&maps_dev->layer[l][RM_REG2], 128, 2, D, ACC_LIN, both, 0);
+        stage(lw[l].reg0, 64, 1, D, ACC_LIN, both, k++ & 1);
+        stage(lw[l].reg2, 64, 1, D, ACC_LIN, both, k++ & 1);
       } else {
-        stage(&maps_dev->layer[l][RM_REG0], 128, 2, D, ACC_LIN, R2F_WAITB, 0);
-        stage(&maps_dev->layer[l][RM_CLS0], 128, 2, D, ACC_LIN + 32, R2F_COMMIT, 0);
-        stage(&maps_dev->layer[l][RM_REG2], 128, 2, D, ACC_LIN, R2F_WAITB, 0);
-        stage(&maps_dev->layer[l][RM_CLS3], 128, 2, D, ACC_LIN + 32, R2F_COMMIT, 1);
+        stage(lw[l].reg0, 64, 1, D, ACC_LIN, R2F_WAITB, k & 1);
+        stage(lw[l].cls0, 64, 1, D, ACC_LIN + 64, R2F_COMMIT, k++ & 1);
+        stage(lw[l].reg2, 64, 1, D, ACC_LIN, R2F_WAITB, k++ & 1);
+        stage(lw[l].cls3, 64, 1, D, ACC_LIN + 64, R2F_COMMIT, 2);
       }
     }
   }
@@ -652,9 +665,8 @@ int build_res2(ddh_handle* h, cudaStream_t st) {
   TRY(dev_alloc(h, o, &C.tap_x1, (size_t)RES_MAX_B * A * D));
   TRY(dev_alloc(h, o, &C.tap_regraw, (size_t)RES_MAX_B * A * 3 * P));
 #undef TRY
-  CU_TRY(h, cudaMemcpyAsync(maps_dev, &M, sizeof(ResMaps), cudaMemcpyHostToDevice, st));
   CU_TRY(h, cudaMemcpyAsync(h->res2_consts, &C, sizeof(R2Consts), cudaMemcpyHostToDevice, st));
-  CU_TRY(h, cudaStreamSynchronize(st));   // maps_host is a local
+  CU_TRY(h, cudaStreamSynchronize(st));
   h->res2_ok = true;
   return DDH_OK;
 }

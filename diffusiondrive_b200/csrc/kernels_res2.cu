@@ -25,6 +25,7 @@
 //
 // Numerics are those of the bf16 tensor engine (kernels_tc.cu): bf16 operands, fp32 accumulate,
 // fp32 LayerNorm / softmax / embeddings / residuals / regression tail.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "geom.cuh"
@@ -34,50 +35,68 @@
 namespace ddh {
 namespace {
 
-constexpr int NT = 352;                      // 8 compute warps + ring TMA + MMA + conv-weight TMA
+constexpr int NT = 352;                      // 8 compute warps + 2 weight-copy warps + MMA warp
+constexpr int NPROD = 2;                     // a thread's bulk copies run one at a time (~750 cycles each,
+                                             // measured: tools/ubench_ingest.cu), so two threads issue them
 constexpr int NCT = 256;                     // compute threads
-constexpr int NAL = 2;                       // anchors per CTA
-constexpr int SLOT = 16 * 1024;              // weight ring slot: 128 rows x 64 bf16
-constexpr int NSLOT = 5;
+constexpr int GF = 4;                        // feature groups (= CTAs per anchor group)
+constexpr int NROW = 8;                      // activation rows of a chain B operand (anchors per group <= 7)
+constexpr int SLOT = 32 * 1024;              // weight ring slot: 64 rows x 256 k bf16, one bulk copy of the
+                                             // pre-swizzled image (pack_sw128_kernel)
+constexpr int NSLOT = 2;
+constexpr int FKC = 4;                       // k-chunks per fill
 constexpr int RING = NSLOT * SLOT;
-constexpr int NCC = D / (RES_CL / 2);        // conv output columns per CTA (32)
-constexpr int A_TILE = 128 * 128;
+constexpr int CROWS = 64;                    // conv tile: 64 unique pixels x 64 output columns per CTA
+constexpr int CCOLS = 64;
+constexpr int CA_TILE = CROWS * 128;
 constexpr int CNS = 4;                       // conv pipeline stages
-constexpr int CSTAGE = A_TILE + NCC * 128;
+constexpr int CSTAGE = CA_TILE + CCOLS * 128;
 constexpr int PIPE = CNS * CSTAGE;
 constexpr int KC_CONV = 9 * (D / 64);        // 36 k-chunks: (tap, 64-channel chunk)
 constexpr int BCH = 1024;                    // chain B operand: 8 rows x 128 B per k-chunk; rows 8..15 of
                                              // the N = 16 operand alias rows 0..7 (descriptor SBO = 0)
 constexpr int BCH32 = 4096;                  // hoisted stage: 32 rows x 128 B
-constexpr uint32_t ACC_CONV = 0, ACC_LIN = 32;
-constexpr int TMEM_COLS = 256;
-constexpr int VS_LD = NCC + 4;
-constexpr int KS_LD = D + 4;                 // padded K rows: conflict-free 128-bit reads, lane = agent
+// Dependent tcgen05.mma (same accumulator) issue ~140 cycles apart whatever their shape (measured), so
+// the 4 K=16 steps of a 64-wide k-chunk go to 4 independent accumulators that the epilogue adds up.
+constexpr int NACC = 4;
+constexpr uint32_t ACC_CONV = 0, ACC_LIN = 256;   // conv: 4 x 64 columns; linear tile t: ACC_LIN + 64 t + 16 j
+constexpr int TMEM_COLS = 512;
+constexpr int VS_LD = CCOLS + 4;
+constexpr int KS_LD = 64 + 4;                // padded K rows (2 heads): conflict-free 128-bit reads, lane = agent
 
-// fixed region behind RING + PIPE
+// exchange region X behind RING + PIPE: two chain B operands and two fp32 row buffers that the
+// CTAs of an anchor group push into; during the conv phase the same bytes hold the sampled-feature
+// partials (pushed by the conv CTAs) and the conv drain staging
+constexpr int X_BOP = 0;                     // 2 x 16 KiB
+constexpr int X_ACT = 32768;                 // 2 x float [NROW][256]
+constexpr int X_SP = 0;                      // float [4 tiles][NAG][256]   (conv phase, <= 28 KiB)
+constexpr int X_VS = 30720;                  // float [64][VS_LD]           (conv phase)
+constexpr int XBYTES = 49152;
+// chain-phase use of the idle conv pipeline buffers
+constexpr int P_KV = 0;                      // float Ks[32][KS_LD] | Vv[32][64]
+constexpr int P_QL = 20480;                  // float q of my two heads [NROW][64]
+constexpr int P_ACT2 = 32768;                // cls branch: 2 x float [NROW][256]
+constexpr int P_BOP2 = 49152;                // cls branch B operand (4 KiB)
+// fixed region behind X
 constexpr int F_CONSTS = 0;                  // R2Consts
-constexpr int F_BOP = 4096;                  // main B operand (16 KiB) | also the conv drain staging
-constexpr int F_BOP2 = F_BOP + 16384;        // cls-branch B operand (4 KiB)
-constexpr int F_Q0 = F_BOP2 + 4096;          // float [NAL][256]
-constexpr int F_X1 = F_Q0 + 2048;
-constexpr int F_T0 = F_X1 + 2048;            // scratch rows (q, r2)
-constexpr int F_SP = F_T0 + 2048;            // float [2 tiles][NAL][256] sampled-feature partials
-constexpr int F_EGO = F_SP + 4096;           // float [L][256]
+constexpr int F_Q0 = 4096;                   // float [NROW][256]
+constexpr int F_X1 = F_Q0 + 8192;
+constexpr int F_EGO = F_X1 + 8192;           // float [L][256]
 constexpr int F_ENT = F_EGO + 4096;          // EntPair [A*P*4] (<= 1024)
 constexpr int F_UPIX = F_ENT + 8192;         // int [rcap] (<= 1024)
 constexpr int F_BM = F_UPIX + 4096;          // uint [HW/32] pixel bitmap | int [HW/32] prefix
 constexpr int F_AW = F_BM + 1024;            // float [L][A*P]
 constexpr int F_PTS = F_AW + 4096;           // float [A*P*2] every anchor's current points
-constexpr int F_OWN = F_PTS + 2048;          // own img [NAL][16] | own pts [NAL][16] | regraw [NAL][24] | modes [NAL][24]
-constexpr int F_RED = F_OWN + 1024;          // block-reduction scratch
-constexpr int F_MISC = F_RED + 512;          // conv bias slice [32] | logits [64] | ints [16]
+constexpr int F_OWN = F_PTS + 2048;          // diffused sample of my outputs: float [NROW][24]
+constexpr int F_MISC = F_OWN + 1024;         // conv bias slice [64] | ints [16]
 constexpr int F_FIN = F_MISC + 512;          // rank 0: scores [32] | modes [A*3P] (<= 768)
 constexpr int F_BAR = F_FIN + 3328;
 constexpr int F_END = F_BAR + 256;
-constexpr int SMEM_BYTES = RING + PIPE + F_END + 1024;
-static_assert(sizeof(R2Consts) <= F_BOP - F_CONSTS, "R2Consts must fit its shared-memory slot");
+constexpr int SMEM_BYTES = RING + PIPE + XBYTES + F_END + 1024;
+static_assert(sizeof(R2Consts) <= F_Q0 - F_CONSTS, "R2Consts must fit its shared-memory slot");
 static_assert(sizeof(R2Consts) % 16 == 0, "R2Consts is copied as uint4");
-static_assert(128 * VS_LD * 4 <= 16384 + 4096, "drain staging must fit the B operand buffers");
+static_assert(X_VS + CROWS * VS_LD * 4 <= XBYTES, "drain staging must fit the exchange region");
+static_assert(4 * 7 * D * 4 <= X_VS, "sampled-feature partials must not reach the drain staging");
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 struct EntPair { int slot; float w; };
@@ -129,9 +148,11 @@ __device__ __forceinline__ void mbar_wait_acq_cluster(uint32_t bar, uint32_t par
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// D = f32, A = B = bf16, K-major, M = 128, N = n
-__device__ __forceinline__ constexpr uint32_t idesc_m128(uint32_t n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+// D = f32, A = B = bf16, K-major, M = 64, N = n.  An M = 64 instruction occupies the tensor pipe
+// for half the time of an M = 128 one whatever N is (measured); its accumulator row r lives in
+// TMEM lane 32 * (r / 16) + r % 16 (probed: tools/ubench_m64.cu).
+__device__ __forceinline__ constexpr uint32_t idesc_m64(uint32_t n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((64u >> 4) << 24);
 }
 // K-major 128-byte-swizzled operand whose 8-row groups are `sbo` bytes apart
 __device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t saddr, uint32_t sbo) {
@@ -204,6 +225,80 @@ __device__ __forceinline__ void layout_item(const TI* __restrict__ src, __nv_bfl
   }
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t u[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(u[i]);
+}
+__device__ __forceinline__ void st_cluster_b16(uint32_t raddr, __nv_bfloat16 v) {
+  asm volatile("st.shared::cluster.b16 [%0], %1;" ::"r"(raddr), "h"(*reinterpret_cast<unsigned short*>(&v)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// my shared memory -> a peer CTA's shared memory; the peer's mbarrier receives the byte count
+__device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes,
+                                                  uint32_t mbar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(mbar_cluster) : "memory");
+}
+// global -> my shared memory, one contiguous chunk; the mbarrier receives the byte count
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void ln_row_reg(float (&v)[8], const float (&g)[8], const float (&b)[8]) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += v[i];
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float d = v[i] - mean;
+    q += d * d;
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / D) + LN_EPS);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = (v[i] - mean) * rstd * g[i] + b[i];
+}
+__device__ __forceinline__ void ldg8(const float* p, int lane, float (&o)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p + lane * 4));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p + 128 + lane * 4));
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
+  o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+// fp32 row buffers are slice-major [feature group][row][64] so that a CTA's slice is contiguous:
+// lane's 8 values of row n (features lane*4+{0..3} and 128+lane*4+{0..3})
+__device__ __forceinline__ void act_load8(const float* act, int n, int lane, float (&o)[8]) {
+  const float* p = act + (lane >> 4) * (NROW * 64) + n * 64 + (lane & 15) * 4;
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 2 * NROW * 64);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
+  o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+
+// lane's 8 values of row n (columns lane*4+{0..3} and 128+lane*4+{0..3}) -> bf16 chain B operand
+__device__ __forceinline__ void bt_store8(uint8_t* bt, int n, int lane, const float (&v)[8]) {
+#pragma unroll
+  for (int h2 = 0; h2 < 2; ++h2) {
+    const int k = h2 * 128 + lane * 4;
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(v[4 * h2 + 0], v[4 * h2 + 1]);
+    __nv_bfloat162 p1 = __floats2bfloat162_rn(v[4 * h2 + 2], v[4 * h2 + 3]);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&p0);
+    u.y = *reinterpret_cast<uint32_t*>(&p1);
+    *reinterpret_cast<uint2*>(bt + sw_off(n, k, BCH)) = u;
+  }
+}
+__device__ __forceinline__ void store8(float* p, int lane, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p + lane * 4) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 128 + lane * 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
 __global__ void __launch_bounds__(NT, 1)
 res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
   extern __shared__ uint8_t smem_raw[];
@@ -216,15 +311,13 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
   const int scene = (int)cluster_id_x();
   uint8_t* pipe = sm + RING;
   const uint32_t pipe_addr = sm_addr + RING;
-  uint8_t* fix = sm + RING + PIPE;
-  const uint32_t fix_addr = sm_addr + RING + PIPE;
+  uint8_t* xr = sm + RING + PIPE;
+  const uint32_t x_addr = sm_addr + RING + PIPE;
+  uint8_t* fix = xr + XBYTES;
+  const uint32_t fix_addr = x_addr + XBYTES;
   const R2Consts& C = *reinterpret_cast<const R2Consts*>(fix + F_CONSTS);
-  uint8_t* bop = fix + F_BOP;
-  uint8_t* bop2 = fix + F_BOP2;
   float* q0_s = reinterpret_cast<float*>(fix + F_Q0);
   float* x1_s = reinterpret_cast<float*>(fix + F_X1);
-  float* t0_s = reinterpret_cast<float*>(fix + F_T0);
-  float* sp_s = reinterpret_cast<float*>(fix + F_SP);
   float* ego_s = reinterpret_cast<float*>(fix + F_EGO);
   EntPair* ent = reinterpret_cast<EntPair*>(fix + F_ENT);
   int* upix_s = reinterpret_cast<int*>(fix + F_UPIX);
@@ -232,13 +325,9 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
   int* pre_s = reinterpret_cast<int*>(fix + F_BM + 512);
   float* aw_s = reinterpret_cast<float*>(fix + F_AW);
   float* pts_s = reinterpret_cast<float*>(fix + F_PTS);
-  float* img_o = reinterpret_cast<float*>(fix + F_OWN);          // [NAL][16]
-  float* pts_o = img_o + NAL * 16;                               // [NAL][16]
-  float* raw_o = pts_o + NAL * 16;                               // [NAL][24]
-  float* red_s = reinterpret_cast<float*>(fix + F_RED);          // 2 x [8][4]
-  float* cbias_s = reinterpret_cast<float*>(fix + F_MISC);       // [32]
-  float* logit_s = cbias_s + 32;                                 // [64]
-  int* ints_s = reinterpret_cast<int*>(logit_s + 64);            // [16]
+  float* img_o = reinterpret_cast<float*>(fix + F_OWN);          // [NROW][24], my outputs only
+  float* cbias_s = reinterpret_cast<float*>(fix + F_MISC);       // [64]
+  int* ints_s = reinterpret_cast<int*>(cbias_s + 64);            // [16]
   unsigned long long* need_s = reinterpret_cast<unsigned long long*>(ints_s + 8);
   float* fin_scores = reinterpret_cast<float*>(fix + F_FIN);     // [32]
   float* fin_modes = fin_scores + 32;                            // [A*3P]
@@ -252,7 +341,8 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
   const uint32_t b_ready = conv_acc + 16;
   const uint32_t conv_go = conv_acc + 24;
   const uint32_t cl_bar = conv_acc + 32;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(fix + F_BAR + (2 * NSLOT + 2 * CNS + 5) * 8);
+  const uint32_t xbar0 = conv_acc + 40;   // two exchange barriers (stage parity): bytes pushed by my group land here
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(fix + F_BAR + (2 * NSLOT + 2 * CNS + 8) * 8);
 
   {  // constants -> shared memory
     const uint4* s = reinterpret_cast<const uint4*>(gconsts);
@@ -267,6 +357,8 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
     mbar_init(b_ready, NCT);
     mbar_init(conv_go, 1);
     mbar_init(cl_bar, RES_CL);
+    mbar_init(xbar0, 1);
+    mbar_init(xbar0 + 8, 1);
     fence_barrier_init();
   }
   if (warp == 8) tmem_alloc<TMEM_COLS>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
@@ -278,30 +370,53 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
 
   const int A = C.A, P = C.P, Na = C.Na, L = C.L, S = C.S, H = C.H, W = C.W;
   const int AP = A * P, HW = H * W;
-  const int tile = rank / (RES_CL / 2), cgp = rank % (RES_CL / 2);
+  const int ag = rank >> 2, fg = rank & 3;          // anchor group, feature group (also conv row tile, column group)
+  const int NAG = (A + 3) >> 2;                     // anchors per group
 
-  // =============================================================== weight-ring TMA thread
-  if (warp == 8) {
+  // =============================================================== weight-copy threads
+  if (warp >= 8 && warp < 8 + NPROD) {
     if (lane == 0) {
-      int seq = 0;
+      const int me = warp - 8;
+      int seq = 0, cg = 0;
+      uint32_t gopar = 0;
       for (int si = 0; si < C.n_stages; ++si) {
         const R2Stage stg = C.stages[si];
-        if (stg.flags & R2F_CONV) continue;
-        const int row0 = (stg.flags & R2F_RANKROWS) ? rank * (int)stg.rows : 0;
-        for (int mt = 0; mt < (int)stg.mtiles; ++mt)
-          for (int kc = 0; kc < (int)stg.kchunks; ++kc) {
-            const int slot = seq % NSLOT, use = seq / NSLOT;
-            if (use > 0) mbar_wait(ring_empty(slot), (uint32_t)((use - 1) & 1));
-            mbar_arrive_expect_tx(ring_full(slot), (uint32_t)stg.rows * 128u);
-            tma_load_2d(sm_addr + slot * SLOT, stg.map, ring_full(slot), kc * 64, row0 + mt * 128);
-            ++seq;
+        if (stg.flags & R2F_CONV) {   // the conv's weight tiles: 8 KiB per k-chunk
+          mbar_wait(conv_go, gopar);
+          gopar ^= 1u;
+          const int nu = *reinterpret_cast<volatile int*>(ints_s + 4);
+          const int passes = (nu + 255) / 256;
+          const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(stg.w) + (size_t)fg * KC_CONV * (CCOLS * 128);
+          for (int pass = 0; pass < passes; ++pass) {
+            if (pass * 256 + ag * CROWS >= nu) continue;
+            for (int kc = 0; kc < KC_CONV; ++kc) {
+              const int g = cg + kc, s = g % CNS;
+              if ((g % NPROD) != me) continue;
+              mbar_wait(conv_empty(s), (uint32_t)(((g / CNS) & 1) ^ 1));
+              mbar_arrive_expect_tx(conv_full(s), CCOLS * 128);
+              bulk_load(pipe_addr + s * CSTAGE + CA_TILE, wsrc + (size_t)kc * (CCOLS * 128), CCOLS * 128, conv_full(s));
+            }
+            cg += KC_CONV;
           }
+          continue;
+        }
+        const uint32_t fill_bytes = (uint32_t)stg.rows * 128u * FKC;
+        const int nfill = (int)stg.mtiles * (int)stg.kchunks / FKC;
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(stg.w) +
+                              (size_t)((stg.flags & R2F_RANK16) ? rank : fg) * nfill * fill_bytes;
+        for (int f = 0; f < nfill; ++f, ++seq) {
+          if ((seq % NPROD) != me) continue;
+          const int slot = seq % NSLOT, use = seq / NSLOT;
+          if (use > 0) mbar_wait(ring_empty(slot), (uint32_t)((use - 1) & 1));
+          mbar_arrive_expect_tx(ring_full(slot), fill_bytes);
+          bulk_load(sm_addr + slot * SLOT, wsrc + (size_t)f * fill_bytes, fill_bytes, ring_full(slot));
+        }
       }
     }
     __syncwarp();
   }
   // =============================================================== MMA thread
-  else if (warp == 9) {
+  else if (warp == 8 + NPROD) {
     if (lane == 0) {
       int seq = 0, cg = 0;
       uint32_t bpar = 0, gopar = 0;
@@ -312,18 +427,18 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
           gopar ^= 1u;
           const int nu = *reinterpret_cast<volatile int*>(ints_s + 4);
           const int passes = (nu + 255) / 256;
-          constexpr uint32_t idesc = idesc_m128(NCC);
+          constexpr uint32_t idesc = idesc_m64(CCOLS);
           for (int pass = 0; pass < passes; ++pass) {
-            if (pass * 256 + tile * 128 >= nu) continue;
+            if (pass * 256 + ag * CROWS >= nu) continue;
             for (int kc = 0; kc < KC_CONV; ++kc) {
               const int g = cg + kc, s = g % CNS;
               mbar_wait(conv_full(s), (uint32_t)((g / CNS) & 1));
               tc_fence_after();
               const uint32_t a_stage = pipe_addr + s * CSTAGE;
 #pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4)
-                umma_bf16(tmem + ACC_CONV, umma_desc_sw128(a_stage + k4 * 32),
-                          umma_desc_sw128(a_stage + A_TILE + k4 * 32), idesc, 1u);
+              for (int k4 = 0; k4 < 4; ++k4)   // accumulator 0 starts at the bias, 1..3 at zero
+                umma_bf16(tmem + ACC_CONV + k4 * CCOLS, umma_desc_sw128(a_stage + k4 * 32),
+                          umma_desc_sw128(a_stage + CA_TILE + k4 * 32), idesc, (kc > 0 || k4 == 0) ? 1u : 0u);
               umma_commit(conv_empty(s));
             }
             umma_commit(conv_acc);
@@ -338,19 +453,24 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
         }
         const bool n32 = (stg.flags & R2F_N32) != 0;
         const uint32_t ncol = n32 ? 32u : 16u;
-        const uint32_t idesc = idesc_m128(ncol);
-        const uint32_t b_addr = fix_addr + (stg.bsel ? F_BOP2 : F_BOP);
+        const uint32_t idesc = idesc_m64(ncol);
+        const uint32_t b_addr = stg.bsel == 2 ? pipe_addr + P_BOP2 : x_addr + X_BOP + stg.bsel * 16384;
         const uint32_t bch = n32 ? BCH32 : BCH, sbo = n32 ? 1024u : 0u;
         for (int mt = 0; mt < (int)stg.mtiles; ++mt)
-          for (int kc = 0; kc < (int)stg.kchunks; ++kc) {
+          for (int kg = 0; kg < (int)stg.kchunks / FKC; ++kg) {
             const int slot = seq % NSLOT;
             mbar_wait(ring_full(slot), (uint32_t)((seq / NSLOT) & 1));
             tc_fence_after();
-            const uint32_t a_base = sm_addr + slot * SLOT;
+            const uint64_t adesc = umma_desc_sw128(sm_addr + slot * SLOT);
+            const uint64_t bdesc = umma_desc_sw128_sbo(b_addr + kg * FKC * bch, sbo);
+            const uint32_t astep = ((uint32_t)stg.rows * 128u) >> 4, bstep = bch >> 4;
+            const uint32_t dcol = tmem + stg.acc_col + mt * 64;
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4)
-              umma_bf16(tmem + stg.acc_col + mt * ncol, umma_desc_sw128(a_base + k4 * 32),
-                        umma_desc_sw128_sbo(b_addr + kc * bch + k4 * 32, sbo), idesc, (kc | k4) ? 1u : 0u);
+            for (int c = 0; c < FKC; ++c)
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4)
+                umma_bf16(dcol + (n32 ? 0 : k4 * 16), adesc + (uint64_t)(c * astep + k4 * 2),
+                          bdesc + (uint64_t)(c * bstep + k4 * 2), idesc, n32 ? ((kg | c | k4) ? 1u : 0u) : ((kg | c) ? 1u : 0u));
             umma_commit(ring_empty(slot));
             ++seq;
           }
@@ -359,40 +479,17 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
     }
     __syncwarp();
   }
-  // =============================================================== conv-weight TMA thread
-  else if (warp == 10) {
-    if (lane == 0) {
-      int cg = 0;
-      uint32_t gopar = 0;
-      for (int si = 0; si < C.n_stages; ++si) {
-        const R2Stage stg = C.stages[si];
-        if (!(stg.flags & R2F_CONV)) continue;
-        mbar_wait(conv_go, gopar);
-        gopar ^= 1u;
-        const int nu = *reinterpret_cast<volatile int*>(ints_s + 4);
-        const int passes = (nu + 255) / 256;
-        for (int pass = 0; pass < passes; ++pass) {
-          if (pass * 256 + tile * 128 >= nu) continue;
-          for (int kc = 0; kc < KC_CONV; ++kc) {
-            const int g = cg + kc, s = g % CNS;
-            mbar_wait(conv_empty(s), (uint32_t)(((g / CNS) & 1) ^ 1));
-            mbar_arrive_expect_tx(conv_full(s), NCC * 128);
-            tma_load_2d(pipe_addr + s * CSTAGE + A_TILE, stg.map, conv_full(s), kc * 64, cgp * NCC);
-          }
-          cg += KC_CONV;
-        }
-      }
-    }
-    __syncwarp();
-  }
   // =============================================================== compute warps
   else {
-    const int quad = warp & 3, half = warp >> 2;
+    const int quad = warp & 3;
     const uint32_t tlane = tmem + ((uint32_t)(quad * 32) << 16);
-    const int own_a[NAL] = {rank, rank + RES_CL};
-    const bool own_v[NAL] = {rank < A, rank + RES_CL < A};
+    const int a0 = ag * NAG;
+    const int n_own = max(0, min(NAG, A - a0));
+    uint32_t peer[GF];          // shared::cluster base address of the CTAs of my anchor group
+#pragma unroll
+    for (int j = 0; j < GF; ++j) peer[j] = mapa(sm_addr, (uint32_t)(ag * GF + j));
     uint32_t acc_par = 0, cl_par = 0, conv_par = 0;
-    int cg = 0, rsel = 0, dbg_i = 0;
+    int cg = 0, dbg_i = 0, k = 0;   // k: linear stage counter (B operand / row buffer parity)
     unsigned long long done_rows = 0ull;
     const __nv_bfloat16* bevn =
         call.bev_nhwc_bf16 ? reinterpret_cast<const __nv_bfloat16*>(call.bev) + (size_t)scene * HW * D
@@ -415,7 +512,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
       cl_par ^= 1u;
       mark(105);
     };
-    // B operand(s) written by this thread -> visible to the tensor core -> count me in
+    // B operand complete (as far as this thread is concerned) -> visible to the tensor core
     auto b_done = [&]() {
       fence_proxy_async();
       tc_fence_before();
@@ -426,54 +523,65 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
       acc_par ^= 1u;
       tc_fence_after();
     };
-    // sums over the 256 features (= compute threads) of two values per thread
-    auto block_sum2 = [&](float& a, float& b) {
-      a = warp_sum(a);
-      b = warp_sum(b);
-      float* r = red_s + rsel * 16;
-      rsel ^= 1;
-      if (lane == 0) { r[warp * 2] = a; r[warp * 2 + 1] = b; }
-      bsync();
-      const float4 r0 = *reinterpret_cast<const float4*>(r), r1 = *reinterpret_cast<const float4*>(r + 4),
-                   r2 = *reinterpret_cast<const float4*>(r + 8), r3 = *reinterpret_cast<const float4*>(r + 12);
-      a = ((r0.x + r0.z) + (r1.x + r1.z)) + ((r2.x + r2.z) + (r3.x + r3.z));
-      b = ((r0.y + r0.w) + (r1.y + r1.w)) + ((r2.y + r2.w) + (r3.y + r3.w));
+    auto bop_ptr = [&](int kk) { return xr + X_BOP + (kk & 1) * 16384; };
+    auto act_ptr = [&](int kk) { return reinterpret_cast<float*>(xr + X_ACT + (kk & 1) * 8192); };
+    // Exchange inside my anchor group.  Warps 0-1 have written this CTA's slice (`bytes` at byte
+    // offset `off` from the shared-memory base, same offset in every CTA); it is copied into the
+    // three peers by the bulk-copy engine, whose completion bytes the peers' exchange barrier of
+    // this stage parity counts.  Optionally a second slice (cls branch) rides in the same phase.
+    uint32_t xbits = 0u;   // bit i: parity of exchange barrier i
+    auto xchg_send = [&](int kk, uint32_t off, uint32_t bytes, uint32_t off2, uint32_t bytes2, bool all_warps) {
+      fence_proxy_async();
+      if (all_warps) bsync(); else named_bar_sync(2, 128);
+      if (tid == 0) {
+        const uint32_t xb = xbar0 + (kk & 1) * 8;
+        mbar_arrive_expect_tx(xb, (GF - 1) * (bytes + bytes2));
+#pragma unroll
+        for (int j = 0; j < GF; ++j) {
+          if (j != fg) {
+            bulk_copy_to_peer(peer[j] + off, sm_addr + off, bytes, peer[j] + (xb - sm_addr));
+            if (bytes2) bulk_copy_to_peer(peer[j] + off2, sm_addr + off2, bytes2, peer[j] + (xb - sm_addr));
+          }
+        }
+      }
     };
-    // LayerNorm over the features of both anchors; this thread holds feature `tid`
-    auto ln_feat = [&](float (&v)[NAL], float g, float bt) {
-      float s0 = v[0], s1 = v[1];
-      block_sum2(s0, s1);
-      const float m0 = s0 * (1.0f / D), m1 = s1 * (1.0f / D);
-      const float d0 = v[0] - m0, d1 = v[1] - m1;
-      float q0 = d0 * d0, q1 = d1 * d1;
-      block_sum2(q0, q1);
-      v[0] = d0 * (1.0f / sqrtf(q0 * (1.0f / D) + LN_EPS)) * g + bt;
-      v[1] = d1 * (1.0f / sqrtf(q1 * (1.0f / D) + LN_EPS)) * g + bt;
+    auto xchg_wait = [&](int kk) {
+      mbar_wait(xbar0 + (kk & 1) * 8, (xbits >> (kk & 1)) & 1u);
+      xbits ^= 1u << (kk & 1);
     };
-    auto acc2 = [&](int mt, int group, float (&v)[NAL]) {   // accumulator of feature tile `mt`
-      tmem_ld2(tlane + ACC_LIN + (uint32_t)(group * 32 + mt * 16), v);
+    // this thread's feature column (warps 0-1: local feature fl of tile mt) of the group's rows
+    auto acc8 = [&](uint32_t acc_col, float (&v)[8]) {
+      uint32_t u[32];
+      tmem_ld32(tlane + acc_col, u);      // columns 16 j + n: accumulator j, row n (n < 8 used)
+      tmem_ld_wait();
+      tmem_ld8(tlane + acc_col + 48, v);  // accumulator 3 lives in columns 48..55 (tmem_ld32 covers 0..31)
+#pragma unroll
+      for (int n = 0; n < 8; ++n)
+        v[n] = (__uint_as_float(u[n]) + __uint_as_float(u[16 + n])) + (v[n] + 0.f);
+      float w[8];
+      tmem_ld8(tlane + acc_col + 32, w);
+#pragma unroll
+      for (int n = 0; n < 8; ++n) v[n] += w[n];
     };
+    const uint32_t off_x = (uint32_t)(RING + PIPE);   // offset of X from the shared-memory base
 
     // ---- img = sqrt(ac) * norm_odo(anchors) + sqrt(1-ac) * noise   (:591-597); every CTA derives
-    // the step-0 points of every anchor itself, owners keep the diffused sample of their anchors
+    // the step-0 points of every anchor itself and keeps the diffused sample of the outputs it owns
     for (int i = tid; i < AP * 2; i += NCT) {
       const float a = __ldg(C.anchors + i);
       const float nv = (i & 1) ? norm_y(a) : norm_x(a);
       const float im = __fadd_rn(__fmul_rn(C.sa_tr, nv), __fmul_rn(C.sb_tr, __ldg(call.noise + (size_t)scene * AP * 2 + i)));
       const float v = fminf(fmaxf(im, -1.0f), 1.0f);
-      const float pt = (i & 1) ? denorm_y(v) : denorm_x(v);
-      pts_s[i] = pt;
-      const int a_i = i / (2 * P), r = i - a_i * 2 * P;
-      if ((a_i & (RES_CL - 1)) == rank) {
-        img_o[(a_i >> 4) * 16 + r] = im;
-        pts_o[(a_i >> 4) * 16 + r] = pt;
-      }
+      pts_s[i] = (i & 1) ? denorm_y(v) : denorm_x(v);
+      const int a_i = i / (2 * P), r = i - a_i * 2 * P, p = r >> 1, comp = r & 1;
+      if (a_i >= a0 && a_i < a0 + n_own) img_o[(a_i - a0) * 24 + p * 3 + comp] = im;
     }
     mark(1);
 
     // ================= hoisted agent K|V and ego vectors (step-invariant, :316-327,355-364),
     // feature-split over the cluster, exchanged through L2
     {
+      uint8_t* bop = xr + X_BOP;
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const int a = warp + 8 * r;
@@ -484,27 +592,27 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
           const float vv[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
 #pragma unroll
           for (int h2 = 0; h2 < 2; ++h2) {
-            const int k = h2 * 128 + lane * 4;
+            const int kk = h2 * 128 + lane * 4;
             __nv_bfloat162 p0 = __floats2bfloat162_rn(vv[4 * h2 + 0], vv[4 * h2 + 1]);
             __nv_bfloat162 p1 = __floats2bfloat162_rn(vv[4 * h2 + 2], vv[4 * h2 + 3]);
             uint2 u;
             u.x = *reinterpret_cast<uint32_t*>(&p0);
             u.y = *reinterpret_cast<uint32_t*>(&p1);
-            *reinterpret_cast<uint2*>(bop + sw_off(a, k, BCH32)) = u;
+            *reinterpret_cast<uint2*>(bop + sw_off(a, kk, BCH32)) = u;
           }
         }
       }
       b_done();
       wait_acc();
       const int rows = 3 * D / RES_CL;   // 48 features of [K | V | ego] per CTA
-      if (half == 0 && quad * 32 < rows) {
-        const int f = quad * 32 + lane;
+      if (warp < 4 && quad * 16 < rows) {
+        const int f = quad * 16 + lane;
         const int gfeat = rank * rows + f;
         for (int l = 0; l < L; ++l) {
           uint32_t u[32];
           tmem_ld32(tlane + ACC_LIN + 32 * l, u);
           tmem_ld_wait();
-          if (f < rows) {
+          if (lane < 16 && f < rows) {
             const float bias = __ldg(C.layer[l].b_kvego + gfeat);
             float* kvl = kvg + (size_t)l * Na * 2 * D;
 #pragma unroll
@@ -524,75 +632,100 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
 
     for (int si = 0; si < S; ++si) {
       const bool last_step = (si == S - 1);
-      // ============ sine embedding of the owner's anchors (blocks.py:22-40) -> B operand (K = 64 P)
+      // ============ sine embedding of the group's anchors (blocks.py:22-40) -> B operand (K = 64 P);
+      // features 2m and 2m+1 share their argument: one sincosf per pair
       {
+        uint8_t* bop = bop_ptr(k);
         const float two_pi = 6.283185307179586f;
-        for (int i = tid; i < NAL * P * 64; i += NCT) {
-          const int n = i / (P * 64), r = i - n * P * 64;
-          const int p = r >> 6, j = r & 63, hf = j >> 5, ii = j & 31;
-          float val = 0.f;
-          if (own_v[n]) {
-            const float v = hf ? pts_o[n * 16 + p * 2 + 0] : pts_o[n * 16 + p * 2 + 1];   // (pos_y | pos_x)
-            const float arg = __fdiv_rn(__fmul_rn(v, two_pi), __ldg(C.dim_t + ii));
-            val = (ii & 1) ? cosf(arg) : sinf(arg);
-          }
-          bop_store(bop, n, r, val);
+        for (int i = tid; i < n_own * P * 32; i += NCT) {
+          const int n = i / (P * 32), r = i - n * P * 32;
+          const int p = r >> 5, jj = r & 31, hf = jj >> 4, m = jj & 15;   // pair m of half hf of pose p
+          const float v = hf ? pts_s[((a0 + n) * P + p) * 2 + 0] : pts_s[((a0 + n) * P + p) * 2 + 1];   // (pos_y | pos_x)
+          const float arg = __fdiv_rn(__fmul_rn(v, two_pi), __ldg(C.dim_t + 2 * m));
+          float sv, cv;
+          sincosf(arg, &sv, &cv);
+          const __nv_bfloat162 pr = __floats2bfloat162_rn(sv, cv);
+          *reinterpret_cast<__nv_bfloat162*>(bop + sw_off(n, p * 64 + hf * 32 + 2 * m, BCH)) = pr;
         }
         b_done();
       }
       mark(10);
       // ============ plan_anchor_encoder (:459-462): Linear(512->256)+ReLU+LN, Linear(256->256)
       {
-        const float bias = __ldg(C.b_enc0 + tid), g = __ldg(C.enc_ln_g + tid), bt = __ldg(C.enc_ln_b + tid);
+        const float bias = (warp < 4 && lane < 16) ? __ldg(C.b_enc0 + fg * 64 + quad * 16 + lane) : 0.f;
+        float g[8], bt[8];
+        if (warp < n_own) { ldg8(C.enc_ln_g, lane, g); ldg8(C.enc_ln_b, lane, bt); }
         wait_acc();
-        float v[NAL];
-        acc2(half, 0, v);
-        v[0] = fmaxf(v[0] + bias, 0.f);
-        v[1] = fmaxf(v[1] + bias, 0.f);
-        ln_feat(v, g, bt);
-        bop_store(bop, 0, tid, v[0]);
-        bop_store(bop, 1, tid, v[1]);
+        if (warp < 4) {
+          float v[8];
+          acc8(ACC_LIN, v);
+          float* sl = act_ptr(k) + fg * (NROW * 64) + quad * 16 + lane;
+#pragma unroll
+          for (int n = 0; n < NROW; ++n)
+            if (lane < 16) sl[n * 64] = fmaxf(v[n] + bias, 0.f);
+          xchg_send(k, off_x + X_ACT + (k & 1) * 8192 + fg * 2048, 2048, 0, 0, false);
+        }
+        xchg_wait(k);
+        if (warp < n_own) {
+          float v[8];
+          act_load8(act_ptr(k), warp, lane, v);
+          ln_row_reg(v, g, bt);
+          bt_store8(bop_ptr(k + 1), warp, lane, v);
+        }
+        ++k;
         b_done();
       }
       mark(11);
       {
-        const float bias = __ldg(C.b_enc3 + tid);
+        const float bias = (warp < 4 && lane < 16) ? __ldg(C.b_enc3 + fg * 64 + quad * 16 + lane) : 0.f;
+        float wa[8][8];   // rows of this CTA's attention-weight head, fetched under the MMA
+        if (warp < n_own && fg < L) {
+#pragma unroll
+          for (int p = 0; p < 8; ++p) ldg8(C.layer[fg].attw_w + (size_t)p * D, lane, wa[p]);
+        }
         wait_acc();
-        float v[NAL];
-        acc2(half, 0, v);
-        q0_s[tid] = v[0] + bias;
-        q0_s[D + tid] = v[1] + bias;
-        if (call.dbg) {
+        if (warp < 4) {
+          float v[8];
+          acc8(ACC_LIN, v);
+          float* sl = act_ptr(k) + fg * (NROW * 64) + quad * 16 + lane;
 #pragma unroll
-          for (int n = 0; n < NAL; ++n)
-            if (own_v[n]) C.tap_q0[((size_t)scene * A + own_a[n]) * D + tid] = v[n] + bias;
+          for (int n = 0; n < NROW; ++n)
+            if (lane < 16) sl[n * 64] = v[n] + bias;
+          xchg_send(k, off_x + X_ACT + (k & 1) * 8192 + fg * 2048, 2048, 0, 0, false);
         }
-        bsync();
-        // attention weights of every layer (blocks.py:98-100): softmax_p(q0 . Wa^T + ba)
-        const int ndot = NAL * L * P;            // (n, l, p)
-        for (int d = warp; d < ndot; d += 8) {
-          const int n = d / (L * P), r = d - n * L * P, l = r / P, p = r - l * P;
-          const float* wr = C.layer[l].attw_w + (size_t)p * D;
-          float s = 0.f;
+        xchg_wait(k);
+        if (warp < n_own) {
+          float v[8];
+          act_load8(act_ptr(k), warp, lane, v);
+          store8(q0_s + warp * D, lane, v);
+          if (call.dbg && fg == 0) store8(C.tap_q0 + ((size_t)scene * A + a0 + warp) * D, lane, v);
+          // attention weights (blocks.py:98-100): softmax_p(q0 . Wa^T + ba); CTA fg of the group
+          // computes layer fg and hands it to the whole cluster
+          if (fg < L) {
+            const int l = fg;
+            float dot = 0.f;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) s = fmaf(q0_s[n * D + lane + 32 * i], __ldg(wr + lane + 32 * i), s);
-          s = warp_sum(s);
-          if (lane == 0) logit_s[d] = s + __ldg(C.layer[l].attw_b + p);
-        }
-        bsync();
-        if (tid < NAL * L * P) {
-          const int n = tid / (L * P), r = tid - n * L * P, l = r / P, p = r - l * P;
-          if (own_v[n]) {
-            const float* lg = logit_s + (n * L + l) * P;
-            float mx = lg[0];
-            for (int o = 1; o < P; ++o) mx = fmaxf(mx, lg[o]);
-            float den = 0.f;
-            for (int o = 0; o < P; ++o) den += expf(lg[o] - mx);
-            const float w = expf(lg[p] - mx) / den;
-            const uint32_t dst = fix_addr + F_AW + (uint32_t)((l * AP + own_a[n] * P + p) * 4);
-            for (int c = 0; c < RES_CL; ++c) st_cluster_f32(mapa(dst, (uint32_t)c), w);
+            for (int p = 0; p < 8; ++p) {
+              float s = 0.f;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) s = fmaf(v[i], wa[p][i], s);
+              s = warp_sum(s);
+              if (lane == p) dot = s;
+            }
+            const float lg = (lane < P) ? dot + __ldg(C.layer[l].attw_b + lane) : -INFINITY;
+            float mx = lg;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+            const float e = (lane < P) ? expf(lg - mx) : 0.f;
+            const float wgt = e / warp_sum(e);
+            // lane p holds weight p: lanes 0..P-1 write it to CTAs 0..15
+            if (lane < P) {
+              const uint32_t dst = fix_addr + F_AW + (uint32_t)((l * AP + (a0 + warp) * P + lane) * 4);
+              for (int c = 0; c < RES_CL; ++c) st_cluster_f32(mapa(dst, (uint32_t)c), wgt);
+            }
           }
         }
+        ++k;
         csync();
       }
       mark(12);
@@ -608,7 +741,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
         {
           const int nwords = HW / 32;
           if (tid < nwords) bm_s[tid] = 0u;
-          if (tid < NCC) cbias_s[tid] = __ldg(LC.b_conv + cgp * NCC + tid);
+          if (tid < CCOLS) cbias_s[tid] = __ldg(LC.b_conv + fg * CCOLS + tid);
           if (tid == 0) *need_s = 0ull;
           Corners c;
           float a_w = 0.f;
@@ -619,8 +752,8 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
           bsync();
           if (tid < AP) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (c.pix[k] >= 0) atomicOr(bm_s + (c.pix[k] >> 5), 1u << (c.pix[k] & 31));
+            for (int q = 0; q < 4; ++q)
+              if (c.pix[q] >= 0) atomicOr(bm_s + (c.pix[q] >> 5), 1u << (c.pix[q] & 31));
           }
           bsync();
           // ordered compaction (pixel order == memory order of the NHWC map)
@@ -657,16 +790,16 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
           done_rows |= need_all;
           if (tid < AP) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int q = 0; q < 4; ++q) {
               EntPair ep;
               ep.slot = -1;
               ep.w = 0.f;
-              if (c.pix[k] >= 0) {
-                const int wd = c.pix[k] >> 5;
-                ep.slot = pre_s[wd] + __popc(bm_s[wd] & ((1u << (c.pix[k] & 31)) - 1u));
-                ep.w = c.w[k] * a_w;
+              if (c.pix[q] >= 0) {
+                const int wd = c.pix[q] >> 5;
+                ep.slot = pre_s[wd] + __popc(bm_s[wd] & ((1u << (c.pix[q] & 31)) - 1u));
+                ep.w = c.w[q] * a_w;
               }
-              ent[tid * 4 + k] = ep;
+              ent[tid * 4 + q] = ep;
             }
           }
         }
@@ -697,22 +830,24 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
         } else {
           bsync();
         }
-        // ============ value_proj conv at the unique pixels + bilinear/attention combine
+        // ============ value_proj conv at the unique pixels + bilinear/attention combine:
+        // CTA (ag, fg) = (64-row tile, 64-column group)
         {
           if (tid == 0) mbar_arrive(conv_go);
           const int passes = (nu + 255) / 256;
-          const int a_c = tid >> 3, cqd = tid & 7;          // combine: (anchor, 4-column group)
-          float4 sacc = make_float4(0.f, 0.f, 0.f, 0.f);
-          float* Vs = reinterpret_cast<float*>(bop);
+          const int a_c = tid >> 4, cqd = tid & 15;         // combine: anchors a_c, a_c + 16; 4-column group
+          float4 sacc[2];
+          sacc[0] = sacc[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          float* Vs = reinterpret_cast<float*>(xr + X_VS);
           for (int pass = 0; pass < passes; ++pass) {
-            const int row_base = pass * 256 + tile * 128;
+            const int row_base = pass * 256 + ag * CROWS;
             if (row_base >= nu) continue;
-            const int rows_valid = min(128, nu - row_base);
+            const int rows_valid = min(CROWS, nu - row_base);
             const int j = tid & 7, rb = tid >> 3;
-            int rowoff[4];
-            uint32_t vmask[4];
+            int rowoff[2];
+            uint32_t vmask[2];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < 2; ++i) {
               const int r = rb + 32 * i;
               rowoff[i] = 0;
               vmask[i] = 0;
@@ -733,19 +868,22 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
               const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
               const int tapoff = (dy * W + dx) * D + (kc & 3) * 64;
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
+              for (int i = 0; i < 2; ++i) {
                 const bool ok = (vmask[i] >> tap) & 1u;
                 const int off = ok ? rowoff[i] + tapoff : 0;
                 cp_async16(a_dst + i * 4096, bevn + off, ok ? 16u : 0u);
               }
               if (kc == 0 && warp < 4) {   // accumulators start at the conv bias
-                uint32_t u[32];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                  const uint4 t4 = *reinterpret_cast<const uint4*>(cbias_s + 4 * q);
-                  u[4 * q + 0] = t4.x; u[4 * q + 1] = t4.y; u[4 * q + 2] = t4.z; u[4 * q + 3] = t4.w;
+                for (int hh = 0; hh < 2; ++hh) {
+                  uint32_t u[32];
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) {
+                    const uint4 t4 = *reinterpret_cast<const uint4*>(cbias_s + hh * 32 + 4 * q);
+                    u[4 * q + 0] = t4.x; u[4 * q + 1] = t4.y; u[4 * q + 2] = t4.z; u[4 * q + 3] = t4.w;
+                  }
+                  tmem_st32(tlane + ACC_CONV + hh * 32, u);
                 }
-                tmem_st32(tlane + ACC_CONV, u);
                 tmem_st_wait();
                 tc_fence_before();
               }
@@ -757,49 +895,72 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
             conv_par ^= 1u;
             tc_fence_after();
             mark(126);
-            if (warp < 4) {   // drain (ReLU) into the staging area
-              float* vrow = Vs + (size_t)(warp * 32 + lane) * VS_LD;
-              uint32_t u0[32];
-              tmem_ld32(tlane + ACC_CONV, u0);
-              tmem_ld_wait();
+            if (warp < 4) {   // drain (ReLU) into the staging area: row quad*16 + lane lives in lanes 0..15
+              float* vrow = Vs + (size_t)(quad * 16 + (lane & 15)) * VS_LD;
 #pragma unroll
-              for (int q = 0; q < 8; ++q)
-                *reinterpret_cast<float4*>(vrow + 4 * q) = make_float4(
-                    fmaxf(__uint_as_float(u0[4 * q]), 0.f), fmaxf(__uint_as_float(u0[4 * q + 1]), 0.f),
-                    fmaxf(__uint_as_float(u0[4 * q + 2]), 0.f), fmaxf(__uint_as_float(u0[4 * q + 3]), 0.f));
+              for (int hh = 0; hh < 2; ++hh) {
+                uint32_t u0[32], u1[32];
+                tmem_ld32(tlane + ACC_CONV + hh * 32, u0);
+                tmem_ld32(tlane + ACC_CONV + CCOLS + hh * 32, u1);
+                tmem_ld_wait();
+                float t[32];
+#pragma unroll
+                for (int q = 0; q < 32; ++q) t[q] = __uint_as_float(u0[q]) + __uint_as_float(u1[q]);
+                tmem_ld32(tlane + ACC_CONV + 2 * CCOLS + hh * 32, u0);
+                tmem_ld32(tlane + ACC_CONV + 3 * CCOLS + hh * 32, u1);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 32; ++q) t[q] += __uint_as_float(u0[q]) + __uint_as_float(u1[q]);
+                if (lane < 16) {
+#pragma unroll
+                  for (int q = 0; q < 8; ++q)
+                    *reinterpret_cast<float4*>(vrow + hh * 32 + 4 * q) = make_float4(
+                        fmaxf(t[4 * q], 0.f), fmaxf(t[4 * q + 1], 0.f), fmaxf(t[4 * q + 2], 0.f), fmaxf(t[4 * q + 3], 0.f));
+                }
+              }
               tc_fence_before();
             }
             bsync();
-            if (a_c < A) {
-              const EntPair* ea = ent + a_c * P * 4;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const int a = a_c + 16 * i;
+              if (a < A) {
+                const EntPair* ea = ent + a * P * 4;
 #pragma unroll 8
-              for (int k = 0; k < P * 4; ++k) {
-                const EntPair e = ea[k];
-                const int rr = e.slot - row_base;
-                if (rr >= 0 && rr < rows_valid) {
-                  const float4 v = *reinterpret_cast<const float4*>(Vs + (size_t)rr * VS_LD + cqd * 4);
-                  sacc.x = fmaf(e.w, v.x, sacc.x); sacc.y = fmaf(e.w, v.y, sacc.y);
-                  sacc.z = fmaf(e.w, v.z, sacc.z); sacc.w = fmaf(e.w, v.w, sacc.w);
+                for (int q = 0; q < P * 4; ++q) {
+                  const EntPair e = ea[q];
+                  const int rr = e.slot - row_base;
+                  if (rr >= 0 && rr < rows_valid) {
+                    const float4 v = *reinterpret_cast<const float4*>(Vs + (size_t)rr * VS_LD + cqd * 4);
+                    sacc[i].x = fmaf(e.w, v.x, sacc[i].x); sacc[i].y = fmaf(e.w, v.y, sacc[i].y);
+                    sacc[i].z = fmaf(e.w, v.z, sacc[i].z); sacc[i].w = fmaf(e.w, v.w, sacc[i].w);
+                  }
                 }
               }
             }
             bsync();
           }
-          // this CTA's [A x 32] slice of the sampled features -> the anchor owners
-          if (a_c < A) {
-            const uint32_t dst = fix_addr + F_SP +
-                                 (uint32_t)(((tile * NAL + (a_c >> 4)) * D + cgp * NCC + cqd * 4) * 4);
-            st_cluster_v4(mapa(dst, (uint32_t)(a_c & (RES_CL - 1))), sacc);
+          // this CTA's [A x 64] slice of the sampled features -> the four CTAs of each anchor's group
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int a = a_c + 16 * i;
+            if (a < A) {
+              const int g_a = a / NAG, n = a - g_a * NAG;
+              const uint32_t d = off_x + X_SP + (uint32_t)(((ag * NAG + n) * D + fg * CCOLS + cqd * 4) * 4);
+#pragma unroll
+              for (int jj = 0; jj < GF; ++jj) st_cluster_v4(mapa(sm_addr + d, (uint32_t)(g_a * GF + jj)), sacc[i]);
+            }
           }
-          // stage this layer's agent K|V (fp32) in the idle conv pipeline buffers
+          // stage the agent K|V of my two heads (fp32) in the idle conv pipeline buffers
           {
             const float* kvl = kvg + (size_t)l * Na * 2 * D;
-            const int n16 = Na * 128;
+            const int n16 = Na * 32;   // per agent: 16 units of K, 16 units of V
             for (int i = tid; i < n16; i += NCT) {
-              const int jrow = i >> 7, u = i & 127;
-              const uint32_t dst = (u < 64) ? pipe_addr + (uint32_t)((jrow * KS_LD + u * 4) * 4)
-                                            : pipe_addr + (uint32_t)(32 * KS_LD * 4 + (jrow * D + (u - 64) * 4) * 4);
-              cp_async16(dst, kvl + (size_t)jrow * 2 * D + u * 4, 16u);
+              const int jrow = i >> 5, u = i & 31;
+              const uint32_t dst = (u < 16) ? pipe_addr + P_KV + (uint32_t)((jrow * KS_LD + u * 4) * 4)
+                                            : pipe_addr + P_KV + (uint32_t)(32 * KS_LD * 4 + (jrow * 64 + (u - 16) * 4) * 4);
+              const float* src = kvl + (size_t)jrow * 2 * D + (u < 16 ? fg * 64 + u * 4 : D + fg * 64 + (u - 16) * 4);
+              cp_async16(dst, src, 16u);
             }
             cp_async_commit();
           }
@@ -808,48 +969,71 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
         mark(22);
         // ============ output_proj + residual (blocks.py:127-129): x1 = S.Wo + b + q0
         {
-          bop_store(bop, 0, tid, sp_s[tid] + sp_s[NAL * D + tid]);
-          bop_store(bop, 1, tid, sp_s[D + tid] + sp_s[NAL * D + D + tid]);
-          b_done();
-          const float bias = __ldg(LC.b_bev_out + tid);
-          wait_acc();
-          float v[NAL];
-          acc2(half, 0, v);
-          v[0] += bias + q0_s[tid];
-          v[1] += bias + q0_s[D + tid];
-          x1_s[tid] = v[0];
-          x1_s[D + tid] = v[1];
-          if (call.dbg) {
+          const int ntile = min(4, (nu + CROWS - 1) / CROWS);   // tiles of the first pass hold everything a tile CTA accumulated
+          float sv[8];
+          if (warp < n_own) {
+            const float* sp = reinterpret_cast<const float*>(xr + X_SP) + warp * D;
+            load8(sp, lane, sv);
+            for (int t = 1; t < ntile; ++t) {
+              float u[8];
+              load8(sp + (size_t)t * NAG * D, lane, u);
 #pragma unroll
-            for (int n = 0; n < NAL; ++n)
-              if (own_v[n]) C.tap_x1[((size_t)scene * A + own_a[n]) * D + tid] = v[n];
+              for (int i = 0; i < 8; ++i) sv[i] += u[i];
+            }
           }
-          bop_store(bop, 0, tid, v[0]);
-          bop_store(bop, 1, tid, v[1]);
+          bsync();   // the partials live where the B operand goes
+          if (warp < n_own) bt_store8(bop_ptr(k), warp, lane, sv);
+          b_done();
+          const int f = fg * 64 + quad * 16 + lane;
+          const float bias = (warp < 4 && lane < 16) ? __ldg(LC.b_bev_out + f) : 0.f;
+          wait_acc();
+          if (warp < 4) {
+            float v[8];
+            acc8(ACC_LIN, v);
+            float* sl = act_ptr(k) + fg * (NROW * 64) + quad * 16 + lane;
+#pragma unroll
+            for (int n = 0; n < NROW; ++n)
+              if (lane < 16) sl[n * 64] = v[n] + bias + q0_s[n * D + f];
+            xchg_send(k, off_x + X_ACT + (k & 1) * 8192 + fg * 2048, 2048, 0, 0, false);
+          }
+          xchg_wait(k);
+          if (warp < n_own) {
+            float v[8];
+            act_load8(act_ptr(k), warp, lane, v);
+            store8(x1_s + warp * D, lane, v);
+            if (call.dbg && fg == 0) store8(C.tap_x1 + ((size_t)scene * A + a0 + warp) * D, lane, v);
+            bt_store8(bop_ptr(k + 1), warp, lane, v);
+          }
+          ++k;
           b_done();
         }
         mark(23);
-        // ============ cross_agent_attention (:316-321,355-357): q projection, softmax(qK^T)V
+        // ============ cross_agent_attention (:316-321,355-357): q projection of my two heads,
+        // softmax(qK^T)V, head outputs straight into the group's next B operand
         {
-          const float bias = __ldg(LC.b_q + tid);
+          float* ql = reinterpret_cast<float*>(pipe + P_QL);      // [NROW][64]
+          const float bias = (warp < 4 && lane < 16) ? __ldg(LC.b_q + fg * 64 + quad * 16 + lane) : 0.f;
           wait_acc();
-          float v[NAL];
-          acc2(half, 0, v);
-          const float scale = 0.17677669529663687f;   // 1/sqrt(32)
-          t0_s[tid] = (v[0] + bias) * scale;
-          t0_s[D + tid] = (v[1] + bias) * scale;
+          if (warp < 4) {
+            float v[8];
+            acc8(ACC_LIN, v);
+            const float scale = 0.17677669529663687f;   // 1/sqrt(32)
+#pragma unroll
+            for (int n = 0; n < NROW; ++n)
+              if (lane < 16) ql[n * 64 + quad * 16 + lane] = (v[n] + bias) * scale;
+          }
           cp_async_wait_all();
           bsync();
-          const float* Ks = reinterpret_cast<const float*>(pipe);
+          const float* Ks = reinterpret_cast<const float*>(pipe + P_KV);
           const float* Vv = Ks + 32 * KS_LD;
-          const int hc = warp * 32;                   // one head per warp
-#pragma unroll
-          for (int n = 0; n < NAL; ++n) {
+          uint8_t* bnext = bop_ptr(k + 1);
+          for (int pr = warp; pr < n_own * 2; pr += 8) {
+            const int n = pr >> 1, hh = pr & 1;
             float s = -INFINITY;
             if (lane < Na) {
               s = 0.f;
-              const float* kr = Ks + lane * KS_LD + hc;
-              const float* qr = t0_s + n * D + hc;
+              const float* kr = Ks + lane * KS_LD + hh * 32;
+              const float* qr = ql + n * 64 + hh * 32;
 #pragma unroll
               for (int c4 = 0; c4 < 8; ++c4) {
                 const float4 kk = *reinterpret_cast<const float4*>(kr + c4 * 4);
@@ -863,178 +1047,242 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
             const float e = (lane < Na) ? expf(s - mx) : 0.f;
             const float pj = e / warp_sum(e);
             float acc = 0.f;
-            for (int jj = 0; jj < Na; ++jj) acc = fmaf(__shfl_sync(0xffffffffu, pj, jj), Vv[jj * D + hc + lane], acc);
-            bop_store(bop, n, hc + lane, acc);
+            for (int jj = 0; jj < Na; ++jj) acc = fmaf(__shfl_sync(0xffffffffu, pj, jj), Vv[jj * 64 + hh * 32 + lane], acc);
+            *reinterpret_cast<__nv_bfloat16*>(bnext + sw_off(n, fg * 64 + hh * 32 + lane, BCH)) = __float2bfloat16_rn(acc);
           }
+          xchg_send(k, off_x + X_BOP + ((k + 1) & 1) * 16384 + fg * BCH, BCH, 0, 0, true);
+          xchg_wait(k);
+          ++k;
           b_done();
         }
         mark(24);
         // ============ attention out_proj + residual, norm1, + ego, norm2   (:355-364)
         {
-          const float bias = __ldg(LC.b_attn_out + tid);
-          const float g1 = __ldg(LC.norm1_g + tid), b1 = __ldg(LC.norm1_b + tid);
-          const float g2 = __ldg(LC.norm2_g + tid), b2 = __ldg(LC.norm2_b + tid);
-          const float eg = ego_s[l * D + tid];
+          const int f = fg * 64 + quad * 16 + lane;
+          const float bias = (warp < 4 && lane < 16) ? __ldg(LC.b_attn_out + f) : 0.f;
+          float g1[8], b1[8], g2[8], b2[8];
+          if (warp < n_own) {
+            ldg8(LC.norm1_g, lane, g1); ldg8(LC.norm1_b, lane, b1);
+            ldg8(LC.norm2_g, lane, g2); ldg8(LC.norm2_b, lane, b2);
+          }
+          mark(129);
           wait_acc();
-          float v[NAL];
-          acc2(half, 0, v);
-          v[0] += bias + x1_s[tid];
-          v[1] += bias + x1_s[D + tid];
-          ln_feat(v, g1, b1);
-          v[0] += eg;
-          v[1] += eg;
-          ln_feat(v, g2, b2);
-          bop_store(bop, 0, tid, v[0]);
-          bop_store(bop, 1, tid, v[1]);
+          mark(130);
+          if (warp < 4) {
+            float v[8];
+            acc8(ACC_LIN, v);
+            float* sl = act_ptr(k) + fg * (NROW * 64) + quad * 16 + lane;
+#pragma unroll
+            for (int n = 0; n < NROW; ++n)
+              if (lane < 16) sl[n * 64] = v[n] + bias + x1_s[n * D + f];
+            mark(131);
+            xchg_send(k, off_x + X_ACT + (k & 1) * 8192 + fg * 2048, 2048, 0, 0, false);
+          }
+          mark(132);
+          xchg_wait(k);
+          mark(133);
+          if (warp < n_own) {
+            float v[8], eg[8];
+            act_load8(act_ptr(k), warp, lane, v);
+            ln_row_reg(v, g1, b1);
+            load8(ego_s + l * D, lane, eg);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += eg[i];
+            ln_row_reg(v, g2, b2);
+            bt_store8(bop_ptr(k + 1), warp, lane, v);
+          }
+          ++k;
+          mark(134);
           b_done();
         }
         mark(25);
-        // ============ FFN up: h = relu(x2.W1 + b)   (:366-368)
+        // ============ FFN up: my F/4 hidden features, h = relu(x2.W1 + b), straight into the
+        // group's next B operand (:366-368)
         {
-          const int ntile = C.F / 256;   // feature tiles per thread (tiles half, half+2, ...)
+          const int fq = C.F / GF, ntl = fq / 64;          // hidden features per CTA (<= 256), 64-row tiles
           float bias[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) bias[i] = (i < ntile) ? __ldg(LC.b_ffn0 + (half + 2 * i) * 128 + quad * 32 + lane) : 0.f;
+          for (int t = 0; t < 4; ++t)
+            bias[t] = (warp < 4 && lane < 16 && t < ntl) ? __ldg(LC.b_ffn0 + fg * fq + t * 64 + quad * 16 + lane) : 0.f;
           wait_acc();
+          if (warp < 4) {
+            uint8_t* bnext = bop_ptr(k + 1);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (i < ntile) {
-              const int mt = half + 2 * i;
-              float v[NAL];
-              acc2(mt, 0, v);
-              const int f = mt * 128 + quad * 32 + lane;
-              bop_store(bop, 0, f, fmaxf(v[0] + bias[i], 0.f));
-              bop_store(bop, 1, f, fmaxf(v[1] + bias[i], 0.f));
+            for (int t = 0; t < 4; ++t) {
+              if (t < ntl) {
+                float v[8];
+                acc8(ACC_LIN + t * 64, v);
+                const int f = fg * fq + t * 64 + quad * 16 + lane;
+#pragma unroll
+                for (int n = 0; n < NROW; ++n)
+                  if (lane < 16) *reinterpret_cast<__nv_bfloat16*>(bnext + sw_off(n, f, BCH)) = __float2bfloat16_rn(fmaxf(v[n] + bias[t], 0.f));
+              }
             }
+            xchg_send(k, off_x + X_BOP + ((k + 1) & 1) * 16384 + fg * ntl * BCH, ntl * BCH, 0, 0, false);
           }
+          xchg_wait(k);
+          ++k;
           b_done();
         }
         mark(26);
         // ============ FFN down, norm3, time FiLM   (:368-373)
         {
-          const float bias = __ldg(LC.b_ffn2 + tid);
-          const float g3 = __ldg(LC.norm3_g + tid), b3 = __ldg(LC.norm3_b + tid);
-          const float* film = C.film + ((size_t)si * L + l) * 2 * D;
-          const float sc = __ldg(film + tid), sh = __ldg(film + D + tid);
+          const float bias = (warp < 4 && lane < 16) ? __ldg(LC.b_ffn2 + fg * 64 + quad * 16 + lane) : 0.f;
+          float g3[8], b3[8], sc[8], sh[8];
+          if (warp < n_own) {
+            const float* film = C.film + ((size_t)si * L + l) * 2 * D;
+            ldg8(LC.norm3_g, lane, g3); ldg8(LC.norm3_b, lane, b3);
+            ldg8(film, lane, sc); ldg8(film + D, lane, sh);
+          }
           wait_acc();
-          float v[NAL];
-          acc2(half, 0, v);
-          v[0] += bias;
-          v[1] += bias;
-          ln_feat(v, g3, b3);
-          v[0] = v[0] * (1.0f + sc) + sh;
-          v[1] = v[1] * (1.0f + sc) + sh;
-          bop_store(bop, 0, tid, v[0]);
-          bop_store(bop, 1, tid, v[1]);
+          if (warp < 4) {
+            float v[8];
+            acc8(ACC_LIN, v);
+            float* sl = act_ptr(k) + fg * (NROW * 64) + quad * 16 + lane;
+#pragma unroll
+            for (int n = 0; n < NROW; ++n)
+              if (lane < 16) sl[n * 64] = v[n] + bias;
+            xchg_send(k, off_x + X_ACT + (k & 1) * 8192 + fg * 2048, 2048, 0, 0, false);
+          }
+          xchg_wait(k);
+          if (warp < n_own) {
+            float v[8];
+            act_load8(act_ptr(k), warp, lane, v);
+            ln_row_reg(v, g3, b3);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = v[i] * (1.0f + sc[i]) + sh[i];
+            bt_store8(bop_ptr(k + 1), warp, lane, v);
+          }
+          ++k;
           b_done();
         }
         mark(27);
         // ============ reg / cls hidden 1   (:221-231)
         {
-          const float bias_r = __ldg(LC.b_reg0 + tid);
-          float bias_c = 0.f, gc = 0.f, bc = 0.f;
-          if (want_cls) { bias_c = __ldg(LC.b_cls0 + tid); gc = __ldg(LC.cls_ln2_g + tid); bc = __ldg(LC.cls_ln2_b + tid); }
-          wait_acc();
-          float v[NAL], c[NAL];
-          acc2(half, 0, v);
-          if (want_cls) acc2(half, 1, c);
-          bop_store(bop, 0, tid, fmaxf(v[0] + bias_r, 0.f));
-          bop_store(bop, 1, tid, fmaxf(v[1] + bias_r, 0.f));
-          if (want_cls) {
-            c[0] = fmaxf(c[0] + bias_c, 0.f);
-            c[1] = fmaxf(c[1] + bias_c, 0.f);
-            ln_feat(c, gc, bc);
-            bop_store(bop2, 0, tid, c[0]);
-            bop_store(bop2, 1, tid, c[1]);
+          const int f = fg * 64 + quad * 16 + lane;
+          float bias_r = 0.f, bias_c = 0.f;
+          if (warp < 4) {
+            bias_r = __ldg(LC.b_reg0 + f);
+            if (want_cls) bias_c = __ldg(LC.b_cls0 + f);
           }
+          float gc[8], bc[8];
+          if (want_cls && warp < n_own) { ldg8(LC.cls_ln2_g, lane, gc); ldg8(LC.cls_ln2_b, lane, bc); }
+          float* act2 = reinterpret_cast<float*>(pipe + P_ACT2);
+          wait_acc();
+          if (warp < 4) {
+            float v[8];
+            acc8(ACC_LIN, v);
+            uint8_t* bnext = bop_ptr(k + 1);
+#pragma unroll
+            for (int n = 0; n < NROW; ++n)
+              if (lane < 16) *reinterpret_cast<__nv_bfloat16*>(bnext + sw_off(n, f, BCH)) = __float2bfloat16_rn(fmaxf(v[n] + bias_r, 0.f));
+            if (want_cls) {
+              acc8(ACC_LIN + 64, v);
+              float* sl = act2 + fg * (NROW * 64) + quad * 16 + lane;
+#pragma unroll
+              for (int n = 0; n < NROW; ++n)
+                if (lane < 16) sl[n * 64] = fmaxf(v[n] + bias_c, 0.f);
+            }
+            xchg_send(k, off_x + X_BOP + ((k + 1) & 1) * 16384 + fg * BCH, BCH,
+                      (uint32_t)(RING + P_ACT2) + fg * 2048, want_cls ? 2048u : 0u, false);
+          }
+          xchg_wait(k);
+          if (want_cls && warp < n_own) {
+            float v[8];
+            act_load8(act2, warp, lane, v);
+            ln_row_reg(v, gc, bc);
+            bt_store8(pipe + P_BOP2, warp, lane, v);
+          }
+          ++k;
           b_done();
         }
         mark(28);
         // ============ reg / cls hidden 2, regression head (256 -> 3P, fp32), cls score
         {
-          const float bias_r = __ldg(LC.b_reg2 + tid);
-          float bias_c = 0.f, gc = 0.f, bc = 0.f, w6 = 0.f;
-          if (want_cls) {
-            bias_c = __ldg(LC.b_cls3 + tid); gc = __ldg(LC.cls_ln5_g + tid); bc = __ldg(LC.cls_ln5_b + tid);
-            w6 = __ldg(LC.cls6_w + tid);
+          const int f = fg * 64 + quad * 16 + lane;
+          float bias_r = 0.f, bias_c = 0.f;
+          if (warp < 4) {
+            bias_r = __ldg(LC.b_reg2 + f);
+            if (want_cls) bias_c = __ldg(LC.b_cls3 + f);
           }
-          // regression-head rows of this warp: outputs c = warp, warp + 8, warp + 16 (3P = 24)
-          float w4[3][8];
+          // regression-head rows of this CTA: outputs c = fg*6 .. fg*6+5 (3P = 24)
+          const int nout = 3 * P / GF;
+          float w4[6][8];
+          if (warp < n_own) {
 #pragma unroll
-          for (int ci = 0; ci < 3; ++ci) {
-            const int c = warp + 8 * ci;
-            if (c < 3 * P) {
-              const float4 w0 = __ldg(reinterpret_cast<const float4*>(LC.reg4_w + (size_t)c * D + lane * 4));
-              const float4 w1 = __ldg(reinterpret_cast<const float4*>(LC.reg4_w + (size_t)c * D + 128 + lane * 4));
-              w4[ci][0] = w0.x; w4[ci][1] = w0.y; w4[ci][2] = w0.z; w4[ci][3] = w0.w;
-              w4[ci][4] = w1.x; w4[ci][5] = w1.y; w4[ci][6] = w1.z; w4[ci][7] = w1.w;
-            }
+            for (int ci = 0; ci < 6; ++ci)
+              if (ci < nout) ldg8(LC.reg4_w + (size_t)(fg * nout + ci) * D, lane, w4[ci]);
           }
+          float* act2 = reinterpret_cast<float*>(pipe + P_ACT2 + 8192);
           wait_acc();
-          float v[NAL], c[NAL];
-          acc2(half, 0, v);
-          if (want_cls) acc2(half, 1, c);
-          t0_s[tid] = fmaxf(v[0] + bias_r, 0.f);
-          t0_s[D + tid] = fmaxf(v[1] + bias_r, 0.f);
-          float score[NAL] = {0.f, 0.f};
-          if (want_cls) {   // scores = LN(c2).w6 + b6   (:221-224)
-            c[0] = fmaxf(c[0] + bias_c, 0.f);
-            c[1] = fmaxf(c[1] + bias_c, 0.f);
-            ln_feat(c, gc, bc);
-            score[0] = c[0] * w6;
-            score[1] = c[1] * w6;
-            block_sum2(score[0], score[1]);
-            const float b6 = __ldg(LC.cls6_b);
-            score[0] += b6;
-            score[1] += b6;
-          } else {
-            bsync();
+          if (warp < 4) {
+            float v[8];
+            acc8(ACC_LIN, v);
+            float* sl = act_ptr(k) + fg * (NROW * 64) + quad * 16 + lane;
+#pragma unroll
+            for (int n = 0; n < NROW; ++n)
+              if (lane < 16) sl[n * 64] = fmaxf(v[n] + bias_r, 0.f);
+            if (want_cls) {
+              acc8(ACC_LIN + 64, v);
+              float* s2 = act2 + fg * (NROW * 64) + quad * 16 + lane;
+#pragma unroll
+              for (int n = 0; n < NROW; ++n)
+                if (lane < 16) s2[n * 64] = fmaxf(v[n] + bias_c, 0.f);
+            }
+            xchg_send(k, off_x + X_ACT + (k & 1) * 8192 + fg * 2048, 2048,
+                      (uint32_t)(RING + P_ACT2 + 8192) + fg * 2048, want_cls ? 2048u : 0u, false);
           }
+          xchg_wait(k);
+          mark(29);
+          if (warp < n_own) {
+            const int n = warp, a = a0 + n;
+            float x[8];
+            act_load8(act_ptr(k), n, lane, x);
+            float mine = 0.f;
 #pragma unroll
-          for (int ci = 0; ci < 3; ++ci) {
-            const int cc = warp + 8 * ci;
-            if (cc < 3 * P) {
-#pragma unroll
-              for (int n = 0; n < NAL; ++n) {
-                float x[8];
-                load8(t0_s + n * D, lane, x);
+            for (int ci = 0; ci < 6; ++ci) {
+              if (ci < nout) {
                 float s = 0.f;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) s = fmaf(x[i], w4[ci][i], s);
                 s = warp_sum(s);
-                if (lane == 0) raw_o[n * 24 + cc] = s + __ldg(LC.reg4_b + cc);
+                if (lane == ci) mine = s;
               }
             }
-          }
-          bsync();
-          mark(29);
-          // reg[..., :2] += points; heading = tanh(.)*pi; next points; DDIM update (:378-380,424,632-636)
-          if (tid < NAL * 3 * P) {
-            const int n = tid / (3 * P), cidx = tid - n * 3 * P;
-            const int p = cidx / 3, comp = cidx - p * 3;
-            if (own_v[n]) {
-              const int a = own_a[n];
-              const float mine = raw_o[n * 24 + cidx];
+            float score = 0.f;
+            if (want_cls) {   // scores = LN(c2).w6 + b6   (:221-224)
+              float c2[8], w6[8], g5[8], b5[8];
+              ldg8(LC.cls_ln5_g, lane, g5); ldg8(LC.cls_ln5_b, lane, b5); ldg8(LC.cls6_w, lane, w6);
+              act_load8(act2, n, lane, c2);
+              ln_row_reg(c2, g5, b5);
+              float s = 0.f;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) s = fmaf(c2[i], w6[i], s);
+              score = warp_sum(s) + __ldg(LC.cls6_b);
+            }
+            // reg[..., :2] += points; heading = tanh(.)*pi; next points; DDIM update (:378-380,424,632-636)
+            if (lane < nout) {
+              const int cidx = fg * nout + lane, p = cidx / 3, comp = cidx - p * 3;
+              mine += __ldg(LC.reg4_b + cidx);
               if (call.dbg) C.tap_regraw[((size_t)scene * A + a) * 3 * P + cidx] = mine;
-              float out, nxt = 0.f;
+              float out;
               if (comp < 2) {
-                const int pi = n * 16 + p * 2 + comp;
-                out = __fadd_rn(mine, pts_o[pi]);
-                nxt = out;
+                const int pi = (a * P + p) * 2 + comp;
+                out = __fadd_rn(mine, pts_s[pi]);
+                float nxt = out;
                 if (do_ddim) {
                   const DdimCoef dc = C.dc[si];
                   const float x0 = comp ? norm_y(out) : norm_x(out);
-                  const float sample = img_o[pi];
+                  const float sample = img_o[n * 24 + cidx];
                   const float eps = __fdiv_rn(__fsub_rn(sample, __fmul_rn(dc.sqrt_ac_t, x0)), dc.sqrt_1m_ac_t);
                   const float x0c = fminf(fmaxf(x0, -1.0f), 1.0f);
                   const float im = __fadd_rn(__fmul_rn(dc.sqrt_ac_prev, x0c), __fmul_rn(dc.sqrt_1m_ac_prev, eps));
-                  img_o[pi] = im;
+                  img_o[n * 24 + cidx] = im;
                   const float vc = fminf(fmaxf(im, -1.0f), 1.0f);
                   nxt = comp ? denorm_y(vc) : denorm_x(vc);
                 }
-                pts_o[pi] = nxt;
-                if (!want_cls) {   // every CTA's next plan needs them
-                  const uint32_t dst = fix_addr + F_PTS + (uint32_t)(((a * P + p) * 2 + comp) * 4);
+                if (!want_cls) {   // every CTA's next plan (and the group's next embedding) needs them
+                  const uint32_t dst = fix_addr + F_PTS + (uint32_t)(pi * 4);
                   for (int cta = 0; cta < RES_CL; ++cta) st_cluster_f32(mapa(dst, (uint32_t)cta), nxt);
                 }
               } else {
@@ -1044,13 +1292,14 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
                 if (call.out_modes) call.out_modes[((size_t)scene * A + a) * 3 * P + cidx] = out;
                 st_cluster_f32(mapa(fix_addr + F_FIN + (uint32_t)((32 + a * 3 * P + cidx) * 4), 0u), out);
                 if (cidx == 0) {
-                  if (call.out_scores) call.out_scores[(size_t)scene * A + a] = score[n];
-                  st_cluster_f32(mapa(fix_addr + F_FIN + (uint32_t)(a * 4), 0u), score[n]);
+                  if (call.out_scores) call.out_scores[(size_t)scene * A + a] = score;
+                  st_cluster_f32(mapa(fix_addr + F_FIN + (uint32_t)(a * 4), 0u), score);
                 }
               }
             }
           }
-          if (!last_layer || want_cls) csync(); else bsync();
+          ++k;
+          csync();
         }
         mark(31);
       }
@@ -1075,7 +1324,27 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
   if (warp == 8) tmem_dealloc<TMEM_COLS>(tmem);
 }
 
+// bf16 [N][K] (K contiguous) -> the shared-memory image of its 64-wide k-chunks: tiles of `rows` rows,
+// [tile][k-chunk][row][128 B], 16-byte units XOR-swizzled by row & 7 (the UMMA 128-byte swizzle),
+// so that a CTA's slice of a stage is one contiguous piece a single bulk copy can fetch.
+__global__ void pack_sw128_kernel(const uint4* __restrict__ W, uint4* __restrict__ out, int N, int K, int rows) {
+  const int upr = K / 8;
+  const long long total = (long long)N * upr;
+  for (long long u = blockIdx.x * (long long)blockDim.x + threadIdx.x; u < total; u += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(u / upr), j8 = (int)(u - (long long)n * upr);
+    const int kc = j8 >> 3, j = j8 & 7, T = n / rows, r = n - T * rows;
+    out[((size_t)(T * (K / 64) + kc) * rows + r) * 8 + (j ^ (r & 7))] = W[u];
+  }
+}
+
 }  // namespace
+
+void launch_pack_sw128(const __nv_bfloat16* W, __nv_bfloat16* out, int N, int K, int rows, cudaStream_t st) {
+  const long long total = (long long)N * (K / 8);
+  const int blocks = (int)((total + 255) / 256);
+  pack_sw128_kernel<<<blocks < 1184 ? blocks : 1184, 256, 0, st>>>(reinterpret_cast<const uint4*>(W),
+                                                                    reinterpret_cast<uint4*>(out), N, K, rows);
+}
 
 int res2_smem_bytes() { return SMEM_BYTES; }
 
@@ -1107,7 +1376,11 @@ int res2_engine_init() {
   res2_cfg(cfg, attr, 1, nullptr);
   int nclusters = 0;
   e = cudaOccupancyMaxActiveClusters(&nclusters, res2_forward_kernel, &cfg);
-  if (e != cudaSuccess || nclusters < 1) { cudaGetLastError(); return 3; }
+  if (e != cudaSuccess || nclusters < 1) {
+    if (getenv("DDH_VERBOSE")) fprintf(stderr, "ddh: res2 occupancy query: %s, clusters %d\n", cudaGetErrorString(e), nclusters);
+    cudaGetLastError();
+    return 3;
+  }
   g_res2_ready = true;
   return 0;
 }

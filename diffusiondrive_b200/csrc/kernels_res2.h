@@ -16,16 +16,17 @@ enum : unsigned char {
   R2F_COMMIT = 2,     // last entry of a stage group: commit the accumulators to the compute warps
   R2F_CONV = 4,       // marker: the value_proj conv of a layer call runs here (map = conv weights)
   R2F_N32 = 8,        // 32 activation rows (hoisted K|V|ego stage), standard operand layout
-  R2F_RANKROWS = 16,  // feature-split stage: this CTA streams rows [rank*rows, +rows)
+  R2F_RANK16 = 16,    // 16-way feature split (hoisted stage): this CTA streams rows [rank*rows, +rows);
+                      // every other stage is 4-way: rows [fg*rows*mtiles, +rows*mtiles), fg = rank & 3
 };
 struct R2Stage {
-  const CUtensorMap* map;   // bf16 [N_out][K] weight matrix, box {64, rows}, 128-byte swizzle
-  unsigned short rows;      // weight rows per ring slot (128; 48 for the hoisted stage)
+  const void* w;            // weights packed by launch_pack_sw128: [tile of `rows` rows][k-chunk][row][128 B]
+  unsigned short rows;      // weight rows per tile (64; 48 for the hoisted stage)
   unsigned short acc_col;   // TMEM column of tile 0
-  unsigned char mtiles;     // 128-row output tiles
+  unsigned char mtiles;     // tiles per CTA
   unsigned char kchunks;    // K / 64
   unsigned char flags;
-  unsigned char bsel;       // 0: main B operand, 1: second (cls branch)
+  unsigned char bsel;       // B operand: 0 / 1 = the two chain buffers (stage parity), 2 = cls branch
 };
 
 struct alignas(16) R2Consts {
@@ -45,6 +46,8 @@ struct alignas(16) R2Consts {
 
 int res2_smem_bytes();
 int res2_engine_init();   // 0 when a 16-CTA cluster of this kernel can be co-scheduled
+// pack-time: bf16 [N][K] -> pre-swizzled shared-memory images of (rows x 64) tiles
+void launch_pack_sw128(const __nv_bfloat16* W, __nv_bfloat16* out, int N, int K, int rows, cudaStream_t st);
 int launch_res2_forward(const R2Consts* consts_dev, const ResCall& call, int B, cudaStream_t st);
 
 }  // namespace ddh

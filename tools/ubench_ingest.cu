@@ -17,8 +17,8 @@
 #include "../diffusiondrive_b200/csrc/tc_ptx.cuh"
 using namespace ddh;
 
-constexpr int SLOT = 16384;
-constexpr int NSLOT = 8;
+constexpr int SLOT = 32768;
+constexpr int NSLOT = 6;
 constexpr int NT = 288;
 
 __device__ __forceinline__ uint32_t ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -41,7 +41,7 @@ __device__ __forceinline__ void arrive_remote(uint32_t raddr) {
 
 __global__ void __launch_bounds__(NT, 1)
 ingest_kernel(const CUtensorMap* maps, const uint8_t* flat, size_t per_cta_bytes, int mode, int nslots_total,
-              int K, long long* out) {
+              int K, long long* out, int sz, int nprod) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;
@@ -68,16 +68,17 @@ ingest_kernel(const CUtensorMap* maps, const uint8_t* flat, size_t per_cta_bytes
   const int kch = K / 64;
   long long t0 = clock64();
   if (mode <= 4) {
-    if (warp == 8 && (tid & 31) == 0) {   // producer
-      for (int q = 0; q < nslots_total; ++q) {
+    if (warp >= 4 && warp < 4 + nprod && (tid & 31) == 0) {   // producers: warp 4 + p takes requests q = p (mod nprod)
+      for (int q = warp - 4; q < nslots_total; q += nprod) {
         const int s = q % NSLOT, use = q / NSLOT;
         if (use > 0) mbar_wait(empty(s), (use - 1) & 1);
-        mbar_arrive_expect_tx(full(s), SLOT);
+        mbar_arrive_expect_tx(full(s), sz);
         if (mode <= 1) {
-          const int tile = q % (per_cta_bytes / SLOT);
-          tma_load_2d(sm + s * SLOT, map, full(s), (tile % kch) * 64, (tile / kch) * 128);
+          const int rows = sz / 128;
+          const int tile = q % (per_cta_bytes / sz);
+          tma_load_2d(sm + s * SLOT, map, full(s), (tile % kch) * 64, (tile / kch) * rows);
         } else if (mode <= 3) {
-          bulk_1d(sm + s * SLOT, base + (size_t)(q % (per_cta_bytes / SLOT)) * SLOT, SLOT, full(s));
+          bulk_1d(sm + s * SLOT, base + (size_t)(q % (per_cta_bytes / sz)) * sz, sz, full(s));
         } else {
           // tell the issuer of this slot that my copy of the slot is free and armed
           const int issuer = q % nc;
@@ -153,30 +154,43 @@ int main(int argc, char** argv) {
   const int smem = NSLOT * SLOT + 1024 + 1024;
   cudaFuncSetAttribute(ingest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaFuncSetAttribute(ingest_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-  const int total = 512;   // slots per CTA = 8 MiB
-  for (int cl : {16, 8, 4, 1}) {
-    for (int mode = 0; mode <= 6; ++mode) {
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(cl);
-      cfg.blockDim = dim3(NT);
-      cfg.dynamicSmemBytes = smem;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-      cfg.attrs = at; cfg.numAttrs = 1;
-      long long h[16];
-      for (int rep = 0; rep < 3; ++rep) {
-        cudaError_t e = cudaLaunchKernelEx(&cfg, ingest_kernel, (const CUtensorMap*)dm, (const uint8_t*)flat, per, mode,
-                                           total, K, out);
-        if (e != cudaSuccess) { printf("launch failed: %s\n", cudaGetErrorString(e)); return 1; }
-        e = cudaDeviceSynchronize();
-        if (e != cudaSuccess) { printf("sync failed: %s\n", cudaGetErrorString(e)); return 1; }
+  for (int cl : {1}) {
+    for (int mode : {0, 2}) {
+      for (int nprod : {1, 2, 4}) for (int sz : {8192, 32768}) {
+        // per-size tensor maps (box rows = sz / 128)
+        for (int r = 0; r < 16; ++r) {
+          cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)N};
+          cuuint64_t gstr[1] = {(cuuint64_t)K * 2};
+          cuuint32_t box[2] = {64, (cuuint32_t)(sz / 128)};
+          cuuint32_t es[2] = {1, 1};
+          enc(&hm[r], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, flat + r * per, gdim, gstr, box, es,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
+        cudaMemcpy(dm, hm, sizeof hm, cudaMemcpyHostToDevice);
+        const int total = (8 << 20) / sz;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(cl);
+        cfg.blockDim = dim3(NT);
+        cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        long long h[16];
+        for (int rep = 0; rep < 3; ++rep) {
+          cudaError_t e = cudaLaunchKernelEx(&cfg, ingest_kernel, (const CUtensorMap*)dm, (const uint8_t*)flat, per, mode,
+                                             total, K, out, sz, nprod);
+          if (e != cudaSuccess) { printf("launch failed: %s\n", cudaGetErrorString(e)); return 1; }
+          e = cudaDeviceSynchronize();
+          if (e != cudaSuccess) { printf("sync failed: %s\n", cudaGetErrorString(e)); return 1; }
+        }
+        cudaMemcpy(h, out, sizeof(long long) * cl, cudaMemcpyDeviceToHost);
+        long long mx = 0;
+        for (int i = 0; i < cl; ++i) mx = h[i] > mx ? h[i] : mx;
+        printf("cluster %2d mode %d producers %d request %5d B: %8lld cycles for 8 MiB per CTA -> %.1f B/clk per CTA, %.0f cycles per request\n",
+               cl, mode, nprod, sz, mx, (double)(8 << 20) / (double)mx, (double)mx / total);
       }
-      cudaMemcpy(h, out, sizeof(long long) * cl, cudaMemcpyDeviceToHost);
-      long long mx = 0;
-      for (int i = 0; i < cl; ++i) mx = h[i] > mx ? h[i] : mx;
-      printf("cluster %2d mode %d: %8lld cycles for %d KiB per CTA -> %.1f B/clk per CTA\n", cl, mode, mx,
-             total * SLOT / 1024, (double)total * SLOT / (double)mx);
     }
   }
   return 0;
