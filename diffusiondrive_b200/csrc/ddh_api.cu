@@ -622,7 +622,7 @@ int build_res2(ddh_handle* h, cudaStream_t st) {
   }
   // the schedule, in the program order of the compute warps (kernels_res2.cu); chain stage k
   // reads B operand buffer k & 1
-  constexpr unsigned short ACC_LIN = 256;   // linear tile t at ACC_LIN + 64 t (4 accumulators of 16 columns)
+  constexpr unsigned short ACC_LIN = 128;   // linear tile t, issuer j at ACC_LIN + 32 t + 16 j; cls branch at ACC_LIN + 64
   int n = 0, k = 0;
   auto stage = [&](const void* m, int rows, int mtiles, int K, int acc_col, int flags, int bsel) {
     R2Stage& g = C.stages[n++];
@@ -632,7 +632,7 @@ int build_res2(ddh_handle* h, cudaStream_t st) {
   };
   const int both = R2F_WAITB | R2F_COMMIT;
   for (int l = 0; l < L; ++l)
-    stage(lw[l].kvego, 3 * D / RES_CL, 1, D, ACC_LIN + 32 * l,
+    stage(lw[l].kvego, 3 * D / RES_CL, 1, D, ACC_LIN + 64 * l,
           R2F_N32 | R2F_RANK16 | (l == 0 ? R2F_WAITB : 0) | (l == L - 1 ? R2F_COMMIT : 0), 0);
   const int fq = F / 4;   // hidden features per CTA
   for (int si = 0; si < S; ++si) {

@@ -35,7 +35,7 @@
 namespace ddh {
 namespace {
 
-constexpr int NT = 352;                      // 8 compute warps + 2 weight-copy warps + MMA warp
+constexpr int NT = 384;                      // 8 compute warps + 2 weight-copy warps + 2 MMA warps
 constexpr int NPROD = 2;                     // a thread's bulk copies run one at a time (~750 cycles each,
                                              // measured: tools/ubench_ingest.cu), so two threads issue them
 constexpr int NCT = 256;                     // compute threads
@@ -56,10 +56,13 @@ constexpr int KC_CONV = 9 * (D / 64);        // 36 k-chunks: (tap, 64-channel ch
 constexpr int BCH = 1024;                    // chain B operand: 8 rows x 128 B per k-chunk; rows 8..15 of
                                              // the N = 16 operand alias rows 0..7 (descriptor SBO = 0)
 constexpr int BCH32 = 4096;                  // hoisted stage: 32 rows x 128 B
-// Dependent tcgen05.mma (same accumulator) issue ~140 cycles apart whatever their shape (measured), so
-// the 4 K=16 steps of a 64-wide k-chunk go to 4 independent accumulators that the epilogue adds up.
-constexpr int NACC = 4;
-constexpr uint32_t ACC_CONV = 0, ACC_LIN = 256;   // conv: 4 x 64 columns; linear tile t: ACC_LIN + 64 t + 16 j
+// A tcgen05.mma costs its ISSUING THREAD ~160 cycles whatever its shape, and threads of different
+// warps issue concurrently (measured: tools/ubench_mma.cu, 159 -> 85 -> 48 cycles per instruction with
+// 1 / 2 / 4 issuers).  NMMA threads therefore share every stage: issuer j takes k-steps 2j, 2j+1 of
+// each 64-wide k-chunk into its own accumulator (a fixed summation order keeps results
+// deterministic); the epilogues add the NMMA accumulators.
+constexpr int NMMA = 2;
+constexpr uint32_t ACC_CONV = 0, ACC_LIN = 128;   // TMEM columns: conv 2 x 64; linear tile t, issuer j at ACC_LIN + 32 t + 16 j
 constexpr int TMEM_COLS = 512;
 constexpr int VS_LD = CCOLS + 4;
 constexpr int KS_LD = 64 + 4;                // padded K rows (2 heads): conflict-free 128-bit reads, lane = agent
@@ -350,10 +353,10 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
     for (int i = tid; i < (int)(sizeof(R2Consts) / 16); i += NT) d[i] = __ldg(s + i);
   }
   if (tid == 0) {
-    for (int s = 0; s < NSLOT; ++s) { mbar_init(ring_full(s), 1); mbar_init(ring_empty(s), 1); }
-    for (int s = 0; s < CNS; ++s) { mbar_init(conv_full(s), NCT + 1); mbar_init(conv_empty(s), 1); }
-    mbar_init(conv_acc, 1);
-    mbar_init(acc_full, 1);
+    for (int s = 0; s < NSLOT; ++s) { mbar_init(ring_full(s), 1); mbar_init(ring_empty(s), NMMA); }
+    for (int s = 0; s < CNS; ++s) { mbar_init(conv_full(s), NCT + 1); mbar_init(conv_empty(s), NMMA); }
+    mbar_init(conv_acc, NMMA);
+    mbar_init(acc_full, NMMA);
     mbar_init(b_ready, NCT);
     mbar_init(conv_go, 1);
     mbar_init(cl_bar, RES_CL);
@@ -416,8 +419,9 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
     __syncwarp();
   }
   // =============================================================== MMA thread
-  else if (warp == 8 + NPROD) {
+  else if (warp >= 8 + NPROD) {
     if (lane == 0) {
+      const int mj = warp - (8 + NPROD);   // issuer index: k-steps 2 mj, 2 mj + 1 of every k-chunk
       int seq = 0, cg = 0;
       uint32_t bpar = 0, gopar = 0;
       for (int si = 0; si < C.n_stages; ++si) {
@@ -436,9 +440,11 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
               tc_fence_after();
               const uint32_t a_stage = pipe_addr + s * CSTAGE;
 #pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4)   // accumulator 0 starts at the bias, 1..3 at zero
-                umma_bf16(tmem + ACC_CONV + k4 * CCOLS, umma_desc_sw128(a_stage + k4 * 32),
-                          umma_desc_sw128(a_stage + CA_TILE + k4 * 32), idesc, (kc > 0 || k4 == 0) ? 1u : 0u);
+              for (int kk = 0; kk < 4 / NMMA; ++kk) {   // issuer 0's accumulator starts at the bias, the others at zero
+                const int k4 = mj * (4 / NMMA) + kk;
+                umma_bf16(tmem + ACC_CONV + mj * CCOLS, umma_desc_sw128(a_stage + k4 * 32),
+                          umma_desc_sw128(a_stage + CA_TILE + k4 * 32), idesc, (mj == 0 || kc > 0 || kk > 0) ? 1u : 0u);
+              }
               umma_commit(conv_empty(s));
             }
             umma_commit(conv_acc);
@@ -464,13 +470,15 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
             const uint64_t adesc = umma_desc_sw128(sm_addr + slot * SLOT);
             const uint64_t bdesc = umma_desc_sw128_sbo(b_addr + kg * FKC * bch, sbo);
             const uint32_t astep = ((uint32_t)stg.rows * 128u) >> 4, bstep = bch >> 4;
-            const uint32_t dcol = tmem + stg.acc_col + mt * 64;
+            const uint32_t dcol = tmem + stg.acc_col + (mt * NMMA + mj) * ncol;
 #pragma unroll
             for (int c = 0; c < FKC; ++c)
 #pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4)
-                umma_bf16(dcol + (n32 ? 0 : k4 * 16), adesc + (uint64_t)(c * astep + k4 * 2),
-                          bdesc + (uint64_t)(c * bstep + k4 * 2), idesc, n32 ? ((kg | c | k4) ? 1u : 0u) : ((kg | c) ? 1u : 0u));
+              for (int kk = 0; kk < 4 / NMMA; ++kk) {
+                const int k4 = mj * (4 / NMMA) + kk;
+                umma_bf16(dcol, adesc + (uint64_t)(c * astep + k4 * 2), bdesc + (uint64_t)(c * bstep + k4 * 2), idesc,
+                          (kg | c | kk) ? 1u : 0u);
+              }
             umma_commit(ring_empty(slot));
             ++seq;
           }
@@ -490,7 +498,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
     for (int j = 0; j < GF; ++j) peer[j] = mapa(sm_addr, (uint32_t)(ag * GF + j));
     uint32_t acc_par = 0, cl_par = 0, conv_par = 0;
     int cg = 0, dbg_i = 0, k = 0;   // k: linear stage counter (B operand / row buffer parity)
-    unsigned long long done_rows = 0ull;
+    if (tid == 0) need_s[1] = 0ull;   // BEV rows already converted (kept in shared memory: a spilled copy costs ~5 k cycles per reload)
     const __nv_bfloat16* bevn =
         call.bev_nhwc_bf16 ? reinterpret_cast<const __nv_bfloat16*>(call.bev) + (size_t)scene * HW * D
                            : C.bev_nhwc + (size_t)scene * HW * D;
@@ -498,7 +506,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
     float* egog = C.egov + (size_t)scene * L * D;
 
     auto mark = [&](int label) {
-      if (call.dbg && scene == 0 && rank == 0 && tid == 0 && dbg_i < 1000)
+      if (call.dbg && scene == 0 && rank == 0 && tid == 0 && dbg_i < 900)
         call.dbg[dbg_i++] = ((long long)label << 48) | (clock64() & 0xFFFFFFFFFFFFll);
     };
     auto bsync = [&]() { named_bar_sync(1, NCT); };
@@ -508,7 +516,12 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
       mark(104);
       bsync();
       if (tid < RES_CL) mbar_arrive_remote_release(mapa(cl_bar, (uint32_t)tid));
-      mbar_wait_acq_cluster(cl_bar, cl_par);
+      // CTA-scope acquire on purpose: a cluster-scope acquire makes the SM drop its L1 (CCTL.IVALL),
+      // after which every register-spill reload misses to L2 (~5 k cycles per barrier, measured).
+      // What crosses CTAs here is either shared memory (not cached) or global memory that the
+      // consumers read with L1-bypassing loads (__ldcg / cp.async.cg); the producers' release is
+      // cluster-scoped.
+      mbar_wait(cl_bar, cl_par);
       cl_par ^= 1u;
       mark(105);
     };
@@ -550,18 +563,15 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
       xbits ^= 1u << (kk & 1);
     };
     // this thread's feature column (warps 0-1: local feature fl of tile mt) of the group's rows
-    auto acc8 = [&](uint32_t acc_col, float (&v)[8]) {
-      uint32_t u[32];
-      tmem_ld32(tlane + acc_col, u);      // columns 16 j + n: accumulator j, row n (n < 8 used)
-      tmem_ld_wait();
-      tmem_ld8(tlane + acc_col + 48, v);  // accumulator 3 lives in columns 48..55 (tmem_ld32 covers 0..31)
+    auto acc8 = [&](uint32_t acc_col, float (&v)[8]) {   // sum of the issuers' accumulators, fixed order
+      tmem_ld8(tlane + acc_col, v);
 #pragma unroll
-      for (int n = 0; n < 8; ++n)
-        v[n] = (__uint_as_float(u[n]) + __uint_as_float(u[16 + n])) + (v[n] + 0.f);
-      float w[8];
-      tmem_ld8(tlane + acc_col + 32, w);
+      for (int j = 1; j < NMMA; ++j) {
+        float w[8];
+        tmem_ld8(tlane + acc_col + j * 16, w);
 #pragma unroll
-      for (int n = 0; n < 8; ++n) v[n] += w[n];
+        for (int n = 0; n < 8; ++n) v[n] += w[n];
+      }
     };
     const uint32_t off_x = (uint32_t)(RING + PIPE);   // offset of X from the shared-memory base
 
@@ -609,9 +619,12 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
         const int f = quad * 16 + lane;
         const int gfeat = rank * rows + f;
         for (int l = 0; l < L; ++l) {
-          uint32_t u[32];
-          tmem_ld32(tlane + ACC_LIN + 32 * l, u);
+          uint32_t u[32], u2[32];
+          tmem_ld32(tlane + ACC_LIN + 64 * l, u);
+          tmem_ld32(tlane + ACC_LIN + 64 * l + 32, u2);
           tmem_ld_wait();
+#pragma unroll
+          for (int a = 0; a < 32; ++a) u[a] = __float_as_uint(__uint_as_float(u[a]) + __uint_as_float(u2[a]));
           if (lane < 16 && f < rows) {
             const float bias = __ldg(C.layer[l].b_kvego + gfeat);
             float* kvl = kvg + (size_t)l * Na * 2 * D;
@@ -742,20 +755,16 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
           const int nwords = HW / 32;
           if (tid < nwords) bm_s[tid] = 0u;
           if (tid < CCOLS) cbias_s[tid] = __ldg(LC.b_conv + fg * CCOLS + tid);
-          if (tid == 0) *need_s = 0ull;
-          Corners c;
-          float a_w = 0.f;
-          if (tid < AP) {
-            c = corners_of(pts_s[tid * 2 + 0], pts_s[tid * 2 + 1], H, W, C.oc);
-            a_w = aw_s[l * AP + tid];
-          }
+          mark(110);
           bsync();
           if (tid < AP) {
+            const Corners c = corners_of(pts_s[tid * 2 + 0], pts_s[tid * 2 + 1], H, W, C.oc);
 #pragma unroll
             for (int q = 0; q < 4; ++q)
               if (c.pix[q] >= 0) atomicOr(bm_s + (c.pix[q] >> 5), 1u << (c.pix[q] & 31));
           }
           bsync();
+          mark(111);
           // ordered compaction (pixel order == memory order of the NHWC map)
           if (tid < 128) {
             const unsigned int bits = tid < nwords ? bm_s[tid] : 0u;
@@ -767,11 +776,13 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
               if (lane >= o) incl += t;
             }
             if (lane == 31) ints_s[warp] = incl;
+            mark(115);
             named_bar_sync(3, 128);
             int base = incl - cnt;
             for (int w = 0; w < warp; ++w) base += ints_s[w];
             if (tid == 127) ints_s[4] = base + cnt;
             if (tid < nwords) pre_s[tid] = base;
+            mark(116);
             if (bits) {
               const int y = (tid * 32) / W, x0 = tid * 32 - y * W;
               unsigned int rest = bits;
@@ -780,29 +791,48 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
                 rest &= rest - 1;
                 upix_s[base++] = (y << 16) | (x0 + b);
               }
-              atomicOr(need_s, (y > 0) ? (7ull << (y - 1)) : 3ull);
             }
+            mark(117);
+            // BEV rows (with their 3x3 halo) this warp's words touch: one shared-memory word per warp
+            // instead of a contended 64-bit atomic per thread
+            {
+              const int y = (tid * 32) / W;
+              const unsigned long long m = bits ? ((y > 0) ? (7ull << (y - 1)) : 3ull) : 0ull;
+              const unsigned int lo = __reduce_or_sync(0xffffffffu, (unsigned int)m);
+              const unsigned int hi = __reduce_or_sync(0xffffffffu, (unsigned int)(m >> 32));
+              if (lane == 0) need_s[2 + warp] = ((unsigned long long)hi << 32) | lo;
+            }
+            mark(118);
           }
+          if (call.dbg && scene == 0 && rank == 0 && lane == 0 && l == 0 && si == 0) call.dbg[900 + warp] = clock64() & 0xFFFFFFFFFFFFll;
           bsync();
+          mark(112);
           nu = ints_s[4];
-          const unsigned long long need_all = (H >= 64) ? *need_s : (*need_s & ((1ull << H) - 1ull));
+          const unsigned long long need_any = (need_s[2] | need_s[3]) | (need_s[4] | need_s[5]);
+          const unsigned long long need_all = (H >= 64) ? need_any : (need_any & ((1ull << H) - 1ull));
+          const unsigned long long done_rows = need_s[1];
           todo = call.bev_nhwc_bf16 ? 0ull : (need_all & ~done_rows);
-          done_rows |= need_all;
-          if (tid < AP) {
+          mark(113);
+          if (tid < AP) {   // corners recomputed: keeping them live across the barriers costs spills
+            const Corners c2 = corners_of(pts_s[tid * 2 + 0], pts_s[tid * 2 + 1], H, W, C.oc);
+            const float a_w = aw_s[l * AP + tid];
+            mark(114);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               EntPair ep;
               ep.slot = -1;
               ep.w = 0.f;
-              if (c.pix[q] >= 0) {
-                const int wd = c.pix[q] >> 5;
-                ep.slot = pre_s[wd] + __popc(bm_s[wd] & ((1u << (c.pix[q] & 31)) - 1u));
-                ep.w = c.w[q] * a_w;
+              if (c2.pix[q] >= 0) {
+                const int wd = c2.pix[q] >> 5;
+                ep.slot = pre_s[wd] + __popc(bm_s[wd] & ((1u << (c2.pix[q] & 31)) - 1u));
+                ep.w = c2.w[q] * a_w;
               }
               ent[tid * 4 + q] = ep;
             }
           }
         }
+        bsync();
+        if (tid == 0) need_s[1] |= (need_s[2] | need_s[3]) | (need_s[4] | need_s[5]);
         mark(20);
         // ============ on-demand BEV layout: the rows this conv call reads, not converted yet
         if (todo) {
@@ -903,43 +933,47 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
                 tmem_ld32(tlane + ACC_CONV + hh * 32, u0);
                 tmem_ld32(tlane + ACC_CONV + CCOLS + hh * 32, u1);
                 tmem_ld_wait();
-                float t[32];
 #pragma unroll
-                for (int q = 0; q < 32; ++q) t[q] = __uint_as_float(u0[q]) + __uint_as_float(u1[q]);
-                tmem_ld32(tlane + ACC_CONV + 2 * CCOLS + hh * 32, u0);
-                tmem_ld32(tlane + ACC_CONV + 3 * CCOLS + hh * 32, u1);
-                tmem_ld_wait();
-#pragma unroll
-                for (int q = 0; q < 32; ++q) t[q] += __uint_as_float(u0[q]) + __uint_as_float(u1[q]);
+                for (int q = 0; q < 32; ++q) u0[q] = __float_as_uint(__uint_as_float(u0[q]) + __uint_as_float(u1[q]));
                 if (lane < 16) {
 #pragma unroll
                   for (int q = 0; q < 8; ++q)
                     *reinterpret_cast<float4*>(vrow + hh * 32 + 4 * q) = make_float4(
-                        fmaxf(t[4 * q], 0.f), fmaxf(t[4 * q + 1], 0.f), fmaxf(t[4 * q + 2], 0.f), fmaxf(t[4 * q + 3], 0.f));
+                        fmaxf(__uint_as_float(u0[4 * q]), 0.f), fmaxf(__uint_as_float(u0[4 * q + 1]), 0.f),
+                        fmaxf(__uint_as_float(u0[4 * q + 2]), 0.f), fmaxf(__uint_as_float(u0[4 * q + 3]), 0.f));
                 }
               }
               tc_fence_before();
             }
             bsync();
+            mark(127);
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
               const int a = a_c + 16 * i;
               if (a < A) {
                 const EntPair* ea = ent + a * P * 4;
-#pragma unroll 8
-                for (int q = 0; q < P * 4; ++q) {
-                  const EntPair e = ea[q];
-                  const int rr = e.slot - row_base;
-                  if (rr >= 0 && rr < rows_valid) {
-                    const float4 v = *reinterpret_cast<const float4*>(Vs + (size_t)rr * VS_LD + cqd * 4);
-                    sacc[i].x = fmaf(e.w, v.x, sacc[i].x); sacc[i].y = fmaf(e.w, v.y, sacc[i].y);
-                    sacc[i].z = fmaf(e.w, v.z, sacc[i].z); sacc[i].w = fmaf(e.w, v.w, sacc[i].w);
+                for (int q0 = 0; q0 < P * 4; q0 += 8) {   // 8 entries in flight, no branches
+                  float wq[8];
+                  float4 vq[8];
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) {
+                    const EntPair e = ea[q0 + q];
+                    const int rr = e.slot - row_base;
+                    const bool ok = rr >= 0 && rr < rows_valid;
+                    wq[q] = ok ? e.w : 0.f;
+                    vq[q] = *reinterpret_cast<const float4*>(Vs + (size_t)(ok ? rr : 0) * VS_LD + cqd * 4);
+                  }
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) {
+                    sacc[i].x = fmaf(wq[q], vq[q].x, sacc[i].x); sacc[i].y = fmaf(wq[q], vq[q].y, sacc[i].y);
+                    sacc[i].z = fmaf(wq[q], vq[q].z, sacc[i].z); sacc[i].w = fmaf(wq[q], vq[q].w, sacc[i].w);
                   }
                 }
               }
             }
             bsync();
           }
+          mark(128);
           // this CTA's [A x 64] slice of the sampled features -> the four CTAs of each anchor's group
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
@@ -951,6 +985,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
               for (int jj = 0; jj < GF; ++jj) st_cluster_v4(mapa(sm_addr + d, (uint32_t)(g_a * GF + jj)), sacc[i]);
             }
           }
+          mark(129);
           // stage the agent K|V of my two heads (fp32) in the idle conv pipeline buffers
           {
             const float* kvl = kvg + (size_t)l * Na * 2 * D;
@@ -1065,9 +1100,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
             ldg8(LC.norm1_g, lane, g1); ldg8(LC.norm1_b, lane, b1);
             ldg8(LC.norm2_g, lane, g2); ldg8(LC.norm2_b, lane, b2);
           }
-          mark(129);
           wait_acc();
-          mark(130);
           if (warp < 4) {
             float v[8];
             acc8(ACC_LIN, v);
@@ -1075,12 +1108,9 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
 #pragma unroll
             for (int n = 0; n < NROW; ++n)
               if (lane < 16) sl[n * 64] = v[n] + bias + x1_s[n * D + f];
-            mark(131);
             xchg_send(k, off_x + X_ACT + (k & 1) * 8192 + fg * 2048, 2048, 0, 0, false);
           }
-          mark(132);
           xchg_wait(k);
-          mark(133);
           if (warp < n_own) {
             float v[8], eg[8];
             act_load8(act_ptr(k), warp, lane, v);
@@ -1092,7 +1122,6 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
             bt_store8(bop_ptr(k + 1), warp, lane, v);
           }
           ++k;
-          mark(134);
           b_done();
         }
         mark(25);
@@ -1111,7 +1140,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
             for (int t = 0; t < 4; ++t) {
               if (t < ntl) {
                 float v[8];
-                acc8(ACC_LIN + t * 64, v);
+                acc8(ACC_LIN + t * 32, v);
                 const int f = fg * fq + t * 64 + quad * 16 + lane;
 #pragma unroll
                 for (int n = 0; n < NROW; ++n)

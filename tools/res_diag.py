@@ -119,8 +119,15 @@ def run_time():
             print(f"[time {name}] B={B} launches={head.last_launch_count()} p50 {ts[len(ts)//2]:.1f} us "
                   f"min {ts[0]:.1f} us", flush=True)
             if B == 1 and res == RES_MODE:
-                dbg = head.debug_tap("dbg", np.int64)[:1000]
+                dbg_all = head.debug_tap("dbg", np.int64)[:1000]
+                dbg = dbg_all[:900]
                 n = int((dbg > 0).sum())
+                extra = dbg_all[900:916]
+                if (extra > 0).any():
+                    lab0 = (dbg[:n] >> 48).tolist()
+                    clk0 = (dbg[:n] & ((1 << 48) - 1)).tolist()
+                    ref = clk0[lab0.index(112)] if 112 in lab0 else clk0[0]
+                    print("  per-warp stamps relative to the first mark 112:", [int(x) - ref if x > 0 else None for x in extra.tolist()])
                 if n > 2:
                     lab = (dbg[:n] >> 48).tolist()
                     clk = (dbg[:n] & ((1 << 48) - 1)).tolist()
