@@ -548,7 +548,7 @@ int build_res2(ddh_handle* h, cudaStream_t st) {
             S = s.num_steps, H = s.bev_h, W = s.bev_w;
   if (h->res_mode != 2 || h->precision != DDH_PREC_BF16) return DDH_OK;
   if (A > 28 || A * P > 256 || P != 8 || Na > 30 || F > 1024 || F % 256 || s.num_heads != 8 ||
-      H * W > 4096 || H > 64 || W % 32 || L > RES_MAX_L || S > RES_MAX_S || s.bev_channels != 256)
+      H * W > 4096 || H > 64 || W % 32 || L > 2 || S > RES_MAX_S || s.bev_channels != 256)
     return DDH_OK;
   if (const int why = res2_engine_init()) {
     if (getenv("DDH_VERBOSE")) fprintf(stderr, "ddh: anchor-resident engine unavailable (init step %d)\n", why);
@@ -622,7 +622,7 @@ int build_res2(ddh_handle* h, cudaStream_t st) {
   }
   // the schedule, in the program order of the compute warps (kernels_res2.cu); chain stage k
   // reads B operand buffer k & 1
-  constexpr unsigned short ACC_LIN = 128;   // linear tile t, issuer j at ACC_LIN + 32 t + 16 j; cls branch at ACC_LIN + 64
+  constexpr unsigned short ACC_LIN = 256;   // linear tile t, issuer j at ACC_LIN + 64 t + 16 j; cls branch at ACC_LIN + 64
   int n = 0, k = 0;
   auto stage = [&](const void* m, int rows, int mtiles, int K, int acc_col, int flags, int bsel) {
     R2Stage& g = C.stages[n++];
@@ -632,7 +632,7 @@ int build_res2(ddh_handle* h, cudaStream_t st) {
   };
   const int both = R2F_WAITB | R2F_COMMIT;
   for (int l = 0; l < L; ++l)
-    stage(lw[l].kvego, 3 * D / RES_CL, 1, D, ACC_LIN + 64 * l,
+    stage(lw[l].kvego, 3 * D / RES_CL, 1, D, ACC_LIN + 128 * l,
           R2F_N32 | R2F_RANK16 | (l == 0 ? R2F_WAITB : 0) | (l == L - 1 ? R2F_COMMIT : 0), 0);
   const int fq = F / 4;   // hidden features per CTA
   for (int si = 0; si < S; ++si) {

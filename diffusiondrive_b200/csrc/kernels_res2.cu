@@ -35,7 +35,7 @@
 namespace ddh {
 namespace {
 
-constexpr int NT = 384;                      // 8 compute warps + 2 weight-copy warps + 2 MMA warps
+constexpr int NT = 384;                      // 8 compute warps + 4 engine warps
 constexpr int NPROD = 2;                     // a thread's bulk copies run one at a time (~750 cycles each,
                                              // measured: tools/ubench_ingest.cu), so two threads issue them
 constexpr int NCT = 256;                     // compute threads
@@ -49,20 +49,25 @@ constexpr int RING = NSLOT * SLOT;
 constexpr int CROWS = 64;                    // conv tile: 64 unique pixels x 64 output columns per CTA
 constexpr int CCOLS = 64;
 constexpr int CA_TILE = CROWS * 128;
-constexpr int CNS = 4;                       // conv pipeline stages
-constexpr int CSTAGE = CA_TILE + CCOLS * 128;
-constexpr int PIPE = CNS * CSTAGE;
+constexpr int CNS = 4;                       // conv pipeline stages of TWO k-chunks each (a stage hand-over costs
+                                             // ~400 cycles whatever it carries): [A0 | A1 | B0 | B1], 32 KiB; the conv
+                                             // borrows the weight ring (idle while it runs): RING + PIPE
+constexpr int CSTAGE = 2 * (CA_TILE + CCOLS * 128);
+constexpr int PIPE = 2 * CSTAGE;
+static_assert(CNS * CSTAGE == RING + PIPE, "conv stages span the weight ring and the pipeline buffers");
 constexpr int KC_CONV = 9 * (D / 64);        // 36 k-chunks: (tap, 64-channel chunk)
+constexpr int KP_CONV = KC_CONV / 2;         // pipeline steps (pairs of k-chunks)
 constexpr int BCH = 1024;                    // chain B operand: 8 rows x 128 B per k-chunk; rows 8..15 of
                                              // the N = 16 operand alias rows 0..7 (descriptor SBO = 0)
 constexpr int BCH32 = 4096;                  // hoisted stage: 32 rows x 128 B
 // A tcgen05.mma costs its ISSUING THREAD ~160 cycles whatever its shape, and threads of different
 // warps issue concurrently (measured: tools/ubench_mma.cu, 159 -> 85 -> 48 cycles per instruction with
-// 1 / 2 / 4 issuers).  NMMA threads therefore share every stage: issuer j takes k-steps 2j, 2j+1 of
-// each 64-wide k-chunk into its own accumulator (a fixed summation order keeps results
-// deterministic); the epilogues add the NMMA accumulators.
-constexpr int NMMA = 2;
-constexpr uint32_t ACC_CONV = 0, ACC_LIN = 128;   // TMEM columns: conv 2 x 64; linear tile t, issuer j at ACC_LIN + 32 t + 16 j
+// 1 / 2 / 4 issuers).  NMMA threads therefore share every stage: issuer j takes k-step j of each
+// 64-wide k-chunk into its own accumulator (a fixed summation order keeps results deterministic)
+// and the epilogues add the NMMA accumulators.  The linear stages are issued by lane 0 of compute
+// warps 4..7 (idle while the tensor core works), the conv by the four engine warps.
+constexpr int NMMA = 4;
+constexpr uint32_t ACC_CONV = 0, ACC_LIN = 256;   // TMEM columns: conv 4 x 64; linear tile t, issuer j at ACC_LIN + 64 t + 16 j
 constexpr int TMEM_COLS = 512;
 constexpr int VS_LD = CCOLS + 4;
 constexpr int KS_LD = 64 + 4;                // padded K rows (2 heads): conflict-free 128-bit reads, lane = agent
@@ -150,6 +155,8 @@ __device__ __forceinline__ void mbar_wait_acq_cluster(uint32_t bar, uint32_t par
   } while (!done);
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // D = f32, A = B = bf16, K-major, M = 64, N = n.  An M = 64 instruction occupies the tensor pipe
 // for half the time of an M = 128 one whatever N is (measured); its accumulator row r lives in
@@ -199,18 +206,22 @@ __device__ __forceinline__ float4 ld4_bev<__nv_bfloat16>(const __nv_bfloat16* p)
 }
 
 // NCHW -> NHWC bf16 for one (row y, 32-pixel block): 256 channels x 32 pixels through a padded
-// shared-memory tile (same scheme as bev_rows_to_nhwc_kernel); 256 compute threads
+// shared-memory tile (same scheme as bev_rows_to_nhwc_kernel); 256 compute threads.  Split in a
+// load half and a store half so that the loads of the next item are in flight while this one is
+// transposed and written.
 template <typename TI>
-__device__ __forceinline__ void layout_item(const TI* __restrict__ src, __nv_bfloat16* __restrict__ dst,
-                                            int HW, int px0, uint32_t* tile_u32, int tid) {
+__device__ __forceinline__ void layout_load(const TI* __restrict__ src, int HW, int px0, int tid, float4 (&v)[8]) {
+  const int px4 = tid & 7, cl = tid >> 3;
+  const TI* s = src + px0 + px4 * 4;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = ld4_bev<TI>(s + (size_t)(i * 32 + cl) * HW);
+}
+__device__ __forceinline__ void layout_store(__nv_bfloat16* __restrict__ dst, int px0, uint32_t* tile_u32, int tid,
+                                             const float4 (&v)[8]) {
   constexpr int LDW = 129;
   constexpr int LDE = LDW * 2;
   __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(tile_u32);
   const int px4 = tid & 7, cl = tid >> 3, lane = tid & 31, warp = tid >> 5;
-  const TI* s = src + px0 + px4 * 4;
-  float4 v[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = ld4_bev<TI>(s + (size_t)(i * 32 + cl) * HW);
   named_bar_sync(1, NCT);   // previous tile fully written out
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -354,7 +365,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
   }
   if (tid == 0) {
     for (int s = 0; s < NSLOT; ++s) { mbar_init(ring_full(s), 1); mbar_init(ring_empty(s), NMMA); }
-    for (int s = 0; s < CNS; ++s) { mbar_init(conv_full(s), NCT + 1); mbar_init(conv_empty(s), NMMA); }
+    for (int s = 0; s < CNS; ++s) { mbar_init(conv_full(s), NCT + 1); mbar_init(conv_empty(s), 2); }
     mbar_init(conv_acc, NMMA);
     mbar_init(acc_full, NMMA);
     mbar_init(b_ready, NCT);
@@ -376,33 +387,51 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
   const int ag = rank >> 2, fg = rank & 3;          // anchor group, feature group (also conv row tile, column group)
   const int NAG = (A + 3) >> 2;                     // anchors per group
 
-  // =============================================================== weight-copy threads
-  if (warp >= 8 && warp < 8 + NPROD) {
+  // =============================================================== engine warps 8..11
+  // Warps 8 and 9 stream the linear stages' weights (a thread's bulk copies run one at a time, so
+  // two threads alternate); all four issue the conv's MMAs, k-step `me` of every k-chunk each.
+  if (warp >= 8) {
     if (lane == 0) {
       const int me = warp - 8;
       int seq = 0, cg = 0;
-      uint32_t gopar = 0;
+      uint32_t gopar = 0, capar = 0;
       for (int si = 0; si < C.n_stages; ++si) {
         const R2Stage stg = C.stages[si];
-        if (stg.flags & R2F_CONV) {   // the conv's weight tiles: 8 KiB per k-chunk
+        if (stg.flags & R2F_CONV) {
           mbar_wait(conv_go, gopar);
           gopar ^= 1u;
           const int nu = *reinterpret_cast<volatile int*>(ints_s + 4);
           const int passes = (nu + 255) / 256;
-          const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(stg.w) + (size_t)fg * KC_CONV * (CCOLS * 128);
+          constexpr uint32_t idesc = idesc_m64(CCOLS);
           for (int pass = 0; pass < passes; ++pass) {
             if (pass * 256 + ag * CROWS >= nu) continue;
-            for (int kc = 0; kc < KC_CONV; ++kc) {
-              const int g = cg + kc, s = g % CNS;
-              if ((g % NPROD) != me) continue;
-              mbar_wait(conv_empty(s), (uint32_t)(((g / CNS) & 1) ^ 1));
-              mbar_arrive_expect_tx(conv_full(s), CCOLS * 128);
-              bulk_load(pipe_addr + s * CSTAGE + CA_TILE, wsrc + (size_t)kc * (CCOLS * 128), CCOLS * 128, conv_full(s));
+            // Step g's two k-chunks go to issuers 2 (g & 1) and 2 (g & 1) + 1: a thread spends ~160 cycles
+            // per tcgen05 instruction (MMA or commit), and a stage is only free again once its issuers
+            // are through, so the work of a step is split while every accumulator keeps a fixed set
+            // of k-chunks (deterministic sums).
+            for (int kp = 0; kp < KP_CONV; ++kp) {
+              const int g = cg + kp, s = g % CNS;
+              if ((me >> 1) != (kp & 1)) continue;
+              const int c = me & 1;
+              mbar_wait(conv_full(s), (uint32_t)((g / CNS) & 1));
+              tc_fence_after();
+              const uint32_t a_stage = sm_addr + s * CSTAGE;
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4)   // issuer 0's accumulator starts at the bias, the others at zero
+                umma_bf16(tmem + ACC_CONV + me * CCOLS, umma_desc_sw128(a_stage + c * CA_TILE + k4 * 32),
+                          umma_desc_sw128(a_stage + 2 * CA_TILE + c * (CCOLS * 128) + k4 * 32), idesc,
+                          (me == 0 || kp >= 2 || k4 > 0) ? 1u : 0u);
+              umma_commit(conv_empty(s));
             }
-            cg += KC_CONV;
+            umma_commit(conv_acc);
+            cg += KP_CONV;
+            // the conv stages alias the weight ring: nobody refills it before the last MMA has read them
+            mbar_wait(conv_acc, capar);
+            capar ^= 1u;
           }
           continue;
         }
+        if (me >= NPROD) continue;
         const uint32_t fill_bytes = (uint32_t)stg.rows * 128u * FKC;
         const int nfill = (int)stg.mtiles * (int)stg.kchunks / FKC;
         const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(stg.w) +
@@ -414,75 +443,6 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
           mbar_arrive_expect_tx(ring_full(slot), fill_bytes);
           bulk_load(sm_addr + slot * SLOT, wsrc + (size_t)f * fill_bytes, fill_bytes, ring_full(slot));
         }
-      }
-    }
-    __syncwarp();
-  }
-  // =============================================================== MMA thread
-  else if (warp >= 8 + NPROD) {
-    if (lane == 0) {
-      const int mj = warp - (8 + NPROD);   // issuer index: k-steps 2 mj, 2 mj + 1 of every k-chunk
-      int seq = 0, cg = 0;
-      uint32_t bpar = 0, gopar = 0;
-      for (int si = 0; si < C.n_stages; ++si) {
-        const R2Stage stg = C.stages[si];
-        if (stg.flags & R2F_CONV) {
-          mbar_wait(conv_go, gopar);
-          gopar ^= 1u;
-          const int nu = *reinterpret_cast<volatile int*>(ints_s + 4);
-          const int passes = (nu + 255) / 256;
-          constexpr uint32_t idesc = idesc_m64(CCOLS);
-          for (int pass = 0; pass < passes; ++pass) {
-            if (pass * 256 + ag * CROWS >= nu) continue;
-            for (int kc = 0; kc < KC_CONV; ++kc) {
-              const int g = cg + kc, s = g % CNS;
-              mbar_wait(conv_full(s), (uint32_t)((g / CNS) & 1));
-              tc_fence_after();
-              const uint32_t a_stage = pipe_addr + s * CSTAGE;
-#pragma unroll
-              for (int kk = 0; kk < 4 / NMMA; ++kk) {   // issuer 0's accumulator starts at the bias, the others at zero
-                const int k4 = mj * (4 / NMMA) + kk;
-                umma_bf16(tmem + ACC_CONV + mj * CCOLS, umma_desc_sw128(a_stage + k4 * 32),
-                          umma_desc_sw128(a_stage + CA_TILE + k4 * 32), idesc, (mj == 0 || kc > 0 || kk > 0) ? 1u : 0u);
-              }
-              umma_commit(conv_empty(s));
-            }
-            umma_commit(conv_acc);
-            cg += KC_CONV;
-          }
-          continue;
-        }
-        if (stg.flags & R2F_WAITB) {
-          mbar_wait(b_ready, bpar);
-          bpar ^= 1u;
-          tc_fence_after();
-        }
-        const bool n32 = (stg.flags & R2F_N32) != 0;
-        const uint32_t ncol = n32 ? 32u : 16u;
-        const uint32_t idesc = idesc_m64(ncol);
-        const uint32_t b_addr = stg.bsel == 2 ? pipe_addr + P_BOP2 : x_addr + X_BOP + stg.bsel * 16384;
-        const uint32_t bch = n32 ? BCH32 : BCH, sbo = n32 ? 1024u : 0u;
-        for (int mt = 0; mt < (int)stg.mtiles; ++mt)
-          for (int kg = 0; kg < (int)stg.kchunks / FKC; ++kg) {
-            const int slot = seq % NSLOT;
-            mbar_wait(ring_full(slot), (uint32_t)((seq / NSLOT) & 1));
-            tc_fence_after();
-            const uint64_t adesc = umma_desc_sw128(sm_addr + slot * SLOT);
-            const uint64_t bdesc = umma_desc_sw128_sbo(b_addr + kg * FKC * bch, sbo);
-            const uint32_t astep = ((uint32_t)stg.rows * 128u) >> 4, bstep = bch >> 4;
-            const uint32_t dcol = tmem + stg.acc_col + (mt * NMMA + mj) * ncol;
-#pragma unroll
-            for (int c = 0; c < FKC; ++c)
-#pragma unroll
-              for (int kk = 0; kk < 4 / NMMA; ++kk) {
-                const int k4 = mj * (4 / NMMA) + kk;
-                umma_bf16(dcol, adesc + (uint64_t)(c * astep + k4 * 2), bdesc + (uint64_t)(c * bstep + k4 * 2), idesc,
-                          (kg | c | kk) ? 1u : 0u);
-              }
-            umma_commit(ring_empty(slot));
-            ++seq;
-          }
-        if (stg.flags & R2F_COMMIT) umma_commit(acc_full);
       }
     }
     __syncwarp();
@@ -525,11 +485,46 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
       cl_par ^= 1u;
       mark(105);
     };
-    // B operand complete (as far as this thread is concerned) -> visible to the tensor core
-    auto b_done = [&]() {
+    // The B operand(s) of the next stage are written: make them visible to the tensor core, meet,
+    // and let lane 0 of warps 4..7 issue the stage (issuer j = warp - 4 takes k-step j of every
+    // k-chunk into accumulator j).  `nent` schedule entries share the operand wait (cls branch: 2).
+    int sidx = 0, wseq = 0;   // next schedule entry; ring fills consumed so far
+    auto b_done = [&](int nent) {
       fence_proxy_async();
       tc_fence_before();
-      mbar_arrive(b_ready);
+      bsync();
+      for (int e = 0; e < nent; ++e) {
+        const R2Stage stg = C.stages[sidx++];
+        const int nfill = (int)stg.mtiles * (int)stg.kchunks / FKC;
+        if (warp >= 4 && lane == 0) {
+          const int mj = warp - 4;
+          tc_fence_after();
+          const bool n32 = (stg.flags & R2F_N32) != 0;
+          const uint32_t ncol = n32 ? 32u : 16u;
+          const uint32_t idesc = idesc_m64(ncol);
+          const uint32_t b_addr = stg.bsel == 2 ? pipe_addr + P_BOP2 : x_addr + X_BOP + stg.bsel * 16384;
+          const uint32_t bch = n32 ? BCH32 : BCH, sbo = n32 ? 1024u : 0u;
+          int sq = wseq;
+          for (int mt = 0; mt < (int)stg.mtiles; ++mt)
+            for (int kg = 0; kg < (int)stg.kchunks / FKC; ++kg, ++sq) {
+              const int slot = sq % NSLOT;
+              mbar_wait(ring_full(slot), (uint32_t)((sq / NSLOT) & 1));
+              tc_fence_after();
+              const uint64_t adesc = umma_desc_sw128(sm_addr + slot * SLOT);
+              const uint64_t bdesc = umma_desc_sw128_sbo(b_addr + kg * FKC * bch, sbo);
+              const uint32_t astep = ((uint32_t)stg.rows * 128u) >> 4, bstep = bch >> 4;
+              const uint32_t dcol = tmem + stg.acc_col + (mt * NMMA + mj) * ncol;
+#pragma unroll
+              for (int c = 0; c < FKC; ++c)
+                umma_bf16(dcol, adesc + (uint64_t)(c * astep + mj * 2), bdesc + (uint64_t)(c * bstep + mj * 2), idesc,
+                          (kg | c) ? 1u : 0u);
+              umma_commit(ring_empty(slot));
+            }
+          if (stg.flags & R2F_COMMIT) umma_commit(acc_full);
+        }
+        __syncwarp();   // the issuer's warp mates wait here instead of spinning beside it
+        wseq += nfill;
+      }
     };
     auto wait_acc = [&]() {
       mbar_wait(acc_full, acc_par);
@@ -612,19 +607,24 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
           }
         }
       }
-      b_done();
+      b_done(L);
       wait_acc();
       const int rows = 3 * D / RES_CL;   // 48 features of [K | V | ego] per CTA
       if (warp < 4 && quad * 16 < rows) {
         const int f = quad * 16 + lane;
         const int gfeat = rank * rows + f;
         for (int l = 0; l < L; ++l) {
-          uint32_t u[32], u2[32];
-          tmem_ld32(tlane + ACC_LIN + 64 * l, u);
-          tmem_ld32(tlane + ACC_LIN + 64 * l + 32, u2);
+          uint32_t u[32];
+          tmem_ld32(tlane + ACC_LIN + 128 * l, u);
           tmem_ld_wait();
 #pragma unroll
-          for (int a = 0; a < 32; ++a) u[a] = __float_as_uint(__uint_as_float(u[a]) + __uint_as_float(u2[a]));
+          for (int j = 1; j < NMMA; ++j) {
+            uint32_t u2[32];
+            tmem_ld32(tlane + ACC_LIN + 128 * l + 32 * j, u2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int a = 0; a < 32; ++a) u[a] = __float_as_uint(__uint_as_float(u[a]) + __uint_as_float(u2[a]));
+          }
           if (lane < 16 && f < rows) {
             const float bias = __ldg(C.layer[l].b_kvego + gfeat);
             float* kvl = kvg + (size_t)l * Na * 2 * D;
@@ -660,7 +660,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
           const __nv_bfloat162 pr = __floats2bfloat162_rn(sv, cv);
           *reinterpret_cast<__nv_bfloat162*>(bop + sw_off(n, p * 64 + hf * 32 + 2 * m, BCH)) = pr;
         }
-        b_done();
+        b_done(1);
       }
       mark(10);
       // ============ plan_anchor_encoder (:459-462): Linear(512->256)+ReLU+LN, Linear(256->256)
@@ -686,7 +686,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
           bt_store8(bop_ptr(k + 1), warp, lane, v);
         }
         ++k;
-        b_done();
+        b_done(1);
       }
       mark(11);
       {
@@ -839,21 +839,27 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
           uint32_t* tile_u32 = reinterpret_cast<uint32_t*>(pipe);
           __nv_bfloat16* dst = C.bev_nhwc + (size_t)scene * HW * D;
           const int tpr = W / 32;
-          unsigned long long rest = todo;
-          int idx = 0;
-          while (rest) {
-            const int y = __ffsll((long long)rest) - 1;
-            rest &= rest - 1;
-            for (int xt = 0; xt < tpr; ++xt, ++idx) {
-              if (idx % RES_CL != rank) continue;
-              const int px0 = y * W + xt * 32;
-              if (call.bev_dtype == 0)
-                layout_item<float>(reinterpret_cast<const float*>(call.bev) + (size_t)scene * D * HW, dst, HW,
-                                   px0, tile_u32, tid);
-              else
-                layout_item<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(call.bev) + (size_t)scene * D * HW,
-                                           dst, HW, px0, tile_u32, tid);
-            }
+          // my items: (needed row, 32-pixel block) number rank, rank + 16, ...
+          auto item_px0 = [&](int it) {   // the it-th (row, block) of `todo`, or -1
+            const int row_i = it / tpr;
+            if (row_i >= __popcll(todo)) return -1;
+            unsigned long long r = todo;
+            for (int q = 0; q < row_i; ++q) r &= r - 1;
+            return (__ffsll((long long)r) - 1) * W + (it - row_i * tpr) * 32;
+          };
+          const bool f32 = call.bev_dtype == 0;
+          const float* src32 = reinterpret_cast<const float*>(call.bev) + (size_t)scene * D * HW;
+          const __nv_bfloat16* src16 = reinterpret_cast<const __nv_bfloat16*>(call.bev) + (size_t)scene * D * HW;
+          float4 va[8], vb[8];
+          int px_cur = item_px0(rank);
+          if (px_cur >= 0) { if (f32) layout_load<float>(src32, HW, px_cur, tid, va); else layout_load<__nv_bfloat16>(src16, HW, px_cur, tid, va); }
+          for (int it = rank; px_cur >= 0; it += RES_CL) {
+            const int px_next = item_px0(it + RES_CL);
+            if (px_next >= 0) { if (f32) layout_load<float>(src32, HW, px_next, tid, vb); else layout_load<__nv_bfloat16>(src16, HW, px_next, tid, vb); }
+            layout_store(dst, px_cur, tile_u32, tid, va);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) va[i] = vb[i];
+            px_cur = px_next;
           }
           csync();
           mark(21);
@@ -864,6 +870,9 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
         // CTA (ag, fg) = (64-row tile, 64-column group)
         {
           if (tid == 0) mbar_arrive(conv_go);
+          // the conv's weight tiles (8 KiB per k-chunk) are fetched by lane 0 of compute warp g % 8, so
+          // that eight threads share the bulk copies (a thread's copies run one at a time)
+          const uint8_t* wconv = reinterpret_cast<const uint8_t*>(C.stages[sidx++].w) + (size_t)fg * KC_CONV * (CCOLS * 128);
           const int passes = (nu + 255) / 256;
           const int a_c = tid >> 4, cqd = tid & 15;         // combine: anchors a_c, a_c + 16; 4-column group
           float4 sacc[2];
@@ -890,19 +899,28 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
               }
             }
             const uint32_t dst_base = rb * 128 + ((j ^ (rb & 7)) << 4);
-            for (int kc = 0; kc < KC_CONV; ++kc) {
-              const int g = cg + kc, s = g % CNS;
+            for (int kp = 0; kp < KP_CONV; ++kp) {
+              const int g = cg + kp, s = g % CNS;
               mbar_wait(conv_empty(s), (uint32_t)(((g / CNS) & 1) ^ 1));
-              const uint32_t a_dst = pipe_addr + s * CSTAGE + dst_base;
-              const int tap = kc >> 2;
-              const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
-              const int tapoff = (dy * W + dx) * D + (kc & 3) * 64;
-#pragma unroll
-              for (int i = 0; i < 2; ++i) {
-                const bool ok = (vmask[i] >> tap) & 1u;
-                const int off = ok ? rowoff[i] + tapoff : 0;
-                cp_async16(a_dst + i * 4096, bevn + off, ok ? 16u : 0u);
+              if (lane == 0 && warp == (g & 7)) {   // both weight tiles of the step are contiguous in the packed image
+                mbar_arrive_expect_tx(conv_full(s), 2 * CCOLS * 128);
+                bulk_load(sm_addr + s * CSTAGE + 2 * CA_TILE, wconv + (size_t)kp * (2 * CCOLS * 128), 2 * CCOLS * 128, conv_full(s));
               }
+#pragma unroll
+              for (int c = 0; c < 2; ++c) {
+                const int kc = kp * 2 + c;
+                const uint32_t a_dst = sm_addr + s * CSTAGE + c * CA_TILE + dst_base;
+                const int tap = kc >> 2;
+                const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+                const int tapoff = (dy * W + dx) * D + (kc & 3) * 64;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                  const bool ok = (vmask[i] >> tap) & 1u;
+                  const int off = ok ? rowoff[i] + tapoff : 0;
+                  cp_async16(a_dst + i * 4096, bevn + off, ok ? 16u : 0u);
+                }
+              }
+              const int kc = kp;   // (bias preload below runs on the first step)
               if (kc == 0 && warp < 4) {   // accumulators start at the conv bias
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
@@ -919,7 +937,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
               }
               cp_async_mbar_arrive_noinc(conv_full(s));
             }
-            cg += KC_CONV;
+            cg += KP_CONV;
             mark(125);
             mbar_wait(conv_acc, conv_par);
             conv_par ^= 1u;
@@ -929,12 +947,17 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
               float* vrow = Vs + (size_t)(quad * 16 + (lane & 15)) * VS_LD;
 #pragma unroll
               for (int hh = 0; hh < 2; ++hh) {
-                uint32_t u0[32], u1[32];
+                uint32_t u0[32];
                 tmem_ld32(tlane + ACC_CONV + hh * 32, u0);
-                tmem_ld32(tlane + ACC_CONV + CCOLS + hh * 32, u1);
                 tmem_ld_wait();
 #pragma unroll
-                for (int q = 0; q < 32; ++q) u0[q] = __float_as_uint(__uint_as_float(u0[q]) + __uint_as_float(u1[q]));
+                for (int j = 1; j < NMMA; ++j) {
+                  uint32_t u1[32];
+                  tmem_ld32(tlane + ACC_CONV + j * CCOLS + hh * 32, u1);
+                  tmem_ld_wait();
+#pragma unroll
+                  for (int q = 0; q < 32; ++q) u0[q] = __float_as_uint(__uint_as_float(u0[q]) + __uint_as_float(u1[q]));
+                }
                 if (lane < 16) {
 #pragma unroll
                   for (int q = 0; q < 8; ++q)
@@ -1018,7 +1041,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
           }
           bsync();   // the partials live where the B operand goes
           if (warp < n_own) bt_store8(bop_ptr(k), warp, lane, sv);
-          b_done();
+          b_done(1);
           const int f = fg * 64 + quad * 16 + lane;
           const float bias = (warp < 4 && lane < 16) ? __ldg(LC.b_bev_out + f) : 0.f;
           wait_acc();
@@ -1040,7 +1063,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
             bt_store8(bop_ptr(k + 1), warp, lane, v);
           }
           ++k;
-          b_done();
+          b_done(1);
         }
         mark(23);
         // ============ cross_agent_attention (:316-321,355-357): q projection of my two heads,
@@ -1088,7 +1111,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
           xchg_send(k, off_x + X_BOP + ((k + 1) & 1) * 16384 + fg * BCH, BCH, 0, 0, true);
           xchg_wait(k);
           ++k;
-          b_done();
+          b_done(1);
         }
         mark(24);
         // ============ attention out_proj + residual, norm1, + ego, norm2   (:355-364)
@@ -1122,7 +1145,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
             bt_store8(bop_ptr(k + 1), warp, lane, v);
           }
           ++k;
-          b_done();
+          b_done(1);
         }
         mark(25);
         // ============ FFN up: my F/4 hidden features, h = relu(x2.W1 + b), straight into the
@@ -1140,7 +1163,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
             for (int t = 0; t < 4; ++t) {
               if (t < ntl) {
                 float v[8];
-                acc8(ACC_LIN + t * 32, v);
+                acc8(ACC_LIN + t * 64, v);
                 const int f = fg * fq + t * 64 + quad * 16 + lane;
 #pragma unroll
                 for (int n = 0; n < NROW; ++n)
@@ -1151,7 +1174,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
           }
           xchg_wait(k);
           ++k;
-          b_done();
+          b_done(1);
         }
         mark(26);
         // ============ FFN down, norm3, time FiLM   (:368-373)
@@ -1183,7 +1206,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
             bt_store8(bop_ptr(k + 1), warp, lane, v);
           }
           ++k;
-          b_done();
+          b_done(want_cls ? 2 : 1);
         }
         mark(27);
         // ============ reg / cls hidden 1   (:221-231)
@@ -1223,7 +1246,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
             bt_store8(pipe + P_BOP2, warp, lane, v);
           }
           ++k;
-          b_done();
+          b_done(want_cls ? 2 : 1);
         }
         mark(28);
         // ============ reg / cls hidden 2, regression head (256 -> 3P, fp32), cls score
