@@ -385,7 +385,9 @@ def run_ours(args):
         lat = {"p50_us": dts[len(dts) // 2], "p90_us": dts[int(len(dts) * 0.9)],
                "wall_p50_us": sorted(wall)[len(wall) // 2], "iters": len(dts),
                "precision": precision, "launches": head.last_launch_count(),
-               "engine": "small-batch engine (kernels_lat.cu), stream launches"}
+               "engine": ("group-resident engine (kernels_res2.cu): the whole forward is one launch on a "
+                          "16-CTA cluster" if head.last_launch_count() == 1
+                          else "small-batch engine (kernels_lat.cu), stream launches")}
         # the same call captured once into a CUDA graph and replayed (no host launch gaps)
         try:
             side = torch.cuda.Stream(device=dev)

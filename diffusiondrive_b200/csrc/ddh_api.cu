@@ -335,6 +335,10 @@ int ensure_ws(ddh_handle* h, int B) {
   cudaDeviceSynchronize();
   free_all(h->owned_ws);
   h->cap_B = 0;
+  // the engines test these pointers to decide what to write: none may survive a change of precision
+  h->emb16 = h->e1_16 = h->q0_16 = h->agents16 = h->ego16 = h->s16 = h->x1_16 = h->o16 = h->x2_16 = h->h16 =
+      h->x3_16 = h->c1_16 = h->r1_16 = nullptr;
+  h->emb32 = h->e1_32 = h->s32 = h->o32 = h->x2_32 = h->h32 = h->x3_32 = h->c1_32 = h->r1_32 = h->V = nullptr;
   const ddh_shape& s = h->shp;
   const size_t M = (size_t)B * s.num_anchors, F = s.d_ffn;
   const int L = s.num_layers;
@@ -1371,7 +1375,6 @@ int ddh_forward(ddh_handle* h, const float* ego, const float* agents, const void
   const ddh_shape& s = h->shp;
   h->ev_used = 0;
   h->ev_spans.clear();
-  CU_TRY(h, cudaMemsetAsync(h->conv_rows, 0, (size_t)s.num_layers * s.num_steps * 4, st));
 
   // <= RES_MAX_B scenes: the whole forward as ONE launch on one 16-CTA cluster per scene,
   // activations resident on the SM that owns the anchor (kernels_res2.cu)
@@ -1404,6 +1407,7 @@ int ddh_forward(ddh_handle* h, const float* ego, const float* agents, const void
     CU_TRY(h, cudaGetLastError());
     return DDH_OK;
   }
+  CU_TRY(h, cudaMemsetAsync(h->conv_rows, 0, (size_t)s.num_layers * s.num_steps * 4, st));
   if (h->res_ok && !h->profiling && h->precision == DDH_PREC_BF16 && B <= RES_MAX_B) {
     ResCall call;
     call.ego = ego; call.agents = agents; call.bev = bev; call.bev_dtype = bev_dtype == DDH_BF16 ? 1 : 0;

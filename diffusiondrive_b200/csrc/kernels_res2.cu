@@ -1,27 +1,45 @@
-// Anchor-resident engine of the ddh planning head (sm_100a): the whole
+// Group-resident engine of the ddh planning head (sm_100a): the whole
 // TrajectoryHead.forward_test (transfuser_model_v2.py:578-641) of one scene runs in ONE kernel on
-// ONE 16-CTA thread-block cluster, and -- unlike the first resident engine (kernels_res.cu), which
-// split every Linear over its output features and exchanged activations through L2 after every
-// stage -- the decoder chain of an anchor never leaves the SM that owns it.
+// ONE 16-CTA thread-block cluster, so that a batch-1 forward costs one launch and the decoder
+// chain never touches global memory.
 //
-// Work split.  CTA `rank` owns anchors {rank, rank + 16} (A <= 32).  Every Linear of the chain is
-//     out^T[f, n] = sum_k W[f, k] * x[n, k]       (tcgen05.mma, M = 128 weight rows, N = 16)
-// with the FULL weight matrix streamed through a shared-memory ring by a dedicated TMA thread that
-// free-runs ahead of the math (weights do not depend on data) and the owner's <= 2 activation
-// rows as the B operand, rebuilt in shared memory by the epilogue of the previous stage: one
-// thread per output feature reads its accumulator from TMEM, applies bias / ReLU / residual /
-// LayerNorm (block reductions) / FiLM and writes the bf16 operand of the next stage.  No global
-// memory, no cluster barrier and no exchange inside the chain.  What does cross CTAs:
-//   * the sampling plan needs every anchor's points and attention weights: owners push them into
-//     all 16 CTAs' shared memory (st.shared::cluster), every CTA then builds the identical plan;
-//   * the on-demand value_proj conv (modules/blocks.py:68-76,114) runs as (128-row tile) x
-//     (32-column group) tcgen05 tiles, one per CTA, gathered from the NHWC bf16 map with
-//     cp.async; each CTA pushes its [A x 32] slice of the sampled features to the anchor owners;
-//   * the step-invariant agent K|V and ego projections are computed once, feature-split, and
-//     exchanged through L2; each CTA stages K|V of a layer in shared memory under the conv;
+// Work split.  The cluster is a 4 x 4 grid: CTA (ag, fg) = (rank / 4, rank % 4) belongs to anchor
+// group ag (anchors [ag*NAG, +NAG), NAG = ceil(A/4) <= 7) and owns feature slice fg of it.  Every
+// Linear of the chain is, per CTA,
+//     out^T[f, n] = sum_k W[f, k] * x[n, k]       (tcgen05.mma, M = 64 weight rows, N = 16)
+// with the CTA's 64 weight rows (F/4 for the FFN up-projection) as the A operand -- pre-swizzled
+// shared-memory images (pack_sw128_kernel) fetched 32 KiB at a time by bulk copies into a two-slot
+// ring, by two free-running threads, ahead of the math -- and the group's <= 8 activation rows as
+// the B operand (rows 8..15 of the N = 16 operand alias rows 0..7 through a zero row-group
+// stride).  Epilogue: one thread per output feature reads TMEM, applies bias / ReLU / residual
+// and writes the CTA's slice, which the bulk-copy engine pushes into the three peers of the group
+// (cp.async.bulk shared::cta -> shared::cluster, completion bytes counted by the peers' exchange
+// barrier); every CTA then applies the row operations (LayerNorm, +ego, FiLM) to the full rows,
+// one warp per anchor, and writes the bf16 operand of the next stage.  Stages whose consumer needs
+// no row operation (FFN hidden, reg hidden, attention output) push bf16 straight into the peers'
+// next operand.  Each CTA runs the attention of two heads (its q slice) on K|V staged in shared
+// memory.  What crosses groups:
+//   * the sampling plan needs every anchor's points and attention weights: they are pushed into
+//     all 16 CTAs (st.shared::cluster), every CTA then builds the identical plan (bitmap + popcount
+//     compaction, no atomics on hot words);
+//   * the on-demand value_proj conv (modules/blocks.py:68-76,114) runs as (64 unique pixels) x
+//     (64 output columns) tcgen05 tiles, one per CTA, gathered from the NHWC bf16 map with
+//     cp.async in steps of two k-chunks over a four-stage pipeline that borrows the idle weight
+//     ring; each CTA pushes its [A x 64] slice of the sampled features to the anchors' groups;
+//   * the step-invariant agent K|V and ego projections are computed once, 16-way feature-split,
+//     and exchanged through L2;
 //   * NCHW callers: the BEV rows a conv call reads are converted on demand, dealt over the CTAs.
 // Cluster-wide synchronisation is an mbarrier per CTA that one thread of every CTA arrives on
-// remotely (release.cluster / acquire.cluster), ~10 times per forward.
+// remotely (release.cluster), ~13 times per forward.
+//
+// Three measured properties of the part shape this design (tools/ubench_*.cu, profiles/):
+//   * a thread's bulk / TMA copies run one at a time, ~750 cycles each whatever their size
+//     -> large (32 KiB) requests from several issuing threads;
+//   * a tcgen05.mma or tcgen05.commit costs its issuing thread ~160 cycles whatever its shape,
+//     and threads of different warps issue concurrently -> four issuers with private accumulators
+//     (fixed k-step assignment keeps sums deterministic);
+//   * handing a pipeline stage over costs ~300-400 cycles whatever it carries -> two k-chunks per
+//     conv step.
 //
 // Numerics are those of the bf16 tensor engine (kernels_tc.cu): bf16 operands, fp32 accumulate,
 // fp32 LayerNorm / softmax / embeddings / residuals / regression tail.
@@ -174,23 +192,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t saddr, uint32_t
   d |= (uint64_t)2 << 61;
   return d;
 }
-__device__ __forceinline__ void tmem_ld2(uint32_t taddr, float (&v)[2]) {
-  uint32_t a, b;
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-  v[0] = __uint_as_float(a);
-  v[1] = __uint_as_float(b);
-}
-
 // byte offset of element (row n, column k) of a K-major, 128-byte-swizzled bf16 operand whose
 // 64-wide k-chunks are `chunk_bytes` apart
 __device__ __forceinline__ uint32_t sw_off(int n, int k, int chunk_bytes) {
   return (uint32_t)((k >> 6) * chunk_bytes + n * 128 + ((((k & 63) >> 3) ^ (n & 7)) << 4) + (k & 7) * 2);
 }
-__device__ __forceinline__ void bop_store(uint8_t* bop, int n, int k, float v) {
-  *reinterpret_cast<__nv_bfloat16*>(bop + sw_off(n, k, BCH)) = __float2bfloat16_rn(v);
-}
-
 template <typename TI>
 __device__ __forceinline__ float4 ld4_bev(const TI* p);
 template <>
@@ -249,10 +255,6 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(u[i]);
 }
-__device__ __forceinline__ void st_cluster_b16(uint32_t raddr, __nv_bfloat16 v) {
-  asm volatile("st.shared::cluster.b16 [%0], %1;" ::"r"(raddr), "h"(*reinterpret_cast<unsigned short*>(&v)) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 // my shared memory -> a peer CTA's shared memory; the peer's mbarrier receives the byte count
 __device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes,
                                                   uint32_t mbar_cluster) {
@@ -476,12 +478,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
       mark(104);
       bsync();
       if (tid < RES_CL) mbar_arrive_remote_release(mapa(cl_bar, (uint32_t)tid));
-      // CTA-scope acquire on purpose: a cluster-scope acquire makes the SM drop its L1 (CCTL.IVALL),
-      // after which every register-spill reload misses to L2 (~5 k cycles per barrier, measured).
-      // What crosses CTAs here is either shared memory (not cached) or global memory that the
-      // consumers read with L1-bypassing loads (__ldcg / cp.async.cg); the producers' release is
-      // cluster-scoped.
-      mbar_wait(cl_bar, cl_par);
+      mbar_wait_acq_cluster(cl_bar, cl_par);
       cl_par ^= 1u;
       mark(105);
     };
