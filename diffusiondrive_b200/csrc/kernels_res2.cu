@@ -745,24 +745,31 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
         const bool last_layer = (l == L - 1);
         const bool want_cls = last_layer && last_step;
         const bool do_ddim = last_layer && !last_step;
-        // ============ sampling plan (blocks.py:98-125), identically in every CTA
+        // ============ sampling plan (blocks.py:98-125), identically in every CTA: bitmap of the
+        // in-bounds bilinear corners, prefix popcount over its words (pixel order == memory order of
+        // the NHWC map), and every corner looks its slot up; the unique-pixel list is written from the
+        // corner side (duplicates store the same value), so nobody walks the bitmap bit by bit
         int nu;
         unsigned long long todo;
         {
           const int nwords = HW / 32;
           if (tid < nwords) bm_s[tid] = 0u;
           if (tid < CCOLS) cbias_s[tid] = __ldg(LC.b_conv + fg * CCOLS + tid);
+          Corners c;
+          float a_w = 0.f;
+          if (tid < AP) {
+            c = corners_of(pts_s[tid * 2 + 0], pts_s[tid * 2 + 1], H, W, C.oc);
+            a_w = aw_s[l * AP + tid];
+          }
           mark(110);
           bsync();
           if (tid < AP) {
-            const Corners c = corners_of(pts_s[tid * 2 + 0], pts_s[tid * 2 + 1], H, W, C.oc);
 #pragma unroll
             for (int q = 0; q < 4; ++q)
               if (c.pix[q] >= 0) atomicOr(bm_s + (c.pix[q] >> 5), 1u << (c.pix[q] & 31));
           }
           bsync();
           mark(111);
-          // ordered compaction (pixel order == memory order of the NHWC map)
           if (tid < 128) {
             const unsigned int bits = tid < nwords ? bm_s[tid] : 0u;
             const int cnt = __popc(bits);
@@ -773,35 +780,19 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
               if (lane >= o) incl += t;
             }
             if (lane == 31) ints_s[warp] = incl;
-            mark(115);
+            // BEV rows (with their 3x3 halo) this warp's words touch: one shared-memory word per warp
+            // (a 64-bit atomic per thread on one word costs ~4 k cycles)
+            const int y = (tid * 32) / W;
+            const unsigned long long m = bits ? ((y > 0) ? (7ull << (y - 1)) : 3ull) : 0ull;
+            const unsigned int lo = __reduce_or_sync(0xffffffffu, (unsigned int)m);
+            const unsigned int hi = __reduce_or_sync(0xffffffffu, (unsigned int)(m >> 32));
+            if (lane == 0) need_s[2 + warp] = ((unsigned long long)hi << 32) | lo;
             named_bar_sync(3, 128);
             int base = incl - cnt;
             for (int w = 0; w < warp; ++w) base += ints_s[w];
             if (tid == 127) ints_s[4] = base + cnt;
             if (tid < nwords) pre_s[tid] = base;
-            mark(116);
-            if (bits) {
-              const int y = (tid * 32) / W, x0 = tid * 32 - y * W;
-              unsigned int rest = bits;
-              while (rest) {
-                const int b = __ffs((int)rest) - 1;
-                rest &= rest - 1;
-                upix_s[base++] = (y << 16) | (x0 + b);
-              }
-            }
-            mark(117);
-            // BEV rows (with their 3x3 halo) this warp's words touch: one shared-memory word per warp
-            // instead of a contended 64-bit atomic per thread
-            {
-              const int y = (tid * 32) / W;
-              const unsigned long long m = bits ? ((y > 0) ? (7ull << (y - 1)) : 3ull) : 0ull;
-              const unsigned int lo = __reduce_or_sync(0xffffffffu, (unsigned int)m);
-              const unsigned int hi = __reduce_or_sync(0xffffffffu, (unsigned int)(m >> 32));
-              if (lane == 0) need_s[2 + warp] = ((unsigned long long)hi << 32) | lo;
-            }
-            mark(118);
           }
-          if (call.dbg && scene == 0 && rank == 0 && lane == 0 && l == 0 && si == 0) call.dbg[900 + warp] = clock64() & 0xFFFFFFFFFFFFll;
           bsync();
           mark(112);
           nu = ints_s[4];
@@ -809,20 +800,18 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
           const unsigned long long need_all = (H >= 64) ? need_any : (need_any & ((1ull << H) - 1ull));
           const unsigned long long done_rows = need_s[1];
           todo = call.bev_nhwc_bf16 ? 0ull : (need_all & ~done_rows);
-          mark(113);
-          if (tid < AP) {   // corners recomputed: keeping them live across the barriers costs spills
-            const Corners c2 = corners_of(pts_s[tid * 2 + 0], pts_s[tid * 2 + 1], H, W, C.oc);
-            const float a_w = aw_s[l * AP + tid];
-            mark(114);
+          if (tid < AP) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               EntPair ep;
               ep.slot = -1;
               ep.w = 0.f;
-              if (c2.pix[q] >= 0) {
-                const int wd = c2.pix[q] >> 5;
-                ep.slot = pre_s[wd] + __popc(bm_s[wd] & ((1u << (c2.pix[q] & 31)) - 1u));
-                ep.w = c2.w[q] * a_w;
+              if (c.pix[q] >= 0) {
+                const int wd = c.pix[q] >> 5;
+                ep.slot = pre_s[wd] + __popc(bm_s[wd] & ((1u << (c.pix[q] & 31)) - 1u));
+                ep.w = c.w[q] * a_w;
+                const int y = c.pix[q] / W;
+                upix_s[ep.slot] = (y << 16) | (c.pix[q] - y * W);
               }
               ent[tid * 4 + q] = ep;
             }
@@ -1287,17 +1276,23 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
             const int n = warp, a = a0 + n;
             float x[8];
             act_load8(act_ptr(k), n, lane, x);
-            float mine = 0.f;
+            float dots[6];
 #pragma unroll
             for (int ci = 0; ci < 6; ++ci) {
+              dots[ci] = 0.f;
               if (ci < nout) {
-                float s = 0.f;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) s = fmaf(x[i], w4[ci][i], s);
-                s = warp_sum(s);
-                if (lane == ci) mine = s;
+                for (int i = 0; i < 8; ++i) dots[ci] = fmaf(x[i], w4[ci][i], dots[ci]);
               }
             }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)   // the six reductions share the shuffle rounds
+#pragma unroll
+              for (int ci = 0; ci < 6; ++ci) dots[ci] += __shfl_xor_sync(0xffffffffu, dots[ci], o);
+            float mine = 0.f;
+#pragma unroll
+            for (int ci = 0; ci < 6; ++ci)
+              if (lane == ci) mine = dots[ci];
             float score = 0.f;
             if (want_cls) {   // scores = LN(c2).w6 + b6   (:221-224)
               float c2[8], w6[8], g5[8], b5[8];
