@@ -266,18 +266,24 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// LayerNorm of a row held by one warp (8 values per lane).  Sum and sum of squares share the
+// five shuffle rounds (the row operation sits on the critical path of every stage); the variance
+// E[x^2] - mean^2 is formed in fp32 from O(1) activations.
 __device__ __forceinline__ void ln_row_reg(float (&v)[8], const float (&g)[8], const float (&b)[8]) {
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) s += v[i];
-  const float mean = warp_sum(s) * (1.0f / D);
-  float q = 0.f;
+  float s = 0.f, q = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const float d = v[i] - mean;
-    q += d * d;
+    s += v[i];
+    q = fmaf(v[i], v[i], q);
   }
-  const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / D) + LN_EPS);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  const float mean = s * (1.0f / D);
+  const float var = fmaxf(q * (1.0f / D) - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + LN_EPS);
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = (v[i] - mean) * rstd * g[i] + b[i];
 }
@@ -651,9 +657,12 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
           const int n = i / (P * 32), r = i - n * P * 32;
           const int p = r >> 5, jj = r & 31, hf = jj >> 4, m = jj & 15;   // pair m of half hf of pose p
           const float v = hf ? pts_s[((a0 + n) * P + p) * 2 + 0] : pts_s[((a0 + n) * P + p) * 2 + 1];   // (pos_y | pos_x)
+          // |arg| <= ~400 rad: reduce to [-pi, pi] in fp32 (error ~3e-5 rad, two orders below the bf16
+          // rounding of the result) and use the fast intrinsics
           const float arg = __fdiv_rn(__fmul_rn(v, two_pi), __ldg(C.dim_t + 2 * m));
+          const float red = fmaf(-two_pi, rintf(arg * 0.15915494309189535f), arg);
           float sv, cv;
-          sincosf(arg, &sv, &cv);
+          __sincosf(red, &sv, &cv);
           const __nv_bfloat162 pr = __floats2bfloat162_rn(sv, cv);
           *reinterpret_cast<__nv_bfloat162*>(bop + sw_off(n, p * 64 + hf * 32 + 2 * m, BCH)) = pr;
         }
@@ -713,15 +722,21 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
           // computes layer fg and hands it to the whole cluster
           if (fg < L) {
             const int l = fg;
-            float dot = 0.f;
+            float dots[8];
 #pragma unroll
             for (int p = 0; p < 8; ++p) {
-              float s = 0.f;
+              dots[p] = 0.f;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) s = fmaf(v[i], wa[p][i], s);
-              s = warp_sum(s);
-              if (lane == p) dot = s;
+              for (int i = 0; i < 8; ++i) dots[p] = fmaf(v[i], wa[p][i], dots[p]);
             }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)   // the eight reductions share the shuffle rounds
+#pragma unroll
+              for (int p = 0; p < 8; ++p) dots[p] += __shfl_xor_sync(0xffffffffu, dots[p], o);
+            float dot = 0.f;
+#pragma unroll
+            for (int p = 0; p < 8; ++p)
+              if (lane == p) dot = dots[p];
             const float lg = (lane < P) ? dot + __ldg(C.layer[l].attw_b + lane) : -INFINITY;
             float mx = lg;
 #pragma unroll

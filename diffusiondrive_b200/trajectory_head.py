@@ -315,9 +315,12 @@ class TrajectoryHead(nn.Module):
         bev = bev_feature.contiguous()
         noise = noise.to(torch.float32).contiguous()
         out_dev = in_dev
-        traj = torch.empty((B, P, 3), dtype=torch.float32, device=out_dev)
-        modes = torch.empty((B, A, P, 3), dtype=torch.float32, device=out_dev)
-        scores = torch.empty((B, A), dtype=torch.float32, device=out_dev)
+        # one allocation for the three float outputs (allocator calls sit on the batch-1 latency path)
+        n_t, n_m, n_s = B * P * 3, B * A * P * 3, B * A
+        flat = torch.empty((n_t + n_m + n_s,), dtype=torch.float32, device=out_dev)
+        traj = flat[:n_t].view(B, P, 3)
+        modes = flat[n_t:n_t + n_m].view(B, A, P, 3)
+        scores = flat[n_t + n_m:].view(B, A)
         idx = torch.empty((B,), dtype=torch.int64, device=out_dev)
 
         with torch.cuda.device(dev):
