@@ -626,7 +626,7 @@ int build_res2(ddh_handle* h, cudaStream_t st) {
   }
   // the schedule, in the program order of the compute warps (kernels_res2.cu); chain stage k
   // reads B operand buffer k & 1
-  constexpr unsigned short ACC_LIN = 256;   // linear tile t, issuer j at ACC_LIN + 64 t + 16 j; cls branch at ACC_LIN + 64
+  constexpr unsigned short ACC_LIN = 256;   // linear tile t, issuer j at ACC_LIN + 32 t + 8 j; cls branch at ACC_LIN + 128
   int n = 0, k = 0;
   auto stage = [&](const void* m, int rows, int mtiles, int K, int acc_col, int flags, int bsel) {
     R2Stage& g = C.stages[n++];
@@ -655,9 +655,9 @@ int build_res2(ddh_handle* h, cudaStream_t st) {
         stage(lw[l].reg2, 64, 1, D, ACC_LIN, both, k++ & 1);
       } else {
         stage(lw[l].reg0, 64, 1, D, ACC_LIN, R2F_WAITB, k & 1);
-        stage(lw[l].cls0, 64, 1, D, ACC_LIN + 64, R2F_COMMIT, k++ & 1);
+        stage(lw[l].cls0, 64, 1, D, ACC_LIN + 128, R2F_COMMIT, k++ & 1);
         stage(lw[l].reg2, 64, 1, D, ACC_LIN, R2F_WAITB, k++ & 1);
-        stage(lw[l].cls3, 64, 1, D, ACC_LIN + 64, R2F_COMMIT, 2);
+        stage(lw[l].cls3, 64, 1, D, ACC_LIN + 128, R2F_COMMIT, 2);
       }
     }
   }

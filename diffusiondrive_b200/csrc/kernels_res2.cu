@@ -85,7 +85,8 @@ constexpr int BCH32 = 4096;                  // hoisted stage: 32 rows x 128 B
 // and the epilogues add the NMMA accumulators.  The linear stages are issued by lane 0 of compute
 // warps 4..7 (idle while the tensor core works), the conv by the four engine warps.
 constexpr int NMMA = 4;
-constexpr uint32_t ACC_CONV = 0, ACC_LIN = 256;   // TMEM columns: conv 4 x 64; linear tile t, issuer j at ACC_LIN + 64 t + 16 j
+constexpr uint32_t ACC_CONV = 0, ACC_LIN = 256;   // TMEM columns: conv 4 x 64; linear tile t, issuer j at ACC_LIN + 32 t + 8 j
+                                                  // (N = 8: one 32-column TMEM load fetches a tile's four accumulators)
 constexpr int TMEM_COLS = 512;
 constexpr int VS_LD = CCOLS + 4;
 constexpr int KS_LD = 64 + 4;                // padded K rows (2 heads): conflict-free 128-bit reads, lane = agent
@@ -245,17 +246,6 @@ __device__ __forceinline__ void layout_store(__nv_bfloat16* __restrict__ dst, in
   }
 }
 
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
-  uint32_t u[8];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
-               : "r"(taddr)
-               : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(u[i]);
-}
-// my shared memory -> a peer CTA's shared memory; the peer's mbarrier receives the byte count
 __device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes,
                                                   uint32_t mbar_cluster) {
   asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -321,8 +311,12 @@ __device__ __forceinline__ void store8(float* p, int lane, const float (&v)[8]) 
   *reinterpret_cast<float4*>(p + 128 + lane * 4) = make_float4(v[4], v[5], v[6], v[7]);
 }
 
+// DBG: debug instantiation (clock64 timeline + taps, ResCall::dbg set); the production one carries none of it
+template <bool DBG>
 __global__ void __launch_bounds__(NT, 1)
-res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
+res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call_in) {
+  ResCall call = call_in;
+  if (!DBG) call.dbg = nullptr;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
@@ -474,7 +468,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
     float* egog = C.egov + (size_t)scene * L * D;
 
     auto mark = [&](int label) {
-      if (call.dbg && scene == 0 && rank == 0 && tid == 0 && dbg_i < 900)
+      if (DBG && call.dbg && scene == 0 && rank == 0 && tid == 0 && dbg_i < 900)
         call.dbg[dbg_i++] = ((long long)label << 48) | (clock64() & 0xFFFFFFFFFFFFll);
     };
     auto bsync = [&]() { named_bar_sync(1, NCT); };
@@ -503,7 +497,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
           const int mj = warp - 4;
           tc_fence_after();
           const bool n32 = (stg.flags & R2F_N32) != 0;
-          const uint32_t ncol = n32 ? 32u : 16u;
+          const uint32_t ncol = n32 ? 32u : 8u;
           const uint32_t idesc = idesc_m64(ncol);
           const uint32_t b_addr = stg.bsel == 2 ? pipe_addr + P_BOP2 : x_addr + X_BOP + stg.bsel * 16384;
           const uint32_t bch = n32 ? BCH32 : BCH, sbo = n32 ? 1024u : 0u;
@@ -561,16 +555,15 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
       xbits ^= 1u << (kk & 1);
     };
     // this thread's feature column (warps 0-1: local feature fl of tile mt) of the group's rows
-    auto acc8 = [&](uint32_t acc_col, float (&v)[8]) {   // sum of the issuers' accumulators, fixed order
-      tmem_ld8(tlane + acc_col, v);
+    auto acc8 = [&](uint32_t acc_col, float (&v)[8]) {   // sum of the four issuers' accumulators, fixed order
+      uint32_t u[32];
+      tmem_ld32(tlane + acc_col, u);
+      tmem_ld_wait();
 #pragma unroll
-      for (int j = 1; j < NMMA; ++j) {
-        float w[8];
-        tmem_ld8(tlane + acc_col + j * 16, w);
-#pragma unroll
-        for (int n = 0; n < 8; ++n) v[n] += w[n];
-      }
+      for (int n = 0; n < 8; ++n)
+        v[n] = ((__uint_as_float(u[n]) + __uint_as_float(u[8 + n])) + __uint_as_float(u[16 + n])) + __uint_as_float(u[24 + n]);
     };
+    static_assert(NMMA == 4, "acc8 adds four 8-column accumulators");
     const uint32_t off_x = (uint32_t)(RING + PIPE);   // offset of X from the shared-memory base
 
     // ---- img = sqrt(ac) * norm_odo(anchors) + sqrt(1-ac) * noise   (:591-597); every CTA derives
@@ -1164,7 +1157,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
             for (int t = 0; t < 4; ++t) {
               if (t < ntl) {
                 float v[8];
-                acc8(ACC_LIN + t * 64, v);
+                acc8(ACC_LIN + t * 32, v);
                 const int f = fg * fq + t * 64 + quad * 16 + lane;
 #pragma unroll
                 for (int n = 0; n < NROW; ++n)
@@ -1230,7 +1223,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
             for (int n = 0; n < NROW; ++n)
               if (lane < 16) *reinterpret_cast<__nv_bfloat16*>(bnext + sw_off(n, f, BCH)) = __float2bfloat16_rn(fmaxf(v[n] + bias_r, 0.f));
             if (want_cls) {
-              acc8(ACC_LIN + 64, v);
+              acc8(ACC_LIN + 128, v);
               float* sl = act2 + fg * (NROW * 64) + quad * 16 + lane;
 #pragma unroll
               for (int n = 0; n < NROW; ++n)
@@ -1276,7 +1269,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call) {
             for (int n = 0; n < NROW; ++n)
               if (lane < 16) sl[n * 64] = fmaxf(v[n] + bias_r, 0.f);
             if (want_cls) {
-              acc8(ACC_LIN + 64, v);
+              acc8(ACC_LIN + 128, v);
               float* s2 = act2 + fg * (NROW * 64) + quad * 16 + lane;
 #pragma unroll
               for (int n = 0; n < NROW; ++n)
@@ -1425,16 +1418,19 @@ static void res2_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int B, 
 
 int res2_engine_init() {
   if (g_res2_ready) return 0;
-  cudaError_t e = cudaFuncSetAttribute(res2_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(res2_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(res2_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) { cudaGetLastError(); return 1; }
-  e = cudaFuncSetAttribute(res2_forward_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  e = cudaFuncSetAttribute(res2_forward_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(res2_forward_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   if (e != cudaSuccess) { cudaGetLastError(); return 2; }
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
   res2_cfg(cfg, attr, 1, nullptr);
   int nclusters = 0;
-  e = cudaOccupancyMaxActiveClusters(&nclusters, res2_forward_kernel, &cfg);
+  e = cudaOccupancyMaxActiveClusters(&nclusters, res2_forward_kernel<false>, &cfg);
   if (e != cudaSuccess || nclusters < 1) {
     if (getenv("DDH_VERBOSE")) fprintf(stderr, "ddh: res2 occupancy query: %s, clusters %d\n", cudaGetErrorString(e), nclusters);
     cudaGetLastError();
@@ -1448,7 +1444,8 @@ int launch_res2_forward(const R2Consts* consts_dev, const ResCall& call, int B, 
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
   res2_cfg(cfg, attr, B, st);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, res2_forward_kernel, consts_dev, call);
+  cudaError_t e = call.dbg ? cudaLaunchKernelEx(&cfg, res2_forward_kernel<true>, consts_dev, call)
+                           : cudaLaunchKernelEx(&cfg, res2_forward_kernel<false>, consts_dev, call);
   return e == cudaSuccess ? 0 : (int)e;
 }
 
