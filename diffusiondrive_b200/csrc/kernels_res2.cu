@@ -6,12 +6,11 @@
 // Work split.  The cluster is a 4 x 4 grid: CTA (ag, fg) = (rank / 4, rank % 4) belongs to anchor
 // group ag (anchors [ag*NAG, +NAG), NAG = ceil(A/4) <= 7) and owns feature slice fg of it.  Every
 // Linear of the chain is, per CTA,
-//     out^T[f, n] = sum_k W[f, k] * x[n, k]       (tcgen05.mma, M = 64 weight rows, N = 16)
+//     out^T[f, n] = sum_k W[f, k] * x[n, k]       (tcgen05.mma, M = 64 weight rows, N = 8)
 // with the CTA's 64 weight rows (F/4 for the FFN up-projection) as the A operand -- pre-swizzled
 // shared-memory images (pack_sw128_kernel) fetched 32 KiB at a time by bulk copies into a two-slot
 // ring, by two free-running threads, ahead of the math -- and the group's <= 8 activation rows as
-// the B operand (rows 8..15 of the N = 16 operand alias rows 0..7 through a zero row-group
-// stride).  Epilogue: one thread per output feature reads TMEM, applies bias / ReLU / residual
+// the B operand.  Epilogue: one thread per output feature reads TMEM, applies bias / ReLU / residual
 // and writes the CTA's slice, which the bulk-copy engine pushes into the three peers of the group
 // (cp.async.bulk shared::cta -> shared::cluster, completion bytes counted by the peers' exchange
 // barrier); every CTA then applies the row operations (LayerNorm, +ego, FiLM) to the full rows,

@@ -19,6 +19,7 @@ accelerated path and raises.
 from __future__ import annotations
 
 import copy
+import contextlib
 import ctypes as C
 from typing import Dict, Optional
 
@@ -323,7 +324,10 @@ class TrajectoryHead(nn.Module):
         scores = flat[n_t + n_m:].view(B, A)
         idx = torch.empty((B,), dtype=torch.int64, device=out_dev)
 
-        with torch.cuda.device(dev):
+        # switching the current device costs ~10 us of host time per call: only when it differs
+        same_dev = dev.index is None or torch.cuda.current_device() == dev.index
+        guard = contextlib.nullcontext() if same_dev else torch.cuda.device(dev)
+        with guard:
             self._ensure_handle(Na, Cc, H, W)
             self._ensure_packed(dev)
             lib, h = self._lib, self._handle
@@ -334,7 +338,8 @@ class TrajectoryHead(nn.Module):
                     _lib.NHWC if bev_layout == "NHWC" else _lib.NCHW,
                     noise.data_ptr(), traj.data_ptr(), modes.data_ptr(), scores.data_ptr(),
                     idx.data_ptr(), B, stream)
-            _lib.check(lib, h, rc, "ddh_forward_host" if host_call else "ddh_forward")
+            if rc:
+                _lib.check(lib, h, rc, "ddh_forward_host" if host_call else "ddh_forward")
         return {"trajectory": traj, "trajectory_modes": modes, "trajectory_scores": scores,
                 "mode_idx": idx}
 
