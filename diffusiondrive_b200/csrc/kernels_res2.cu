@@ -1078,28 +1078,61 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call_in)
           const float* Ks = reinterpret_cast<const float*>(pipe + P_KV);
           const float* Vv = Ks + 32 * KS_LD;
           uint8_t* bnext = bop_ptr(k + 1);
-          for (int pr = warp; pr < n_own * 2; pr += 8) {
-            const int n = pr >> 1, hh = pr & 1;
-            float s = -INFINITY;
-            if (lane < Na) {
-              s = 0.f;
-              const float* kr = Ks + lane * KS_LD + hh * 32;
-              const float* qr = ql + n * 64 + hh * 32;
+          // one (anchor, head) pair per HALF-warp, so that the group's <= 14 pairs run in one round:
+          // a lane scores agents l16 and l16 + 16 and accumulates output dims l16 and l16 + 16
+          {
+            const int pr = warp * 2 + (lane >> 4), l16 = lane & 15;
+            const bool live = pr < n_own * 2;
+            const int n = live ? pr >> 1 : 0, hh = pr & 1;
+            const float* qr = ql + n * 64 + hh * 32;
+            float s0 = -INFINITY, s1 = -INFINITY;
+            if (l16 < Na) {
+              s0 = 0.f;
+              const float* kr = Ks + l16 * KS_LD + hh * 32;
 #pragma unroll
               for (int c4 = 0; c4 < 8; ++c4) {
                 const float4 kk = *reinterpret_cast<const float4*>(kr + c4 * 4);
                 const float4 qq = *reinterpret_cast<const float4*>(qr + c4 * 4);
-                s = fmaf(qq.x, kk.x, s); s = fmaf(qq.y, kk.y, s); s = fmaf(qq.z, kk.z, s); s = fmaf(qq.w, kk.w, s);
+                s0 = fmaf(qq.x, kk.x, s0); s0 = fmaf(qq.y, kk.y, s0); s0 = fmaf(qq.z, kk.z, s0); s0 = fmaf(qq.w, kk.w, s0);
               }
             }
-            float mx = s;
+            if (l16 + 16 < Na) {
+              s1 = 0.f;
+              const float* kr = Ks + (l16 + 16) * KS_LD + hh * 32;
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-            const float e = (lane < Na) ? expf(s - mx) : 0.f;
-            const float pj = e / warp_sum(e);
-            float acc = 0.f;
-            for (int jj = 0; jj < Na; ++jj) acc = fmaf(__shfl_sync(0xffffffffu, pj, jj), Vv[jj * 64 + hh * 32 + lane], acc);
-            *reinterpret_cast<__nv_bfloat16*>(bnext + sw_off(n, fg * 64 + hh * 32 + lane, BCH)) = __float2bfloat16_rn(acc);
+              for (int c4 = 0; c4 < 8; ++c4) {
+                const float4 kk = *reinterpret_cast<const float4*>(kr + c4 * 4);
+                const float4 qq = *reinterpret_cast<const float4*>(qr + c4 * 4);
+                s1 = fmaf(qq.x, kk.x, s1); s1 = fmaf(qq.y, kk.y, s1); s1 = fmaf(qq.z, kk.z, s1); s1 = fmaf(qq.w, kk.w, s1);
+              }
+            }
+            float mx = fmaxf(s0, s1);
+#pragma unroll
+            for (int off = 8; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+            const float e0 = (l16 < Na) ? expf(s0 - mx) : 0.f;
+            const float e1 = (l16 + 16 < Na) ? expf(s1 - mx) : 0.f;
+            float den = e0 + e1;
+#pragma unroll
+            for (int off = 8; off > 0; off >>= 1) den += __shfl_xor_sync(0xffffffffu, den, off);
+            const float p0 = e0 / den, p1 = e1 / den;
+            float acc0 = 0.f, acc1 = 0.f;
+            const float* vcol = Vv + hh * 32 + l16;
+            const int nlo = min(Na, 16);
+            for (int jj = 0; jj < nlo; ++jj) {
+              const float pj = __shfl_sync(0xffffffffu, p0, jj, 16);
+              acc0 = fmaf(pj, vcol[jj * 64], acc0);
+              acc1 = fmaf(pj, vcol[jj * 64 + 16], acc1);
+            }
+            for (int jj = 16; jj < Na; ++jj) {
+              const float pj = __shfl_sync(0xffffffffu, p1, jj - 16, 16);
+              acc0 = fmaf(pj, vcol[jj * 64], acc0);
+              acc1 = fmaf(pj, vcol[jj * 64 + 16], acc1);
+            }
+            if (live) {
+              const int f0 = fg * 64 + hh * 32 + l16;
+              *reinterpret_cast<__nv_bfloat16*>(bnext + sw_off(n, f0, BCH)) = __float2bfloat16_rn(acc0);
+              *reinterpret_cast<__nv_bfloat16*>(bnext + sw_off(n, f0 + 16, BCH)) = __float2bfloat16_rn(acc1);
+            }
           }
           xchg_send(k, off_x + X_BOP + ((k + 1) & 1) * 16384 + fg * BCH, BCH, 0, 0, true);
           xchg_wait(k);
