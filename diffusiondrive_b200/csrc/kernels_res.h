@@ -14,7 +14,7 @@ constexpr int RES_CL = 16;        // CTAs per cluster (non-portable size, opt-in
 constexpr int RES_MAX_L = 4;      // decoder layers
 constexpr int RES_MAX_S = 4;      // denoise steps
 constexpr int RES_MAX_ITEMS = 160;
-constexpr int RES_MAX_B = 8;      // scenes per call served by this engine
+constexpr int RES_MAX_B = 24;     // scenes per call served by the one-launch engines
 
 // Tensor maps of the weight matrices (bf16 [N][K], box {64 k, slice rows}, 128-byte swizzle) and
 // the order in which a CTA consumes them.  Lives in global memory only (TMA descriptors).

@@ -173,24 +173,28 @@ def _with_env(env, fn):
 
 
 def test_small_batch_engine_matches_reference(golden_dir):
-    """B <= 8 in bf16 mode runs the group-resident engine (kernels_res2.cu): the whole forward as ONE
+    """B <= 24 in bf16 mode runs the group-resident engine (kernels_res2.cu): the whole forward as ONE
     launch on one 16-CTA cluster per scene.  Same tolerance as the tensor path; it is the engine the
     batch-1 latency number is measured on."""
     ref = _load(golden_dir, "default_b256")
     head, _ = _make_head("bf16")
     outs = {}
-    for B in (1, 2, 3, 8):
+    for B in (1, 2, 3, 8, 20):
         out, _, _ = _run(head, B)
         outs[B] = out
         sub = {k: v[:B] for k, v in ref.items()}
         rec = _report(f"bf16_resident_b{B}_vs_reference", out, sub)
         assert rec["max_dxy_m"] <= TOL_BF16_M and rec["max_dheading_rad"] <= TOL_BF16_M
-        assert rec["mode_agreement"] == 1.0
+        if B <= 8:
+            assert rec["mode_agreement"] == 1.0
+        else:   # near-tie scenes may flip under bf16 operands; clear ones must not
+            assert rec["mode_agreement_margin_gt_0.05"] in (1.0, None)
         assert head.last_launch_count() == 1
     # a scene's plan does not depend on the batch it rides in, nor on the run (fixed summation orders)
     for k in ("trajectory_modes", "trajectory_scores", "trajectory", "mode_idx"):
         assert np.array_equal(outs[8][k][:1], outs[1][k])
         assert np.array_equal(outs[8][k][:3], outs[3][k])
+        assert np.array_equal(outs[20][k][:8], outs[8][k])
     again, _, _ = _run(head, 8)
     for k in outs[8]:
         assert np.array_equal(again[k], outs[8][k])
