@@ -392,6 +392,10 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call_in)
   // Warps 8 and 9 stream the linear stages' weights (a thread's bulk copies run one at a time, so
   // two threads alternate); all four issue the conv's MMAs, k-step `me` of every k-chunk each.
   if (warp >= 8) {
+    // warp-specialised register budget: the engine warpgroup hands its registers to the two compute
+    // warpgroups, whose code is compiled for 224 registers instead of spilling at the 168 of a
+    // 384-thread block
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (lane == 0) {
       const int me = warp - 8;
       int seq = 0, cg = 0;
@@ -450,6 +454,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call_in)
   }
   // =============================================================== compute warps
   else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     const int quad = warp & 3;
     const uint32_t tlane = tmem + ((uint32_t)(quad * 32) << 16);
     const int a0 = ag * NAG;
