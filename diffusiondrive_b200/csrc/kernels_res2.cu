@@ -1154,7 +1154,9 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call_in)
             ldg8(LC.norm1_g, lane, g1); ldg8(LC.norm1_b, lane, b1);
             ldg8(LC.norm2_g, lane, g2); ldg8(LC.norm2_b, lane, b2);
           }
+          mark(130);
           wait_acc();
+          mark(131);
           if (warp < 4) {
             float v[8];
             acc8(ACC_LIN, v);
@@ -1162,9 +1164,12 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call_in)
 #pragma unroll
             for (int n = 0; n < NROW; ++n)
               if (lane < 16) sl[n * 64] = v[n] + bias + x1_s[n * D + f];
+            mark(132);
             xchg_send(k, off_x + X_ACT + (k & 1) * 8192 + fg * 2048, 2048, 0, 0, false);
           }
+          mark(133);
           xchg_wait(k);
+          mark(134);
           if (warp < n_own) {
             float v[8], eg[8];
             act_load8(act_ptr(k), warp, lane, v);
@@ -1176,6 +1181,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call_in)
             bt_store8(bop_ptr(k + 1), warp, lane, v);
           }
           ++k;
+          mark(135);
           b_done(1);
         }
         mark(25);
