@@ -1443,7 +1443,7 @@ void launch_pack_sw128(const __nv_bfloat16* W, __nv_bfloat16* out, int N, int K,
 
 int res2_smem_bytes() { return SMEM_BYTES; }
 
-static bool g_res2_ready = false;
+static bool g_res2_ready[64] = {};   // per device: function attributes are per-device state
 
 static void res2_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int B, cudaStream_t st) {
   cfg = {};
@@ -1460,7 +1460,9 @@ static void res2_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int B, 
 }
 
 int res2_engine_init() {
-  if (g_res2_ready) return 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 4;
+  if (g_res2_ready[dev]) return 0;
   cudaError_t e = cudaFuncSetAttribute(res2_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        SMEM_BYTES);
   if (e == cudaSuccess)
@@ -1479,7 +1481,7 @@ int res2_engine_init() {
     cudaGetLastError();
     return 3;
   }
-  g_res2_ready = true;
+  g_res2_ready[dev] = true;
   return 0;
 }
 
