@@ -695,9 +695,11 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call_in)
       {
         const float bias = (warp < 4 && lane < 16) ? __ldg(C.b_enc3 + fg * 64 + quad * 16 + lane) : 0.f;
         float wa[8][8];   // rows of this CTA's attention-weight head, fetched under the MMA
+        float ba = 0.f;
         if (warp < n_own && fg < L) {
 #pragma unroll
           for (int p = 0; p < 8; ++p) ldg8(C.layer[fg].attw_w + (size_t)p * D, lane, wa[p]);
+          if (lane < P) ba = __ldg(C.layer[fg].attw_b + lane);
         }
         wait_acc();
         if (warp < 4) {
@@ -734,7 +736,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call_in)
 #pragma unroll
             for (int p = 0; p < 8; ++p)
               if (lane == p) dot = dots[p];
-            const float lg = (lane < P) ? dot + __ldg(C.layer[l].attw_b + lane) : -INFINITY;
+            const float lg = (lane < P) ? dot + ba : -INFINITY;
             float mx = lg;
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
@@ -1297,10 +1299,12 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call_in)
           // regression-head rows of this CTA: outputs c = fg*6 .. fg*6+5 (3P = 24)
           const int nout = 3 * P / GF;
           float w4[6][8];
+          float b4 = 0.f;   // fetched under the MMA: a global load after the exchange would sit on the critical path
           if (warp < n_own) {
 #pragma unroll
             for (int ci = 0; ci < 6; ++ci)
               if (ci < nout) ldg8(LC.reg4_w + (size_t)(fg * nout + ci) * D, lane, w4[ci]);
+            if (lane < nout) b4 = __ldg(LC.reg4_b + fg * nout + lane);
           }
           float* act2 = reinterpret_cast<float*>(pipe + P_ACT2 + 8192);
           wait_acc();
@@ -1358,7 +1362,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call_in)
             // reg[..., :2] += points; heading = tanh(.)*pi; next points; DDIM update (:378-380,424,632-636)
             if (lane < nout) {
               const int cidx = fg * nout + lane, p = cidx / 3, comp = cidx - p * 3;
-              mine += __ldg(LC.reg4_b + cidx);
+              mine += b4;
               if (call.dbg) C.tap_regraw[((size_t)scene * A + a) * 3 * P + cidx] = mine;
               float out;
               if (comp < 2) {
