@@ -70,6 +70,7 @@ SIGNATURES = {
                                    _fp, C.c_int, C.c_void_p]),
     "ddh_last_launch_count": (C.c_int, [C.c_void_p]),
     "ddh_set_concurrency": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "ddh_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "ddh_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "ddh_get_profile": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "ddh_debug_copy": (C.c_longlong, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]),

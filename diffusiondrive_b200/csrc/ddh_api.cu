@@ -23,6 +23,7 @@
 
 #include "../../include/ddh.h"
 #include "kernels.h"
+#include "kernels_chain.h"
 #include "kernels_res.h"
 #include "kernels_res2.h"
 
@@ -46,6 +47,8 @@ struct PackedLayer {
   float *norm3_g = nullptr, *norm3_b = nullptr;
   float *cls_ln2_g = nullptr, *cls_ln2_b = nullptr, *cls_ln5_g = nullptr, *cls_ln5_b = nullptr;
   float *cls6_w = nullptr, *cls6_b = nullptr, *reg4_w = nullptr, *reg4_b = nullptr;
+  __nv_bfloat16* reg4_hl = nullptr;   // [64][256]: bf16 hi rows 0.., lo rows 32.. (chain engine tail)
+  CUtensorMap reg4_map;
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -132,6 +135,14 @@ struct ddh_handle {
   std::vector<void*> owned_res2;
   R2Consts* res2_consts = nullptr;
   R2Consts res2_host;
+  // scene-tile chain engine (kernels_chain.cu): B > RES_MAX_B in bf16 mode
+  int chain_enabled = 1;
+  bool chain_ok = false;
+  int chain_spt = 0;                           // scenes per 128-row tile
+  __nv_bfloat16* kv16 = nullptr;               // [L][B*Na][CH_KV_LD]
+  float* q0t = nullptr;                        // [tiles][64][128] float4
+  CUtensorMap smap;                            // S16 [B*A][256], box {64, 128}
+  std::vector<ChainArgs> chain_prog;           // [S] encoder programs, then [S][L] layer programs
   std::map<std::string, std::pair<const void*, size_t>> taps;
   int launches = 0;
   // optional per-stage device timing (ddh_set_profiling)
@@ -327,6 +338,10 @@ size_t ws_bytes_for(const ddh_shape& s, int B, int precision) {
   b += (size_t)B * rcap * 4 + B * 4 + M * s.num_poses * 4 * 8;
   b += (size_t)B * rcap * Dm * 4;                        // V
   b += M * s.num_poses * 3 * 4 + M * 4;
+  if (precision == DDH_PREC_BF16 && s.num_anchors <= 128) {   // chain engine: bf16 K|V, tiled q0
+    const size_t spt = 128 / s.num_anchors, tiles = (B + spt - 1) / spt;
+    b += (size_t)s.num_layers * B * s.num_agents * CH_KV_LD * 2 + tiles * 128 * Dm * 4;
+  }
   return b;
 }
 
@@ -378,6 +393,13 @@ int ensure_ws(ddh_handle* h, int B) {
     WS(h->h16, M * F); WS(h->x3_16, M * D); WS(h->c1_16, M * D); WS(h->r1_16, M * D);
     // fp32 taps kept for debugging only where cheap
     WS(h->s32, M * D); WS(h->x2_32, M * D); WS(h->x3_32, M * D);
+    if (h->chain_ok) {
+      const size_t tiles = ((size_t)B + h->chain_spt - 1) / h->chain_spt;
+      WS(h->kv16, (size_t)L * B * s.num_agents * CH_KV_LD);
+      WS(h->q0t, tiles * 128 * D);
+      rc = encode_wmap(h, &h->smap, h->s16, (int)M, D, 128);
+      if (rc) return rc;
+    }
   } else {
     WS(h->emb32, M * 512); WS(h->e1_32, M * D);
     WS(h->s32, M * D); WS(h->o32, M * D); WS(h->x2_32, M * D);
@@ -785,7 +807,8 @@ int ddh_pack_weights(ddh_handle* h, const ddh_weight_ptrs* w, int precision, voi
   // a change of precision changes the workspace layout
   cudaDeviceSynchronize();
   free_all(h->owned_w);
-  if (precision != h->precision) { free_all(h->owned_ws); h->cap_B = 0; }
+  free_all(h->owned_ws);   // the workspace layout depends on precision and engine selection
+  h->cap_B = 0;
   h->packed = false;
   h->precision = precision;
   if (precision == DDH_PREC_BF16 && tc_conv_smem_bytes(s.num_anchors, s.num_poses * 4) > 227 * 1024)
@@ -873,6 +896,19 @@ int ddh_pack_weights(ddh_handle* h, const ddh_weight_ptrs* w, int precision, voi
     TRY(pack_linear(h, pl.reg2, lw.reg2_w, lw.reg2_b, D, D, st));
     TRY(copy_vec(h, &pl.reg4_w, lw.reg4_w, (size_t)3 * P * D, st));
     TRY(copy_vec(h, &pl.reg4_b, lw.reg4_b, 3 * P, st));
+    if (precision == DDH_PREC_BF16) {
+      TRY(dev_alloc(h, h->owned_w, &pl.reg4_hl, (size_t)64 * D));
+      launch_pack_hilo(lw.reg4_w, pl.reg4_hl, 3 * P, D, st);
+      TRY(encode_wmap(h, &pl.reg4_map, pl.reg4_hl, 64, D, 64));
+    }
+  }
+  // scene-tile chain engine: shape limits of kernels_chain.cu
+  h->chain_ok = false;
+  h->chain_prog.clear();
+  if (precision == DDH_PREC_BF16 && h->chain_enabled && A <= 128 && F <= 1024 && P == 8 &&
+      s.num_agents <= 32 && chain_engine_init() == 0) {
+    h->chain_ok = true;
+    h->chain_spt = 128 / A;
   }
 #undef TRY
   CU_TRY(h, cudaGetLastError());
@@ -1134,6 +1170,244 @@ int forward_small(ddh_handle* h, const float* ego, const float* agents, const vo
   return DDH_OK;
 }
 
+
+// ---- scene-tile chain engine (kernels_chain.cu): the program tables
+struct ProgBuilder {
+  ChainArgs& a;
+  int nops = 0, nsteps = 0, npar = 0, parpos = 0, nmaps = 0;
+  explicit ProgBuilder(ChainArgs& a_) : a(a_) {}
+  int map(const CUtensorMap& m) { a.maps[nmaps] = m; return nmaps++; }
+  int par(const float* src, int n) {
+    const int off = parpos;
+    a.par[npar++] = ChainParSrc{src, n, off};
+    parpos += (n + 3) / 4 * 4;
+    return off;
+  }
+  int op(int map, int a_chunk, int nk, int k0, int n0, int acc_col, int flags) {
+    ChainOp& o = a.ops[nops];
+    o.map = (uint8_t)map; o.a_chunk = (uint8_t)a_chunk; o.nk = (uint8_t)nk; o.k0 = (uint8_t)k0;
+    o.n0 = (uint16_t)n0; o.acc_col = (uint16_t)acc_col; o.flags = (uint8_t)flags;
+    return nops++;
+  }
+  void step(int op0, int nops_, int epi, int flags, int dst_chunk, int acc_col,
+            std::initializer_list<int> pars) {
+    ChainStep& st = a.steps[nsteps++];
+    st.op0 = (uint8_t)op0; st.nops = (uint8_t)nops_; st.epi = (uint8_t)epi; st.flags = (uint8_t)flags;
+    st.dst_chunk = (uint8_t)dst_chunk; st.acc_col = (uint16_t)acc_col;
+    int i = 0;
+    for (int v : pars) st.par[i++] = (uint16_t)v;
+  }
+  bool finish() {
+    a.n_steps = nsteps; a.n_par = npar;
+    return nops <= CH_MAX_OPS && nsteps <= CH_MAX_STEPS && npar <= CH_MAX_PAR && nmaps <= CH_MAX_MAPS &&
+           parpos <= CH_PAR_FLOATS;
+  }
+};
+
+// embedding + plan_anchor_encoder (:459-462, 601-609) of denoise step si
+bool build_enc_program(ddh_handle* h, int si, ChainArgs& a) {
+  memset(&a, 0, sizeof a);
+  ProgBuilder b(a);
+  const int m0 = b.map(h->enc0.map), m3 = b.map(h->enc3.map);
+  const int p_b0 = b.par(h->enc0.bias, D), p_g = b.par(h->enc_ln_g, D), p_b = b.par(h->enc_ln_b, D);
+  const int p_b3 = b.par(h->enc3.bias, D), p_dt = b.par(h->dim_t, 32);
+  int o = b.op(m0, 0, h->enc0.K / 64, 0, 0, 0, 0);
+  b.step(o, 1, CE_RELU_LN, 0, 0, 0, {p_b0, p_g, p_b, 0, 0, p_dt});
+  o = b.op(m3, 0, 4, 0, 0, 256, 0);
+  b.step(o, 1, CE_Q0, 0, 0, 256, {p_b3});
+  a.mode = 1;
+  a.first_step = si == 0 ? 1 : 0;
+  const float ac_tr = h->ac[h->shp.trunc_timestep];
+  a.sa = sqrtf(ac_tr); a.sb = sqrtf(1.0f - ac_tr);
+  return b.finish();
+}
+
+// one decoder-layer call after the BEV sampling (:355-380), layer l of denoise step si
+bool build_layer_program(ddh_handle* h, int si, int l, ChainArgs& a) {
+  memset(&a, 0, sizeof a);
+  const ddh_shape& s = h->shp;
+  const PackedLayer& pl = h->layers[l];
+  const int L = s.num_layers, S = s.num_steps, nb = s.d_ffn / D;
+  const bool last = (si == S - 1) && (l == L - 1);
+  ProgBuilder b(a);
+  const int m_bo = b.map(pl.bev_out.map), m_q = b.map(pl.q.map), m_ao = b.map(pl.attn_out.map);
+  const int m_f0 = b.map(pl.ffn0.map), m_f2 = b.map(pl.ffn2.map);
+  const int m_r0 = b.map(pl.reg0.map), m_r2 = b.map(pl.reg2.map), m_r4 = b.map(pl.reg4_map);
+  const int p_bbo = b.par(pl.bev_out.bias, D), p_bao = b.par(pl.attn_out.bias, D), p_bq = b.par(pl.q.bias, D);
+  const int p_n1g = b.par(pl.norm1_g, D), p_n1b = b.par(pl.norm1_b, D);
+  const int p_n2g = b.par(pl.norm2_g, D), p_n2b = b.par(pl.norm2_b, D);
+  const int p_bf0 = b.par(pl.ffn0.bias, s.d_ffn), p_bf2 = b.par(pl.ffn2.bias, D);
+  const int p_n3g = b.par(pl.norm3_g, D), p_n3b = b.par(pl.norm3_b, D);
+  const int p_film = b.par(h->film + ((size_t)si * L + l) * 2 * D, 2 * D);
+  const int p_br0 = b.par(pl.reg0.bias, D), p_br2 = b.par(pl.reg2.bias, D);
+  const int p_br4 = b.par(pl.reg4_b, 3 * s.num_poses);
+  constexpr int R0 = 0, R1 = 4, T0 = 0, T1 = 256;
+  int o;
+  // cross_bev_attention output_proj + residual (modules/blocks.py:127-129)
+  o = b.op(m_bo, R0, 4, 0, 0, T0, 0);
+  b.step(o, 1, CE_X1, CS_WAIT_S, R0, T0, {p_bbo, p_bao});
+  // cross_agent_attention: q projection, attention core (:355-357)
+  o = b.op(m_q, R0, 4, 0, 0, T1, 0);
+  b.step(o, 1, CE_ATTN, CS_KVGO, R1, T1, {p_bq});
+  // out_proj accumulated onto x1 (+ bias) already in TMEM; norm1, + ego, norm2 (:358-365)
+  o = b.op(m_ao, R1, 4, 0, 0, T0, CO_ACCUM);
+  b.step(o, 1, CE_LN2EGO, 0, R0, T0, {p_n1g, p_n1b, p_n2g, p_n2b});
+  // ffn (:368): hidden blocks of 256 streamed through region 1 as k-blocks of ffn.2
+  o = b.op(m_f0, R0, 4, 0, 0, T1, 0);
+  b.step(o, 1, CE_RELU, 0, R1, T1, {p_bf0});
+  for (int j = 1; j < nb; ++j) {
+    o = b.op(m_f2, R1, 4, 4 * (j - 1), 0, T0, j > 1 ? CO_ACCUM : 0);
+    b.op(m_f0, R0, 4, 0, D * j, T1, 0);
+    b.step(o, 2, CE_RELU, 0, R1, T1, {p_bf0 + D * j});
+  }
+  o = b.op(m_f2, R1, 4, 4 * (nb - 1), 0, T0, nb > 1 ? CO_ACCUM : 0);
+  b.step(o, 1, CE_LN_FILM, 0, R0, T0, {p_bf2, p_n3g, p_n3b, p_film});   // norm3 + time FiLM (:368-373)
+  // task_decoder (:244-256, 376-380)
+  o = b.op(m_r0, R0, 4, 0, 0, T1, 0);
+  b.step(o, 1, CE_RELU, last ? 0 : CS_SAFREE, R1, T1, {p_br0});
+  o = b.op(m_r2, R1, 4, 0, 0, T1, 0);
+  b.step(o, 1, CE_RELU, 0, R1, T1, {p_br2});
+  if (!last) {
+    o = b.op(m_r4, R1, 4, 0, 0, T1, CO_N64);
+    b.step(o, 1, CE_TAIL, 0, R1, T1, {p_br4});
+  } else {   // cls branch only where it is read (:631)
+    const int m_c0 = b.map(pl.cls0.map), m_c3 = b.map(pl.cls3.map);
+    const int p_bc0 = b.par(pl.cls0.bias, D), p_l2g = b.par(pl.cls_ln2_g, D), p_l2b = b.par(pl.cls_ln2_b, D);
+    const int p_bc3 = b.par(pl.cls3.bias, D), p_l5g = b.par(pl.cls_ln5_g, D), p_l5b = b.par(pl.cls_ln5_b, D);
+    const int p_w6 = b.par(pl.cls6_w, D), p_b6 = b.par(pl.cls6_b, 1);
+    o = b.op(m_r4, R1, 4, 0, 0, T1, CO_N64);
+    b.op(m_c0, R0, 4, 0, 0, T0, 0);
+    b.step(o, 2, CE_TAIL, CS_SAFREE, R1, T1, {p_br4});
+    b.step(0, 0, CE_RELU_LN, 0, R1, T0, {p_bc0, p_l2g, p_l2b});
+    o = b.op(m_c3, R1, 4, 0, 0, T0, 0);
+    b.step(o, 1, CE_SCORE, 0, R1, T0, {p_bc3, p_l5g, p_l5b, p_w6, p_b6});
+  }
+  a.mode = 0;
+  a.do_ddim = (l == L - 1 && si != S - 1) ? 1 : 0;
+  a.dc = DdimCoef{0.f, 1.f, 1.f, 0.f};
+  if (a.do_ddim) {
+    const int t = h->roll[si], prev = t - 1;   // set_timesteps(1000) => step ratio 1 (:584)
+    const float ac_t = h->ac[t], ac_p = prev >= 0 ? h->ac[prev] : 1.0f;
+    a.dc = DdimCoef{sqrtf(ac_t), sqrtf(1.0f - ac_t), sqrtf(ac_p), sqrtf(1.0f - ac_p)};
+  }
+  return b.finish();
+}
+
+int build_chain_programs(ddh_handle* h) {
+  const ddh_shape& s = h->shp;
+  const int L = s.num_layers, S = s.num_steps;
+  h->chain_prog.assign((size_t)S + (size_t)S * L, ChainArgs());
+  for (int si = 0; si < S; ++si) {
+    if (!build_enc_program(h, si, h->chain_prog[si]))
+      return fail(h, DDH_ERR_UNSUPPORTED, "chain engine: encoder program exceeds the table sizes");
+    for (int l = 0; l < L; ++l)
+      if (!build_layer_program(h, si, l, h->chain_prog[S + (size_t)si * L + l]))
+        return fail(h, DDH_ERR_UNSUPPORTED, "chain engine: layer program exceeds the table sizes");
+  }
+  return DDH_OK;
+}
+
+// forward_test (:578-641) on the scene-tile chain engine: per denoise step one encoder launch, per
+// decoder layer plan -> on-demand layout -> conv (+ fused combine) -> chain.
+int forward_fused(ddh_handle* h, const float* ego, const float* agents, const void* bev,
+                  int bev_dtype, int bev_layout, const float* noise, float* out_traj,
+                  float* out_modes, float* out_scores, int64_t* out_mode_idx, int B,
+                  cudaStream_t st) {
+  const ddh_shape& s = h->shp;
+  const int A = s.num_anchors, P = s.num_poses, Na = s.num_agents, L = s.num_layers, S = s.num_steps;
+  const int HW = s.bev_h * s.bev_w;
+  int rc;
+  if (h->chain_prog.empty()) { rc = build_chain_programs(h); if (rc) return rc; }
+  const int spt = h->chain_spt, n_tiles = (B + spt - 1) / spt;
+  const void* bevn = bev;
+  const bool lazy = bev_layout == DDH_NCHW && h->lazy_layout && s.bev_h <= 64 && !h->profiling_eager;
+  { ProfSpan ps(h, ST_BEV, st);
+  if (bev_layout == DDH_NCHW) {
+    if (lazy) {
+      CU_TRY(h, cudaMemsetAsync(h->done_rows, 0, (size_t)B * 8, st));
+    } else {
+      launch_bev_to_nhwc(bev, bev_dtype, h->bev_nhwc, DDH_BF16, B, s.bev_channels, HW, st);
+      h->launches++;
+    }
+    bevn = h->bev_nhwc;
+  } else if (bev_dtype != DDH_BF16) {
+    launch_cast_f32_bf16(reinterpret_cast<const float*>(bev), reinterpret_cast<__nv_bfloat16*>(h->bev_nhwc),
+                         (size_t)B * HW * s.bev_channels, st);
+    h->launches++;
+    bevn = h->bev_nhwc;
+  }
+  }
+  // hoisted per (scene, layer): agent K|V (bf16, padded rows: the attention's ldmatrix operand) and
+  // the collapsed ego vector
+  { ProfSpan ps(h, ST_HOIST, st);
+  launch_cast_f32_bf16(agents, h->agents16, (size_t)B * Na * D, st);
+  launch_cast_f32_bf16(ego, h->ego16, (size_t)B * D, st);
+  h->launches += 2;
+  for (int l = 0; l < L; ++l) {
+    RowEpi e;
+    e.out_bf16 = h->kv16 + (size_t)l * B * Na * CH_KV_LD;
+    e.ldo16 = CH_KV_LD;
+    run_gemm(h, h->layers[l].kv, nullptr, h->agents16, D, B * Na, e, st);
+    RowEpi e2;
+    e2.out_f32 = h->egov + (size_t)l * B * D;
+    e2.ldo32 = D;
+    run_gemm(h, h->layers[l].ego, nullptr, h->ego16, D, B, e2, st);
+  }
+  }
+  float* modes = out_modes ? out_modes : h->modes_buf;
+  float* scores = out_scores ? out_scores : h->scores_buf;
+  OdoConsts oc{s.lidar_max_x, s.lidar_max_y};
+  auto fill = [&](ChainArgs& a) {
+    a.B = B; a.A = A; a.Na = Na; a.P = P; a.spt = spt; a.n_tiles = n_tiles;
+    a.anchors = h->anchors; a.noise = noise; a.img = h->img; a.pts = h->pts; a.q0t = h->q0t;
+    a.modes = modes; a.scores = scores; a.smap = h->smap; a.dbg = nullptr;
+  };
+  for (int si = 0; si < S; ++si) {
+    { ProfSpan ps(h, ST_EMBED, st);
+    ChainArgs& a = h->chain_prog[si];
+    fill(a);
+    launch_chain(a, st);
+    h->launches++; }
+    for (int l = 0; l < L; ++l) {
+      const PackedLayer& pl = h->layers[l];
+      { ProfSpan ps(h, ST_PLAN, st);
+      launch_plan(h->q0t, pl.attw_w, pl.attw_b, h->pts, h->upix, h->nuniq, h->ent_slot, h->ent_w,
+                  h->conv_rows + si * L + l, lazy ? h->need_rows : nullptr, h->done_rows, B, A, P,
+                  s.bev_h, s.bev_w, h->rcap, oc, st, spt);
+      h->launches++; }
+      if (lazy) {
+        ProfSpan ps(h, ST_BEV, st);
+        launch_bev_rows_to_nhwc(bev, bev_dtype, h->bev_nhwc, DDH_BF16, h->need_rows, B, s.bev_channels,
+                                s.bev_h, s.bev_w, st);
+        h->launches++;
+      }
+      { ProfSpan ps(h, ST_CONV, st);
+      GemmParams gp;
+      gp.K = pl.conv.K;
+      gp.bev = bevn; gp.upix = h->upix; gp.nuniq = h->nuniq; gp.rcap = h->rcap;
+      gp.H = s.bev_h; gp.W_ = s.bev_w; gp.C = s.bev_channels;
+      gp.epi.bias = pl.conv.bias; gp.epi.relu = 1;
+      gp.dbg = h->tl_gemm < 0 ? h->dbg : nullptr;
+      gp.ent_slot = h->ent_slot; gp.ent_w = h->ent_w; gp.n_anchor = A; gp.ent_per_anchor = P * 4;
+      gp.epi.out_f32 = h->s32; gp.epi.ldo32 = D; gp.epi.out_bf16 = h->s16; gp.epi.ldo16 = D;
+      launch_tc_conv(gp, pl.conv.map, B, st);
+      h->launches++; }
+      { ProfSpan ps(h, ST_GEMM, st);
+      ChainArgs& a = h->chain_prog[S + (size_t)si * L + l];
+      fill(a);
+      a.kv16 = h->kv16 + (size_t)l * B * Na * CH_KV_LD;
+      a.egov = h->egov + (size_t)l * B * D;
+      launch_chain(a, st);
+      h->launches++; }
+    }
+  }
+  { ProfSpan ps(h, ST_SELECT, st);
+  launch_select(scores, modes, out_traj, reinterpret_cast<long long*>(out_mode_idx), B, A, P, st);
+  h->launches++; }
+  CU_TRY(h, cudaGetLastError());
+  return DDH_OK;
+}
+
 int forward_range(ddh_handle* h, const float* ego, const float* agents, const void* bev,
                   int bev_dtype, int bev_layout, const float* noise, float* out_traj,
                   float* out_modes, float* out_scores, int64_t* out_mode_idx, int s0, int B,
@@ -1364,8 +1638,9 @@ int ddh_forward(ddh_handle* h, const float* ego, const float* agents, const void
   if ((bev_dtype != DDH_F32 && bev_dtype != DDH_BF16) || (bev_layout != DDH_NCHW && bev_layout != DDH_NHWC))
     return fail(h, DDH_ERR_BAD_ARG, "ddh_forward: bad bev dtype/layout");
   if ((reinterpret_cast<uintptr_t>(bev) | reinterpret_cast<uintptr_t>(ego) |
-       reinterpret_cast<uintptr_t>(agents)) & 15)
-    return fail(h, DDH_ERR_ALIGNMENT, "ddh_forward: ego/agents/bev must be 16-byte aligned");
+       reinterpret_cast<uintptr_t>(agents) | reinterpret_cast<uintptr_t>(noise) |
+       reinterpret_cast<uintptr_t>(out_modes)) & 15)
+    return fail(h, DDH_ERR_ALIGNMENT, "ddh_forward: ego/agents/bev/noise/out_modes must be 16-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int rc = ensure_ws(h, B);
   if (rc) return rc;
@@ -1442,6 +1717,13 @@ int ddh_forward(ddh_handle* h, const float* ego, const float* agents, const void
     h->taps["res_regraw"] = {R.regraw, MA * 3 * s.num_poses * 4};
     h->taps["res_emb16"] = {R.emb16, MA * 64 * s.num_poses * 2};
     h->taps["res_o16"] = {R.o16, MA * D * 2}; h->taps["res_h16"] = {R.h16, MA * s.d_ffn * 2};
+    CU_TRY(h, cudaGetLastError());
+    return DDH_OK;
+  }
+  if (h->chain_ok && h->precision == DDH_PREC_BF16) {
+    rc = forward_fused(h, ego, agents, bev, bev_dtype, bev_layout, noise, out_traj, out_modes, out_scores,
+                       out_mode_idx, B, st);
+    if (rc) return rc;
     CU_TRY(h, cudaGetLastError());
     return DDH_OK;
   }
@@ -1545,6 +1827,21 @@ int ddh_set_concurrency(ddh_handle* h, int chunks, int min_chunk_scenes) {
     return fail(h, DDH_ERR_BAD_ARG, "ddh_set_concurrency: bad argument");
   h->chunks = chunks;
   h->min_chunk_scenes = min_chunk_scenes;
+  return DDH_OK;
+}
+
+int ddh_set_option(ddh_handle* h, const char* name, int value) {
+  if (!h || !name) return fail(h, DDH_ERR_BAD_ARG, "ddh_set_option: null argument");
+  const std::string n(name);
+  bool repack = false;
+  if (n == "lazy_layout") h->lazy_layout = value;
+  else if (n == "chain_engine") { repack = h->chain_enabled != value; h->chain_enabled = value; }
+  else if (n == "resident_engine") { repack = h->res_mode != (value ? 2 : 0); h->res_mode = value ? 2 : 0; }
+  else if (n == "small_batch_engine") h->lat_enabled = value;
+  else if (n == "debug_taps") h->debug_taps = value != 0;
+  else if (n == "timeline_gemm") h->tl_gemm = value;
+  else return fail(h, DDH_ERR_BAD_ARG, "ddh_set_option: unknown option " + n);
+  if (repack) h->packed = false;   // engine selection is fixed at pack time: the caller packs again
   return DDH_OK;
 }
 

@@ -32,7 +32,7 @@ void launch_embed(const float* img, float* pts, float* emb32, __nv_bfloat16* emb
 void launch_plan(const float* q0, const float* attw_w, const float* attw_b, const float* pts,
                  int* upix, int* nuniq, int* ent_slot, float* ent_w, int* rows_total,
                  unsigned long long* need_rows, unsigned long long* done_rows, int B, int A, int P,
-                 int H, int W, int rcap, OdoConsts oc, cudaStream_t st);
+                 int H, int W, int rcap, OdoConsts oc, cudaStream_t st, int q0_spt = 0);
 void launch_bev_rows_to_nhwc(const void* src, int src_dtype, void* dst, int dst_dtype,
                              const unsigned long long* todo, int B, int C, int H, int W,
                              cudaStream_t st);
@@ -53,6 +53,7 @@ void launch_pack_conv_bf16(const float* w, __nv_bfloat16* dst, int Cout, int Cin
 void launch_matvec(const float* W, const float* x, const float* b, float* y, int n_out, int k,
                    int act_in_mish, cudaStream_t st);
 void launch_time_sinemb(float* emb, int dim, int timestep, cudaStream_t st);
+void launch_pack_hilo(const float* w, __nv_bfloat16* dst, int n_out, int k, cudaStream_t st);
 
 // ---- kernels_lat.cu (small-batch latency engine: column-split fp32 x bf16 linears) ---------
 struct LatLinearArgs {

@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(256) plan_kernel(const float* __restrict__ q0,
                                                    unsigned long long* __restrict__ need_rows,
                                                    unsigned long long* __restrict__ done_rows,
                                                    int A, int P, int H, int W, int rcap,
-                                                   OdoConsts oc) {
+                                                   OdoConsts oc, int q0_spt) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int HW = H * W;
   unsigned short* table = reinterpret_cast<unsigned short*>(smraw);        // [HW]
@@ -468,10 +468,20 @@ __global__ void __launch_bounds__(256) plan_kernel(const float* __restrict__ q0,
   for (int i = tid; i < HW; i += 256) table[i] = 0;
   // ---- attention weights: P (=8) logits per anchor, softmax over the poses
   for (int a = warp; a < A; a += 8) {
-    const float* q = q0 + ((size_t)scene * A + a) * D;
     float qv[8];
+    if (q0_spt > 0) {
+      // chain engine layout (kernels_chain.cu): [tile][64 column groups][128 rows] float4
+      const int tile = scene / q0_spt, r = (scene - tile * q0_spt) * A + a;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) qv[i] = q[lane + 32 * i];
+      for (int i = 0; i < 8; ++i) {
+        const int col = lane + 32 * i;
+        qv[i] = q0[(((size_t)tile * 64 + (col >> 2)) * 128 + r) * 4 + (col & 3)];
+      }
+    } else {
+      const float* q = q0 + ((size_t)scene * A + a) * D;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) qv[i] = q[lane + 32 * i];
+    }
     float logit[8];
 #pragma unroll
     for (int o = 0; o < 8; ++o) {
@@ -564,7 +574,7 @@ __global__ void __launch_bounds__(256) plan_kernel(const float* __restrict__ q0,
 void launch_plan(const float* q0, const float* attw_w, const float* attw_b, const float* pts,
                  int* upix, int* nuniq, int* ent_slot, float* ent_w, int* rows_total,
                  unsigned long long* need_rows, unsigned long long* done_rows, int B, int A, int P,
-                 int H, int W, int rcap, OdoConsts oc, cudaStream_t st) {
+                 int H, int W, int rcap, OdoConsts oc, cudaStream_t st, int q0_spt) {
   const int smem = ((H * W * 2 + 15) / 16) * 16 + A * P * 4;
   static int cur = 0;
   if (smem > cur) {
@@ -572,7 +582,7 @@ void launch_plan(const float* q0, const float* attw_w, const float* attw_b, cons
     cur = smem;
   }
   plan_kernel<<<B, 256, smem, st>>>(q0, attw_w, attw_b, pts, upix, nuniq, ent_slot, ent_w,
-                                     rows_total, need_rows, done_rows, A, P, H, W, rcap, oc);
+                                     rows_total, need_rows, done_rows, A, P, H, W, rcap, oc, q0_spt);
 }
 
 // ===================================================================================
@@ -906,6 +916,27 @@ void launch_pack_conv_f32(const float* w, float* dst, int Cout, int Cin, cudaStr
 void launch_pack_conv_bf16(const float* w, __nv_bfloat16* dst, int Cout, int Cin,
                            cudaStream_t st) {
   pack_conv_bf16_kernel<<<592, 256, 0, st>>>(w, dst, Cout, Cin);
+}
+
+// reg head weight [n_out][k] fp32 -> bf16 [64][k]: rows 0.. hold the bf16 rounding (hi) of W, rows
+// 32.. the bf16 rounding of the remainder (lo), so that r . (hi + lo) carries ~16 mantissa bits of W
+__global__ void pack_hilo_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ d, int n_out,
+                                 int k) {
+  const int n = 64 * k;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int row = i / k, col = i - row * k;
+    const int o = row & 31;
+    float v = 0.f;
+    if (o < n_out) {
+      const float x = w[(size_t)o * k + col];
+      const float hi = __bfloat162float(__float2bfloat16_rn(x));
+      v = (row < 32) ? hi : (x - hi);
+    }
+    d[i] = __float2bfloat16_rn(v);
+  }
+}
+void launch_pack_hilo(const float* w, __nv_bfloat16* dst, int n_out, int k, cudaStream_t st) {
+  pack_hilo_kernel<<<64, 256, 0, st>>>(w, dst, n_out, k);
 }
 
 // y[o] = sum_k W[o][k] * act(x[k]) + b[o]   (torch Linear layout), one warp per output

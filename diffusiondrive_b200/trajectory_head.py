@@ -150,6 +150,7 @@ class TrajectoryHead(nn.Module):
         self._handle_key = None
         self._packed_sig = None
         self._keepalive = None
+        self._options: Dict[str, int] = {}
         self.frozen = False     # True: skip the per-call "did the weights change" check
         self.register_load_state_dict_post_hook(lambda *_: self._invalidate())
 
@@ -190,6 +191,8 @@ class TrajectoryHead(nn.Module):
         rc = lib.ddh_set_alphas_cumprod(hp, C.cast(ac.data_ptr(), C.POINTER(C.c_float)),
                                         ac.numel())
         _lib.check(lib, hp, rc, "ddh_set_alphas_cumprod")
+        for name, value in self._options.items():
+            _lib.check(lib, hp, lib.ddh_set_option(hp, name.encode(), int(value)), "ddh_set_option")
 
     def _signature(self):
         return (self.precision,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
@@ -370,6 +373,16 @@ class TrajectoryHead(nn.Module):
         _lib.check(self._lib, self._handle,
                    self._lib.ddh_set_concurrency(self._handle, int(chunks), int(min_chunk_scenes)),
                    "ddh_set_concurrency")
+
+    def set_option(self, name: str, value: int) -> None:
+        """Execution option by name (see ddh_set_option in include/ddh.h); engine selection
+        options take effect at the next (automatic) weight packing."""
+        self._options[name] = int(value)
+        if self._handle is not None:
+            _lib.check(self._lib, self._handle,
+                       self._lib.ddh_set_option(self._handle, name.encode(), int(value)),
+                       "ddh_set_option")
+        self._invalidate()
 
     def set_profiling(self, on: bool) -> None:
         """Bracket every stage of the next forwards with CUDA events (bench.py roofline leg)."""

@@ -191,6 +191,19 @@ DDH_API int ddh_last_launch_count(const ddh_handle *h);
  * 2 chunks gain ~1 % at 4096 scenes on a B200. */
 DDH_API int ddh_set_concurrency(ddh_handle *h, int chunks, int min_chunk_scenes);
 
+/* Execution options (engine selection and debugging), by name; none of them changes results
+ * beyond the engines' documented tolerances.  Engine selection is fixed when the weights are
+ * packed: after changing "chain_engine" or "resident_engine" ddh_forward fails with
+ * DDH_ERR_NOT_PACKED until ddh_pack_weights is called again.
+ *   "resident_engine"    1  B <= 24, bf16: whole forward as one launch (kernels_res2.cu)
+ *   "chain_engine"       1  bf16: scene-tile chain kernel per decoder-layer call (kernels_chain.cu);
+ *                           0: one tcgen05 GEMM launch per Linear (kernels_tc.cu)
+ *   "small_batch_engine" 1  B <= 2 multi-launch latency engine when the two above are off
+ *   "lazy_layout"        1  NCHW input: convert BEV segments on demand; 0: whole map up front
+ *   "debug_taps"         0  keep fp32 copies of intermediate activations for ddh_debug_copy
+ *   "timeline_gemm"     -1  index of the dense GEMM launch to stamp (DDH_TIMELINE builds) */
+DDH_API int ddh_set_option(ddh_handle *h, const char *name, int value);
+
 /* Optional per-stage device timing: when on, ddh_forward brackets each stage with CUDA events
  * on the caller's stream.  ddh_get_profile synchronises and returns the summed duration and
  * the number of timed spans of one stage of the LAST forward.  Stages: "bev_layout",

@@ -1,0 +1,84 @@
+"""GPU diagnostic of the scene-tile chain engine: fused vs per-Linear launches vs golden."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from diffusiondrive_b200 import HeadConfig, TrajectoryHead, synth  # noqa: E402
+
+
+def make(chain, layers=2, anchors=20, steps=2):
+    sd = synth.make_state_dict(num_layers=layers, num_anchors=anchors)
+    head = TrajectoryHead(8, 1024, 256, None, HeadConfig(num_decoder_layers=layers, step_num=steps),
+                          plan_anchor=sd["plan_anchor"].numpy(), precision="bf16")
+    head.load_state_dict(sd)
+    head = head.cuda().eval()
+    head.set_option("chain_engine", chain)
+    return head
+
+
+def run(head, B, anchors=20, hw=(64, 64)):
+    ft = synth.make_features(B, bev_h=hw[0], bev_w=hw[1])
+    nz = synth.make_noise(B, num_anchors=anchors)
+    out = head(ft["ego_query"].cuda(), ft["agents_query"].cuda(), ft["bev_feature"].cuda(), noise=nz.cuda())
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy() for k, v in out.items()}
+
+
+def cmp(tag, a, b):
+    d = {k: float(np.abs(a[k].astype(np.float64) - b[k].astype(np.float64)).max()) for k in ("trajectory_modes", "trajectory_scores")}
+    d["mode_agree"] = float((a["mode_idx"] == b["mode_idx"]).mean())
+    d["finite"] = bool(np.isfinite(a["trajectory_modes"]).all())
+    print(tag, json.dumps(d), flush=True)
+
+
+def main():
+    what = sys.argv[1] if len(sys.argv) > 1 else "parity"
+    if what == "parity":
+        for B in (30, 64, 256):
+            f = run(make(1), B)
+            u = run(make(0), B)
+            cmp(f"fused_vs_unfused_B{B}", f, u)
+            z = np.load(os.path.join(ROOT, "tests", "golden", "default_b256.npz"))
+            ref = {k: z[k][:B] for k in ("trajectory_modes", "trajectory_scores", "mode_idx")}
+            cmp(f"fused_vs_golden_B{B}", f, ref)
+            cmp(f"unfused_vs_golden_B{B}", u, ref)
+        f = run(make(1, 4, 64, 3), 2, 64, (128, 128))
+        z = np.load(os.path.join(ROOT, "tests", "golden", "stress_b2.npz"))
+        cmp("fused_stress_vs_golden", f, {k: z[k] for k in ("trajectory_modes", "trajectory_scores", "mode_idx")})
+    elif what == "time":
+        B = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+        for chain in (1, 0):
+            head = make(chain)
+            g = torch.Generator(device="cuda").manual_seed(3000)
+            ego = torch.randn(B, 1, 256, device="cuda", generator=g)
+            agents = torch.randn(B, 30, 256, device="cuda", generator=g)
+            bev = torch.randn(B, 256, 64, 64, device="cuda", generator=g)
+            noise = torch.randn(B, 20, 8, 2, device="cuda", generator=g)
+            for _ in range(3):
+                head(ego, agents, bev, noise=noise)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                head(ego, agents, bev, noise=noise)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            head.set_profiling(True)
+            head(ego, agents, bev, noise=noise)
+            prof = head.stage_profile()
+            head.set_profiling(False)
+            print(json.dumps({"chain": chain, "B": B, "ms": ms, "scenes_per_s": B / ms * 1e3,
+                              "launches": head.last_launch_count(),
+                              "stage_ms": {k: round(v["ms"], 3) for k, v in prof.items()}}), flush=True)
+            del head
+
+
+if __name__ == "__main__":
+    main()
