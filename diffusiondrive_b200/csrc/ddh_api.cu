@@ -24,7 +24,6 @@
 #include "../../include/ddh.h"
 #include "kernels.h"
 #include "kernels_chain.h"
-#include "kernels_res.h"
 #include "kernels_res2.h"
 
 using namespace ddh;
@@ -115,22 +114,8 @@ struct ddh_handle {
   void* hs_bev = nullptr;
   long long* hs_idx = nullptr;
 
-  // small-batch latency engine (B <= kLatMaxB, bf16-packed weights): fp32 activations
-  int lat_enabled = 1;
-  std::vector<void*> owned_lat;
-  float *lt_emb = nullptr, *lt_e1 = nullptr, *lt_kv = nullptr, *lt_ego = nullptr, *lt_spart = nullptr,
-        *lt_x1 = nullptr, *lt_o = nullptr, *lt_y2 = nullptr, *lt_h = nullptr, *lt_y3 = nullptr,
-        *lt_r1 = nullptr, *lt_c1 = nullptr, *lt_r2 = nullptr, *lt_c2 = nullptr;
-  unsigned int* lt_bar = nullptr;              // [S*L] grid-barrier counters of the cooperative layer kernel
-  int lat_coop = 0;                            // env DDH_LAT_COOP=1: decoder layer as one cooperative kernel (measured slower)
-  // resident engine (kernels_res.cu): the whole forward of <= RES_MAX_B scenes in one launch
-  int res_enabled = 1;                         // env DDH_RES=0 disables it
-  bool res_ok = false;
-  std::vector<void*> owned_res;
-  ResConsts* res_consts = nullptr;             // device copy
-  ResConsts res_host;                          // host mirror (workspace pointers for the debug taps)
   // anchor-resident engine (kernels_res2.cu): same one-launch contract, activations stay on-chip
-  int res_mode = 2;                            // env DDH_RES: 0 off, 1 first-generation engine, 2 anchor-resident
+  int res_mode = 2;                            // option "resident_engine": 2 on, 0 off
   bool res2_ok = false;
   std::vector<void*> owned_res2;
   R2Consts* res2_consts = nullptr;
@@ -151,9 +136,12 @@ struct ddh_handle {
   std::vector<std::pair<int, int>> ev_spans;   // (stage id, index of the begin event)
   int ev_used = 0;
   int* conv_rows = nullptr;                    // [S*L] unique value_proj rows per conv launch
-  unsigned long long* need_rows = nullptr;     // [B] BEV rows (+halo) the coming conv call reads
-  unsigned long long* done_rows = nullptr;     // [B] BEV rows already converted to NHWC
-  int lazy_layout = 1;                         // convert BEV rows on demand (H <= 64, NCHW input)
+  unsigned int* need_seg = nullptr;            // [B][seg_nw32] BEV segments (+halo) the coming conv call reads
+  unsigned int* done_seg = nullptr;            // [B][seg_nw32] BEV segments already converted to NHWC
+  int lazy_layout = 1;                         // convert BEV segments on demand (NCHW input)
+  int seg_px = 8;                              // pixels per segment (8 or 16), option "layout_segment"
+  int seg_nw32 = 0;                            // 32-bit mask words per scene (0: map too large, eager layout)
+  int chain_timeline = -1;                     // option "chain_timeline": index of the chain launch to stamp
   bool profiling_eager = false;
   bool debug_taps = false;                     // env DDH_DEBUG_TAPS=1: keep fp32 copies of x2/x3 in bf16 mode
   long long* dbg = nullptr;                    // timeline stamps (DDH_TIMELINE builds)
@@ -375,8 +363,13 @@ int ensure_ws(ddh_handle* h, int B) {
   WS(h->upix, (size_t)B * h->rcap);
   WS(h->nuniq, B);
   WS(h->conv_rows, s.num_layers * s.num_steps);
-  WS(h->need_rows, B);
-  WS(h->done_rows, B);
+  {
+    const int spr = s.bev_w / h->seg_px;
+    const int bits = s.bev_h * spr;
+    h->seg_nw32 = (s.bev_w % h->seg_px == 0 && bits <= 2048) ? (bits + 31) / 32 : 0;
+  }
+  WS(h->need_seg, (size_t)B * std::max(h->seg_nw32, 1));
+  WS(h->done_seg, (size_t)B * std::max(h->seg_nw32, 1));
   WS(h->dbg, 1024);
   WS(h->ent_slot, M * s.num_poses * 4);
   WS(h->ent_w, M * s.num_poses * 4);
@@ -423,7 +416,7 @@ void register_taps(ddh_handle* h, int B) {
   t["upix"] = {h->upix, (size_t)B * h->rcap * 4};
   t["nuniq"] = {h->nuniq, (size_t)B * 4};
   t["dbg"] = {h->dbg, (size_t)1024 * 8};
-  t["done_rows"] = {h->done_rows, (size_t)B * 8};
+  t["done_seg"] = {h->done_seg, (size_t)B * std::max(h->seg_nw32, 1) * 4};
   t["conv_rows"] = {h->conv_rows, (size_t)s.num_layers * s.num_steps * 4};
   t["ent_slot"] = {h->ent_slot, M * s.num_poses * 4 * 4};
   t["ent_w"] = {h->ent_w, M * s.num_poses * 4 * 4};
@@ -441,128 +434,6 @@ void register_taps(ddh_handle* h, int B) {
   else t["bev_nhwc"] = {h->bev_nhwc, (size_t)B * s.bev_h * s.bev_w * s.bev_channels * 4};
 }
 
-// Resident engine (kernels_res.cu): tensor maps with per-CTA slice boxes, the weight item order,
-// constants and exchange buffers.  Leaves h->res_ok false when the shape is outside the engine's
-// limits or a 16-CTA cluster cannot be scheduled (the other engines then serve small batches).
-int build_res(ddh_handle* h, cudaStream_t st) {
-  h->res_ok = false;
-  free_all(h->owned_res);
-  h->res_consts = nullptr;
-  const ddh_shape& s = h->shp;
-  const int A = s.num_anchors, P = s.num_poses, Na = s.num_agents, F = s.d_ffn, L = s.num_layers,
-            S = s.num_steps, H = s.bev_h, W = s.bev_w;
-  if (!h->res_enabled || h->precision != DDH_PREC_BF16) return DDH_OK;
-  if (A > 32 || A * P > 256 || P != 8 || Na > 31 || F > 1024 || F % 128 || s.num_heads != 8 ||
-      H * W > 4096 || H > 64 || W % 32 || L > RES_MAX_L || S > RES_MAX_S || s.bev_channels != 256)
-    return DDH_OK;
-  if (res_engine_init() != 0) return DDH_OK;
-  auto& o = h->owned_res;
-  int rc;
-#define TRY(x) do { rc = (x); if (rc) return rc; } while (0)
-  ResMaps* maps_dev = nullptr;
-  TRY(dev_alloc(h, o, &maps_dev, 1));
-  TRY(dev_alloc(h, o, &h->res_consts, 1));
-  std::vector<ResMaps> maps_host(1);
-  ResMaps& M = maps_host[0];
-  ResConsts& C = h->res_host;
-  memset(&C, 0, sizeof C);
-  const int NC = D / RES_CL;
-  TRY(encode_wmap(h, &M.enc0, h->enc0.w16, D, 64 * P, NC));
-  TRY(encode_wmap(h, &M.enc3, h->enc3.w16, D, D, NC));
-  for (int l = 0; l < L; ++l) {
-    PackedLayer& pl = h->layers[l];
-    // [Wkv ; Wego] stacked: one streamed item per layer for the hoisted K|V and ego projections
-    __nv_bfloat16* kvego;
-    float* b_kvego;
-    TRY(dev_alloc(h, o, &kvego, (size_t)3 * D * D));
-    TRY(dev_alloc(h, o, &b_kvego, (size_t)3 * D));
-    CU_TRY(h, cudaMemcpyAsync(kvego, pl.kv.w16, (size_t)2 * D * D * 2, cudaMemcpyDeviceToDevice, st));
-    CU_TRY(h, cudaMemcpyAsync(kvego + (size_t)2 * D * D, pl.ego.w16, (size_t)D * D * 2, cudaMemcpyDeviceToDevice, st));
-    CU_TRY(h, cudaMemcpyAsync(b_kvego, pl.kv.bias, (size_t)2 * D * 4, cudaMemcpyDeviceToDevice, st));
-    CU_TRY(h, cudaMemcpyAsync(b_kvego + 2 * D, pl.ego.bias, (size_t)D * 4, cudaMemcpyDeviceToDevice, st));
-    TRY(encode_wmap(h, &M.layer[l][RM_KVEGO], kvego, 3 * D, D, 3 * D / RES_CL));
-    TRY(encode_wmap(h, &M.layer[l][RM_BEV_OUT], pl.bev_out.w16, D, D, NC));
-    TRY(encode_wmap(h, &M.layer[l][RM_Q], pl.q.w16, D, D, 32));
-    TRY(encode_wmap(h, &M.layer[l][RM_ATTN_OUT], pl.attn_out.w16, D, D, NC));
-    TRY(encode_wmap(h, &M.layer[l][RM_FFN0], pl.ffn0.w16, F, D, F / RES_CL));
-    TRY(encode_wmap(h, &M.layer[l][RM_FFN2], pl.ffn2.w16, D, F, NC));
-    TRY(encode_wmap(h, &M.layer[l][RM_REG0], pl.reg0.w16, D, D, NC));
-    TRY(encode_wmap(h, &M.layer[l][RM_REG2], pl.reg2.w16, D, D, NC));
-    TRY(encode_wmap(h, &M.layer[l][RM_CLS0], pl.cls0.w16, D, D, NC));
-    TRY(encode_wmap(h, &M.layer[l][RM_CLS3], pl.cls3.w16, D, D, NC));
-    TRY(encode_wmap(h, &M.layer[l][RM_CONV], pl.conv.w16, D, pl.conv.K, D / (RES_CL / 2)));
-    ResLayerC& lc = C.layer[l];
-    lc.b_kvego = b_kvego; lc.b_bev_out = pl.bev_out.bias; lc.b_q = pl.q.bias;
-    lc.b_attn_out = pl.attn_out.bias; lc.b_ffn0 = pl.ffn0.bias; lc.b_ffn2 = pl.ffn2.bias;
-    lc.b_reg0 = pl.reg0.bias; lc.b_reg2 = pl.reg2.bias; lc.b_cls0 = pl.cls0.bias;
-    lc.b_cls3 = pl.cls3.bias; lc.b_conv = pl.conv.bias;
-    lc.attw_w = pl.attw_w; lc.attw_b = pl.attw_b;
-    lc.norm1_g = pl.norm1_g; lc.norm1_b = pl.norm1_b; lc.norm2_g = pl.norm2_g; lc.norm2_b = pl.norm2_b;
-    lc.norm3_g = pl.norm3_g; lc.norm3_b = pl.norm3_b;
-    lc.cls_ln2_g = pl.cls_ln2_g; lc.cls_ln2_b = pl.cls_ln2_b;
-    lc.cls_ln5_g = pl.cls_ln5_g; lc.cls_ln5_b = pl.cls_ln5_b;
-    lc.cls6_w = pl.cls6_w; lc.cls6_b = pl.cls6_b; lc.reg4_w = pl.reg4_w; lc.reg4_b = pl.reg4_b;
-    lc.conv_map = &maps_dev->layer[l][RM_CONV];
-  }
-  C.b_enc0 = h->enc0.bias; C.b_enc3 = h->enc3.bias; C.enc_ln_g = h->enc_ln_g; C.enc_ln_b = h->enc_ln_b;
-  C.anchors = h->anchors; C.dim_t = h->dim_t; C.film = h->film;
-  C.A = A; C.P = P; C.Na = Na; C.F = F; C.L = L; C.S = S; C.H = H; C.W = W; C.heads = s.num_heads;
-  C.rcap = (int)std::min((size_t)A * P * 4, (size_t)H * W);
-  C.tiles_max = (C.rcap + 127) / 128;
-  C.oc = OdoConsts{s.lidar_max_x, s.lidar_max_y};
-  const float ac_tr = h->ac[s.trunc_timestep];
-  C.sa_tr = sqrtf(ac_tr); C.sb_tr = sqrtf(1.0f - ac_tr);
-  for (int si = 0; si < S; ++si) {
-    const int t = h->roll[si], prev = t - 1;
-    const float ac_t = h->ac[t], ac_p = prev >= 0 ? h->ac[prev] : 1.0f;
-    C.dc[si] = DdimCoef{sqrtf(ac_t), sqrtf(1.0f - ac_t), sqrtf(ac_p), sqrtf(1.0f - ac_p)};
-  }
-  // weight items in the order the kernel's stages consume them
-  int n = 0;
-  auto item = [&](const CUtensorMap* m, int rows, int K, int n_total) {
-    C.items[n].map = m; C.items[n].rows = (unsigned short)rows;
-    C.items[n].kchunks = (unsigned short)(K / 64); C.items[n].n_total = n_total;
-    ++n;
-  };
-  for (int l = 0; l < L; ++l) item(&maps_dev->layer[l][RM_KVEGO], 3 * D / RES_CL, D, 3 * D);
-  for (int si = 0; si < S; ++si) {
-    item(&maps_dev->enc0, NC, 64 * P, D);
-    item(&maps_dev->enc3, NC, D, D);
-    for (int l = 0; l < L; ++l) {
-      const bool want_cls = (si == S - 1) && (l == L - 1);
-      item(&maps_dev->layer[l][RM_BEV_OUT], NC, D, D);
-      item(&maps_dev->layer[l][RM_Q], 32, D, D);
-      item(&maps_dev->layer[l][RM_ATTN_OUT], NC, D, D);
-      item(&maps_dev->layer[l][RM_FFN0], F / RES_CL, D, F);
-      item(&maps_dev->layer[l][RM_FFN2], NC, F, D);
-      item(&maps_dev->layer[l][RM_REG0], NC, D, D);
-      if (want_cls) item(&maps_dev->layer[l][RM_CLS0], NC, D, D);
-      item(&maps_dev->layer[l][RM_REG2], NC, D, D);
-      if (want_cls) item(&maps_dev->layer[l][RM_CLS3], NC, D, D);
-    }
-  }
-  C.n_items = n;
-  // exchange buffers
-  const size_t MB = (size_t)RES_MAX_B * A;
-  TRY(dev_alloc(h, o, &C.emb16, MB * 64 * P)); TRY(dev_alloc(h, o, &C.o16, MB * D));
-  TRY(dev_alloc(h, o, &C.h16, MB * F)); TRY(dev_alloc(h, o, &C.r1_16, MB * D));
-  TRY(dev_alloc(h, o, &C.e1, MB * D)); TRY(dev_alloc(h, o, &C.q0, MB * D));
-  TRY(dev_alloc(h, o, &C.spart, MB * D * C.tiles_max));
-  TRY(dev_alloc(h, o, &C.x1, MB * D)); TRY(dev_alloc(h, o, &C.y2, MB * D));
-  TRY(dev_alloc(h, o, &C.y3, MB * D)); TRY(dev_alloc(h, o, &C.c1, MB * D));
-  TRY(dev_alloc(h, o, &C.r2, MB * D)); TRY(dev_alloc(h, o, &C.c2, MB * D));
-  TRY(dev_alloc(h, o, &C.regraw, MB * 3 * P));
-  TRY(dev_alloc(h, o, &C.kv, (size_t)RES_MAX_B * L * Na * 2 * D));
-  TRY(dev_alloc(h, o, &C.egov, (size_t)RES_MAX_B * L * D));
-  TRY(dev_alloc(h, o, &C.bev_nhwc, (size_t)RES_MAX_B * H * W * D));
-#undef TRY
-  CU_TRY(h, cudaMemcpyAsync(maps_dev, &M, sizeof(ResMaps), cudaMemcpyHostToDevice, st));
-  CU_TRY(h, cudaMemcpyAsync(h->res_consts, &C, sizeof(ResConsts), cudaMemcpyHostToDevice, st));
-  CU_TRY(h, cudaStreamSynchronize(st));   // maps_host is a local
-  h->res_ok = true;
-  return DDH_OK;
-}
-
 // Anchor-resident engine (kernels_res2.cu): full-matrix tensor maps (box 64 k x 128 rows), the
 // static stage schedule its TMA / MMA threads walk, constants and the L2 exchange buffers.
 int build_res2(ddh_handle* h, cudaStream_t st) {
@@ -577,7 +448,7 @@ int build_res2(ddh_handle* h, cudaStream_t st) {
       H * W > 4096 || H > 64 || W % 32 || L > 2 || S > RES_MAX_S || s.bev_channels != 256)
     return DDH_OK;
   if (const int why = res2_engine_init()) {
-    if (getenv("DDH_VERBOSE")) fprintf(stderr, "ddh: anchor-resident engine unavailable (init step %d)\n", why);
+    (void)why;
     return DDH_OK;
   }
   auto& o = h->owned_res2;
@@ -744,13 +615,6 @@ int ddh_create(const ddh_shape* s, ddh_handle** out) {
 #undef REQUIRE
   ddh_handle* h = new ddh_handle();
   h->shp = *s;
-  if (const char* e = getenv("DDH_TIMELINE_GEMM")) h->tl_gemm = atoi(e);
-  if (const char* e = getenv("DDH_LAZY_LAYOUT")) h->lazy_layout = atoi(e);
-  if (const char* e = getenv("DDH_LAT")) h->lat_enabled = atoi(e);
-  if (const char* e = getenv("DDH_LAT_COOP")) h->lat_coop = atoi(e);
-  if (const char* e = getenv("DDH_RES")) { h->res_mode = atoi(e); h->res_enabled = (h->res_mode == 1); }
-  else h->res_enabled = 0;
-  if (const char* e = getenv("DDH_DEBUG_TAPS")) h->debug_taps = atoi(e) != 0;
   default_alphas_cumprod(h->ac);
   make_roll(s->num_steps, h->roll);
   *out = h;
@@ -762,8 +626,6 @@ void ddh_destroy(ddh_handle* h) {
   free_all(h->owned_w);
   free_all(h->owned_ws);
   free_all(h->owned_host);
-  free_all(h->owned_lat);
-  free_all(h->owned_res);
   free_all(h->owned_res2);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   for (cudaEvent_t e : h->sync_events) cudaEventDestroy(e);
@@ -912,8 +774,6 @@ int ddh_pack_weights(ddh_handle* h, const ddh_weight_ptrs* w, int precision, voi
   }
 #undef TRY
   CU_TRY(h, cudaGetLastError());
-  rc = build_res(h, st);
-  if (rc) return rc;
   rc = build_res2(h, st);
   if (rc) return rc;
   h->packed = true;
@@ -965,209 +825,6 @@ View make_view(const ddh_handle* h, int s0) {
   const size_t bev_elt = h->precision == DDH_PREC_BF16 ? 2 : 4;
   v.bev_nhwc = h->bev_nhwc ? (unsigned char*)h->bev_nhwc + z * s.bev_h * s.bev_w * s.bev_channels * bev_elt : nullptr;
   return v;
-}
-
-// forward_test (:578-641) for the `B` scenes starting at scene `s0` of a call of `Btot` scenes,
-// all launches on `st`.  `layout_done` (optional) is recorded right after the BEV layout pass.
-constexpr int kLatMaxB = 2;
-
-int ensure_lat_ws(ddh_handle* h) {
-  if (h->lt_emb) return DDH_OK;
-  const ddh_shape& s = h->shp;
-  const size_t M = (size_t)kLatMaxB * s.num_anchors, F = s.d_ffn, L = s.num_layers;
-  const size_t tiles = (h->rcap + 127) / 128;
-  auto& o = h->owned_lat;
-  int rc;
-#define LW(ptr, count) do { rc = dev_alloc(h, o, &(ptr), (size_t)(count)); if (rc) return rc; } while (0)
-  LW(h->lt_emb, M * 64 * s.num_poses); LW(h->lt_e1, M * D);
-  LW(h->lt_kv, L * kLatMaxB * s.num_agents * 2 * D); LW(h->lt_ego, L * kLatMaxB * D);
-  LW(h->lt_spart, tiles * M * D);
-  LW(h->lt_x1, M * D); LW(h->lt_o, M * D); LW(h->lt_y2, M * D); LW(h->lt_h, M * F);
-  LW(h->lt_y3, M * D); LW(h->lt_r1, M * D); LW(h->lt_c1, M * D); LW(h->lt_r2, M * D);
-  LW(h->lt_c2, M * D);
-  LW(h->lt_bar, (size_t)s.num_layers * s.num_steps);
-#undef LW
-  return DDH_OK;
-}
-
-// forward_test for one or two scenes on the small-batch engine (kernels_lat.cu + lat_conv_kernel):
-// same algebra as forward_range, fp32 activations, LayerNorm applied by the consumer.
-int forward_small(ddh_handle* h, const float* ego, const float* agents, const void* bev,
-                  int bev_dtype, int bev_layout, const float* noise, float* out_traj,
-                  float* out_modes, float* out_scores, int64_t* out_mode_idx, int B,
-                  cudaStream_t st) {
-  int rc = ensure_lat_ws(h);
-  if (rc) return rc;
-  const ddh_shape& s = h->shp;
-  const int A = s.num_anchors, P = s.num_poses, Na = s.num_agents, L = s.num_layers, S = s.num_steps;
-  const int M = B * A, HW = s.bev_h * s.bev_w;
-  const void* bevn = bev;
-  const bool lazy = bev_layout == DDH_NCHW && h->lazy_layout && s.bev_h <= 64;
-  { ProfSpan ps(h, ST_BEV, st);
-  if (bev_layout == DDH_NCHW) {
-    if (lazy) {
-      CU_TRY(h, cudaMemsetAsync(h->done_rows, 0, (size_t)B * 8, st));
-    } else {
-      launch_bev_to_nhwc(bev, bev_dtype, h->bev_nhwc, DDH_BF16, B, s.bev_channels, HW, st);
-      h->launches++;
-    }
-    bevn = h->bev_nhwc;
-  } else if (bev_dtype != DDH_BF16) {
-    launch_cast_f32_bf16(reinterpret_cast<const float*>(bev),
-                         reinterpret_cast<__nv_bfloat16*>(h->bev_nhwc),
-                         (size_t)B * HW * s.bev_channels, st);
-    h->launches++;
-    bevn = h->bev_nhwc;
-  }
-  }
-  auto lin = [&](const PackedLinear& Lw, const float* Ain, int Mrows, float* out, int relu,
-                 const float* res) {
-    LatLinearArgs a;
-    a.A = Ain; a.M = Mrows; a.K = Lw.K; a.N = Lw.N; a.W = Lw.w16; a.bias = Lw.bias; a.relu = relu;
-    a.res = res; a.out = out; a.ldo = Lw.N;
-    return a;
-  };
-  { ProfSpan ps(h, ST_HOIST, st);
-  LatLinearArgs sets[4];
-  int nset = 0;
-  for (int l = 0; l < L; ++l) {
-    sets[nset++] = lin(h->layers[l].kv, agents, B * Na, h->lt_kv + (size_t)l * kLatMaxB * Na * 2 * D, 0, nullptr);
-    sets[nset++] = lin(h->layers[l].ego, ego, B, h->lt_ego + (size_t)l * kLatMaxB * D, 0, nullptr);
-    if (nset == 4 || l == L - 1) {
-      launch_lat_linear_multi(sets, nset, st);
-      h->launches++;
-      nset = 0;
-    }
-  }
-  }
-  const float ac_tr = h->ac[s.trunc_timestep];
-  { ProfSpan ps(h, ST_INIT, st);
-  launch_init_img(h->anchors, noise, h->img, B, A * P, sqrtf(ac_tr), sqrtf(1.0f - ac_tr), st);
-  h->launches++; }
-  float* modes = out_modes ? out_modes : h->modes_buf;
-  float* scores = out_scores ? out_scores : h->scores_buf;
-  OdoConsts oc{s.lidar_max_x, s.lidar_max_y};
-  const int part_stride = kLatMaxB * A * D;
-  bool coop = h->lat_coop && !h->profiling && s.d_ffn <= 1024;
-  if (coop) CU_TRY(h, cudaMemsetAsync(h->lt_bar, 0, (size_t)L * S * 4, st));
-  for (int si = 0; si < S; ++si) {
-    { ProfSpan ps(h, ST_EMBED, st);
-    launch_embed(h->img, h->pts, h->lt_emb, nullptr, M, P, h->dim_t, st);
-    launch_lat_linear(lin(h->enc0, h->lt_emb, M, h->lt_e1, 1, nullptr), st);
-    LatLinearArgs a = lin(h->enc3, h->lt_e1, M, h->q0_32, 0, nullptr);
-    a.prologue = 1; a.ln1_g = h->enc_ln_g; a.ln1_b = h->enc_ln_b;
-    launch_lat_linear(a, st);
-    h->launches += 3; }
-    for (int l = 0; l < L; ++l) {
-      const PackedLayer& pl = h->layers[l];
-      const bool last_layer = (l == L - 1), last_step = (si == S - 1);
-      { ProfSpan ps(h, ST_PLAN, st);
-      launch_plan(h->q0_32, pl.attw_w, pl.attw_b, h->pts, h->upix, h->nuniq, h->ent_slot, h->ent_w,
-                  h->conv_rows + si * L + l, lazy ? h->need_rows : nullptr, h->done_rows, B, A, P,
-                  s.bev_h, s.bev_w, h->rcap, oc, st);
-      h->launches++; }
-      if (lazy) {
-        ProfSpan ps(h, ST_BEV, st);
-        launch_bev_rows_to_nhwc(bev, bev_dtype, h->bev_nhwc, DDH_BF16, h->need_rows, B,
-                                s.bev_channels, s.bev_h, s.bev_w, st);
-        h->launches++;
-      }
-      { ProfSpan ps(h, ST_CONV, st);
-      GemmParams gp;
-      gp.K = pl.conv.K;
-      gp.bev = bevn; gp.upix = h->upix; gp.nuniq = h->nuniq; gp.rcap = h->rcap;
-      gp.H = s.bev_h; gp.W_ = s.bev_w; gp.C = s.bev_channels;
-      gp.epi.bias = pl.conv.bias;
-      gp.ent_slot = h->ent_slot; gp.ent_w = h->ent_w; gp.n_anchor = A; gp.ent_per_anchor = P * 4;
-      launch_lat_conv(gp, pl.conv.map64, h->lt_spart, part_stride, B, st);
-      h->launches++; }
-      DdimCoef dc{0.f, 1.f, 1.f, 0.f};
-      const int do_ddim = (last_layer && !last_step) ? 1 : 0;
-      if (do_ddim) {
-        const int t = h->roll[si], prev = t - 1;
-        const float ac_t = h->ac[t], ac_p = prev >= 0 ? h->ac[prev] : 1.0f;
-        dc.sqrt_ac_t = sqrtf(ac_t); dc.sqrt_1m_ac_t = sqrtf(1.0f - ac_t);
-        dc.sqrt_ac_prev = sqrtf(ac_p); dc.sqrt_1m_ac_prev = sqrtf(1.0f - ac_p);
-      }
-      if (coop) {   // the eight post-conv stages as one cooperative kernel
-        LatLayerArgs g;
-        g.bev_out = lin(pl.bev_out, h->lt_spart, M, h->lt_x1, 0, h->q0_32);
-        g.bev_out.prologue = 4; g.bev_out.nuniq = h->nuniq; g.bev_out.rows_per_group = A;
-        g.bev_out.part_stride = part_stride; g.bev_out.max_parts = (h->rcap + 127) / 128;
-        g.wq = pl.q.w16; g.bq = pl.q.bias; g.kv = h->lt_kv + (size_t)l * kLatMaxB * Na * 2 * D;
-        g.o = h->lt_o; g.A = A; g.Na = Na; g.B = B; g.heads = s.num_heads;
-        g.attn_out = lin(pl.attn_out, h->lt_o, M, h->lt_y2, 0, h->lt_x1);
-        g.ffn0 = lin(pl.ffn0, h->lt_y2, M, h->lt_h, 1, nullptr);
-        g.ffn0.prologue = 2; g.ffn0.ln1_g = pl.norm1_g; g.ffn0.ln1_b = pl.norm1_b;
-        g.ffn0.rowvec = h->lt_ego + (size_t)l * kLatMaxB * D; g.ffn0.rows_per_group = A;
-        g.ffn0.ln2_g = pl.norm2_g; g.ffn0.ln2_b = pl.norm2_b;
-        g.ffn2 = lin(pl.ffn2, h->lt_h, M, h->lt_y3, 0, nullptr);
-        g.reg0 = lin(pl.reg0, h->lt_y3, M, h->lt_r1, 1, nullptr);
-        g.reg0.prologue = 3; g.reg0.ln1_g = pl.norm3_g; g.reg0.ln1_b = pl.norm3_b;
-        g.reg0.film = h->film + ((size_t)si * L + l) * 2 * D;
-        g.cls0 = lin(pl.cls0, h->lt_y3, M, h->lt_c1, 1, nullptr);
-        g.cls0.prologue = 3; g.cls0.ln1_g = pl.norm3_g; g.cls0.ln1_b = pl.norm3_b; g.cls0.film = g.reg0.film;
-        g.reg2 = lin(pl.reg2, h->lt_r1, M, h->lt_r2, 1, nullptr);
-        g.cls3 = lin(pl.cls3, h->lt_c1, M, h->lt_c2, 1, nullptr);
-        g.cls3.prologue = 1; g.cls3.ln1_g = pl.cls_ln2_g; g.cls3.ln1_b = pl.cls_ln2_b;
-        g.w4 = pl.reg4_w; g.b4 = pl.reg4_b; g.pts = h->pts; g.img = h->img; g.modes = modes;
-        g.M = M; g.P = P; g.do_ddim = do_ddim; g.dc = dc;
-        g.want_cls = (last_layer && last_step) ? 1 : 0;
-        g.cls_g = pl.cls_ln5_g; g.cls_b = pl.cls_ln5_b; g.w6 = pl.cls6_w; g.b6 = pl.cls6_b;
-        g.scores = scores; g.bar = h->lt_bar + si * L + l; g.dbg = h->dbg;
-        if (launch_lat_layer(g, st) == 0) {
-          h->launches++;
-          continue;
-        }
-        coop = false;   // cooperative launch unavailable: fall through to per-stage launches
-      }
-      { ProfSpan ps(h, ST_GEMM, st);
-      LatLinearArgs a = lin(pl.bev_out, h->lt_spart, M, h->lt_x1, 0, h->q0_32);
-      a.prologue = 4; a.nuniq = h->nuniq; a.rows_per_group = A; a.part_stride = part_stride;
-      a.max_parts = (h->rcap + 127) / 128;
-      launch_lat_linear(a, st);
-      h->launches++; }
-      { ProfSpan ps(h, ST_ATTN, st);
-      launch_lat_qattn(h->lt_x1, pl.q.w16, pl.q.bias, h->lt_kv + (size_t)l * kLatMaxB * Na * 2 * D,
-                       h->lt_o, B, A, Na, s.num_heads, st);
-      h->launches++; }
-      { ProfSpan ps(h, ST_GEMM, st);
-      launch_lat_linear(lin(pl.attn_out, h->lt_o, M, h->lt_y2, 0, h->lt_x1), st);
-      LatLinearArgs a = lin(pl.ffn0, h->lt_y2, M, h->lt_h, 1, nullptr);
-      a.prologue = 2; a.ln1_g = pl.norm1_g; a.ln1_b = pl.norm1_b;
-      a.rowvec = h->lt_ego + (size_t)l * kLatMaxB * D; a.rows_per_group = A;
-      a.ln2_g = pl.norm2_g; a.ln2_b = pl.norm2_b;
-      launch_lat_linear(a, st);
-      launch_lat_linear(lin(pl.ffn2, h->lt_h, M, h->lt_y3, 0, nullptr), st);
-      const bool want_cls = last_layer && last_step;
-      LatLinearArgs duo[2];
-      duo[0] = lin(pl.reg0, h->lt_y3, M, h->lt_r1, 1, nullptr);
-      duo[0].prologue = 3; duo[0].ln1_g = pl.norm3_g; duo[0].ln1_b = pl.norm3_b;
-      duo[0].film = h->film + ((size_t)si * L + l) * 2 * D;
-      duo[1] = lin(pl.cls0, h->lt_y3, M, h->lt_c1, 1, nullptr);
-      duo[1].prologue = 3; duo[1].ln1_g = pl.norm3_g; duo[1].ln1_b = pl.norm3_b;
-      duo[1].film = duo[0].film;
-      launch_lat_linear_multi(duo, want_cls ? 2 : 1, st);
-      duo[0] = lin(pl.reg2, h->lt_r1, M, h->lt_r2, 1, nullptr);
-      duo[1] = lin(pl.cls3, h->lt_c1, M, h->lt_c2, 1, nullptr);
-      duo[1].prologue = 1; duo[1].ln1_g = pl.cls_ln2_g; duo[1].ln1_b = pl.cls_ln2_b;
-      launch_lat_linear_multi(duo, want_cls ? 2 : 1, st);
-      h->launches += 5;
-      if (want_cls) {
-        launch_lat_cls(h->lt_c2, pl.cls_ln5_g, pl.cls_ln5_b, pl.cls6_w, pl.cls6_b, scores, M, st);
-        h->launches += 1;
-      }
-      }
-      { ProfSpan ps(h, ST_REG, st);
-      launch_lat_reg_finish(h->lt_r2, pl.reg4_w, pl.reg4_b, h->pts, h->img, modes, M, P, do_ddim, dc, st);
-      h->launches++; }
-    }
-  }
-  { ProfSpan ps(h, ST_SELECT, st);
-  launch_select(scores, modes, out_traj, reinterpret_cast<long long*>(out_mode_idx), B, A, P, st);
-  h->launches++; }
-  CU_TRY(h, cudaGetLastError());
-  return DDH_OK;
 }
 
 
@@ -1320,11 +977,12 @@ int forward_fused(ddh_handle* h, const float* ego, const float* agents, const vo
   if (h->chain_prog.empty()) { rc = build_chain_programs(h); if (rc) return rc; }
   const int spt = h->chain_spt, n_tiles = (B + spt - 1) / spt;
   const void* bevn = bev;
-  const bool lazy = bev_layout == DDH_NCHW && h->lazy_layout && s.bev_h <= 64 && !h->profiling_eager;
+  const bool lazy = bev_layout == DDH_NCHW && h->lazy_layout && h->seg_nw32 > 0 && !h->profiling_eager;
+  const int seg_shift = h->seg_px == 16 ? 4 : 3;
   { ProfSpan ps(h, ST_BEV, st);
   if (bev_layout == DDH_NCHW) {
     if (lazy) {
-      CU_TRY(h, cudaMemsetAsync(h->done_rows, 0, (size_t)B * 8, st));
+      CU_TRY(h, cudaMemsetAsync(h->done_seg, 0, (size_t)B * h->seg_nw32 * 4, st));
     } else {
       launch_bev_to_nhwc(bev, bev_dtype, h->bev_nhwc, DDH_BF16, B, s.bev_channels, HW, st);
       h->launches++;
@@ -1372,13 +1030,13 @@ int forward_fused(ddh_handle* h, const float* ego, const float* agents, const vo
       const PackedLayer& pl = h->layers[l];
       { ProfSpan ps(h, ST_PLAN, st);
       launch_plan(h->q0t, pl.attw_w, pl.attw_b, h->pts, h->upix, h->nuniq, h->ent_slot, h->ent_w,
-                  h->conv_rows + si * L + l, lazy ? h->need_rows : nullptr, h->done_rows, B, A, P,
-                  s.bev_h, s.bev_w, h->rcap, oc, st, spt);
+                  h->conv_rows + si * L + l, lazy ? h->need_seg : nullptr, h->done_seg, seg_shift,
+                  h->seg_nw32, B, A, P, s.bev_h, s.bev_w, h->rcap, oc, st, spt);
       h->launches++; }
       if (lazy) {
         ProfSpan ps(h, ST_BEV, st);
-        launch_bev_rows_to_nhwc(bev, bev_dtype, h->bev_nhwc, DDH_BF16, h->need_rows, B, s.bev_channels,
-                                s.bev_h, s.bev_w, st);
+        launch_bev_segs_to_nhwc(bev, bev_dtype, h->bev_nhwc, DDH_BF16, h->need_seg, h->seg_nw32,
+                                h->seg_px, B, s.bev_channels, s.bev_h, s.bev_w, st);
         h->launches++;
       }
       { ProfSpan ps(h, ST_CONV, st);
@@ -1395,6 +1053,7 @@ int forward_fused(ddh_handle* h, const float* ego, const float* agents, const vo
       { ProfSpan ps(h, ST_GEMM, st);
       ChainArgs& a = h->chain_prog[S + (size_t)si * L + l];
       fill(a);
+      if (h->chain_timeline == si * L + l) a.dbg = h->dbg;
       a.kv16 = h->kv16 + (size_t)l * B * Na * CH_KV_LD;
       a.egov = h->egov + (size_t)l * B * D;
       launch_chain(a, st);
@@ -1428,13 +1087,14 @@ int forward_range(ddh_handle* h, const float* ego, const float* agents, const vo
   // ---- BEV map -> NHWC in the engine's operand type.  NCHW input with H <= 64: rows are
   // converted on demand before each conv call (only rows a conv will read); otherwise up front.
   const void* bevn = bev;
-  const bool lazy = bev_layout == DDH_NCHW && h->lazy_layout && s.bev_h <= 64 && !h->profiling_eager;
-  unsigned long long* need_rows = lazy ? h->need_rows + s0 : nullptr;
-  unsigned long long* done_rows = lazy ? h->done_rows + s0 : nullptr;
+  const bool lazy = bev_layout == DDH_NCHW && h->lazy_layout && h->seg_nw32 > 0 && !h->profiling_eager;
+  const int seg_shift = h->seg_px == 16 ? 4 : 3;
+  unsigned int* need_seg = lazy ? h->need_seg + (size_t)s0 * h->seg_nw32 : nullptr;
+  unsigned int* done_seg = lazy ? h->done_seg + (size_t)s0 * h->seg_nw32 : nullptr;
   { ProfSpan ps(h, ST_BEV, st);
   if (bev_layout == DDH_NCHW) {
     if (lazy) {
-      CU_TRY(h, cudaMemsetAsync(done_rows, 0, (size_t)B * 8, st));
+      CU_TRY(h, cudaMemsetAsync(done_seg, 0, (size_t)B * h->seg_nw32 * 4, st));
     } else {
       launch_bev_to_nhwc(bev, bev_dtype, v.bev_nhwc, want_dtype, B, s.bev_channels, HW, st);
       h->launches++;
@@ -1506,12 +1166,12 @@ int forward_range(ddh_handle* h, const float* ego, const float* agents, const vo
       // -- cross_bev_attention (modules/blocks.py:88-129)
       { ProfSpan ps(h, ST_PLAN, st);
       launch_plan(v.q0_32, pl.attw_w, pl.attw_b, v.pts, v.upix, v.nuniq, v.ent_slot,
-                  v.ent_w, h->conv_rows + si * L + l, need_rows, done_rows, B, A, P, s.bev_h,
-                  s.bev_w, h->rcap, oc, st); }
+                  v.ent_w, h->conv_rows + si * L + l, need_seg, done_seg, seg_shift, h->seg_nw32, B, A,
+                  P, s.bev_h, s.bev_w, h->rcap, oc, st); }
       if (lazy) {
         ProfSpan ps(h, ST_BEV, st);
-        launch_bev_rows_to_nhwc(bev, bev_dtype, v.bev_nhwc, want_dtype, need_rows, B,
-                                s.bev_channels, s.bev_h, s.bev_w, st);
+        launch_bev_segs_to_nhwc(bev, bev_dtype, v.bev_nhwc, want_dtype, need_seg, h->seg_nw32, h->seg_px,
+                                B, s.bev_channels, s.bev_h, s.bev_w, st);
         h->launches++;
         if (layout_event_pending) {   // the next chunk may start: its layout runs under our conv
           CU_TRY(h, cudaEventRecord(layout_done, st));
@@ -1560,7 +1220,8 @@ int forward_range(ddh_handle* h, const float* ego, const float* agents, const vo
       launch_attn_core(v.qh32, v.kv32 + (size_t)l * Btot * Na * 2 * D, v.o32, v.o16, B, A, Na,
                        s.num_heads, st); }
       h->launches++;
-      ProfSpan* chain = new ProfSpan(h, ST_GEMM, st);
+      {
+      ProfSpan chain(h, ST_GEMM, st);
       {
         RowEpi e;
         e.res = v.x1_32; e.ldres = D;
@@ -1603,7 +1264,7 @@ int forward_range(ddh_handle* h, const float* ego, const float* agents, const vo
         e2.out_f32 = v.r2_32; e2.ldo32 = D;
         run_gemm(h, pl.reg2, v.r1_32, v.r1_16, D, M, e2, st);
       }
-      delete chain;
+      }
       DdimCoef dc{0.f, 1.f, 1.f, 0.f};
       const int do_ddim = (last_layer && !last_step) ? 1 : 0;
       if (do_ddim) {
@@ -1686,40 +1347,6 @@ int ddh_forward(ddh_handle* h, const float* ego, const float* agents, const void
     return DDH_OK;
   }
   CU_TRY(h, cudaMemsetAsync(h->conv_rows, 0, (size_t)s.num_layers * s.num_steps * 4, st));
-  if (h->res_ok && !h->profiling && h->precision == DDH_PREC_BF16 && B <= RES_MAX_B) {
-    ResCall call;
-    call.ego = ego; call.agents = agents; call.bev = bev; call.bev_dtype = bev_dtype == DDH_BF16 ? 1 : 0;
-    call.bev_nhwc_bf16 = (bev_layout == DDH_NHWC) ? 1 : 0;
-    h->launches = 0;
-    if (bev_layout == DDH_NHWC && bev_dtype != DDH_BF16) {   // NHWC fp32: one cast pass in front
-      launch_cast_f32_bf16(reinterpret_cast<const float*>(bev), h->res_host.bev_nhwc,
-                           (size_t)B * s.bev_h * s.bev_w * s.bev_channels, st);
-      call.bev = h->res_host.bev_nhwc;
-      call.bev_dtype = 1;
-      h->launches++;
-    }
-    call.noise = noise; call.out_traj = out_traj;
-    call.out_modes = out_modes ? out_modes : h->modes_buf;
-    call.out_scores = out_scores ? out_scores : h->scores_buf;
-    call.out_mode_idx = reinterpret_cast<long long*>(out_mode_idx);
-    call.dbg = h->debug_taps ? h->dbg : nullptr;
-    const int e = launch_res_forward(h->res_consts, call, B, st);
-    if (e) return fail(h, DDH_ERR_CUDA, std::string("res_forward launch: ") + cudaGetErrorString((cudaError_t)e));
-    h->launches++;
-    const ResConsts& R = h->res_host;
-    const size_t MA = (size_t)B * s.num_anchors;
-    h->taps["res_q0"] = {R.q0, MA * D * 4}; h->taps["res_x1"] = {R.x1, MA * D * 4};
-    h->taps["res_y2"] = {R.y2, MA * D * 4}; h->taps["res_y3"] = {R.y3, MA * D * 4};
-    h->taps["res_r2"] = {R.r2, MA * D * 4}; h->taps["res_e1"] = {R.e1, MA * D * 4};
-    h->taps["res_spart"] = {R.spart, MA * D * 4 * R.tiles_max};
-    h->taps["res_kv"] = {R.kv, (size_t)B * s.num_layers * s.num_agents * 2 * D * 4};
-    h->taps["res_egov"] = {R.egov, (size_t)B * s.num_layers * D * 4};
-    h->taps["res_regraw"] = {R.regraw, MA * 3 * s.num_poses * 4};
-    h->taps["res_emb16"] = {R.emb16, MA * 64 * s.num_poses * 2};
-    h->taps["res_o16"] = {R.o16, MA * D * 2}; h->taps["res_h16"] = {R.h16, MA * s.d_ffn * 2};
-    CU_TRY(h, cudaGetLastError());
-    return DDH_OK;
-  }
   if (h->chain_ok && h->precision == DDH_PREC_BF16) {
     rc = forward_fused(h, ego, agents, bev, bev_dtype, bev_layout, noise, out_traj, out_modes, out_scores,
                        out_mode_idx, B, st);
@@ -1729,16 +1356,6 @@ int ddh_forward(ddh_handle* h, const float* ego, const float* agents, const void
   }
   // Scene chunks on two streams: scenes are independent, so chunk c+1's HBM-bound layout pass
   // runs under chunk c's tensor-bound conv/GEMMs.  Chunk c starts once layout(c-1) is done.
-  if (h->lat_enabled && h->precision == DDH_PREC_BF16 && B <= kLatMaxB &&
-      s.d_ffn <= 1024 &&
-      (size_t)B * s.num_anchors * std::max(s.d_ffn, 64 * s.num_poses) * 4 <= 200 * 1024 &&
-      (size_t)B * s.num_agents * 256 * 4 <= 200 * 1024) {
-    rc = forward_small(h, ego, agents, bev, bev_dtype, bev_layout, noise, out_traj, out_modes,
-                       out_scores, out_mode_idx, B, st);
-    if (rc) return rc;
-    CU_TRY(h, cudaGetLastError());
-    return DDH_OK;
-  }
   int nchunk = 1;
   if (!h->profiling && h->chunks > 1 && B >= h->chunks * h->min_chunk_scenes) nchunk = h->chunks;
   if (nchunk == 1) {
@@ -1837,8 +1454,12 @@ int ddh_set_option(ddh_handle* h, const char* name, int value) {
   if (n == "lazy_layout") h->lazy_layout = value;
   else if (n == "chain_engine") { repack = h->chain_enabled != value; h->chain_enabled = value; }
   else if (n == "resident_engine") { repack = h->res_mode != (value ? 2 : 0); h->res_mode = value ? 2 : 0; }
-  else if (n == "small_batch_engine") h->lat_enabled = value;
   else if (n == "debug_taps") h->debug_taps = value != 0;
+  else if (n == "chain_timeline") h->chain_timeline = value;
+  else if (n == "layout_segment") {
+    if (value != 8 && value != 16) return fail(h, DDH_ERR_BAD_ARG, "ddh_set_option: layout_segment must be 8 or 16");
+    if (h->seg_px != value) { h->seg_px = value; cudaDeviceSynchronize(); free_all(h->owned_ws); h->cap_B = 0; h->chain_prog.clear(); }
+  }
   else if (n == "timeline_gemm") h->tl_gemm = value;
   else return fail(h, DDH_ERR_BAD_ARG, "ddh_set_option: unknown option " + n);
   if (repack) h->packed = false;   // engine selection is fixed at pack time: the caller packs again

@@ -31,10 +31,11 @@ void launch_embed(const float* img, float* pts, float* emb32, __nv_bfloat16* emb
                   const float* dim_t_dev, cudaStream_t st);
 void launch_plan(const float* q0, const float* attw_w, const float* attw_b, const float* pts,
                  int* upix, int* nuniq, int* ent_slot, float* ent_w, int* rows_total,
-                 unsigned long long* need_rows, unsigned long long* done_rows, int B, int A, int P,
-                 int H, int W, int rcap, OdoConsts oc, cudaStream_t st, int q0_spt = 0);
-void launch_bev_rows_to_nhwc(const void* src, int src_dtype, void* dst, int dst_dtype,
-                             const unsigned long long* todo, int B, int C, int H, int W,
+                 unsigned int* need_seg, unsigned int* done_seg, int seg_shift, int nw32, int B, int A,
+                 int P, int H, int W, int rcap, OdoConsts oc, cudaStream_t st, int q0_spt = 0);
+// on-demand layout conversion of the BEV segments (seg = 8 or 16 pixels of a row) flagged in todo
+void launch_bev_segs_to_nhwc(const void* src, int src_dtype, void* dst, int dst_dtype,
+                             const unsigned int* todo, int nw32, int seg, int B, int C, int H, int W,
                              cudaStream_t st);
 void launch_combine(const float* V, const int* ent_slot, const float* ent_w, float* s32,
                     __nv_bfloat16* s16, int B, int A, int P, int rcap, cudaStream_t st);
@@ -54,41 +55,6 @@ void launch_matvec(const float* W, const float* x, const float* b, float* y, int
                    int act_in_mish, cudaStream_t st);
 void launch_time_sinemb(float* emb, int dim, int timestep, cudaStream_t st);
 void launch_pack_hilo(const float* w, __nv_bfloat16* dst, int n_out, int k, cudaStream_t st);
-
-// ---- kernels_lat.cu (small-batch latency engine: column-split fp32 x bf16 linears) ---------
-struct LatLinearArgs {
-  const float* A = nullptr; int M = 0, K = 0, N = 0;
-  const __nv_bfloat16* W = nullptr; const float* bias = nullptr; int relu = 0;
-  const float* res = nullptr; float* out = nullptr; int ldo = 0;
-  int prologue = 0;   // 0 none, 1 LN, 2 LN+ego+LN, 3 LN+FiLM, 4 sum of conv partials
-  const float *ln1_g = nullptr, *ln1_b = nullptr, *rowvec = nullptr; int rows_per_group = 1;
-  const float *ln2_g = nullptr, *ln2_b = nullptr, *film = nullptr;
-  const int* nuniq = nullptr; int part_stride = 0; int max_parts = 1;
-};
-void launch_lat_linear(const LatLinearArgs& a, cudaStream_t st);
-void launch_lat_linear_multi(const LatLinearArgs* args, int n, cudaStream_t st);   // n <= 4
-void launch_lat_reg_finish(const float* r2, const float* w4, const float* b4, float* pts, float* img,
-                           float* modes, int M, int P, int do_ddim, DdimCoef dc, cudaStream_t st);
-void launch_lat_qattn(const float* x1, const __nv_bfloat16* wq, const float* bq, const float* kv,
-                      float* o, int B, int A, int Na, int heads, cudaStream_t st);
-void launch_lat_cls(const float* c2, const float* g, const float* b, const float* w6,
-                    const float* b6, float* scores, int M, cudaStream_t st);
-// one decoder layer after the conv as one cooperative kernel (grid barriers between stages);
-// returns 0 on success, non-zero if cooperative launch is unavailable / failed
-struct LatLayerArgs {
-  LatLinearArgs bev_out, attn_out, ffn0, ffn2, reg0, cls0, reg2, cls3;
-  const __nv_bfloat16* wq = nullptr; const float* bq = nullptr; const float* kv = nullptr;
-  float* o = nullptr; int A = 0, Na = 0, B = 0, heads = 0;
-  const float* w4 = nullptr; const float* b4 = nullptr; float* pts = nullptr; float* img = nullptr;
-  float* modes = nullptr; int M = 0, P = 0, do_ddim = 0; DdimCoef dc{0.f, 1.f, 1.f, 0.f};
-  int want_cls = 0; const float *cls_g = nullptr, *cls_b = nullptr, *w6 = nullptr, *b6 = nullptr;
-  float* scores = nullptr; unsigned int* bar = nullptr; long long* dbg = nullptr;
-};
-int launch_lat_layer(const LatLayerArgs& a, cudaStream_t st);
-// tile/column-split tcgen05 conv for one or two scenes: grid (4 column quarters, row tiles, B);
-// writes per-tile partial sums S_part[tile][B*A][256] (fp32)
-void launch_lat_conv(const GemmParams& p, const CUtensorMap& wmap64, float* s_part,
-                     int part_stride, int B, cudaStream_t st);
 
 // ---- kernels_tc.cu (tcgen05 / TMEM / TMA engine) ----------------------------------
 // W is described by a TMA tensor map over a bf16 [N_total][K] matrix (box 64 x 256,

@@ -53,12 +53,20 @@ constexpr int CH_SMEM = OFF_BAR + 256 + 1024;
 static_assert(CH_SMEM <= 227 * 1024, "shared memory budget");
 
 // barrier slots (8 bytes each) behind OFF_BAR
+// Timeline (args.dbg != nullptr): CTA 0 stamps clock64 during its second tile.  Layout (long long):
+//   [0] tile start (compute warp 0), [1 + 4 j + {0,1,2}] compute step j: wait begin, accumulators ready,
+//   epilogue done; [128 + 2 j + {0,1}] MMA thread step j: operands ready, all MMAs issued.
+#define CH_STAMP(cond, idx) do { if (args.dbg && blockIdx.x == 0 && (cond)) args.dbg[idx] = clock64(); } while (0)
+
 constexpr int B_WFULL = 0, B_WEMPTY = 2, B_AREADY = 4, B_ACC = 5, B_SFULL = 6, B_SAFREE = 7,
               B_KVGO = 8, B_KVFULL = 9, B_KVEMPTY = 11, B_TMEM = 14;
 
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void l2_prefetch(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -225,6 +233,7 @@ __global__ void __launch_bounds__(CH_NT, 1) chain_kernel(const __grid_constant__
             mbar_wait(BAR(B_AREADY), (uint32_t)(it * n_steps + j) & 1u);
             if (st.flags & CS_WAIT_S) mbar_wait(BAR(B_SFULL), (uint32_t)it & 1u);
             tc_fence_after();
+            CH_STAMP(it == 1, 128 + 2 * j);
             for (int o = 0; o < st.nops; ++o) {
               const ChainOp op = args.ops[st.op0 + o];
               const uint32_t idesc = (op.flags & CO_N64) ? idesc64 : idesc256;
@@ -242,6 +251,7 @@ __global__ void __launch_bounds__(CH_NT, 1) chain_kernel(const __grid_constant__
               }
             }
             umma_commit(BAR(B_ACC));
+            CH_STAMP(it == 1, 128 + 2 * j + 1);
             if (st.flags & CS_KVGO) umma_commit(BAR(B_KVGO));
             if (st.flags & CS_SAFREE) umma_commit(BAR(B_SAFREE));
           }
@@ -252,7 +262,17 @@ __global__ void __launch_bounds__(CH_NT, 1) chain_kernel(const __grid_constant__
       if (lane == 0 && args.mode == 0) {
         int it = 0;
         uint32_t n = 0;   // running scene count (K|V slot ring)
+        // K|V (HBM-resident: 128 MB per layer at 4096 scenes) and q0 of a tile are pulled into L2 one
+        // tile ahead, so that the attention's bulk copies and the x1 epilogue see L2 latency
+        auto prefetch_tile = [&](int tile) {
+          if (tile >= args.n_tiles) return;
+          const int nsc = min(spt, B - tile * spt);
+          l2_prefetch(args.kv16 + (size_t)tile * spt * Na * CH_KV_LD, (uint32_t)(nsc * kv_bytes));
+          l2_prefetch(args.q0t + (size_t)tile * 128 * D, 128 * D * 4);
+        };
+        prefetch_tile(blockIdx.x);
         for (int tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x, ++it) {
+          prefetch_tile(tile + gridDim.x);
           if (it > 0) mbar_wait(BAR(B_SAFREE), (uint32_t)(it - 1) & 1u);
           mbar_arrive_expect_tx(BAR(B_SFULL), 4 * CH_CHUNK);
           for (int kc = 0; kc < 4; ++kc)
@@ -288,6 +308,7 @@ __global__ void __launch_bounds__(CH_NT, 1) chain_kernel(const __grid_constant__
       const long long m = (long long)tile * rows_per_tile + r;
       const bool valid = r < rows_per_tile && m < M;
       const long long mc = valid ? m : 0;    // clamped row for loads of rows that do not exist
+      CH_STAMP(it == 1 && threadIdx.x == 0, 0);
       if (args.mode == 1) {
         // ---- clamp + denorm_odo (:601-602), sine embedding (modules/blocks.py:22-40) of poses
         // 4 hf .. 4 hf + 3 of row r, written as chunks p of the A operand (64 features per pose:
@@ -342,9 +363,14 @@ __global__ void __launch_bounds__(CH_NT, 1) chain_kernel(const __grid_constant__
               uint32_t w[4];
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
+                // one Cody-Waite step to [-pi, pi], then the SFU: |error| ~1e-6 for arguments up to
+                // ~360 rad, far below the bf16 rounding of the operand (the fp32 engine keeps sinf/cosf)
                 const float arg = __fdiv_rn(num, dimt[2 * (4 * u + k)]);
+                const float kk = rintf(arg * 0.15915494309189535f);
+                float red = fmaf(-kk, 6.28318548202514648f, arg);
+                red = fmaf(-kk, -1.7484556000744883e-7f, red);
                 float sn, cs;
-                sincosf(arg, &sn, &cs);
+                __sincosf(red, &sn, &cs);
                 w[k] = pack_bf16(sn, cs);
               }
               *reinterpret_cast<uint4*>(base + (((half * 4 + u) ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -358,9 +384,11 @@ __global__ void __launch_bounds__(CH_NT, 1) chain_kernel(const __grid_constant__
 
       for (int j = 0; j < n_steps; ++j) {
         const ChainStep st = args.steps[j];
+        CH_STAMP(it == 1 && threadIdx.x == 0, 1 + 4 * j);
         mbar_wait(BAR(B_ACC), acc_par);
         acc_par ^= 1u;
         tc_fence_after();
+        CH_STAMP(it == 1 && threadIdx.x == 0, 1 + 4 * j + 1);
         const uint32_t tacc = c.trow + st.acc_col + cbase;
         uint8_t* dst = sm + st.dst_chunk * CH_CHUNK;
         switch (st.epi) {
@@ -368,11 +396,16 @@ __global__ void __launch_bounds__(CH_NT, 1) chain_kernel(const __grid_constant__
             const float* b0 = par + st.par[0] + cbase;
             const float* b1 = par + st.par[1] + cbase;
             const float4* q0 = reinterpret_cast<const float4*>(args.q0t) + ((size_t)tile * 64 + hf * 32) * 128 + r;
-#pragma unroll 1
-            for (int b = 0; b < 4; ++b) {
-              float4 qv[8];
+            float4 qv[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) qv[i] = __ldg(q0 + (size_t)(b * 8 + i) * 128);
+            for (int i = 0; i < 8; ++i) qv[i] = __ldg(q0 + (size_t)i * 128);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              float4 qn[8];
+              if (b < 3) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) qn[i] = __ldg(q0 + (size_t)((b + 1) * 8 + i) * 128);
+              }
               float v[32];
               ld_blk(tacc + b * 32, v);
               add_par(b0 + b * 32, v);
@@ -383,6 +416,10 @@ __global__ void __launch_bounds__(CH_NT, 1) chain_kernel(const __grid_constant__
               st_operand(dst, r, cbase + b * 32, v);
               add_par(b1 + b * 32, v);
               st_blk(tacc + b * 32, v);
+              if (b < 3) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) qv[i] = qn[i];
+              }
             }
             tmem_st_wait();
           } break;
@@ -399,7 +436,9 @@ __global__ void __launch_bounds__(CH_NT, 1) chain_kernel(const __grid_constant__
               for (int i = 0; i < 32; ++i) v[i] *= qscale;
               st_operand(dst, r, cbase + b * 32, v);
             }
+            CH_STAMP(it == 1 && threadIdx.x == 0, 64);
             named_bar_sync(1, CH_NCT);
+            CH_STAMP(it == 1 && threadIdx.x == 0, 65);
             // ---- attention: warp = head, one scene at a time (K|V staged by the loader in region 0),
             // 16 query rows per m-tile; the output overwrites q in place (same warp, same columns)
             const int h = warp;
@@ -411,7 +450,9 @@ __global__ void __launch_bounds__(CH_NT, 1) chain_kernel(const __grid_constant__
             const int MT = (A + 15) >> 4;
             for (int sl = 0; sl < nsc; ++sl, ++kvn) {
               const uint32_t slot = kvn % kv_nslot, use = kvn / kv_nslot;
+              CH_STAMP(it == 1 && threadIdx.x == 0, 66 + 3 * sl);
               mbar_wait(BAR(B_KVFULL + slot), use & 1u);
+              CH_STAMP(it == 1 && threadIdx.x == 0, 67 + 3 * sl);
               const uint32_t kvb = sm_addr + slot * (2 * CH_CHUNK);
               uint32_t kf[4][4], vf[4][4];
 #pragma unroll
@@ -496,6 +537,7 @@ __global__ void __launch_bounds__(CH_NT, 1) chain_kernel(const __grid_constant__
                 }
               }
               __syncwarp();
+              CH_STAMP(it == 1 && threadIdx.x == 0, 68 + 3 * sl);
               if (lane == 0) mbar_arrive(BAR(B_KVEMPTY + slot));
             }
           } break;
@@ -508,18 +550,23 @@ __global__ void __launch_bounds__(CH_NT, 1) chain_kernel(const __grid_constant__
 #pragma unroll
               for (int i = 0; i < 32; ++i) { s += v[i]; qq = fmaf(v[i], v[i], qq); }
             }
-            float mean, rstd;
-            ln_stats(c, s, qq, mean, rstd);
             const long long scene = mc / A;
             const float4* ego = reinterpret_cast<const float4*>(args.egov + scene * D + cbase);
+            float4 ev[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ev[i] = __ldg(ego + i);
+            float mean, rstd;
+            ln_stats(c, s, qq, mean, rstd);
             const float* g1 = par + st.par[0] + cbase;
             const float* be1 = par + st.par[1] + cbase;
             s = 0.f; qq = 0.f;
-#pragma unroll 1
-            for (int b = 0; b < 4; ++b) {
-              float4 ev[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) ev[i] = __ldg(ego + b * 8 + i);
+            for (int b = 0; b < 4; ++b) {
+              float4 en[8];
+              if (b < 3) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) en[i] = __ldg(ego + (b + 1) * 8 + i);
+              }
               float v[32];
               ld_blk(tacc + b * 32, v);
 #pragma unroll
@@ -534,6 +581,10 @@ __global__ void __launch_bounds__(CH_NT, 1) chain_kernel(const __grid_constant__
 #pragma unroll
               for (int i = 0; i < 32; ++i) { s += v[i]; qq = fmaf(v[i], v[i], qq); }
               st_blk(tacc + b * 32, v);
+              if (b < 3) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) ev[i] = en[i];
+              }
             }
             tmem_st_wait();
             ln_stats(c, s, qq, mean, rstd);
@@ -639,61 +690,67 @@ __global__ void __launch_bounds__(CH_NT, 1) chain_kernel(const __grid_constant__
             }
           } break;
           case CE_TAIL: {
-            // reg = r2 . W4^T as [hi | lo] bf16 halves of W4 (columns 0-31 / 32-63), fp32 sum
-            if (hf == 0) {
-              float hi[32], lo[32];
-              ld_blk(c.trow + st.acc_col, hi);
-              ld_blk(c.trow + st.acc_col + 32, lo);
-              if (valid) {
-                const float* b4 = par + st.par[0];
-                float pt[16], im[16];
+            // reg = r2 . W4^T as [hi | lo] bf16 halves of W4 (columns 0-31 / 32-63), fp32 sum; the
+            // thread of column half hf finishes poses 4 hf .. 4 hf + 3 (outputs 12 hf .. 12 hf + 11)
+            float hi[32], lo[32];
+            ld_blk(c.trow + st.acc_col, hi);
+            ld_blk(c.trow + st.acc_col + 32, lo);
+            if (valid) {
+              const float* b4 = par + st.par[0] + 12 * hf;
+              float raw[12];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float4 p4 = *(reinterpret_cast<const float4*>(args.pts + m * 16) + i);
-                  pt[4 * i] = p4.x; pt[4 * i + 1] = p4.y; pt[4 * i + 2] = p4.z; pt[4 * i + 3] = p4.w;
+              for (int o = 0; o < 12; ++o) {
+                float h_ = 0.f, l_ = 0.f;
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {   // compile-time indices: no local-memory arrays
+                  if (hf == k) { h_ = hi[12 * k + o]; l_ = lo[12 * k + o]; }
                 }
-                if (args.do_ddim) {
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    const float4 p4 = *(reinterpret_cast<const float4*>(args.img + m * 16) + i);
-                    im[4 * i] = p4.x; im[4 * i + 1] = p4.y; im[4 * i + 2] = p4.z; im[4 * i + 3] = p4.w;
-                  }
-                }
-                float out[24];
-                const DdimCoef dc = args.dc;
-#pragma unroll
-                for (int o = 0; o < 24; ++o) {
-                  const int p = o / 3, comp = o - p * 3;
-                  const float raw = (hi[o] + lo[o]) + b4[o];
-                  if (comp < 2) {
-                    const float val = __fadd_rn(raw, pt[p * 2 + comp]);
-                    pt[p * 2 + comp] = val;
-                    out[o] = val;
-                    if (args.do_ddim) {
-                      const float x0 = comp ? norm_y(val) : norm_x(val);
-                      const float eps = __fdiv_rn(__fsub_rn(im[p * 2 + comp], __fmul_rn(dc.sqrt_ac_t, x0)), dc.sqrt_1m_ac_t);
-                      const float x0c = fminf(fmaxf(x0, -1.0f), 1.0f);
-                      im[p * 2 + comp] = __fadd_rn(__fmul_rn(dc.sqrt_ac_prev, x0c), __fmul_rn(dc.sqrt_1m_ac_prev, eps));
-                    }
-                  } else {
-                    out[o] = __fmul_rn(tanhf(raw), 3.14159265358979323846f);
-                  }
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                  *(reinterpret_cast<float4*>(args.pts + m * 16) + i) =
-                      make_float4(pt[4 * i], pt[4 * i + 1], pt[4 * i + 2], pt[4 * i + 3]);
-                if (args.do_ddim) {
-#pragma unroll
-                  for (int i = 0; i < 4; ++i)
-                    *(reinterpret_cast<float4*>(args.img + m * 16) + i) =
-                        make_float4(im[4 * i], im[4 * i + 1], im[4 * i + 2], im[4 * i + 3]);
-                }
-#pragma unroll
-                for (int i = 0; i < 6; ++i)
-                  *(reinterpret_cast<float4*>(args.modes + m * 24) + i) =
-                      make_float4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
+                raw[o] = (h_ + l_) + b4[o];
               }
+              float pt[8], im[8];
+              {
+                const float4 p0 = *reinterpret_cast<const float4*>(args.pts + m * 16 + 8 * hf);
+                const float4 p1 = *(reinterpret_cast<const float4*>(args.pts + m * 16 + 8 * hf) + 1);
+                pt[0] = p0.x; pt[1] = p0.y; pt[2] = p0.z; pt[3] = p0.w;
+                pt[4] = p1.x; pt[5] = p1.y; pt[6] = p1.z; pt[7] = p1.w;
+              }
+              if (args.do_ddim) {
+                const float4 p0 = *reinterpret_cast<const float4*>(args.img + m * 16 + 8 * hf);
+                const float4 p1 = *(reinterpret_cast<const float4*>(args.img + m * 16 + 8 * hf) + 1);
+                im[0] = p0.x; im[1] = p0.y; im[2] = p0.z; im[3] = p0.w;
+                im[4] = p1.x; im[5] = p1.y; im[6] = p1.z; im[7] = p1.w;
+              }
+              float out[12];
+              const DdimCoef dc = args.dc;
+#pragma unroll
+              for (int o = 0; o < 12; ++o) {
+                const int p = o / 3, comp = o - p * 3;
+                if (comp < 2) {
+                  const float val = __fadd_rn(raw[o], pt[p * 2 + comp]);
+                  pt[p * 2 + comp] = val;
+                  out[o] = val;
+                  if (args.do_ddim) {
+                    const float x0 = comp ? norm_y(val) : norm_x(val);
+                    const float eps = __fdiv_rn(__fsub_rn(im[p * 2 + comp], __fmul_rn(dc.sqrt_ac_t, x0)), dc.sqrt_1m_ac_t);
+                    const float x0c = fminf(fmaxf(x0, -1.0f), 1.0f);
+                    im[p * 2 + comp] = __fadd_rn(__fmul_rn(dc.sqrt_ac_prev, x0c), __fmul_rn(dc.sqrt_1m_ac_prev, eps));
+                  }
+                } else {
+                  out[o] = __fmul_rn(tanhf(raw[o]), 3.14159265358979323846f);
+                }
+              }
+              float4* pd = reinterpret_cast<float4*>(args.pts + m * 16 + 8 * hf);
+              pd[0] = make_float4(pt[0], pt[1], pt[2], pt[3]);
+              pd[1] = make_float4(pt[4], pt[5], pt[6], pt[7]);
+              if (args.do_ddim) {
+                float4* id = reinterpret_cast<float4*>(args.img + m * 16 + 8 * hf);
+                id[0] = make_float4(im[0], im[1], im[2], im[3]);
+                id[1] = make_float4(im[4], im[5], im[6], im[7]);
+              }
+              float4* md = reinterpret_cast<float4*>(args.modes + m * 24 + 12 * hf);
+              md[0] = make_float4(out[0], out[1], out[2], out[3]);
+              md[1] = make_float4(out[4], out[5], out[6], out[7]);
+              md[2] = make_float4(out[8], out[9], out[10], out[11]);
             }
           } break;
           case CE_Q0: {
@@ -711,6 +768,7 @@ __global__ void __launch_bounds__(CH_NT, 1) chain_kernel(const __grid_constant__
           } break;
           default: break;
         }
+        CH_STAMP(it == 1 && threadIdx.x == 0, 1 + 4 * j + 2);
         if (j + 1 < n_steps) {   // the arrival after a tile's last epilogue is the next tile's first one
           fence_proxy_async();
           tc_fence_before();

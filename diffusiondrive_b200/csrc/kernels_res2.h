@@ -3,9 +3,43 @@
 // TrajectoryHead.forward_test (transfuser_model_v2.py:578-641) in ONE kernel, and the decoder
 // chain of an anchor never leaves the SM that owns it.  See kernels_res2.cu for the design.
 #pragma once
-#include "kernels_res.h"
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "kernels.h"
 
 namespace ddh {
+
+constexpr int RES_CL = 16;        // CTAs per cluster (non-portable size, opt-in)
+constexpr int RES_MAX_L = 4;      // decoder layers
+constexpr int RES_MAX_S = 4;      // denoise steps
+constexpr int RES_MAX_B = 24;     // scenes per call served by the one-launch engines
+
+
+struct ResLayerC {
+  const float *b_kvego, *b_bev_out, *b_q, *b_attn_out, *b_ffn0, *b_ffn2, *b_reg0, *b_reg2, *b_cls0,
+      *b_cls3, *b_conv;
+  const float *attw_w, *attw_b, *norm1_g, *norm1_b, *norm2_g, *norm2_b, *norm3_g, *norm3_b;
+  const float *cls_ln2_g, *cls_ln2_b, *cls_ln5_g, *cls_ln5_b, *cls6_w, *cls6_b, *reg4_w, *reg4_b;
+  const CUtensorMap* conv_map;
+};
+
+
+struct ResCall {
+  const float* ego;       // [B][1][256]
+  const float* agents;    // [B][Na][256]
+  const void* bev;        // NCHW f32/bf16 or NHWC bf16
+  int bev_dtype;          // 0 f32, 1 bf16
+  int bev_nhwc_bf16;      // 1: gather straight from the caller's NHWC bf16 map
+  const float* noise;     // [B][A][P][2]
+  float* out_traj;        // [B][P][3] or null
+  float* out_modes;       // [B][A][P][3]
+  float* out_scores;      // [B][A]
+  long long* out_mode_idx;
+  long long* dbg;         // optional clock64 stamps of cluster 0 / rank 0
+};
+
 
 constexpr int R2_MAX_STAGES = 160;
 

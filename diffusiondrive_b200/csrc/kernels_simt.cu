@@ -254,80 +254,101 @@ static void bev_launch(const void* src, void* dst, int B, int C, int HW, cudaStr
                                                           reinterpret_cast<TO*>(dst), C, HW);
 }
 
-// On-demand variant: converts only the BEV rows the coming conv call reads and that are not
-// converted yet (todo mask written by plan_kernel, which also maintains the done mask), 32 pixels
-// x 256 channels per tile; one CTA per scene at large batch, rows dealt over gridDim.y CTAs at
-// small batch.  Trajectories only ever sample the forward part of the map, so ~45 %
-// of the rows are never touched.  H <= 64.
-template <typename TI, typename TO>
-__global__ void __launch_bounds__(256) bev_rows_to_nhwc_kernel(
-    const TI* __restrict__ src, TO* __restrict__ dst, const unsigned long long* __restrict__ todo_rows,
-    int C, int H, int W) {
-  constexpr int PXT = 32;
-  constexpr int LDW = (sizeof(TO) == 2) ? 129 : 257;
-  extern __shared__ __align__(16) uint32_t tile_u32[];
-  TO* tile = reinterpret_cast<TO*>(tile_u32);
-  constexpr int LDE = LDW * 4 / sizeof(TO);
-  constexpr int G = PXT / 4, CL = 256 / G;
-  const int b = blockIdx.x;
-  const unsigned long long todo = todo_rows[b];   // written by plan_kernel
-  if (!todo) return;
-  const int tid = threadIdx.x, px4 = tid % G, cl = tid / G;
-  const int lane = tid & 31, warp = tid >> 5;
-  const int HW = H * W;
-  constexpr int WORDS = 256 * sizeof(TO) / 4;
-  unsigned long long rest = todo;
-  int idx = 0;
-  while (rest) {
-    const int y = __ffsll((long long)rest) - 1;
-    rest &= rest - 1;
-    if ((idx++ % (int)gridDim.y) != (int)blockIdx.y) continue;   // rows dealt round-robin over y
-    for (int x0 = 0; x0 < W; x0 += PXT) {
-      const int px0 = y * W + x0;
-      const TI* s = src + (size_t)b * C * HW + px0 + px4 * 4;
-      float4 v[256 / CL];
+// On-demand variant: converts only the BEV segments (SEG pixels of one row) the coming conv call
+// reads and that are not converted yet (todo bit mask written by plan_kernel, which also maintains
+// the done mask).  One CTA per scene at large batch (segments dealt over gridDim.y CTAs at small
+// batch), thread = channel: per step two segments are read (SEG*4 contiguous bytes per channel
+// plane), transposed through shared memory and written as SEG x 512-byte pixel lines.
+// Trajectories sample ~250 of 4096 pixels; with 8-pixel segments ~20 % of the map is converted.
+template <typename TI, typename TO, int SEG>
+__global__ void __launch_bounds__(256) bev_segs_to_nhwc_kernel(
+    const TI* __restrict__ src, TO* __restrict__ dst, const unsigned int* __restrict__ todo,
+    int nw32, int C, int H, int W) {
+  constexpr int NSEG = 2;                       // segments per step
+  extern __shared__ __align__(16) unsigned char seg_raw[];
+  TO* tile = reinterpret_cast<TO*>(seg_raw);    // [NSEG * SEG px][256 channels]
+  __shared__ unsigned short list[2048];
+  __shared__ int cnt[65];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int HW = H * W, segs_per_row = W / SEG;
+  unsigned int word = 0;
+  if (tid < nw32) word = todo[(size_t)b * nw32 + tid];
+  if (tid < 64) cnt[tid] = __popc(word);
+  __syncthreads();
+  if (tid < nw32) {
+    int off = 0;
+    for (int i = 0; i < tid; ++i) off += cnt[i];
+    while (word) {
+      const int bit = __ffs((int)word) - 1;
+      word &= word - 1;
+      list[off++] = (unsigned short)(tid * 32 + bit);
+    }
+    if (tid == nw32 - 1) cnt[64] = off;
+  }
+  __syncthreads();
+  const int n = cnt[64];
+  if (n == 0) return;
+  const TI* sb = src + (size_t)b * C * HW + (size_t)tid * HW;
+  TO* db = dst + (size_t)b * HW * C;
+  constexpr int V4_PER_ROW = 256 * sizeof(TO) / 16;   // uint4 per pixel line
+  for (int i = NSEG * blockIdx.y; i < n; i += NSEG * gridDim.y) {
+    const int ns = min(NSEG, n - i);
+    int px0[NSEG];
+    float4 v[NSEG][SEG / 4];
 #pragma unroll
-      for (int i = 0; i < 256 / CL; ++i) v[i] = ld4<TI>(s + (size_t)(i * CL + cl) * HW);
-      __syncthreads();   // previous tile fully written out
+    for (int sgi = 0; sgi < NSEG; ++sgi) {
+      const int sidx = list[min(i + sgi, n - 1)];
+      const int y = sidx / segs_per_row;
+      px0[sgi] = y * W + (sidx - y * segs_per_row) * SEG;
+      if (sgi < ns) {
 #pragma unroll
-      for (int i = 0; i < 256 / CL; ++i) {
-        const int c = i * CL + cl;
-        tile[(px4 * 4 + 0) * LDE + c] = (TO)v[i].x;
-        tile[(px4 * 4 + 1) * LDE + c] = (TO)v[i].y;
-        tile[(px4 * 4 + 2) * LDE + c] = (TO)v[i].z;
-        tile[(px4 * 4 + 3) * LDE + c] = (TO)v[i].w;
+        for (int q = 0; q < SEG / 4; ++q) v[sgi][q] = ld4<TI>(sb + px0[sgi] + 4 * q);
       }
-      __syncthreads();
-      uint32_t* d = reinterpret_cast<uint32_t*>(dst + ((size_t)b * HW + px0) * C);
-      for (int px = warp; px < PXT; px += 8) {
+    }
+    __syncthreads();   // previous step fully written out
 #pragma unroll
-        for (int w = lane; w < WORDS; w += 32) d[(size_t)px * WORDS + w] = tile_u32[px * LDW + w];
+    for (int sgi = 0; sgi < NSEG; ++sgi) {
+      if (sgi < ns) {
+#pragma unroll
+        for (int q = 0; q < SEG / 4; ++q) {
+          TO* t = tile + (size_t)(sgi * SEG + 4 * q) * 256 + tid;
+          t[0] = (TO)v[sgi][q].x; t[256] = (TO)v[sgi][q].y; t[512] = (TO)v[sgi][q].z; t[768] = (TO)v[sgi][q].w;
+        }
       }
+    }
+    __syncthreads();
+    for (int u = tid; u < ns * SEG * V4_PER_ROW; u += 256) {
+      const int row = u / V4_PER_ROW, part = u - row * V4_PER_ROW;
+      const int sgi = row / SEG, px = row - sgi * SEG;
+      reinterpret_cast<uint4*>(db + (size_t)(px0[sgi] + px) * C)[part] =
+          reinterpret_cast<const uint4*>(tile + (size_t)row * 256)[part];
     }
   }
 }
 
 template <typename TI, typename TO>
-static void bev_rows_launch(const void* src, void* dst, const unsigned long long* todo, int B,
-                            int C, int H, int W, cudaStream_t st) {
-  constexpr int LDW = (sizeof(TO) == 2) ? 129 : 257;
-  const int smem = 32 * LDW * 4;
-  int ysplit = 592 / (B > 0 ? B : 1);     // small batches: spread one scene's rows over CTAs
+static void bev_segs_launch(const void* src, void* dst, const unsigned int* todo, int nw32, int seg,
+                            int B, int C, int H, int W, cudaStream_t st) {
+  int ysplit = 592 / (B > 0 ? B : 1);     // small batches: spread one scene's segments over CTAs
   ysplit = ysplit < 1 ? 1 : (ysplit > 32 ? 32 : ysplit);
   dim3 grid(B, ysplit);
-  bev_rows_to_nhwc_kernel<TI, TO><<<grid, 256, smem, st>>>(
-      reinterpret_cast<const TI*>(src), reinterpret_cast<TO*>(dst), todo, C, H, W);
+  if (seg == 8)
+    bev_segs_to_nhwc_kernel<TI, TO, 8><<<grid, 256, 2 * 8 * 256 * sizeof(TO), st>>>(
+        reinterpret_cast<const TI*>(src), reinterpret_cast<TO*>(dst), todo, nw32, C, H, W);
+  else
+    bev_segs_to_nhwc_kernel<TI, TO, 16><<<grid, 256, 2 * 16 * 256 * sizeof(TO), st>>>(
+        reinterpret_cast<const TI*>(src), reinterpret_cast<TO*>(dst), todo, nw32, C, H, W);
 }
 
-void launch_bev_rows_to_nhwc(const void* src, int src_dtype, void* dst, int dst_dtype,
-                             const unsigned long long* todo, int B, int C, int H, int W,
+void launch_bev_segs_to_nhwc(const void* src, int src_dtype, void* dst, int dst_dtype,
+                             const unsigned int* todo, int nw32, int seg, int B, int C, int H, int W,
                              cudaStream_t st) {
-  if (src_dtype == 0 && dst_dtype == 0) bev_rows_launch<float, float>(src, dst, todo, B, C, H, W, st);
+  if (src_dtype == 0 && dst_dtype == 0) bev_segs_launch<float, float>(src, dst, todo, nw32, seg, B, C, H, W, st);
   else if (src_dtype == 0 && dst_dtype == 1)
-    bev_rows_launch<float, __nv_bfloat16>(src, dst, todo, B, C, H, W, st);
+    bev_segs_launch<float, __nv_bfloat16>(src, dst, todo, nw32, seg, B, C, H, W, st);
   else if (src_dtype == 1 && dst_dtype == 1)
-    bev_rows_launch<__nv_bfloat16, __nv_bfloat16>(src, dst, todo, B, C, H, W, st);
-  else bev_rows_launch<__nv_bfloat16, float>(src, dst, todo, B, C, H, W, st);
+    bev_segs_launch<__nv_bfloat16, __nv_bfloat16>(src, dst, todo, nw32, seg, B, C, H, W, st);
+  else bev_segs_launch<__nv_bfloat16, float>(src, dst, todo, nw32, seg, B, C, H, W, st);
 }
 
 void launch_bev_to_nhwc(const void* src, int src_dtype, void* dst, int dst_dtype, int B, int C,
@@ -450,8 +471,9 @@ __global__ void __launch_bounds__(256) plan_kernel(const float* __restrict__ q0,
                                                    int* __restrict__ ent_slot,
                                                    float* __restrict__ ent_w,
                                                    int* __restrict__ rows_total,
-                                                   unsigned long long* __restrict__ need_rows,
-                                                   unsigned long long* __restrict__ done_rows,
+                                                   unsigned int* __restrict__ need_seg,
+                                                   unsigned int* __restrict__ done_seg,
+                                                   int seg_shift, int nw32,
                                                    int A, int P, int H, int W, int rcap,
                                                    OdoConsts oc, int q0_spt) {
   extern __shared__ __align__(16) unsigned char smraw[];
@@ -460,9 +482,9 @@ __global__ void __launch_bounds__(256) plan_kernel(const float* __restrict__ q0,
   float* aw = reinterpret_cast<float*>(smraw + ((HW * 2 + 15) / 16) * 16);  // [A*P]
   __shared__ int warp_tot[8];
   __shared__ int total_s;
-  __shared__ unsigned long long need_s;
+  __shared__ unsigned int seg_s[64];   // BEV segments (2^seg_shift pixels of a row) the conv will read
   const int scene = blockIdx.x;
-  if (threadIdx.x == 0) need_s = 0ull;
+  if (threadIdx.x < 64) seg_s[threadIdx.x] = 0u;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   for (int i = tid; i < HW; i += 256) table[i] = 0;
@@ -530,27 +552,43 @@ __global__ void __launch_bounds__(256) plan_kernel(const float* __restrict__ q0,
   int base = incl - cnt;
   for (int w = 0; w < warp; ++w) base += warp_tot[w];
   if (tid == 255) total_s = base + cnt;
-  unsigned long long need = 0ull;   // rows y-1..y+1 of every unique pixel (H <= 64 only)
+  // segments covering the 3x3 neighbourhood of every unique pixel; a thread's pixels are
+  // consecutive, so it marks [xmin - 1, xmax + 1] of rows y - 1 .. y + 1 once per row it touches
+  const int segs_per_row = W >> seg_shift;
+  int cur_y = -1, xmin = 0, xmax = 0;
+  auto flush = [&]() {
+    if (cur_y < 0 || !need_seg) return;
+    const int s0 = max(xmin - 1, 0) >> seg_shift, s1 = min(xmax + 1, W - 1) >> seg_shift;
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int yy = cur_y + dy;
+      if (yy < 0 || yy >= H) continue;
+      for (int sg = s0; sg <= s1; ++sg) {
+        const int bit = yy * segs_per_row + sg;
+        atomicOr(&seg_s[bit >> 5], 1u << (bit & 31));
+      }
+    }
+  };
   for (int i = beg; i < end; ++i) {
     if (table[i]) {
-      const int yy = i / W;
-      upix[(size_t)scene * rcap + base] = (yy << 16) | (i - yy * W);   // packed (y, x)
+      const int yy = i / W, xx = i - yy * W;
+      upix[(size_t)scene * rcap + base] = (yy << 16) | xx;   // packed (y, x)
       table[i] = (unsigned short)(base + 1);
       ++base;
-      need |= (yy > 0) ? (7ull << (yy - 1)) : 3ull;
+      if (yy != cur_y) { flush(); cur_y = yy; xmin = xx; }
+      xmax = xx;
     }
   }
-  if (need_rows && need) atomicOr(&need_s, need);
+  flush();
   __syncthreads();
   if (tid == 0) {
     nuniq[scene] = total_s;
     if (rows_total) atomicAdd(rows_total, total_s);
-    if (need_rows) {   // rows still to convert for the coming conv call; mark them converted
-      const unsigned long long need = (H >= 64) ? need_s : (need_s & ((1ull << H) - 1ull));
-      const unsigned long long done = done_rows[scene];
-      need_rows[scene] = need & ~done;
-      done_rows[scene] = done | need;
-    }
+  }
+  if (need_seg && tid < nw32) {   // segments still to convert for the coming conv call; mark them converted
+    const unsigned int need = seg_s[tid];
+    const unsigned int done = done_seg[(size_t)scene * nw32 + tid];
+    need_seg[(size_t)scene * nw32 + tid] = need & ~done;
+    done_seg[(size_t)scene * nw32 + tid] = done | need;
   }
   // ---- entries
   for (int e = tid; e < AP; e += 256) {
@@ -573,8 +611,8 @@ __global__ void __launch_bounds__(256) plan_kernel(const float* __restrict__ q0,
 }
 void launch_plan(const float* q0, const float* attw_w, const float* attw_b, const float* pts,
                  int* upix, int* nuniq, int* ent_slot, float* ent_w, int* rows_total,
-                 unsigned long long* need_rows, unsigned long long* done_rows, int B, int A, int P,
-                 int H, int W, int rcap, OdoConsts oc, cudaStream_t st, int q0_spt) {
+                 unsigned int* need_seg, unsigned int* done_seg, int seg_shift, int nw32, int B, int A,
+                 int P, int H, int W, int rcap, OdoConsts oc, cudaStream_t st, int q0_spt) {
   const int smem = ((H * W * 2 + 15) / 16) * 16 + A * P * 4;
   static int cur = 0;
   if (smem > cur) {
@@ -582,7 +620,8 @@ void launch_plan(const float* q0, const float* attw_w, const float* attw_b, cons
     cur = smem;
   }
   plan_kernel<<<B, 256, smem, st>>>(q0, attw_w, attw_b, pts, upix, nuniq, ent_slot, ent_w,
-                                     rows_total, need_rows, done_rows, A, P, H, W, rcap, oc, q0_spt);
+                                     rows_total, need_seg, done_seg, seg_shift, nw32, A, P, H, W,
+                                     rcap, oc, q0_spt);
 }
 
 // ===================================================================================

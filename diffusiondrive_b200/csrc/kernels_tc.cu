@@ -753,220 +753,6 @@ tc_conv_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap) {
   if (warp == 5) tmem_dealloc<NT * D>(tmem_base);
 }
 
-// ===================================================================================
-// Small-batch variant of the conv: one CTA = one 128-row tile of a scene x one 64-column
-// quarter of N, so a single scene spreads over 8+ SMs (the full-width kernel above keeps one
-// scene on one SM, ~45 us).  Each CTA gathers only its tile's patches (590 KB) and streams a
-// quarter of the weights; it combines the rows of ITS tile and writes a partial sum
-// S_part[tile][anchor row][its 64 columns]; the consumer adds the tiles in fixed order.
-// ===================================================================================
-constexpr int L_NS = 4;
-constexpr int L_BTILE = 64 * TC_BK * 2;                  // 8 KiB: 64 weight rows x 64 k
-constexpr int L_STAGE = TC_A_TILE + L_BTILE;             // 24 KiB
-constexpr int L_PIPE = L_NS * L_STAGE;                   // 96 KiB
-constexpr int L_VS_LD = 64 + 4;
-
-__global__ void __launch_bounds__(TC_THREADS, 1)
-lat_conv_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap, float* s_part,
-                int part_stride) {
-  constexpr int NS = L_NS;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
-  uint8_t* sm = smem_raw + pad;
-  const uint32_t sm_addr = raw_addr + pad;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cq = blockIdx.x, tile = blockIdx.y, scene = blockIdx.z;
-  const int nu = p.nuniq[scene];
-  const int row_base = tile * TC_BM;
-  if (row_base >= nu) return;
-  const int rows_valid = min(TC_BM, nu - row_base);
-  const int A = p.n_anchor, n_ent = p.n_anchor * p.ent_per_anchor;
-  const int ent_bytes = ((n_ent * 8 + 15) / 16) * 16;
-  EntPair* ent = reinterpret_cast<EntPair*>(sm + L_PIPE);
-  float* bias_s = reinterpret_cast<float*>(sm + L_PIPE + ent_bytes);   // [64]
-  const TcBars bars{sm_addr + L_PIPE + ent_bytes + 256, NS};
-  volatile uint32_t* tmem_slot =
-      reinterpret_cast<volatile uint32_t*>(sm + L_PIPE + ent_bytes + 256 + (2 * NS + 2) * 8);
-  constexpr int KC = 9 * (D / TC_BK);
-
-  int yx0[8];
-  if (warp < 4) {
-    const int rb0 = threadIdx.x >> 3;
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      yx0[i] = __ldg(p.upix + (size_t)scene * p.rcap + min(row_base + rb0 + 16 * i, nu - 1));
-  }
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < NS; ++s) {
-      mbar_init(bars.full(s), 128 + 1);
-      mbar_init(bars.empty(s), 1);
-    }
-    mbar_init(bars.accum(), 1);
-    fence_barrier_init();
-  }
-  if (warp == 5) tmem_alloc<64>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
-  if (warp == 4 && lane == 0) tma_prefetch_desc(&wmap);
-  if (threadIdx.x >= 128 && threadIdx.x < 144)
-    reinterpret_cast<float4*>(bias_s)[threadIdx.x - 128] =
-        __ldg(reinterpret_cast<const float4*>(p.epi.bias + cq * 64) + (threadIdx.x - 128));
-  {
-    // entry table: 4 (slot, weight) pairs in flight per thread and batch
-    const int* es = p.ent_slot + (size_t)scene * n_ent;
-    const float* ew = p.ent_w + (size_t)scene * n_ent;
-    for (int base = threadIdx.x; base < n_ent; base += TC_THREADS * 4) {
-      EntPair e[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = base + u * TC_THREADS;
-        if (i < n_ent) { e[u].slot = __ldg(es + i); e[u].w = __ldg(ew + i); }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = base + u * TC_THREADS;
-        if (i < n_ent) ent[i] = e[u];
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp < 4) {
-    const int tid = threadIdx.x;
-    const int j = tid & 7, rb = tid >> 3;
-    const __nv_bfloat16* bev = reinterpret_cast<const __nv_bfloat16*>(p.bev) +
-                               (size_t)scene * p.H * p.W_ * D;
-    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
-    int rowoff[8];
-    uint32_t vmask[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = rb + 16 * i;
-      rowoff[i] = 0;
-      vmask[i] = 0;
-      if (r < rows_valid) {
-        const int y = yx0[i] >> 16, x = yx0[i] & 0xffff;
-        rowoff[i] = (y * p.W_ + x) * D + j * 8;
-        const uint32_t xm = (x > 0 ? 1u : 0u) | 2u | (x + 1 < p.W_ ? 4u : 0u);
-        vmask[i] = (y > 0 ? xm : 0u) | (xm << 3) | (y + 1 < p.H ? (xm << 6) : 0u);
-      }
-    }
-    const uint32_t dst_base = rb * 128 + ((j ^ (rb & 7)) << 4);
-    for (int kc = 0; kc < KC; ++kc) {
-      const int s = kc % NS;
-      mbar_wait(bars.empty(s), ((kc / NS) & 1) ^ 1);
-      const uint32_t a_dst = sm_addr + s * L_STAGE + dst_base;
-      const int tap = kc >> 2;
-      const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
-      const int tapoff = (dy * p.W_ + dx) * D + (kc & 3) * TC_BK;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const bool ok = (vmask[i] >> tap) & 1u;
-        const int off = ok ? rowoff[i] + tapoff : 0;
-        cp_async16(a_dst + i * 2048, bev + off, ok ? 16u : 0u);
-      }
-      if (kc == 0) {   // accumulators start at the bias
-#pragma unroll 1
-        for (int cb = 0; cb < 2; ++cb) {
-          uint32_t u[32];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const uint4 t4 = *reinterpret_cast<const uint4*>(bias_s + cb * 32 + 4 * q);
-            u[4 * q + 0] = t4.x; u[4 * q + 1] = t4.y; u[4 * q + 2] = t4.z; u[4 * q + 3] = t4.w;
-          }
-          tmem_st32(trow + cb * 32, u);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-      }
-      cp_async_mbar_arrive_noinc(bars.full(s));
-    }
-    // ---- drain (ReLU) into the staging area, combine this tile's rows
-    mbar_wait(bars.accum(), 0);
-    tc_fence_after();
-    float* Vs = reinterpret_cast<float*>(sm);
-    {
-      float* vrow = Vs + (size_t)(warp * 32 + lane) * L_VS_LD;
-      uint32_t u0[32], u1[32];
-      tmem_ld32(trow, u0);
-      tmem_ld32(trow + 32, u1);
-      tmem_ld_wait();
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        *reinterpret_cast<float4*>(vrow + 4 * q) =
-            make_float4(fmaxf(__uint_as_float(u0[4 * q]), 0.f), fmaxf(__uint_as_float(u0[4 * q + 1]), 0.f),
-                        fmaxf(__uint_as_float(u0[4 * q + 2]), 0.f), fmaxf(__uint_as_float(u0[4 * q + 3]), 0.f));
-        *reinterpret_cast<float4*>(vrow + 32 + 4 * q) =
-            make_float4(fmaxf(__uint_as_float(u1[4 * q]), 0.f), fmaxf(__uint_as_float(u1[4 * q + 1]), 0.f),
-                        fmaxf(__uint_as_float(u1[4 * q + 2]), 0.f), fmaxf(__uint_as_float(u1[4 * q + 3]), 0.f));
-      }
-    }
-    named_bar_sync(1, 128);
-    const int cqd = tid & 15, ag = tid >> 4;
-    for (int a = ag; a < A; a += 8) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      const EntPair* ea = ent + a * p.ent_per_anchor;
-#pragma unroll 8
-      for (int k = 0; k < p.ent_per_anchor; ++k) {
-        const EntPair e = ea[k];
-        const int rr = e.slot - row_base;
-        if (rr >= 0 && rr < rows_valid) {
-          const float4 v = *reinterpret_cast<const float4*>(Vs + (size_t)rr * L_VS_LD + cqd * 4);
-          acc.x = fmaf(e.w, v.x, acc.x); acc.y = fmaf(e.w, v.y, acc.y);
-          acc.z = fmaf(e.w, v.z, acc.z); acc.w = fmaf(e.w, v.w, acc.w);
-        }
-      }
-      *reinterpret_cast<float4*>(s_part + (size_t)tile * part_stride +
-                                 ((size_t)scene * A + a) * D + cq * 64 + cqd * 4) = acc;
-    }
-  } else if (warp == 4) {
-    if (lane == 0) {
-      for (int kc = 0; kc < KC; ++kc) {
-        const int s = kc % NS;
-        mbar_wait(bars.empty(s), ((kc / NS) & 1) ^ 1);
-        mbar_arrive_expect_tx(bars.full(s), L_BTILE);
-        tma_load_2d(sm_addr + s * L_STAGE + TC_A_TILE, &wmap, bars.full(s), kc * TC_BK, cq * 64);
-      }
-    }
-    __syncwarp();
-  } else {
-    if (lane == 0) {
-      // D=f32, A=B=bf16, K-major, M=128, N=64
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-      for (int kc = 0; kc < KC; ++kc) {
-        const int s = kc % NS;
-        mbar_wait(bars.full(s), (kc / NS) & 1);
-        tc_fence_after();
-        const uint32_t a_stage = sm_addr + s * L_STAGE;
-        mma_chunk<1>(a_stage, a_stage + TC_A_TILE, tmem_base, 1, false, idesc, bars.empty(s));
-      }
-      umma_commit(bars.accum());
-    }
-    __syncwarp();
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 5) tmem_dealloc<64>(tmem_base);
-}
-
-int lat_conv_smem_bytes(int A, int ent_per_anchor) {
-  return L_PIPE + ((A * ent_per_anchor * 8 + 15) / 16) * 16 + 256 + TC_BAR_BYTES + 1024;
-}
-
-void launch_lat_conv(const GemmParams& p, const CUtensorMap& wmap64, float* s_part,
-                     int part_stride, int B, cudaStream_t st) {
-  const int smem = lat_conv_smem_bytes(p.n_anchor, p.ent_per_anchor);
-  static int cur = 0;
-  if (smem > cur) {
-    cudaFuncSetAttribute(lat_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cur = smem;
-  }
-  dim3 grid(4, (p.rcap + TC_BM - 1) / TC_BM, B);
-  lat_conv_kernel<<<grid, TC_THREADS, smem, st>>>(p, wmap64, s_part, part_stride);
-}
-
 int tc_engine_init() {
   cudaError_t e;
   e = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM);

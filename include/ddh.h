@@ -198,8 +198,10 @@ DDH_API int ddh_set_concurrency(ddh_handle *h, int chunks, int min_chunk_scenes)
  *   "resident_engine"    1  B <= 24, bf16: whole forward as one launch (kernels_res2.cu)
  *   "chain_engine"       1  bf16: scene-tile chain kernel per decoder-layer call (kernels_chain.cu);
  *                           0: one tcgen05 GEMM launch per Linear (kernels_tc.cu)
- *   "small_batch_engine" 1  B <= 2 multi-launch latency engine when the two above are off
  *   "lazy_layout"        1  NCHW input: convert BEV segments on demand; 0: whole map up front
+ *   "layout_segment"     8  pixels per on-demand layout segment (8 or 16)
+ *   "chain_timeline"    -1  index (step * layers + layer) of the chain launch that stamps clock64
+ *                           into the "dbg" tap (CTA 0, second tile)
  *   "debug_taps"         0  keep fp32 copies of intermediate activations for ddh_debug_copy
  *   "timeline_gemm"     -1  index of the dense GEMM launch to stamp (DDH_TIMELINE builds) */
 DDH_API int ddh_set_option(ddh_handle *h, const char *name, int value);

@@ -159,19 +159,6 @@ def test_bf16_b256_within_tolerance(golden_dir):
     assert rec["mode_agreement_margin_gt_0.05"] == 1.0
 
 
-def _with_env(env, fn):
-    old = {k: os.environ.get(k) for k in env}
-    os.environ.update(env)
-    try:
-        return fn()
-    finally:
-        for k, v in old.items():
-            if v is None:
-                os.environ.pop(k, None)
-            else:
-                os.environ[k] = v
-
-
 def test_small_batch_engine_matches_reference(golden_dir):
     """B <= 24 in bf16 mode runs the group-resident engine (kernels_res2.cu): the whole forward as ONE
     launch on one 16-CTA cluster per scene.  Same tolerance as the tensor path; it is the engine the
@@ -200,25 +187,46 @@ def test_small_batch_engine_matches_reference(golden_dir):
         assert np.array_equal(again[k], outs[8][k])
 
 
-def test_small_batch_engines_agree():
-    """The group-resident engine (default), the first-generation resident engine (DDH_RES=1), the
-    multi-launch small-batch engine (DDH_RES=0) and the full-width tensor engine (DDH_RES=0,
-    DDH_LAT=0) compute the same head with the same bf16-operand numerics."""
+def test_engines_agree():
+    """The group-resident engine (default for B <= 24), the scene-tile chain engine (default above,
+    and for any B when the resident engine is off) and the per-Linear tensor engine compute the same
+    head with the same bf16-operand numerics."""
     B = 2
     base, _, _ = _run(_make_head("bf16")[0], B)
-    for env in ({"DDH_RES": "1"}, {"DDH_RES": "0"}, {"DDH_RES": "0", "DDH_LAT": "0"}):
-        def run():
-            head, _ = _make_head("bf16")
-            out, _, _ = _run(head, B)
-            return out, head.last_launch_count()
-        out, launches = _with_env(env, run)
-        assert launches >= 1
-        if env == {"DDH_RES": "1"}:
-            assert launches == 1
-        else:
-            assert launches > 1
+    for opts, launches_min, launches_max in (({"resident_engine": 0}, 20, 40),
+                                             ({"resident_engine": 0, "chain_engine": 0}, 41, 200)):
+        head, _ = _make_head("bf16")
+        for k, v in opts.items():
+            head.set_option(k, v)
+        out, _, _ = _run(head, B)
+        assert launches_min <= head.last_launch_count() <= launches_max, (opts, head.last_launch_count())
         assert np.abs(out["trajectory_modes"] - base["trajectory_modes"]).max() <= TOL_BF16_M
         assert np.array_equal(out["mode_idx"], base["mode_idx"])
+
+
+def test_chain_engine_matches_per_linear_engine(golden_dir):
+    """Scene-tile chain engine (kernels_chain.cu) against one tcgen05 GEMM launch per Linear: same
+    operands, bf16 agent attention and bf16 regression-tail input in the chain engine only; ragged
+    tile (B not a multiple of 6 scenes per tile), determinism, scene independence."""
+    ref = _load(golden_dir, "default_b256")
+    B = 77
+    chain, _ = _make_head("bf16")
+    plain, _ = _make_head("bf16")
+    plain.set_option("chain_engine", 0)
+    a, _, _ = _run(chain, B)
+    b, _, _ = _run(plain, B)
+    assert plain.last_launch_count() > chain.last_launch_count() > 1
+    assert np.abs(a["trajectory_modes"] - b["trajectory_modes"]).max() <= TOL_BF16_M
+    assert np.abs(a["trajectory_scores"] - b["trajectory_scores"]).max() <= 0.05
+    sub = {k: v[:B] for k, v in ref.items()}
+    rec = _report("bf16_chain_b77_vs_reference", a, sub)
+    assert rec["max_dxy_m"] <= TOL_BF16_M and rec["max_dheading_rad"] <= TOL_BF16_M
+    again, _, _ = _run(chain, B)
+    for k in a:
+        assert np.array_equal(again[k], a[k]), k
+    small, _, _ = _run(chain, 31)
+    for k in a:
+        assert np.array_equal(small[k], a[k][:31]), k
 
 
 def test_resident_engine_nhwc_bf16_input_and_fallback(golden_dir):
@@ -311,23 +319,22 @@ def test_execution_options_do_not_change_results():
             assert torch.equal(out[k], base[k]), (precision, "profiling", k)
         assert prof["conv"]["spans"] == 4 and prof["conv"]["ms"] > 0
         assert sum(v["ms"] for v in prof.values()) > 0
-        # rows converted on demand: a strict subset of the map for forward-driving anchors
-        done = head.debug_tap("done_rows", np.uint64)[:B]
-        rows = np.array([bin(int(x)).count("1") for x in done])
-        assert (rows > 8).all() and (rows < 64).all()
-    os.environ["DDH_LAZY_LAYOUT"] = "0"
-    try:
-        for precision in ("fp32", "bf16"):
-            eager, _ = _make_head(precision)
-            lazy_ref, _ = _make_head(precision)
-            a = eager(*args, noise=nz)
-            os.environ["DDH_LAZY_LAYOUT"] = "1"
-            b = lazy_ref(*args, noise=nz)
-            os.environ["DDH_LAZY_LAYOUT"] = "0"
-            for k in a:
-                assert torch.equal(a[k], b[k]), (precision, "lazy-vs-eager", k)
-    finally:
-        os.environ.pop("DDH_LAZY_LAYOUT", None)
+        # 8-pixel segments converted on demand: a small part of the 512 segments of the map
+        done = head.debug_tap("done_seg", np.uint32).reshape(-1, 16)[:B]
+        segs = np.array([sum(bin(int(x)).count("1") for x in row) for row in done])
+        assert (segs > 30).all() and (segs < 256).all()
+    for precision in ("fp32", "bf16"):
+        eager, _ = _make_head(precision)
+        eager.set_option("lazy_layout", 0)
+        seg16, _ = _make_head(precision)
+        seg16.set_option("layout_segment", 16)
+        lazy_ref, _ = _make_head(precision)
+        a = eager(*args, noise=nz)
+        b = lazy_ref(*args, noise=nz)
+        c = seg16(*args, noise=nz)
+        for k in a:
+            assert torch.equal(a[k], b[k]), (precision, "lazy-vs-eager", k)
+            assert torch.equal(a[k], c[k]), (precision, "segment-16-vs-eager", k)
 
 
 def test_scene_independence_and_determinism_full_size():

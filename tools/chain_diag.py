@@ -53,8 +53,10 @@ def main():
         cmp("fused_stress_vs_golden", f, {k: z[k] for k in ("trajectory_modes", "trajectory_scores", "mode_idx")})
     elif what == "time":
         B = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
-        for chain in (1, 0):
+        seg = int(sys.argv[3]) if len(sys.argv) > 3 else 8
+        for chain in (1,) if len(sys.argv) > 3 else (1, 0):
             head = make(chain)
+            head.set_option("layout_segment", seg)
             g = torch.Generator(device="cuda").manual_seed(3000)
             ego = torch.randn(B, 1, 256, device="cuda", generator=g)
             agents = torch.randn(B, 30, 256, device="cuda", generator=g)
@@ -74,11 +76,50 @@ def main():
             head(ego, agents, bev, noise=noise)
             prof = head.stage_profile()
             head.set_profiling(False)
-            print(json.dumps({"chain": chain, "B": B, "ms": ms, "scenes_per_s": B / ms * 1e3,
+            print(json.dumps({"chain": chain, "B": B, "seg": seg, "ms": ms, "scenes_per_s": B / ms * 1e3,
                               "launches": head.last_launch_count(),
                               "stage_ms": {k: round(v["ms"], 3) for k, v in prof.items()}}), flush=True)
             del head
 
 
+def timeline(B=4096, launch=1):
+    """clock64 stamps of CTA 0's second tile in one chain launch (option chain_timeline)."""
+    head = make(1)
+    g = torch.Generator(device="cuda").manual_seed(3000)
+    ego = torch.randn(B, 1, 256, device="cuda", generator=g)
+    agents = torch.randn(B, 30, 256, device="cuda", generator=g)
+    bev = torch.randn(B, 256, 64, 64, device="cuda", generator=g)
+    noise = torch.randn(B, 20, 8, 2, device="cuda", generator=g)
+    head(ego, agents, bev, noise=noise)
+    head.set_option("chain_timeline", launch)
+    head.set_profiling(True)        # (the resident engine is bypassed; B is large anyway)
+    head(ego, agents, bev, noise=noise)
+    torch.cuda.synchronize()
+    d = head.debug_tap("dbg", np.int64)
+    head.set_profiling(False)
+    t0 = int(d[0])
+    names = ["x1", "attn", "ln2ego", "relu_f0", "relu_f1", "relu_f2", "relu_f3", "ln_film", "reg0", "reg2",
+             "tail", "cls0_ln", "score"]
+    print(f"chain launch {launch}: CTA 0, second tile; cycles relative to the tile start")
+    prev_end = 0
+    for j in range(13):
+        w0, acc, end = (int(d[1 + 4 * j + k]) - t0 for k in range(3))
+        m0, m1 = int(d[128 + 2 * j]) - t0, int(d[128 + 2 * j + 1]) - t0
+        if end < 0 or end > 10_000_000:
+            break
+        print(f"step {j:2d} {names[j]:8s} mma: operands ready {m0:7d}, issued {m1:7d} (issue {m1 - m0:6d}) | "
+              f"compute: wait from {w0:7d}, acc ready {acc:7d} (waited {acc - w0:6d}), epilogue done {end:7d} "
+              f"(epilogue {end - acc:6d})")
+        prev_end = end
+    print("tile total", prev_end)
+    print("attention: q epilogue done", int(d[64]) - t0, "barrier passed", int(d[65]) - t0)
+    for sl in range(6):
+        a, b, c = (int(d[66 + 3 * sl + k]) - t0 for k in range(3))
+        print(f"  scene {sl}: wait K|V from {a} until {b} ({b - a}), compute until {c} ({c - b})")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "timeline":
+        timeline(int(sys.argv[2]) if len(sys.argv) > 2 else 4096, int(sys.argv[3]) if len(sys.argv) > 3 else 1)
+        sys.exit(0)
     main()
