@@ -141,7 +141,9 @@ struct ddh_handle {
   int lazy_layout = 1;                         // convert BEV segments on demand (NCHW input)
   int seg_px = 8;                              // pixels per segment (8 or 16), option "layout_segment"
   int seg_nw32 = 0;                            // 32-bit mask words per scene (0: map too large, eager layout)
-  int chain_timeline = -1;                     // option "chain_timeline": index of the chain launch to stamp
+  int persistent_conv = 1;                     // option "persistent_conv": tc_conv2_kernel (1) or one CTA per scene (0)
+  int chain_timeline = -1;
+  int conv_timeline = -1;                      // option "conv_timeline": index of the conv launch to stamp                     // option "chain_timeline": index of the chain launch to stamp
   bool profiling_eager = false;
   bool debug_taps = false;                     // env DDH_DEBUG_TAPS=1: keep fp32 copies of x2/x3 in bf16 mode
   long long* dbg = nullptr;                    // timeline stamps (DDH_TIMELINE builds)
@@ -1045,10 +1047,10 @@ int forward_fused(ddh_handle* h, const float* ego, const float* agents, const vo
       gp.bev = bevn; gp.upix = h->upix; gp.nuniq = h->nuniq; gp.rcap = h->rcap;
       gp.H = s.bev_h; gp.W_ = s.bev_w; gp.C = s.bev_channels;
       gp.epi.bias = pl.conv.bias; gp.epi.relu = 1;
-      gp.dbg = h->tl_gemm < 0 ? h->dbg : nullptr;
+      gp.dbg = (h->conv_timeline == si * L + l) ? h->dbg + 256 : nullptr;
       gp.ent_slot = h->ent_slot; gp.ent_w = h->ent_w; gp.n_anchor = A; gp.ent_per_anchor = P * 4;
       gp.epi.out_f32 = h->s32; gp.epi.ldo32 = D; gp.epi.out_bf16 = h->s16; gp.epi.ldo16 = D;
-      launch_tc_conv(gp, pl.conv.map, B, st);
+      launch_tc_conv(gp, pl.conv.map, B, st, h->persistent_conv != 0);
       h->launches++; }
       { ProfSpan ps(h, ST_GEMM, st);
       ChainArgs& a = h->chain_prog[S + (size_t)si * L + l];
@@ -1189,8 +1191,8 @@ int forward_range(ddh_handle* h, const float* ego, const float* agents, const vo
           gp.dbg = h->tl_gemm < 0 ? h->dbg : nullptr;
           gp.ent_slot = v.ent_slot; gp.ent_w = v.ent_w; gp.n_anchor = A; gp.ent_per_anchor = P * 4;
           gp.epi.out_f32 = v.s32; gp.epi.ldo32 = D; gp.epi.out_bf16 = v.s16; gp.epi.ldo16 = D;
-          launch_tc_conv(gp, pl.conv.map, B, st);
-          h->launches += 2;
+          launch_tc_conv(gp, pl.conv.map, B, st, h->persistent_conv != 0);
+          h->launches += 1;
         } else {
           gp.epi.out_f32 = v.V; gp.epi.ldo32 = D;
           gp.W = pl.conv.wt32; gp.ldw = D;
@@ -1456,6 +1458,8 @@ int ddh_set_option(ddh_handle* h, const char* name, int value) {
   else if (n == "resident_engine") { repack = h->res_mode != (value ? 2 : 0); h->res_mode = value ? 2 : 0; }
   else if (n == "debug_taps") h->debug_taps = value != 0;
   else if (n == "chain_timeline") h->chain_timeline = value;
+  else if (n == "persistent_conv") h->persistent_conv = value;
+  else if (n == "conv_timeline") h->conv_timeline = value;
   else if (n == "layout_segment") {
     if (value != 8 && value != 16) return fail(h, DDH_ERR_BAD_ARG, "ddh_set_option: layout_segment must be 8 or 16");
     if (h->seg_px != value) { h->seg_px = value; cudaDeviceSynchronize(); free_all(h->owned_ws); h->cap_B = 0; h->chain_prog.clear(); }

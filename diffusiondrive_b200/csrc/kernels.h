@@ -60,7 +60,8 @@ void launch_pack_hilo(const float* w, __nv_bfloat16* dst, int n_out, int k, cuda
 // W is described by a TMA tensor map over a bf16 [N_total][K] matrix (box 64 x 256,
 // 128-byte swizzle).  A is bf16 [M][lda] (dense) or gathered from the NHWC bf16 BEV map.
 void launch_tc_gemm(const GemmParams& p, const CUtensorMap& wmap, int n_total, cudaStream_t st);
-void launch_tc_conv(const GemmParams& p, const CUtensorMap& wmap, int B, cudaStream_t st);
+void launch_tc_conv(const GemmParams& p, const CUtensorMap& wmap, int B, cudaStream_t st,
+                    bool persistent = true);
 int tc_conv_smem_bytes(int A, int ent_per_anchor);
 int tc_engine_init();   // sets max dynamic smem attributes; returns cudaError_t as int
 

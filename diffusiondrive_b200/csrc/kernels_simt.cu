@@ -260,12 +260,11 @@ static void bev_launch(const void* src, void* dst, int B, int C, int HW, cudaStr
 // batch), thread = channel: per step two segments are read (SEG*4 contiguous bytes per channel
 // plane), transposed through shared memory and written as SEG x 512-byte pixel lines.
 // Trajectories sample ~250 of 4096 pixels; with 8-pixel segments ~20 % of the map is converted.
-template <typename TI, typename TO, int SEG>
+template <typename TI, typename TO, int SEG, int NSEG>
 __global__ void __launch_bounds__(256) bev_segs_to_nhwc_kernel(
     const TI* __restrict__ src, TO* __restrict__ dst, const unsigned int* __restrict__ todo,
     int nw32, int C, int H, int W) {
-  constexpr int NSEG = 2;                       // segments per step
-  extern __shared__ __align__(16) unsigned char seg_raw[];
+  extern __shared__ __align__(16) unsigned char seg_raw[];   // NSEG segments per step
   TO* tile = reinterpret_cast<TO*>(seg_raw);    // [NSEG * SEG px][256 channels]
   __shared__ unsigned short list[2048];
   __shared__ int cnt[65];
@@ -332,11 +331,13 @@ static void bev_segs_launch(const void* src, void* dst, const unsigned int* todo
   int ysplit = 592 / (B > 0 ? B : 1);     // small batches: spread one scene's segments over CTAs
   ysplit = ysplit < 1 ? 1 : (ysplit > 32 ? 32 : ysplit);
   dim3 grid(B, ysplit);
+  // 8-pixel segments: four per step (consecutive list entries are usually neighbours in x, so a
+  // thread's reads of one channel plane coalesce into 64/128-byte runs); 16-pixel: two per step
   if (seg == 8)
-    bev_segs_to_nhwc_kernel<TI, TO, 8><<<grid, 256, 2 * 8 * 256 * sizeof(TO), st>>>(
+    bev_segs_to_nhwc_kernel<TI, TO, 8, 4><<<grid, 256, 4 * 8 * 256 * sizeof(TO), st>>>(
         reinterpret_cast<const TI*>(src), reinterpret_cast<TO*>(dst), todo, nw32, C, H, W);
   else
-    bev_segs_to_nhwc_kernel<TI, TO, 16><<<grid, 256, 2 * 16 * 256 * sizeof(TO), st>>>(
+    bev_segs_to_nhwc_kernel<TI, TO, 16, 2><<<grid, 256, 2 * 16 * 256 * sizeof(TO), st>>>(
         reinterpret_cast<const TI*>(src), reinterpret_cast<TO*>(dst), todo, nw32, C, H, W);
 }
 

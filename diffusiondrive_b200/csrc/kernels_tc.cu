@@ -753,11 +753,332 @@ tc_conv_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap) {
   if (warp == 5) tmem_dealloc<NT * D>(tmem_base);
 }
 
+// ===================================================================================
+// Persistent variant of the conv (default): one CTA per SM walks scenes blockIdx.x, + gridDim.x, ...
+// so that barrier / TMEM set-up is paid once, the next scene's pixel list is fetched under the
+// current scene's main loop, and EIGHT dedicated epilogue warps (two per TMEM lane quarter, one
+// 128-row tile each) drain and combine, instead of the four producer warps switching roles.
+//   warps 0-3   A producers (cp.async gather)        warp 4  TMA (weights)     warp 5  MMA issuer
+//   warps 6-13  epilogue: bias + ReLU drain of tile (w - 6) / 4 into the staging area (aliasing the
+//               idle pipeline buffers), bilinear * attention combine with the anchors dealt over
+//               the eight warps; the scene's entry table is fetched while the main loop runs
+// Same arithmetic as tc_conv_kernel except that the bias is added at the drain (acc + bias) instead
+// of seeding the accumulators.
+// ===================================================================================
+// timeline (p.dbg != nullptr): CTA 0 stamps clock64 during the first pass of its second scene
+#define C2_STAMP(cond, idx) do { if (p.dbg && blockIdx.x == 0 && (cond)) p.dbg[idx] = clock64(); } while (0)
+constexpr int C2_THREADS = 448;
+constexpr int C2_EPI = 256;
+
+__global__ void __launch_bounds__(C2_THREADS, 1)
+tc_conv2_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap, int B) {
+  constexpr int NS = C_NS, NT = C_NT;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
+  uint8_t* sm = smem_raw + pad;
+  const uint32_t sm_addr = raw_addr + pad;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int A = p.n_anchor, n_ent = p.n_anchor * p.ent_per_anchor;
+  float* S32 = p.epi.out_f32;
+  __nv_bfloat16* S16 = p.epi.out_bf16;
+  const int ent_bytes = ((n_ent * 8 + 15) / 16) * 16;
+  EntPair* ent = reinterpret_cast<EntPair*>(sm + C_PIPE);
+  float* bias_s = reinterpret_cast<float*>(sm + C_PIPE + ent_bytes);          // [256]
+  const TcBars bars{sm_addr + C_PIPE + ent_bytes + D * 4, NS};
+  volatile uint32_t* tmem_slot =
+      reinterpret_cast<volatile uint32_t*>(sm + C_PIPE + ent_bytes + D * 4 + (2 * NS + 2) * 8);
+  constexpr int KC = 9 * (D / TC_BK);   // 36 k-chunks: (tap, 64-channel chunk)
+  constexpr int RPT = NT * 8;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(bars.full(s), 128 + 1);
+      mbar_init(bars.empty(s), 1);
+    }
+    mbar_init(bars.accum(), 1);
+    mbar_init(bars.passgo(), C2_EPI);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc<NT * D>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  if (warp == 4 && lane == 0) tma_prefetch_desc(&wmap);
+  if (threadIdx.x < 64)
+    reinterpret_cast<float4*>(bias_s)[threadIdx.x] = __ldg(reinterpret_cast<const float4*>(p.epi.bias) + threadIdx.x);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ======================= A producers: gather 3x3xC patches =========================
+    const int tid = threadIdx.x;
+    const int j = tid & 7, rb = tid >> 3;
+    const uint32_t dst_base = rb * 128 + ((j ^ (rb & 7)) << 4);
+    int g = 0, pi = 0, sidx = 0;
+    int scene = blockIdx.x;
+    int nu = scene < B ? __ldg(p.nuniq + scene) : 0;
+    int yx0[RPT];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i)
+      yx0[i] = (scene < B && nu > 0) ? __ldg(p.upix + (size_t)scene * p.rcap + min(rb + 16 * i, nu - 1)) : 0;
+    while (scene < B) {
+      // the next scene's pixel list (first pass) is fetched now and consumed after this scene
+      const int scene_n = scene + gridDim.x;
+      const int nu_n = scene_n < B ? __ldg(p.nuniq + scene_n) : 0;
+      int yxn[RPT];
+#pragma unroll
+      for (int i = 0; i < RPT; ++i)
+        yxn[i] = (scene_n < B && nu_n > 0) ? __ldg(p.upix + (size_t)scene_n * p.rcap + min(rb + 16 * i, nu_n - 1)) : 0;
+      const __nv_bfloat16* bev = reinterpret_cast<const __nv_bfloat16*>(p.bev) + (size_t)scene * p.H * p.W_ * D;
+      const int passes = (nu + NT * TC_BM - 1) / (NT * TC_BM);
+      for (int pass = 0; pass < passes; ++pass, ++pi) {
+        const int row_base = pass * NT * TC_BM;
+        const int rows_valid = min(NT * TC_BM, nu - row_base);
+        const int nt_active = (rows_valid + TC_BM - 1) / TC_BM;
+        if (pass > 0) {
+#pragma unroll
+          for (int i = 0; i < RPT; ++i)
+            yx0[i] = __ldg(p.upix + (size_t)scene * p.rcap + min(row_base + rb + 16 * i, nu - 1));
+        }
+        int rowoff[RPT];
+        uint32_t vmask[RPT];
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          const int r = rb + 16 * i;
+          rowoff[i] = 0;
+          vmask[i] = 0;
+          if (r < rows_valid) {
+            const int yx = yx0[i];   // (y << 16) | x
+            const int y = yx >> 16, x = yx & 0xffff;
+            rowoff[i] = (y * p.W_ + x) * D + j * 8;
+            const uint32_t xm = (x > 0 ? 1u : 0u) | 2u | (x + 1 < p.W_ ? 4u : 0u);
+            vmask[i] = (y > 0 ? xm : 0u) | (xm << 3) | (y + 1 < p.H ? (xm << 6) : 0u);
+          }
+        }
+        // the staging area of the previous pass aliases the pipeline buffers
+        C2_STAMP(sidx == 1 && pass == 0 && tid == 0, 0);
+        if (pi > 0) mbar_wait(bars.passgo(), (uint32_t)(pi - 1) & 1u);
+        C2_STAMP(sidx == 1 && pass == 0 && tid == 0, 1);
+        for (int kc = 0; kc < KC; ++kc, ++g) {
+          const int s = g % NS;
+          mbar_wait(bars.empty(s), ((g / NS) & 1) ^ 1);
+          C2_STAMP(sidx == 1 && pass == 0 && tid == 0 && (kc & 3) == 0, 2 + (kc >> 2));
+          const uint32_t a_dst = sm_addr + s * C_STAGE + dst_base;
+          const int tap = kc >> 2;
+          const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+          const int tapoff = (dy * p.W_ + dx) * D + (kc & 3) * TC_BK;
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) {
+            if (i < 8 * nt_active) {
+              const bool ok = (vmask[i] >> tap) & 1u;
+              const int off = ok ? rowoff[i] + tapoff : 0;
+              cp_async16(a_dst + i * 2048, bev + off, ok ? 16u : 0u);
+            }
+          }
+          cp_async_mbar_arrive_noinc(bars.full(s));
+        }
+      }
+      scene = scene_n;
+      nu = nu_n;
+      ++sidx;
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) yx0[i] = yxn[i];
+    }
+  } else if (warp == 4) {
+    // ======================= TMA producer (weights) ====================================
+    if (lane == 0) {
+      int g = 0, pi = 0;
+      for (int scene = blockIdx.x; scene < B; scene += gridDim.x) {
+        const int nu = __ldg(p.nuniq + scene);
+        const int passes = (nu + NT * TC_BM - 1) / (NT * TC_BM);
+        for (int pass = 0; pass < passes; ++pass, ++pi) {
+          if (pi > 0) mbar_wait(bars.passgo(), (uint32_t)(pi - 1) & 1u);
+          for (int kc = 0; kc < KC; ++kc, ++g) {
+            const int s = g % NS;
+            mbar_wait(bars.empty(s), ((g / NS) & 1) ^ 1);
+            mbar_arrive_expect_tx(bars.full(s), TC_B_TILE);
+            tma_load_2d(sm_addr + s * C_STAGE + NT * TC_A_TILE, &wmap, bars.full(s), kc * TC_BK, 0);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // ======================= MMA issuer ================================================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16_m128_n256();
+      int g = 0, sidx = 0;
+      for (int scene = blockIdx.x; scene < B; scene += gridDim.x, ++sidx) {
+        const int nu = __ldg(p.nuniq + scene);
+        const int passes = (nu + NT * TC_BM - 1) / (NT * TC_BM);
+        for (int pass = 0; pass < passes; ++pass) {
+          const int rows_valid = min(NT * TC_BM, nu - pass * NT * TC_BM);
+          const int nt_active = (rows_valid + TC_BM - 1) / TC_BM;
+          // (the accumulators of the previous pass are drained: the operands of this pass were only
+          // produced after the producers saw its epilogue finish)
+          for (int kc = 0; kc < KC; ++kc, ++g) {
+            const int s = g % NS;
+            mbar_wait(bars.full(s), (g / NS) & 1);
+            tc_fence_after();
+            C2_STAMP(sidx == 1 && pass == 0 && (kc & 3) == 0, 16 + (kc >> 2));
+            const uint32_t a_stage = sm_addr + s * C_STAGE;
+            mma_chunk<NT>(a_stage, a_stage + NT * TC_A_TILE, tmem_base, nt_active, kc == 0, idesc,
+                          bars.empty(s));
+          }
+          umma_commit(bars.accum());
+          C2_STAMP(sidx == 1 && pass == 0, 25);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ======================= epilogue warps ============================================
+    const int ew = warp - 6;                 // 0..7
+    const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    // warp w may only touch TMEM lanes 32 * (w % 4) ..; warps 6..9 cover the four quarters of tile 0,
+    // warps 10..13 those of tile 1
+    const int tile_of_warp = (ew < 4) ? 0 : 1;
+    const int etid = threadIdx.x - 6 * 32;   // 0..255
+    float* Vs = reinterpret_cast<float*>(sm);
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + tile_of_warp * D;
+    int pi = 0, sidx = 0;
+    for (int scene = blockIdx.x; scene < B; scene += gridDim.x, ++sidx) {
+      const int nu = __ldg(p.nuniq + scene);
+      if (nu == 0) {   // every sample point fell outside the grid: grid_sample returns zeros
+        for (int i = etid; i < A * D; i += C2_EPI) {
+          if (S32) S32[(size_t)scene * A * D + i] = 0.f;
+          if (S16) S16[(size_t)scene * A * D + i] = __float2bfloat16_rn(0.f);
+        }
+        continue;
+      }
+      {  // entry table of this scene (the previous scene's combine is behind a barrier of these warps)
+        const int* es = p.ent_slot + (size_t)scene * n_ent;
+        const float* ew_ = p.ent_w + (size_t)scene * n_ent;
+        for (int base = etid; base < n_ent; base += C2_EPI * 4) {
+          EntPair e[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = base + u * C2_EPI;
+            if (i < n_ent) { e[u].slot = __ldg(es + i); e[u].w = __ldg(ew_ + i); }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = base + u * C2_EPI;
+            if (i < n_ent) ent[i] = e[u];
+          }
+        }
+      }
+      named_bar_sync(1, C2_EPI);
+      const int passes = (nu + NT * TC_BM - 1) / (NT * TC_BM);
+      for (int pass = 0; pass < passes; ++pass, ++pi) {
+        const int row_base = pass * NT * TC_BM;
+        const int rows_valid = min(NT * TC_BM, nu - row_base);
+        const int nt_active = (rows_valid + TC_BM - 1) / TC_BM;
+        C2_STAMP(sidx == 1 && pass == 0 && etid == 0, 32);
+        mbar_wait(bars.accum(), (uint32_t)pi & 1u);
+        tc_fence_after();
+        C2_STAMP(sidx == 1 && pass == 0 && etid == 0, 33);
+        for (int half = 0; half < 2; ++half) {
+          if (tile_of_warp < nt_active) {
+            float* vrow = Vs + (size_t)(tile_of_warp * TC_BM + q * 32 + lane) * C_VS_LD;
+#pragma unroll 1
+            for (int cb = 0; cb < 4; cb += 2) {
+              uint32_t u0[32], u1[32];
+              const int col = half * 128 + cb * 32;
+              tmem_ld32(trow + col, u0);
+              tmem_ld32(trow + col + 32, u1);
+              tmem_ld_wait();
+#pragma unroll
+              for (int qq = 0; qq < 8; ++qq) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bias_s + col + 4 * qq);
+                float4 o;
+                o.x = fmaxf(__uint_as_float(u0[4 * qq + 0]) + b4.x, 0.f);
+                o.y = fmaxf(__uint_as_float(u0[4 * qq + 1]) + b4.y, 0.f);
+                o.z = fmaxf(__uint_as_float(u0[4 * qq + 2]) + b4.z, 0.f);
+                o.w = fmaxf(__uint_as_float(u0[4 * qq + 3]) + b4.w, 0.f);
+                *reinterpret_cast<float4*>(vrow + cb * 32 + 4 * qq) = o;
+              }
+#pragma unroll
+              for (int qq = 0; qq < 8; ++qq) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bias_s + col + 32 + 4 * qq);
+                float4 o;
+                o.x = fmaxf(__uint_as_float(u1[4 * qq + 0]) + b4.x, 0.f);
+                o.y = fmaxf(__uint_as_float(u1[4 * qq + 1]) + b4.y, 0.f);
+                o.z = fmaxf(__uint_as_float(u1[4 * qq + 2]) + b4.z, 0.f);
+                o.w = fmaxf(__uint_as_float(u1[4 * qq + 3]) + b4.w, 0.f);
+                *reinterpret_cast<float4*>(vrow + cb * 32 + 32 + 4 * qq) = o;
+              }
+            }
+          }
+          C2_STAMP(sidx == 1 && pass == 0 && etid == 0, 34 + 3 * half);
+          named_bar_sync(1, C2_EPI);
+          C2_STAMP(sidx == 1 && pass == 0 && etid == 0, 35 + 3 * half);
+          for (int a = ew; a < A; a += 8) {
+            // lane k fetches entry k of the anchor once; (row, weight) pairs are then broadcast by
+            // shuffles, rows outside this pass contribute weight 0 on a clamped row: branch-free,
+            // eight independent staging reads in flight (same summation order as the entry order)
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            const EntPair* ea = ent + a * p.ent_per_anchor;
+            for (int k0 = 0; k0 < p.ent_per_anchor; k0 += 32) {
+              EntPair mine;
+              mine.slot = -1; mine.w = 0.f;
+              if (k0 + lane < p.ent_per_anchor) mine = ea[k0 + lane];
+              const int rr = mine.slot - row_base;
+              const bool ok = rr >= 0 && rr < rows_valid;
+              const int rrc = ok ? rr * C_VS_LD : 0;
+              const float wv = ok ? mine.w : 0.f;
+#pragma unroll 8
+              for (int k = 0; k < 32; ++k) {
+                const int off = __shfl_sync(0xffffffffu, rrc, k);
+                const float wk = __shfl_sync(0xffffffffu, wv, k);
+                const float4 v = *reinterpret_cast<const float4*>(Vs + off + lane * 4);
+                acc.x = fmaf(wk, v.x, acc.x);
+                acc.y = fmaf(wk, v.y, acc.y);
+                acc.z = fmaf(wk, v.z, acc.z);
+                acc.w = fmaf(wk, v.w, acc.w);
+              }
+            }
+            const size_t o = ((size_t)scene * A + a) * D + half * 128 + lane * 4;
+            if (pass > 0) {   // same thread wrote it in the previous pass: deterministic RMW
+              const float4 old = *reinterpret_cast<const float4*>(S32 + o);
+              acc.x += old.x; acc.y += old.y; acc.z += old.z; acc.w += old.w;
+            }
+            if (pass + 1 < passes) {          // fp32 partial sums only between passes
+              *reinterpret_cast<float4*>(S32 + o) = acc;
+            } else if (S16) {                 // final value: the bf16 A operand of output_proj
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(acc.x, acc.y);
+              __nv_bfloat162 h1 = __floats2bfloat162_rn(acc.z, acc.w);
+              uint2 u2;
+              u2.x = *reinterpret_cast<uint32_t*>(&h0);
+              u2.y = *reinterpret_cast<uint32_t*>(&h1);
+              *reinterpret_cast<uint2*>(S16 + o) = u2;
+            }
+          }
+          C2_STAMP(sidx == 1 && pass == 0 && etid == 0, 36 + 3 * half);
+          named_bar_sync(1, C2_EPI);
+        }
+        C2_STAMP(sidx == 1 && pass == 0 && etid == 0, 40);
+        // staging (generic proxy) is done: the weight TMA of the next pass may overwrite it, and
+        // the accumulators may be overwritten by the next pass's first MMA
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(bars.passgo());
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<NT * D>(tmem_base);
+}
+
 int tc_engine_init() {
   cudaError_t e;
   e = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM);
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           227 * 1024);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(tc_conv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            227 * 1024);
   return (int)e;
 }
@@ -780,7 +1101,7 @@ int tc_conv_smem_bytes(int A, int ent_per_anchor) {
   return C_PIPE + ((A * ent_per_anchor * 8 + 15) / 16) * 16 + D * 4 + TC_BAR_BYTES + 1024;
 }
 
-void launch_tc_conv(const GemmParams& p0, const CUtensorMap& wmap, int B, cudaStream_t st) {
+void launch_tc_conv(const GemmParams& p0, const CUtensorMap& wmap, int B, cudaStream_t st, bool persistent) {
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
@@ -790,7 +1111,10 @@ void launch_tc_conv(const GemmParams& p0, const CUtensorMap& wmap, int B, cudaSt
   }
   GemmParams p = p0;
   p.M = num_sms;
-  tc_conv_kernel<<<B, TC_THREADS, tc_conv_smem_bytes(p.n_anchor, p.ent_per_anchor), st>>>(p, wmap);
+  if (persistent)
+    tc_conv2_kernel<<<B < num_sms ? B : num_sms, C2_THREADS, tc_conv_smem_bytes(p.n_anchor, p.ent_per_anchor), st>>>(p, wmap, B);
+  else
+    tc_conv_kernel<<<B, TC_THREADS, tc_conv_smem_bytes(p.n_anchor, p.ent_per_anchor), st>>>(p, wmap);
 }
 
 }  // namespace ddh

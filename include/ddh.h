@@ -200,6 +200,8 @@ DDH_API int ddh_set_concurrency(ddh_handle *h, int chunks, int min_chunk_scenes)
  *                           0: one tcgen05 GEMM launch per Linear (kernels_tc.cu)
  *   "lazy_layout"        1  NCHW input: convert BEV segments on demand; 0: whole map up front
  *   "layout_segment"     8  pixels per on-demand layout segment (8 or 16)
+ *   "persistent_conv"    1  value_proj conv as one persistent CTA per SM with dedicated epilogue
+ *                           warps (tc_conv2_kernel); 0: one CTA per scene (tc_conv_kernel)
  *   "chain_timeline"    -1  index (step * layers + layer) of the chain launch that stamps clock64
  *                           into the "dbg" tap (CTA 0, second tile)
  *   "debug_taps"         0  keep fp32 copies of intermediate activations for ddh_debug_copy

@@ -54,9 +54,11 @@ def main():
     elif what == "time":
         B = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
         seg = int(sys.argv[3]) if len(sys.argv) > 3 else 8
+        pconv = int(sys.argv[4]) if len(sys.argv) > 4 else 1
         for chain in (1,) if len(sys.argv) > 3 else (1, 0):
             head = make(chain)
             head.set_option("layout_segment", seg)
+            head.set_option("persistent_conv", pconv)
             g = torch.Generator(device="cuda").manual_seed(3000)
             ego = torch.randn(B, 1, 256, device="cuda", generator=g)
             agents = torch.randn(B, 30, 256, device="cuda", generator=g)
@@ -76,7 +78,7 @@ def main():
             head(ego, agents, bev, noise=noise)
             prof = head.stage_profile()
             head.set_profiling(False)
-            print(json.dumps({"chain": chain, "B": B, "seg": seg, "ms": ms, "scenes_per_s": B / ms * 1e3,
+            print(json.dumps({"chain": chain, "B": B, "seg": seg, "pconv": pconv, "ms": ms, "scenes_per_s": B / ms * 1e3,
                               "launches": head.last_launch_count(),
                               "stage_ms": {k: round(v["ms"], 3) for k, v in prof.items()}}), flush=True)
             del head
@@ -118,7 +120,34 @@ def timeline(B=4096, launch=1):
         print(f"  scene {sl}: wait K|V from {a} until {b} ({b - a}), compute until {c} ({c - b})")
 
 
+def conv_timeline(B=4096, launch=1):
+    head = make(1)
+    g = torch.Generator(device="cuda").manual_seed(3000)
+    ego = torch.randn(B, 1, 256, device="cuda", generator=g)
+    agents = torch.randn(B, 30, 256, device="cuda", generator=g)
+    bev = torch.randn(B, 256, 64, 64, device="cuda", generator=g)
+    noise = torch.randn(B, 20, 8, 2, device="cuda", generator=g)
+    head(ego, agents, bev, noise=noise)
+    head.set_option("conv_timeline", launch)
+    head.set_profiling(True)
+    head(ego, agents, bev, noise=noise)
+    torch.cuda.synchronize()
+    d = head.debug_tap("dbg", np.int64)[256:]
+    nu = head.debug_tap("nuniq", np.int32)
+    head.set_profiling(False)
+    t0 = int(d[0])
+    rel = lambda i: int(d[i]) - t0
+    print(f"conv launch {launch}: CTA 0, second scene (scene 148, nuniq {nu[148]}), first pass; cycles since the producers were ready")
+    print("producer: passgo ok", rel(1), "| chunk issue starts (every 4th):", [rel(2 + k) for k in range(9)])
+    print("mma: operands ready (every 4th chunk):", [rel(16 + k) for k in range(9)], "| committed", rel(25))
+    print("epilogue: wait from", rel(32), "accum ok", rel(33), "| half0 drained", rel(34), "synced", rel(35), "combined", rel(36),
+          "| half1 drained", rel(37), "synced", rel(38), "combined", rel(39), "| done", rel(40))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "convtl":
+        conv_timeline(int(sys.argv[2]) if len(sys.argv) > 2 else 4096, int(sys.argv[3]) if len(sys.argv) > 3 else 1)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "timeline":
         timeline(int(sys.argv[2]) if len(sys.argv) > 2 else 4096, int(sys.argv[3]) if len(sys.argv) > 3 else 1)
         sys.exit(0)
