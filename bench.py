@@ -123,6 +123,24 @@ def cpu_oracle_rate(batch: int, reps: int, warm: int):
     return batch / (sum(times) / len(times)), sum(times) / len(times), torch.get_num_threads()
 
 
+def cpu_oracle_b1_p50(reps: int = 9, warm: int = 2):
+    """p50 latency (ms) of a single-scene forward of the oracle port."""
+    import torch
+    from diffusiondrive_b200 import synth
+    from oracle import head_oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = synth.make_state_dict()
+    ft = synth.make_features(1)
+    nz = synth.make_noise(1)
+    times = []
+    for i in range(warm + reps):
+        t0 = time.perf_counter()
+        head_oracle.forward_test(sd, ft["ego_query"], ft["agents_query"], ft["bev_feature"], nz)
+        if i >= warm:
+            times.append((time.perf_counter() - t0) * 1e3)
+    return statistics.median(times)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -141,7 +159,7 @@ def run_reference(args):
                    "note": "CPU arm = oracle port of the reference algorithm as written "
                            "(the reference is pure Python/PyTorch and cannot travel to this box)"},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": sample},
+                         "sample": sample, "b1_p50_ms": cpu_oracle_b1_p50()},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -160,6 +178,11 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if rank == 0:
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            os.environ["DDH_NCCL_LOG"] = os.path.join(ROOT, "gpurun_out", "nccl_rank0.log")
+            os.environ.setdefault("NCCL_DEBUG", "INFO")
+            os.environ.setdefault("NCCL_DEBUG_FILE", os.environ["DDH_NCCL_LOG"])
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -196,9 +219,18 @@ def run_ours(args):
     head.frozen = False
     total = B * world
 
-    def step():
+    ag_events = []
+
+    def step(time_gather=False):
         out = head(ego, agents, bev, noise=noise)
         if world > 1:
+            if time_gather:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                res = gather_scenes(out["trajectory"], total)
+                b.record()
+                ag_events.append((a, b))
+                return res, out
             return gather_scenes(out["trajectory"], total), out
         return out["trajectory"], out
 
@@ -230,13 +262,14 @@ def run_ours(args):
     t_begin = time.time()
     e0.record()
     for _ in range(args.steps):
-        step()
+        step(time_gather=True)
     e1.record()
     torch.cuda.synchronize()
     t_end = time.time()
     if world > 1:
         dist.barrier()
     clocks = sampler.stop(t_begin, t_end)
+    allgather_ms = (statistics.median(a.elapsed_time(b) for a, b in ag_events) if ag_events else None)
     elapsed_ms = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([elapsed_ms], device=dev)
@@ -261,19 +294,25 @@ def run_ours(args):
         flops_unique = rows_unique * FLOP_PER_CONV_ROW
         flops_contract = B * CONTRACT_ROWS_PER_SCENE_CALL * FLOP_PER_CONV_ROW
         achieved = flops_unique / (conv_ms * 1e-3) / 1e12
-        traffic = None
+        traffic, tensor_active = None, None
         tpath = os.path.join(ROOT, "profiles", "conv_traffic.json")
         if os.path.exists(tpath):
             try:
                 with open(tpath) as fh:
-                    traffic = json.load(fh).get("dram_bytes_per_launch")
+                    tj = json.load(fh)
+                traffic = tj.get("dram_bytes_per_launch")
+                tensor_active = tj.get("tensor_active_pct")
             except Exception:
                 traffic = None
         roofline = {
-            "kernel": "tc_conv_kernel (on-demand value_proj conv + fused combine, tcgen05)",
+            "kernel": "tc_conv2_kernel (persistent on-demand value_proj conv + fused combine, tcgen05)",
             "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"],
             "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"],
-            "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside the step)",
+            "frac_burst": achieved / peaks["bf16_tflops"], "peak_burst": peaks["bf16_tflops"],
+            "tensor_active_pct_ncu": tensor_active,
+            "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside the step); "
+                           "frac_burst is against the burst figure; tensor_active_pct_ncu is "
+                           "sm__pipe_tensor_cycles_active of the committed ncu capture (profiles/)",
             "traffic": traffic,
             "flops_per_launch": flops_unique,
             "flops_per_launch_basis": "unique sampled pixels (exact dedup) x 2*2304*256",
@@ -422,13 +461,98 @@ def run_ours(args):
     except Exception as ex:
         lat = {"error": repr(ex)}
 
+    # ---- batch-1 through the host-buffer entry point (what AbstractAgent.compute_trajectory does,
+    # abstract_agent.py:65-86: CPU tensors in, numpy out): wall clock around the whole call
+    lat_host = None
+    try:
+        if args.quick:
+            raise RuntimeError("skipped (--quick)")
+        h1 = tuple(t[:1].cpu().pin_memory() for t in (ego, agents, bev))
+        hn = noise[:1].cpu().pin_memory()
+        for _ in range(5):
+            head(*h1, noise=hn)
+        wall = []
+        for _ in range(min(args.latency_iters, 100)):
+            t0 = time.perf_counter()
+            o = head(*h1, noise=hn)
+            _ = o["trajectory"].numpy()
+            wall.append((time.perf_counter() - t0) * 1e6)
+        wall.sort()
+        lat_host = {"p50_us": wall[len(wall) // 2], "p90_us": wall[int(len(wall) * 0.9)], "iters": len(wall),
+                    "h2d_bytes": sum(x.numel() * x.element_size() for x in h1 + (hn,)),
+                    "path": "ddh_forward_host, B=1: pinned fp32 NCHW inputs -> H2D -> forward -> D2H -> sync"}
+    except Exception as ex:
+        lat_host = {"error": repr(ex)}
+
+    # ---- the other BASELINE.json configurations: configs[1] (fp32, 256 scenes) and configs[4]
+    # (stress: 64 anchors, 3 steps, 4 layers, 128x128 BEV), each with its parity against the
+    # live-reference golden fixtures
+    extra_cfg = None
+    if rank == 0 and world == 1 and not args.quick:
+        extra_cfg = {}
+
+        def timed(h, tensors, nz, iters):
+            for _ in range(2):
+                o = h(*tensors, noise=nz)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(iters):
+                o = h(*tensors, noise=nz)
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / iters, o
+
+        def par(o, z, n):
+            m = o["trajectory_modes"][:n].float().cpu().numpy()
+            return {"scenes": n,
+                    "max_dxy_m": float(np.abs(m[..., :2] - z["trajectory_modes"][:n, ..., :2]).max()),
+                    "max_dheading_rad": float(np.abs(m[..., 2] - z["trajectory_modes"][:n, ..., 2]).max()),
+                    "mode_agreement": float((o["mode_idx"][:n].cpu().numpy() == z["mode_idx"][:n]).mean())}
+        try:
+            z256 = np.load(gold_path)
+            h32 = TrajectoryHead(P, 1024, D, None, HeadConfig(), plan_anchor=sd["plan_anchor"].numpy(),
+                                 precision="fp32")
+            h32.load_state_dict(sd)
+            h32 = h32.to(dev).eval()
+            t256 = (ego[:256], agents[:256], bev[:256])
+            ms, o = timed(h32, t256, noise[:256], 3)
+            extra_cfg["fp32_b256"] = {"config": "BASELINE configs[1]: fp32 engine, 256 scenes, 1 GPU",
+                                      "ms_per_step": ms, "value": 256 / (ms * 1e-3), "unit": UNIT,
+                                      "parity": dict(par(o, z256, 256), tolerance_m=1e-4)}
+            del h32
+            zs = np.load(os.path.join(ROOT, "tests", "golden", "stress_b2.npz"))
+            sds = synth.make_state_dict(num_layers=4, num_anchors=64)
+            for prec, Bs, iters, tol in (("bf16", 512, 3, 2e-2), ("fp32", 64, 2, 1e-4)):
+                hs = TrajectoryHead(P, 1024, D, None, HeadConfig(num_decoder_layers=4, step_num=3),
+                                    plan_anchor=sds["plan_anchor"].numpy(), precision=prec)
+                hs.load_state_dict(sds)
+                hs = hs.to(dev).eval()
+                gs = torch.Generator(device=dev).manual_seed(synth.SEED_THROUGHPUT + 17)
+                ts = [torch.randn(Bs, 1, D, device=dev, generator=gs), torch.randn(Bs, NA, D, device=dev, generator=gs),
+                      torch.randn(Bs, C_BEV, 128, 128, device=dev, generator=gs)]
+                ns = torch.randn(Bs, 64, P, 2, device=dev, generator=gs)
+                fs = synth.make_features(2, bev_h=128, bev_w=128)
+                ts[0][:2], ts[1][:2], ts[2][:2] = (fs["ego_query"].to(dev), fs["agents_query"].to(dev),
+                                                   fs["bev_feature"].to(dev))
+                ns[:2] = synth.make_noise(2, num_anchors=64).to(dev)
+                ms, o = timed(hs, tuple(ts), ns, iters)
+                extra_cfg[f"stress_{prec}_b{Bs}"] = {
+                    "config": "BASELINE configs[4]: 64 anchors, 3 DDIM steps, 4 decoder layers, BEV 256x128x128",
+                    "ms_per_step": ms, "value": Bs / (ms * 1e-3), "unit": UNIT,
+                    "launches": hs.last_launch_count(), "parity": dict(par(o, zs, 2), tolerance_m=tol)}
+                del hs, ts, ns
+        except Exception as ex:
+            extra_cfg["error"] = repr(ex)
+
     # ---- CPU baseline (oracle port) on this box's host cores, rank 0 at N = 1 only
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.quick:
         rate, sec, threads = cpu_oracle_rate(args.ref_batch, 3, 1)
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{args.ref_batch} scenes x 3 timed forwards (+1 warm-up) of the oracle "
-                         f"port, fp32, {threads} torch threads, {sec * 1e3:.0f} ms per forward"}
+                         f"port, fp32, {threads} torch threads, {sec * 1e3:.0f} ms per forward",
+               "b1_p50_ms": cpu_oracle_b1_p50(5, 1)}
 
     if rank == 0:
         line = {
@@ -450,13 +574,28 @@ def run_ours(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step,
             "roofline": roofline, "roofline_hbm_stage": hbm, "cpu_baseline": cpu,
-            "latency_b1": lat, "parity": parity, "nhwc_bf16_input": nhwc,
+            "latency_b1": lat, "latency_b1_host": lat_host, "parity": parity, "nhwc_bf16_input": nhwc,
+            "extra_configs": extra_cfg, "allgather_ms": allgather_ms, "comm_log_tail": _nccl_log_tail(),
             "stage_ms": {k: round(v["ms"], 4) for k, v in prof.items()},
         }
         _emit(args.real_stdout, line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _nccl_log_tail():
+    """NCCL's own init lines (NCCL_DEBUG=INFO is sent to a file per rank so that stdout stays one
+    JSON line); the lines that name the transport / algorithm are kept."""
+    path = os.environ.get("DDH_NCCL_LOG")
+    if not path or not os.path.exists(path):
+        return None
+    keep = []
+    with open(path, errors="replace") as fh:
+        for ln in fh:
+            if any(k in ln for k in ("NCCL version", "Init COMPLETE", "NVLS", "via P2P", "Channel 00/", "nRanks")):
+                keep.append(ln.strip()[-200:])
+    return keep[:12]
 
 
 def _claim_stdout() -> int:

@@ -144,7 +144,7 @@ def make_state_dict(seed: int = SEED_WEIGHTS, num_layers: int = 2, num_anchors: 
 
 
 def make_features(batch: int, seed: int = SEED_FEATURES, num_agents: int = 30, d_model: int = 256,
-                  bev_c: int = 256, bev_h: int = 64, bev_w: int = 64
+                  bev_c: int = 256, bev_h: int = 64, bev_w: int = 64, start: int = 0
                   ) -> Dict[str, torch.Tensor]:
     """iid N(0,1) stand-ins for the three LayerNorm-ed backbone outputs the head reads.
 
@@ -152,7 +152,8 @@ def make_features(batch: int, seed: int = SEED_FEATURES, num_agents: int = 30, d
     ego_query (B,1,D), agents_query (B,Na,D), bev_feature (B,C,H,W) NCHW contiguous,
     status_encoding (B,1,D) (dead input, kept for the signature).
     Scenes are drawn one at a time so that scene ``i`` is the same tensor for
-    every batch size (a B=1 run is the first scene of a B=256 run).
+    every batch size (a B=1 run is the first scene of a B=256 run); ``start`` draws scenes
+    ``start .. start + batch - 1`` of that sequence.
     """
     ego = torch.empty(batch, 1, d_model)
     agents = torch.empty(batch, num_agents, d_model)
@@ -160,7 +161,7 @@ def make_features(batch: int, seed: int = SEED_FEATURES, num_agents: int = 30, d
     status = torch.empty(batch, 1, d_model)
     for i in range(batch):
         g = torch.Generator(device="cpu")
-        g.manual_seed(seed * 1_000_003 + i)
+        g.manual_seed(seed * 1_000_003 + start + i)
         ego[i] = torch.randn(1, d_model, generator=g)
         agents[i] = torch.randn(num_agents, d_model, generator=g)
         status[i] = torch.randn(1, d_model, generator=g)
@@ -169,13 +170,13 @@ def make_features(batch: int, seed: int = SEED_FEATURES, num_agents: int = 30, d
             "status_encoding": status}
 
 
-def make_noise(batch: int, seed: int = SEED_NOISE, num_anchors: int = 20, num_poses: int = 8
-               ) -> torch.Tensor:
+def make_noise(batch: int, seed: int = SEED_NOISE, num_anchors: int = 20, num_poses: int = 8,
+               start: int = 0) -> torch.Tensor:
     """Host-generated DDIM noise (B, A, P, 2), injected in place of the reference's
     ``torch.randn(img.shape)`` (transfuser_model_v2.py:593)."""
     out = torch.empty(batch, num_anchors, num_poses, 2)
     for i in range(batch):
         g = torch.Generator(device="cpu")
-        g.manual_seed(seed * 1_000_003 + i)
+        g.manual_seed(seed * 1_000_003 + start + i)
         out[i] = torch.randn(num_anchors, num_poses, 2, generator=g)
     return out

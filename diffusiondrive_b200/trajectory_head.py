@@ -151,6 +151,12 @@ class TrajectoryHead(nn.Module):
         self._packed_sig = None
         self._keepalive = None
         self._options: Dict[str, int] = {}
+        # bf16 engine only: scenes whose top-1/top-2 score gap is below this margin are re-planned by
+        # the fp32 engine (near-tie scenes are the only ones whose selected mode can flip under bf16
+        # operands).  None: off.
+        self.rescore_margin: Optional[float] = None
+        self._twin = []         # [fp32 twin head, signature]; a list keeps it out of the module tree
+        self.last_rescored = 0
         self.frozen = False     # True: skip the per-call "did the weights change" check
         self.register_load_state_dict_post_hook(lambda *_: self._invalidate())
 
@@ -343,8 +349,34 @@ class TrajectoryHead(nn.Module):
                     idx.data_ptr(), B, stream)
             if rc:
                 _lib.check(lib, h, rc, "ddh_forward_host" if host_call else "ddh_forward")
-        return {"trajectory": traj, "trajectory_modes": modes, "trajectory_scores": scores,
-                "mode_idx": idx}
+        out = {"trajectory": traj, "trajectory_modes": modes, "trajectory_scores": scores,
+               "mode_idx": idx}
+        self.last_rescored = 0
+        if self.rescore_margin is not None and self.precision == "bf16" and A > 1 and not host_call:
+            self._rescore_near_ties(out, ego, agents, bev, noise, bev_layout)
+        return out
+
+    def _rescore_near_ties(self, out, ego, agents, bev, noise, bev_layout):
+        """Re-plan near-tie scenes with the fp32 engine (same C ABI, a second handle) and patch
+        their rows of the output tensors in place."""
+        top2 = torch.topk(out["trajectory_scores"], 2, dim=1).values
+        pick = torch.nonzero((top2[:, 0] - top2[:, 1]) < float(self.rescore_margin)).flatten()
+        n = int(pick.numel())
+        self.last_rescored = n
+        if n == 0:
+            return
+        sig = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if not self._twin or self._twin[1] != sig:
+            twin = TrajectoryHead(self._num_poses, self._d_ffn, self._d_model, None, self._config,
+                                  plan_anchor=self.plan_anchor.detach().cpu().numpy(), precision="fp32")
+            twin.load_state_dict(self.state_dict())
+            twin = twin.to(self.plan_anchor.device).eval()
+            self._twin[:] = [twin, sig]
+        twin = self._twin[0]
+        fix = twin(ego.index_select(0, pick), agents.index_select(0, pick),
+                   bev.index_select(0, pick), noise=noise.index_select(0, pick), bev_layout=bev_layout)
+        for k in out:
+            out[k].index_copy_(0, pick, fix[k])
 
     # -------------------------------------------------------------- test hooks
     def debug_tap(self, name: str, dtype=np.float32) -> np.ndarray:

@@ -173,7 +173,8 @@ DDH_API int ddh_forward(ddh_handle *h, const float *ego, const float *agents, co
                 void *stream);
 
 /* Same call with HOST buffers (pinned memory recommended): copies the inputs to the
- * device, runs ddh_forward, copies the outputs back and synchronises `stream`.
+ * device (a pinned NCHW map is read in place, see option "host_zero_copy"), runs ddh_forward,
+ * copies the outputs back and synchronises `stream`.
  * This is the end-to-end path a CPU-resident caller (abstract_agent.py:65-86) uses. */
 DDH_API int ddh_forward_host(ddh_handle *h, const float *ego, const float *agents, const void *bev,
                      int bev_dtype, int bev_layout, const float *noise, float *out_traj,
@@ -200,6 +201,8 @@ DDH_API int ddh_set_concurrency(ddh_handle *h, int chunks, int min_chunk_scenes)
  *                           0: one tcgen05 GEMM launch per Linear (kernels_tc.cu)
  *   "lazy_layout"        1  NCHW input: convert BEV segments on demand; 0: whole map up front
  *   "layout_segment"     8  pixels per on-demand layout segment (8 or 16)
+ *   "host_zero_copy"     1  ddh_forward_host: a pinned NCHW bev_feature is read in place across PCIe by
+ *                           the on-demand layout pass (only the needed segments) instead of copied whole
  *   "persistent_conv"    1  value_proj conv as one persistent CTA per SM with dedicated epilogue
  *                           warps (tc_conv2_kernel); 0: one CTA per scene (tc_conv_kernel)
  *   "chain_timeline"    -1  index (step * layers + layer) of the chain launch that stamps clock64

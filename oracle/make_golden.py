@@ -132,13 +132,31 @@ def main():
         trajs, regs, clss = [], [], []
         for s0 in range(0, B, 32):
             n = min(32, B - s0)
-            feats = synth.make_features(s0 + n)
-            feats = {k: v[s0:s0 + n] for k, v in feats.items()}
-            noise = synth.make_noise(s0 + n)[s0:s0 + n]
+            feats = synth.make_features(n, start=s0)
+            noise = synth.make_noise(n, start=s0)
             t, r, c = run_reference_default(head, feats, noise)
             trajs.append(t), regs.append(r), clss.append(c)
         _save(name, torch.cat(trajs), torch.cat(regs), torch.cat(clss),
               dict(meta_base, batch=B, anchors=20, steps=2, layers=2, bev=[64, 64]))
+
+    # ---- mode-agreement statistics at BASELINE's full batch: scores / selected mode / selected
+    # trajectory of 4096 scenes (all-mode poses are not stored: 7.9 MB)
+    if "--full" in sys.argv:
+        B = 4096
+        trajs, clss = [], []
+        for s0 in range(0, B, 32):
+            feats = synth.make_features(32, start=s0)
+            noise = synth.make_noise(32, start=s0)
+            t, _r, c = run_reference_default(head, feats, noise)
+            trajs.append(t), clss.append(c)
+        cls = torch.cat(clss)
+        path = os.path.join(GOLDEN_DIR, "default_b4096_scores.npz")
+        np.savez_compressed(path, trajectory=torch.cat(trajs).numpy().astype(np.float32),
+                            trajectory_scores=cls.numpy().astype(np.float32),
+                            mode_idx=cls.argmax(-1).numpy().astype(np.int64),
+                            meta=np.frombuffer(json.dumps(dict(meta_base, batch=B, anchors=20, steps=2,
+                                                               layers=2, bev=[64, 64])).encode(), dtype=np.uint8))
+        print(f"wrote {path}: {os.path.getsize(path) / 1024:.1f} KiB")
 
     # ---- stress configuration: 64 anchors, 3 steps, 4 layers, 128x128 BEV
     sd = synth.make_state_dict(num_layers=4, num_anchors=64)

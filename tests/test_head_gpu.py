@@ -155,8 +155,44 @@ def test_bf16_b256_within_tolerance(golden_dir):
     same = out["mode_idx"] == ref["mode_idx"]
     assert np.abs(out["trajectory"][same] - ref["trajectory"][same]).max() <= TOL_BF16_M
     # near-tie scenes may flip under bf16 operands; clear ones must not
-    assert rec["mode_agreement"] >= 0.95
+    assert rec["mode_agreement"] >= 0.975          # measured 0.988 (3 of 256 scenes, all with margin < 0.02)
     assert rec["mode_agreement_margin_gt_0.05"] == 1.0
+
+
+def test_bf16_mode_agreement_1024_scenes_and_near_tie_replan(golden_dir):
+    """Selected-mode agreement with the live reference over 1024 scenes of the 4096-scene fixture
+    (tools/mode_agreement.py runs all 4096): plain bf16 flips only near ties; with
+    rescore_margin the near-tie scenes are re-planned by the fp32 engine and agreement reaches
+    the north-star's 99.9 %."""
+    z = np.load(os.path.join(golden_dir, "default_b4096_scores.npz"))
+    N, CH = 1024, 256
+    head, _ = _make_head("bf16")
+    srt = np.sort(z["trajectory_scores"][:N], axis=1)
+    margin = srt[:, -1] - srt[:, -2]
+    res = {}
+    for m in (None, 0.05):
+        head.rescore_margin = m
+        idx, tr, resc = [], [], 0
+        for s0 in range(0, N, CH):
+            ft = synth.make_features(CH, start=s0)
+            nz = synth.make_noise(CH, start=s0)
+            o = head(ft["ego_query"].cuda(), ft["agents_query"].cuda(), ft["bev_feature"].cuda(), noise=nz.cuda())
+            idx.append(o["mode_idx"].cpu().numpy()); tr.append(o["trajectory"].cpu().numpy())
+            resc += head.last_rescored
+        idx, tr = np.concatenate(idx), np.concatenate(tr)
+        agree = idx == z["mode_idx"][:N]
+        res[m] = (agree, resc)
+        rec = {"tag": f"bf16_modes_1024_rescore_{m}", "mode_agreement": float(agree.mean()),
+               "rescored": resc, "flips_max_ref_margin": float(margin[~agree].max()) if (~agree).any() else None}
+        print("PARITY", json.dumps(rec))
+        with open("gpurun_out/parity.jsonl", "a") as fh:
+            fh.write(json.dumps(rec) + "\n")
+        assert np.abs(tr[agree] - z["trajectory"][:N][agree]).max() <= TOL_BF16_M
+    plain, _ = res[None]
+    assert plain.mean() >= 0.975 and plain[margin > 0.05].all()
+    fixed, resc = res[0.05]
+    assert 0 < resc < N // 2
+    assert fixed.mean() >= 0.999
 
 
 def test_small_batch_engine_matches_reference(golden_dir):

@@ -140,3 +140,15 @@ def test_oracle_bit_matches_live_reference(tmp_path):
     assert (out["trajectory_modes"] - reg).abs().max() <= TOL_M
     assert (out["trajectory"] - traj).abs().max() <= TOL_M
     assert (out["trajectory_scores"] - cls).abs().max() <= 1e-5
+
+
+def test_full_batch_scores_fixture_is_consistent(golden_dir):
+    """default_b4096_scores.npz (scores / modes of 4096 scenes from the live reference) extends
+    default_b256.npz: its first 256 scenes are the same reference outputs."""
+    a = np.load(os.path.join(golden_dir, "default_b256.npz"))
+    b = np.load(os.path.join(golden_dir, "default_b4096_scores.npz"))
+    assert b["trajectory_scores"].shape == (4096, 20) and b["mode_idx"].shape == (4096,)
+    assert np.array_equal(b["trajectory_scores"][:256], a["trajectory_scores"])
+    assert np.array_equal(b["mode_idx"][:256], a["mode_idx"])
+    assert np.array_equal(b["trajectory"][:256], a["trajectory"])
+    assert np.array_equal(b["mode_idx"], b["trajectory_scores"].argmax(1))
