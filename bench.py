@@ -186,6 +186,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = _bind_to_gpu_numa_node(local_rank)
     B = args.batch
     precision = args.precision
 
@@ -398,8 +399,11 @@ def run_ours(args):
         e2e = {"value": Be * world / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "scenes_per_step_per_gpu": Be, "ms_per_step": ms,
                "steps": k_e2e,
-               "path": "TrajectoryHead.forward with CPU (pinned) tensors -> ddh_forward_host: "
-                       "H2D of fp32 NCHW inputs, forward, D2H of trajectory/modes/scores/idx"}
+               "path": "TrajectoryHead.forward with CPU (pinned) tensors -> ddh_forward_host: H2D of ego/agents/"
+                       "noise, the pinned fp32 NCHW map read in place across PCIe by the on-demand layout "
+                       "pass (64-pixel runs, ~55 % of the map crosses the link), forward, D2H of "
+                       "trajectory/modes/scores/idx",
+               "note": "h2d_bytes_per_step counts the full input tensors handed to the call"}
         del h_ego, h_agents, h_bev, h_noise
     except Exception as ex:          # keep the bench line even if pinning fails on a small host
         e2e = {"value": None, "unit": UNIT, "error": repr(ex)}
@@ -575,13 +579,47 @@ def run_ours(args):
             "gpu_launches_per_step": launches_per_step,
             "roofline": roofline, "roofline_hbm_stage": hbm, "cpu_baseline": cpu,
             "latency_b1": lat, "latency_b1_host": lat_host, "parity": parity, "nhwc_bf16_input": nhwc,
-            "extra_configs": extra_cfg, "allgather_ms": allgather_ms, "comm_log_tail": _nccl_log_tail(),
+            "extra_configs": extra_cfg, "allgather_ms": allgather_ms, "numa_binding": numa, "comm_log_tail": _nccl_log_tail(),
             "stage_ms": {k: round(v["ms"], 4) for k, v in prof.items()},
         }
         _emit(args.real_stdout, line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _bind_to_gpu_numa_node(local_rank: int):
+    """Run this rank on the CPUs local to its GPU so that the pinned host buffers of the e2e leg
+    are first-touched on the GPU's NUMA node (8 ranks sharing one node's memory controller was the
+    e2e limiter of round 1).  Returns a short description for the JSON line."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        with open(base + "/local_cpulist") as fh:
+            txt = fh.read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        node = None
+        try:
+            with open(base + "/numa_node") as fh:
+                node = int(fh.read().strip())
+        except Exception:
+            pass
+        if use:
+            os.sched_setaffinity(0, use)
+            return {"gpu": bdf, "numa_node": node, "cpus": len(use)}
+        return {"gpu": bdf, "numa_node": node, "cpus": 0, "note": "local cpus not in this process's cpuset"}
+    except Exception as ex:
+        return {"error": repr(ex)}
 
 
 def _nccl_log_tail():

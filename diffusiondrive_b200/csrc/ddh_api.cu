@@ -141,6 +141,9 @@ struct ddh_handle {
   int lazy_layout = 1;                         // convert BEV segments on demand (NCHW input)
   int seg_px = 8;                              // pixels per segment (8 or 16), option "layout_segment"
   int seg_nw32 = 0;                            // 32-bit mask words per scene (0: map too large, eager layout)
+  int host_seg_px = 64;                        // option "host_segment": 16 / 32 / 64 pixels when reading a host map
+  int seg_px_call = 8;                         // granularity of the current call (pick_segments)
+  bool host_map_call = false;                  // the current call reads a pinned host map in place
   int host_zero_copy = 1;                      // option "host_zero_copy": ddh_forward_host reads pinned maps in place
   int persistent_conv = 1;                     // option "persistent_conv": tc_conv2_kernel (1) or one CTA per scene (0)
   int chain_timeline = -1;
@@ -366,13 +369,8 @@ int ensure_ws(ddh_handle* h, int B) {
   WS(h->upix, (size_t)B * h->rcap);
   WS(h->nuniq, B);
   WS(h->conv_rows, s.num_layers * s.num_steps);
-  {
-    const int spr = s.bev_w / h->seg_px;
-    const int bits = s.bev_h * spr;
-    h->seg_nw32 = (s.bev_w % h->seg_px == 0 && bits <= 2048) ? (bits + 31) / 32 : 0;
-  }
-  WS(h->need_seg, (size_t)B * std::max(h->seg_nw32, 1));
-  WS(h->done_seg, (size_t)B * std::max(h->seg_nw32, 1));
+  WS(h->need_seg, (size_t)B * 64);
+  WS(h->done_seg, (size_t)B * 64);
   WS(h->dbg, 1024);
   WS(h->ent_slot, M * s.num_poses * 4);
   WS(h->ent_w, M * s.num_poses * 4);
@@ -419,7 +417,7 @@ void register_taps(ddh_handle* h, int B) {
   t["upix"] = {h->upix, (size_t)B * h->rcap * 4};
   t["nuniq"] = {h->nuniq, (size_t)B * 4};
   t["dbg"] = {h->dbg, (size_t)1024 * 8};
-  t["done_seg"] = {h->done_seg, (size_t)B * std::max(h->seg_nw32, 1) * 4};
+  t["done_seg"] = {h->done_seg, (size_t)B * std::max(h->seg_nw32, 1) * 4};   // (of the last forward)
   t["conv_rows"] = {h->conv_rows, (size_t)s.num_layers * s.num_steps * 4};
   t["ent_slot"] = {h->ent_slot, M * s.num_poses * 4 * 4};
   t["ent_w"] = {h->ent_w, M * s.num_poses * 4 * 4};
@@ -831,6 +829,19 @@ View make_view(const ddh_handle* h, int s0) {
 }
 
 
+// On-demand layout granularity of this call: segments of seg_px pixels (32 when the map is read in
+// place from pinned host memory), mask words per scene; 0 words = map too large for the masks.
+void pick_segments(ddh_handle* h) {
+  const ddh_shape& s = h->shp;
+  h->seg_px_call = h->host_map_call ? h->host_seg_px : h->seg_px;
+  // (a host map is read in whole 64-pixel runs when the width allows: 256-byte PCIe reads)
+  while (h->seg_px_call > h->seg_px && (s.bev_w % h->seg_px_call || s.bev_h * (s.bev_w / h->seg_px_call) > 2048))
+    h->seg_px_call >>= 1;
+  if (s.bev_w % h->seg_px_call) h->seg_px_call = h->seg_px;
+  const int bits = s.bev_h * (s.bev_w / h->seg_px_call);
+  h->seg_nw32 = (s.bev_w % h->seg_px_call == 0 && bits <= 2048) ? (bits + 31) / 32 : 0;
+}
+
 // ---- scene-tile chain engine (kernels_chain.cu): the program tables
 struct ProgBuilder {
   ChainArgs& a;
@@ -980,8 +991,9 @@ int forward_fused(ddh_handle* h, const float* ego, const float* agents, const vo
   if (h->chain_prog.empty()) { rc = build_chain_programs(h); if (rc) return rc; }
   const int spt = h->chain_spt, n_tiles = (B + spt - 1) / spt;
   const void* bevn = bev;
+  pick_segments(h);
   const bool lazy = bev_layout == DDH_NCHW && h->lazy_layout && h->seg_nw32 > 0 && !h->profiling_eager;
-  const int seg_shift = h->seg_px == 16 ? 4 : 3;
+  const int seg_shift = h->seg_px_call == 64 ? 6 : h->seg_px_call == 32 ? 5 : (h->seg_px_call == 16 ? 4 : 3);
   { ProfSpan ps(h, ST_BEV, st);
   if (bev_layout == DDH_NCHW) {
     if (lazy) {
@@ -1039,7 +1051,8 @@ int forward_fused(ddh_handle* h, const float* ego, const float* agents, const vo
       if (lazy) {
         ProfSpan ps(h, ST_BEV, st);
         launch_bev_segs_to_nhwc(bev, bev_dtype, h->bev_nhwc, DDH_BF16, h->need_seg, h->seg_nw32,
-                                h->seg_px, B, s.bev_channels, s.bev_h, s.bev_w, st);
+                                (h->host_map_call && h->seg_px_call == 16) ? -16 : h->seg_px_call, B,
+                                s.bev_channels, s.bev_h, s.bev_w, st);
         h->launches++;
       }
       { ProfSpan ps(h, ST_CONV, st);
@@ -1090,8 +1103,9 @@ int forward_range(ddh_handle* h, const float* ego, const float* agents, const vo
   // ---- BEV map -> NHWC in the engine's operand type.  NCHW input with H <= 64: rows are
   // converted on demand before each conv call (only rows a conv will read); otherwise up front.
   const void* bevn = bev;
+  if (s0 == 0) pick_segments(h);
   const bool lazy = bev_layout == DDH_NCHW && h->lazy_layout && h->seg_nw32 > 0 && !h->profiling_eager;
-  const int seg_shift = h->seg_px == 16 ? 4 : 3;
+  const int seg_shift = h->seg_px_call == 64 ? 6 : h->seg_px_call == 32 ? 5 : (h->seg_px_call == 16 ? 4 : 3);
   unsigned int* need_seg = lazy ? h->need_seg + (size_t)s0 * h->seg_nw32 : nullptr;
   unsigned int* done_seg = lazy ? h->done_seg + (size_t)s0 * h->seg_nw32 : nullptr;
   { ProfSpan ps(h, ST_BEV, st);
@@ -1173,7 +1187,7 @@ int forward_range(ddh_handle* h, const float* ego, const float* agents, const vo
                   P, s.bev_h, s.bev_w, h->rcap, oc, st); }
       if (lazy) {
         ProfSpan ps(h, ST_BEV, st);
-        launch_bev_segs_to_nhwc(bev, bev_dtype, v.bev_nhwc, want_dtype, need_seg, h->seg_nw32, h->seg_px,
+        launch_bev_segs_to_nhwc(bev, bev_dtype, v.bev_nhwc, want_dtype, need_seg, h->seg_nw32, h->seg_px_call,
                                 B, s.bev_channels, s.bev_h, s.bev_w, st);
         h->launches++;
         if (layout_event_pending) {   // the next chunk may start: its layout runs under our conv
@@ -1412,16 +1426,18 @@ int ddh_forward_host(ddh_handle* h, const float* ego, const float* agents, const
   // engine's in-kernel one) reads only the segments the conv calls need straight across PCIe,
   // ~20 % of the map instead of all of it.
   const void* bev_dev = nullptr;
+  h->host_map_call = false;
+  const bool resident_b = h->res2_ok && h->precision == DDH_PREC_BF16 && B <= RES_MAX_B;
   if (h->host_zero_copy && bev_layout == DDH_NCHW && h->lazy_layout) {
-    const bool resident = h->res2_ok && h->precision == DDH_PREC_BF16 && B <= RES_MAX_B;
-    const int spr = s.bev_w / h->seg_px, bits = s.bev_h * spr;
-    const bool lazy_ok = (s.bev_w % h->seg_px == 0 && bits <= 2048);
+    const bool resident = resident_b;
+    const bool lazy_ok = (s.bev_w % 8 == 0 && s.bev_h * (s.bev_w / std::min(64, (int)s.bev_w)) <= 2048);
     cudaPointerAttributes at;
     if ((resident || lazy_ok) && cudaPointerGetAttributes(&at, bev) == cudaSuccess &&
         at.type == cudaMemoryTypeHost && at.devicePointer != nullptr)
       bev_dev = at.devicePointer;
     else
       cudaGetLastError();   // pageable memory: clear the sticky "invalid value"
+    h->host_map_call = bev_dev != nullptr;
   }
   const size_t bev_stage = bev_dev ? 0 : bev_bytes;
   if (B > h->host_cap_B || bev_stage > h->host_bev_bytes) {
@@ -1450,6 +1466,7 @@ int ddh_forward_host(ddh_handle* h, const float* ego, const float* agents, const
   int rc = ddh_forward(h, h->hs_ego, h->hs_agents, bev_dev, bev_dtype, bev_layout, h->hs_noise,
                        h->hs_traj, h->hs_modes, h->hs_scores, reinterpret_cast<int64_t*>(h->hs_idx),
                        B, stream);
+  h->host_map_call = false;
   if (rc) return rc;
   if (out_traj) CU_TRY(h, cudaMemcpyAsync(out_traj, h->hs_traj, (size_t)B * P * 3 * 4, cudaMemcpyDeviceToHost, st));
   if (out_modes) CU_TRY(h, cudaMemcpyAsync(out_modes, h->hs_modes, (size_t)B * A * P * 3 * 4, cudaMemcpyDeviceToHost, st));
@@ -1481,6 +1498,10 @@ int ddh_set_option(ddh_handle* h, const char* name, int value) {
   else if (n == "persistent_conv") h->persistent_conv = value;
   else if (n == "conv_timeline") h->conv_timeline = value;
   else if (n == "host_zero_copy") h->host_zero_copy = value;
+  else if (n == "host_segment") {
+    if (value != 16 && value != 32 && value != 64) return fail(h, DDH_ERR_BAD_ARG, "ddh_set_option: host_segment must be 16, 32 or 64");
+    h->host_seg_px = value;
+  }
   else if (n == "layout_segment") {
     if (value != 8 && value != 16) return fail(h, DDH_ERR_BAD_ARG, "ddh_set_option: layout_segment must be 8 or 16");
     if (h->seg_px != value) { h->seg_px = value; cudaDeviceSynchronize(); free_all(h->owned_ws); h->cap_B = 0; h->chain_prog.clear(); }

@@ -325,6 +325,68 @@ __global__ void __launch_bounds__(256) bev_segs_to_nhwc_kernel(
   }
 }
 
+// 32-pixel segments with lanes along the pixels: 8 consecutive lanes read 128 contiguous bytes of one
+// channel plane.  Used when the source map is pinned HOST memory read in place across PCIe
+// (ddh_forward_host): requests of 128 bytes instead of 32 keep the link busy.
+template <typename TI, typename TO, int PXT>
+__global__ void __launch_bounds__(256) bev_segs_px_to_nhwc_kernel(
+    const TI* __restrict__ src, TO* __restrict__ dst, const unsigned int* __restrict__ todo,
+    int nw32, int C, int H, int W) {
+  constexpr int LDW = (sizeof(TO) == 2) ? 129 : 257;
+  constexpr int G = PXT / 4;          // lanes along the pixels (float4 each)
+  constexpr int CL = 256 / G;         // channels covered per iteration
+  extern __shared__ __align__(16) unsigned char seg_raw[];
+  uint32_t* tile_u32 = reinterpret_cast<uint32_t*>(seg_raw);
+  TO* tile = reinterpret_cast<TO*>(seg_raw);
+  constexpr int LDE = LDW * 4 / sizeof(TO);
+  __shared__ unsigned short list[2048];
+  __shared__ int cnt[65];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int HW = H * W, segs_per_row = W / PXT;
+  unsigned int word = 0;
+  if (tid < nw32) word = todo[(size_t)b * nw32 + tid];
+  if (tid < 64) cnt[tid] = __popc(word);
+  __syncthreads();
+  if (tid < nw32) {
+    int off = 0;
+    for (int i = 0; i < tid; ++i) off += cnt[i];
+    while (word) {
+      const int bit = __ffs((int)word) - 1;
+      word &= word - 1;
+      list[off++] = (unsigned short)(tid * 32 + bit);
+    }
+    if (tid == nw32 - 1) cnt[64] = off;
+  }
+  __syncthreads();
+  const int n = cnt[64];
+  const int px4 = tid % G, cl = tid / G, lane = tid & 31, warp = tid >> 5;
+  constexpr int WORDS = 256 * sizeof(TO) / 4;
+  for (int i = blockIdx.y; i < n; i += gridDim.y) {
+    const int sidx = list[i];
+    const int y = sidx / segs_per_row;
+    const int px0 = y * W + (sidx - y * segs_per_row) * PXT;
+    const TI* sp = src + (size_t)b * C * HW + px0 + px4 * 4;
+    float4 v[256 / CL];
+#pragma unroll
+    for (int k = 0; k < 256 / CL; ++k) v[k] = ld4<TI>(sp + (size_t)(k * CL + cl) * HW);
+    __syncthreads();   // previous tile fully written out
+#pragma unroll
+    for (int k = 0; k < 256 / CL; ++k) {
+      const int c = k * CL + cl;
+      tile[(px4 * 4 + 0) * LDE + c] = (TO)v[k].x;
+      tile[(px4 * 4 + 1) * LDE + c] = (TO)v[k].y;
+      tile[(px4 * 4 + 2) * LDE + c] = (TO)v[k].z;
+      tile[(px4 * 4 + 3) * LDE + c] = (TO)v[k].w;
+    }
+    __syncthreads();
+    uint32_t* d = reinterpret_cast<uint32_t*>(dst + ((size_t)b * HW + px0) * C);
+    for (int px = warp; px < PXT; px += 8) {
+#pragma unroll
+      for (int w = lane; w < WORDS; w += 32) d[(size_t)px * WORDS + w] = tile_u32[px * LDW + w];
+    }
+  }
+}
+
 template <typename TI, typename TO>
 static void bev_segs_launch(const void* src, void* dst, const unsigned int* todo, int nw32, int seg,
                             int B, int C, int H, int W, cudaStream_t st) {
@@ -333,7 +395,22 @@ static void bev_segs_launch(const void* src, void* dst, const unsigned int* todo
   dim3 grid(B, ysplit);
   // 8-pixel segments: four per step (consecutive list entries are usually neighbours in x, so a
   // thread's reads of one channel plane coalesce into 64/128-byte runs); 16-pixel: two per step
-  if (seg == 8)
+  if (seg == 64) {
+    constexpr int smem64 = 64 * ((sizeof(TO) == 2) ? 129 : 257) * 4;
+    static bool once = false;
+    if (!once) {
+      cudaFuncSetAttribute(bev_segs_px_to_nhwc_kernel<TI, TO, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64);
+      once = true;
+    }
+    bev_segs_px_to_nhwc_kernel<TI, TO, 64><<<grid, 256, smem64, st>>>(
+        reinterpret_cast<const TI*>(src), reinterpret_cast<TO*>(dst), todo, nw32, C, H, W);
+  } else if (seg == 32)
+    bev_segs_px_to_nhwc_kernel<TI, TO, 32><<<grid, 256, 32 * ((sizeof(TO) == 2) ? 129 : 257) * 4, st>>>(
+        reinterpret_cast<const TI*>(src), reinterpret_cast<TO*>(dst), todo, nw32, C, H, W);
+  else if (seg == -16)   // 16-pixel segments, lanes along the pixels (pinned host source)
+    bev_segs_px_to_nhwc_kernel<TI, TO, 16><<<grid, 256, 16 * ((sizeof(TO) == 2) ? 129 : 257) * 4, st>>>(
+        reinterpret_cast<const TI*>(src), reinterpret_cast<TO*>(dst), todo, nw32, C, H, W);
+  else if (seg == 8)
     bev_segs_to_nhwc_kernel<TI, TO, 8, 4><<<grid, 256, 4 * 8 * 256 * sizeof(TO), st>>>(
         reinterpret_cast<const TI*>(src), reinterpret_cast<TO*>(dst), todo, nw32, C, H, W);
   else

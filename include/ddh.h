@@ -203,6 +203,8 @@ DDH_API int ddh_set_concurrency(ddh_handle *h, int chunks, int min_chunk_scenes)
  *   "layout_segment"     8  pixels per on-demand layout segment (8 or 16)
  *   "host_zero_copy"     1  ddh_forward_host: a pinned NCHW bev_feature is read in place across PCIe by
  *                           the on-demand layout pass (only the needed segments) instead of copied whole
+ *   "host_segment"      64  pixels per segment when the map is read in place from pinned host memory
+ *                           (16, 32 or 64: 256-byte PCIe reads measured fastest)
  *   "persistent_conv"    1  value_proj conv as one persistent CTA per SM with dedicated epilogue
  *                           warps (tc_conv2_kernel); 0: one CTA per scene (tc_conv_kernel)
  *   "chain_timeline"    -1  index (step * layers + layer) of the chain launch that stamps clock64
