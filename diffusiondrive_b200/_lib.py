@@ -68,6 +68,9 @@ SIGNATURES = {
                               C.c_int, C.c_void_p]),
     "ddh_forward_host": (C.c_int, [C.c_void_p, _fp, _fp, _fp, C.c_int, C.c_int, _fp, _fp, _fp, _fp,
                                    _fp, C.c_int, C.c_void_p]),
+    "ddh_bev_producer_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "ddh_bev_producer": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, C.c_int, _fp, C.c_void_p]),
     "ddh_last_launch_count": (C.c_int, [C.c_void_p]),
     "ddh_set_concurrency": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "ddh_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "_ddh.so")
 STAMP = os.path.join(HERE, "_ddh.so.stamp")
-SOURCES = ["ddh_api.cu", "kernels_simt.cu", "kernels_tc.cu", "kernels_chain.cu", "kernels_res2.cu"]
+SOURCES = ["ddh_api.cu", "kernels_simt.cu", "kernels_tc.cu", "kernels_chain.cu", "kernels_producer.cu", "kernels_res2.cu"]
 HEADERS = ["common.cuh", "kernels.h", "kernels_chain.h", "kernels_res2.h", "tc_ptx.cuh", "geom.cuh", os.path.join("..", "..", "include", "ddh.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -1476,6 +1476,36 @@ int ddh_forward_host(ddh_handle* h, const float* ego, const float* agents, const
   return DDH_OK;
 }
 
+size_t ddh_bev_producer_scratch_bytes(int B, int grid, int bev_channels) {
+  if (B <= 0 || grid <= 0 || bev_channels <= 0) return 0;
+  return bev_producer_scratch_bytes(B, grid, bev_channels);
+}
+
+int ddh_bev_producer(const float* keyval_tokens, const float* bev_map, const float* weight,
+                     const float* bias, const float* ln_weight, const float* ln_bias, void* out,
+                     int out_dtype, int B, int H, int W, int grid, int bev_channels, void* scratch,
+                     void* stream) {
+  if (!keyval_tokens || !bev_map || !weight || !bias || !ln_weight || !ln_bias || !out || !scratch || B <= 0)
+    return fail(nullptr, DDH_ERR_BAD_ARG, "ddh_bev_producer: null argument or B <= 0");
+  if (out_dtype != DDH_F32 && out_dtype != DDH_BF16)
+    return fail(nullptr, DDH_ERR_BAD_ARG, "ddh_bev_producer: bad output dtype");
+  if (H <= 0 || W <= 0 || W % 32 || (H * W) % 32 || grid < 1 || grid > 64 || bev_channels < 1 ||
+      bev_channels > 128 || bev_channels % 4)
+    return fail(nullptr, DDH_ERR_UNSUPPORTED, "ddh_bev_producer: need W % 32 == 0, grid in [1, 64], bev_channels % 4 == 0 and <= 128");
+  if ((reinterpret_cast<uintptr_t>(keyval_tokens) | reinterpret_cast<uintptr_t>(bev_map) |
+       reinterpret_cast<uintptr_t>(weight) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(scratch) |
+       reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(ln_weight) | reinterpret_cast<uintptr_t>(ln_bias)) & 15)
+    return fail(nullptr, DDH_ERR_ALIGNMENT, "ddh_bev_producer: pointers must be 16-byte aligned");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, DDH_ERR_CUDA, "ddh_bev_producer: no CUDA device (there is no CPU fallback)");
+  const int e = launch_bev_producer(keyval_tokens, bev_map, weight, bias, ln_weight, ln_bias, out,
+                                    out_dtype == DDH_BF16 ? 1 : 0, B, H, W, grid, bev_channels,
+                                    reinterpret_cast<float*>(scratch), reinterpret_cast<cudaStream_t>(stream));
+  if (e) return fail(nullptr, DDH_ERR_CUDA, std::string("ddh_bev_producer: ") + cudaGetErrorString((cudaError_t)e));
+  return DDH_OK;
+}
+
 int ddh_last_launch_count(const ddh_handle* h) { return h ? h->launches : 0; }
 
 int ddh_set_concurrency(ddh_handle* h, int chunks, int min_chunk_scenes) {

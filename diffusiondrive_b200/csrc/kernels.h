@@ -56,6 +56,12 @@ void launch_matvec(const float* W, const float* x, const float* b, float* y, int
 void launch_time_sinemb(float* emb, int dim, int timestep, cudaStream_t st);
 void launch_pack_hilo(const float* w, __nv_bfloat16* dst, int n_out, int k, cudaStream_t st);
 
+// ---- kernels_producer.cu (cross_bev_feature producer, transfuser_model_v2.py:121-140)
+size_t bev_producer_scratch_bytes(int B, int g, int cb);
+int launch_bev_producer(const float* tok, const float* map, const float* w, const float* bias,
+                        const float* ln_g, const float* ln_b, void* out, int out_bf16, int B, int H, int W,
+                        int g, int cb, float* scratch, cudaStream_t st);
+
 // ---- kernels_tc.cu (tcgen05 / TMEM / TMA engine) ----------------------------------
 // W is described by a TMA tensor map over a bf16 [N_total][K] matrix (box 64 x 256,
 // 128-byte swizzle).  A is bf16 [M][lda] (dense) or gathered from the NHWC bf16 BEV map.

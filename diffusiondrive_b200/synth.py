@@ -180,3 +180,50 @@ def make_noise(batch: int, seed: int = SEED_NOISE, num_anchors: int = 20, num_po
         g.manual_seed(seed * 1_000_003 + start + i)
         out[i] = torch.randn(num_anchors, num_poses, 2, generator=g)
     return out
+
+
+SEED_AGENT = 4000
+AGENT_GAIN = 1.0          # variance gain of the random conv / linear weights (see make_agent_state_dict)
+
+
+def make_agent_state_dict(agent, seed: int = SEED_AGENT) -> Dict[str, torch.Tensor]:
+    """Random weights for every tensor of a ``DiffusionDriveAgent`` (same names as the reference
+    ``V2TransfuserModel``), drawn in the module's own state_dict order from one seeded CPU
+    generator; the planning head's tensors are those of ``make_state_dict`` so that the head
+    fixtures stay comparable.  BatchNorm running statistics are perturbed (eval mode uses them)."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    head_sd = make_state_dict()
+    out: Dict[str, torch.Tensor] = {}
+    for name, t in agent.state_dict().items():
+        leaf = name.rsplit(".", 1)[-1]
+        if name.startswith("_trajectory_head."):
+            out[name] = head_sd[name[len("_trajectory_head."):]].clone()
+        elif leaf == "num_batches_tracked":
+            out[name] = torch.zeros_like(t)
+        elif leaf == "running_var":
+            out[name] = 1.0 + 0.2 * torch.rand(t.shape, generator=g)
+        elif leaf == "running_mean":
+            out[name] = 0.1 * torch.randn(t.shape, generator=g)
+        elif t.dim() == 1 and leaf == "weight":            # BatchNorm / LayerNorm scale
+            out[name] = 1.0 + 0.1 * torch.randn(t.shape, generator=g)
+        elif "embedding" in name or leaf == "pos_emb":
+            out[name] = 0.5 * torch.randn(t.shape, generator=g)
+        elif t.dim() == 1:                                  # biases
+            out[name] = 0.05 * torch.randn(t.shape, generator=g)
+        else:
+            fan_in = int(np.prod(t.shape[1:]))
+            # He-style scale keeps activations O(1) through the ReLU stacks
+            out[name] = torch.randn(t.shape, generator=g) * math.sqrt(AGENT_GAIN / fan_in)
+        out[name] = out[name].to(t.dtype).contiguous()
+    return out
+
+
+def make_agent_inputs(batch: int, seed: int = SEED_AGENT + 1) -> Dict[str, torch.Tensor]:
+    """camera (B,3,256,1024), LiDAR histogram (B,1,256,256), status (B,8): the feature dict of
+    TransfuserFeatureBuilder (transfuser_features.py:25-139), iid stand-ins."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    return {"camera_feature": torch.rand(batch, 3, 256, 1024, generator=g),
+            "lidar_feature": (torch.rand(batch, 1, 256, 256, generator=g) > 0.9).float(),
+            "status_feature": torch.randn(batch, 8, generator=g)}

@@ -181,6 +181,22 @@ DDH_API int ddh_forward_host(ddh_handle *h, const float *ego, const float *agent
                      float *out_modes, float *out_scores, int64_t *out_mode_idx, int B,
                      void *stream);
 
+/* cross_bev_feature producer: the stage of V2TransfuserModel.forward
+ * that builds the head's BEV input (transfuser_model_v2.py:121-140 with bev_proj, :96):
+ *   out[b,y,x,:] = LayerNorm(ReLU(W . cat(bilinear_up(keyval tokens)[b,:,y,x], bev_map[b,:,y,x]) + bias))
+ *   keyval_tokens [B, grid*grid, 256] f32   keyval[:, :-1] of :115-119 (token t = y*grid + x)
+ *   bev_map       [B, Cb, H, W] f32         bev_feature_upscale, NCHW (:110)
+ *   weight [256, 256+Cb], bias / ln_weight / ln_bias [256]   bev_proj.{0,2}
+ *   out           [B, H, W, 256] f32 or bf16 (NHWC: what ddh_forward takes with DDH_NHWC; the
+ *                 reference's permute to NCHW, :138-140, is not materialised)
+ *   scratch       ddh_bev_producer_scratch_bytes(B, grid, Cb) bytes of device memory
+ * Device pointers, 16-byte aligned; asynchronous on `stream`; W % 32 == 0. */
+DDH_API size_t ddh_bev_producer_scratch_bytes(int B, int grid, int bev_channels);
+DDH_API int ddh_bev_producer(const float *keyval_tokens, const float *bev_map, const float *weight,
+                     const float *bias, const float *ln_weight, const float *ln_bias, void *out,
+                     int out_dtype, int B, int H, int W, int grid, int bev_channels, void *scratch,
+                     void *stream);
+
 /* Number of kernel launches issued by the last ddh_forward on this handle. */
 DDH_API int ddh_last_launch_count(const ddh_handle *h);
 

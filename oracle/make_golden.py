@@ -116,9 +116,50 @@ def _save(name, traj, reg, cls, meta):
     print(f"wrote {path}: {os.path.getsize(path) / 1024:.1f} KiB")
 
 
+def make_agent_fixture(tmp):
+    """BASELINE configs[3]: the LIVE reference V2TransfuserModel (timm stand-in on torchvision's
+    resnet34, oracle/ref_import.py) on seeded synthetic weights / sensors, batch 1: the planned
+    trajectory, all-mode poses and scores, the queries and a subsample of cross_bev_feature."""
+    from diffusiondrive_b200.agent import DiffusionDriveAgent
+    anchors = synth.make_state_dict()["plan_anchor"].numpy()
+    mine = DiffusionDriveAgent(anchors, precision="fp32").eval()      # (only to enumerate tensor names)
+    sd = synth.make_agent_state_dict(mine)
+    apath = os.path.join(tmp, "anchors20_agent.npy")
+    np.save(apath, anchors)
+    ref, _cfg = ref_import.build_reference_model(sd, apath)
+    feats = synth.make_agent_inputs(1)
+    noise = synth.make_noise(1)
+    cap = {}
+    h1 = ref._trajectory_head.register_forward_pre_hook(
+        lambda m, a: cap.update(ego=a[0].clone(), agents=a[1].clone(), bev=a[2].clone()))
+    h2 = ref._trajectory_head.diff_decoder.register_forward_hook(
+        lambda m, i, o: cap.update(reg=o[0][-1].clone(), cls=o[1][-1].clone()))
+    try:
+        with torch.no_grad(), _InjectNoise(noise):
+            out = ref(feats)
+    finally:
+        h1.remove(), h2.remove()
+    path = os.path.join(GOLDEN_DIR, "full_agent_b1.npz")
+    np.savez_compressed(
+        path, trajectory=out["trajectory"].numpy(), trajectory_modes=cap["reg"].numpy(),
+        trajectory_scores=cap["cls"].numpy(), mode_idx=cap["cls"].argmax(-1).numpy().astype(np.int64),
+        agent_states=out["agent_states"].numpy(), agent_labels=out["agent_labels"].numpy(),
+        ego_query=cap["ego"].numpy(), agents_query=cap["agents"].numpy(),
+        cross_bev_sub=cap["bev"][:, :, ::8, ::8].numpy(), cross_bev_abs_mean=np.float32(cap["bev"].abs().mean()),
+        bev_semantic_sub=out["bev_semantic_map"][:, :, ::16, ::16].numpy(),
+        meta=np.frombuffer(json.dumps({"torch": torch.__version__, "seed_agent": synth.SEED_AGENT,
+                                       "gain": synth.AGENT_GAIN, "params": int(sum(p.numel() for p in ref.parameters())),
+                                       "source": "live reference V2TransfuserModel via oracle/ref_import.py"}).encode(),
+                           dtype=np.uint8))
+    print(f"wrote {path}: {os.path.getsize(path) / 1024:.1f} KiB")
+
+
 def main():
     torch.set_num_threads(os.cpu_count() or 1)
     tmp = tempfile.mkdtemp()
+    if "--agent-only" in sys.argv:
+        make_agent_fixture(tmp)
+        return
     meta_base = {"torch": torch.__version__, "seed_weights": synth.SEED_WEIGHTS,
                  "seed_features": synth.SEED_FEATURES, "seed_noise": synth.SEED_NOISE,
                  "source": "live reference TrajectoryHead via oracle/ref_import.py"}
@@ -170,6 +211,8 @@ def main():
     t, r, c = run_reference_steps(head, mod, feats, noise, step_num=3)
     _save("stress_b2", t, r, c,
           dict(meta_base, batch=B, anchors=64, steps=3, layers=4, bev=[128, 128]))
+
+    make_agent_fixture(tmp)
 
     # ---- DDIM table pin (oracle/ddim.py is a restatement: "parity unpinned" upstream)
     from oracle.ddim import DDIMSchedulerRestated

@@ -69,7 +69,7 @@ def load_reference():
 
     # stub only what is really absent from this image
     import importlib.util
-    missing = tuple(n for n in _STUB_TOP if importlib.util.find_spec(n) is None)
+    missing = tuple(n for n in _STUB_TOP if n not in sys.modules and importlib.util.find_spec(n) is None)
     finder = _Finder()
     finder.names = missing
     sys.meta_path.insert(0, finder)
@@ -128,3 +128,56 @@ def build_reference_head(state_dict, anchors_npy_path: str, num_layers: int = 2)
     missing, unexpected = head.load_state_dict(state_dict, strict=True)
     assert not missing and not unexpected
     return head.eval(), cfg
+
+
+# ------------------------------------------------------------------------------------------
+# Full model (BASELINE configs[3]): V2TransfuserModel needs ``timm.create_model(...,
+# features_only=True)``; timm is absent, so a functional stand-in built on torchvision's resnet34
+# is installed: an ``nn.ModuleDict`` with timm's child names (conv1, bn1, act1, maxpool,
+# layer1..4), ``return_layers`` (5 entries, so the reference skips the stem: start_index = 1,
+# transfuser_backbone.py:62-65) and ``feature_info.info``.
+def _install_timm_shim():
+    import torch.nn as nn
+    import torchvision
+
+    class FeatureNet(nn.ModuleDict):
+        def __init__(self, in_chans):
+            m = torchvision.models.resnet34(weights=None)
+            if in_chans != 3:
+                m.conv1 = nn.Conv2d(in_chans, 64, 7, 2, 3, bias=False)
+            super().__init__({"conv1": m.conv1, "bn1": m.bn1, "act1": m.relu, "maxpool": m.maxpool,
+                              "layer1": m.layer1, "layer2": m.layer2, "layer3": m.layer3,
+                              "layer4": m.layer4})
+            self.return_layers = {"act1": "0", "layer1": "1", "layer2": "2", "layer3": "3", "layer4": "4"}
+            self.feature_info = types.SimpleNamespace(info=[
+                {"num_chs": c, "reduction": r} for c, r in zip((64, 64, 128, 256, 512), (2, 4, 8, 16, 32))])
+
+    def create_model(name, pretrained=False, features_only=True, in_chans=3, **kw):
+        assert name == "resnet34" and features_only
+        return FeatureNet(in_chans)
+
+    timm = types.ModuleType("timm")
+    timm.create_model = create_model
+    timm.__spec__ = importlib.machinery.ModuleSpec("timm", None)
+    sys.modules["timm"] = timm
+
+
+def build_reference_model(state_dict, anchors_npy_path: str):
+    """The live reference ``V2TransfuserModel`` (transfuser_model_v2.py:19-162) with ``state_dict``."""
+    _install_timm_shim()
+    for name in [n for n in sys.modules if n.startswith("navsim.agents.diffusiondrive.transfuser_backbone")]:
+        del sys.modules[name]
+    global _cached
+    _cached = None
+    _, TransfuserConfig, mod = load_reference()
+    import importlib
+    bb = importlib.import_module("navsim.agents.diffusiondrive.transfuser_backbone")
+    import timm as shim
+    bb.timm = shim
+    mod.TransfuserBackbone = bb.TransfuserBackbone
+    cfg = TransfuserConfig()
+    cfg.plan_anchor_path = anchors_npy_path
+    model = mod.V2TransfuserModel(cfg)
+    missing, unexpected = model.load_state_dict(state_dict, strict=True)
+    assert not missing and not unexpected
+    return model.eval(), cfg
