@@ -14,7 +14,8 @@ Mirrors the reference module of seulbinHwang/DiffusionDrive
 The module tree below only HOLDS the parameters; all arithmetic of ``forward_test``
 (:578-641) happens behind the C ABI in include/ddh.h.  There is no PyTorch or CPU
 fallback for inference.  Training (``forward_train``, :520-576) is outside the
-accelerated path and raises.
+accelerated path: in training mode ``forward`` delegates to the differentiable PyTorch
+restatement in train_torch.py (autograd is needed there).
 """
 from __future__ import annotations
 
@@ -284,10 +285,16 @@ class TrajectoryHead(nn.Module):
         (B,H,W,C), the layout the producer holds one line before the permute (:136-140).
         """
         if self.training:
-            raise NotImplementedError(
-                "diffusiondrive_b200.TrajectoryHead accelerates the inference path "
-                "(forward_test); forward_train (transfuser_model_v2.py:520-576) is out of scope. "
-                "Call .eval() first.")
+            # forward_train (:520-576) needs autograd: plain PyTorch on the module's device, NOT the
+            # accelerated path (train_torch.py); inference below never takes this branch
+            if targets is None:
+                raise ValueError("TrajectoryHead in training mode needs targets['trajectory'] "
+                                 "(transfuser_model_v2.py:510-518); call .eval() for inference")
+            if bev_layout != "NCHW":
+                raise ValueError("forward_train takes bev_feature as NCHW")
+            from . import train_torch
+            return train_torch.forward_train(self, ego_query, agents_query, bev_feature, targets,
+                                             ddim_alphas_cumprod(), noise=noise)
         return self.forward_test(ego_query, agents_query, bev_feature, bev_spatial_shape,
                                  status_encoding, global_img, noise=noise, bev_layout=bev_layout)
 

@@ -42,11 +42,11 @@ def test_anchor_file_constructor(tmp_path):
     assert tuple(head.plan_anchor.shape) == (20, 8, 2)
 
 
-def test_no_cpu_fallback_and_training_raises():
+def test_no_cpu_fallback_for_inference():
     head, sd = _head()
     ft = synth.make_features(1)
     head.train()
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError, match="targets"):      # training mode needs targets (forward_train)
         head(ft["ego_query"], ft["agents_query"], ft["bev_feature"], (64, 64), ft["status_encoding"])
     head.eval()
     with pytest.raises(RuntimeError, match="no CPU fallback"):
