@@ -1,6 +1,6 @@
 """GPU diagnostic of the resident (one-launch) engine: stage taps against the oracle trace on a
 1-step / 1-layer head, end-to-end parity on the default head for several batch sizes, the old
-small-batch engine beside it, batch-1 latency (stream launches and CUDA-graph replay) and the
+chain engine beside it, batch-1 latency (stream launches and CUDA-graph replay) and the
 in-kernel clock64 timeline.
 
 Usage (GPU box):  python tools/res_diag.py [stage|full|time|all]
@@ -13,7 +13,6 @@ import time
 import numpy as np
 import torch
 
-os.environ.setdefault("DDH_DEBUG_TAPS", "1")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
@@ -21,7 +20,7 @@ from diffusiondrive_b200 import HeadConfig, TrajectoryHead, synth, _lib  # noqa:
 from oracle import head_oracle  # noqa: E402
 
 
-RES_MODE = int(os.environ.get("RES_MODE", "2"))
+RES_MODE = 2
 
 
 def err(a, b):
@@ -31,11 +30,13 @@ def err(a, b):
 
 
 def make_head(cfg, sd, res):
-    os.environ["DDH_RES"] = str(int(res))
+    """res = 2: group-resident engine (default for B <= 24); 0: chain engine for every batch size."""
     head = TrajectoryHead(8, 1024, 256, None, cfg, plan_anchor=sd["plan_anchor"].numpy(), precision="bf16")
     head.load_state_dict(sd)
     head = head.cuda().eval()
-    ft = synth.make_features(1)     # the handle reads DDH_RES when it is created (first forward)
+    head.set_option("debug_taps", 1)
+    head.set_option("resident_engine", 1 if res else 0)
+    ft = synth.make_features(1)
     head(ft["ego_query"].cuda(), ft["agents_query"].cuda(), ft["bev_feature"].cuda(), noise=synth.make_noise(1).cuda())
     torch.cuda.synchronize()
     return head
@@ -73,7 +74,7 @@ def run_stage(B=2):
 def run_full():
     sd = synth.make_state_dict()
     cfg = HeadConfig()
-    heads = {"res": make_head(cfg, sd, RES_MODE), "lat": make_head(cfg, sd, 0)}
+    heads = {"res": make_head(cfg, sd, RES_MODE), "chain": make_head(cfg, sd, 0)}
     for B in (1, 2, 3, 8):
         ft = synth.make_features(B)
         nz = synth.make_noise(B)
@@ -99,7 +100,7 @@ def run_full():
 def run_time():
     sd = synth.make_state_dict()
     cfg = HeadConfig()
-    modes = (("res", RES_MODE),) if os.environ.get("ONLY_RES") else (("res", RES_MODE), ("res1", 1), ("lat", 0))
+    modes = (("res", RES_MODE),) if os.environ.get("ONLY_RES") else (("res", RES_MODE), ("chain", 0))
     for name, res in modes:
         head = make_head(cfg, sd, res)
         for B in ((1,) if os.environ.get("ONLY_RES") else (1, 2, 4, 8)):
