@@ -179,10 +179,8 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if rank == 0:
-            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-            os.environ["DDH_NCCL_LOG"] = os.path.join(ROOT, "gpurun_out", "nccl_rank0.log")
             os.environ.setdefault("NCCL_DEBUG", "INFO")
-            os.environ.setdefault("NCCL_DEBUG_FILE", os.environ["DDH_NCCL_LOG"])
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -685,26 +683,42 @@ def _bind_to_gpu_numa_node(local_rank: int):
         return {"error": repr(ex)}
 
 
+_STDOUT_CAPTURE = None
+
+
 def _nccl_log_tail():
-    """NCCL's own init lines (NCCL_DEBUG=INFO is sent to a file per rank so that stdout stays one
-    JSON line); the lines that name the transport / algorithm are kept."""
-    path = os.environ.get("DDH_NCCL_LOG")
-    if not path or not os.path.exists(path):
+    """NCCL's own init lines.  Everything libraries print on stdout is captured in a per-process
+    file (stdout itself stays ONE JSON line); the lines that name the NCCL version / transport are
+    returned for the JSON record and the whole capture is forwarded to stderr."""
+    if not _STDOUT_CAPTURE or not os.path.exists(_STDOUT_CAPTURE):
         return None
+    sys.stdout.flush()
     keep = []
-    with open(path, errors="replace") as fh:
-        for ln in fh:
-            if any(k in ln for k in ("NCCL version", "Init COMPLETE", "NVLS", "via P2P", "Channel 00/", "nRanks")):
-                keep.append(ln.strip()[-200:])
-    return keep[:12]
+    with open(_STDOUT_CAPTURE, errors="replace") as fh:
+        text = fh.read()
+    for ln in text.splitlines():
+        if "NCCL" in ln and any(k in ln for k in ("version", "Init COMPLETE", "NVLS", "via P2P", "Channel 00", "nRanks",
+                                                   "Using network", "comm 0x")):
+            keep.append(ln.strip()[-220:])
+    if text:
+        sys.stderr.write(text)
+    return keep[:16] or None
 
 
 def _claim_stdout() -> int:
     """Keep stdout clean for the ONE JSON line: libraries (NCCL prints its version banner on
     stdout) are sent to stderr; returns the fd of the real stdout."""
+    global _STDOUT_CAPTURE
     sys.stdout.flush()
     real = os.dup(1)
-    os.dup2(2, 1)
+    try:
+        import tempfile
+        fd, _STDOUT_CAPTURE = tempfile.mkstemp(prefix="ddh_bench_stdout_", suffix=".log")
+        os.dup2(fd, 1)
+        os.close(fd)
+    except Exception:
+        _STDOUT_CAPTURE = None
+        os.dup2(2, 1)
     return real
 
 

@@ -145,7 +145,8 @@ struct ddh_handle {
   int seg_px_call = 8;                         // granularity of the current call (pick_segments)
   bool host_map_call = false;                  // the current call reads a pinned host map in place
   int host_zero_copy = 1;                      // option "host_zero_copy": ddh_forward_host reads pinned maps in place
-  int persistent_conv = 1;                     // option "persistent_conv": tc_conv2_kernel (1) or one CTA per scene (0)
+  int persistent_conv = 2;                     // option "persistent_conv": 2 tc_conv3_kernel (combine on the tensor core),
+                                               // 1 tc_conv2_kernel (CUDA-core combine), 0 one CTA per scene
   int chain_timeline = -1;
   int conv_timeline = -1;                      // option "conv_timeline": index of the conv launch to stamp                     // option "chain_timeline": index of the chain launch to stamp
   bool profiling_eager = false;
@@ -1030,6 +1031,7 @@ int forward_fused(ddh_handle* h, const float* ego, const float* agents, const vo
   float* modes = out_modes ? out_modes : h->modes_buf;
   float* scores = out_scores ? out_scores : h->scores_buf;
   OdoConsts oc{s.lidar_max_x, s.lidar_max_y};
+  const int conv_mode = (h->persistent_conv >= 2 && A <= 64 && P == 8) ? 2 : (h->persistent_conv ? 1 : 0);
   auto fill = [&](ChainArgs& a) {
     a.B = B; a.A = A; a.Na = Na; a.P = P; a.spt = spt; a.n_tiles = n_tiles;
     a.anchors = h->anchors; a.noise = noise; a.img = h->img; a.pts = h->pts; a.q0t = h->q0t;
@@ -1064,7 +1066,7 @@ int forward_fused(ddh_handle* h, const float* ego, const float* agents, const vo
       gp.dbg = (h->conv_timeline == si * L + l) ? h->dbg + 256 : nullptr;
       gp.ent_slot = h->ent_slot; gp.ent_w = h->ent_w; gp.n_anchor = A; gp.ent_per_anchor = P * 4;
       gp.epi.out_f32 = h->s32; gp.epi.ldo32 = D; gp.epi.out_bf16 = h->s16; gp.epi.ldo16 = D;
-      launch_tc_conv(gp, pl.conv.map, B, st, h->persistent_conv != 0);
+      launch_tc_conv(gp, pl.conv.map, B, st, conv_mode);
       h->launches++; }
       { ProfSpan ps(h, ST_GEMM, st);
       ChainArgs& a = h->chain_prog[S + (size_t)si * L + l];
@@ -1206,7 +1208,7 @@ int forward_range(ddh_handle* h, const float* ego, const float* agents, const vo
           gp.dbg = h->tl_gemm < 0 ? h->dbg : nullptr;
           gp.ent_slot = v.ent_slot; gp.ent_w = v.ent_w; gp.n_anchor = A; gp.ent_per_anchor = P * 4;
           gp.epi.out_f32 = v.s32; gp.epi.ldo32 = D; gp.epi.out_bf16 = v.s16; gp.epi.ldo16 = D;
-          launch_tc_conv(gp, pl.conv.map, B, st, h->persistent_conv != 0);
+          launch_tc_conv(gp, pl.conv.map, B, st, h->persistent_conv != 0 ? 1 : 0);
           h->launches += 1;
         } else {
           gp.epi.out_f32 = v.V; gp.epi.ldo32 = D;

@@ -66,8 +66,9 @@ int launch_bev_producer(const float* tok, const float* map, const float* w, cons
 // W is described by a TMA tensor map over a bf16 [N_total][K] matrix (box 64 x 256,
 // 128-byte swizzle).  A is bf16 [M][lda] (dense) or gathered from the NHWC bf16 BEV map.
 void launch_tc_gemm(const GemmParams& p, const CUtensorMap& wmap, int n_total, cudaStream_t st);
-void launch_tc_conv(const GemmParams& p, const CUtensorMap& wmap, int B, cudaStream_t st,
-                    bool persistent = true);
+// mode 0: one CTA per scene; 1: persistent, CUDA-core combine; 2: persistent, combine on the tensor
+// core (n_anchor <= 64, ent_per_anchor == 32; other shapes fall back to mode 1)
+void launch_tc_conv(const GemmParams& p, const CUtensorMap& wmap, int B, cudaStream_t st, int mode = 1);
 int tc_conv_smem_bytes(int A, int ent_per_anchor);
 int tc_engine_init();   // sets max dynamic smem attributes; returns cudaError_t as int
 

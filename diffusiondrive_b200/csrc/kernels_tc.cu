@@ -1071,6 +1071,365 @@ tc_conv2_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap, in
   if (warp == 5) tmem_dealloc<NT * D>(tmem_base);
 }
 
+// ===================================================================================
+// tc_conv3_kernel: persistent conv with the bilinear x attention combine ON THE TENSOR CORE.
+//
+// The main loop swaps the operand roles of tc_conv2_kernel: the weight tile [256 channels x 64 k]
+// is the A operand (two M = 128 channel tiles) and the gathered patches [<= 256 pixel rows x 64 k]
+// are the B operand (N = 256, or 128 when the pass has <= 128 rows), so the accumulators hold
+// V^T: TMEM lane = output channel, column = pixel row.  A thread of the epilogue warps then owns one
+// channel: bias + ReLU + bf16 and its row of V^T goes straight into the K-major, 128-byte-swizzled
+// layout of a B operand [256 channels][K = pixel rows] (16-byte vector stores, the same pattern as
+// the chain kernel's operand writes).  The combine
+//     S[a, c] = sum_r Wc[a, r] * V[r, c]          (Wc: merged weights per anchor: the epilogue warps
+//                                                  build them from the entry tables while the main
+//                                                  loop runs -- duplicates of a pixel summed in entry
+//                                                  order by MATCH -- and scatter them after it)
+// is 8-16 more tcgen05.mma (A = Wc [128 anchor rows (only n_anchor valid) x K], B = V^T), whose
+// accumulator rows (lane = anchor) are written out as bf16 S.  The CUDA-core combine of
+// tc_conv2_kernel read 655 KB of staged fp32 per scene and was shared-memory-bandwidth bound
+// (~10 k cycles); here the epilogue is one drain pass plus 16 MMAs.
+// Numerics: V and the combine weights are rounded to bf16 before the weighted sum (fp32 accumulate).
+// Shared memory: V^T aliases pipeline stages 0-1 (128 KiB), Wc stage 2 (4 x 16 KiB K-chunks, only
+// the first n_anchor rows of each are written; the MMA's other rows read stale bytes whose
+// products land in accumulator rows nobody reads).
+// ===================================================================================
+constexpr int C3_VT_CHUNK = 256 * 128;     // V^T operand: 64 pixel rows (K) x 256 channels
+constexpr int C3_WC_OFF = 2 * C_STAGE;     // Wc operand region (pipeline stage 2)
+constexpr int C3_THREADS = C2_THREADS + 32;   // + warp 14: second MMA issuer (channel tile 1)
+
+__global__ void __launch_bounds__(C3_THREADS, 1)
+tc_conv3_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap, int B) {
+  constexpr int NS = C_NS, NT = C_NT;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
+  uint8_t* sm = smem_raw + pad;
+  const uint32_t sm_addr = raw_addr + pad;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int A = p.n_anchor;
+  float* S32 = p.epi.out_f32;
+  __nv_bfloat16* S16 = p.epi.out_bf16;
+  float* bias_s = reinterpret_cast<float*>(sm + C_PIPE);          // [256]
+  const uint32_t bar0 = sm_addr + C_PIPE + D * 4;
+  auto full = [&](int s) { return bar0 + s * 8; };
+  auto empty = [&](int s) { return bar0 + (NS + s) * 8; };
+  const uint32_t accum = bar0 + 2 * NS * 8, vt_ready = accum + 8, comb_done = accum + 16, passgo = accum + 24;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + C_PIPE + D * 4 + (2 * NS + 4) * 8);
+  constexpr int KC = 9 * (D / TC_BK);
+  constexpr int RPT = NT * 8;
+
+  if (threadIdx.x == 0) {
+    // two MMA issuers (a tcgen05.mma costs its issuing thread ~130-160 cycles whatever its shape;
+    // threads of different warps issue concurrently): each releases a stage / commits the pass
+    for (int s = 0; s < NS; ++s) { mbar_init(full(s), 128 + 1); mbar_init(empty(s), 2); }
+    mbar_init(accum, 2);
+    mbar_init(vt_ready, C2_EPI);
+    mbar_init(comb_done, 1);
+    mbar_init(passgo, C2_EPI);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc<NT * D>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  if (warp == 4 && lane == 0) tma_prefetch_desc(&wmap);
+  if (threadIdx.x < 64)
+    reinterpret_cast<float4*>(bias_s)[threadIdx.x] = __ldg(reinterpret_cast<const float4*>(p.epi.bias) + threadIdx.x);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ======================= producers: gather 3x3xC patches (B operand) ===============
+    const int tid = threadIdx.x;
+    const int j = tid & 7, rb = tid >> 3;
+    const uint32_t dst_base = rb * 128 + ((j ^ (rb & 7)) << 4);
+    int g = 0, pi = 0, sidx = 0;
+    int scene = blockIdx.x;
+    int nu = scene < B ? __ldg(p.nuniq + scene) : 0;
+    int yx0[RPT];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i)
+      yx0[i] = (scene < B && nu > 0) ? __ldg(p.upix + (size_t)scene * p.rcap + min(rb + 16 * i, nu - 1)) : 0;
+    while (scene < B) {
+      const int scene_n = scene + gridDim.x;
+      const int nu_n = scene_n < B ? __ldg(p.nuniq + scene_n) : 0;
+      int yxn[RPT];
+#pragma unroll
+      for (int i = 0; i < RPT; ++i)
+        yxn[i] = (scene_n < B && nu_n > 0) ? __ldg(p.upix + (size_t)scene_n * p.rcap + min(rb + 16 * i, nu_n - 1)) : 0;
+      const __nv_bfloat16* bev = reinterpret_cast<const __nv_bfloat16*>(p.bev) + (size_t)scene * p.H * p.W_ * D;
+      const int passes = (nu + NT * TC_BM - 1) / (NT * TC_BM);
+      for (int pass = 0; pass < passes; ++pass, ++pi) {
+        const int row_base = pass * NT * TC_BM;
+        const int rows_valid = min(NT * TC_BM, nu - row_base);
+        const int nt_active = (rows_valid + TC_BM - 1) / TC_BM;
+        if (pass > 0) {
+#pragma unroll
+          for (int i = 0; i < RPT; ++i)
+            yx0[i] = __ldg(p.upix + (size_t)scene * p.rcap + min(row_base + rb + 16 * i, nu - 1));
+        }
+        int rowoff[RPT];
+        uint32_t vmask[RPT];
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          const int r = rb + 16 * i;
+          rowoff[i] = 0;
+          vmask[i] = 0;
+          if (r < rows_valid) {
+            const int yx = yx0[i];
+            const int y = yx >> 16, x = yx & 0xffff;
+            rowoff[i] = (y * p.W_ + x) * D + j * 8;
+            const uint32_t xm = (x > 0 ? 1u : 0u) | 2u | (x + 1 < p.W_ ? 4u : 0u);
+            vmask[i] = (y > 0 ? xm : 0u) | (xm << 3) | (y + 1 < p.H ? (xm << 6) : 0u);
+          }
+        }
+        C2_STAMP(sidx == 1 && pass == 0 && tid == 0, 0);
+        if (pi > 0) mbar_wait(passgo, (uint32_t)(pi - 1) & 1u);   // V^T / Wc of the previous pass alias the pipeline
+        C2_STAMP(sidx == 1 && pass == 0 && tid == 0, 1);
+        for (int kc = 0; kc < KC; ++kc, ++g) {
+          const int s = g % NS;
+          mbar_wait(empty(s), ((g / NS) & 1) ^ 1);
+          C2_STAMP(sidx == 1 && pass == 0 && tid == 0 && (kc & 3) == 0, 2 + (kc >> 2));
+          const uint32_t a_dst = sm_addr + s * C_STAGE + dst_base;
+          const int tap = kc >> 2;
+          const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+          const int tapoff = (dy * p.W_ + dx) * D + (kc & 3) * TC_BK;
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) {
+            if (i < 8 * nt_active) {
+              const bool ok = (vmask[i] >> tap) & 1u;
+              const int off = ok ? rowoff[i] + tapoff : 0;
+              cp_async16(a_dst + i * 2048, bev + off, ok ? 16u : 0u);
+            }
+          }
+          cp_async_mbar_arrive_noinc(full(s));
+        }
+      }
+      scene = scene_n;
+      nu = nu_n;
+      ++sidx;
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) yx0[i] = yxn[i];
+    }
+  } else if (warp == 4) {
+    // ======================= TMA producer (weights: A operand) =========================
+    if (lane == 0) {
+      int g = 0, pi = 0;
+      for (int scene = blockIdx.x; scene < B; scene += gridDim.x) {
+        const int nu = __ldg(p.nuniq + scene);
+        const int passes = (nu + NT * TC_BM - 1) / (NT * TC_BM);
+        for (int pass = 0; pass < passes; ++pass, ++pi) {
+          if (pi > 0) mbar_wait(passgo, (uint32_t)(pi - 1) & 1u);
+          for (int kc = 0; kc < KC; ++kc, ++g) {
+            const int s = g % NS;
+            mbar_wait(empty(s), ((g / NS) & 1) ^ 1);
+            mbar_arrive_expect_tx(full(s), TC_B_TILE);
+            tma_load_2d(sm_addr + s * C_STAGE + NT * TC_A_TILE, &wmap, full(s), kc * TC_BK, 0);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5 || warp == 14) {
+    // ======================= MMA issuers: warp 5 channel tile 0 (+ the combine), warp 14 tile 1 ==
+    if (lane == 0) {
+      const int mt = warp == 5 ? 0 : 1;
+      const uint32_t idesc256 = umma_idesc_bf16_m128_n256();
+      const uint32_t idesc128 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+      int g = 0, sidx = 0;
+      uint32_t pi = 0;
+      for (int scene = blockIdx.x; scene < B; scene += gridDim.x, ++sidx) {
+        const int nu = __ldg(p.nuniq + scene);
+        const int passes = (nu + NT * TC_BM - 1) / (NT * TC_BM);
+        for (int pass = 0; pass < passes; ++pass, ++pi) {
+          const int rows_valid = min(NT * TC_BM, nu - pass * NT * TC_BM);
+          const int nt_active = (rows_valid + TC_BM - 1) / TC_BM;
+          const uint32_t idesc = nt_active == 2 ? idesc256 : idesc128;
+          for (int kc = 0; kc < KC; ++kc, ++g) {
+            const int s = g % NS;
+            mbar_wait(full(s), (g / NS) & 1);
+            tc_fence_after();
+            C2_STAMP(mt == 0 && sidx == 1 && pass == 0 && (kc & 3) == 0, 16 + (kc >> 2));
+            const uint32_t p_stage = sm_addr + s * C_STAGE;             // patches: B operand
+            const uint32_t w_stage = p_stage + NT * TC_A_TILE;          // weights: A operand
+#pragma unroll
+            for (int k4 = 0; k4 < TC_BK / 16; ++k4)
+              umma_bf16(tmem_base + mt * D, umma_desc_sw128(w_stage + mt * TC_A_TILE + k4 * 32),
+                        umma_desc_sw128(p_stage + k4 * 32), idesc, (kc == 0 && k4 == 0) ? 0u : 1u);
+            umma_commit(empty(s));
+          }
+          umma_commit(accum);
+          C2_STAMP(mt == 0 && sidx == 1 && pass == 0, 25);
+          if (mt == 0) {
+            // ---- combine: S^(pass)[a, c] = Wc[a, r] . V^T[c, r], K = the pass's pixel rows
+            mbar_wait(vt_ready, pi & 1u);
+            tc_fence_after();
+            const int kch = nt_active * 2;
+            for (int kc = 0; kc < kch; ++kc)
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4)
+                umma_bf16(tmem_base, umma_desc_sw128(sm_addr + C3_WC_OFF + kc * TC_A_TILE + k4 * 32),
+                          umma_desc_sw128(sm_addr + kc * C3_VT_CHUNK + k4 * 32), idesc256, (kc | k4) ? 1u : 0u);
+            umma_commit(comb_done);
+            C2_STAMP(sidx == 1 && pass == 0, 26);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp < 14) {
+    // ======================= epilogue warps ============================================
+    const int ew = warp - 6;                 // 0..7
+    const int q = warp & 3;                  // TMEM lane quarter
+    const int mt = ew >> 2;                  // channel tile (drain) / column half (final store)
+    const int etid = threadIdx.x - 6 * 32;   // 0..255
+    const int c = mt * TC_BM + q * 32 + lane;   // the channel this thread drains
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float bias_c = bias_s[c];
+    uint32_t pi = 0;
+    int sidx = 0;
+    for (int scene = blockIdx.x; scene < B; scene += gridDim.x, ++sidx) {
+      const int nu = __ldg(p.nuniq + scene);
+      if (nu == 0) {   // every sample point fell outside the grid: grid_sample returns zeros
+        for (int i = etid; i < A * D; i += C2_EPI) {
+          if (S32) S32[(size_t)scene * A * D + i] = 0.f;
+          if (S16) S16[(size_t)scene * A * D + i] = __float2bfloat16_rn(0.f);
+        }
+        continue;
+      }
+      // ---- merged combine weights of this warp's anchors (a = ew + 8 i), built while the main loop
+      // runs: lane k = entry k (pose, corner); entries of one anchor that hit the same unique pixel are
+      // summed in entry order by the first of them (MATCH groups the lanes), so sums are deterministic
+      int mslot[8];
+      float msum[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int a = ew + 8 * i;
+        mslot[i] = -1;
+        msum[i] = 0.f;
+        if (a < A) {
+          const int slot = __ldg(p.ent_slot + ((size_t)scene * A + a) * 32 + lane);
+          const float wv = __ldg(p.ent_w + ((size_t)scene * A + a) * 32 + lane);
+          const unsigned grp = __match_any_sync(0xffffffffu, slot);
+          const int most = __reduce_max_sync(0xffffffffu, __popc(grp));
+          unsigned m = grp;
+          float sum = 0.f;
+          for (int t = 0; t < most; ++t) {
+            const int src = m ? (__ffs((int)m) - 1) : lane;
+            const float wk = __shfl_sync(0xffffffffu, wv, src);
+            if (m) sum += wk;
+            m &= m - 1;
+          }
+          if (slot >= 0 && (__ffs((int)grp) - 1) == lane) { mslot[i] = slot; msum[i] = sum; }
+        }
+      }
+      const int passes = (nu + NT * TC_BM - 1) / (NT * TC_BM);
+      for (int pass = 0; pass < passes; ++pass, ++pi) {
+        const int row_base = pass * NT * TC_BM;
+        const int rows_valid = min(NT * TC_BM, nu - row_base);
+        const int nt_active = (rows_valid + TC_BM - 1) / TC_BM;
+        const int upa = nt_active * 16;          // 16-byte units (8 pixel rows) per anchor row of Wc
+        const int n_units = A * upa;
+        C2_STAMP(sidx == 1 && pass == 0 && etid == 0, 32);
+        mbar_wait(accum, pi & 1u);
+        tc_fence_after();
+        C2_STAMP(sidx == 1 && pass == 0 && etid == 0, 33);
+        for (int u = etid; u < n_units; u += C2_EPI) {
+          const int a = u / upa, k8 = u - a * upa;
+          *reinterpret_cast<uint4*>(sm + C3_WC_OFF + (k8 >> 3) * TC_A_TILE + a * 128 + (((k8 & 7) ^ (a & 7)) << 4)) =
+              make_uint4(0u, 0u, 0u, 0u);
+        }
+        named_bar_sync(1, C2_EPI);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int a = ew + 8 * i;
+          const int rr = mslot[i] - row_base;
+          if (mslot[i] >= 0 && rr >= 0 && rr < nt_active * TC_BM)
+            *reinterpret_cast<__nv_bfloat16*>(sm + C3_WC_OFF + (rr >> 6) * TC_A_TILE + a * 128 +
+                                              ((((rr & 63) >> 3) ^ (a & 7)) << 4) + (rr & 7) * 2) = __float2bfloat16_rn(msum[i]);
+        }
+        // ---- drain: this thread's channel row of V^T, 32 pixel rows at a time
+        const int nblk = nt_active * 4;
+#pragma unroll 1
+        for (int b = 0; b < nblk; ++b) {
+          uint32_t u32[32];
+          tmem_ld32(tlane + mt * D + b * 32, u32);
+          tmem_ld_wait();
+          uint8_t* dst = sm + (b >> 1) * C3_VT_CHUNK + c * 128;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 w;
+            uint32_t* wp = &w.x;
+#pragma unroll
+            for (int h2 = 0; h2 < 4; ++h2) {
+              const float lo = fmaxf(__uint_as_float(u32[8 * i + 2 * h2]) + bias_c, 0.f);
+              const float hi = fmaxf(__uint_as_float(u32[8 * i + 2 * h2 + 1]) + bias_c, 0.f);
+              const __nv_bfloat162 hh = __floats2bfloat162_rn(lo, hi);
+              wp[h2] = *reinterpret_cast<const uint32_t*>(&hh);
+            }
+            *reinterpret_cast<uint4*>(dst + ((((b & 1) * 4 + i) ^ (c & 7)) << 4)) = w;
+          }
+        }
+        C2_STAMP(sidx == 1 && pass == 0 && etid == 0, 34);
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(vt_ready);
+        // ---- S rows of this pass: anchor a = 32 q + lane, columns 128 mt .. + 127
+        mbar_wait(comb_done, pi & 1u);
+        tc_fence_after();
+        C2_STAMP(sidx == 1 && pass == 0 && etid == 0, 35);
+        const int a = q * 32 + lane;
+        if (q * 32 < A) {
+#pragma unroll 1
+          for (int b = 0; b < 4; ++b) {
+            uint32_t u32[32];
+            tmem_ld32(tlane + mt * 128 + b * 32, u32);
+            tmem_ld_wait();
+            if (a < A) {
+              const size_t o = ((size_t)scene * A + a) * D + mt * 128 + b * 32;
+              float v[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(u32[i]);
+              if (pass > 0) {   // same thread wrote it in the previous pass: deterministic RMW
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float4 old = *reinterpret_cast<const float4*>(S32 + o + 4 * i);
+                  v[4 * i] += old.x; v[4 * i + 1] += old.y; v[4 * i + 2] += old.z; v[4 * i + 3] += old.w;
+                }
+              }
+              if (pass + 1 < passes) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  *reinterpret_cast<float4*>(S32 + o + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+              } else if (S16) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  uint4 w;
+                  uint32_t* wp = &w.x;
+#pragma unroll
+                  for (int h2 = 0; h2 < 4; ++h2) {
+                    const __nv_bfloat162 hh = __floats2bfloat162_rn(v[8 * i + 2 * h2], v[8 * i + 2 * h2 + 1]);
+                    wp[h2] = *reinterpret_cast<const uint32_t*>(&hh);
+                  }
+                  *reinterpret_cast<uint4*>(S16 + o + 8 * i) = w;
+                }
+              }
+            }
+          }
+        }
+        C2_STAMP(sidx == 1 && pass == 0 && etid == 0, 40);
+        // V^T / Wc (generic-proxy writes, read by the MMA) and the accumulators may be overwritten
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(passgo);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<NT * D>(tmem_base);
+}
+
 int tc_engine_init() {
   cudaError_t e;
   e = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM);
@@ -1080,6 +1439,9 @@ int tc_engine_init() {
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(tc_conv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            227 * 1024);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(tc_conv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           C_PIPE + D * 4 + TC_BAR_BYTES + 1024);
   return (int)e;
 }
 
@@ -1101,7 +1463,7 @@ int tc_conv_smem_bytes(int A, int ent_per_anchor) {
   return C_PIPE + ((A * ent_per_anchor * 8 + 15) / 16) * 16 + D * 4 + TC_BAR_BYTES + 1024;
 }
 
-void launch_tc_conv(const GemmParams& p0, const CUtensorMap& wmap, int B, cudaStream_t st, bool persistent) {
+void launch_tc_conv(const GemmParams& p0, const CUtensorMap& wmap, int B, cudaStream_t st, int mode) {
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
@@ -1111,7 +1473,9 @@ void launch_tc_conv(const GemmParams& p0, const CUtensorMap& wmap, int B, cudaSt
   }
   GemmParams p = p0;
   p.M = num_sms;
-  if (persistent)
+  if (mode == 2 && p.n_anchor <= 64 && p.ent_per_anchor == 32)
+    tc_conv3_kernel<<<B < num_sms ? B : num_sms, C3_THREADS, C_PIPE + D * 4 + TC_BAR_BYTES + 1024, st>>>(p, wmap, B);
+  else if (mode >= 1)
     tc_conv2_kernel<<<B < num_sms ? B : num_sms, C2_THREADS, tc_conv_smem_bytes(p.n_anchor, p.ent_per_anchor), st>>>(p, wmap, B);
   else
     tc_conv_kernel<<<B, TC_THREADS, tc_conv_smem_bytes(p.n_anchor, p.ent_per_anchor), st>>>(p, wmap);

@@ -221,8 +221,9 @@ DDH_API int ddh_set_concurrency(ddh_handle *h, int chunks, int min_chunk_scenes)
  *                           the on-demand layout pass (only the needed segments) instead of copied whole
  *   "host_segment"      64  pixels per segment when the map is read in place from pinned host memory
  *                           (16, 32 or 64: 256-byte PCIe reads measured fastest)
- *   "persistent_conv"    1  value_proj conv as one persistent CTA per SM with dedicated epilogue
- *                           warps (tc_conv2_kernel); 0: one CTA per scene (tc_conv_kernel)
+ *   "persistent_conv"    2  value_proj conv as one persistent CTA per SM: 2 = bilinear x attention combine
+ *                           on the tensor core (tc_conv3_kernel), 1 = CUDA-core combine
+ *                           (tc_conv2_kernel); 0: one CTA per scene (tc_conv_kernel)
  *   "chain_timeline"    -1  index (step * layers + layer) of the chain launch that stamps clock64
  *                           into the "dbg" tap (CTA 0, second tile)
  *   "debug_taps"         0  keep fp32 copies of intermediate activations for ddh_debug_copy
