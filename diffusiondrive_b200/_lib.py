@@ -84,6 +84,14 @@ SIGNATURES = {
 _lib = None
 
 
+def use_library(path: str) -> None:
+    """Test hook: bind another build of the same ABI (the -DDDH_CHECKED library) for every handle
+    created from now on.  Existing ``TrajectoryHead`` instances keep the library they loaded."""
+    global _lib, LIB_PATH
+    LIB_PATH = path
+    _lib = None
+
+
 def load() -> C.CDLL:
     """Load the extension; fail loudly when it has not been built."""
     global _lib

@@ -14,6 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "_ddh.so")
 STAMP = os.path.join(HERE, "_ddh.so.stamp")
+# the same sources with -DDDH_CHECKED: bounded mbarrier waits + index asserts (tests/test_checked_build.py)
+OUT_CHECKED = os.path.join(HERE, "_ddh_checked.so")
 SOURCES = ["ddh_api.cu", "kernels_simt.cu", "kernels_tc.cu", "kernels_chain.cu", "kernels_producer.cu", "kernels_res2.cu"]
 HEADERS = ["common.cuh", "kernels.h", "kernels_chain.h", "kernels_res2.h", "tc_ptx.cuh", "geom.cuh", os.path.join("..", "..", "include", "ddh.h")]
 NVCC_FLAGS = [
@@ -32,27 +34,31 @@ def _digest() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    dig = _digest()
-    if not force and os.path.exists(OUT) and os.path.exists(STAMP):
-        with open(STAMP) as fh:
+def build(force: bool = False, verbose: bool = False, checked: bool = False) -> str:
+    out = OUT_CHECKED if checked else OUT
+    stamp = out + ".stamp"
+    dig = _digest() + ("-checked" if checked else "")
+    if not force and os.path.exists(out) and os.path.exists(stamp):
+        with open(stamp) as fh:
             if fh.read().strip() == dig:
-                return OUT
+                return out
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+    flags = NVCC_FLAGS + (["-DDDH_CHECKED"] if checked else [])
+    cmd = [nvcc] + flags + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr
-    with open(os.path.join(HERE, "_ddh.build.log"), "w") as fh:
+    with open(os.path.join(HERE, "_ddh_checked.build.log" if checked else "_ddh.build.log"), "w") as fh:
         fh.write(" ".join(cmd) + "\n" + log)
     if res.returncode != 0:
         sys.stderr.write(log)
         raise RuntimeError("nvcc failed building the ddh extension")
     if verbose:
         print(log)
-    with open(STAMP, "w") as fh:
+    with open(stamp, "w") as fh:
         fh.write(dig)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build(force="--force" in sys.argv, checked=True))

@@ -578,11 +578,11 @@ extern "C" {
 int ddh_abi_version(void) { return DDH_ABI_VERSION; }
 
 const char* ddh_build_info(void) {
-  return "ddh sm_100a: engines=simt_f32,tcgen05_bf16; tma=weights; cuda "
-#ifdef __CUDACC_VER_MAJOR__
-         "nvcc"
+  return "ddh sm_100a: engines=simt_f32,tcgen05_bf16(chain,conv3,resident); tma=weights,features; "
+#ifdef DDH_CHECKED
+         "checked build (bounded mbarrier waits, index asserts); "
 #endif
-         ;
+         "cuda nvcc";
 }
 
 const char* ddh_last_error(const ddh_handle* h) {

@@ -124,6 +124,7 @@ __device__ __forceinline__ void add_par(const float* p, float (&v)[32]) {
 // 32 columns of row r -> bf16 A operand (128-byte swizzle, K-major: chunk c0/64, row r at r*128,
 // 16-byte unit u at (u ^ (r & 7)) * 16)
 __device__ __forceinline__ void st_operand(uint8_t* region, int r, int c0, const float (&v)[32]) {
+  DDH_ASSERT(r >= 0 && r < 128 && c0 >= 0 && c0 + 32 <= 256);
   uint8_t* base = region + (c0 >> 6) * CH_CHUNK + r * 128;
   const int u0 = (c0 & 63) >> 3;
 #pragma unroll
@@ -235,7 +236,9 @@ __global__ void __launch_bounds__(CH_NT, 1) chain_kernel(const __grid_constant__
             tc_fence_after();
             CH_STAMP(it == 1, 128 + 2 * j);
             for (int o = 0; o < st.nops; ++o) {
+              DDH_ASSERT(st.op0 + o < CH_MAX_OPS);
               const ChainOp op = args.ops[st.op0 + o];
+              DDH_ASSERT(op.map < CH_MAX_MAPS && op.a_chunk + op.nk <= 8 && op.acc_col + ((op.flags & CO_N64) ? 64 : 256) <= 512);
               const uint32_t idesc = (op.flags & CO_N64) ? idesc64 : idesc256;
               for (int kc = 0; kc < op.nk; ++kc, ++g) {
                 const uint32_t s = g % CH_NS;
@@ -281,6 +284,8 @@ __global__ void __launch_bounds__(CH_NT, 1) chain_kernel(const __grid_constant__
           const int nsc = min(spt, B - tile * spt);
           for (int sl = 0; sl < nsc; ++sl, ++n) {
             const uint32_t slot = n % kv_nslot, use = n / kv_nslot;
+            DDH_ASSERT((slot + 1) * (uint32_t)kv_bytes <= 4u * CH_CHUNK || kv_nslot == 1);
+            DDH_ASSERT(tile * spt + sl < B);
             mbar_wait(BAR(B_KVEMPTY + slot), (use & 1u) ^ 1u);
             mbar_arrive_expect_tx(BAR(B_KVFULL + slot), kv_bytes);
             bulk_load(sm_addr + slot * (2 * CH_CHUNK),
@@ -384,6 +389,8 @@ __global__ void __launch_bounds__(CH_NT, 1) chain_kernel(const __grid_constant__
 
       for (int j = 0; j < n_steps; ++j) {
         const ChainStep st = args.steps[j];
+        DDH_ASSERT(st.dst_chunk <= 4 && st.acc_col <= 256 && st.epi <= CE_Q0);
+        DDH_ASSERT(st.par[0] + 256 <= CH_PAR_FLOATS + 1024);
         CH_STAMP(it == 1 && threadIdx.x == 0, 1 + 4 * j);
         mbar_wait(BAR(B_ACC), acc_par);
         acc_par ^= 1u;
@@ -526,6 +533,7 @@ __global__ void __launch_bounds__(CH_NT, 1) chain_kernel(const __grid_constant__
                   const int col = hcol + 8 * jd + 2 * t;
                   if (ra < A) {
                     const int rr = sl * A + ra;
+                    DDH_ASSERT(rr < 128 && col + 1 < 64);
                     *reinterpret_cast<uint32_t*>(oreg + rr * 128 + (((col >> 3) ^ (rr & 7)) << 4) + (col & 7) * 2) =
                         pack_bf16(oacc[0] * inv0, oacc[1] * inv0);
                   }
@@ -696,6 +704,7 @@ __global__ void __launch_bounds__(CH_NT, 1) chain_kernel(const __grid_constant__
             ld_blk(c.trow + st.acc_col, hi);
             ld_blk(c.trow + st.acc_col + 32, lo);
             if (valid) {
+              DDH_ASSERT(m >= 0 && m < M);
               const float* b4 = par + st.par[0] + 12 * hf;
               float raw[12];
 #pragma unroll

@@ -8,6 +8,7 @@
 
 #include "kernels.h"
 #include "geom.cuh"
+#include "tc_ptx.cuh"
 
 namespace ddh {
 
@@ -649,6 +650,7 @@ __global__ void __launch_bounds__(256) plan_kernel(const float* __restrict__ q0,
   for (int i = beg; i < end; ++i) {
     if (table[i]) {
       const int yy = i / W, xx = i - yy * W;
+      DDH_ASSERT(base < rcap);
       upix[(size_t)scene * rcap + base] = (yy << 16) | xx;   // packed (y, x)
       table[i] = (unsigned short)(base + 1);
       ++base;

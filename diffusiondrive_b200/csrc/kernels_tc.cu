@@ -1178,6 +1178,7 @@ tc_conv3_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap, in
           if (r < rows_valid) {
             const int yx = yx0[i];
             const int y = yx >> 16, x = yx & 0xffff;
+            DDH_ASSERT(y >= 0 && y < p.H && x >= 0 && x < p.W_);
             rowoff[i] = (y * p.W_ + x) * D + j * 8;
             const uint32_t xm = (x > 0 ? 1u : 0u) | 2u | (x + 1 < p.W_ ? 4u : 0u);
             vmask[i] = (y > 0 ? xm : 0u) | (xm << 3) | (y + 1 < p.H ? (xm << 6) : 0u);
@@ -1344,6 +1345,7 @@ tc_conv3_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap, in
         for (int i = 0; i < 8; ++i) {
           const int a = ew + 8 * i;
           const int rr = mslot[i] - row_base;
+          DDH_ASSERT(mslot[i] < nu);
           if (mslot[i] >= 0 && rr >= 0 && rr < nt_active * TC_BM)
             *reinterpret_cast<__nv_bfloat16*>(sm + C3_WC_OFF + (rr >> 6) * TC_A_TILE + a * 128 +
                                               ((((rr & 63) >> 3) ^ (a & 7)) << 4) + (rr & 7) * 2) = __float2bfloat16_rn(msum[i]);
@@ -1387,6 +1389,7 @@ tc_conv3_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap, in
             tmem_ld_wait();
             if (a < A) {
               const size_t o = ((size_t)scene * A + a) * D + mt * 128 + b * 32;
+              DDH_ASSERT(scene < B && o + 32 <= (size_t)B * A * D);
               float v[32];
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(u32[i]);

@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace ddh {
 
@@ -22,8 +23,28 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                : "memory");
 }
+// -DDDH_CHECKED builds (diffusiondrive_b200/_ddh_checked.so, exercised by tests/test_checked_build.py):
+// every mbarrier wait is bounded, so a protocol error traps with a message instead of hanging the GPU, and
+// DDH_ASSERT guards the index arithmetic of the hand-rolled pipelines.  compute-sanitizer is not
+// available on the GPU pool; this is the memory-safety / phase tooling of the repo.
+#ifdef DDH_CHECKED
+#define DDH_ASSERT(cond)                                                                          \
+  do {                                                                                            \
+    if (!(cond)) {                                                                                \
+      printf("DDH_ASSERT failed: %s  (%s:%d, block %d thread %d)\n", #cond, __FILE__, __LINE__,     \
+             (int)blockIdx.x, (int)threadIdx.x);                                                  \
+      __trap();                                                                                   \
+    }                                                                                             \
+  } while (0)
+#else
+#define DDH_ASSERT(cond) do { } while (0)
+#endif
+
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
+#ifdef DDH_CHECKED
+  unsigned long long spins = 0;
+#endif
   do {
     asm volatile(
         "{\n"
@@ -34,6 +55,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(done)
         : "r"(bar), "r"(parity)
         : "memory");
+#ifdef DDH_CHECKED
+    if (!done && ++spins > (1ull << 24)) {   // (each try_wait suspends for a while: seconds, not microseconds)
+      printf("DDH_CHECKED: mbarrier wait timed out (block %d thread %d, barrier 0x%x, parity %u)\n",
+             (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+      __trap();
+    }
+#endif
   } while (!done);
 }
 __device__ __forceinline__ void fence_barrier_init() {

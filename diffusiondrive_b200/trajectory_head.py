@@ -327,10 +327,10 @@ class TrajectoryHead(nn.Module):
         if not host_call and in_dev != dev:
             raise RuntimeError(f"inputs on {in_dev} but parameters on {dev}")
 
-        ego = ego_query.to(torch.float32).contiguous()
-        agents = agents_query.to(torch.float32).contiguous()
-        bev = bev_feature.contiguous()
-        noise = noise.to(torch.float32).contiguous()
+        def f32c(t):     # (no-op checks are cheaper than .to().contiguous() on the batch-1 latency path)
+            return t if (t.dtype is torch.float32 and t.is_contiguous()) else t.to(torch.float32).contiguous()
+        ego, agents, noise = f32c(ego_query), f32c(agents_query), f32c(noise)
+        bev = bev_feature if bev_feature.is_contiguous() else bev_feature.contiguous()
         out_dev = in_dev
         # one allocation for the three float outputs (allocator calls sit on the batch-1 latency path)
         n_t, n_m, n_s = B * P * 3, B * A * P * 3, B * A
@@ -347,7 +347,8 @@ class TrajectoryHead(nn.Module):
             self._ensure_handle(Na, Cc, H, W)
             self._ensure_packed(dev)
             lib, h = self._lib, self._handle
-            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            stream = torch._C._cuda_getCurrentRawStream(dev.index if dev.index is not None
+                                                        else torch.cuda.current_device())
             fn = lib.ddh_forward_host if host_call else lib.ddh_forward
             rc = fn(h, ego.data_ptr(), agents.data_ptr(), bev.data_ptr(),
                     _lib.BF16 if bev.dtype == torch.bfloat16 else _lib.F32,
