@@ -304,7 +304,7 @@ def run_ours(args):
             except Exception:
                 traffic = None
         roofline = {
-            "kernel": "tc_conv2_kernel (persistent on-demand value_proj conv + fused combine, tcgen05)",
+            "kernel": "tc_conv3_kernel (persistent on-demand value_proj conv, bilinear x attention combine as tcgen05.mma)",
             "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"],
             "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"],
             "frac_burst": achieved / peaks["bf16_tflops"], "peak_burst": peaks["bf16_tflops"],
