@@ -52,6 +52,25 @@ class WeightPtrs(C.Structure):
     _fields_ = [(n, _fp) for n in GLOBAL_FIELDS] + [("layers", C.POINTER(LayerWeights))]
 
 
+class QdecShape(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("num_queries", "num_keys", "d_model", "d_ffn", "num_heads",
+                                         "num_layers")]
+
+
+QDEC_LAYER_FIELDS = ("self_in_w", "self_in_b", "self_out_w", "self_out_b", "cross_in_w", "cross_in_b",
+                     "cross_out_w", "cross_out_b", "lin1_w", "lin1_b", "lin2_w", "lin2_b",
+                     "norm1_w", "norm1_b", "norm2_w", "norm2_b", "norm3_w", "norm3_b")
+
+
+class QdecLayerWeights(C.Structure):
+    _fields_ = [(n, _fp) for n in QDEC_LAYER_FIELDS]
+
+
+class QdecWeightPtrs(C.Structure):
+    _fields_ = [("query_embedding", _fp), ("layers", C.POINTER(QdecLayerWeights))] + [
+        (n, _fp) for n in ("states0_w", "states0_b", "states2_w", "states2_b", "label_w", "label_b")]
+
+
 # name -> (restype, argtypes); every symbol declared in include/ddh.h
 SIGNATURES = {
     "ddh_abi_version": (C.c_int, []),
@@ -71,6 +90,11 @@ SIGNATURES = {
     "ddh_bev_producer_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "ddh_bev_producer": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_int, _fp, C.c_void_p]),
+    "ddh_qdec_create": (C.c_int, [C.POINTER(QdecShape), C.POINTER(C.c_void_p)]),
+    "ddh_qdec_destroy": (None, [C.c_void_p]),
+    "ddh_qdec_last_error": (C.c_char_p, [C.c_void_p]),
+    "ddh_qdec_pack_weights": (C.c_int, [C.c_void_p, C.POINTER(QdecWeightPtrs), C.c_int, C.c_void_p]),
+    "ddh_qdec_forward": (C.c_int, [C.c_void_p, _fp, _fp, _fp, _fp, C.c_int, C.c_void_p]),
     "ddh_last_launch_count": (C.c_int, [C.c_void_p]),
     "ddh_set_concurrency": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "ddh_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),

@@ -210,6 +210,95 @@ def bev_producer_cuda(keyval_tokens, bev_map, weight, bias, ln_w, ln_b, out_dtyp
     return out
 
 
+# ------------------------------------------------------------------ query decoder (row N3)
+class QueryDecoderNative:
+    """``_tf_decoder`` (3 x nn.TransformerDecoderLayer, transfuser_model_v2.py:73-80,141-146) and
+    ``_agent_head`` (:165-205) behind the C ABI (``ddh_qdec_*``): the head's GEMM engines plus a small
+    attention kernel.  Holds no parameters of its own: it packs the agent's modules."""
+
+    def __init__(self, agent: "DiffusionDriveAgent", precision: str):
+        self.agent, self.precision = agent, precision
+        self._lib = _lib.load()
+        self._h = None
+        self._sig = None
+        self.last_launches = 0
+
+    def __del__(self):
+        try:
+            if self._h is not None:
+                self._lib.ddh_qdec_destroy(self._h)
+        except Exception:
+            pass
+
+    def _params(self):
+        a = self.agent
+        return list(a._tf_decoder.parameters()) + list(a._agent_head.parameters()) + [a._query_embedding.weight]
+
+    def _ensure(self, n_keys: int, dev):
+        a, lib = self.agent, self._lib
+        sig = (self.precision, n_keys) + tuple((p.data_ptr(), p._version) for p in self._params())
+        if sig == self._sig:
+            return
+        layers = list(a._tf_decoder.layers)
+        if self._h is None:
+            l0 = layers[0]
+            shp = _lib.QdecShape(a._query_embedding.weight.shape[0], n_keys, l0.linear1.in_features,
+                                 l0.linear1.out_features, l0.self_attn.num_heads, len(layers))
+            hp = C.c_void_p()
+            rc = lib.ddh_qdec_create(C.byref(shp), C.byref(hp))
+            if rc:
+                raise RuntimeError(f"ddh_qdec_create failed ({rc}): {lib.ddh_qdec_last_error(None).decode()}")
+            self._h = hp
+        keep = []
+
+        def ptr(t):
+            t = t.detach().to(device=dev, dtype=torch.float32).contiguous()
+            keep.append(t)
+            return t.data_ptr()
+        lw = (_lib.QdecLayerWeights * len(layers))()
+        for i, l in enumerate(layers):
+            for name, t in (("self_in_w", l.self_attn.in_proj_weight), ("self_in_b", l.self_attn.in_proj_bias),
+                            ("self_out_w", l.self_attn.out_proj.weight), ("self_out_b", l.self_attn.out_proj.bias),
+                            ("cross_in_w", l.multihead_attn.in_proj_weight), ("cross_in_b", l.multihead_attn.in_proj_bias),
+                            ("cross_out_w", l.multihead_attn.out_proj.weight), ("cross_out_b", l.multihead_attn.out_proj.bias),
+                            ("lin1_w", l.linear1.weight), ("lin1_b", l.linear1.bias), ("lin2_w", l.linear2.weight),
+                            ("lin2_b", l.linear2.bias), ("norm1_w", l.norm1.weight), ("norm1_b", l.norm1.bias),
+                            ("norm2_w", l.norm2.weight), ("norm2_b", l.norm2.bias), ("norm3_w", l.norm3.weight),
+                            ("norm3_b", l.norm3.bias)):
+                setattr(lw[i], name, ptr(t))
+        wp = _lib.QdecWeightPtrs()
+        wp.query_embedding = ptr(a._query_embedding.weight)
+        wp.layers = C.cast(lw, C.POINTER(_lib.QdecLayerWeights))
+        ah = a._agent_head
+        wp.states0_w, wp.states0_b = ptr(ah._mlp_states[0].weight), ptr(ah._mlp_states[0].bias)
+        wp.states2_w, wp.states2_b = ptr(ah._mlp_states[2].weight), ptr(ah._mlp_states[2].bias)
+        wp.label_w, wp.label_b = ptr(ah._mlp_label[0].weight), ptr(ah._mlp_label[0].bias)
+        stream = torch.cuda.current_stream(dev)
+        rc = lib.ddh_qdec_pack_weights(self._h, C.byref(wp), _lib.PREC_BF16 if self.precision == "bf16" else _lib.PREC_FP32,
+                                       C.c_void_p(stream.cuda_stream))
+        if rc:
+            raise RuntimeError(f"ddh_qdec_pack_weights failed ({rc}): {lib.ddh_qdec_last_error(self._h).decode()}")
+        stream.synchronize()
+        self._sig = sig
+
+    def __call__(self, keyval: torch.Tensor):
+        """keyval (B,Nk,256) f32 CUDA -> (query_out (B,Q,256), agent_states (B,Q-1,5), agent_labels (B,Q-1))."""
+        if keyval.device.type != "cuda":
+            raise RuntimeError("QueryDecoderNative: CUDA tensors expected (there is no CPU fallback)")
+        kv = keyval.to(torch.float32).contiguous()
+        b, nk, d = kv.shape
+        self._ensure(nk, kv.device)
+        nq = self.agent._query_embedding.weight.shape[0]
+        qo = torch.empty((b, nq, d), dtype=torch.float32, device=kv.device)
+        st = torch.empty((b, nq - 1, 5), dtype=torch.float32, device=kv.device)
+        lb = torch.empty((b, nq - 1), dtype=torch.float32, device=kv.device)
+        rc = self._lib.ddh_qdec_forward(self._h, kv.data_ptr(), qo.data_ptr(), st.data_ptr(), lb.data_ptr(), b,
+                                        C.c_void_p(torch.cuda.current_stream(kv.device).cuda_stream))
+        if rc:
+            raise RuntimeError(f"ddh_qdec_forward failed ({rc}): {self._lib.ddh_qdec_last_error(self._h).decode()}")
+        return qo, st, lb
+
+
 # ------------------------------------------------------------------ the agent
 class DiffusionDriveAgent(nn.Module):
     """``V2TransfuserModel`` with the B200-native planning head and BEV producer."""
@@ -238,27 +327,46 @@ class DiffusionDriveAgent(nn.Module):
         self.bev_proj = nn.Sequential(nn.Linear(d_model + bev_channels, d_model), nn.ReLU(inplace=True),
                                       nn.LayerNorm(d_model))
         self.semantic_map = True          # the reference always computes it (aux output)
+        self.native_query_decoder = False  # True: _tf_decoder + _agent_head through ddh_qdec_* (row N3)
+        self._qdec = []                    # [QueryDecoderNative] (a list keeps it out of the module tree)
         self.backbone_autocast = None     # e.g. torch.bfloat16: run backbone / query decoder under autocast
 
-    def pre_head(self, features: Dict[str, torch.Tensor]):
-        """Everything in front of the planning head, up to (but not including) bev_proj."""
+    def tokens(self, features: Dict[str, torch.Tensor]):
+        """Backbone, 8x8 BEV tokens + status token with the key/value embedding (:110-119)."""
         cam, lidar, status = features["camera_feature"], features["lidar_feature"], features["status_feature"]
         bev_up, x4 = self._backbone(cam, lidar)
         tokens = self._bev_downscale(x4).flatten(-2, -1).permute(0, 2, 1)
         status_enc = self._status_encoding(status)
         keyval = torch.cat((tokens, status_enc[:, None]), 1) + self._keyval_embedding.weight[None]
-        query = self._query_embedding.weight[None].expand(cam.shape[0], -1, -1)
+        return bev_up, keyval, status_enc
+
+    def pre_head(self, features: Dict[str, torch.Tensor]):
+        """Everything in front of the planning head, up to (but not including) bev_proj."""
+        bev_up, keyval, status_enc = self.tokens(features)
+        query = self._query_embedding.weight[None].expand(keyval.shape[0], -1, -1)
         ego_q, agents_q = self._tf_decoder(query, keyval).split(self._query_splits, 1)
         return bev_up, keyval, status_enc, ego_q, agents_q
 
     def forward(self, features: Dict[str, torch.Tensor], targets=None, *,
                 noise: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         cast = self.backbone_autocast
+        native = self.native_query_decoder
         with torch.autocast("cuda", dtype=cast if cast is not None else torch.bfloat16, enabled=cast is not None):
-            bev_up, keyval, status_enc, ego_q, agents_q = self.pre_head(features)
+            if native:
+                bev_up, keyval, status_enc = self.tokens(features)
+            else:
+                bev_up, keyval, status_enc, ego_q, agents_q = self.pre_head(features)
             out = {}
             if self.semantic_map:
                 out["bev_semantic_map"] = self._bev_semantic_head(bev_up)
+        agent_out = None
+        if native:
+            prec = self._trajectory_head.precision
+            if not self._qdec or self._qdec[0].precision != prec:
+                self._qdec[:] = [QueryDecoderNative(self, prec)]
+            q_out, states, labels = self._qdec[0](keyval.float())
+            ego_q, agents_q = q_out.split(self._query_splits, 1)
+            agent_out = {"agent_states": states, "agent_labels": labels}
         fp32 = self._trajectory_head.precision == "fp32"
         cross = bev_producer_cuda(keyval[:, :-1].float(), bev_up.float(), self.bev_proj[0].weight,
                                   self.bev_proj[0].bias, self.bev_proj[2].weight, self.bev_proj[2].bias,
@@ -266,5 +374,5 @@ class DiffusionDriveAgent(nn.Module):
         out.update(self._trajectory_head(ego_q.float().contiguous(), agents_q.float().contiguous(), cross,
                                          tuple(bev_up.shape[2:]), status_enc[:, None], noise=noise,
                                          bev_layout="NHWC"))
-        out.update(self._agent_head(agents_q.float()))
+        out.update(agent_out if agent_out is not None else self._agent_head(agents_q.float()))
         return out

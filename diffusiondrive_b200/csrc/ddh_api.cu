@@ -1508,6 +1508,178 @@ int ddh_bev_producer(const float* keyval_tokens, const float* bev_map, const flo
   return DDH_OK;
 }
 
+// ---- query decoder + AgentHead (row N3): the head's GEMM engines + a small attention kernel ----
+struct QdecLayer {
+  PackedLinear self_in, self_out, cross_q, cross_kv, cross_out, lin1, lin2;
+  float *n1g = nullptr, *n1b = nullptr, *n2g = nullptr, *n2b = nullptr, *n3g = nullptr, *n3b = nullptr;
+};
+struct ddh_qdec {
+  ddh_handle ctx;            // precision, packed-weight ownership, TMA encoder, error text
+  ddh_qdec_shape shp;
+  std::vector<QdecLayer> layers;
+  PackedLinear states0;
+  float *qemb = nullptr, *states2_w = nullptr, *states2_b = nullptr, *label_w = nullptr, *label_b = nullptr;
+  int cap_B = 0;
+  std::vector<void*> ws;
+  float *x32 = nullptr, *y32 = nullptr, *qkv32 = nullptr, *o32 = nullptr, *qc32 = nullptr, *kvc32 = nullptr, *h32 = nullptr;
+  __nv_bfloat16 *x16 = nullptr, *y16 = nullptr, *o16 = nullptr, *mem16 = nullptr, *h16 = nullptr;
+};
+
+int ddh_qdec_create(const ddh_qdec_shape* s, ddh_qdec** out) {
+  if (!s || !out) return fail(nullptr, DDH_ERR_BAD_ARG, "ddh_qdec_create: null argument");
+  *out = nullptr;
+  if (s->d_model != 256 || s->num_heads != 8 || s->num_queries < 1 || s->num_queries > 32 ||
+      s->num_keys < 1 || s->num_keys > 96 || s->d_ffn <= 0 || s->d_ffn % 256 || s->num_layers < 1 ||
+      s->num_layers > 16)
+    return fail(nullptr, DDH_ERR_UNSUPPORTED,
+                "ddh_qdec_create: need d_model 256, 8 heads, <= 32 queries, <= 96 keys, d_ffn % 256 == 0");
+  ddh_qdec* q = new ddh_qdec();
+  q->shp = *s;
+  memset(&q->ctx.shp, 0, sizeof q->ctx.shp);
+  *out = q;
+  return DDH_OK;
+}
+
+void ddh_qdec_destroy(ddh_qdec* q) {
+  if (!q) return;
+  free_all(q->ctx.owned_w);
+  free_all(q->ws);
+  delete q;
+}
+
+const char* ddh_qdec_last_error(const ddh_qdec* q) { return q ? q->ctx.err.c_str() : g_create_error.c_str(); }
+
+int ddh_qdec_pack_weights(ddh_qdec* q, const ddh_qdec_weight_ptrs* w, int precision, void* stream) {
+  if (!q || !w || !w->layers) return fail(q ? &q->ctx : nullptr, DDH_ERR_BAD_ARG, "ddh_qdec_pack_weights: null argument");
+  ddh_handle* h = &q->ctx;
+  if (precision != DDH_PREC_FP32 && precision != DDH_PREC_BF16)
+    return fail(h, DDH_ERR_BAD_ARG, "ddh_qdec_pack_weights: unknown precision");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(h, DDH_ERR_CUDA, "ddh_qdec_pack_weights: no CUDA device (there is no CPU fallback)");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaDeviceSynchronize();
+  free_all(h->owned_w);
+  free_all(q->ws);
+  q->cap_B = 0;
+  h->packed = false;
+  h->precision = precision;
+  if (precision == DDH_PREC_BF16 && !h->tc_ready) {
+    int e = tc_engine_init();
+    if (e) return fail(h, DDH_ERR_CUDA, std::string("tc_engine_init: ") + cudaGetErrorString((cudaError_t)e));
+    h->tc_ready = true;
+  }
+  const ddh_qdec_shape& s = q->shp;
+  const int F = s.d_ffn, Q = s.num_queries;
+  int rc;
+#define TRY(x) do { rc = (x); if (rc) return rc; } while (0)
+  TRY(copy_vec(h, &q->qemb, w->query_embedding, (size_t)Q * D, st));
+  q->layers.assign(s.num_layers, QdecLayer());
+  for (int l = 0; l < s.num_layers; ++l) {
+    const ddh_qdec_layer_weights& lw = w->layers[l];
+    QdecLayer& pl = q->layers[l];
+    TRY(pack_linear(h, pl.self_in, lw.self_in_w, lw.self_in_b, 3 * D, D, st));
+    TRY(pack_linear(h, pl.self_out, lw.self_out_w, lw.self_out_b, D, D, st));
+    TRY(pack_linear(h, pl.cross_q, lw.cross_in_w, lw.cross_in_b, D, D, st));
+    TRY(pack_linear(h, pl.cross_kv, lw.cross_in_w + (size_t)D * D, lw.cross_in_b + D, 2 * D, D, st));
+    TRY(pack_linear(h, pl.cross_out, lw.cross_out_w, lw.cross_out_b, D, D, st));
+    TRY(pack_linear(h, pl.lin1, lw.lin1_w, lw.lin1_b, F, D, st));
+    TRY(pack_linear(h, pl.lin2, lw.lin2_w, lw.lin2_b, D, F, st));
+    TRY(copy_vec(h, &pl.n1g, lw.norm1_w, D, st)); TRY(copy_vec(h, &pl.n1b, lw.norm1_b, D, st));
+    TRY(copy_vec(h, &pl.n2g, lw.norm2_w, D, st)); TRY(copy_vec(h, &pl.n2b, lw.norm2_b, D, st));
+    TRY(copy_vec(h, &pl.n3g, lw.norm3_w, D, st)); TRY(copy_vec(h, &pl.n3b, lw.norm3_b, D, st));
+  }
+  TRY(pack_linear(h, q->states0, w->states0_w, w->states0_b, F, D, st));
+  TRY(copy_vec(h, &q->states2_w, w->states2_w, (size_t)5 * F, st));
+  TRY(copy_vec(h, &q->states2_b, w->states2_b, 5, st));
+  TRY(copy_vec(h, &q->label_w, w->label_w, D, st));
+  TRY(copy_vec(h, &q->label_b, w->label_b, 1, st));
+#undef TRY
+  CU_TRY(h, cudaGetLastError());
+  h->packed = true;
+  return DDH_OK;
+}
+
+int ddh_qdec_forward(ddh_qdec* q, const float* keyval, float* query_out, float* agent_states,
+                     float* agent_labels, int B, void* stream) {
+  if (!q) return DDH_ERR_BAD_ARG;
+  ddh_handle* h = &q->ctx;
+  if (!h->packed) return fail(h, DDH_ERR_NOT_PACKED, "ddh_qdec_forward: weights not packed");
+  if (!keyval || B <= 0) return fail(h, DDH_ERR_BAD_ARG, "ddh_qdec_forward: null input or B <= 0");
+  if (reinterpret_cast<uintptr_t>(keyval) & 15) return fail(h, DDH_ERR_ALIGNMENT, "ddh_qdec_forward: keyval must be 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const ddh_qdec_shape& s = q->shp;
+  const int Q = s.num_queries, Nk = s.num_keys, F = s.d_ffn, M = B * Q, MK = B * Nk;
+  const bool bf = h->precision == DDH_PREC_BF16;
+  int rc;
+  if (B > q->cap_B) {
+    cudaDeviceSynchronize();
+    free_all(q->ws);
+    q->cap_B = 0;
+#define WS(ptr, count) do { rc = dev_alloc(h, q->ws, &(ptr), (size_t)(count)); if (rc) return rc; } while (0)
+    WS(q->x32, (size_t)M * D); WS(q->y32, (size_t)M * D); WS(q->qkv32, (size_t)M * 3 * D); WS(q->o32, (size_t)M * D);
+    WS(q->qc32, (size_t)M * D); WS(q->kvc32, (size_t)MK * 2 * D); WS(q->h32, (size_t)M * F);
+    if (bf) {
+      WS(q->x16, (size_t)M * D); WS(q->y16, (size_t)M * D); WS(q->o16, (size_t)M * D);
+      WS(q->mem16, (size_t)MK * D); WS(q->h16, (size_t)M * F);
+    } else {
+      q->x16 = q->y16 = q->o16 = q->mem16 = q->h16 = nullptr;
+    }
+#undef WS
+    q->cap_B = B;
+  }
+  h->launches = 0;
+  launch_broadcast_rows(q->qemb, q->x32, q->x16, Q, (size_t)M * D, st);
+  h->launches++;
+  if (bf) { launch_cast_f32_bf16(keyval, q->mem16, (size_t)MK * D, st); h->launches++; }
+  float *x32 = q->x32, *y32 = q->y32;
+  __nv_bfloat16 *x16 = q->x16, *y16 = q->y16;
+  for (int l = 0; l < s.num_layers; ++l) {
+    const QdecLayer& pl = q->layers[l];
+    // x = norm1(x + self_attn(x, x, x))
+    { RowEpi e; e.out_f32 = q->qkv32; e.ldo32 = 3 * D;
+      run_gemm(h, pl.self_in, x32, x16, D, M, e, st); }
+    rc = launch_mha_small(q->qkv32, 3 * D, q->qkv32 + D, 3 * D, q->o32, q->o16, B, Q, Q, st);
+    if (rc) return fail(h, DDH_ERR_CUDA, "ddh_qdec_forward: attention launch failed");
+    h->launches++;
+    { RowEpi e; e.res = x32; e.ldres = D; e.ln1_g = pl.n1g; e.ln1_b = pl.n1b;
+      e.out_f32 = y32; e.ldo32 = D; e.out_bf16 = y16; e.ldo16 = D;
+      run_gemm(h, pl.self_out, q->o32, q->o16, D, M, e, st); }
+    // y = norm2(y + multihead_attn(y, memory, memory))
+    { RowEpi e; e.out_f32 = q->qc32; e.ldo32 = D;
+      run_gemm(h, pl.cross_q, y32, y16, D, M, e, st); }
+    { RowEpi e; e.out_f32 = q->kvc32; e.ldo32 = 2 * D;
+      run_gemm(h, pl.cross_kv, keyval, q->mem16, D, MK, e, st); }
+    rc = launch_mha_small(q->qc32, D, q->kvc32, 2 * D, q->o32, q->o16, B, Q, Nk, st);
+    if (rc) return fail(h, DDH_ERR_CUDA, "ddh_qdec_forward: attention launch failed");
+    h->launches++;
+    { RowEpi e; e.res = y32; e.ldres = D; e.ln1_g = pl.n2g; e.ln1_b = pl.n2b;
+      e.out_f32 = x32; e.ldo32 = D; e.out_bf16 = x16; e.ldo16 = D;
+      run_gemm(h, pl.cross_out, q->o32, q->o16, D, M, e, st); }
+    // x = norm3(x + linear2(relu(linear1(x))))
+    { RowEpi e; e.relu = 1; e.out_f32 = bf ? nullptr : q->h32; e.ldo32 = F; e.out_bf16 = q->h16; e.ldo16 = F;
+      run_gemm(h, pl.lin1, x32, x16, D, M, e, st); }
+    { RowEpi e; e.res = x32; e.ldres = D; e.ln1_g = pl.n3g; e.ln1_b = pl.n3b;
+      e.out_f32 = y32; e.ldo32 = D; e.out_bf16 = y16; e.ldo16 = D;
+      run_gemm(h, pl.lin2, q->h32, q->h16, F, M, e, st); }
+    std::swap(x32, y32);
+    std::swap(x16, y16);
+  }
+  if (query_out) CU_TRY(h, cudaMemcpyAsync(query_out, x32, (size_t)M * D * 4, cudaMemcpyDeviceToDevice, st));
+  if (agent_states) {
+    RowEpi e; e.relu = 1; e.out_f32 = q->h32; e.ldo32 = F;
+    run_gemm(h, q->states0, x32, x16, D, M, e, st);
+    launch_rowdot(q->h32, F, q->states2_w, q->states2_b, agent_states, M, F, 5, Q, 1, 1, st);
+    h->launches++;
+  }
+  if (agent_labels) {
+    launch_rowdot(x32, D, q->label_w, q->label_b, agent_labels, M, D, 1, Q, 1, 0, st);
+    h->launches++;
+  }
+  CU_TRY(h, cudaGetLastError());
+  return DDH_OK;
+}
+
 int ddh_last_launch_count(const ddh_handle* h) { return h ? h->launches : 0; }
 
 int ddh_set_concurrency(ddh_handle* h, int chunks, int min_chunk_scenes) {

@@ -46,6 +46,14 @@ void launch_reg_finish(const float* r2, const float* w4, const float* b4, float*
 void launch_select(const float* scores, const float* modes, float* traj, long long* mode_idx,
                    int B, int A, int P, cudaStream_t st);
 
+// query decoder pieces (kernels_simt.cu)
+int launch_mha_small(const float* q, int ldq, const float* kv, int ldkv, float* o32, __nv_bfloat16* o16,
+                     int B, int nq, int nk, cudaStream_t st);
+void launch_rowdot(const float* x, int ldx, const float* w, const float* b, float* y, int M, int K, int n_out,
+                   int rows_per_group, int skip_first, int states, cudaStream_t st);
+void launch_broadcast_rows(const float* emb, float* x32, __nv_bfloat16* x16, int rows_per_group, size_t n,
+                           cudaStream_t st);
+
 // pack-time helpers
 void launch_transpose_f32(const float* src, float* dst, int rows, int cols, cudaStream_t st);
 void launch_pack_conv_f32(const float* w, float* dst, int Cout, int Cin, cudaStream_t st);

@@ -962,6 +962,136 @@ void launch_reg_finish(const float* r2, const float* w4, const float* b4, float*
   reg_finish_kernel<<<(M + 63) / 64, 256, 0, st>>>(r2, w4, b4, pts, img, modes, M, P, do_ddim, dc);
 }
 
+// ===================================================================================
+// Generic small multi-head attention (query decoder of V2TransfuserModel, nn.TransformerDecoder
+// self- and cross-attention, transfuser_model_v2.py:73-80,141-146): per scene and head
+// softmax(q k^T / sqrt(32)) v with head_dim 32, up to 32 queries and any number of keys that fits
+// shared memory.  One CTA per scene, one warp per head, one lane per query; K|V rows are staged in
+// shared memory (fp32) and read as broadcasts; online softmax over the keys.
+//   q  [B*nq rows][ldq],   kv [B*nk rows][ldkv] with K at column 0 and V at column 256 of the row
+// ===================================================================================
+__global__ void __launch_bounds__(256) mha_small_kernel(const float* __restrict__ q, int ldq,
+                                                        const float* __restrict__ kv, int ldkv,
+                                                        float* __restrict__ o32,
+                                                        __nv_bfloat16* __restrict__ o16, int nq, int nk) {
+  extern __shared__ __align__(16) float kvs[];   // [nk][512]
+  const int scene = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < nk * 128; i += 256) {
+    const int r = i >> 7, c4 = i & 127;
+    reinterpret_cast<float4*>(kvs)[i] = __ldg(reinterpret_cast<const float4*>(kv + ((size_t)scene * nk + r) * ldkv) + c4);
+  }
+  __syncthreads();
+  const bool act = lane < nq;
+  const size_t row = (size_t)scene * nq + (act ? lane : 0);
+  const float scale = 0.17677669529663687f;   // 1 / sqrt(32)
+  float qv[32], o[32];
+#pragma unroll
+  for (int c4 = 0; c4 < 8; ++c4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(q + row * ldq + h * 32) + c4);
+    qv[4 * c4] = t.x * scale; qv[4 * c4 + 1] = t.y * scale; qv[4 * c4 + 2] = t.z * scale; qv[4 * c4 + 3] = t.w * scale;
+  }
+#pragma unroll
+  for (int c = 0; c < 32; ++c) o[c] = 0.f;
+  float mx = -INFINITY, den = 0.f;
+  for (int j = 0; j < nk; ++j) {
+    const float4* kr = reinterpret_cast<const float4*>(kvs + (size_t)j * 512 + h * 32);
+    float sc = 0.f;
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) {
+      const float4 k4 = kr[c4];
+      sc = fmaf(qv[4 * c4], k4.x, sc); sc = fmaf(qv[4 * c4 + 1], k4.y, sc);
+      sc = fmaf(qv[4 * c4 + 2], k4.z, sc); sc = fmaf(qv[4 * c4 + 3], k4.w, sc);
+    }
+    const float nm = fmaxf(mx, sc);
+    const float alpha = expf(mx - nm), pj = expf(sc - nm);
+    den = den * alpha + pj;
+    mx = nm;
+    const float4* vr = reinterpret_cast<const float4*>(kvs + (size_t)j * 512 + 256 + h * 32);
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) {
+      const float4 v4 = vr[c4];
+      o[4 * c4] = fmaf(pj, v4.x, o[4 * c4] * alpha); o[4 * c4 + 1] = fmaf(pj, v4.y, o[4 * c4 + 1] * alpha);
+      o[4 * c4 + 2] = fmaf(pj, v4.z, o[4 * c4 + 2] * alpha); o[4 * c4 + 3] = fmaf(pj, v4.w, o[4 * c4 + 3] * alpha);
+    }
+  }
+  if (!act) return;
+  const float inv = 1.0f / den;
+  if (o32) {
+    float4* d = reinterpret_cast<float4*>(o32 + row * D + h * 32);
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4)
+      d[c4] = make_float4(o[4 * c4] * inv, o[4 * c4 + 1] * inv, o[4 * c4 + 2] * inv, o[4 * c4 + 3] * inv);
+  }
+  if (o16) {
+    uint4* d = reinterpret_cast<uint4*>(o16 + row * D + h * 32);
+#pragma unroll
+    for (int c8 = 0; c8 < 4; ++c8) {
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(o[8 * c8] * inv, o[8 * c8 + 1] * inv);
+      __nv_bfloat162 h1 = __floats2bfloat162_rn(o[8 * c8 + 2] * inv, o[8 * c8 + 3] * inv);
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(o[8 * c8 + 4] * inv, o[8 * c8 + 5] * inv);
+      __nv_bfloat162 h3 = __floats2bfloat162_rn(o[8 * c8 + 6] * inv, o[8 * c8 + 7] * inv);
+      uint4 u;
+      u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+      u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+      d[c8] = u;
+    }
+  }
+}
+int launch_mha_small(const float* q, int ldq, const float* kv, int ldkv, float* o32, __nv_bfloat16* o16,
+                     int B, int nq, int nk, cudaStream_t st) {
+  const int smem = nk * 512 * 4;
+  static int cur = 0;
+  if (smem > cur) {
+    cudaError_t e = cudaFuncSetAttribute(mha_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    cur = smem;
+  }
+  mha_small_kernel<<<B, 256, smem, st>>>(q, ldq, kv, ldkv, o32, o16, nq, nk);
+  return 0;
+}
+
+// y[m][o] = x[m] . w[o] + b[o] for a handful of outputs per row (AgentHead's last Linears,
+// transfuser_model_v2.py:187-203), one warp per row.  agent_states: tanh * 32 on outputs 0-1,
+// tanh * pi on output 2.
+__global__ void __launch_bounds__(256) rowdot_kernel(const float* __restrict__ x, int ldx,
+                                                     const float* __restrict__ w, const float* __restrict__ b,
+                                                     float* __restrict__ y, int M, int K, int n_out,
+                                                     int rows_per_group, int skip_first, int states) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int out_rows_per_group = rows_per_group - skip_first;
+  if (r >= M) return;
+  const int g = r / rows_per_group, i = r - g * rows_per_group;
+  if (i < skip_first) return;
+  const float* xr = x + (size_t)r * ldx;
+  for (int o = 0; o < n_out; ++o) {
+    float s = 0.f;
+    for (int k = lane; k < K; k += 32) s = fmaf(xr[k], w[(size_t)o * K + k], s);
+    s = warp_sum(s) + b[o];
+    if (states) s = (o < 2) ? tanhf(s) * 32.0f : (o == 2 ? tanhf(s) * 3.14159265358979323846f : s);
+    if (lane == 0) y[((size_t)g * out_rows_per_group + (i - skip_first)) * n_out + o] = s;
+  }
+}
+void launch_rowdot(const float* x, int ldx, const float* w, const float* b, float* y, int M, int K, int n_out,
+                   int rows_per_group, int skip_first, int states, cudaStream_t st) {
+  rowdot_kernel<<<(M + 7) / 8, 256, 0, st>>>(x, ldx, w, b, y, M, K, n_out, rows_per_group, skip_first, states);
+}
+
+// x[b][q][:] = emb[q][:]  (the query embedding is the first layer's input for every scene, :141)
+__global__ void broadcast_rows_kernel(const float* __restrict__ emb, float* __restrict__ x32,
+                                      __nv_bfloat16* __restrict__ x16, int rows_per_group, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / D;
+    const float v = emb[(r % rows_per_group) * D + (i - r * D)];
+    x32[i] = v;
+    if (x16) x16[i] = __float2bfloat16_rn(v);
+  }
+}
+void launch_broadcast_rows(const float* emb, float* x32, __nv_bfloat16* x16, int rows_per_group, size_t n,
+                           cudaStream_t st) {
+  const int blocks = (int)min((size_t)148 * 8, (n + 255) / 256);
+  broadcast_rows_kernel<<<blocks, 256, 0, st>>>(emb, x32, x16, rows_per_group, n);
+}
+
 // mode = argmax(cls) (first maximum wins), trajectory = reg[b, mode]          (:637-640)
 __global__ void select_kernel(const float* __restrict__ scores, const float* __restrict__ modes,
                               float* __restrict__ traj, long long* __restrict__ mode_idx, int B,

@@ -197,6 +197,49 @@ DDH_API int ddh_bev_producer(const float *keyval_tokens, const float *bev_map, c
                      int out_dtype, int B, int H, int W, int grid, int bev_channels, void *scratch,
                      void *stream);
 
+/* ---- query decoder + AgentHead ------------------------------------
+ * V2TransfuserModel.forward :141-146,159-160: query = _query_embedding.weight repeated per scene,
+ * query_out = nn.TransformerDecoder(3 x nn.TransformerDecoderLayer(d 256, 8 heads, ffn 1024, post-norm,
+ * ReLU), norm=None)(query, keyval); agent_states / agent_labels = AgentHead(query_out[:, 1:]) (:165-205).
+ * Same engines as the head: DDH_PREC_FP32 = CUDA-core GEMMs, DDH_PREC_BF16 = tcgen05 GEMMs; the
+ * attention (<= 32 queries) and LayerNorms are fp32 in both. */
+typedef struct ddh_qdec_shape {
+  int32_t num_queries;   /* [31] 1 ego + num_bounding_boxes, <= 32                    */
+  int32_t num_keys;      /* [65] 8x8 BEV tokens + status token, <= 96                 */
+  int32_t d_model;       /* [256] must be 256                                         */
+  int32_t d_ffn;         /* [1024] multiple of 256                                    */
+  int32_t num_heads;     /* [8] head_dim must be 32                                   */
+  int32_t num_layers;    /* [3] tf_num_layers                                         */
+} ddh_qdec_shape;
+
+typedef struct ddh_qdec_layer_weights {   /* nn.TransformerDecoderLayer, torch layouts, device f32 */
+  const float *self_in_w, *self_in_b;     /* self_attn.in_proj       [3D,D], [3D]      */
+  const float *self_out_w, *self_out_b;   /* self_attn.out_proj      [D,D], [D]        */
+  const float *cross_in_w, *cross_in_b;   /* multihead_attn.in_proj  [3D,D], [3D]      */
+  const float *cross_out_w, *cross_out_b; /* multihead_attn.out_proj [D,D], [D]        */
+  const float *lin1_w, *lin1_b;           /* linear1 [F,D], [F]                        */
+  const float *lin2_w, *lin2_b;           /* linear2 [D,F], [D]                        */
+  const float *norm1_w, *norm1_b, *norm2_w, *norm2_b, *norm3_w, *norm3_b;
+} ddh_qdec_layer_weights;
+
+typedef struct ddh_qdec_weight_ptrs {
+  const float *query_embedding;           /* _query_embedding.weight [Q,D]             */
+  const ddh_qdec_layer_weights *layers;   /* HOST array of num_layers entries          */
+  const float *states0_w, *states0_b;     /* _agent_head._mlp_states.0 [F,D], [F]      */
+  const float *states2_w, *states2_b;     /* _agent_head._mlp_states.2 [5,F], [5]      */
+  const float *label_w, *label_b;         /* _agent_head._mlp_label.0  [1,D], [1]      */
+} ddh_qdec_weight_ptrs;
+
+typedef struct ddh_qdec ddh_qdec;
+DDH_API int ddh_qdec_create(const ddh_qdec_shape *shape, ddh_qdec **out);
+DDH_API void ddh_qdec_destroy(ddh_qdec *q);
+DDH_API const char *ddh_qdec_last_error(const ddh_qdec *q);
+DDH_API int ddh_qdec_pack_weights(ddh_qdec *q, const ddh_qdec_weight_ptrs *w, int precision, void *stream);
+/* keyval [B,Nk,D] f32 (device) -> query_out [B,Q,D], agent_states [B,Q-1,5], agent_labels [B,Q-1]
+ * (any output may be NULL); asynchronous on `stream` (workspace growth on a larger B synchronises). */
+DDH_API int ddh_qdec_forward(ddh_qdec *q, const float *keyval, float *query_out, float *agent_states,
+                     float *agent_labels, int B, void *stream);
+
 /* Number of kernel launches issued by the last ddh_forward on this handle. */
 DDH_API int ddh_last_launch_count(const ddh_handle *h);
 
