@@ -561,8 +561,10 @@ def run_ours(args):
             nz1 = synth.make_noise(1).to(dev)
             full_agent = {"config": "BASELINE configs[3]: camera 3x256x1024 + LiDAR 1x256x256 + status, batch 1, "
                                     "60.7 M parameters, random init", "paper_fps": 45.0}
-            for tag, cast in (("backbone_fp32_tf32", None), ("backbone_bf16_autocast", torch.bfloat16)):
+            for tag, cast, native in (("backbone_fp32_tf32", None, False), ("backbone_bf16_autocast", torch.bfloat16, False),
+                                      ("backbone_bf16_autocast_native_query_decoder", torch.bfloat16, True)):
                 agent.backbone_autocast = cast
+                agent.native_query_decoder = native
                 with torch.no_grad():
                     for _ in range(5):
                         o = agent(feats, noise=nz1)
@@ -602,6 +604,7 @@ def run_ours(args):
                         rec["fps"] = 1e3 / rec["eager_p50_ms"]
                     full_agent[tag] = rec
             agent.backbone_autocast = None
+            agent.native_query_decoder = False
             head_us = (lat or {}).get("graph_p50_us") or (lat or {}).get("p50_us")
             best = min(v.get("graph_p50_ms", v["eager_p50_ms"]) for k, v in full_agent.items() if isinstance(v, dict))
             full_agent["head_share"] = (head_us * 1e-3 / best) if head_us else None
