@@ -1098,6 +1098,17 @@ constexpr int C3_VT_CHUNK = 256 * 128;     // V^T operand: 64 pixel rows (K) x 2
 constexpr int C3_WC_OFF = 2 * C_STAGE;     // Wc operand region (pipeline stage 2)
 constexpr int C3_THREADS = C2_THREADS + 32;   // + warp 14: second MMA issuer (channel tile 1)
 
+// A scene's unique pixel rows are split into ceil(nu / 256) passes of EQUAL size, rounded up to the MMA's
+// N granularity (16): 276 rows run as 2 x 144 instead of 256 + 128-padded, and a single-pass scene uses
+// N = roundup16(nu) instead of 256 -- the main loop is tensor-bound, so its time is proportional to N.
+struct C3Split { int passes, rpp; };
+__device__ __forceinline__ C3Split c3_split(int nu) {
+  C3Split s;
+  s.passes = (nu + 255) / 256;
+  s.rpp = s.passes ? (((nu + s.passes - 1) / s.passes + 15) & ~15) : 0;
+  return s;
+}
+
 __global__ void __launch_bounds__(C3_THREADS, 1)
 tc_conv3_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap, int B) {
   constexpr int NS = C_NS, NT = C_NT;
@@ -1158,11 +1169,11 @@ tc_conv3_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap, in
       for (int i = 0; i < RPT; ++i)
         yxn[i] = (scene_n < B && nu_n > 0) ? __ldg(p.upix + (size_t)scene_n * p.rcap + min(rb + 16 * i, nu_n - 1)) : 0;
       const __nv_bfloat16* bev = reinterpret_cast<const __nv_bfloat16*>(p.bev) + (size_t)scene * p.H * p.W_ * D;
-      const int passes = (nu + NT * TC_BM - 1) / (NT * TC_BM);
+      const C3Split sp = c3_split(nu);
+      const int passes = sp.passes, ngrp = sp.rpp >> 4;      // ngrp: 16-row groups per pass (N / 16)
       for (int pass = 0; pass < passes; ++pass, ++pi) {
-        const int row_base = pass * NT * TC_BM;
-        const int rows_valid = min(NT * TC_BM, nu - row_base);
-        const int nt_active = (rows_valid + TC_BM - 1) / TC_BM;
+        const int row_base = pass * sp.rpp;
+        const int rows_valid = min(sp.rpp, nu - row_base);
         if (pass > 0) {
 #pragma unroll
           for (int i = 0; i < RPT; ++i)
@@ -1197,7 +1208,7 @@ tc_conv3_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap, in
           const int tapoff = (dy * p.W_ + dx) * D + (kc & 3) * TC_BK;
 #pragma unroll
           for (int i = 0; i < RPT; ++i) {
-            if (i < 8 * nt_active) {
+            if (i < ngrp) {
               const bool ok = (vmask[i] >> tap) & 1u;
               const int off = ok ? rowoff[i] + tapoff : 0;
               cp_async16(a_dst + i * 2048, bev + off, ok ? 16u : 0u);
@@ -1218,7 +1229,7 @@ tc_conv3_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap, in
       int g = 0, pi = 0;
       for (int scene = blockIdx.x; scene < B; scene += gridDim.x) {
         const int nu = __ldg(p.nuniq + scene);
-        const int passes = (nu + NT * TC_BM - 1) / (NT * TC_BM);
+        const int passes = c3_split(nu).passes;
         for (int pass = 0; pass < passes; ++pass, ++pi) {
           if (pi > 0) mbar_wait(passgo, (uint32_t)(pi - 1) & 1u);
           for (int kc = 0; kc < KC; ++kc, ++g) {
@@ -1236,16 +1247,15 @@ tc_conv3_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap, in
     if (lane == 0) {
       const int mt = warp == 5 ? 0 : 1;
       const uint32_t idesc256 = umma_idesc_bf16_m128_n256();
-      const uint32_t idesc128 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
       int g = 0, sidx = 0;
       uint32_t pi = 0;
       for (int scene = blockIdx.x; scene < B; scene += gridDim.x, ++sidx) {
         const int nu = __ldg(p.nuniq + scene);
-        const int passes = (nu + NT * TC_BM - 1) / (NT * TC_BM);
+        const C3Split sp = c3_split(nu);
+        const int passes = sp.passes;
+        // D = f32, A = B = bf16, K-major, M = 128, N = rows of a pass
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)sp.rpp >> 3) << 17) | ((128u >> 4) << 24);
         for (int pass = 0; pass < passes; ++pass, ++pi) {
-          const int rows_valid = min(NT * TC_BM, nu - pass * NT * TC_BM);
-          const int nt_active = (rows_valid + TC_BM - 1) / TC_BM;
-          const uint32_t idesc = nt_active == 2 ? idesc256 : idesc128;
           for (int kc = 0; kc < KC; ++kc, ++g) {
             const int s = g % NS;
             mbar_wait(full(s), (g / NS) & 1);
@@ -1265,12 +1275,12 @@ tc_conv3_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap, in
             // ---- combine: S^(pass)[a, c] = Wc[a, r] . V^T[c, r], K = the pass's pixel rows
             mbar_wait(vt_ready, pi & 1u);
             tc_fence_after();
-            const int kch = nt_active * 2;
-            for (int kc = 0; kc < kch; ++kc)
-#pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4)
-                umma_bf16(tmem_base, umma_desc_sw128(sm_addr + C3_WC_OFF + kc * TC_A_TILE + k4 * 32),
-                          umma_desc_sw128(sm_addr + kc * C3_VT_CHUNK + k4 * 32), idesc256, (kc | k4) ? 1u : 0u);
+            const int ksteps = sp.rpp >> 4;      // K = the pass's pixel rows, 16 per instruction
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const int kc = ks >> 2, k4 = ks & 3;
+              umma_bf16(tmem_base, umma_desc_sw128(sm_addr + C3_WC_OFF + kc * TC_A_TILE + k4 * 32),
+                        umma_desc_sw128(sm_addr + kc * C3_VT_CHUNK + k4 * 32), idesc256, ks ? 1u : 0u);
+            }
             umma_commit(comb_done);
             C2_STAMP(sidx == 1 && pass == 0, 26);
           }
@@ -1324,12 +1334,11 @@ tc_conv3_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap, in
           if (slot >= 0 && (__ffs((int)grp) - 1) == lane) { mslot[i] = slot; msum[i] = sum; }
         }
       }
-      const int passes = (nu + NT * TC_BM - 1) / (NT * TC_BM);
+      const C3Split sp = c3_split(nu);
+      const int passes = sp.passes;
       for (int pass = 0; pass < passes; ++pass, ++pi) {
-        const int row_base = pass * NT * TC_BM;
-        const int rows_valid = min(NT * TC_BM, nu - row_base);
-        const int nt_active = (rows_valid + TC_BM - 1) / TC_BM;
-        const int upa = nt_active * 16;          // 16-byte units (8 pixel rows) per anchor row of Wc
+        const int row_base = pass * sp.rpp;
+        const int upa = sp.rpp >> 3;             // 16-byte units (8 pixel rows) per anchor row of Wc
         const int n_units = A * upa;
         C2_STAMP(sidx == 1 && pass == 0 && etid == 0, 32);
         mbar_wait(accum, pi & 1u);
@@ -1346,12 +1355,12 @@ tc_conv3_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap, in
           const int a = ew + 8 * i;
           const int rr = mslot[i] - row_base;
           DDH_ASSERT(mslot[i] < nu);
-          if (mslot[i] >= 0 && rr >= 0 && rr < nt_active * TC_BM)
+          if (mslot[i] >= 0 && rr >= 0 && rr < sp.rpp)
             *reinterpret_cast<__nv_bfloat16*>(sm + C3_WC_OFF + (rr >> 6) * TC_A_TILE + a * 128 +
                                               ((((rr & 63) >> 3) ^ (a & 7)) << 4) + (rr & 7) * 2) = __float2bfloat16_rn(msum[i]);
         }
         // ---- drain: this thread's channel row of V^T, 32 pixel rows at a time
-        const int nblk = nt_active * 4;
+        const int nblk = (sp.rpp + 31) >> 5;     // (a last half block reads 16 stale columns: never used as K)
 #pragma unroll 1
         for (int b = 0; b < nblk; ++b) {
           uint32_t u32[32];
