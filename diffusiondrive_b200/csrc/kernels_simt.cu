@@ -566,8 +566,14 @@ __global__ void __launch_bounds__(256) plan_kernel(const float* __restrict__ q0,
   if (threadIdx.x < 64) seg_s[threadIdx.x] = 0u;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  for (int i = tid; i < HW; i += 256) table[i] = 0;
-  // ---- attention weights: P (=8) logits per anchor, softmax over the poses
+  for (int i = tid; i < HW / 8; i += 256) reinterpret_cast<uint4*>(table)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = (HW / 8) * 8 + tid; i < HW; i += 256) table[i] = 0;
+  // ---- attention weights: P (=8) logits per anchor, softmax over the poses; the 8 x 256 head is
+  // staged in shared memory once per CTA
+  __shared__ __align__(16) float ww[8 * D];
+  for (int i = tid; i < 8 * D / 4; i += 256)
+    reinterpret_cast<float4*>(ww)[i] = __ldg(reinterpret_cast<const float4*>(attw_w) + i);
+  __syncthreads();
   for (int a = warp; a < A; a += 8) {
     float qv[8];
     if (q0_spt > 0) {
@@ -588,7 +594,7 @@ __global__ void __launch_bounds__(256) plan_kernel(const float* __restrict__ q0,
     for (int o = 0; o < 8; ++o) {
       float s = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) s = fmaf(qv[i], attw_w[o * D + lane + 32 * i], s);
+      for (int i = 0; i < 8; ++i) s = fmaf(qv[i], ww[o * D + lane + 32 * i], s);
       logit[o] = warp_sum(s) + attw_b[o];
     }
     float mx = logit[0];
@@ -619,7 +625,23 @@ __global__ void __launch_bounds__(256) plan_kernel(const float* __restrict__ q0,
   const int ipt = (HW + 255) / 256;
   const int beg = tid * ipt, end = min(HW, beg + ipt);
   int cnt = 0;
-  for (int i = beg; i < end; ++i) cnt += table[i] ? 1 : 0;
+  // a thread's run of table entries as a bit mask (runs of 16: two 16-byte reads instead of 16
+  // bank-conflicting 2-byte ones); longer runs fall back to the scalar scan
+  unsigned int present = 0;
+  const bool fast = ipt == 16 && (HW & 15) == 0;
+  if (fast) {
+    const uint4 t0 = *reinterpret_cast<const uint4*>(table + beg);
+    const uint4 t1 = *reinterpret_cast<const uint4*>(table + beg + 8);
+    const unsigned int w[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (w[k] & 0xffffu) present |= 1u << (2 * k);
+      if (w[k] >> 16) present |= 1u << (2 * k + 1);
+    }
+    cnt = __popc(present);
+  } else {
+    for (int i = beg; i < end; ++i) cnt += table[i] ? 1 : 0;
+  }
   int incl = cnt;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -648,7 +670,7 @@ __global__ void __launch_bounds__(256) plan_kernel(const float* __restrict__ q0,
     }
   };
   for (int i = beg; i < end; ++i) {
-    if (table[i]) {
+    if (fast ? ((present >> (i - beg)) & 1u) : (table[i] != 0)) {
       const int yy = i / W, xx = i - yy * W;
       DDH_ASSERT(base < rcap);
       upix[(size_t)scene * rcap + base] = (yy << 16) | xx;   // packed (y, x)
