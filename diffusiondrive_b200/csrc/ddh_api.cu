@@ -120,6 +120,11 @@ struct ddh_handle {
   std::vector<void*> owned_res2;
   R2Consts* res2_consts = nullptr;
   R2Consts res2_host;
+  // dense mode of the resident engine (whole-map value_proj on helper clusters, kernels_res2.h)
+  int dense_max_b = 1;                         // option "dense_conv": largest batch served this way (0: off)
+  bool dense_ok = false;
+  DenseArgs dense_host;
+  const void* dense_amap_base = nullptr;       // base address the A tensor map currently describes
   // scene-tile chain engine (kernels_chain.cu): B > RES_MAX_B in bf16 mode
   int chain_enabled = 1;
   bool chain_ok = false;
@@ -263,6 +268,21 @@ int encode_wmap(ddh_handle* h, CUtensorMap* out, void* w16, int N, int K, int bo
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(h, DDH_ERR_CUDA, "cuTensorMapEncodeTiled failed, CUresult " + std::to_string((int)r));
+  return DDH_OK;
+}
+
+// TMA tensor map over an NHWC bf16 feature map [B][H][W][256]: box {64 channels, 64 pixels, 2 rows,
+// 1 scene}, 128-byte swizzle; coordinates outside the map read as zeros (the conv's padding).
+int encode_nhwc_map(ddh_handle* h, CUtensorMap* out, const void* base, int B, int H, int W) {
+  const cuuint64_t gdim[4] = {256, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  const cuuint64_t gstride[3] = {512, (cuuint64_t)W * 512, (cuuint64_t)H * W * 512};
+  const cuuint32_t box[4] = {64, 64, 2, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = h->encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(h, DDH_ERR_CUDA, "cuTensorMapEncodeTiled (NHWC map) failed, CUresult " + std::to_string((int)r));
   return DDH_OK;
 }
 
@@ -563,6 +583,20 @@ int build_res2(ddh_handle* h, cudaStream_t st) {
   TRY(dev_alloc(h, o, &C.tap_q0, (size_t)RES_MAX_B * A * D));
   TRY(dev_alloc(h, o, &C.tap_x1, (size_t)RES_MAX_B * A * D));
   TRY(dev_alloc(h, o, &C.tap_regraw, (size_t)RES_MAX_B * A * 3 * P));
+  // dense mode: whole-map value_proj on helper clusters of the same launch
+  h->dense_ok = false;
+  h->dense_amap_base = nullptr;
+  if (W == 64 && H % 2 == 0 && res2_max_clusters() >= 2 && h->encode) {
+    DenseArgs& da = h->dense_host;
+    memset(&da, 0, sizeof da);
+    TRY(dev_alloc(h, o, &da.V, (size_t)DENSE_MAX_B * L * H * W * D));
+    TRY(dev_alloc(h, o, &da.ctrl, (size_t)DC_WORDS));
+    CU_TRY(h, cudaMemsetAsync(da.ctrl, 0, (size_t)DC_WORDS * 4, st));
+    for (int l = 0; l < L; ++l) { da.wmap[l] = h->layers[l].conv.map; da.bias[l] = h->layers[l].conv.bias; }
+    da.L = L; da.H = H; da.W = W;
+    da.enabled = 1;
+    h->dense_ok = true;
+  }
 #undef TRY
   CU_TRY(h, cudaMemcpyAsync(h->res2_consts, &C, sizeof(R2Consts), cudaMemcpyHostToDevice, st));
   CU_TRY(h, cudaStreamSynchronize(st));
@@ -1351,7 +1385,24 @@ int ddh_forward(ddh_handle* h, const float* ego, const float* agents, const void
     call.out_scores = out_scores ? out_scores : h->scores_buf;
     call.out_mode_idx = reinterpret_cast<long long*>(out_mode_idx);
     call.dbg = h->debug_taps ? h->dbg : nullptr;
-    const int e = launch_res2_forward(h->res2_consts, call, B, st);
+    // dense mode (tiny batches): the launch carries helper clusters that run value_proj over the whole
+    // map while the scene clusters do the embedding / encoder; not when the map is read in place
+    // from pinned host memory (the helpers would pull all of it across PCIe)
+    const DenseArgs* dense = nullptr;
+    if (h->dense_ok && B <= h->dense_max_b && B <= DENSE_MAX_B && !h->host_map_call) {
+      DenseArgs& da = h->dense_host;
+      const void* base = call.bev_nhwc_bf16 ? call.bev : h->res2_host.bev_nhwc;
+      if (base != h->dense_amap_base) {
+        rc = encode_nhwc_map(h, &da.amap, base, call.bev_nhwc_bf16 ? B : RES_MAX_B, s.bev_h, s.bev_w);
+        if (rc) return rc;
+        h->dense_amap_base = call.bev_nhwc_bf16 ? nullptr : base;   // a caller's map is re-described every call (its extent is B)
+      }
+      da.nhwc = call.bev_nhwc_bf16 ? nullptr : h->res2_host.bev_nhwc;
+      da.B = B;
+      da.n_helper_ctas = RES_CL * std::max(1, std::min(8, res2_max_clusters() - B));
+      dense = &da;
+    }
+    const int e = launch_res2_forward(h->res2_consts, call, B, st, dense);
     if (e) return fail(h, DDH_ERR_CUDA, std::string("res2_forward launch: ") + cudaGetErrorString((cudaError_t)e));
     h->launches++;
     if (h->debug_taps) {
@@ -1361,6 +1412,8 @@ int ddh_forward(ddh_handle* h, const float* ego, const float* agents, const void
       h->taps["res_regraw"] = {R.tap_regraw, MA * 3 * s.num_poses * 4};
       h->taps["res_kv"] = {R.kv, (size_t)B * s.num_layers * s.num_agents * 2 * D * 4};
       h->taps["res_egov"] = {R.egov, (size_t)B * s.num_layers * D * 4};
+      if (dense) h->taps["dense_v"] = {dense->V, (size_t)B * s.num_layers * s.bev_h * s.bev_w * D * 2};
+      else h->taps.erase("dense_v");
     }
     CU_TRY(h, cudaGetLastError());
     return DDH_OK;
@@ -1698,6 +1751,10 @@ int ddh_set_option(ddh_handle* h, const char* name, int value) {
   else if (n == "chain_engine") { repack = h->chain_enabled != value; h->chain_enabled = value; }
   else if (n == "resident_engine") { repack = h->res_mode != (value ? 2 : 0); h->res_mode = value ? 2 : 0; }
   else if (n == "debug_taps") h->debug_taps = value != 0;
+  else if (n == "dense_conv") {
+    if (value < 0 || value > DENSE_MAX_B) return fail(h, DDH_ERR_BAD_ARG, "ddh_set_option: dense_conv must be 0.." + std::to_string(DENSE_MAX_B));
+    h->dense_max_b = value;
+  }
   else if (n == "chain_timeline") h->chain_timeline = value;
   else if (n == "persistent_conv") h->persistent_conv = value;
   else if (n == "conv_timeline") h->conv_timeline = value;

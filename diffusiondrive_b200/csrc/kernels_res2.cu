@@ -310,10 +310,180 @@ __device__ __forceinline__ void store8(float* p, int lane, const float (&v)[8]) 
   *reinterpret_cast<float4*>(p + 128 + lane * 4) = make_float4(v[4], v[5], v[6], v[7]);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Helper clusters of a dense-mode launch (DenseArgs, kernels_res2.h): whole-map value_proj + ReLU
+// (modules/blocks.py:68-76,114) for every layer, ahead of the scene cluster that samples it.
+//   layout job (b, y):   BEV row y of scene b, NCHW f32/bf16 -> NHWC bf16 (256 threads), flag DC_ROW
+//   conv job (l, b, t):  pixels [128 t, +128) (two map rows) x 256 output channels, K = 9 x 256 as 36
+//                        k-chunks of (tap, 64 channels).  A tile = TMA box {64 ch, 64 px, 2 rows} of the
+//                        NHWC map at (dx, y0 + dy): the zero padding of the conv is the TMA's out-of-bounds
+//                        fill; B tile = [256 x 64] of the packed weights.  Four 48 KiB stages, one
+//                        producer thread per stage (a thread's TMA copies run one at a time), two MMA
+//                        issuers with private accumulators (chunks of equal parity; a thread spends
+//                        ~160 cycles per tcgen05.mma, the tensor core 128), four epilogue warps:
+//                        sum, + bias, ReLU, bf16, 512-byte pixel lines to V; counter DC_VDONE.
+// Jobs are claimed from DC_JOB in order (layout first), so a conv job only ever waits for layout
+// jobs that running CTAs hold.
+constexpr int HSTAGE = 49152, HNS = 4, HKC = 36;
+static_assert(HNS * HSTAGE <= RING + PIPE + XBYTES + F_UPIX, "helper stages end below its small shared-memory items");
+__device__ __forceinline__ void dense_helper_role(const ResCall& call, const DenseArgs& da, uint8_t* sm,
+                                                  uint32_t sm_addr, uint8_t* fix, uint32_t hbar, uint32_t tmem, int tid,
+                                                  long long* hdbg) {
+  const int warp = tid >> 5, lane = tid & 31;
+  const long long t_enter = clock64();
+  const int H = da.H, W = da.W, L = da.L, B = da.B, HW = H * W;
+  const int tiles = HW / 128;
+  const int hpr = W / 32;                              // 32-pixel layout jobs per BEV row
+  const int n_layout = da.nhwc ? B * H * hpr : 0;
+  const int total = n_layout + B * L * tiles;
+  int* ctrl = da.ctrl;
+  volatile int* job_slot = reinterpret_cast<volatile int*>(fix + F_BAR + 248);
+  float* bias_s = reinterpret_cast<float*>(fix + F_UPIX);
+  auto full = [&](int s) { return hbar + s * 8; };
+  auto empty = [&](int s) { return hbar + (HNS + s) * 8; };
+  const uint32_t accf = hbar + 2 * HNS * 8;
+  uint32_t g = 0, acc_par = 0;   // k-chunks this CTA has pipelined so far; accumulator phase
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&da.amap);
+    for (int l = 0; l < L; ++l) tma_prefetch_desc(&da.wmap[l]);
+  }
+  for (bool first = true;; first = false) {
+    if (tid == 0 && !first) *job_slot = atomicAdd(ctrl + DC_JOB, 1);   // (the first job was claimed in the kernel prologue)
+    __syncthreads();
+    const int job = *job_slot;
+    __syncthreads();
+    if (job >= total) break;
+    if (job < n_layout) {
+      const int b = job / (H * hpr), r = job - b * (H * hpr), y = r / hpr, x0 = (r - y * hpr) * 32;
+      if (tid < NCT) {
+        __nv_bfloat16* dst = da.nhwc + (size_t)b * HW * D;
+        uint32_t* tile_u32 = reinterpret_cast<uint32_t*>(sm);
+        float4 v[8];
+        if (call.bev_dtype == 0)
+          layout_load<float>(reinterpret_cast<const float*>(call.bev) + (size_t)b * D * HW, HW, y * W + x0, tid, v);
+        else
+          layout_load<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(call.bev) + (size_t)b * D * HW, HW, y * W + x0, tid, v);
+        layout_store(dst, y * W + x0, tile_u32, tid, v);
+        __threadfence();
+        fence_proxy_async_all();
+        named_bar_sync(1, NCT);
+        if (tid == 0) atomicAdd(ctrl + DC_ROW + b * H + y, 1);   // (release: every writer fenced before the barrier)
+      }
+      continue;
+    }
+    const int idx = job - n_layout;
+    // debug timeline of the CTA that runs conv job 0: clock64 per label, globaltimer at the end
+    long long* hd = (hdbg && idx == 0) ? hdbg : nullptr;
+    if (hd && tid == 0) { hd[0] = t_enter; hd[1] = clock64(); }
+    const int l = idx / (B * tiles), r = idx - l * (B * tiles), b = r / tiles, t = r - b * tiles;
+    const int y0 = t * (128 / W);
+    if (warp < HNS) {
+      if (lane == 0) {
+        if (da.nhwc) {   // the rows (with halo) this tile reads
+          const int ylo = max(0, y0 - 1), yhi = min(H - 1, y0 + 128 / W);
+          for (int y = ylo; y <= yhi; ++y) wait_flag_ge(ctrl + DC_ROW + b * H + y, hpr);
+          fence_proxy_async_all();
+        }
+        if (hd && warp == 0) hd[2] = clock64();
+        fence_proxy_async();   // the layout tile (generic writes) aliases stage 0
+        for (int c = warp; c < HKC; c += HNS) {
+          const uint32_t gi = g + c;
+          const int s = (int)(gi % HNS);
+          const uint32_t use = gi / HNS;
+          if (use > 0) mbar_wait(empty(s), (use - 1) & 1u);
+          const int tap = c >> 2, dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+          const uint32_t st_addr = sm_addr + s * HSTAGE;
+          mbar_arrive_expect_tx(full(s), HSTAGE);
+          tma_load_4d(st_addr, &da.amap, full(s), (c & 3) * 64, dx, y0 + dy, b);
+          tma_load_2d(st_addr + 16384, &da.wmap[l], full(s), c * 64, 0);
+        }
+      }
+    } else if (warp < HNS + 2) {
+      if (lane == 0) {
+        const int j = warp - HNS;
+        const uint32_t idesc = umma_idesc_bf16_m128_n256();
+        for (int c = j; c < HKC; c += 2) {
+          const uint32_t gi = g + c;
+          const int s = (int)(gi % HNS);
+          mbar_wait(full(s), (gi / HNS) & 1u);
+          tc_fence_after();
+          if (hd && c == 0) hd[3] = clock64();
+          const uint32_t st_addr = sm_addr + s * HSTAGE;
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)
+            umma_bf16(tmem + j * 256, umma_desc_sw128(st_addr + k4 * 32), umma_desc_sw128(st_addr + 16384 + k4 * 32),
+                      idesc, (c >= 2 || k4 > 0) ? 1u : 0u);
+          umma_commit(empty(s));
+        }
+        umma_commit(accf);
+        if (hd && j == 0) hd[4] = clock64();
+      }
+    } else if (warp >= 8) {
+      const int et = tid - 256, q = warp - 8;
+      bias_s[et] = __ldg(da.bias[l] + et);
+      bias_s[et + 128] = __ldg(da.bias[l] + et + 128);
+      named_bar_sync(2, 128);
+      mbar_wait(accf, acc_par);
+      tc_fence_after();
+      if (hd && et == 0) hd[5] = clock64();
+      const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
+      // pixel row m = q*32 + lane: bf16 line staged in shared memory (pitch 528 B: conflict-free 16-byte
+      // writes at a 512-byte lane stride), then written out as whole 512-byte lines per warp instruction
+      // (the pipeline stages are idle: every MMA of the job has completed)
+      constexpr int EPITCH = 528;
+      uint8_t* stg = sm + (size_t)(q * 32) * EPITCH;
+#pragma unroll 1
+      for (int cb = 0; cb < 8; ++cb) {
+        uint32_t u0[32], u1[32];
+        tmem_ld32(tl + cb * 32, u0);
+        tmem_ld32(tl + 256 + cb * 32, u1);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float x0 = fmaxf(__uint_as_float(u0[2 * i]) + __uint_as_float(u1[2 * i]) + bias_s[cb * 32 + 2 * i], 0.f);
+          const float x1 = fmaxf(__uint_as_float(u0[2 * i + 1]) + __uint_as_float(u1[2 * i + 1]) + bias_s[cb * 32 + 2 * i + 1], 0.f);
+          const __nv_bfloat162 pr = __floats2bfloat162_rn(x0, x1);
+          pk[i] = *reinterpret_cast<const uint32_t*>(&pr);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<uint4*>(stg + (size_t)lane * EPITCH + cb * 64 + i * 16) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+      }
+      __syncwarp();
+      uint4* vout = reinterpret_cast<uint4*>(da.V + (((size_t)b * L + l) * HW + (size_t)t * 128 + q * 32) * D);
+#pragma unroll 4
+      for (int m = 0; m < 32; ++m)
+        vout[(size_t)m * 32 + lane] = *reinterpret_cast<const uint4*>(stg + (size_t)m * EPITCH + lane * 16);
+      __threadfence();
+      tc_fence_before();
+      named_bar_sync(2, 128);
+      if (et == 0) atomicAdd(ctrl + DC_VDONE + b * L + l, 1);
+      if (hd && et == 0) {
+        hd[6] = clock64();
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        hd[10] = (long long)gt;
+      }
+    }
+    g += HKC;
+    acc_par ^= 1u;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+  if (tid == 0) {
+    __threadfence();
+    atomicAdd(ctrl + DC_EXIT, 1);
+  }
+}
+
 // DBG: debug instantiation (clock64 timeline + taps, ResCall::dbg set); the production one carries none of it
 template <bool DBG>
 __global__ void __launch_bounds__(NT, 1)
-res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call_in) {
+res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call_in,
+                    const __grid_constant__ DenseArgs da) {
   ResCall call = call_in;
   if (!DBG) call.dbg = nullptr;
   extern __shared__ uint8_t smem_raw[];
@@ -358,6 +528,8 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call_in)
   const uint32_t cl_bar = conv_acc + 32;
   const uint32_t xbar0 = conv_acc + 40;   // two exchange barriers (stage parity): bytes pushed by my group land here
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(fix + F_BAR + (2 * NSLOT + 2 * CNS + 8) * 8);
+  const uint32_t hbar = bar + 176;        // helper role (dense mode): 9 barriers, then its job slot at F_BAR + 248
+  static_assert((2 * NSLOT + 2 * CNS + 8) * 8 + 4 <= 176 && 176 + (2 * HNS + 1) * 8 <= 248, "barrier area layout");
 
   {  // constants -> shared memory
     const uint4* s = reinterpret_cast<const uint4*>(gconsts);
@@ -374,14 +546,29 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call_in)
     mbar_init(cl_bar, RES_CL);
     mbar_init(xbar0, 1);
     mbar_init(xbar0 + 8, 1);
+    for (int i = 0; i < 2 * HNS; ++i) mbar_init(hbar + i * 8, 1);   // helper role: stage full / empty
+    mbar_init(hbar + 2 * HNS * 8, 2);                               // helper role: both issuers' accumulators
     fence_barrier_init();
   }
+  // helper CTA of a dense-mode launch: claim the first job now, the atomic's round trip hides
+  // under the rest of the prologue
+  if (da.enabled && (int)cluster_id_x() >= da.B && tid == 0)
+    *reinterpret_cast<volatile int*>(fix + F_BAR + 248) = atomicAdd(da.ctrl + DC_JOB, 1);
   if (warp == 8) tmem_alloc<TMEM_COLS>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   cluster_sync_hw();   // every CTA's barriers exist before anyone arrives remotely
+
+  if (da.enabled && (int)cluster_id_x() >= da.B) {   // helper cluster of a dense-mode launch
+    dense_helper_role(call, da, sm, sm_addr, fix, hbar, tmem, tid, (DBG && call.dbg) ? call.dbg + 920 : nullptr);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_hw();
+    if (warp == 8) tmem_dealloc<TMEM_COLS>(tmem);
+    return;
+  }
 
   const int A = C.A, P = C.P, Na = C.Na, L = C.L, S = C.S, H = C.H, W = C.W;
   const int AP = A * P, HW = H * W;
@@ -403,6 +590,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call_in)
       for (int si = 0; si < C.n_stages; ++si) {
         const R2Stage stg = C.stages[si];
         if (stg.flags & R2F_CONV) {
+          if (call.dense) continue;   // value_proj comes from the helper clusters
           mbar_wait(conv_go, gopar);
           gopar ^= 1u;
           const int nu = *reinterpret_cast<volatile int*>(ints_s + 4);
@@ -475,6 +663,11 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call_in)
       if (DBG && call.dbg && scene == 0 && rank == 0 && tid == 0 && dbg_i < 900)
         call.dbg[dbg_i++] = ((long long)label << 48) | (clock64() & 0xFFFFFFFFFFFFll);
     };
+    if (DBG && call.dbg && scene == 0 && rank == 0 && tid == 0) {
+      unsigned long long gt;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+      call.dbg[920 + 11] = (long long)gt;
+    }
     auto bsync = [&]() { named_bar_sync(1, NCT); };
     // all compute threads of all CTAs; release/acquire at cluster scope (covers the remote
     // shared-memory pushes and the global memory exchanged through L2)
@@ -763,256 +956,16 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call_in)
         // in-bounds bilinear corners, prefix popcount over its words (pixel order == memory order of
         // the NHWC map), and every corner looks its slot up; the unique-pixel list is written from the
         // corner side (duplicates store the same value), so nobody walks the bitmap bit by bit
-        int nu;
-        unsigned long long todo;
-        {
-          const int nwords = HW / 32;
-          if (tid < nwords) bm_s[tid] = 0u;
-          if (tid < CCOLS) cbias_s[tid] = __ldg(LC.b_conv + fg * CCOLS + tid);
-          Corners c;
-          float a_w = 0.f;
-          if (tid < AP) {
-            c = corners_of(pts_s[tid * 2 + 0], pts_s[tid * 2 + 1], H, W, C.oc);
-            a_w = aw_s[l * AP + tid];
-          }
-          mark(110);
-          bsync();
-          if (tid < AP) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (c.pix[q] >= 0) atomicOr(bm_s + (c.pix[q] >> 5), 1u << (c.pix[q] & 31));
-          }
-          bsync();
-          mark(111);
-          if (tid < 128) {
-            const unsigned int bits = tid < nwords ? bm_s[tid] : 0u;
-            const int cnt = __popc(bits);
-            int incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-              const int t = __shfl_up_sync(0xffffffffu, incl, o);
-              if (lane >= o) incl += t;
-            }
-            if (lane == 31) ints_s[warp] = incl;
-            // BEV rows (with their 3x3 halo) this warp's words touch: one shared-memory word per warp
-            // (a 64-bit atomic per thread on one word costs ~4 k cycles)
-            const int y = (tid * 32) / W;
-            const unsigned long long m = bits ? ((y > 0) ? (7ull << (y - 1)) : 3ull) : 0ull;
-            const unsigned int lo = __reduce_or_sync(0xffffffffu, (unsigned int)m);
-            const unsigned int hi = __reduce_or_sync(0xffffffffu, (unsigned int)(m >> 32));
-            if (lane == 0) need_s[2 + warp] = ((unsigned long long)hi << 32) | lo;
-            named_bar_sync(3, 128);
-            int base = incl - cnt;
-            for (int w = 0; w < warp; ++w) base += ints_s[w];
-            if (tid == 127) ints_s[4] = base + cnt;
-            if (tid < nwords) pre_s[tid] = base;
-          }
-          bsync();
-          mark(112);
-          nu = ints_s[4];
-          const unsigned long long need_any = (need_s[2] | need_s[3]) | (need_s[4] | need_s[5]);
-          const unsigned long long need_all = (H >= 64) ? need_any : (need_any & ((1ull << H) - 1ull));
-          const unsigned long long done_rows = need_s[1];
-          todo = call.bev_nhwc_bf16 ? 0ull : (need_all & ~done_rows);
-          if (tid < AP) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              EntPair ep;
-              ep.slot = -1;
-              ep.w = 0.f;
-              if (c.pix[q] >= 0) {
-                const int wd = c.pix[q] >> 5;
-                ep.slot = pre_s[wd] + __popc(bm_s[wd] & ((1u << (c.pix[q] & 31)) - 1u));
-                ep.w = c.w[q] * a_w;
-                const int y = c.pix[q] / W;
-                upix_s[ep.slot] = (y << 16) | (c.pix[q] - y * W);
-              }
-              ent[tid * 4 + q] = ep;
-            }
-          }
-        }
-        bsync();
-        if (tid == 0) need_s[1] |= (need_s[2] | need_s[3]) | (need_s[4] | need_s[5]);
-        mark(20);
-        // ============ on-demand BEV layout: the rows this conv call reads, not converted yet
-        if (todo) {
-          uint32_t* tile_u32 = reinterpret_cast<uint32_t*>(pipe);
-          __nv_bfloat16* dst = C.bev_nhwc + (size_t)scene * HW * D;
-          const int tpr = W / 32;
-          // my items: (needed row, 32-pixel block) number rank, rank + 16, ...
-          auto item_px0 = [&](int it) {   // the it-th (row, block) of `todo`, or -1
-            const int row_i = it / tpr;
-            if (row_i >= __popcll(todo)) return -1;
-            unsigned long long r = todo;
-            for (int q = 0; q < row_i; ++q) r &= r - 1;
-            return (__ffsll((long long)r) - 1) * W + (it - row_i * tpr) * 32;
-          };
-          const bool f32 = call.bev_dtype == 0;
-          const float* src32 = reinterpret_cast<const float*>(call.bev) + (size_t)scene * D * HW;
-          const __nv_bfloat16* src16 = reinterpret_cast<const __nv_bfloat16*>(call.bev) + (size_t)scene * D * HW;
-          float4 va[8], vb[8];
-          int px_cur = item_px0(rank);
-          if (px_cur >= 0) { if (f32) layout_load<float>(src32, HW, px_cur, tid, va); else layout_load<__nv_bfloat16>(src16, HW, px_cur, tid, va); }
-          for (int it = rank; px_cur >= 0; it += RES_CL) {
-            const int px_next = item_px0(it + RES_CL);
-            if (px_next >= 0) { if (f32) layout_load<float>(src32, HW, px_next, tid, vb); else layout_load<__nv_bfloat16>(src16, HW, px_next, tid, vb); }
-            layout_store(dst, px_cur, tile_u32, tid, va);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) va[i] = vb[i];
-            px_cur = px_next;
-          }
-          csync();
-          mark(21);
-        } else {
-          bsync();
-        }
-        // ============ value_proj conv at the unique pixels + bilinear/attention combine:
-        // CTA (ag, fg) = (64-row tile, 64-column group)
-        {
-          if (tid == 0) mbar_arrive(conv_go);
-          // the conv's weight tiles (8 KiB per k-chunk) are fetched by lane 0 of compute warp g % 8, so
-          // that eight threads share the bulk copies (a thread's copies run one at a time)
-          const uint8_t* wconv = reinterpret_cast<const uint8_t*>(C.stages[sidx++].w) + (size_t)fg * KC_CONV * (CCOLS * 128);
-          const int passes = (nu + 255) / 256;
-          const int a_c = tid >> 4, cqd = tid & 15;         // combine: anchors a_c, a_c + 16; 4-column group
-          float4 sacc[2];
-          sacc[0] = sacc[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-          float* Vs = reinterpret_cast<float*>(xr + X_VS);
-          for (int pass = 0; pass < passes; ++pass) {
-            const int row_base = pass * 256 + ag * CROWS;
-            if (row_base >= nu) continue;
-            const int rows_valid = min(CROWS, nu - row_base);
-            const int j = tid & 7, rb = tid >> 3;
-            int rowoff[2];
-            uint32_t vmask[2];
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const int r = rb + 32 * i;
-              rowoff[i] = 0;
-              vmask[i] = 0;
-              if (r < rows_valid) {
-                const int yx = upix_s[row_base + r];
-                const int y = yx >> 16, x = yx & 0xffff;
-                rowoff[i] = (y * W + x) * D + j * 8;
-                const uint32_t xm = (x > 0 ? 1u : 0u) | 2u | (x + 1 < W ? 4u : 0u);
-                vmask[i] = (y > 0 ? xm : 0u) | (xm << 3) | (y + 1 < H ? (xm << 6) : 0u);
-              }
-            }
-            const uint32_t dst_base = rb * 128 + ((j ^ (rb & 7)) << 4);
-            for (int kp = 0; kp < KP_CONV; ++kp) {
-              const int g = cg + kp, s = g % CNS;
-              mbar_wait(conv_empty(s), (uint32_t)(((g / CNS) & 1) ^ 1));
-              if (lane == 0 && warp == (g & 7)) {   // both weight tiles of the step are contiguous in the packed image
-                mbar_arrive_expect_tx(conv_full(s), 2 * CCOLS * 128);
-                bulk_load(sm_addr + s * CSTAGE + 2 * CA_TILE, wconv + (size_t)kp * (2 * CCOLS * 128), 2 * CCOLS * 128, conv_full(s));
-              }
-#pragma unroll
-              for (int c = 0; c < 2; ++c) {
-                const int kc = kp * 2 + c;
-                const uint32_t a_dst = sm_addr + s * CSTAGE + c * CA_TILE + dst_base;
-                const int tap = kc >> 2;
-                const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
-                const int tapoff = (dy * W + dx) * D + (kc & 3) * 64;
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                  const bool ok = (vmask[i] >> tap) & 1u;
-                  const int off = ok ? rowoff[i] + tapoff : 0;
-                  cp_async16(a_dst + i * 4096, bevn + off, ok ? 16u : 0u);
-                }
-              }
-              const int kc = kp;   // (bias preload below runs on the first step)
-              if (kc == 0 && warp < 4) {   // accumulators start at the conv bias
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                  uint32_t u[32];
-#pragma unroll
-                  for (int q = 0; q < 8; ++q) {
-                    const uint4 t4 = *reinterpret_cast<const uint4*>(cbias_s + hh * 32 + 4 * q);
-                    u[4 * q + 0] = t4.x; u[4 * q + 1] = t4.y; u[4 * q + 2] = t4.z; u[4 * q + 3] = t4.w;
-                  }
-                  tmem_st32(tlane + ACC_CONV + hh * 32, u);
-                }
-                tmem_st_wait();
-                tc_fence_before();
-              }
-              cp_async_mbar_arrive_noinc(conv_full(s));
-            }
-            cg += KP_CONV;
-            mark(125);
-            mbar_wait(conv_acc, conv_par);
-            conv_par ^= 1u;
-            tc_fence_after();
-            mark(126);
-            if (warp < 4) {   // drain (ReLU) into the staging area: row quad*16 + lane lives in lanes 0..15
-              float* vrow = Vs + (size_t)(quad * 16 + (lane & 15)) * VS_LD;
-#pragma unroll
-              for (int hh = 0; hh < 2; ++hh) {
-                uint32_t u0[32];
-                tmem_ld32(tlane + ACC_CONV + hh * 32, u0);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 1; j < NMMA; ++j) {
-                  uint32_t u1[32];
-                  tmem_ld32(tlane + ACC_CONV + j * CCOLS + hh * 32, u1);
-                  tmem_ld_wait();
-#pragma unroll
-                  for (int q = 0; q < 32; ++q) u0[q] = __float_as_uint(__uint_as_float(u0[q]) + __uint_as_float(u1[q]));
-                }
-                if (lane < 16) {
-#pragma unroll
-                  for (int q = 0; q < 8; ++q)
-                    *reinterpret_cast<float4*>(vrow + hh * 32 + 4 * q) = make_float4(
-                        fmaxf(__uint_as_float(u0[4 * q]), 0.f), fmaxf(__uint_as_float(u0[4 * q + 1]), 0.f),
-                        fmaxf(__uint_as_float(u0[4 * q + 2]), 0.f), fmaxf(__uint_as_float(u0[4 * q + 3]), 0.f));
-                }
-              }
-              tc_fence_before();
-            }
-            bsync();
-            mark(127);
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const int a = a_c + 16 * i;
-              if (a < A) {
-                const EntPair* ea = ent + a * P * 4;
-                for (int q0 = 0; q0 < P * 4; q0 += 8) {   // 8 entries in flight, no branches
-                  float wq[8];
-                  float4 vq[8];
-#pragma unroll
-                  for (int q = 0; q < 8; ++q) {
-                    const EntPair e = ea[q0 + q];
-                    const int rr = e.slot - row_base;
-                    const bool ok = rr >= 0 && rr < rows_valid;
-                    wq[q] = ok ? e.w : 0.f;
-                    vq[q] = *reinterpret_cast<const float4*>(Vs + (size_t)(ok ? rr : 0) * VS_LD + cqd * 4);
-                  }
-#pragma unroll
-                  for (int q = 0; q < 8; ++q) {
-                    sacc[i].x = fmaf(wq[q], vq[q].x, sacc[i].x); sacc[i].y = fmaf(wq[q], vq[q].y, sacc[i].y);
-                    sacc[i].z = fmaf(wq[q], vq[q].z, sacc[i].z); sacc[i].w = fmaf(wq[q], vq[q].w, sacc[i].w);
-                  }
-                }
-              }
-            }
-            bsync();
-          }
-          mark(128);
-          // this CTA's [A x 64] slice of the sampled features -> the four CTAs of each anchor's group
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const int a = a_c + 16 * i;
-            if (a < A) {
-              const int g_a = a / NAG, n = a - g_a * NAG;
-              const uint32_t d = off_x + X_SP + (uint32_t)(((ag * NAG + n) * D + fg * CCOLS + cqd * 4) * 4);
-#pragma unroll
-              for (int jj = 0; jj < GF; ++jj) st_cluster_v4(mapa(sm_addr + d, (uint32_t)(g_a * GF + jj)), sacc[i]);
-            }
-          }
-          mark(129);
-          // stage the agent K|V of my two heads (fp32) in the idle conv pipeline buffers
-          {
+        int nu = 0;
+        if (call.dense) {
+          // ============ dense mode: ReLU(value_proj) of the whole map was written by the helper clusters;
+          // sample it at the 4 bilinear corners of my group's anchors (blocks.py:98-125).  Work item =
+          // (anchor, half of its 8 points): a lane owns 8 channels, 16 corner lines (512 B each) in flight.
+          ++sidx;   // the conv entry of the schedule
+          const __nv_bfloat16* Vl = da.V + ((size_t)scene * L + l) * HW * D;
+          {  // stage the agent K|V of my two heads (fp32) in the idle conv pipeline buffers
             const float* kvl = kvg + (size_t)l * Na * 2 * D;
-            const int n16 = Na * 32;   // per agent: 16 units of K, 16 units of V
+            const int n16 = Na * 32;
             for (int i = tid; i < n16; i += NCT) {
               const int jrow = i >> 5, u = i & 31;
               const uint32_t dst = (u < 16) ? pipe_addr + P_KV + (uint32_t)((jrow * KS_LD + u * 4) * 4)
@@ -1022,12 +975,324 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call_in)
             }
             cp_async_commit();
           }
-          csync();
+          // corner (pixel, bilinear x attention weight) pairs of my anchors' points: one thread per point
+          if (tid < n_own * P) {
+            const int ap = a0 * P + tid;
+            const Corners c = corners_of(pts_s[ap * 2 + 0], pts_s[ap * 2 + 1], H, W, C.oc);
+            const float a_w = aw_s[l * AP + ap];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              EntPair ep;
+              ep.slot = c.pix[q] >= 0 ? c.pix[q] : 0;
+              ep.w = c.pix[q] >= 0 ? c.w[q] * a_w : 0.f;
+              ent[tid * 4 + q] = ep;
+            }
+          }
+          if (DBG && call.dbg && scene == 0 && rank == 0 && tid == 0 && si == 0 && l == 0) {
+            unsigned long long gt;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+            call.dbg[920 + 12] = (long long)gt;   // the scene cluster reaches its first gather
+          }
+          if (si == 0) wait_flag_ge(da.ctrl + DC_VDONE + scene * L + l, HW / 128);
+          bsync();
+          mark(120);
+          float* part = reinterpret_cast<float*>(xr + X_SP);   // [half][NAG][256], summed by the bev_out stage
+          for (int item = warp; item < 2 * n_own; item += 8) {
+            const int n = item >> 1, hf = item & 1;
+            const EntPair* ea = ent + (n * P + hf * 4) * 4;
+            uint4 v[16];
+            float wq[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const EntPair ep = ea[e];
+              wq[e] = ep.w;
+              v[e] = __ldcg(reinterpret_cast<const uint4*>(Vl + (size_t)ep.slot * D + lane * 8));
+            }
+            float acc[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const uint32_t uu[4] = {v[e].x, v[e].y, v[e].z, v[e].w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const __nv_bfloat162 pr = *reinterpret_cast<const __nv_bfloat162*>(&uu[i]);
+                acc[2 * i] = fmaf(wq[e], __low2float(pr), acc[2 * i]);
+                acc[2 * i + 1] = fmaf(wq[e], __high2float(pr), acc[2 * i + 1]);
+              }
+            }
+            float* pd = part + (size_t)(hf * NAG + n) * D + lane * 8;
+            *reinterpret_cast<float4*>(pd) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            *reinterpret_cast<float4*>(pd + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+          }
+          mark(121);
+          bsync();
+        } else {
+          unsigned long long todo;
+          {
+            const int nwords = HW / 32;
+            if (tid < nwords) bm_s[tid] = 0u;
+            if (tid < CCOLS) cbias_s[tid] = __ldg(LC.b_conv + fg * CCOLS + tid);
+            Corners c;
+            float a_w = 0.f;
+            if (tid < AP) {
+              c = corners_of(pts_s[tid * 2 + 0], pts_s[tid * 2 + 1], H, W, C.oc);
+              a_w = aw_s[l * AP + tid];
+            }
+            mark(110);
+            bsync();
+            if (tid < AP) {
+  #pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (c.pix[q] >= 0) atomicOr(bm_s + (c.pix[q] >> 5), 1u << (c.pix[q] & 31));
+            }
+            bsync();
+            mark(111);
+            if (tid < 128) {
+              const unsigned int bits = tid < nwords ? bm_s[tid] : 0u;
+              const int cnt = __popc(bits);
+              int incl = cnt;
+  #pragma unroll
+              for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+              }
+              if (lane == 31) ints_s[warp] = incl;
+              // BEV rows (with their 3x3 halo) this warp's words touch: one shared-memory word per warp
+              // (a 64-bit atomic per thread on one word costs ~4 k cycles)
+              const int y = (tid * 32) / W;
+              const unsigned long long m = bits ? ((y > 0) ? (7ull << (y - 1)) : 3ull) : 0ull;
+              const unsigned int lo = __reduce_or_sync(0xffffffffu, (unsigned int)m);
+              const unsigned int hi = __reduce_or_sync(0xffffffffu, (unsigned int)(m >> 32));
+              if (lane == 0) need_s[2 + warp] = ((unsigned long long)hi << 32) | lo;
+              named_bar_sync(3, 128);
+              int base = incl - cnt;
+              for (int w = 0; w < warp; ++w) base += ints_s[w];
+              if (tid == 127) ints_s[4] = base + cnt;
+              if (tid < nwords) pre_s[tid] = base;
+            }
+            bsync();
+            mark(112);
+            nu = ints_s[4];
+            const unsigned long long need_any = (need_s[2] | need_s[3]) | (need_s[4] | need_s[5]);
+            const unsigned long long need_all = (H >= 64) ? need_any : (need_any & ((1ull << H) - 1ull));
+            const unsigned long long done_rows = need_s[1];
+            todo = call.bev_nhwc_bf16 ? 0ull : (need_all & ~done_rows);
+            if (tid < AP) {
+  #pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                EntPair ep;
+                ep.slot = -1;
+                ep.w = 0.f;
+                if (c.pix[q] >= 0) {
+                  const int wd = c.pix[q] >> 5;
+                  ep.slot = pre_s[wd] + __popc(bm_s[wd] & ((1u << (c.pix[q] & 31)) - 1u));
+                  ep.w = c.w[q] * a_w;
+                  const int y = c.pix[q] / W;
+                  upix_s[ep.slot] = (y << 16) | (c.pix[q] - y * W);
+                }
+                ent[tid * 4 + q] = ep;
+              }
+            }
+          }
+          bsync();
+          if (tid == 0) need_s[1] |= (need_s[2] | need_s[3]) | (need_s[4] | need_s[5]);
+          mark(20);
+          // ============ on-demand BEV layout: the rows this conv call reads, not converted yet
+          if (todo) {
+            uint32_t* tile_u32 = reinterpret_cast<uint32_t*>(pipe);
+            __nv_bfloat16* dst = C.bev_nhwc + (size_t)scene * HW * D;
+            const int tpr = W / 32;
+            // my items: (needed row, 32-pixel block) number rank, rank + 16, ...
+            auto item_px0 = [&](int it) {   // the it-th (row, block) of `todo`, or -1
+              const int row_i = it / tpr;
+              if (row_i >= __popcll(todo)) return -1;
+              unsigned long long r = todo;
+              for (int q = 0; q < row_i; ++q) r &= r - 1;
+              return (__ffsll((long long)r) - 1) * W + (it - row_i * tpr) * 32;
+            };
+            const bool f32 = call.bev_dtype == 0;
+            const float* src32 = reinterpret_cast<const float*>(call.bev) + (size_t)scene * D * HW;
+            const __nv_bfloat16* src16 = reinterpret_cast<const __nv_bfloat16*>(call.bev) + (size_t)scene * D * HW;
+            float4 va[8], vb[8];
+            int px_cur = item_px0(rank);
+            if (px_cur >= 0) { if (f32) layout_load<float>(src32, HW, px_cur, tid, va); else layout_load<__nv_bfloat16>(src16, HW, px_cur, tid, va); }
+            for (int it = rank; px_cur >= 0; it += RES_CL) {
+              const int px_next = item_px0(it + RES_CL);
+              if (px_next >= 0) { if (f32) layout_load<float>(src32, HW, px_next, tid, vb); else layout_load<__nv_bfloat16>(src16, HW, px_next, tid, vb); }
+              layout_store(dst, px_cur, tile_u32, tid, va);
+  #pragma unroll
+              for (int i = 0; i < 8; ++i) va[i] = vb[i];
+              px_cur = px_next;
+            }
+            csync();
+            mark(21);
+          } else {
+            bsync();
+          }
+          // ============ value_proj conv at the unique pixels + bilinear/attention combine:
+          // CTA (ag, fg) = (64-row tile, 64-column group)
+          {
+            if (tid == 0) mbar_arrive(conv_go);
+            // the conv's weight tiles (8 KiB per k-chunk) are fetched by lane 0 of compute warp g % 8, so
+            // that eight threads share the bulk copies (a thread's copies run one at a time)
+            const uint8_t* wconv = reinterpret_cast<const uint8_t*>(C.stages[sidx++].w) + (size_t)fg * KC_CONV * (CCOLS * 128);
+            const int passes = (nu + 255) / 256;
+            const int a_c = tid >> 4, cqd = tid & 15;         // combine: anchors a_c, a_c + 16; 4-column group
+            float4 sacc[2];
+            sacc[0] = sacc[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            float* Vs = reinterpret_cast<float*>(xr + X_VS);
+            for (int pass = 0; pass < passes; ++pass) {
+              const int row_base = pass * 256 + ag * CROWS;
+              if (row_base >= nu) continue;
+              const int rows_valid = min(CROWS, nu - row_base);
+              const int j = tid & 7, rb = tid >> 3;
+              int rowoff[2];
+              uint32_t vmask[2];
+  #pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                const int r = rb + 32 * i;
+                rowoff[i] = 0;
+                vmask[i] = 0;
+                if (r < rows_valid) {
+                  const int yx = upix_s[row_base + r];
+                  const int y = yx >> 16, x = yx & 0xffff;
+                  rowoff[i] = (y * W + x) * D + j * 8;
+                  const uint32_t xm = (x > 0 ? 1u : 0u) | 2u | (x + 1 < W ? 4u : 0u);
+                  vmask[i] = (y > 0 ? xm : 0u) | (xm << 3) | (y + 1 < H ? (xm << 6) : 0u);
+                }
+              }
+              const uint32_t dst_base = rb * 128 + ((j ^ (rb & 7)) << 4);
+              for (int kp = 0; kp < KP_CONV; ++kp) {
+                const int g = cg + kp, s = g % CNS;
+                mbar_wait(conv_empty(s), (uint32_t)(((g / CNS) & 1) ^ 1));
+                if (lane == 0 && warp == (g & 7)) {   // both weight tiles of the step are contiguous in the packed image
+                  mbar_arrive_expect_tx(conv_full(s), 2 * CCOLS * 128);
+                  bulk_load(sm_addr + s * CSTAGE + 2 * CA_TILE, wconv + (size_t)kp * (2 * CCOLS * 128), 2 * CCOLS * 128, conv_full(s));
+                }
+  #pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                  const int kc = kp * 2 + c;
+                  const uint32_t a_dst = sm_addr + s * CSTAGE + c * CA_TILE + dst_base;
+                  const int tap = kc >> 2;
+                  const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+                  const int tapoff = (dy * W + dx) * D + (kc & 3) * 64;
+  #pragma unroll
+                  for (int i = 0; i < 2; ++i) {
+                    const bool ok = (vmask[i] >> tap) & 1u;
+                    const int off = ok ? rowoff[i] + tapoff : 0;
+                    cp_async16(a_dst + i * 4096, bevn + off, ok ? 16u : 0u);
+                  }
+                }
+                const int kc = kp;   // (bias preload below runs on the first step)
+                if (kc == 0 && warp < 4) {   // accumulators start at the conv bias
+  #pragma unroll
+                  for (int hh = 0; hh < 2; ++hh) {
+                    uint32_t u[32];
+  #pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                      const uint4 t4 = *reinterpret_cast<const uint4*>(cbias_s + hh * 32 + 4 * q);
+                      u[4 * q + 0] = t4.x; u[4 * q + 1] = t4.y; u[4 * q + 2] = t4.z; u[4 * q + 3] = t4.w;
+                    }
+                    tmem_st32(tlane + ACC_CONV + hh * 32, u);
+                  }
+                  tmem_st_wait();
+                  tc_fence_before();
+                }
+                cp_async_mbar_arrive_noinc(conv_full(s));
+              }
+              cg += KP_CONV;
+              mark(125);
+              mbar_wait(conv_acc, conv_par);
+              conv_par ^= 1u;
+              tc_fence_after();
+              mark(126);
+              if (warp < 4) {   // drain (ReLU) into the staging area: row quad*16 + lane lives in lanes 0..15
+                float* vrow = Vs + (size_t)(quad * 16 + (lane & 15)) * VS_LD;
+  #pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                  uint32_t u0[32];
+                  tmem_ld32(tlane + ACC_CONV + hh * 32, u0);
+                  tmem_ld_wait();
+  #pragma unroll
+                  for (int j = 1; j < NMMA; ++j) {
+                    uint32_t u1[32];
+                    tmem_ld32(tlane + ACC_CONV + j * CCOLS + hh * 32, u1);
+                    tmem_ld_wait();
+  #pragma unroll
+                    for (int q = 0; q < 32; ++q) u0[q] = __float_as_uint(__uint_as_float(u0[q]) + __uint_as_float(u1[q]));
+                  }
+                  if (lane < 16) {
+  #pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                      *reinterpret_cast<float4*>(vrow + hh * 32 + 4 * q) = make_float4(
+                          fmaxf(__uint_as_float(u0[4 * q]), 0.f), fmaxf(__uint_as_float(u0[4 * q + 1]), 0.f),
+                          fmaxf(__uint_as_float(u0[4 * q + 2]), 0.f), fmaxf(__uint_as_float(u0[4 * q + 3]), 0.f));
+                  }
+                }
+                tc_fence_before();
+              }
+              bsync();
+              mark(127);
+  #pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                const int a = a_c + 16 * i;
+                if (a < A) {
+                  const EntPair* ea = ent + a * P * 4;
+                  for (int q0 = 0; q0 < P * 4; q0 += 8) {   // 8 entries in flight, no branches
+                    float wq[8];
+                    float4 vq[8];
+  #pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                      const EntPair e = ea[q0 + q];
+                      const int rr = e.slot - row_base;
+                      const bool ok = rr >= 0 && rr < rows_valid;
+                      wq[q] = ok ? e.w : 0.f;
+                      vq[q] = *reinterpret_cast<const float4*>(Vs + (size_t)(ok ? rr : 0) * VS_LD + cqd * 4);
+                    }
+  #pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                      sacc[i].x = fmaf(wq[q], vq[q].x, sacc[i].x); sacc[i].y = fmaf(wq[q], vq[q].y, sacc[i].y);
+                      sacc[i].z = fmaf(wq[q], vq[q].z, sacc[i].z); sacc[i].w = fmaf(wq[q], vq[q].w, sacc[i].w);
+                    }
+                  }
+                }
+              }
+              bsync();
+            }
+            mark(128);
+            // this CTA's [A x 64] slice of the sampled features -> the four CTAs of each anchor's group
+  #pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const int a = a_c + 16 * i;
+              if (a < A) {
+                const int g_a = a / NAG, n = a - g_a * NAG;
+                const uint32_t d = off_x + X_SP + (uint32_t)(((ag * NAG + n) * D + fg * CCOLS + cqd * 4) * 4);
+  #pragma unroll
+                for (int jj = 0; jj < GF; ++jj) st_cluster_v4(mapa(sm_addr + d, (uint32_t)(g_a * GF + jj)), sacc[i]);
+              }
+            }
+            mark(129);
+            // stage the agent K|V of my two heads (fp32) in the idle conv pipeline buffers
+            {
+              const float* kvl = kvg + (size_t)l * Na * 2 * D;
+              const int n16 = Na * 32;   // per agent: 16 units of K, 16 units of V
+              for (int i = tid; i < n16; i += NCT) {
+                const int jrow = i >> 5, u = i & 31;
+                const uint32_t dst = (u < 16) ? pipe_addr + P_KV + (uint32_t)((jrow * KS_LD + u * 4) * 4)
+                                              : pipe_addr + P_KV + (uint32_t)(32 * KS_LD * 4 + (jrow * 64 + (u - 16) * 4) * 4);
+                const float* src = kvl + (size_t)jrow * 2 * D + (u < 16 ? fg * 64 + u * 4 : D + fg * 64 + (u - 16) * 4);
+                cp_async16(dst, src, 16u);
+              }
+              cp_async_commit();
+            }
+            csync();
+          }
         }
         mark(22);
         // ============ output_proj + residual (blocks.py:127-129): x1 = S.Wo + b + q0
         {
-          const int ntile = min(4, (nu + CROWS - 1) / CROWS);   // tiles of the first pass hold everything a tile CTA accumulated
+          const int ntile = call.dense ? 2 : min(4, (nu + CROWS - 1) / CROWS);   // tiles of the first pass hold everything a tile CTA accumulated
           float sv[8];
           if (warp < n_own) {
             const float* sp = reinterpret_cast<const float*>(xr + X_SP) + warp * D;
@@ -1415,6 +1680,16 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call_in)
       if (call.out_traj)
         for (int i = tid; i < 3 * P; i += NCT) call.out_traj[(size_t)scene * 3 * P + i] = fin_modes[best * 3 * P + i];
     }
+    // dense mode: the last scene cluster to finish waits until every helper CTA has left its job
+    // loop and clears the control words for the next launch
+    if (call.dense && rank == 0 && tid == 0) {
+      int* ctrl = da.ctrl;
+      if (atomicAdd(ctrl + DC_CHAINS, 1) == da.B - 1) {
+        wait_flag_ge(ctrl + DC_EXIT, da.n_helper_ctas);
+        for (int i = 0; i < DC_WORDS; ++i) ctrl[i] = 0;
+        __threadfence();
+      }
+    }
     mark(99);
   }
   tc_fence_before();
@@ -1448,6 +1723,7 @@ void launch_pack_sw128(const __nv_bfloat16* W, __nv_bfloat16* out, int N, int K,
 int res2_smem_bytes() { return SMEM_BYTES; }
 
 static bool g_res2_ready[64] = {};   // per device: function attributes are per-device state
+static int g_res2_clusters[64] = {};  // co-resident clusters of the engine (occupancy query)
 
 static void res2_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int B, cudaStream_t st) {
   cfg = {};
@@ -1485,16 +1761,28 @@ int res2_engine_init() {
     cudaGetLastError();
     return 3;
   }
+  g_res2_clusters[dev] = nclusters;
   g_res2_ready[dev] = true;
   return 0;
 }
 
-int launch_res2_forward(const R2Consts* consts_dev, const ResCall& call, int B, cudaStream_t st) {
+int res2_max_clusters() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  return g_res2_clusters[dev];
+}
+
+int launch_res2_forward(const R2Consts* consts_dev, const ResCall& call_in, int B, cudaStream_t st,
+                        const DenseArgs* dense) {
+  static const DenseArgs no_dense = {};
+  ResCall call = call_in;
+  call.dense = (dense && dense->enabled) ? 1 : 0;
+  const DenseArgs& da = call.dense ? *dense : no_dense;
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
-  res2_cfg(cfg, attr, B, st);
-  cudaError_t e = call.dbg ? cudaLaunchKernelEx(&cfg, res2_forward_kernel<true>, consts_dev, call)
-                           : cudaLaunchKernelEx(&cfg, res2_forward_kernel<false>, consts_dev, call);
+  res2_cfg(cfg, attr, B + (call.dense ? da.n_helper_ctas / RES_CL : 0), st);
+  cudaError_t e = call.dbg ? cudaLaunchKernelEx(&cfg, res2_forward_kernel<true>, consts_dev, call, da)
+                           : cudaLaunchKernelEx(&cfg, res2_forward_kernel<false>, consts_dev, call, da);
   return e == cudaSuccess ? 0 : (int)e;
 }
 

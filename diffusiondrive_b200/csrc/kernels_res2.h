@@ -38,6 +38,36 @@ struct ResCall {
   float* out_scores;      // [B][A]
   long long* out_mode_idx;
   long long* dbg;         // optional clock64 stamps of cluster 0 / rank 0
+  int dense;              // 1: value_proj comes from the whole-map conv of the helper clusters (DenseArgs)
+  int pad0;
+};
+
+// Whole-map value_proj for very small batches (B <= DENSE_MAX_B).  One scene's 3x3 conv over the
+// full 64x64 map is 4.8 GFLOP per layer -- a few microseconds on the SMs the 16-CTA scene cluster
+// leaves idle -- while the on-demand conv (plan, dedup, layout, gathered GEMM, combine) sits four
+// times on the scene cluster's critical path.  In dense mode the SAME launch carries extra "helper"
+// clusters that (1) convert the NCHW map to NHWC bf16 and (2) run value_proj + ReLU for every pixel
+// of every layer on tcgen05 (TMA-fed implicit GEMM, 128 pixels x 256 channels per job), writing
+// V[b][l][pixel][256] bf16 to L2; the scene clusters only gather the 4 bilinear corners of their own
+// anchors' sample points.  Jobs are claimed from a counter (work stealing: any resident helper CTA
+// makes progress, so the scheme cannot deadlock on co-residency); completion flags live in `ctrl`.
+constexpr int DENSE_MAX_B = 2;
+enum : int {
+  DC_JOB = 0,       // next job to claim
+  DC_EXIT = 1,      // helper CTAs that have left their job loop
+  DC_CHAINS = 2,    // scene clusters that have finished
+  DC_VDONE = 8,     // [B][L] 128-pixel tiles of V written
+  DC_ROW = 16,      // [B][H] BEV row converted to NHWC bf16
+  DC_WORDS = DC_ROW + DENSE_MAX_B * 64,
+};
+struct DenseArgs {
+  CUtensorMap amap;                // NHWC bf16 map [B][H][W][256]: box {64 channels, 64 pixels, 2 rows, 1 scene}
+  CUtensorMap wmap[RES_MAX_L];     // value_proj weights [256][9*256] (tap, channel), box {64, 256}
+  const float* bias[RES_MAX_L];
+  __nv_bfloat16* V;                // [B][L][H*W][256]
+  __nv_bfloat16* nhwc;             // destination of the layout jobs; null: the caller's map is NHWC bf16 already
+  int* ctrl;                       // [DC_WORDS], all zero between launches
+  int enabled, n_helper_ctas, B, L, H, W;
 };
 
 
@@ -82,6 +112,9 @@ int res2_smem_bytes();
 int res2_engine_init();   // 0 when a 16-CTA cluster of this kernel can be co-scheduled
 // pack-time: bf16 [N][K] -> pre-swizzled shared-memory images of (rows x 64) tiles
 void launch_pack_sw128(const __nv_bfloat16* W, __nv_bfloat16* out, int N, int K, int rows, cudaStream_t st);
-int launch_res2_forward(const R2Consts* consts_dev, const ResCall& call, int B, cudaStream_t st);
+int res2_max_clusters();  // co-resident 16-CTA clusters of the engine on an idle device (after res2_engine_init)
+// dense: null or DenseArgs with enabled = 1 (the launch then carries n_helper_ctas / 16 helper clusters)
+int launch_res2_forward(const R2Consts* consts_dev, const ResCall& call, int B, cudaStream_t st,
+                        const DenseArgs* dense);
 
 }  // namespace ddh

@@ -92,6 +92,39 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// generic <-> async proxy ordering for every state space (global data written with st.global and
+// then read by TMA inside the same kernel)
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// spin until *p >= want (gpu-scope acquire); bounded in -DDDH_CHECKED builds
+__device__ __forceinline__ void wait_flag_ge(const int* p, int want) {
+#ifdef DDH_CHECKED
+  unsigned long long spins = 0;
+#endif
+  while (ld_acquire_gpu(p) < want) {
+    __nanosleep(32);
+#ifdef DDH_CHECKED
+    if (++spins > (1ull << 26)) {
+      printf("DDH_CHECKED: flag wait timed out (block %d thread %d, want %d)\n", (int)blockIdx.x, (int)threadIdx.x, want);
+      __trap();
+    }
+#endif
+  }
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }

@@ -256,6 +256,10 @@ DDH_API int ddh_set_concurrency(ddh_handle *h, int chunks, int min_chunk_scenes)
  * packed: after changing "chain_engine" or "resident_engine" ddh_forward fails with
  * DDH_ERR_NOT_PACKED until ddh_pack_weights is called again.
  *   "resident_engine"    1  B <= 24, bf16: whole forward as one launch (kernels_res2.cu)
+ *   "dense_conv"         1  resident engine, B <= value (0..2): value_proj + ReLU of the WHOLE map runs on
+ *                           helper clusters of the same launch (TMA-fed tcgen05 implicit GEMM) under the
+ *                           embedding / encoder, and the scene cluster only gathers bilinear corners;
+ *                           0: on-demand conv at the unique sampled pixels for every batch size
  *   "chain_engine"       1  bf16: scene-tile chain kernel per decoder-layer call (kernels_chain.cu);
  *                           0: one tcgen05 GEMM launch per Linear (kernels_tc.cu)
  *   "lazy_layout"        1  NCHW input: convert BEV segments on demand; 0: whole map up front

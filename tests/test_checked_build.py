@@ -20,7 +20,7 @@ if %(checked)d:
 info = _lib.load().ddh_build_info().decode()
 assert ("checked" in info) == bool(%(checked)d), info
 out = {}
-for tag, prec, B, opts in (("chain", "bf16", 77, {}), ("resident", "bf16", 3, {}), ("per_linear", "bf16", 9, {"chain_engine": 0, "resident_engine": 0}),
+for tag, prec, B, opts in (("chain", "bf16", 77, {}), ("resident", "bf16", 3, {}), ("resident_dense", "bf16", 2, {"dense_conv": 2}), ("per_linear", "bf16", 9, {"chain_engine": 0, "resident_engine": 0}),
                            ("conv2", "bf16", 40, {"persistent_conv": 1}), ("fp32", "fp32", 5, {})):
     sd = synth.make_state_dict()
     head = TrajectoryHead(8, 1024, 256, None, HeadConfig(), plan_anchor=sd["plan_anchor"].numpy(), precision=prec)

@@ -198,29 +198,84 @@ def test_bf16_mode_agreement_1024_scenes_and_near_tie_replan(golden_dir):
 def test_small_batch_engine_matches_reference(golden_dir):
     """B <= 24 in bf16 mode runs the group-resident engine (kernels_res2.cu): the whole forward as ONE
     launch on one 16-CTA cluster per scene.  Same tolerance as the tensor path; it is the engine the
-    batch-1 latency number is measured on."""
+    batch-1 latency number is measured on (B = 1 in its dense mode, see the next test)."""
     ref = _load(golden_dir, "default_b256")
     head, _ = _make_head("bf16")
+    ondemand, _ = _make_head("bf16")
+    ondemand.set_option("dense_conv", 0)
     outs = {}
     for B in (1, 2, 3, 8, 20):
-        out, _, _ = _run(head, B)
-        outs[B] = out
-        sub = {k: v[:B] for k, v in ref.items()}
-        rec = _report(f"bf16_resident_b{B}_vs_reference", out, sub)
-        assert rec["max_dxy_m"] <= TOL_BF16_M and rec["max_dheading_rad"] <= TOL_BF16_M
-        if B <= 8:
-            assert rec["mode_agreement"] == 1.0
-        else:   # near-tie scenes may flip under bf16 operands; clear ones must not
-            assert rec["mode_agreement_margin_gt_0.05"] in (1.0, None)
-        assert head.last_launch_count() == 1
-    # a scene's plan does not depend on the batch it rides in, nor on the run (fixed summation orders)
+        for h, tag in ((head, ""), (ondemand, "_ondemand")):
+            out, _, _ = _run(h, B)
+            sub = {k: v[:B] for k, v in ref.items()}
+            rec = _report(f"bf16_resident{tag}_b{B}_vs_reference", out, sub)
+            assert rec["max_dxy_m"] <= TOL_BF16_M and rec["max_dheading_rad"] <= TOL_BF16_M
+            if B <= 8:
+                assert rec["mode_agreement"] == 1.0
+            else:   # near-tie scenes may flip under bf16 operands; clear ones must not
+                assert rec["mode_agreement_margin_gt_0.05"] in (1.0, None)
+            assert h.last_launch_count() == 1
+            if tag:
+                outs[B] = out
+    # with one conv algorithm for every batch size a scene's plan does not depend on the batch it
+    # rides in, nor on the run (fixed summation orders)
     for k in ("trajectory_modes", "trajectory_scores", "trajectory", "mode_idx"):
         assert np.array_equal(outs[8][k][:1], outs[1][k])
         assert np.array_equal(outs[8][k][:3], outs[3][k])
         assert np.array_equal(outs[20][k][:8], outs[8][k])
-    again, _, _ = _run(head, 8)
+    again, _, _ = _run(ondemand, 8)
     for k in outs[8]:
         assert np.array_equal(again[k], outs[8][k])
+
+
+def test_resident_engine_dense_mode(golden_dir):
+    """Dense mode of the resident engine (default for B = 1, option dense_conv up to 2): helper clusters
+    of the same launch run value_proj + ReLU over the WHOLE map (TMA-fed tcgen05 implicit GEMM) and the
+    scene clusters gather bilinear corners from it.  Checked: the map itself against torch's conv2d on
+    the same bf16 operands, parity with the live-reference golden, layouts, batch independence,
+    determinism and that the control words are clean after every launch (repeated calls)."""
+    ref = _load(golden_dir, "default_b256")
+    head, sd = _make_head("bf16")
+    head.set_option("dense_conv", 2)
+    head.set_option("debug_taps", 1)
+    outs = {}
+    for B in (1, 2):
+        ft = synth.make_features(B)
+        bev = ft["bev_feature"].cuda()
+        for rep in range(3):
+            out, _, _ = _run(head, B)
+            assert head.last_launch_count() == 1
+            if rep:
+                for k in out:
+                    assert np.array_equal(out[k], outs[B][k]), (B, rep, k)
+            outs[B] = out
+        v = torch.from_numpy(head.debug_tap("dense_v", np.uint16).astype(np.int32)).cuda()
+        v = (v << 16).view(torch.float32).view(B, 2, 64, 64, 256)
+        for l in range(2):
+            w = sd[f"diff_decoder.layers.{l}.cross_bev_attention.value_proj.0.weight"].cuda()
+            b = sd[f"diff_decoder.layers.{l}.cross_bev_attention.value_proj.0.bias"].cuda()
+            want = torch.nn.functional.conv2d(bev.bfloat16().float(), w.bfloat16().float(), b, padding=1).relu()
+            want = want.permute(0, 2, 3, 1)
+            # fp32 accumulation in another order, then one bf16 rounding: half an ulp of the largest value
+            assert (v[:, l] - want).abs().max().item() <= 2.0 ** -7 * max(1.0, want.max().item()) / 2 + 1e-3
+        rec = _report(f"bf16_resident_dense_b{B}_vs_reference", out, {k: x[:B] for k, x in ref.items()})
+        assert rec["max_dxy_m"] <= TOL_BF16_M and rec["max_dheading_rad"] <= TOL_BF16_M
+        assert rec["mode_agreement"] == 1.0
+    for k in outs[1]:
+        assert np.array_equal(outs[2][k][:1], outs[1][k]), k
+    # NHWC bf16 input: no layout jobs, the TMA reads the caller's map
+    ft = synth.make_features(2)
+    nz = synth.make_noise(2)
+    nhwc = ft["bev_feature"].cuda().permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+    o2 = head(ft["ego_query"].cuda(), ft["agents_query"].cuda(), nhwc, noise=nz.cuda(), bev_layout="NHWC")
+    torch.cuda.synchronize()
+    for k in outs[2]:
+        assert np.array_equal(o2[k].cpu().numpy(), outs[2][k]), k
+    # the default: dense at B = 1 only
+    plain, _ = _make_head("bf16")
+    o1, _, _ = _run(plain, 1)
+    for k in outs[1]:
+        assert np.array_equal(o1[k], outs[1][k]), k
 
 
 def test_engines_agree():
