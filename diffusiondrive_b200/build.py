@@ -59,6 +59,35 @@ def build(force: bool = False, verbose: bool = False, checked: bool = False) -> 
     return out
 
 
+# ---- optional PyTorch binding above the C ABI (csrc/torch_binding.cpp): removes ~10 us of Python from
+# the batch-1 call; the head works without it (ctypes path).  Host-only C++ (g++ through
+# torch.utils.cpp_extension / ninja), built in-tree so that it travels to the GPU box.
+TORCH_SRC = os.path.join(CSRC, "torch_binding.cpp")
+TORCH_DIR = os.path.join(HERE, "_torch_build")
+TORCH_OUT = os.path.join(TORCH_DIR, "_ddh_torch.so")
+
+
+def build_torch_binding(force: bool = False) -> str:
+    import torch
+    with open(TORCH_SRC, "rb") as fh:
+        dig = hashlib.sha256(fh.read() + torch.__version__.encode()).hexdigest()
+    stamp = TORCH_OUT + ".stamp"
+    if not force and os.path.exists(TORCH_OUT) and os.path.exists(stamp):
+        with open(stamp) as fh:
+            if fh.read().strip() == dig:
+                return TORCH_OUT
+    from torch.utils import cpp_extension
+    os.makedirs(TORCH_DIR, exist_ok=True)
+    cpp_extension.load(name="_ddh_torch", sources=[TORCH_SRC], build_directory=TORCH_DIR,
+                       extra_cflags=["-O2"], with_cuda=True, is_python_module=False, verbose=False)
+    if not os.path.exists(TORCH_OUT):
+        raise RuntimeError("torch binding did not build")
+    with open(stamp, "w") as fh:
+        fh.write(dig)
+    return TORCH_OUT
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
     print(build(force="--force" in sys.argv, checked=True))
+    print(build_torch_binding(force="--force" in sys.argv))

@@ -348,8 +348,16 @@ __device__ __forceinline__ void dense_helper_role(const ResCall& call, const Den
     tma_prefetch_desc(&da.amap);
     for (int l = 0; l < L; ++l) tma_prefetch_desc(&da.wmap[l]);
   }
+  // tid 0 keeps one claim in flight: the job after the current one is requested before the current
+  // one starts, so the atomic's round trip never sits between two jobs (the first job was claimed
+  // in the kernel prologue)
+  int next_job = 0;
+  if (tid == 0) next_job = atomicAdd(ctrl + DC_JOB, 1);
   for (bool first = true;; first = false) {
-    if (tid == 0 && !first) *job_slot = atomicAdd(ctrl + DC_JOB, 1);   // (the first job was claimed in the kernel prologue)
+    if (tid == 0 && !first) {
+      *job_slot = next_job;
+      if (next_job < total) next_job = atomicAdd(ctrl + DC_JOB, 1);
+    }
     __syncthreads();
     const int job = *job_slot;
     __syncthreads();
@@ -380,13 +388,7 @@ __device__ __forceinline__ void dense_helper_role(const ResCall& call, const Den
     const int y0 = t * (128 / W);
     if (warp < HNS) {
       if (lane == 0) {
-        if (da.nhwc) {   // the rows (with halo) this tile reads
-          const int ylo = max(0, y0 - 1), yhi = min(H - 1, y0 + 128 / W);
-          for (int y = ylo; y <= yhi; ++y) wait_flag_ge(ctrl + DC_ROW + b * H + y, hpr);
-          fence_proxy_async_all();
-        }
-        if (hd && warp == 0) hd[2] = clock64();
-        fence_proxy_async();   // the layout tile (generic writes) aliases stage 0
+        fence_proxy_async();   // the layout tile / the previous job's staging (generic writes) alias the stages
         for (int c = warp; c < HKC; c += HNS) {
           const uint32_t gi = g + c;
           const int s = (int)(gi % HNS);
@@ -395,8 +397,14 @@ __device__ __forceinline__ void dense_helper_role(const ResCall& call, const Den
           const int tap = c >> 2, dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
           const uint32_t st_addr = sm_addr + s * HSTAGE;
           mbar_arrive_expect_tx(full(s), HSTAGE);
+          tma_load_2d(st_addr + 16384, &da.wmap[l], full(s), c * 64, 0);   // weights first: they need no layout
+          if (c == warp && da.nhwc) {   // the rows (with halo) this tile reads
+            const int ylo = max(0, y0 - 1), yhi = min(H - 1, y0 + 128 / W);
+            for (int y = ylo; y <= yhi; ++y) wait_flag_ge(ctrl + DC_ROW + b * H + y, hpr);
+            fence_proxy_async_all();
+            if (hd && warp == 0) hd[2] = clock64();
+          }
           tma_load_4d(st_addr, &da.amap, full(s), (c & 3) * 64, dx, y0 + dy, b);
-          tma_load_2d(st_addr + 16384, &da.wmap[l], full(s), c * 64, 0);
         }
       }
     } else if (warp < HNS + 2) {
@@ -420,21 +428,28 @@ __device__ __forceinline__ void dense_helper_role(const ResCall& call, const Den
         if (hd && j == 0) hd[4] = clock64();
       }
     } else if (warp >= 8) {
-      const int et = tid - 256, q = warp - 8;
+      const int et = tid - 256;
       bias_s[et] = __ldg(da.bias[l] + et);
       bias_s[et + 128] = __ldg(da.bias[l] + et + 128);
-      named_bar_sync(2, 128);
-      mbar_wait(accf, acc_par);
-      tc_fence_after();
-      if (hd && et == 0) hd[5] = clock64();
-      const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
-      // pixel row m = q*32 + lane: bf16 line staged in shared memory (pitch 528 B: conflict-free 16-byte
-      // writes at a 512-byte lane stride), then written out as whole 512-byte lines per warp instruction
-      // (the pipeline stages are idle: every MMA of the job has completed)
+    }
+    __syncwarp();
+    __syncthreads();   // the bias is staged; producers and issuers have issued everything
+    mbar_wait(accf, acc_par);
+    tc_fence_after();
+    if (hd && tid == 0) hd[5] = clock64();
+    {
+      // Epilogue on all twelve warps: warp w reads TMEM lane quarter w % 4 (pixel rows 32 (w % 4) + lane),
+      // column blocks {0,1,2} / {3,4,5} / {6,7} by w / 4: sum of the two issuers' accumulators + bias, ReLU,
+      // bf16 into a shared-memory line (pitch 528 B: conflict-free 16-byte writes at a 512-byte lane
+      // stride; the pipeline stages are idle, every MMA of the job has completed), then whole 512-byte
+      // pixel lines per warp instruction to V
       constexpr int EPITCH = 528;
-      uint8_t* stg = sm + (size_t)(q * 32) * EPITCH;
+      const int q = warp & 3, wg = warp >> 2;
+      const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
+      uint8_t* stg = sm + (size_t)(q * 32 + lane) * EPITCH;
+      const int cb0 = wg * 3, cb1 = min(8, cb0 + 3);
 #pragma unroll 1
-      for (int cb = 0; cb < 8; ++cb) {
+      for (int cb = cb0; cb < cb1; ++cb) {
         uint32_t u0[32], u1[32];
         tmem_ld32(tl + cb * 32, u0);
         tmem_ld32(tl + 256 + cb * 32, u1);
@@ -449,22 +464,25 @@ __device__ __forceinline__ void dense_helper_role(const ResCall& call, const Den
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          *reinterpret_cast<uint4*>(stg + (size_t)lane * EPITCH + cb * 64 + i * 16) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+          *reinterpret_cast<uint4*>(stg + cb * 64 + i * 16) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
       }
-      __syncwarp();
-      uint4* vout = reinterpret_cast<uint4*>(da.V + (((size_t)b * L + l) * HW + (size_t)t * 128 + q * 32) * D);
-#pragma unroll 4
-      for (int m = 0; m < 32; ++m)
-        vout[(size_t)m * 32 + lane] = *reinterpret_cast<const uint4*>(stg + (size_t)m * EPITCH + lane * 16);
-      __threadfence();
       tc_fence_before();
-      named_bar_sync(2, 128);
-      if (et == 0) atomicAdd(ctrl + DC_VDONE + b * L + l, 1);
-      if (hd && et == 0) {
-        hd[6] = clock64();
-        unsigned long long gt;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-        hd[10] = (long long)gt;
+      __syncthreads();
+      if (hd && tid == 0) hd[7] = clock64();
+      uint4* vout = reinterpret_cast<uint4*>(da.V + (((size_t)b * L + l) * HW + (size_t)t * 128) * D);
+      for (int m = warp; m < 128; m += NT / 32)
+        vout[(size_t)m * 32 + lane] = *reinterpret_cast<const uint4*>(sm + (size_t)m * EPITCH + lane * 16);
+      if (hd && tid == 0) hd[8] = clock64();
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) {
+        atomicAdd(ctrl + DC_VDONE + b * L + l, 1);
+        if (hd) {
+          hd[6] = clock64();
+          unsigned long long gt;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+          hd[10] = (long long)gt;
+        }
       }
     }
     g += HKC;
@@ -528,6 +546,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call_in,
   const uint32_t cl_bar = conv_acc + 32;
   const uint32_t xbar0 = conv_acc + 40;   // two exchange barriers (stage parity): bytes pushed by my group land here
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(fix + F_BAR + (2 * NSLOT + 2 * CNS + 8) * 8);
+  const uint32_t gbar = bar + 168;        // dense mode: exchange of the sampled-feature k-chunks inside an anchor group
   const uint32_t hbar = bar + 176;        // helper role (dense mode): 9 barriers, then its job slot at F_BAR + 248
   static_assert((2 * NSLOT + 2 * CNS + 8) * 8 + 4 <= 176 && 176 + (2 * HNS + 1) * 8 <= 248, "barrier area layout");
 
@@ -546,6 +565,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call_in,
     mbar_init(cl_bar, RES_CL);
     mbar_init(xbar0, 1);
     mbar_init(xbar0 + 8, 1);
+    mbar_init(gbar, 1);
     for (int i = 0; i < 2 * HNS; ++i) mbar_init(hbar + i * 8, 1);   // helper role: stage full / empty
     mbar_init(hbar + 2 * HNS * 8, 2);                               // helper role: both issuers' accumulators
     fence_barrier_init();
@@ -650,7 +670,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call_in,
     uint32_t peer[GF];          // shared::cluster base address of the CTAs of my anchor group
 #pragma unroll
     for (int j = 0; j < GF; ++j) peer[j] = mapa(sm_addr, (uint32_t)(ag * GF + j));
-    uint32_t acc_par = 0, cl_par = 0, conv_par = 0;
+    uint32_t acc_par = 0, cl_par = 0, conv_par = 0, gpar = 0;
     int cg = 0, dbg_i = 0, k = 0;   // k: linear stage counter (B operand / row buffer parity)
     if (tid == 0) need_s[1] = 0ull;   // BEV rows already converted (kept in shared memory: a spilled copy costs ~5 k cycles per reload)
     const __nv_bfloat16* bevn =
@@ -996,37 +1016,73 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call_in,
           if (si == 0) wait_flag_ge(da.ctrl + DC_VDONE + scene * L + l, HW / 128);
           bsync();
           mark(120);
-          float* part = reinterpret_cast<float*>(xr + X_SP);   // [half][NAG][256], summed by the bev_out stage
-          for (int item = warp; item < 2 * n_own; item += 8) {
-            const int n = item >> 1, hf = item & 1;
-            const EntPair* ea = ent + (n * P + hf * 4) * 4;
-            uint4 v[16];
-            float wq[16];
+          // CTA (ag, fg) reads channels [64 fg, +64) of every corner line of its group's anchors: 8 lanes
+          // per line (16 B each), four lines per warp instruction, warp w takes lines 4w..4w+3 of each
+          // anchor -> one load per anchor and lane, all in flight together
+          // Rolled, register-light loops on purpose (the chain code around it is register-bound and a shuffle
+          // reduction here serialised into a 3.5 k-cycle chain): the CTA's 128-byte slices of the corner lines
+          // go to shared memory with cp.async, 16 B per lane, a warp instruction fetching lines 4w..4w+3 of
+          // one anchor; then lane = channel pair sums its warp's four lines straight from shared memory.
+          float* gp = reinterpret_cast<float*>(xr + X_ACT);      // [8 warps][NROW][64] partial sums (row buffers idle)
+          {
+            const uint32_t wstage = pipe_addr + P_ACT2 + (uint32_t)(warp * 512);   // + j * 4096: [4 lines][128 B]
+            const EntPair* em = ent + warp * 4;
+            const __nv_bfloat16* vsrc = Vl + fg * 64 + (lane & 7) * 8;
+#pragma unroll 1
+            for (int j = 0; j < n_own; ++j)
+              cp_async16(wstage + j * 4096 + lane * 16, vsrc + (size_t)em[j * 32 + (lane >> 3)].slot * D, 16u);
+            cp_async_commit();
+            mark(124);
+            cp_async_wait_all();
+            __syncwarp();
+            mark(125);
+            float2* pd = reinterpret_cast<float2*>(gp + (size_t)(warp * NROW) * 64) + lane;
+            const uint8_t* wst = pipe + P_ACT2 + warp * 512 + lane * 4;
+#pragma unroll 1
+            for (int j = 0; j < n_own; ++j) {
+              float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const EntPair ep = ea[e];
-              wq[e] = ep.w;
-              v[e] = __ldcg(reinterpret_cast<const uint4*>(Vl + (size_t)ep.slot * D + lane * 8));
-            }
-            float acc[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const uint32_t uu[4] = {v[e].x, v[e].y, v[e].z, v[e].w};
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const __nv_bfloat162 pr = *reinterpret_cast<const __nv_bfloat162*>(&uu[i]);
-                acc[2 * i] = fmaf(wq[e], __low2float(pr), acc[2 * i]);
-                acc[2 * i + 1] = fmaf(wq[e], __high2float(pr), acc[2 * i + 1]);
+              for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat162 pr = *reinterpret_cast<const __nv_bfloat162*>(wst + j * 4096 + e * 128);
+                const float we = em[j * 32 + e].w;
+                s0 = fmaf(we, __low2float(pr), s0);
+                s1 = fmaf(we, __high2float(pr), s1);
               }
+              pd[j * 32] = make_float2(s0, s1);
             }
-            float* pd = part + (size_t)(hf * NAG + n) * D + lane * 8;
-            *reinterpret_cast<float4*>(pd) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-            *reinterpret_cast<float4*>(pd + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+          }
+          mark(126);
+          bsync();
+          mark(122);
+          // the eight warps' partials in a fixed order -> bf16 -> my k-chunk of the group's B operand,
+          // which the bulk-copy engine pushes into the three peers (their chunks land in mine)
+          {
+            uint8_t* bop = bop_ptr(k);
+            for (int i = tid; i < n_own * 32; i += NCT) {
+              const int j = i >> 5, c2 = (i & 31) * 2;
+              float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+              for (int w8 = 0; w8 < 8; ++w8) {
+                const float2 t2 = *reinterpret_cast<const float2*>(gp + (size_t)(w8 * NROW + j) * 64 + c2);
+                s0 += t2.x;
+                s1 += t2.y;
+              }
+              *reinterpret_cast<__nv_bfloat162*>(bop + sw_off(j, fg * 64 + c2, BCH)) = __floats2bfloat162_rn(s0, s1);
+            }
+            fence_proxy_async();
+            bsync();
+            mark(123);
+            if (tid == 0) {
+              const uint32_t off = off_x + X_BOP + (uint32_t)(k & 1) * 16384u + (uint32_t)fg * BCH;
+              mbar_arrive_expect_tx(gbar, (GF - 1) * BCH);
+#pragma unroll
+              for (int j = 0; j < GF; ++j)
+                if (j != fg) bulk_copy_to_peer(peer[j] + off, sm_addr + off, BCH, peer[j] + (gbar - sm_addr));
+            }
+            mbar_wait(gbar, gpar);
+            gpar ^= 1u;
           }
           mark(121);
-          bsync();
         } else {
           unsigned long long todo;
           {
@@ -1292,20 +1348,22 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call_in,
         mark(22);
         // ============ output_proj + residual (blocks.py:127-129): x1 = S.Wo + b + q0
         {
-          const int ntile = call.dense ? 2 : min(4, (nu + CROWS - 1) / CROWS);   // tiles of the first pass hold everything a tile CTA accumulated
-          float sv[8];
-          if (warp < n_own) {
-            const float* sp = reinterpret_cast<const float*>(xr + X_SP) + warp * D;
-            load8(sp, lane, sv);
-            for (int t = 1; t < ntile; ++t) {
-              float u[8];
-              load8(sp + (size_t)t * NAG * D, lane, u);
+          const int ntile = min(4, (nu + CROWS - 1) / CROWS);   // tiles of the first pass hold everything a tile CTA accumulated
+          if (!call.dense) {   // (dense mode: the gather wrote and exchanged the operand already)
+            float sv[8];
+            if (warp < n_own) {
+              const float* sp = reinterpret_cast<const float*>(xr + X_SP) + warp * D;
+              load8(sp, lane, sv);
+              for (int t = 1; t < ntile; ++t) {
+                float u[8];
+                load8(sp + (size_t)t * NAG * D, lane, u);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) sv[i] += u[i];
+                for (int i = 0; i < 8; ++i) sv[i] += u[i];
+              }
             }
+            bsync();   // the partials live where the B operand goes
+            if (warp < n_own) bt_store8(bop_ptr(k), warp, lane, sv);
           }
-          bsync();   // the partials live where the B operand goes
-          if (warp < n_own) bt_store8(bop_ptr(k), warp, lane, sv);
           b_done(1);
           const int f = fg * 64 + quad * 16 + lane;
           const float bias = (warp < 4 && lane < 16) ? __ldg(LC.b_bev_out + f) : 0.f;
@@ -1682,13 +1740,16 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call_in,
     }
     // dense mode: the last scene cluster to finish waits until every helper CTA has left its job
     // loop and clears the control words for the next launch
-    if (call.dense && rank == 0 && tid == 0) {
+    if (call.dense && rank == 0) {
       int* ctrl = da.ctrl;
-      if (atomicAdd(ctrl + DC_CHAINS, 1) == da.B - 1) {
-        wait_flag_ge(ctrl + DC_EXIT, da.n_helper_ctas);
-        for (int i = 0; i < DC_WORDS; ++i) ctrl[i] = 0;
-        __threadfence();
+      if (tid == 0) {
+        const bool last = atomicAdd(ctrl + DC_CHAINS, 1) == da.B - 1;
+        if (last) wait_flag_ge(ctrl + DC_EXIT, da.n_helper_ctas);
+        ints_s[0] = last ? 1 : 0;
       }
+      bsync();
+      if (ints_s[0])
+        for (int i = tid; i < DC_WORDS; i += NCT) ctrl[i] = 0;
     }
     mark(99);
   }

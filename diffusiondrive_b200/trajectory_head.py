@@ -22,6 +22,8 @@ from __future__ import annotations
 import copy
 import contextlib
 import ctypes as C
+import importlib.util
+import os
 from typing import Dict, Optional
 
 import numpy as np
@@ -30,6 +32,26 @@ import torch.nn as nn
 
 from . import _lib
 from .config import HeadConfig, NUM_TRAIN_TIMESTEPS
+
+
+_BINDING = [False, None]   # [looked for, module]
+
+
+def _torch_binding():
+    """Optional C++ binding above the C ABI (csrc/torch_binding.cpp, built by build.py): output
+    allocation, stream lookup and the ddh_forward call in one C++ function.  Absent: the ctypes path."""
+    if not _BINDING[0]:
+        _BINDING[0] = True
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_torch_build", "_ddh_torch.so")
+        if os.path.exists(path) and not os.environ.get("DDH_NO_TORCH_BINDING"):
+            try:
+                spec = importlib.util.spec_from_file_location("_ddh_torch", path)
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+                _BINDING[1] = mod
+            except Exception:     # built against another torch: keep the ctypes path
+                _BINDING[1] = None
+    return _BINDING[1]
 
 
 # ------------------------------------------------------------------ parameter holders
@@ -159,6 +181,7 @@ class TrajectoryHead(nn.Module):
         self._twin = []         # [fp32 twin head, signature]; a list keeps it out of the module tree
         self.last_rescored = 0
         self.frozen = False     # True: skip the per-call "did the weights change" check
+        self._fast = None       # (binding function, argument tail) of the C++ call path, see forward
         self._call_key = None   # signature of the last validated call (forward_test)
         self._call_info = None
         self._out_sizes: Dict[int, tuple] = {}
@@ -167,9 +190,11 @@ class TrajectoryHead(nn.Module):
     # -------------------------------------------------------------- ABI plumbing
     def _invalidate(self):
         self._packed_sig = None
+        self._fast = None
 
     def _apply(self, fn, *args, **kwargs):   # .to() / .cuda(): the cached call validation names a device
         self._call_key = None
+        self._fast = None
         return super()._apply(fn, *args, **kwargs)
 
     def __del__(self):
@@ -185,6 +210,7 @@ class TrajectoryHead(nn.Module):
         if self._handle is not None and key == self._handle_key:
             return
         lib = self._lib = _lib.load()
+        self._fast = None
         if self._handle is not None:
             lib.ddh_destroy(self._handle)
             self._handle = None
@@ -291,6 +317,15 @@ class TrajectoryHead(nn.Module):
         :593; when omitted it is drawn the same way.  ``bev_layout="NHWC"`` accepts the map as
         (B,H,W,C), the layout the producer holds one line before the permute (:136-140).
         """
+        fast = self._fast
+        if fast is not None and self.frozen and not self.training and self.rescore_margin is None:
+            # frozen weights, device tensors, handle and packing in place: one C++ call (torch_binding.cpp)
+            out = fast[0](fast[1], fast[2], ego_query, agents_query, bev_feature, noise,
+                          1 if bev_layout == "NHWC" else 0, *fast[3])
+            if out.__class__ is dict:
+                return out
+            if out is not None:
+                _lib.check(self._lib, self._handle, out, "ddh_forward")
         if self.training:
             # forward_train (:520-576) needs autograd: plain PyTorch on the module's device, NOT the
             # accelerated path (train_torch.py); inference below never takes this branch
@@ -397,6 +432,12 @@ class TrajectoryHead(nn.Module):
         out = {"trajectory": traj, "trajectory_modes": modes, "trajectory_scores": scores,
                "mode_idx": idx}
         self.last_rescored = 0
+        if self._fast is None and not host_call and self.frozen:
+            mod = _torch_binding()
+            if mod is not None:
+                self._fast = (mod.forward_fast, C.cast(lib.ddh_forward, C.c_void_p).value, h.value,
+                              (self.plan_anchor.shape[0], self._num_poses, Na, Cc, H, W,
+                               dev_index if dev_index is not None else torch.cuda.current_device()))
         if self.rescore_margin is not None and self.precision == "bf16" and self.plan_anchor.shape[0] > 1 \
                 and not host_call:
             with torch.no_grad():

@@ -126,9 +126,9 @@ def run_time():
             print(line, flush=True)
             if taps and dense:
                 hd = head.debug_tap("dbg", np.int64)[920:940]
-                rel = [int(x - hd[0]) if x > 0 else None for x in hd[:7]]
+                rel = [int(x - hd[0]) if x > 0 else None for x in hd[:9]]
                 print("  helper CTA of conv job 0 (cycles since role entry): claimed %s, rows ready %s, first stage full %s, "
-                      "MMAs issued %s, accumulators ready %s, epilogue done %s" % tuple(rel[1:7]))
+                      "MMAs issued %s, accumulators ready %s, epilogue done %s (staged %s, lines written %s)" % tuple(rel[1:9]))
                 print(f"  globaltimer: helper job-0 done {int(hd[10] - hd[11])} ns after the scene cluster's start; "
                       f"scene cluster at its first gather after {int(hd[12] - hd[11])} ns", flush=True)
             if taps:
