@@ -430,9 +430,34 @@ def run_ours(args):
         lat = {"p50_us": dts[len(dts) // 2], "p90_us": dts[int(len(dts) * 0.9)],
                "wall_p50_us": sorted(wall)[len(wall) // 2], "iters": len(dts),
                "precision": precision, "launches": head.last_launch_count(),
-               "engine": ("group-resident engine (kernels_res2.cu): the whole forward is one launch on a "
-                          "16-CTA cluster" if head.last_launch_count() == 1
-                          else "small-batch engine (kernels_lat.cu), stream launches")}
+               "engine": ("group-resident engine (kernels_res2.cu), dense mode: ONE launch = one 16-CTA scene cluster "
+                          "+ 8 helper clusters that run value_proj over the whole 64x64 map on tcgen05 (TMA implicit "
+                          "GEMM) under the embedding/encoder; the scene cluster gathers bilinear corners"
+                          if head.last_launch_count() == 1 else "stream launches"),
+               "call_path": "TrajectoryHead.forward -> C++ binding (torch_binding.cpp) -> ddh_forward"
+                            if getattr(head, "_fast", None) is not None else "TrajectoryHead.forward -> ctypes -> ddh_forward",
+               "target_us": 150.0}
+        try:   # the same measurement with the on-demand conv (dense_conv = 0), for the record
+            head.set_option("dense_conv", 0)
+            head.frozen = True
+            for _ in range(10):
+                head(*one, noise=n1)
+            torch.cuda.synchronize()
+            od = []
+            for a, b in e1s[:100]:
+                a.record()
+                head(*one, noise=n1)
+                b.record()
+                b.synchronize()
+                od.append(a.elapsed_time(b) * 1e3)
+            od.sort()
+            lat["ondemand_conv_p50_us"] = od[len(od) // 2]
+        finally:
+            head.set_option("dense_conv", 1)
+            head.frozen = True
+            for _ in range(5):
+                head(*one, noise=n1)
+            torch.cuda.synchronize()
         # the same call captured once into a CUDA graph and replayed (no host launch gaps)
         try:
             side = torch.cuda.Stream(device=dev)
