@@ -179,6 +179,7 @@ struct GemmParams {
   int n_anchor = 0;
   int ent_per_anchor = 0;          // P * 4
   long long* dbg = nullptr;        // optional timeline (DDH_TIMELINE builds): CTA 0 clock64 stamps
+  int* sched = nullptr;            // tc_conv3_kernel: global scene counter (zeroed before the launch) or null = static deal
 };
 
 }  // namespace ddh

@@ -141,6 +141,8 @@ struct ddh_handle {
   std::vector<std::pair<int, int>> ev_spans;   // (stage id, index of the begin event)
   int ev_used = 0;
   int* conv_rows = nullptr;                    // [S*L] unique value_proj rows per conv launch
+  int* conv_sched = nullptr;                   // scene counter of the persistent conv's dynamic scene queue
+  int conv_dynamic = 1;                        // option "conv_dynamic": 1 scenes are dealt to the conv CTAs on demand, 0 round-robin
   unsigned int* need_seg = nullptr;            // [B][seg_nw32] BEV segments (+halo) the coming conv call reads
   unsigned int* done_seg = nullptr;            // [B][seg_nw32] BEV segments already converted to NHWC
   int lazy_layout = 1;                         // convert BEV segments on demand (NCHW input)
@@ -390,6 +392,7 @@ int ensure_ws(ddh_handle* h, int B) {
   WS(h->upix, (size_t)B * h->rcap);
   WS(h->nuniq, B);
   WS(h->conv_rows, s.num_layers * s.num_steps);
+  WS(h->conv_sched, 4);
   WS(h->need_seg, (size_t)B * 64);
   WS(h->done_seg, (size_t)B * 64);
   WS(h->dbg, 1024);
@@ -1100,6 +1103,10 @@ int forward_fused(ddh_handle* h, const float* ego, const float* agents, const vo
       gp.dbg = (h->conv_timeline == si * L + l) ? h->dbg + 256 : nullptr;
       gp.ent_slot = h->ent_slot; gp.ent_w = h->ent_w; gp.n_anchor = A; gp.ent_per_anchor = P * 4;
       gp.epi.out_f32 = h->s32; gp.epi.ldo32 = D; gp.epi.out_bf16 = h->s16; gp.epi.ldo16 = D;
+      if (conv_mode == 2 && h->conv_dynamic) {
+        CU_TRY(h, cudaMemsetAsync(h->conv_sched, 0, 4, st));
+        gp.sched = h->conv_sched;
+      }
       launch_tc_conv(gp, pl.conv.map, B, st, conv_mode);
       h->launches++; }
       { ProfSpan ps(h, ST_GEMM, st);
@@ -1758,6 +1765,7 @@ int ddh_set_option(ddh_handle* h, const char* name, int value) {
   else if (n == "chain_timeline") h->chain_timeline = value;
   else if (n == "persistent_conv") h->persistent_conv = value;
   else if (n == "conv_timeline") h->conv_timeline = value;
+  else if (n == "conv_dynamic") h->conv_dynamic = value;
   else if (n == "host_zero_copy") h->host_zero_copy = value;
   else if (n == "host_segment") {
     if (value != 16 && value != 32 && value != 64) return fail(h, DDH_ERR_BAD_ARG, "ddh_set_option: host_segment must be 16, 32 or 64");

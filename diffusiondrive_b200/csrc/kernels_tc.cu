@@ -1127,6 +1127,22 @@ tc_conv3_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap, in
   auto empty = [&](int s) { return bar0 + (NS + s) * 8; };
   const uint32_t accum = bar0 + 2 * NS * 8, vt_ready = accum + 8, comb_done = accum + 16, passgo = accum + 24;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + C_PIPE + D * 4 + (2 * NS + 4) * 8);
+  // Scene queue.  The k-th scene of this CTA is blockIdx.x for k = 0 and comes from a global counter
+  // after that (p.sched; static round-robin when it is null): scenes differ in unique pixels and
+  // passes, and with ~28 scenes per CTA a static deal left the SMs idle for ~12 % of the launch
+  // waiting for the slowest one.  MMA issuer 0 requests scene k + 2 when it starts scene k and
+  // publishes it (slot (k + 1) & 3, one mbarrier phase per use) after the scene's last MMA, so the
+  // atomic's round trip hides under the main loop; every role reads the queue in order.  A slot is
+  // reused four scenes later: by then every role has read it (no role is more than one scene away
+  // from the issuer: producers wait for the epilogue's passgo, the epilogue for the issuer's commits).
+  static_assert((2 * NS + 4) * 8 + 4 <= 96 && 144 <= TC_BAR_BYTES, "barrier area layout");
+  const uint32_t qf0 = bar0 + 96;
+  volatile int* sq = reinterpret_cast<volatile int*>(sm + C_PIPE + D * 4 + 128);
+  auto scene_at = [&](int kk) -> int {
+    if (kk == 0) return (int)blockIdx.x;
+    mbar_wait(qf0 + ((kk - 1) & 3) * 8, (uint32_t)((kk - 1) >> 2) & 1u);
+    return sq[(kk - 1) & 3];
+  };
   constexpr int KC = 9 * (D / TC_BK);
   constexpr int RPT = NT * 8;
 
@@ -1138,6 +1154,7 @@ tc_conv3_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap, in
     mbar_init(vt_ready, C2_EPI);
     mbar_init(comb_done, 1);
     mbar_init(passgo, C2_EPI);
+    for (int i = 0; i < 4; ++i) mbar_init(qf0 + i * 8, 1);
     fence_barrier_init();
   }
   if (warp == 5) tmem_alloc<NT * D>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
@@ -1155,14 +1172,14 @@ tc_conv3_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap, in
     const int j = tid & 7, rb = tid >> 3;
     const uint32_t dst_base = rb * 128 + ((j ^ (rb & 7)) << 4);
     int g = 0, pi = 0, sidx = 0;
-    int scene = blockIdx.x;
+    int scene = scene_at(0);
     int nu = scene < B ? __ldg(p.nuniq + scene) : 0;
     int yx0[RPT];
 #pragma unroll
     for (int i = 0; i < RPT; ++i)
       yx0[i] = (scene < B && nu > 0) ? __ldg(p.upix + (size_t)scene * p.rcap + min(rb + 16 * i, nu - 1)) : 0;
     while (scene < B) {
-      const int scene_n = scene + gridDim.x;
+      const int scene_n = scene_at(sidx + 1);
       const int nu_n = scene_n < B ? __ldg(p.nuniq + scene_n) : 0;
       int yxn[RPT];
 #pragma unroll
@@ -1226,8 +1243,8 @@ tc_conv3_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap, in
   } else if (warp == 4) {
     // ======================= TMA producer (weights: A operand) =========================
     if (lane == 0) {
-      int g = 0, pi = 0;
-      for (int scene = blockIdx.x; scene < B; scene += gridDim.x) {
+      int g = 0, pi = 0, sk = 0;
+      for (int scene = scene_at(0); scene < B; scene = scene_at(++sk)) {
         const int nu = __ldg(p.nuniq + scene);
         const int passes = c3_split(nu).passes;
         for (int pass = 0; pass < passes; ++pass, ++pi) {
@@ -1246,13 +1263,27 @@ tc_conv3_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap, in
     // ======================= MMA issuers: warp 5 channel tile 0 (+ the combine), warp 14 tile 1 ==
     if (lane == 0) {
       const int mt = warp == 5 ? 0 : 1;
-      const uint32_t idesc256 = umma_idesc_bf16_m128_n256();
+      // combine: M = 64 (<= 64 anchor rows; an M = 64 instruction holds the tensor pipe half as long as
+      // M = 128), N = 256 channels; accumulator row r lives in TMEM lane 32 (r / 16) + r % 16
+      const uint32_t idesc256 = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((64u >> 4) << 24);
       int g = 0, sidx = 0;
       uint32_t pi = 0;
-      for (int scene = blockIdx.x; scene < B; scene += gridDim.x, ++sidx) {
+      // issuer 0 runs the scene queue: `req` = the scene requested at the start of the current one
+      auto request = [&](int kk) -> int {   // kk-th scene of this CTA, kk >= 1
+        const int sc = p.sched ? (int)gridDim.x + atomicAdd(p.sched, 1) : (int)blockIdx.x + kk * (int)gridDim.x;
+        return sc < B ? sc : B;
+      };
+      auto publish = [&](int kk, int sc) {
+        sq[(kk - 1) & 3] = sc;
+        mbar_arrive(qf0 + ((kk - 1) & 3) * 8);
+      };
+      if (mt == 0) publish(1, request(1));
+      for (int scene = scene_at(0); scene < B; scene = scene_at(++sidx)) {
+        const int req = mt == 0 ? request(sidx + 2) : 0;
         const int nu = __ldg(p.nuniq + scene);
         const C3Split sp = c3_split(nu);
         const int passes = sp.passes;
+        if (mt == 0 && passes == 0) publish(sidx + 2, req);
         // D = f32, A = B = bf16, K-major, M = 128, N = rows of a pass
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)sp.rpp >> 3) << 17) | ((128u >> 4) << 24);
         for (int pass = 0; pass < passes; ++pass, ++pi) {
@@ -1271,6 +1302,7 @@ tc_conv3_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap, in
           }
           umma_commit(accum);
           C2_STAMP(mt == 0 && sidx == 1 && pass == 0, 25);
+          if (mt == 0 && pass == 0) publish(sidx + 2, req);
           if (mt == 0) {
             // ---- combine: S^(pass)[a, c] = Wc[a, r] . V^T[c, r], K = the pass's pixel rows
             mbar_wait(vt_ready, pi & 1u);
@@ -1299,7 +1331,7 @@ tc_conv3_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap, in
     const float bias_c = bias_s[c];
     uint32_t pi = 0;
     int sidx = 0;
-    for (int scene = blockIdx.x; scene < B; scene += gridDim.x, ++sidx) {
+    for (int scene = scene_at(0); scene < B; scene = scene_at(++sidx)) {
       const int nu = __ldg(p.nuniq + scene);
       if (nu == 0) {   // every sample point fell outside the grid: grid_sample returns zeros
         for (int i = etid; i < A * D; i += C2_EPI) {
@@ -1385,12 +1417,12 @@ tc_conv3_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap, in
         fence_proxy_async();
         tc_fence_before();
         mbar_arrive(vt_ready);
-        // ---- S rows of this pass: anchor a = 32 q + lane, columns 128 mt .. + 127
+        // ---- S rows of this pass: anchor a = 16 q + lane (lanes 0-15 of quarter q), columns 128 mt .. + 127
         mbar_wait(comb_done, pi & 1u);
         tc_fence_after();
         C2_STAMP(sidx == 1 && pass == 0 && etid == 0, 35);
-        const int a = q * 32 + lane;
-        if (q * 32 < A) {
+        const int a = lane < 16 ? q * 16 + lane : A;   // (M = 64 accumulator layout)
+        if (q * 16 < A) {
 #pragma unroll 1
           for (int b = 0; b < 4; ++b) {
             uint32_t u32[32];

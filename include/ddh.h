@@ -271,6 +271,8 @@ DDH_API int ddh_set_concurrency(ddh_handle *h, int chunks, int min_chunk_scenes)
  *   "persistent_conv"    2  value_proj conv as one persistent CTA per SM: 2 = bilinear x attention combine
  *                           on the tensor core (tc_conv3_kernel), 1 = CUDA-core combine
  *                           (tc_conv2_kernel); 0: one CTA per scene (tc_conv_kernel)
+ *   "conv_dynamic"       1  tc_conv3_kernel deals scenes to its persistent CTAs on demand (global counter) instead
+ *                           of round-robin: removes the end-of-launch tail of unequal scenes
  *   "chain_timeline"    -1  index (step * layers + layer) of the chain launch that stamps clock64
  *                           into the "dbg" tap (CTA 0, second tile)
  *   "debug_taps"         0  keep fp32 copies of intermediate activations for ddh_debug_copy
