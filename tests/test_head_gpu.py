@@ -426,6 +426,18 @@ def test_execution_options_do_not_change_results():
         for k in a:
             assert torch.equal(a[k], b[k]), (precision, "lazy-vs-eager", k)
             assert torch.equal(a[k], c[k]), (precision, "segment-16-vs-eager", k)
+    # the persistent conv deals scenes to its CTAs on demand (global counter): which CTA runs a scene
+    # does not change its result; 600 scenes = four per CTA, ragged
+    Bq = 600
+    ftq = synth.make_features(Bq)
+    nzq = synth.make_noise(Bq).cuda()
+    argq = (ftq["ego_query"].cuda(), ftq["agents_query"].cuda(), ftq["bev_feature"].cuda())
+    dyn, _ = _make_head("bf16")
+    a = {k: v.clone() for k, v in dyn(*argq, noise=nzq).items()}
+    dyn.set_option("conv_dynamic", 0)
+    b = dyn(*argq, noise=nzq)
+    for k in a:
+        assert torch.equal(a[k], b[k]), ("conv_dynamic", k)
 
 
 def test_scene_independence_and_determinism_full_size():
