@@ -544,9 +544,24 @@ def run_ours(args):
             h32 = h32.to(dev).eval()
             t256 = (ego[:256], agents[:256], bev[:256])
             ms, o = timed(h32, t256, noise[:256], 3)
+            # roofline of the fp32 engine (CUDA-core FMA): executed FLOPs (same exact dedup as the bf16
+            # engine: unique rows x 2*2304*256 per conv call + 0.195 GFLOP of decoder chain per scene)
+            # against 148 SMs x 128 FMA/clk x 2 at the maximum SM clock
+            rows32 = None
+            try:
+                rows32 = float(h32.debug_tap("conv_rows", np.int32).sum())
+            except Exception:
+                pass
+            fl32 = (rows32 * 2 * 2304 * 256 + 256 * 0.195e9) if rows32 else None
+            peak32 = 148 * 128 * 2 * 1.965e9 / 1e12
             extra_cfg["fp32_b256"] = {"config": "BASELINE configs[1]: fp32 engine, 256 scenes, 1 GPU",
                                       "ms_per_step": ms, "value": 256 / (ms * 1e-3), "unit": UNIT,
-                                      "parity": dict(par(o, z256, 256), tolerance_m=1e-4)}
+                                      "parity": dict(par(o, z256, 256), tolerance_m=1e-4),
+                                      "roofline": {"bound": "fp32 FMA (CUDA cores)", "unit": "TFLOP/s",
+                                                   "achieved": fl32 / (ms * 1e-3) / 1e12 if fl32 else None,
+                                                   "peak": peak32,
+                                                   "frac": fl32 / (ms * 1e-3) / 1e12 / peak32 if fl32 else None,
+                                                   "peak_source": "148 SMs x 128 FMA/clk x 2 x 1.965 GHz (nominal)"}}
             del h32
             zs = np.load(os.path.join(ROOT, "tests", "golden", "stress_b2.npz"))
             sds = synth.make_state_dict(num_layers=4, num_anchors=64)

@@ -97,3 +97,18 @@ def test_forward_requires_pack_and_device(lib):
         assert rc == -4
         assert b"no CUDA device" in lib.ddh_last_error(h)
     lib.ddh_destroy(h)
+
+
+def test_torch_binding_is_built_and_declines_cpu_tensors():
+    """The optional C++ binding above the C ABI (csrc/torch_binding.cpp): built in-tree by build.py,
+    importable without a GPU, and it returns None (general Python path) for anything that is not a
+    plain CUDA call -- here CPU tensors -- instead of touching the C ABI."""
+    import torch
+    from diffusiondrive_b200 import build, trajectory_head
+    assert os.path.exists(build.build_torch_binding())
+    mod = trajectory_head._torch_binding()
+    assert mod is not None and hasattr(mod, "forward_fast")
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):   # no CUDA runtime to ask for the current device
+            mod.forward_fast(0, 0, torch.zeros(1, 1, 256), torch.zeros(1, 30, 256), torch.zeros(1, 256, 64, 64),
+                             None, 0, 20, 8, 30, 256, 64, 64, 0)
