@@ -117,7 +117,7 @@ constexpr int F_OWN = F_PTS + 2048;          // diffused sample of my outputs: f
 constexpr int F_MISC = F_OWN + 1024;         // conv bias slice [64] | ints [16]
 constexpr int F_FIN = F_MISC + 512;          // rank 0: scores [32] | modes [A*3P] (<= 768)
 constexpr int F_BAR = F_FIN + 3328;
-constexpr int F_END = F_BAR + 256;
+constexpr int F_END = F_BAR + 320;          // (256..263: anchor-group barrier of the dense mode)
 constexpr int SMEM_BYTES = RING + PIPE + XBYTES + F_END + 1024;
 static_assert(sizeof(R2Consts) <= F_Q0 - F_CONSTS, "R2Consts must fit its shared-memory slot");
 static_assert(sizeof(R2Consts) % 16 == 0, "R2Consts is copied as uint4");
@@ -546,6 +546,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call_in,
   const uint32_t cl_bar = conv_acc + 32;
   const uint32_t xbar0 = conv_acc + 40;   // two exchange barriers (stage parity): bytes pushed by my group land here
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(fix + F_BAR + (2 * NSLOT + 2 * CNS + 8) * 8);
+  const uint32_t grp_bar = bar + 256;     // dense mode: barrier of the four CTAs of an anchor group
   const uint32_t gbar = bar + 168;        // dense mode: exchange of the sampled-feature k-chunks inside an anchor group
   const uint32_t hbar = bar + 176;        // helper role (dense mode): 9 barriers, then its job slot at F_BAR + 248
   static_assert((2 * NSLOT + 2 * CNS + 8) * 8 + 4 <= 176 && 176 + (2 * HNS + 1) * 8 <= 248, "barrier area layout");
@@ -566,6 +567,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call_in,
     mbar_init(xbar0, 1);
     mbar_init(xbar0 + 8, 1);
     mbar_init(gbar, 1);
+    mbar_init(grp_bar, GF);
     for (int i = 0; i < 2 * HNS; ++i) mbar_init(hbar + i * 8, 1);   // helper role: stage full / empty
     mbar_init(hbar + 2 * HNS * 8, 2);                               // helper role: both issuers' accumulators
     fence_barrier_init();
@@ -697,6 +699,17 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call_in,
       if (tid < RES_CL) mbar_arrive_remote_release(mapa(cl_bar, (uint32_t)tid));
       mbar_wait_acq_cluster(cl_bar, cl_par);
       cl_par ^= 1u;
+      mark(105);
+    };
+    // dense mode: after the hoisted stage the anchor groups are independent (each samples V for its own
+    // anchors only), so the per-step / per-layer meetings shrink from the cluster to the group's four CTAs
+    uint32_t grp_par = 0;
+    auto gsync = [&]() {
+      mark(104);
+      bsync();
+      if (tid < GF) mbar_arrive_remote_release(mapa(grp_bar, (uint32_t)(ag * GF + tid)));
+      mbar_wait_acq_cluster(grp_bar, grp_par);
+      grp_par ^= 1u;
       mark(105);
     };
     // The B operand(s) of the next stage are written: make them visible to the tensor core, meet,
@@ -958,12 +971,17 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call_in,
             // lane p holds weight p: lanes 0..P-1 write it to CTAs 0..15
             if (lane < P) {
               const uint32_t dst = fix_addr + F_AW + (uint32_t)((l * AP + (a0 + warp) * P + lane) * 4);
-              for (int c = 0; c < RES_CL; ++c) st_cluster_f32(mapa(dst, (uint32_t)c), wgt);
+              if (call.dense) {   // only my group samples my anchors
+#pragma unroll
+                for (int c = 0; c < GF; ++c) st_cluster_f32(mapa(dst, (uint32_t)(ag * GF + c)), wgt);
+              } else {
+                for (int c = 0; c < RES_CL; ++c) st_cluster_f32(mapa(dst, (uint32_t)c), wgt);
+              }
             }
           }
         }
         ++k;
-        csync();
+        if (call.dense) gsync(); else csync();
       }
       mark(12);
 
@@ -1705,7 +1723,12 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call_in,
                 }
                 if (!want_cls) {   // every CTA's next plan (and the group's next embedding) needs them
                   const uint32_t dst = fix_addr + F_PTS + (uint32_t)(pi * 4);
-                  for (int cta = 0; cta < RES_CL; ++cta) st_cluster_f32(mapa(dst, (uint32_t)cta), nxt);
+                  if (call.dense) {   // only my group embeds / samples my anchors
+#pragma unroll
+                    for (int cta = 0; cta < GF; ++cta) st_cluster_f32(mapa(dst, (uint32_t)(ag * GF + cta)), nxt);
+                  } else {
+                    for (int cta = 0; cta < RES_CL; ++cta) st_cluster_f32(mapa(dst, (uint32_t)cta), nxt);
+                  }
                 }
               } else {
                 out = __fmul_rn(tanhf(mine), 3.14159265358979323846f);
@@ -1721,7 +1744,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call_in,
             }
           }
           ++k;
-          csync();
+          if (call.dense && !want_cls) gsync(); else csync();   // (the final scores / modes go to rank 0: cluster-wide)
         }
         mark(31);
       }
@@ -1743,7 +1766,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call_in,
     if (call.dense && rank == 0) {
       int* ctrl = da.ctrl;
       if (tid == 0) {
-        const bool last = atomicAdd(ctrl + DC_CHAINS, 1) == da.B - 1;
+        const bool last = da.B == 1 || atomicAdd(ctrl + DC_CHAINS, 1) == da.B - 1;
         if (last) wait_flag_ge(ctrl + DC_EXIT, da.n_helper_ctas);
         ints_s[0] = last ? 1 : 0;
       }

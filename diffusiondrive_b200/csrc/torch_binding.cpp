@@ -49,18 +49,35 @@ py::object forward_fast(std::uintptr_t fn, std::uintptr_t handle, const at::Tens
   }
   const int64_t n_t = B * P * 3, n_m = B * A * P * 3, n_s = B * A;
   const int64_t off_i = (n_t + n_m + n_s + 1) & ~int64_t(1);   // int64 mode_idx: 8-byte aligned tail
-  at::Tensor flat = at::empty({off_i + 2 * B}, ego.options());
-  float* base = flat.data_ptr<float>();
-  at::Tensor traj = flat.as_strided({B, P, 3}, {P * 3, 3, 1}, 0);
-  at::Tensor modes = flat.as_strided({B, A, P, 3}, {A * P * 3, P * 3, 3, 1}, n_t);
-  at::Tensor scores = flat.as_strided({B, A}, {A, 1}, n_t + n_m);
-  at::Tensor idx = flat.as_strided({2 * B}, {1}, off_i).view(at::kLong);
+  const int64_t total = off_i + 2 * B;
+  // Everything before the launch is on the latency path (the GPU idles until the kernel arrives), so
+  // the output block of THIS call was allocated right after the previous launch (one spare per
+  // thread, same size and device), and the views are made after the launch.  Every call still
+  // returns fresh tensors: a spare is handed out once.
+  static thread_local at::Tensor spare;
+  static thread_local cudaStream_t spare_stream = nullptr;   // (the caching allocator ties a block to its stream)
   cudaStream_t st = c10::cuda::getCurrentCUDAStream(dev).stream();
+  at::Tensor flat;
+  if (spare.defined() && spare.numel() == total && spare.get_device() == dev && spare_stream == st) {
+    flat = std::move(spare);
+    spare = at::Tensor();
+  } else {
+    flat = at::empty({total}, ego.options());
+  }
+  float* base = flat.data_ptr<float>();
   const int rc = reinterpret_cast<ForwardFn>(fn)(
       reinterpret_cast<void*>(handle), ego.data_ptr<float>(), agents.data_ptr<float>(), bev.data_ptr(),
       bt == at::kBFloat16 ? 1 : 0, bev_layout, noise.data_ptr<float>(), base, base + n_t, base + n_t + n_m,
       reinterpret_cast<int64_t*>(base + off_i), (int)B, reinterpret_cast<void*>(st));
   if (rc != 0) return py::int_(rc);
+  at::Tensor traj = flat.as_strided({B, P, 3}, {P * 3, 3, 1}, 0);
+  at::Tensor modes = flat.as_strided({B, A, P, 3}, {A * P * 3, P * 3, 3, 1}, n_t);
+  at::Tensor scores = flat.as_strided({B, A}, {A, 1}, n_t + n_m);
+  at::Tensor idx = flat.as_strided({2 * B}, {1}, off_i).view(at::kLong);
+  if (B <= 64) {   // for the next call (small batches only)
+    spare = at::empty({total}, ego.options());
+    spare_stream = st;
+  }
   py::dict out;
   out["trajectory"] = traj;
   out["trajectory_modes"] = modes;
