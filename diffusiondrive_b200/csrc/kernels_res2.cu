@@ -368,15 +368,18 @@ __device__ __forceinline__ void dense_helper_role(const ResCall& call, const Den
         __nv_bfloat16* dst = da.nhwc + (size_t)b * HW * D;
         uint32_t* tile_u32 = reinterpret_cast<uint32_t*>(sm);
         float4 v[8];
+        long long* hl = (hdbg && first && tid == 0) ? hdbg + 13 : nullptr;   // debug timeline of the CTA's first layout job
+        if (hl) { hl[0] = job; hl[1] = clock64() - t_enter; }
         if (call.bev_dtype == 0)
           layout_load<float>(reinterpret_cast<const float*>(call.bev) + (size_t)b * D * HW, HW, y * W + x0, tid, v);
         else
           layout_load<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(call.bev) + (size_t)b * D * HW, HW, y * W + x0, tid, v);
         layout_store(dst, y * W + x0, tile_u32, tid, v);
-        __threadfence();
-        fence_proxy_async_all();
+        if (hl) hl[2] = clock64() - t_enter;
+        __threadfence();   // (the generic -> async proxy fence is the reader's: it precedes the TMA loads)
         named_bar_sync(1, NCT);
         if (tid == 0) atomicAdd(ctrl + DC_ROW + b * H + y, 1);   // (release: every writer fenced before the barrier)
+        if (hl) hl[3] = clock64() - t_enter;
       }
       continue;
     }
@@ -399,8 +402,23 @@ __device__ __forceinline__ void dense_helper_role(const ResCall& call, const Den
           mbar_arrive_expect_tx(full(s), HSTAGE);
           tma_load_2d(st_addr + 16384, &da.wmap[l], full(s), c * 64, 0);   // weights first: they need no layout
           if (c == warp && da.nhwc) {   // the rows (with halo) this tile reads
+            // (the <= 4 flags are read together and acquired with one fence: four dependent
+            // ld.acquire round trips cost ~2.8 k cycles even when every row is ready)
             const int ylo = max(0, y0 - 1), yhi = min(H - 1, y0 + 128 / W);
-            for (int y = ylo; y <= yhi; ++y) wait_flag_ge(ctrl + DC_ROW + b * H + y, hpr);
+            const volatile int* rf = ctrl + DC_ROW + b * H;
+#ifdef DDH_CHECKED
+            unsigned long long spins = 0;
+#endif
+            for (;;) {
+              int lo = hpr;
+              for (int y = ylo; y <= yhi; ++y) lo = min(lo, rf[y]);
+              if (lo >= hpr) break;
+              __nanosleep(32);
+#ifdef DDH_CHECKED
+              if (++spins > (1ull << 26)) { printf("DDH_CHECKED: row flag wait timed out (block %d)\n", (int)blockIdx.x); __trap(); }
+#endif
+            }
+            __threadfence();
             fence_proxy_async_all();
             if (hd && warp == 0) hd[2] = clock64();
           }

@@ -129,6 +129,7 @@ def run_time():
                 rel = [int(x - hd[0]) if x > 0 else None for x in hd[:9]]
                 print("  helper CTA of conv job 0 (cycles since role entry): claimed %s, rows ready %s, first stage full %s, "
                       "MMAs issued %s, accumulators ready %s, epilogue done %s (staged %s, lines written %s)" % tuple(rel[1:9]))
+                print(f"  a helper CTA's first layout job (job {int(hd[13])}): starts {int(hd[14])}, stored {int(hd[15])}, flagged {int(hd[16])} cycles after role entry")
                 print(f"  globaltimer: helper job-0 done {int(hd[10] - hd[11])} ns after the scene cluster's start; "
                       f"scene cluster at its first gather after {int(hd[12] - hd[11])} ns", flush=True)
             if taps:
