@@ -542,7 +542,7 @@ void launch_embed(const float* img, float* pts, float* emb32, __nv_bfloat16* emb
 // (the only pixels at which value_proj has to be evaluated), and per (anchor, pose, corner) the slot of its pixel
 // in that list with the combined weight bilinear * aw.
 // ===================================================================================
-__global__ void __launch_bounds__(256) plan_kernel(const float* __restrict__ q0,
+__global__ void __launch_bounds__(256, 6) plan_kernel(const float* __restrict__ q0,
                                                    const float* __restrict__ attw_w,
                                                    const float* __restrict__ attw_b,
                                                    const float* __restrict__ pts,
@@ -669,16 +669,20 @@ __global__ void __launch_bounds__(256) plan_kernel(const float* __restrict__ q0,
       }
     }
   };
-  for (int i = beg; i < end; ++i) {
-    if (fast ? ((present >> (i - beg)) & 1u) : (table[i] != 0)) {
-      const int yy = i / W, xx = i - yy * W;
-      DDH_ASSERT(base < rcap);
-      upix[(size_t)scene * rcap + base] = (yy << 16) | xx;   // packed (y, x)
-      table[i] = (unsigned short)(base + 1);
-      ++base;
-      if (yy != cur_y) { flush(); cur_y = yy; xmin = xx; }
-      xmax = xx;
-    }
+  auto take = [&](int i) {
+    const int yy = i / W, xx = i - yy * W;
+    DDH_ASSERT(base < rcap);
+    upix[(size_t)scene * rcap + base] = (yy << 16) | xx;   // packed (y, x)
+    table[i] = (unsigned short)(base + 1);
+    ++base;
+    if (yy != cur_y) { flush(); cur_y = yy; xmin = xx; }
+    xmax = xx;
+  };
+  if (fast) {   // walk the set bits only (a thread's 16 pixels hold ~1 sampled pixel on average)
+    for (unsigned int m = present; m; m &= m - 1) take(beg + __ffs((int)m) - 1);
+  } else {
+    for (int i = beg; i < end; ++i)
+      if (table[i] != 0) take(i);
   }
   flush();
   __syncthreads();
