@@ -595,7 +595,10 @@ int build_res2(ddh_handle* h, cudaStream_t st) {
     TRY(dev_alloc(h, o, &da.V, (size_t)DENSE_MAX_B * L * H * W * D));
     TRY(dev_alloc(h, o, &da.ctrl, (size_t)DC_WORDS));
     CU_TRY(h, cudaMemsetAsync(da.ctrl, 0, (size_t)DC_WORDS * 4, st));
-    for (int l = 0; l < L; ++l) { da.wmap[l] = h->layers[l].conv.map; da.bias[l] = h->layers[l].conv.bias; }
+    for (int l = 0; l < L; ++l) {   // weight tiles of a job: [128 channels x 64 k]
+      TRY(encode_wmap(h, &da.wmap[l], h->layers[l].conv.w16, 256, h->layers[l].conv.K, 128));
+      da.bias[l] = h->layers[l].conv.bias;
+    }
     da.L = L; da.H = H; da.W = W;
     da.enabled = 1;
     h->dense_ok = true;

@@ -315,17 +315,19 @@ __device__ __forceinline__ void store8(float* p, int lane, const float (&v)[8]) 
 // Helper clusters of a dense-mode launch (DenseArgs, kernels_res2.h): whole-map value_proj + ReLU
 // (modules/blocks.py:68-76,114) for every layer, ahead of the scene cluster that samples it.
 //   layout job (b, y):   BEV row y of scene b, NCHW f32/bf16 -> NHWC bf16 (256 threads), flag DC_ROW
-//   conv job (l, b, t):  pixels [128 t, +128) (two map rows) x 256 output channels, K = 9 x 256 as 36
-//                        k-chunks of (tap, 64 channels).  A tile = TMA box {64 ch, 64 px, 2 rows} of the
+//   conv job (l, b, t, half):  pixels [128 t, +128) (two map rows) x 128 output channels, K = 9 x 256 as
+//                        36 k-chunks of (tap, 64 channels).  A tile = TMA box {64 ch, 64 px, 2 rows} of the
 //                        NHWC map at (dx, y0 + dy): the zero padding of the conv is the TMA's out-of-bounds
-//                        fill; B tile = [256 x 64] of the packed weights.  Four 48 KiB stages, one
-//                        producer thread per stage (a thread's TMA copies run one at a time), two MMA
+//                        fill; B tile = [128 x 64] of the packed weights.  Four 32 KiB stages, one A and one
+//                        B producer thread per stage (a thread's TMA copies run one at a time), two MMA
 //                        issuers with private accumulators (chunks of equal parity; a thread spends
-//                        ~160 cycles per tcgen05.mma, the tensor core 128), four epilogue warps:
-//                        sum, + bias, ReLU, bf16, 512-byte pixel lines to V; counter DC_VDONE.
+//                        ~160 cycles per tcgen05.mma), epilogue on all twelve warps: sum, + bias, ReLU,
+//                        bf16, 256-byte half lines to V; counter DC_VDONE.  Layer l starts when layer l - 1
+//                        is complete: the 64 jobs of one layer already pull what the chip's L2 delivers
+//                        (~6.3 KB/clk), so the first map is ready at ~15 us instead of ~21 us.
 // Jobs are claimed from DC_JOB in order (layout first), so a conv job only ever waits for layout
 // jobs that running CTAs hold.
-constexpr int HSTAGE = 49152, HNS = 4, HKC = 36;
+constexpr int HSTAGE = 32768, HNS = 4, HKC = 36;   // stage = A tile [128 px x 64] + B tile [128 ch x 64]
 static_assert(HNS * HSTAGE <= RING + PIPE + XBYTES + F_UPIX, "helper stages end below its small shared-memory items");
 __device__ __forceinline__ void dense_helper_role(const ResCall& call, const DenseArgs& da, uint8_t* sm,
                                                   uint32_t sm_addr, uint8_t* fix, uint32_t hbar, uint32_t tmem, int tid,
@@ -336,7 +338,7 @@ __device__ __forceinline__ void dense_helper_role(const ResCall& call, const Den
   const int tiles = HW / 128;
   const int hpr = W / 32;                              // 32-pixel layout jobs per BEV row
   const int n_layout = da.nhwc ? B * H * hpr : 0;
-  const int total = n_layout + B * L * tiles;
+  const int total = n_layout + B * L * tiles * 2;
   int* ctrl = da.ctrl;
   volatile int* job_slot = reinterpret_cast<volatile int*>(fix + F_BAR + 248);
   float* bias_s = reinterpret_cast<float*>(fix + F_UPIX);
@@ -387,10 +389,20 @@ __device__ __forceinline__ void dense_helper_role(const ResCall& call, const Den
     // debug timeline of the CTA that runs conv job 0: clock64 per label, globaltimer at the end
     long long* hd = (hdbg && idx == 0) ? hdbg : nullptr;
     if (hd && tid == 0) { hd[0] = t_enter; hd[1] = clock64(); }
-    const int l = idx / (B * tiles), r = idx - l * (B * tiles), b = r / tiles, t = r - b * tiles;
+    // conv job = (layer, scene, 128-pixel tile, 128-channel half), the two halves of a tile adjacent in
+    // the order (their A tiles hit in L2)
+    const int jpl = B * tiles * 2;
+    const int l = idx / jpl, r = idx - l * jpl, b = r / (tiles * 2), t = (r - b * (tiles * 2)) >> 1, hf = r & 1;
     const int y0 = t * (128 / W);
+    // Layer l waits for layer l - 1: all 64 CTAs of a layer together pull 64 x 32 KiB per k-chunk through
+    // the chip's ~6.3 KB/clk of L2 bandwidth, so running both layers at once would only make the first
+    // map -- the one the scene cluster is waiting for -- finish later
+    if (l > 0) {
+      if (tid == 0) wait_flag_ge(ctrl + DC_VDONE + b * L + l - 1, tiles * 2);
+      __syncthreads();
+    }
     if (warp < HNS) {
-      if (lane == 0) {
+      if (lane == 0) {   // A tiles (map patches), stage = warp
         fence_proxy_async();   // the layout tile / the previous job's staging (generic writes) alias the stages
         for (int c = warp; c < HKC; c += HNS) {
           const uint32_t gi = g + c;
@@ -399,8 +411,7 @@ __device__ __forceinline__ void dense_helper_role(const ResCall& call, const Den
           if (use > 0) mbar_wait(empty(s), (use - 1) & 1u);
           const int tap = c >> 2, dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
           const uint32_t st_addr = sm_addr + s * HSTAGE;
-          mbar_arrive_expect_tx(full(s), HSTAGE);
-          tma_load_2d(st_addr + 16384, &da.wmap[l], full(s), c * 64, 0);   // weights first: they need no layout
+          mbar_arrive_expect_tx(full(s), 16384);
           if (c == warp && da.nhwc) {   // the rows (with halo) this tile reads
             // (the <= 4 flags are read together and acquired with one fence: four dependent
             // ld.acquire round trips cost ~2.8 k cycles even when every row is ready)
@@ -426,9 +437,9 @@ __device__ __forceinline__ void dense_helper_role(const ResCall& call, const Den
         }
       }
     } else if (warp < HNS + 2) {
-      if (lane == 0) {
+      if (lane == 0) {   // MMA issuers: k-chunks of equal parity, private accumulators
         const int j = warp - HNS;
-        const uint32_t idesc = umma_idesc_bf16_m128_n256();
+        constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);   // M 128, N 128
         for (int c = j; c < HKC; c += 2) {
           const uint32_t gi = g + c;
           const int s = (int)(gi % HNS);
@@ -438,7 +449,7 @@ __device__ __forceinline__ void dense_helper_role(const ResCall& call, const Den
           const uint32_t st_addr = sm_addr + s * HSTAGE;
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4)
-            umma_bf16(tmem + j * 256, umma_desc_sw128(st_addr + k4 * 32), umma_desc_sw128(st_addr + 16384 + k4 * 32),
+            umma_bf16(tmem + j * 128, umma_desc_sw128(st_addr + k4 * 32), umma_desc_sw128(st_addr + 16384 + k4 * 32),
                       idesc, (c >= 2 || k4 > 0) ? 1u : 0u);
           umma_commit(empty(s));
         }
@@ -446,9 +457,21 @@ __device__ __forceinline__ void dense_helper_role(const ResCall& call, const Den
         if (hd && j == 0) hd[4] = clock64();
       }
     } else if (warp >= 8) {
-      const int et = tid - 256;
-      bias_s[et] = __ldg(da.bias[l] + et);
-      bias_s[et + 128] = __ldg(da.bias[l] + et + 128);
+      if (lane == 0) {   // B tiles (128 weight rows of this half), stage = warp - 8: a thread's TMA copies run one
+                         // at a time, so the two operands of a stage come from two threads
+        for (int c = warp - 8; c < HKC; c += HNS) {
+          const uint32_t gi = g + c;
+          const int s = (int)(gi % HNS);
+          const uint32_t use = gi / HNS;
+          if (use > 0) mbar_wait(empty(s), (use - 1) & 1u);
+          mbar_arrive_expect_tx(full(s), 16384);
+          tma_load_2d(sm_addr + s * HSTAGE + 16384, &da.wmap[l], full(s), c * 64, hf * 128);
+        }
+      }
+    } else {
+      const int et = tid - 192;   // warps 6, 7: the bias of this half
+      bias_s[et] = __ldg(da.bias[l] + hf * 128 + et);
+      bias_s[et + 64] = __ldg(da.bias[l] + hf * 128 + et + 64);
     }
     __syncwarp();
     __syncthreads();   // the bias is staged; producers and issuers have issued everything
@@ -457,20 +480,20 @@ __device__ __forceinline__ void dense_helper_role(const ResCall& call, const Den
     if (hd && tid == 0) hd[5] = clock64();
     {
       // Epilogue on all twelve warps: warp w reads TMEM lane quarter w % 4 (pixel rows 32 (w % 4) + lane),
-      // column blocks {0,1,2} / {3,4,5} / {6,7} by w / 4: sum of the two issuers' accumulators + bias, ReLU,
-      // bf16 into a shared-memory line (pitch 528 B: conflict-free 16-byte writes at a 512-byte lane
-      // stride; the pipeline stages are idle, every MMA of the job has completed), then whole 512-byte
-      // pixel lines per warp instruction to V
-      constexpr int EPITCH = 528;
+      // column blocks {0,1} / {2} / {3} by w / 4: sum of the two issuers' accumulators + bias, ReLU, bf16
+      // into a shared-memory line (pitch 272 B: conflict-free 16-byte writes at a 256-byte lane stride;
+      // the pipeline stages are idle, every MMA of the job has completed), then the 256-byte half lines
+      // of two pixels per warp instruction to V
+      constexpr int EPITCH = 272;
       const int q = warp & 3, wg = warp >> 2;
       const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
       uint8_t* stg = sm + (size_t)(q * 32 + lane) * EPITCH;
-      const int cb0 = wg * 3, cb1 = min(8, cb0 + 3);
+      const int cb0 = wg == 0 ? 0 : wg + 1, cb1 = wg == 0 ? 2 : wg + 2;
 #pragma unroll 1
       for (int cb = cb0; cb < cb1; ++cb) {
         uint32_t u0[32], u1[32];
         tmem_ld32(tl + cb * 32, u0);
-        tmem_ld32(tl + 256 + cb * 32, u1);
+        tmem_ld32(tl + 128 + cb * 32, u1);
         tmem_ld_wait();
         uint32_t pk[16];
 #pragma unroll
@@ -487,9 +510,9 @@ __device__ __forceinline__ void dense_helper_role(const ResCall& call, const Den
       tc_fence_before();
       __syncthreads();
       if (hd && tid == 0) hd[7] = clock64();
-      uint4* vout = reinterpret_cast<uint4*>(da.V + (((size_t)b * L + l) * HW + (size_t)t * 128) * D);
-      for (int m = warp; m < 128; m += NT / 32)
-        vout[(size_t)m * 32 + lane] = *reinterpret_cast<const uint4*>(sm + (size_t)m * EPITCH + lane * 16);
+      uint4* vout = reinterpret_cast<uint4*>(da.V + (((size_t)b * L + l) * HW + (size_t)t * 128) * D + hf * 128);
+      for (int m = warp * 2 + (lane >> 4); m < 128; m += NT / 16)
+        vout[(size_t)m * 32 + (lane & 15)] = *reinterpret_cast<const uint4*>(sm + (size_t)m * EPITCH + (lane & 15) * 16);
       if (hd && tid == 0) hd[8] = clock64();
       __threadfence();
       __syncthreads();
@@ -586,7 +609,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call_in,
     mbar_init(xbar0 + 8, 1);
     mbar_init(gbar, 1);
     mbar_init(grp_bar, GF);
-    for (int i = 0; i < 2 * HNS; ++i) mbar_init(hbar + i * 8, 1);   // helper role: stage full / empty
+    for (int i = 0; i < HNS; ++i) { mbar_init(hbar + i * 8, 2); mbar_init(hbar + (HNS + i) * 8, 1); }   // helper role: stage full (A and B producer) / empty
     mbar_init(hbar + 2 * HNS * 8, 2);                               // helper role: both issuers' accumulators
     fence_barrier_init();
   }
@@ -1049,7 +1072,7 @@ res2_forward_kernel(const R2Consts* __restrict__ gconsts, const ResCall call_in,
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
             call.dbg[920 + 12] = (long long)gt;   // the scene cluster reaches its first gather
           }
-          if (si == 0) wait_flag_ge(da.ctrl + DC_VDONE + scene * L + l, HW / 128);
+          if (si == 0) wait_flag_ge(da.ctrl + DC_VDONE + scene * L + l, 2 * (HW / 128));
           bsync();
           mark(120);
           // CTA (ag, fg) reads channels [64 fg, +64) of every corner line of its group's anchors: 8 lanes

@@ -56,13 +56,13 @@ enum : int {
   DC_JOB = 0,       // next job to claim
   DC_EXIT = 1,      // helper CTAs that have left their job loop
   DC_CHAINS = 2,    // scene clusters that have finished
-  DC_VDONE = 8,     // [B][L] 128-pixel tiles of V written
+  DC_VDONE = 8,     // [B][L] half tiles (128 pixels x 128 channels) of V written
   DC_ROW = 16,      // [B][H] BEV row converted to NHWC bf16
   DC_WORDS = DC_ROW + DENSE_MAX_B * 64,
 };
 struct DenseArgs {
   CUtensorMap amap;                // NHWC bf16 map [B][H][W][256]: box {64 channels, 64 pixels, 2 rows, 1 scene}
-  CUtensorMap wmap[RES_MAX_L];     // value_proj weights [256][9*256] (tap, channel), box {64, 256}
+  CUtensorMap wmap[RES_MAX_L];     // value_proj weights [256][9*256] (tap, channel), box {64 k, 128 channels}
   const float* bias[RES_MAX_L];
   __nv_bfloat16* V;                // [B][L][H*W][256]
   __nv_bfloat16* nhwc;             // destination of the layout jobs; null: the caller's map is NHWC bf16 already
