@@ -431,7 +431,7 @@ def run_ours(args):
                "wall_p50_us": sorted(wall)[len(wall) // 2], "iters": len(dts),
                "precision": precision, "launches": head.last_launch_count(),
                "engine": ("group-resident engine (kernels_res2.cu), dense mode: ONE launch = one 16-CTA scene cluster "
-                          "+ 8 helper clusters that run value_proj over the whole 64x64 map on tcgen05 (TMA implicit "
+                          "+ helper clusters (6 on a B200) that run value_proj over the whole 64x64 map on tcgen05 (TMA implicit "
                           "GEMM) under the embedding/encoder; the scene cluster gathers bilinear corners"
                           if head.last_launch_count() == 1 else "stream launches"),
                "call_path": "TrajectoryHead.forward -> C++ binding (torch_binding.cpp) -> ddh_forward"
