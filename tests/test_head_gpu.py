@@ -276,6 +276,27 @@ def test_resident_engine_dense_mode(golden_dir):
     o1, _, _ = _run(plain, 1)
     for k in outs[1]:
         assert np.array_equal(o1[k], outs[1][k]), k
+    # other input forms at B = 1: NHWC fp32 (cast pass in front, then the TMA reads the working copy),
+    # NCHW bf16 (layout jobs read bf16), CPU tensors (host call: on-demand engine reading the pinned map
+    # in place -- another conv algorithm, same tolerance)
+    ft1 = synth.make_features(1)
+    nz1 = synth.make_noise(1)
+    a1 = (ft1["ego_query"].cuda(), ft1["agents_query"].cuda())
+    bev1 = ft1["bev_feature"].cuda()
+    o_nhwc32 = plain(*a1, bev1.permute(0, 2, 3, 1).contiguous(), noise=nz1.cuda(), bev_layout="NHWC")
+    torch.cuda.synchronize()
+    for k in outs[1]:
+        assert np.array_equal(o_nhwc32[k].cpu().numpy(), outs[1][k]), k
+    bev16 = bev1.bfloat16()
+    o_b16 = plain(*a1, bev16, noise=nz1.cuda())
+    o_b16_ref = plain(*a1, bev16.float(), noise=nz1.cuda())
+    torch.cuda.synchronize()
+    for k in outs[1]:
+        assert torch.equal(o_b16[k], o_b16_ref[k]), k
+    o_host = plain(ft1["ego_query"], ft1["agents_query"], ft1["bev_feature"], noise=nz1)
+    assert o_host["trajectory"].device.type == "cpu"
+    assert np.abs(o_host["trajectory_modes"].numpy() - outs[1]["trajectory_modes"]).max() <= TOL_BF16_M
+    assert np.array_equal(o_host["mode_idx"].numpy(), outs[1]["mode_idx"])
 
 
 def test_engines_agree():
