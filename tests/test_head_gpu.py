@@ -299,6 +299,35 @@ def test_resident_engine_dense_mode(golden_dir):
     assert np.array_equal(o_host["mode_idx"].numpy(), outs[1]["mode_idx"])
 
 
+def test_dense_mode_concurrent_launches():
+    """Two heads (two handles, two control blocks) launching dense batch-1 forwards on two streams at the
+    same time: the helper clusters of either launch may or may not be resident together -- jobs are
+    claimed from a counter, so any resident helper makes progress -- and the results equal the
+    sequential ones."""
+    heads = [_make_head("bf16")[0] for _ in range(2)]
+    ins = []
+    for i in range(2):
+        ft = synth.make_features(3)
+        ins.append((ft["ego_query"][i:i + 1].cuda(), ft["agents_query"][i:i + 1].cuda(),
+                    ft["bev_feature"][i:i + 1].cuda().contiguous(), synth.make_noise(3)[i:i + 1].cuda().contiguous()))
+    want = []
+    for h, x in zip(heads, ins):
+        want.append({k: v.clone() for k, v in h(*x[:3], noise=x[3]).items()})
+        assert h.last_launch_count() == 1
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = [[], []]
+    for it in range(40):
+        for i in range(2):
+            with torch.cuda.stream(streams[i]):
+                outs[i].append(heads[i](*ins[i][:3], noise=ins[i][3]))
+    torch.cuda.synchronize()
+    for i in range(2):
+        for o in outs[i]:
+            for k in want[i]:
+                assert torch.equal(o[k], want[i][k]), (i, k)
+
+
 def test_engines_agree():
     """The group-resident engine (default for B <= 24), the scene-tile chain engine (default above,
     and for any B when the resident engine is off) and the per-Linear tensor engine compute the same
