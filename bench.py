@@ -557,11 +557,16 @@ def run_ours(args):
             extra_cfg["fp32_b256"] = {"config": "BASELINE configs[1]: fp32 engine, 256 scenes, 1 GPU",
                                       "ms_per_step": ms, "value": 256 / (ms * 1e-3), "unit": UNIT,
                                       "parity": dict(par(o, z256, 256), tolerance_m=1e-4),
-                                      "roofline": {"bound": "fp32 FMA (CUDA cores)", "unit": "TFLOP/s",
+                                      "engine": "value_proj as 3xTF32 on tcgen05 (fp32 operands split hi/lo, three "
+                                                "kind::tf32 products, fp32 accumulate), fp32 combine and decoder chain on "
+                                                "the CUDA cores",
+                                      "roofline": {"bound": "mixed: 3xTF32 tensor conv + fp32 FMA chain", "unit": "TFLOP/s",
                                                    "achieved": fl32 / (ms * 1e-3) / 1e12 if fl32 else None,
                                                    "peak": peak32,
                                                    "frac": fl32 / (ms * 1e-3) / 1e12 / peak32 if fl32 else None,
-                                                   "peak_source": "148 SMs x 128 FMA/clk x 2 x 1.965 GHz (nominal)"}}
+                                                   "peak_source": "fp32 FMA peak 148 SMs x 128 FMA/clk x 2 x 1.965 GHz (nominal); "
+                                                                  "achieved = fp32-equivalent executed FLOPs per second of the "
+                                                                  "whole forward (the conv's tensor-core work is 3x its fp32 FLOPs)"}}
             del h32
             zs = np.load(os.path.join(ROOT, "tests", "golden", "stress_b2.npz"))
             sds = synth.make_state_dict(num_layers=4, num_anchors=64)

@@ -169,6 +169,7 @@ struct GemmParams {
   RowEpi epi;
   // conv gather
   const void* bev = nullptr;  // NHWC [B][H][W][C]
+  const void* bev_lo = nullptr;  // 3xTF32 conv: the low-order plane a - tf32(a) of the fp32 map (bev = the high one)
   const int* upix = nullptr;  // [B][rcap]
   const int* nuniq = nullptr; // [B]
   int rcap = 0;

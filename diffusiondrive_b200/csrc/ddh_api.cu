@@ -35,6 +35,8 @@ struct PackedLinear {
   __nv_bfloat16* w16 = nullptr;   // [N][K] bf16 (tensor engine)
   CUtensorMap map;
   CUtensorMap map64;              // conv only: 64-row box for the small-batch kernel
+  float* w2_32 = nullptr;         // conv only, fp32 engine: [N][w_hi (K) | w_lo (K)] for the 3xTF32 conv
+  CUtensorMap map_tf32;           // over w2_32: box {32 k, 256 rows}
   float* bias = nullptr;          // [N]
   int N = 0, K = 0;
 };
@@ -142,6 +144,9 @@ struct ddh_handle {
   int ev_used = 0;
   int* conv_rows = nullptr;                    // [S*L] unique value_proj rows per conv launch
   int* conv_sched = nullptr;                   // scene counter of the persistent conv's dynamic scene queue
+  int fp32_tensor_conv = 1;                    // option "fp32_tensor_conv": fp32 engine runs value_proj as 3xTF32 on the tensor core
+  bool tf32_conv_ok = false;                   // packed for it (fp32 precision, <= 64 anchors x 32 entries, smem fits)
+  void* bev_nhwc_lo = nullptr;                 // low-order plane of the fp32 NHWC working copy
   int conv_dynamic = 1;                        // option "conv_dynamic": 1 scenes are dealt to the conv CTAs on demand, 0 round-robin
   unsigned int* need_seg = nullptr;            // [B][seg_nw32] BEV segments (+halo) the coming conv call reads
   unsigned int* done_seg = nullptr;            // [B][seg_nw32] BEV segments already converted to NHWC
@@ -288,6 +293,28 @@ int encode_nhwc_map(ddh_handle* h, CUtensorMap* out, const void* base, int B, in
   return DDH_OK;
 }
 
+// TMA tensor map over an fp32 [N][K2] matrix: box {32 k (128 bytes), 256 rows}, 128-byte swizzle.
+int encode_wmap_f32(ddh_handle* h, CUtensorMap* out, void* w32, int N, int K2) {
+  if (!h->encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+      return fail(h, DDH_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    h->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)K2, (cuuint64_t)N};
+  const cuuint64_t gstride[1] = {(cuuint64_t)K2 * 4};
+  const cuuint32_t box[2] = {32, 256};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = h->encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, w32, gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(h, DDH_ERR_CUDA, "cuTensorMapEncodeTiled (fp32) failed, CUresult " + std::to_string((int)r));
+  return DDH_OK;
+}
+
 int make_wmap(ddh_handle* h, PackedLinear& L, int box_rows = 256) {
   return encode_wmap(h, box_rows == 256 ? &L.map : &L.map64, L.w16, L.N, L.K, box_rows);
 }
@@ -383,6 +410,12 @@ int ensure_ws(ddh_handle* h, int B) {
     unsigned char* p = nullptr;
     WS(p, (size_t)B * s.bev_h * s.bev_w * s.bev_channels * (bf ? 2 : 4));
     h->bev_nhwc = p;
+  }
+  h->bev_nhwc_lo = nullptr;
+  if (!bf && h->tf32_conv_ok) {
+    unsigned char* p = nullptr;
+    WS(p, (size_t)B * s.bev_h * s.bev_w * s.bev_channels * 4);
+    h->bev_nhwc_lo = p;
   }
   WS(h->img, M * s.num_poses * 2);
   WS(h->pts, M * s.num_poses * 2);
@@ -722,6 +755,18 @@ int ddh_pack_weights(ddh_handle* h, const ddh_weight_ptrs* w, int precision, voi
     if (e) return fail(h, DDH_ERR_CUDA, std::string("tc_engine_init: ") + cudaGetErrorString((cudaError_t)e));
     h->tc_ready = true;
   }
+  // fp32 engine: value_proj as 3xTF32 on the tensor core (tc_conv2_kernel<true>) when its shared
+  // memory fits; everything else of the fp32 engine stays on the CUDA cores
+  h->tf32_conv_ok = false;
+  if (precision == DDH_PREC_FP32 && h->fp32_tensor_conv && s.bev_channels == 256 &&
+      tc_conv_smem_bytes(s.num_anchors, s.num_poses * 4) <= 227 * 1024) {
+    if (!h->tc_ready) {
+      int e = tc_engine_init();
+      if (e) return fail(h, DDH_ERR_CUDA, std::string("tc_engine_init: ") + cudaGetErrorString((cudaError_t)e));
+      h->tc_ready = true;
+    }
+    h->tf32_conv_ok = true;
+  }
   int rc;
 #define TRY(x) do { rc = (x); if (rc) return rc; } while (0)
   const int A = s.num_anchors, P = s.num_poses, F = s.d_ffn, L = s.num_layers, S = s.num_steps;
@@ -758,6 +803,11 @@ int ddh_pack_weights(ddh_handle* h, const ddh_weight_ptrs* w, int precision, voi
     if (precision == DDH_PREC_FP32) {
       TRY(dev_alloc(h, h->owned_w, &pl.conv.wt32, (size_t)256 * pl.conv.K));
       launch_pack_conv_f32(lw.bev_conv_w, pl.conv.wt32, 256, s.bev_channels, st);
+      if (h->tf32_conv_ok) {
+        TRY(dev_alloc(h, h->owned_w, &pl.conv.w2_32, (size_t)256 * 2 * pl.conv.K));
+        launch_pack_conv_tf32x2(lw.bev_conv_w, pl.conv.w2_32, 256, s.bev_channels, st);
+        TRY(encode_wmap_f32(h, &pl.conv.map_tf32, pl.conv.w2_32, 256, 2 * pl.conv.K));
+      }
     } else {
       TRY(dev_alloc(h, h->owned_w, &pl.conv.w16, (size_t)256 * pl.conv.K));
       launch_pack_conv_bf16(lw.bev_conv_w, pl.conv.w16, 256, s.bev_channels, st);
@@ -1154,21 +1204,43 @@ int forward_range(ddh_handle* h, const float* ego, const float* agents, const vo
   const int seg_shift = h->seg_px_call == 64 ? 6 : h->seg_px_call == 32 ? 5 : (h->seg_px_call == 16 ? 4 : 3);
   unsigned int* need_seg = lazy ? h->need_seg + (size_t)s0 * h->seg_nw32 : nullptr;
   unsigned int* done_seg = lazy ? h->done_seg + (size_t)s0 * h->seg_nw32 : nullptr;
+  // fp32 engine: value_proj as 3xTF32 on the tensor core.  Its operands are a high / low plane pair of
+  // the NHWC fp32 map: written directly by the on-demand layout pass (8- / 16-pixel device segments),
+  // or by a split pass behind the eager layout / in front for NHWC input.  A pinned host map read in
+  // place (other segment kernels) keeps the CUDA-core conv.
+  const bool lazy_split = lazy && (h->seg_px_call == 8 || h->seg_px_call == 16);
+  const bool tf32_conv = !bf && h->tf32_conv_ok && h->bev_nhwc_lo && !h->host_map_call && (!lazy || lazy_split);
+  void* bev_lo = tf32_conv ? (unsigned char*)h->bev_nhwc_lo + (size_t)s0 * HW * s.bev_channels * 4 : nullptr;
   { ProfSpan ps(h, ST_BEV, st);
+  const size_t n_map = (size_t)B * HW * s.bev_channels;
   if (bev_layout == DDH_NCHW) {
     if (lazy) {
       CU_TRY(h, cudaMemsetAsync(done_seg, 0, (size_t)B * h->seg_nw32 * 4, st));
     } else {
       launch_bev_to_nhwc(bev, bev_dtype, v.bev_nhwc, want_dtype, B, s.bev_channels, HW, st);
       h->launches++;
+      if (tf32_conv) {
+        launch_split_tf32(reinterpret_cast<const float*>(v.bev_nhwc), reinterpret_cast<float*>(v.bev_nhwc),
+                          reinterpret_cast<float*>(bev_lo), n_map, st);
+        h->launches++;
+      }
     }
     bevn = v.bev_nhwc;
   } else if (bev_dtype != want_dtype) {
-    const size_t n = (size_t)B * HW * s.bev_channels;
     if (bf) launch_cast_f32_bf16(reinterpret_cast<const float*>(bev),
-                                 reinterpret_cast<__nv_bfloat16*>(v.bev_nhwc), n, st);
+                                 reinterpret_cast<__nv_bfloat16*>(v.bev_nhwc), n_map, st);
     else launch_cast_bf16_f32(reinterpret_cast<const __nv_bfloat16*>(bev),
-                              reinterpret_cast<float*>(v.bev_nhwc), n, st);
+                              reinterpret_cast<float*>(v.bev_nhwc), n_map, st);
+    h->launches++;
+    bevn = v.bev_nhwc;
+    if (tf32_conv) {   // (bf16 values: the low plane is zero)
+      launch_split_tf32(reinterpret_cast<const float*>(v.bev_nhwc), reinterpret_cast<float*>(v.bev_nhwc),
+                        reinterpret_cast<float*>(bev_lo), n_map, st);
+      h->launches++;
+    }
+  } else if (tf32_conv) {   // NHWC fp32 input: planes of the caller's map into the working copy
+    launch_split_tf32(reinterpret_cast<const float*>(bev), reinterpret_cast<float*>(v.bev_nhwc),
+                      reinterpret_cast<float*>(bev_lo), n_map, st);
     h->launches++;
     bevn = v.bev_nhwc;
   }
@@ -1234,7 +1306,7 @@ int forward_range(ddh_handle* h, const float* ego, const float* agents, const vo
       if (lazy) {
         ProfSpan ps(h, ST_BEV, st);
         launch_bev_segs_to_nhwc(bev, bev_dtype, v.bev_nhwc, want_dtype, need_seg, h->seg_nw32, h->seg_px_call,
-                                B, s.bev_channels, s.bev_h, s.bev_w, st);
+                                B, s.bev_channels, s.bev_h, s.bev_w, st, tf32_conv ? bev_lo : nullptr);
         h->launches++;
         if (layout_event_pending) {   // the next chunk may start: its layout runs under our conv
           CU_TRY(h, cudaEventRecord(layout_done, st));
@@ -1254,13 +1326,19 @@ int forward_range(ddh_handle* h, const float* ego, const float* agents, const vo
           gp.epi.out_f32 = v.s32; gp.epi.ldo32 = D; gp.epi.out_bf16 = v.s16; gp.epi.ldo16 = D;
           launch_tc_conv(gp, pl.conv.map, B, st, h->persistent_conv != 0 ? 1 : 0);
           h->launches += 1;
+        } else if (tf32_conv) {   // fp32 engine, 3xTF32 on the tensor core, fp32 combine fused: S in fp32
+          gp.bev_lo = bev_lo;
+          gp.ent_slot = v.ent_slot; gp.ent_w = v.ent_w; gp.n_anchor = A; gp.ent_per_anchor = P * 4;
+          gp.epi.out_f32 = v.s32; gp.epi.ldo32 = D;
+          launch_tc_conv_tf32(gp, pl.conv.map_tf32, B, st);
+          h->launches += 1;
         } else {
           gp.epi.out_f32 = v.V; gp.epi.ldo32 = D;
           gp.W = pl.conv.wt32; gp.ldw = D;
           launch_simt_conv(gp, B, st);
         }
       }
-      if (!bf) {
+      if (!bf && !tf32_conv) {
         ProfSpan ps(h, ST_COMBINE, st);
         launch_combine(v.V, v.ent_slot, v.ent_w, v.s32, v.s16, B, A, P, h->rcap, st);
         h->launches += 3;
@@ -1769,6 +1847,7 @@ int ddh_set_option(ddh_handle* h, const char* name, int value) {
   else if (n == "persistent_conv") h->persistent_conv = value;
   else if (n == "conv_timeline") h->conv_timeline = value;
   else if (n == "conv_dynamic") h->conv_dynamic = value;
+  else if (n == "fp32_tensor_conv") { repack = h->fp32_tensor_conv != value; h->fp32_tensor_conv = value; }
   else if (n == "host_zero_copy") h->host_zero_copy = value;
   else if (n == "host_segment") {
     if (value != 16 && value != 32 && value != 64) return fail(h, DDH_ERR_BAD_ARG, "ddh_set_option: host_segment must be 16, 32 or 64");

@@ -36,7 +36,9 @@ void launch_plan(const float* q0, const float* attw_w, const float* attw_b, cons
 // on-demand layout conversion of the BEV segments (seg = 8 or 16 pixels of a row) flagged in todo
 void launch_bev_segs_to_nhwc(const void* src, int src_dtype, void* dst, int dst_dtype,
                              const unsigned int* todo, int nw32, int seg, int B, int C, int H, int W,
-                             cudaStream_t st);
+                             cudaStream_t st, void* dst_lo = nullptr);
+void launch_split_tf32(const float* src, float* hi, float* lo, size_t n, cudaStream_t st);
+void launch_pack_conv_tf32x2(const float* w, float* dst, int Cout, int Cin, cudaStream_t st);
 void launch_combine(const float* V, const int* ent_slot, const float* ent_w, float* s32,
                     __nv_bfloat16* s16, int B, int A, int P, int rcap, cudaStream_t st);
 void launch_attn_core(const float* qh, const float* kv, float* o32, __nv_bfloat16* o16, int B,
@@ -77,6 +79,7 @@ void launch_tc_gemm(const GemmParams& p, const CUtensorMap& wmap, int n_total, c
 // mode 0: one CTA per scene; 1: persistent, CUDA-core combine; 2: persistent, combine on the tensor
 // core (n_anchor <= 64, ent_per_anchor == 32; other shapes fall back to mode 1)
 void launch_tc_conv(const GemmParams& p, const CUtensorMap& wmap, int B, cudaStream_t st, int mode = 1);
+void launch_tc_conv_tf32(const GemmParams& p, const CUtensorMap& wmap, int B, cudaStream_t st);
 int tc_conv_smem_bytes(int A, int ent_per_anchor);
 int tc_engine_init();   // sets max dynamic smem attributes; returns cudaError_t as int
 

@@ -264,7 +264,7 @@ static void bev_launch(const void* src, void* dst, int B, int C, int HW, cudaStr
 template <typename TI, typename TO, int SEG, int NSEG>
 __global__ void __launch_bounds__(256) bev_segs_to_nhwc_kernel(
     const TI* __restrict__ src, TO* __restrict__ dst, const unsigned int* __restrict__ todo,
-    int nw32, int C, int H, int W) {
+    int nw32, int C, int H, int W, TO* __restrict__ dst_lo) {
   extern __shared__ __align__(16) unsigned char seg_raw[];   // NSEG segments per step
   TO* tile = reinterpret_cast<TO*>(seg_raw);    // [NSEG * SEG px][256 channels]
   __shared__ unsigned short list[2048];
@@ -320,8 +320,20 @@ __global__ void __launch_bounds__(256) bev_segs_to_nhwc_kernel(
     for (int u = tid; u < ns * SEG * V4_PER_ROW; u += 256) {
       const int row = u / V4_PER_ROW, part = u - row * V4_PER_ROW;
       const int sgi = row / SEG, px = row - sgi * SEG;
-      reinterpret_cast<uint4*>(db + (size_t)(px0[sgi] + px) * C)[part] =
-          reinterpret_cast<const uint4*>(tile + (size_t)row * 256)[part];
+      const uint4 v = reinterpret_cast<const uint4*>(tile + (size_t)row * 256)[part];
+      if (sizeof(TO) == 4 && dst_lo) {
+        // fp32 engine with the 3xTF32 conv: high plane = the 10 mantissa bits the tensor core reads,
+        // low plane = the exact remainder
+        const uint4 hi = make_uint4(v.x & 0xFFFFE000u, v.y & 0xFFFFE000u, v.z & 0xFFFFE000u, v.w & 0xFFFFE000u);
+        const uint4 lo = make_uint4(__float_as_uint(__uint_as_float(v.x) - __uint_as_float(hi.x)),
+                                    __float_as_uint(__uint_as_float(v.y) - __uint_as_float(hi.y)),
+                                    __float_as_uint(__uint_as_float(v.z) - __uint_as_float(hi.z)),
+                                    __float_as_uint(__uint_as_float(v.w) - __uint_as_float(hi.w)));
+        reinterpret_cast<uint4*>(db + (size_t)(px0[sgi] + px) * C)[part] = hi;
+        reinterpret_cast<uint4*>(dst_lo + (size_t)b * HW * C + (size_t)(px0[sgi] + px) * C)[part] = lo;
+      } else {
+        reinterpret_cast<uint4*>(db + (size_t)(px0[sgi] + px) * C)[part] = v;
+      }
     }
   }
 }
@@ -390,7 +402,7 @@ __global__ void __launch_bounds__(256) bev_segs_px_to_nhwc_kernel(
 
 template <typename TI, typename TO>
 static void bev_segs_launch(const void* src, void* dst, const unsigned int* todo, int nw32, int seg,
-                            int B, int C, int H, int W, cudaStream_t st) {
+                            int B, int C, int H, int W, cudaStream_t st, void* dst_lo = nullptr) {
   int ysplit = 592 / (B > 0 ? B : 1);     // small batches: spread one scene's segments over CTAs
   ysplit = ysplit < 1 ? 1 : (ysplit > 32 ? 32 : ysplit);
   dim3 grid(B, ysplit);
@@ -413,21 +425,23 @@ static void bev_segs_launch(const void* src, void* dst, const unsigned int* todo
         reinterpret_cast<const TI*>(src), reinterpret_cast<TO*>(dst), todo, nw32, C, H, W);
   else if (seg == 8)
     bev_segs_to_nhwc_kernel<TI, TO, 8, 4><<<grid, 256, 4 * 8 * 256 * sizeof(TO), st>>>(
-        reinterpret_cast<const TI*>(src), reinterpret_cast<TO*>(dst), todo, nw32, C, H, W);
+        reinterpret_cast<const TI*>(src), reinterpret_cast<TO*>(dst), todo, nw32, C, H, W, reinterpret_cast<TO*>(dst_lo));
   else
     bev_segs_to_nhwc_kernel<TI, TO, 16, 2><<<grid, 256, 2 * 16 * 256 * sizeof(TO), st>>>(
-        reinterpret_cast<const TI*>(src), reinterpret_cast<TO*>(dst), todo, nw32, C, H, W);
+        reinterpret_cast<const TI*>(src), reinterpret_cast<TO*>(dst), todo, nw32, C, H, W, reinterpret_cast<TO*>(dst_lo));
 }
 
 void launch_bev_segs_to_nhwc(const void* src, int src_dtype, void* dst, int dst_dtype,
                              const unsigned int* todo, int nw32, int seg, int B, int C, int H, int W,
-                             cudaStream_t st) {
-  if (src_dtype == 0 && dst_dtype == 0) bev_segs_launch<float, float>(src, dst, todo, nw32, seg, B, C, H, W, st);
+                             cudaStream_t st, void* dst_lo) {
+  // dst_lo (fp32 destination, 8- or 16-pixel device segments only): write the map as a high / low
+  // plane pair for the 3xTF32 conv
+  if (src_dtype == 0 && dst_dtype == 0) bev_segs_launch<float, float>(src, dst, todo, nw32, seg, B, C, H, W, st, dst_lo);
   else if (src_dtype == 0 && dst_dtype == 1)
     bev_segs_launch<float, __nv_bfloat16>(src, dst, todo, nw32, seg, B, C, H, W, st);
   else if (src_dtype == 1 && dst_dtype == 1)
     bev_segs_launch<__nv_bfloat16, __nv_bfloat16>(src, dst, todo, nw32, seg, B, C, H, W, st);
-  else bev_segs_launch<__nv_bfloat16, float>(src, dst, todo, nw32, seg, B, C, H, W, st);
+  else bev_segs_launch<__nv_bfloat16, float>(src, dst, todo, nw32, seg, B, C, H, W, st, dst_lo);
 }
 
 void launch_bev_to_nhwc(const void* src, int src_dtype, void* dst, int dst_dtype, int B, int C,
@@ -457,6 +471,27 @@ __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ s, float*
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n4; i += stride) reinterpret_cast<float4*>(d)[i] = ld4<__nv_bfloat16>(s + i * 4);
+}
+// 3xTF32 operand planes of an fp32 array: hi = the 10 mantissa bits the tensor core reads, lo = x - hi
+// (exact).  src may alias hi.
+__global__ void split_tf32_kernel(const float* s, float* hi, float* lo, size_t n4) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(s)[i];
+    float4 h;
+    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+    reinterpret_cast<float4*>(hi)[i] = h;
+    reinterpret_cast<float4*>(lo)[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+  }
+}
+void launch_split_tf32(const float* src, float* hi, float* lo, size_t n, cudaStream_t st) {
+  const size_t n4 = n / 4;
+  const int blocks = (int)min((size_t)148 * 16, (n4 + 255) / 256);
+  split_tf32_kernel<<<blocks > 0 ? blocks : 1, 256, 0, st>>>(src, hi, lo, n4);
 }
 void launch_cast_f32_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t st) {
   const size_t n4 = n / 4;
@@ -1184,6 +1219,23 @@ __global__ void pack_conv_bf16_kernel(const float* __restrict__ w, __nv_bfloat16
     const int c = (int)(k % Cin), tap = (int)(k / Cin);
     d[i] = __float2bfloat16_rn(w[((size_t)o * Cin + c) * 9 + tap]);
   }
+}
+// conv weight -> fp32 [Cout][w_hi (9*Cin) | w_lo (9*Cin)], K ordered (tap, channel): the B operand of the
+// 3xTF32 conv (w_hi = the 10 mantissa bits the tensor core reads, w_lo = w - w_hi, exact)
+__global__ void pack_conv_tf32x2_kernel(const float* __restrict__ w, float* __restrict__ d, int Cout, int Cin) {
+  const size_t K = (size_t)Cin * 9, n = (size_t)Cout * K;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t k = i % K;
+    const int o = (int)(i / K);
+    const int c = (int)(k % Cin), tap = (int)(k / Cin);
+    const float x = w[((size_t)o * Cin + c) * 9 + tap];
+    const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    d[(size_t)o * 2 * K + k] = hi;
+    d[(size_t)o * 2 * K + K + k] = x - hi;
+  }
+}
+void launch_pack_conv_tf32x2(const float* w, float* dst, int Cout, int Cin, cudaStream_t st) {
+  pack_conv_tf32x2_kernel<<<592, 256, 0, st>>>(w, dst, Cout, Cin);
 }
 void launch_pack_conv_f32(const float* w, float* dst, int Cout, int Cin, cudaStream_t st) {
   pack_conv_f32_kernel<<<592, 256, 0, st>>>(w, dst, Cout, Cin);

@@ -68,16 +68,17 @@ struct TcBars {
 };
 
 // One k-chunk of MMAs: NT_ACTIVE row tiles x (64/16) instructions, then release the stage.
-template <int NT>
+template <int NT, bool TF32 = false>
 __device__ __forceinline__ void mma_chunk(uint32_t a_stage, uint32_t b_stage, uint32_t tmem_base,
                                           int nt_active, bool first, uint32_t idesc,
                                           uint32_t empty_bar) {
   for (int t = 0; t < nt_active; ++t) {
 #pragma unroll
-    for (int k4 = 0; k4 < TC_BK / 16; ++k4) {
+    for (int k4 = 0; k4 < TC_BK / 16; ++k4) {   // 32 bytes of K per instruction: 16 bf16 or 8 tf32
       const uint64_t adesc = umma_desc_sw128(a_stage + t * TC_A_TILE + k4 * 32);
       const uint64_t bdesc = umma_desc_sw128(b_stage + k4 * 32);
-      umma_bf16(tmem_base + t * D, adesc, bdesc, idesc, (first && k4 == 0) ? 0u : 1u);
+      if (TF32) umma_tf32(tmem_base + t * D, adesc, bdesc, idesc, (first && k4 == 0) ? 0u : 1u);
+      else umma_bf16(tmem_base + t * D, adesc, bdesc, idesc, (first && k4 == 0) ? 0u : 1u);
     }
   }
   umma_commit(empty_bar);
@@ -770,6 +771,7 @@ tc_conv_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap) {
 constexpr int C2_THREADS = 448;
 constexpr int C2_EPI = 256;
 
+template <bool TF32>
 __global__ void __launch_bounds__(C2_THREADS, 1)
 tc_conv2_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap, int B) {
   constexpr int NS = C_NS, NT = C_NT;
@@ -788,7 +790,15 @@ tc_conv2_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap, in
   const TcBars bars{sm_addr + C_PIPE + ent_bytes + D * 4, NS};
   volatile uint32_t* tmem_slot =
       reinterpret_cast<volatile uint32_t*>(sm + C_PIPE + ent_bytes + D * 4 + (2 * NS + 2) * 8);
-  constexpr int KC = 9 * (D / TC_BK);   // 36 k-chunks: (tap, 64-channel chunk)
+  // bf16: 36 k-chunks (tap, 64-channel chunk).  TF32 (fp32 engine, 3xTF32): a k-chunk is 32 fp32 channels
+  // (the same 128 bytes per row), 72 per operand-plane combination, and three combinations run into
+  // the same accumulators, small terms first: (a_hi, w_lo), (a_lo, w_hi), (a_hi, w_hi), where x_hi keeps
+  // the 10 mantissa bits the tensor core reads and x_lo = x - x_hi (exact): the dropped a_lo . w_lo is
+  // ~2^-22 of the product, i.e. fp32-level accuracy
+  constexpr int ES = TF32 ? 4 : 2;                 // bytes per element
+  constexpr int CPT = D * ES / 128;                // k-chunks per tap
+  constexpr int KC1 = 9 * CPT;                     // k-chunks of one plane combination
+  constexpr int KC = TF32 ? 3 * KC1 : KC1;
   constexpr int RPT = NT * 8;
 
   if (threadIdx.x == 0) {
@@ -829,7 +839,8 @@ tc_conv2_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap, in
 #pragma unroll
       for (int i = 0; i < RPT; ++i)
         yxn[i] = (scene_n < B && nu_n > 0) ? __ldg(p.upix + (size_t)scene_n * p.rcap + min(rb + 16 * i, nu_n - 1)) : 0;
-      const __nv_bfloat16* bev = reinterpret_cast<const __nv_bfloat16*>(p.bev) + (size_t)scene * p.H * p.W_ * D;
+      const uint8_t* bev = reinterpret_cast<const uint8_t*>(p.bev) + (size_t)scene * p.H * p.W_ * D * ES;
+      const uint8_t* bev_lo = TF32 ? reinterpret_cast<const uint8_t*>(p.bev_lo) + (size_t)scene * p.H * p.W_ * D * ES : bev;
       const int passes = (nu + NT * TC_BM - 1) / (NT * TC_BM);
       for (int pass = 0; pass < passes; ++pass, ++pi) {
         const int row_base = pass * NT * TC_BM;
@@ -850,7 +861,7 @@ tc_conv2_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap, in
           if (r < rows_valid) {
             const int yx = yx0[i];   // (y << 16) | x
             const int y = yx >> 16, x = yx & 0xffff;
-            rowoff[i] = (y * p.W_ + x) * D + j * 8;
+            rowoff[i] = (y * p.W_ + x) * D * ES + j * 16;   // bytes
             const uint32_t xm = (x > 0 ? 1u : 0u) | 2u | (x + 1 < p.W_ ? 4u : 0u);
             vmask[i] = (y > 0 ? xm : 0u) | (xm << 3) | (y + 1 < p.H ? (xm << 6) : 0u);
           }
@@ -864,15 +875,17 @@ tc_conv2_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap, in
           mbar_wait(bars.empty(s), ((g / NS) & 1) ^ 1);
           C2_STAMP(sidx == 1 && pass == 0 && tid == 0 && (kc & 3) == 0, 2 + (kc >> 2));
           const uint32_t a_dst = sm_addr + s * C_STAGE + dst_base;
-          const int tap = kc >> 2;
+          const int combo = kc / KC1, kc1 = kc - combo * KC1;
+          const int tap = kc1 / CPT;
           const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
-          const int tapoff = (dy * p.W_ + dx) * D + (kc & 3) * TC_BK;
+          const int tapoff = (dy * p.W_ + dx) * D * ES + (kc1 - tap * CPT) * 128;   // bytes
+          const uint8_t* plane = (TF32 && combo == 1) ? bev_lo : bev;
 #pragma unroll
           for (int i = 0; i < RPT; ++i) {
             if (i < 8 * nt_active) {
               const bool ok = (vmask[i] >> tap) & 1u;
               const int off = ok ? rowoff[i] + tapoff : 0;
-              cp_async16(a_dst + i * 2048, bev + off, ok ? 16u : 0u);
+              cp_async16(a_dst + i * 2048, plane + off, ok ? 16u : 0u);
             }
           }
           cp_async_mbar_arrive_noinc(bars.full(s));
@@ -897,7 +910,10 @@ tc_conv2_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap, in
             const int s = g % NS;
             mbar_wait(bars.empty(s), ((g / NS) & 1) ^ 1);
             mbar_arrive_expect_tx(bars.full(s), TC_B_TILE);
-            tma_load_2d(sm_addr + s * C_STAGE + NT * TC_A_TILE, &wmap, bars.full(s), kc * TC_BK, 0);
+            // element coordinate along K; TF32: the packed matrix is [256][w_hi (K) | w_lo (K)]
+            const int combo = kc / KC1, kc1 = kc - combo * KC1;
+            const int k0 = TF32 ? ((combo == 0 ? p.K : 0) + kc1 * 32) : kc * TC_BK;
+            tma_load_2d(sm_addr + s * C_STAGE + NT * TC_A_TILE, &wmap, bars.full(s), k0, 0);
           }
         }
       }
@@ -906,7 +922,7 @@ tc_conv2_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap, in
   } else if (warp == 5) {
     // ======================= MMA issuer ================================================
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16_m128_n256();
+      const uint32_t idesc = TF32 ? umma_idesc_tf32_m128_n256() : umma_idesc_bf16_m128_n256();
       int g = 0, sidx = 0;
       for (int scene = blockIdx.x; scene < B; scene += gridDim.x, ++sidx) {
         const int nu = __ldg(p.nuniq + scene);
@@ -922,8 +938,8 @@ tc_conv2_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap, in
             tc_fence_after();
             C2_STAMP(sidx == 1 && pass == 0 && (kc & 3) == 0, 16 + (kc >> 2));
             const uint32_t a_stage = sm_addr + s * C_STAGE;
-            mma_chunk<NT>(a_stage, a_stage + NT * TC_A_TILE, tmem_base, nt_active, kc == 0, idesc,
-                          bars.empty(s));
+            mma_chunk<NT, TF32>(a_stage, a_stage + NT * TC_A_TILE, tmem_base, nt_active, kc == 0, idesc,
+                                bars.empty(s));
           }
           umma_commit(bars.accum());
           C2_STAMP(sidx == 1 && pass == 0, 25);
@@ -1052,6 +1068,8 @@ tc_conv2_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap, in
               u2.x = *reinterpret_cast<uint32_t*>(&h0);
               u2.y = *reinterpret_cast<uint32_t*>(&h1);
               *reinterpret_cast<uint2*>(S16 + o) = u2;
+            } else {                          // fp32 engine: S feeds the fp32 output_proj
+              *reinterpret_cast<float4*>(S32 + o) = acc;
             }
           }
           C2_STAMP(sidx == 1 && pass == 0 && etid == 0, 36 + 3 * half);
@@ -1481,7 +1499,10 @@ int tc_engine_init() {
   e = cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            227 * 1024);
   if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(tc_conv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  e = cudaFuncSetAttribute(tc_conv2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           227 * 1024);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(tc_conv2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            227 * 1024);
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(tc_conv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1520,9 +1541,25 @@ void launch_tc_conv(const GemmParams& p0, const CUtensorMap& wmap, int B, cudaSt
   if (mode == 2 && p.n_anchor <= 64 && p.ent_per_anchor == 32)
     tc_conv3_kernel<<<B < num_sms ? B : num_sms, C3_THREADS, C_PIPE + D * 4 + TC_BAR_BYTES + 1024, st>>>(p, wmap, B);
   else if (mode >= 1)
-    tc_conv2_kernel<<<B < num_sms ? B : num_sms, C2_THREADS, tc_conv_smem_bytes(p.n_anchor, p.ent_per_anchor), st>>>(p, wmap, B);
+    tc_conv2_kernel<false><<<B < num_sms ? B : num_sms, C2_THREADS, tc_conv_smem_bytes(p.n_anchor, p.ent_per_anchor), st>>>(p, wmap, B);
   else
     tc_conv_kernel<<<B, TC_THREADS, tc_conv_smem_bytes(p.n_anchor, p.ent_per_anchor), st>>>(p, wmap);
+}
+
+// fp32 engine: the same persistent conv with fp32 operands on the tensor core as 3xTF32 (p.bev /
+// p.bev_lo: high / low plane of the NHWC fp32 map, wmap: fp32 [256][w_hi | w_lo], box {32, 256});
+// fp32 combine on the CUDA cores, S written as fp32
+void launch_tc_conv_tf32(const GemmParams& p0, const CUtensorMap& wmap, int B, cudaStream_t st) {
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  GemmParams p = p0;
+  p.M = num_sms;
+  tc_conv2_kernel<true><<<B < num_sms ? B : num_sms, C2_THREADS, tc_conv_smem_bytes(p.n_anchor, p.ent_per_anchor), st>>>(p, wmap, B);
 }
 
 }  // namespace ddh

@@ -502,7 +502,7 @@ class TrajectoryHead(nn.Module):
             _lib.check(self._lib, self._handle,
                        self._lib.ddh_set_option(self._handle, name.encode(), int(value)),
                        "ddh_set_option")
-        if name in ("chain_engine", "resident_engine"):   # engine selection is fixed when the weights are packed
+        if name in ("chain_engine", "resident_engine", "fp32_tensor_conv"):   # engine selection is fixed when the weights are packed
             self._invalidate()
 
     def set_profiling(self, on: bool) -> None:

@@ -271,6 +271,10 @@ DDH_API int ddh_set_concurrency(ddh_handle *h, int chunks, int min_chunk_scenes)
  *   "persistent_conv"    2  value_proj conv as one persistent CTA per SM: 2 = bilinear x attention combine
  *                           on the tensor core (tc_conv3_kernel), 1 = CUDA-core combine
  *                           (tc_conv2_kernel); 0: one CTA per scene (tc_conv_kernel)
+ *   "fp32_tensor_conv"   1  fp32 engine: value_proj runs on the tensor core as 3xTF32 (fp32 operands split in
+ *                           a 10-bit-mantissa high part and an exact remainder, three tcgen05 kind::tf32
+ *                           products, fp32 accumulate: fp32-level accuracy); 0: CUDA-core conv.  Fixed at
+ *                           pack time like the engine options
  *   "conv_dynamic"       1  tc_conv3_kernel deals scenes to its persistent CTAs on demand (global counter) instead
  *                           of round-robin: removes the end-of-launch tail of unequal scenes
  *   "chain_timeline"    -1  index (step * layers + layer) of the chain launch that stamps clock64
