@@ -181,6 +181,11 @@ struct GemmParams {
   int ent_per_anchor = 0;          // P * 4
   long long* dbg = nullptr;        // optional timeline (DDH_TIMELINE builds): CTA 0 clock64 stamps
   int* sched = nullptr;            // tc_conv3_kernel: global scene counter (zeroed before the launch) or null = static deal
+  // value rows kept across denoise steps (PlanReuse, kernels.h): bf16 [B * vcap][256] of one layer
+  __nv_bfloat16* vout = nullptr;   // tc_conv3_kernel: also store row r of a scene at scene * vcap + r; tc_convv_kernel: output
+  int vcap = 0;
+  const int2* vrows = nullptr;     // tc_convv_kernel: (pixel index in the batch, value row) per list entry
+  const int* n_vrows = nullptr;    // tc_convv_kernel: device count of list entries
 };
 
 }  // namespace ddh

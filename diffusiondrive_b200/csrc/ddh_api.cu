@@ -148,6 +148,15 @@ struct ddh_handle {
   bool tf32_conv_ok = false;                   // packed for it (fp32 precision, <= 64 anchors x 32 entries, smem fits)
   void* bev_nhwc_lo = nullptr;                 // low-order plane of the fp32 NHWC working copy
   int conv_dynamic = 1;                        // option "conv_dynamic": 1 scenes are dealt to the conv CTAs on demand, 0 round-robin
+  // value rows kept across denoise steps (PlanReuse, kernels.h): value_proj(bev) of a layer is the same
+  // in every step, so steps after the first evaluate only the pixels no earlier step sampled
+  int conv_reuse = 1;                          // option "conv_reuse"
+  __nv_bfloat16* vkeep = nullptr;              // [L][B * vcap][256] value rows
+  int vcap = 0;                                // rows per scene and layer: min(H*W, steps * rcap)
+  unsigned short* slot_tab = nullptr;          // [L][B][H*W] pixel -> slot + 1
+  int* slot_cnt = nullptr;                     // [L][B]
+  int2* new_list = nullptr;                    // [B * rcap] rows of the current call without a kept value
+  int* new_count = nullptr;                    // [S*L] their number per conv call
   unsigned int* need_seg = nullptr;            // [B][seg_nw32] BEV segments (+halo) the coming conv call reads
   unsigned int* done_seg = nullptr;            // [B][seg_nw32] BEV segments already converted to NHWC
   int lazy_layout = 1;                         // convert BEV segments on demand (NCHW input)
@@ -176,10 +185,10 @@ namespace {
 
 const char* const kStageNames[] = {"bev_layout", "hoist_kv_ego", "embed_encode", "plan", "conv",
                                    "combine", "gemm_chain", "attn_core", "reg_finish", "select",
-                                   "init"};
+                                   "init", "conv_new"};
 constexpr int kNumStages = sizeof(kStageNames) / sizeof(kStageNames[0]);
 enum { ST_BEV = 0, ST_HOIST, ST_EMBED, ST_PLAN, ST_CONV, ST_COMBINE, ST_GEMM, ST_ATTN, ST_REG,
-       ST_SELECT, ST_INIT };
+       ST_SELECT, ST_INIT, ST_CONV_NEW };
 
 struct ProfSpan {
   ddh_handle* h;
@@ -398,6 +407,7 @@ int ensure_ws(ddh_handle* h, int B) {
   h->emb16 = h->e1_16 = h->q0_16 = h->agents16 = h->ego16 = h->s16 = h->x1_16 = h->o16 = h->x2_16 = h->h16 =
       h->x3_16 = h->c1_16 = h->r1_16 = nullptr;
   h->emb32 = h->e1_32 = h->s32 = h->o32 = h->x2_32 = h->h32 = h->x3_32 = h->c1_32 = h->r1_32 = h->V = nullptr;
+  h->vkeep = nullptr;
   const ddh_shape& s = h->shp;
   const size_t M = (size_t)B * s.num_anchors, F = s.d_ffn;
   const int L = s.num_layers;
@@ -450,6 +460,21 @@ int ensure_ws(ddh_handle* h, int B) {
       WS(h->q0t, tiles * 128 * D);
       rc = encode_wmap(h, &h->smap, h->s16, (int)M, D, 128);
       if (rc) return rc;
+      // kept value rows: only when they take a modest share of the free memory (the engine works without)
+      h->vkeep = nullptr;
+      h->vcap = (int)std::min((size_t)s.bev_h * s.bev_w, (size_t)s.num_steps * h->rcap);
+      const size_t keep_bytes = (size_t)L * B * h->vcap * D * 2, HWs = (size_t)s.bev_h * s.bev_w;
+      size_t free_b = 0, total_b = 0;
+      cudaMemGetInfo(&free_b, &total_b);
+      if (h->conv_reuse && s.num_steps >= 2 && B > RES_MAX_B && h->vcap < 0x7fff && (HWs & 7) == 0 &&
+          (size_t)B * HWs < ((size_t)1 << 31) && (size_t)B * h->vcap < ((size_t)1 << 31) &&
+          keep_bytes <= free_b / 3) {
+        WS(h->vkeep, (size_t)L * B * h->vcap * D);
+        WS(h->slot_tab, (size_t)L * B * HWs);
+        WS(h->slot_cnt, (size_t)L * B);
+        WS(h->new_list, (size_t)B * h->rcap);
+        WS(h->new_count, (size_t)s.num_layers * s.num_steps);
+      }
     }
   } else {
     WS(h->emb32, M * 512); WS(h->e1_32, M * D);
@@ -1127,6 +1152,8 @@ int forward_fused(ddh_handle* h, const float* ego, const float* agents, const vo
     a.anchors = h->anchors; a.noise = noise; a.img = h->img; a.pts = h->pts; a.q0t = h->q0t;
     a.modes = modes; a.scores = scores; a.smap = h->smap; a.dbg = nullptr;
   };
+  const bool reuse = h->conv_reuse && h->vkeep && conv_mode == 2 && S >= 2;
+  if (reuse) CU_TRY(h, cudaMemsetAsync(h->new_count, 0, (size_t)S * L * 4, st));
   for (int si = 0; si < S; ++si) {
     { ProfSpan ps(h, ST_EMBED, st);
     ChainArgs& a = h->chain_prog[si];
@@ -1135,10 +1162,22 @@ int forward_fused(ddh_handle* h, const float* ego, const float* agents, const vo
     h->launches++; }
     for (int l = 0; l < L; ++l) {
       const PackedLayer& pl = h->layers[l];
+      PlanReuse ru;
+      __nv_bfloat16* vkeep_l = nullptr;
+      if (reuse) {
+        ru.mode = si == 0 ? 1 : 2;
+        ru.keep = si + 1 < S;
+        ru.slot_tab = h->slot_tab + (size_t)l * B * HW;
+        ru.slot_cnt = h->slot_cnt + (size_t)l * B;
+        ru.new_list = h->new_list;
+        ru.new_count = h->new_count + si * L + l;
+        ru.vcap = h->vcap;
+        vkeep_l = h->vkeep + (size_t)l * B * h->vcap * D;
+      }
       { ProfSpan ps(h, ST_PLAN, st);
       launch_plan(h->q0t, pl.attw_w, pl.attw_b, h->pts, h->upix, h->nuniq, h->ent_slot, h->ent_w,
                   h->conv_rows + si * L + l, lazy ? h->need_seg : nullptr, h->done_seg, seg_shift,
-                  h->seg_nw32, B, A, P, s.bev_h, s.bev_w, h->rcap, oc, st, spt);
+                  h->seg_nw32, B, A, P, s.bev_h, s.bev_w, h->rcap, oc, st, spt, ru);
       h->launches++; }
       if (lazy) {
         ProfSpan ps(h, ST_BEV, st);
@@ -1147,21 +1186,34 @@ int forward_fused(ddh_handle* h, const float* ego, const float* agents, const vo
                                 s.bev_channels, s.bev_h, s.bev_w, st);
         h->launches++;
       }
-      { ProfSpan ps(h, ST_CONV, st);
       GemmParams gp;
       gp.K = pl.conv.K;
       gp.bev = bevn; gp.upix = h->upix; gp.nuniq = h->nuniq; gp.rcap = h->rcap;
       gp.H = s.bev_h; gp.W_ = s.bev_w; gp.C = s.bev_channels;
       gp.epi.bias = pl.conv.bias; gp.epi.relu = 1;
-      gp.dbg = (h->conv_timeline == si * L + l) ? h->dbg + 256 : nullptr;
-      gp.ent_slot = h->ent_slot; gp.ent_w = h->ent_w; gp.n_anchor = A; gp.ent_per_anchor = P * 4;
-      gp.epi.out_f32 = h->s32; gp.epi.ldo32 = D; gp.epi.out_bf16 = h->s16; gp.epi.ldo16 = D;
-      if (conv_mode == 2 && h->conv_dynamic) {
-        CU_TRY(h, cudaMemsetAsync(h->conv_sched, 0, 4, st));
-        gp.sched = h->conv_sched;
+      gp.vout = vkeep_l; gp.vcap = h->vcap;
+      if (ru.mode != 2) {
+        ProfSpan ps(h, ST_CONV, st);
+        gp.dbg = (h->conv_timeline == si * L + l) ? h->dbg + 256 : nullptr;
+        gp.ent_slot = h->ent_slot; gp.ent_w = h->ent_w; gp.n_anchor = A; gp.ent_per_anchor = P * 4;
+        gp.epi.out_f32 = h->s32; gp.epi.ldo32 = D; gp.epi.out_bf16 = h->s16; gp.epi.ldo16 = D;
+        if (conv_mode == 2 && h->conv_dynamic) {
+          CU_TRY(h, cudaMemsetAsync(h->conv_sched, 0, 4, st));
+          gp.sched = h->conv_sched;
+        }
+        launch_tc_conv(gp, pl.conv.map, B, st, conv_mode);
+        h->launches++;
+      } else {
+        // a later denoise step: value rows of the few pixels no earlier step sampled, then the combine
+        // over the kept rows (modules/blocks.py:114 is step-invariant; :117-126 is not)
+        { ProfSpan ps(h, ST_CONV_NEW, st);
+        gp.vrows = h->new_list; gp.n_vrows = ru.new_count;
+        launch_tc_convv(gp, pl.conv.map, st);
+        h->launches++; }
+        { ProfSpan ps(h, ST_COMBINE, st);
+        launch_combine_rows(vkeep_l, h->ent_slot, h->ent_w, h->s16, B, A, P * 4, h->vcap, st);
+        h->launches++; }
       }
-      launch_tc_conv(gp, pl.conv.map, B, st, conv_mode);
-      h->launches++; }
       { ProfSpan ps(h, ST_GEMM, st);
       ChainArgs& a = h->chain_prog[S + (size_t)si * L + l];
       fill(a);
@@ -1847,6 +1899,10 @@ int ddh_set_option(ddh_handle* h, const char* name, int value) {
   else if (n == "persistent_conv") h->persistent_conv = value;
   else if (n == "conv_timeline") h->conv_timeline = value;
   else if (n == "conv_dynamic") h->conv_dynamic = value;
+  else if (n == "conv_reuse") {
+    if ((h->conv_reuse != 0) != (value != 0)) { cudaDeviceSynchronize(); free_all(h->owned_ws); h->cap_B = 0; h->vkeep = nullptr; h->chain_prog.clear(); }
+    h->conv_reuse = value != 0;
+  }
   else if (n == "fp32_tensor_conv") { repack = h->fp32_tensor_conv != value; h->fp32_tensor_conv = value; }
   else if (n == "host_zero_copy") h->host_zero_copy = value;
   else if (n == "host_segment") {

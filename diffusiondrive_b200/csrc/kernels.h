@@ -29,10 +29,29 @@ void launch_init_img(const float* anchors, const float* noise, float* img, int B
                      float sqrt_ac, float sqrt_1m_ac, cudaStream_t st);
 void launch_embed(const float* img, float* pts, float* emb32, __nv_bfloat16* emb16, int M, int P,
                   const float* dim_t_dev, cudaStream_t st);
+// Value-row reuse across denoise steps (forward_fused): value_proj(bev) of a layer does not depend on
+// the denoise step, so the rows of V a step produced are kept ([B][vcap][256] bf16 per layer) and a
+// later step only evaluates the pixels that have no row yet.
+//   mode 0  off;  1  first step: the scene's unique pixels go to upix as before and the pixel -> slot
+//   table is saved;  2  later step: sampled pixels without a row are appended to the cross-scene list
+//   new_list (x = pixel index in the batch, y = value row it fills) and get the scene's next slots
+struct PlanReuse {
+  int mode = 0;
+  int keep = 1;                           // write the slot table back (0 in the last step)
+  unsigned short* slot_tab = nullptr;     // [B][H*W] slot + 1 of a pixel's value row, 0 = none
+  int* slot_cnt = nullptr;                // [B] rows a scene holds
+  int2* new_list = nullptr;
+  int* new_count = nullptr;               // rows in new_list (zeroed before the forward)
+  int vcap = 0;                           // row capacity per scene
+};
 void launch_plan(const float* q0, const float* attw_w, const float* attw_b, const float* pts,
                  int* upix, int* nuniq, int* ent_slot, float* ent_w, int* rows_total,
                  unsigned int* need_seg, unsigned int* done_seg, int seg_shift, int nw32, int B, int A,
-                 int P, int H, int W, int rcap, OdoConsts oc, cudaStream_t st, int q0_spt = 0);
+                 int P, int H, int W, int rcap, OdoConsts oc, cudaStream_t st, int q0_spt = 0,
+                 PlanReuse ru = PlanReuse());
+// S[scene, a, :] = sum_k w[scene, a, k] * V[scene * vcap + slot[scene, a, k], :]  (bf16 rows, fp32 sum)
+void launch_combine_rows(const __nv_bfloat16* V, const int* ent_slot, const float* ent_w,
+                         __nv_bfloat16* s16, int B, int A, int ent_per_anchor, int vcap, cudaStream_t st);
 // on-demand layout conversion of the BEV segments (seg = 8 or 16 pixels of a row) flagged in todo
 void launch_bev_segs_to_nhwc(const void* src, int src_dtype, void* dst, int dst_dtype,
                              const unsigned int* todo, int nw32, int seg, int B, int C, int H, int W,
@@ -79,6 +98,7 @@ void launch_tc_gemm(const GemmParams& p, const CUtensorMap& wmap, int n_total, c
 // mode 0: one CTA per scene; 1: persistent, CUDA-core combine; 2: persistent, combine on the tensor
 // core (n_anchor <= 64, ent_per_anchor == 32; other shapes fall back to mode 1)
 void launch_tc_conv(const GemmParams& p, const CUtensorMap& wmap, int B, cudaStream_t st, int mode = 1);
+void launch_tc_convv(const GemmParams& p, const CUtensorMap& wmap, cudaStream_t st);
 void launch_tc_conv_tf32(const GemmParams& p, const CUtensorMap& wmap, int B, cudaStream_t st);
 int tc_conv_smem_bytes(int A, int ent_per_anchor);
 int tc_engine_init();   // sets max dynamic smem attributes; returns cudaError_t as int

@@ -589,7 +589,7 @@ __global__ void __launch_bounds__(256, 6) plan_kernel(const float* __restrict__ 
                                                    unsigned int* __restrict__ done_seg,
                                                    int seg_shift, int nw32,
                                                    int A, int P, int H, int W, int rcap,
-                                                   OdoConsts oc, int q0_spt) {
+                                                   OdoConsts oc, int q0_spt, PlanReuse ru) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int HW = H * W;
   unsigned short* table = reinterpret_cast<unsigned short*>(smraw);        // [HW]
@@ -601,8 +601,19 @@ __global__ void __launch_bounds__(256, 6) plan_kernel(const float* __restrict__ 
   if (threadIdx.x < 64) seg_s[threadIdx.x] = 0u;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  for (int i = tid; i < HW / 8; i += 256) reinterpret_cast<uint4*>(table)[i] = make_uint4(0u, 0u, 0u, 0u);
-  for (int i = (HW / 8) * 8 + tid; i < HW; i += 256) table[i] = 0;
+  // table[pixel] = slot + 1 of a pixel whose value row exists (0: none); bit 15 marks the pixels this
+  // call samples.  A later denoise step of the same layer (ru.mode == 2) starts from the table the
+  // earlier steps left: value_proj(bev) does not depend on the step, so only pixels without a row
+  // are handed to the conv.
+  if (ru.mode == 2) {
+    const uint4* src = reinterpret_cast<const uint4*>(ru.slot_tab + (size_t)scene * HW);
+    for (int i = tid; i < HW / 8; i += 256) reinterpret_cast<uint4*>(table)[i] = __ldg(src + i);
+    for (int i = (HW / 8) * 8 + tid; i < HW; i += 256) table[i] = ru.slot_tab[(size_t)scene * HW + i];
+  } else {
+    for (int i = tid; i < HW / 8; i += 256) reinterpret_cast<uint4*>(table)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = (HW / 8) * 8 + tid; i < HW; i += 256) table[i] = 0;
+  }
+  __shared__ int reuse_s[2];   // rows the scene already has, base of its rows in the global new-row list
   // ---- attention weights: P (=8) logits per anchor, softmax over the poses; the 8 x 256 head is
   // staged in shared memory once per CTA
   __shared__ __align__(16) float ww[8 * D];
@@ -653,10 +664,11 @@ __global__ void __launch_bounds__(256, 6) plan_kernel(const float* __restrict__ 
     const float py = pts[((size_t)scene * AP + e) * 2 + 1];
     const Corners c = corners_of(px, py, H, W, oc);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) if (c.pix[k] >= 0) table[c.pix[k]] = 1;
+    for (int k = 0; k < 4; ++k)   // (racing writers of one entry all store the same value)
+      if (c.pix[k] >= 0) table[c.pix[k]] = (unsigned short)(table[c.pix[k]] | 0x8000u);
   }
   __syncthreads();
-  // ---- ordered compaction (pixel order == memory order of the NHWC map)
+  // ---- ordered compaction of the sampled pixels that have no value row yet (pixel order == memory order of the NHWC map)
   const int ipt = (HW + 255) / 256;
   const int beg = tid * ipt, end = min(HW, beg + ipt);
   int cnt = 0;
@@ -670,12 +682,12 @@ __global__ void __launch_bounds__(256, 6) plan_kernel(const float* __restrict__ 
     const unsigned int w[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      if (w[k] & 0xffffu) present |= 1u << (2 * k);
-      if (w[k] >> 16) present |= 1u << (2 * k + 1);
+      if ((w[k] & 0xffffu) == 0x8000u) present |= 1u << (2 * k);
+      if ((w[k] >> 16) == 0x8000u) present |= 1u << (2 * k + 1);
     }
     cnt = __popc(present);
   } else {
-    for (int i = beg; i < end; ++i) cnt += table[i] ? 1 : 0;
+    for (int i = beg; i < end; ++i) cnt += table[i] == 0x8000u ? 1 : 0;
   }
   int incl = cnt;
 #pragma unroll
@@ -687,7 +699,20 @@ __global__ void __launch_bounds__(256, 6) plan_kernel(const float* __restrict__ 
   __syncthreads();
   int base = incl - cnt;
   for (int w = 0; w < warp; ++w) base += warp_tot[w];
-  if (tid == 255) total_s = base + cnt;
+  if (tid == 255) {
+    const int total = base + cnt;
+    total_s = total;
+    int have = 0, gbase = 0;
+    if (ru.mode == 2) {
+      have = ru.slot_cnt[scene];
+      gbase = total ? atomicAdd(ru.new_count, total) : 0;
+    }
+    if (ru.mode) ru.slot_cnt[scene] = have + total;
+    reuse_s[0] = have;
+    reuse_s[1] = gbase;
+  }
+  if (ru.mode == 2) __syncthreads();
+  const int have = ru.mode == 2 ? reuse_s[0] : 0, gbase = ru.mode == 2 ? reuse_s[1] : 0;
   // segments covering the 3x3 neighbourhood of every unique pixel; a thread's pixels are
   // consecutive, so it marks [xmin - 1, xmax + 1] of rows y - 1 .. y + 1 once per row it touches
   const int segs_per_row = W >> seg_shift;
@@ -706,9 +731,14 @@ __global__ void __launch_bounds__(256, 6) plan_kernel(const float* __restrict__ 
   };
   auto take = [&](int i) {
     const int yy = i / W, xx = i - yy * W;
-    DDH_ASSERT(base < rcap);
-    upix[(size_t)scene * rcap + base] = (yy << 16) | xx;   // packed (y, x)
-    table[i] = (unsigned short)(base + 1);
+    if (ru.mode == 2) {   // row of the cross-scene list: (pixel of the batch, value row it fills)
+      DDH_ASSERT(have + base < ru.vcap);
+      ru.new_list[gbase + base] = make_int2(scene * HW + i, scene * ru.vcap + have + base);
+    } else {
+      DDH_ASSERT(base < rcap);
+      upix[(size_t)scene * rcap + base] = (yy << 16) | xx;   // packed (y, x)
+    }
+    table[i] = (unsigned short)(have + base + 1);
     ++base;
     if (yy != cur_y) { flush(); cur_y = yy; xmin = xx; }
     xmax = xx;
@@ -717,13 +747,23 @@ __global__ void __launch_bounds__(256, 6) plan_kernel(const float* __restrict__ 
     for (unsigned int m = present; m; m &= m - 1) take(beg + __ffs((int)m) - 1);
   } else {
     for (int i = beg; i < end; ++i)
-      if (table[i] != 0) take(i);
+      if (table[i] == 0x8000u) take(i);
   }
   flush();
   __syncthreads();
   if (tid == 0) {
-    nuniq[scene] = total_s;
+    if (ru.mode != 2) nuniq[scene] = total_s;
     if (rows_total) atomicAdd(rows_total, total_s);
+  }
+  if (ru.mode && ru.keep) {   // slot table for the next denoise step
+    uint4* dst = reinterpret_cast<uint4*>(ru.slot_tab + (size_t)scene * HW);
+    for (int i = tid; i < HW / 8; i += 256) {
+      uint4 t = reinterpret_cast<const uint4*>(table)[i];
+      t.x &= 0x7fff7fffu; t.y &= 0x7fff7fffu; t.z &= 0x7fff7fffu; t.w &= 0x7fff7fffu;
+      dst[i] = t;
+    }
+    for (int i = (HW / 8) * 8 + tid; i < HW; i += 256)
+      ru.slot_tab[(size_t)scene * HW + i] = (unsigned short)(table[i] & 0x7fffu);
   }
   if (need_seg && tid < nw32) {   // segments still to convert for the coming conv call; mark them converted
     const unsigned int need = seg_s[tid];
@@ -741,7 +781,7 @@ __global__ void __launch_bounds__(256, 6) plan_kernel(const float* __restrict__ 
     for (int k = 0; k < 4; ++k) {
       const size_t o = ((size_t)scene * AP + e) * 4 + k;
       if (c.pix[k] >= 0) {
-        ent_slot[o] = (int)table[c.pix[k]] - 1;
+        ent_slot[o] = (int)(table[c.pix[k]] & 0x7fffu) - 1;
         ent_w[o] = c.w[k] * a_w;
       } else {
         ent_slot[o] = -1;
@@ -753,7 +793,8 @@ __global__ void __launch_bounds__(256, 6) plan_kernel(const float* __restrict__ 
 void launch_plan(const float* q0, const float* attw_w, const float* attw_b, const float* pts,
                  int* upix, int* nuniq, int* ent_slot, float* ent_w, int* rows_total,
                  unsigned int* need_seg, unsigned int* done_seg, int seg_shift, int nw32, int B, int A,
-                 int P, int H, int W, int rcap, OdoConsts oc, cudaStream_t st, int q0_spt) {
+                 int P, int H, int W, int rcap, OdoConsts oc, cudaStream_t st, int q0_spt,
+                 PlanReuse ru) {
   const int smem = ((H * W * 2 + 15) / 16) * 16 + A * P * 4;
   static int cur = 0;
   if (smem > cur) {
@@ -762,7 +803,7 @@ void launch_plan(const float* q0, const float* attw_w, const float* attw_b, cons
   }
   plan_kernel<<<B, 256, smem, st>>>(q0, attw_w, attw_b, pts, upix, nuniq, ent_slot, ent_w,
                                      rows_total, need_seg, done_seg, seg_shift, nw32, A, P, H, W,
-                                     rcap, oc, q0_spt);
+                                     rcap, oc, q0_spt, ru);
 }
 
 // ===================================================================================
@@ -809,6 +850,67 @@ void launch_combine(const float* V, const int* ent_slot, const float* ent_w, flo
     cur = smem;
   }
   combine_kernel<<<B, 256, smem, st>>>(V, ent_slot, ent_w, s32, s16, A, P, rcap);
+}
+
+// ===================================================================================
+// The same combine over the kept value rows of a layer (denoise steps after the first, PlanReuse):
+//   S[a, :] = sum_k w[a, k] * V[scene * vcap + slot[a, k], :]      k = (pose, corner), in entry order
+// One CTA per scene, one warp per anchor (round robin), one lane per 8 channels: an entry is one 512-byte
+// row read by the whole warp (L1/L2 hits after the scene's first touch of a row); lane k holds entry k.
+// ===================================================================================
+__global__ void __launch_bounds__(256) combine_rows_kernel(const __nv_bfloat16* __restrict__ V,
+                                                           const int* __restrict__ ent_slot,
+                                                           const float* __restrict__ ent_w,
+                                                           __nv_bfloat16* __restrict__ s16, int A,
+                                                           int epa, int vcap) {
+  const int scene = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint4* rows = reinterpret_cast<const uint4*>(V) + (size_t)scene * vcap * 32 + lane;
+  for (int a = warp; a < A; a += 8) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    const size_t e0 = ((size_t)scene * A + a) * epa;
+    for (int kb = 0; kb < epa; kb += 32) {
+      const int n = min(32, epa - kb);
+      int slot = -1;
+      float wv = 0.f;
+      if (lane < n) { slot = __ldg(ent_slot + e0 + kb + lane); wv = __ldg(ent_w + e0 + kb + lane); }
+      DDH_ASSERT(slot < vcap);
+#pragma unroll 1
+      for (int k0 = 0; k0 < n; k0 += 8) {
+        uint4 v[8];
+        float wk[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int sl = __shfl_sync(0xffffffffu, slot, (k0 + u) & 31);
+          wk[u] = __shfl_sync(0xffffffffu, wv, (k0 + u) & 31);
+          const bool ok = sl >= 0 && k0 + u < n;   // warp-uniform; a missing corner reads nothing
+          v[u] = ok ? __ldg(rows + (size_t)sl * 32) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const uint32_t w4[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+          for (int h2 = 0; h2 < 4; ++h2) {
+            acc[2 * h2] = fmaf(wk[u], __uint_as_float(w4[h2] << 16), acc[2 * h2]);
+            acc[2 * h2 + 1] = fmaf(wk[u], __uint_as_float(w4[h2] & 0xffff0000u), acc[2 * h2 + 1]);
+          }
+        }
+      }
+    }
+    uint4 o;
+    uint32_t* op = &o.x;
+#pragma unroll
+    for (int h2 = 0; h2 < 4; ++h2) {
+      const __nv_bfloat162 hh = __floats2bfloat162_rn(acc[2 * h2], acc[2 * h2 + 1]);
+      op[h2] = *reinterpret_cast<const uint32_t*>(&hh);
+    }
+    reinterpret_cast<uint4*>(s16)[((size_t)scene * A + a) * 32 + lane] = o;
+  }
+}
+void launch_combine_rows(const __nv_bfloat16* V, const int* ent_slot, const float* ent_w,
+                         __nv_bfloat16* s16, int B, int A, int ent_per_anchor, int vcap, cudaStream_t st) {
+  combine_rows_kernel<<<B, 256, 0, st>>>(V, ent_slot, ent_w, s16, A, ent_per_anchor, vcap);
 }
 
 // ===================================================================================

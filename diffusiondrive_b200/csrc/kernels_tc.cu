@@ -14,6 +14,7 @@
 // (modules/blocks.py:68-76,114): row r of a scene is the 3x3xC patch around the r-th unique
 // sampled pixel, gathered from the NHWC bf16 BEV map with zero padding; K = 9*C ordered
 // (tap, channel) to match the packed weights.
+#include <type_traits>
 #include "kernels.h"
 #include "tc_ptx.cuh"
 
@@ -484,6 +485,10 @@ struct EntPair { int slot; float w; };
 
 
 
+// VOUT = true (tc_convv_kernel's role, denoise steps after the first with PlanReuse): the rows are a
+// contiguous share of the cross-scene list p.vrows (pixel index in the batch, value row) and the epilogue
+// writes V rows (bias + ReLU, bf16) to p.vout instead of combining them; no entry tables.
+template <bool VOUT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_conv_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap) {
   constexpr int NS = C_NS, NT = C_NT;
@@ -494,12 +499,26 @@ tc_conv_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap) {
   const uint32_t sm_addr = raw_addr + pad;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int scene = blockIdx.x;
-  const int nu = p.nuniq[scene];
+  int nu, r0 = 0;
+  if (VOUT) {
+    const int count = __ldg(p.n_vrows);
+    const int per = (((count + (int)gridDim.x - 1) / (int)gridDim.x) + 15) & ~15;
+    r0 = (int)blockIdx.x * per;
+    nu = min(per, count - r0);
+    if (nu <= 0) return;
+  } else {
+    nu = p.nuniq[scene];
+  }
   const int A = p.n_anchor, n_ent = p.n_anchor * p.ent_per_anchor;
   float* S32 = p.epi.out_f32;
   __nv_bfloat16* S16 = p.epi.out_bf16;
+  const int HWp = p.H * p.W_;
+  using off_type = typename std::conditional<VOUT, long long, int>::type;
+  auto row_src = [&](int r) -> int {   // r already clamped to the CTA's rows
+    return VOUT ? __ldg(&p.vrows[r0 + r].x) : __ldg(p.upix + (size_t)scene * p.rcap + r);
+  };
 
-  if (nu == 0) {   // every sample point fell outside the grid: grid_sample returns zeros
+  if (!VOUT && nu == 0) {   // every sample point fell outside the grid: grid_sample returns zeros
     for (int i = threadIdx.x; i < A * D; i += TC_THREADS) {
       if (S32) S32[(size_t)scene * A * D + i] = 0.f;
       if (S16) S16[(size_t)scene * A * D + i] = __float2bfloat16_rn(0.f);
@@ -524,7 +543,7 @@ tc_conv_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap) {
     const int rb0 = threadIdx.x >> 3;
 #pragma unroll
     for (int i = 0; i < RPT; ++i)
-      yx0[i] = __ldg(p.upix + (size_t)scene * p.rcap + min(rb0 + 16 * i, nu - 1));
+      yx0[i] = row_src(min(rb0 + 16 * i, nu - 1));
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < NS; ++s) {
@@ -567,7 +586,7 @@ tc_conv_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap) {
     const int tid = threadIdx.x;
     const int j = tid & 7, rb = tid >> 3;
     const __nv_bfloat16* bev = reinterpret_cast<const __nv_bfloat16*>(p.bev) +
-                               (size_t)scene * p.H * p.W_ * D;
+                               (VOUT ? (size_t)0 : (size_t)scene * p.H * p.W_ * D);
     float* Vs = reinterpret_cast<float*>(sm);
     const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
     int g = 0;
@@ -579,12 +598,12 @@ tc_conv_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap) {
       // Loop-invariant per thread: the swizzled destination (row r = rb + 16 i always has
       // r & 7 == rb & 7, and consecutive i are 2048 B apart), the element offset of the row's
       // centre pixel and a 9-bit mask of the taps that fall inside the map.
-      int rowoff[RPT];
+      off_type rowoff[RPT];
       uint32_t vmask[RPT];
       if (pass > 0) {
 #pragma unroll
         for (int i = 0; i < RPT; ++i)
-          yx0[i] = __ldg(p.upix + (size_t)scene * p.rcap + min(row_base + rb + 16 * i, nu - 1));
+          yx0[i] = row_src(min(row_base + rb + 16 * i, nu - 1));
       }
 #pragma unroll
       for (int i = 0; i < RPT; ++i) {
@@ -592,9 +611,15 @@ tc_conv_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap) {
         rowoff[i] = 0;
         vmask[i] = 0;
         if (r < rows_valid) {
-          const int yx = yx0[i];   // (y << 16) | x
-          const int y = yx >> 16, x = yx & 0xffff;
-          rowoff[i] = (y * p.W_ + x) * D + j * 8;
+          int y, x;
+          if (VOUT) {   // pixel index in the batch
+            const int rem = yx0[i] % HWp;
+            y = rem / p.W_; x = rem - y * p.W_;
+            rowoff[i] = (off_type)yx0[i] * D + j * 8;
+          } else {      // (y << 16) | x
+            y = yx0[i] >> 16; x = yx0[i] & 0xffff;
+            rowoff[i] = (y * p.W_ + x) * D + j * 8;
+          }
           const uint32_t xm = (x > 0 ? 1u : 0u) | 2u | (x + 1 < p.W_ ? 4u : 0u);
           vmask[i] = (y > 0 ? xm : 0u) | (xm << 3) | (y + 1 < p.H ? (xm << 6) : 0u);
         }
@@ -612,7 +637,7 @@ tc_conv_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap) {
         for (int i = 0; i < RPT; ++i) {
           if (i < 8 * nt_active) {
             const bool ok = (vmask[i] >> tap) & 1u;
-            const int off = ok ? rowoff[i] + tapoff : 0;
+            const off_type off = ok ? rowoff[i] + tapoff : 0;
             cp_async16(a_dst + i * 2048, bev + off, ok ? 16u : 0u);
           }
         }
@@ -641,7 +666,36 @@ tc_conv_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap) {
       mbar_wait(bars.accum(), pass & 1);
       if (tid == 0) TL_STAMP(3, pass * 4 + 0, 1);
       tc_fence_after();
-      for (int half = 0; half < 2; ++half) {
+      if (VOUT) {
+        // ---------------- value rows out: thread = row (TMEM lane), 512 contiguous bytes
+        for (int t = 0; t < nt_active; ++t) {
+          const int r = t * TC_BM + warp * 32 + lane;
+          const bool rok = r < rows_valid;
+          const int vrow = rok ? __ldg(&p.vrows[r0 + row_base + r].y) : 0;
+          uint4* dst = reinterpret_cast<uint4*>(p.vout + (size_t)vrow * D);
+#pragma unroll 1
+          for (int cb = 0; cb < D / 32; ++cb) {
+            uint32_t u0[32];
+            tmem_ld32(trow + t * D + cb * 32, u0);
+            tmem_ld_wait();
+            if (rok) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint4 w;
+                uint32_t* wp = &w.x;
+#pragma unroll
+                for (int h2 = 0; h2 < 4; ++h2) {
+                  const __nv_bfloat162 hh = __floats2bfloat162_rn(fmaxf(__uint_as_float(u0[8 * q + 2 * h2]), 0.f),
+                                                                   fmaxf(__uint_as_float(u0[8 * q + 2 * h2 + 1]), 0.f));
+                  wp[h2] = *reinterpret_cast<const uint32_t*>(&hh);
+                }
+                dst[cb * 4 + q] = w;
+              }
+            }
+          }
+        }
+      }
+      for (int half = 0; half < (VOUT ? 0 : 2); ++half) {
         for (int t = 0; t < nt_active; ++t) {
           float* vrow = Vs + (size_t)(t * TC_BM + warp * 32 + lane) * C_VS_LD;
 #pragma unroll 1
@@ -1435,6 +1489,23 @@ tc_conv3_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap, in
         fence_proxy_async();
         tc_fence_before();
         mbar_arrive(vt_ready);
+        if (p.vout) {
+          // kept value rows (PlanReuse): row r of the scene, channel c, read back from the V^T operand while
+          // the combine MMAs run (the stores hide in the wait below); a warp writes 64 contiguous bytes per row
+          __nv_bfloat16* vo = p.vout + ((size_t)scene * p.vcap + row_base) * D + c;
+          const int vn = min(sp.rpp, nu - row_base);
+#pragma unroll 1
+          for (int k8 = 0; k8 * 8 < vn; ++k8) {
+            const uint4 w = *reinterpret_cast<const uint4*>(sm + (k8 >> 3) * C3_VT_CHUNK + c * 128 + (((k8 & 7) ^ (c & 7)) << 4));
+            const uint32_t wp[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int h2 = 0; h2 < 4; ++h2) {
+              const __nv_bfloat162 hh = *reinterpret_cast<const __nv_bfloat162*>(&wp[h2]);
+              if (k8 * 8 + 2 * h2 < vn) vo[(size_t)(k8 * 8 + 2 * h2) * D] = hh.x;
+              if (k8 * 8 + 2 * h2 + 1 < vn) vo[(size_t)(k8 * 8 + 2 * h2 + 1) * D] = hh.y;
+            }
+          }
+        }
         // ---- S rows of this pass: anchor a = 16 q + lane (lanes 0-15 of quarter q), columns 128 mt .. + 127
         mbar_wait(comb_done, pi & 1u);
         tc_fence_after();
@@ -1496,7 +1567,10 @@ int tc_engine_init() {
   cudaError_t e;
   e = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM);
   if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  e = cudaFuncSetAttribute(tc_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           227 * 1024);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(tc_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            227 * 1024);
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(tc_conv2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1543,7 +1617,20 @@ void launch_tc_conv(const GemmParams& p0, const CUtensorMap& wmap, int B, cudaSt
   else if (mode >= 1)
     tc_conv2_kernel<false><<<B < num_sms ? B : num_sms, C2_THREADS, tc_conv_smem_bytes(p.n_anchor, p.ent_per_anchor), st>>>(p, wmap, B);
   else
-    tc_conv_kernel<<<B, TC_THREADS, tc_conv_smem_bytes(p.n_anchor, p.ent_per_anchor), st>>>(p, wmap);
+    tc_conv_kernel<false><<<B, TC_THREADS, tc_conv_smem_bytes(p.n_anchor, p.ent_per_anchor), st>>>(p, wmap);
+}
+
+// value rows of the cross-scene list p.vrows[0 .. *p.n_vrows) -> p.vout (PlanReuse): the device-side count
+// is split evenly over one CTA per SM; CTAs without rows leave at once
+void launch_tc_convv(const GemmParams& p0, const CUtensorMap& wmap, cudaStream_t st) {
+  int dev = 0, num_sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  if (num_sms <= 0) num_sms = 148;
+  GemmParams p = p0;
+  p.n_anchor = 0;
+  p.ent_per_anchor = 0;
+  tc_conv_kernel<true><<<num_sms, TC_THREADS, tc_conv_smem_bytes(0, 0), st>>>(p, wmap);
 }
 
 // fp32 engine: the same persistent conv with fp32 operands on the tensor core as 3xTF32 (p.bev /

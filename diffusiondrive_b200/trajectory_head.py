@@ -486,7 +486,7 @@ class TrajectoryHead(nn.Module):
             size *= 4
 
     STAGES = ("bev_layout", "hoist_kv_ego", "init", "embed_encode", "plan", "conv", "combine",
-              "gemm_chain", "attn_core", "reg_finish", "select")
+              "gemm_chain", "attn_core", "reg_finish", "select", "conv_new")
 
     def set_concurrency(self, chunks: int, min_chunk_scenes: int = 512) -> None:
         """Scene-chunk concurrency of a forward (see ddh_set_concurrency in include/ddh.h)."""

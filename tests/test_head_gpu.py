@@ -458,7 +458,11 @@ def test_execution_options_do_not_change_results():
         head.set_profiling(False)
         for k in base:
             assert torch.equal(out[k], base[k]), (precision, "profiling", k)
-        assert prof["conv"]["spans"] == 4 and prof["conv"]["ms"] > 0
+        if precision == "bf16":   # chain engine: the second denoise step reuses the first one's value rows
+            assert prof["conv"]["spans"] == 2 and prof["conv_new"]["spans"] == 2 and prof["combine"]["spans"] == 2
+        else:
+            assert prof["conv"]["spans"] == 4
+        assert prof["conv"]["ms"] > 0
         assert sum(v["ms"] for v in prof.values()) > 0
         # 8-pixel segments converted on demand: a small part of the 512 segments of the map
         done = head.debug_tap("done_seg", np.uint32).reshape(-1, 16)[:B]
@@ -488,6 +492,63 @@ def test_execution_options_do_not_change_results():
     b = dyn(*argq, noise=nzq)
     for k in a:
         assert torch.equal(a[k], b[k]), ("conv_dynamic", k)
+
+
+def test_value_row_reuse_across_denoise_steps():
+    """value_proj(bev) of a layer (modules/blocks.py:114) does not depend on the denoise step: the chain
+    engine keeps the rows it evaluated and later steps evaluate only pixels no earlier step sampled
+    (option conv_reuse).  Checked against the fp32 oracle and against the engine without reuse, with
+    widened noise so that the second step samples many new pixels, and with three denoise steps."""
+    from oracle.head_oracle import forward_test
+    B = 64
+    ft = synth.make_features(B)
+    nz = synth.make_noise(B) * 6.0
+    args = (ft["ego_query"].cuda(), ft["agents_query"].cuda(), ft["bev_feature"].cuda())
+    head, sd = _make_head("bf16")
+    a = {k: v.clone() for k, v in head(*args, noise=nz.cuda()).items()}
+    rows = head.debug_tap("conv_rows", np.int32)
+    assert rows.shape[0] == 4 and (rows[:2] > 100 * B).all()
+    assert (rows[2:] > 0).all() and (rows[2:] < rows[:2]).all(), rows   # new pixels only
+    a2 = head(*args, noise=nz.cuda())
+    for k in a:
+        assert torch.equal(a[k], a2[k]), ("rerun", k)
+    head.set_option("conv_reuse", 0)
+    b = head(*args, noise=nz.cuda())
+    rows_off = head.debug_tap("conv_rows", np.int32)
+    assert (rows_off[2:] > rows[2:]).all()
+    ref = forward_test(sd, ft["ego_query"], ft["agents_query"], ft["bev_feature"], nz)
+    for tag, o in (("reuse", a), ("no-reuse", b)):
+        rec = _report("bf16 wide noise B=64 " + tag + " vs oracle",
+                      {k: v.cpu().numpy() for k, v in o.items()}, {k: v.numpy() for k, v in ref.items()})
+        assert rec["max_dxy_m"] <= TOL_BF16_M
+    d = (a["trajectory_modes"] - b["trajectory_modes"])[..., :2].abs().max().item()
+    assert d <= 1e-2, d
+    # default noise, ragged batch: nearly every pixel of the second step has a row already
+    Bq = 300
+    ftq = synth.make_features(Bq)
+    nzq = synth.make_noise(Bq).cuda()
+    argq = (ftq["ego_query"].cuda(), ftq["agents_query"].cuda(), ftq["bev_feature"].cuda())
+    head.set_option("conv_reuse", 1)
+    c = {k: v.clone() for k, v in head(*argq, noise=nzq).items()}
+    rows = head.debug_tap("conv_rows", np.int32)
+    assert (rows[2:] < rows[:2] // 10).all(), rows
+    head.set_option("conv_reuse", 0)
+    e = head(*argq, noise=nzq)
+    assert (c["trajectory_modes"] - e["trajectory_modes"])[..., :2].abs().max().item() <= 1e-2
+    assert (c["mode_idx"] == e["mode_idx"]).float().mean().item() >= 0.97
+    # three denoise steps: rows accumulate over two later steps
+    head3, sd3 = _make_head("bf16", step_num=3)
+    B3 = 40
+    ft3 = synth.make_features(B3)
+    nz3 = synth.make_noise(B3) * 4.0
+    arg3 = (ft3["ego_query"].cuda(), ft3["agents_query"].cuda(), ft3["bev_feature"].cuda())
+    o3 = {k: v.clone() for k, v in head3(*arg3, noise=nz3.cuda()).items()}
+    rows3 = head3.debug_tap("conv_rows", np.int32)
+    assert rows3.shape[0] == 6 and (rows3[2:] < rows3[:2].min()).all(), rows3
+    ref3 = forward_test(sd3, ft3["ego_query"], ft3["agents_query"], ft3["bev_feature"], nz3, step_num=3)
+    rec = _report("bf16 3 steps B=40 reuse vs oracle", {k: v.cpu().numpy() for k, v in o3.items()},
+                  {k: v.numpy() for k, v in ref3.items()})
+    assert rec["max_dxy_m"] <= TOL_BF16_M
 
 
 def test_scene_independence_and_determinism_full_size():
