@@ -157,6 +157,10 @@ struct ddh_handle {
   int* slot_cnt = nullptr;                     // [L][B]
   int2* new_list = nullptr;                    // [B * rcap] rows of the current call without a kept value
   int* new_count = nullptr;                    // [S*L] their number per conv call
+  // attention-weight logits hoisted into the encoder program of the chain engine (ChainArgs::logit_part)
+  float* attw_all = nullptr;                   // [L][P][256] the layers' attention_weights.weight, contiguous
+  float* logit_part = nullptr;                 // [tiles][2][128][CH_LOGITS]
+  bool logits_hoisted = false;
   unsigned int* need_seg = nullptr;            // [B][seg_nw32] BEV segments (+halo) the coming conv call reads
   unsigned int* done_seg = nullptr;            // [B][seg_nw32] BEV segments already converted to NHWC
   int lazy_layout = 1;                         // convert BEV segments on demand (NCHW input)
@@ -394,6 +398,10 @@ size_t ws_bytes_for(const ddh_shape& s, int B, int precision) {
   if (precision == DDH_PREC_BF16 && s.num_anchors <= 128) {   // chain engine: bf16 K|V, tiled q0
     const size_t spt = 128 / s.num_anchors, tiles = (B + spt - 1) / spt;
     b += (size_t)s.num_layers * B * s.num_agents * CH_KV_LD * 2 + tiles * 128 * Dm * 4;
+    if (s.num_steps >= 2 && B > RES_MAX_B) {   // kept value rows (conv_reuse; skipped when memory is short)
+      const size_t HWs = (size_t)s.bev_h * s.bev_w, vcap = std::min(HWs, (size_t)s.num_steps * rcap);
+      b += (size_t)s.num_layers * B * (vcap * Dm * 2 + HWs * 2 + 4) + (size_t)B * rcap * 8;
+    }
   }
   return b;
 }
@@ -458,6 +466,7 @@ int ensure_ws(ddh_handle* h, int B) {
       const size_t tiles = ((size_t)B + h->chain_spt - 1) / h->chain_spt;
       WS(h->kv16, (size_t)L * B * s.num_agents * CH_KV_LD);
       WS(h->q0t, tiles * 128 * D);
+      WS(h->logit_part, tiles * 2 * 128 * CH_LOGITS);
       rc = encode_wmap(h, &h->smap, h->s16, (int)M, D, 128);
       if (rc) return rc;
       // kept value rows: only when they take a modest share of the free memory (the engine works without)
@@ -841,6 +850,9 @@ int ddh_pack_weights(ddh_handle* h, const ddh_weight_ptrs* w, int precision, voi
     }
     TRY(copy_vec(h, &pl.attw_w, lw.bev_attw_w, (size_t)P * D, st));
     TRY(copy_vec(h, &pl.attw_b, lw.bev_attw_b, P, st));
+    if (l == 0) TRY(dev_alloc(h, h->owned_w, &h->attw_all, (size_t)L * P * D));
+    CU_TRY(h, cudaMemcpyAsync(h->attw_all + (size_t)l * P * D, lw.bev_attw_w, (size_t)P * D * sizeof(float),
+                              cudaMemcpyDeviceToDevice, st));
     TRY(pack_linear(h, pl.bev_out, lw.bev_out_w, lw.bev_out_b, D, D, st));
     TRY(pack_linear(h, pl.q, lw.agent_in_w, lw.agent_in_b, D, D, st));
     TRY(pack_linear(h, pl.kv, lw.agent_in_w + (size_t)D * D, lw.agent_in_b + D, 2 * D, D, st));
@@ -998,10 +1010,14 @@ bool build_enc_program(ddh_handle* h, int si, ChainArgs& a) {
   const int m0 = b.map(h->enc0.map), m3 = b.map(h->enc3.map);
   const int p_b0 = b.par(h->enc0.bias, D), p_g = b.par(h->enc_ln_g, D), p_b = b.par(h->enc_ln_b, D);
   const int p_b3 = b.par(h->enc3.bias, D), p_dt = b.par(h->dim_t, 32);
+  // attention-weight logits of every layer ride on the q0 epilogue when they fit (<= CH_LOGITS per row)
+  const int nlog = h->shp.num_layers * h->shp.num_poses;
+  h->logits_hoisted = h->shp.num_poses == 8 && nlog <= CH_LOGITS && h->attw_all != nullptr;
+  const int p_lw = h->logits_hoisted ? b.par(h->attw_all, nlog * D) : 0;
   int o = b.op(m0, 0, h->enc0.K / 64, 0, 0, 0, 0);
   b.step(o, 1, CE_RELU_LN, 0, 0, 0, {p_b0, p_g, p_b, 0, 0, p_dt});
   o = b.op(m3, 0, 4, 0, 0, 256, 0);
-  b.step(o, 1, CE_Q0, 0, 0, 256, {p_b3});
+  b.step(o, 1, CE_Q0, 0, 0, 256, {p_b3, p_lw, h->logits_hoisted ? nlog : 0});
   a.mode = 1;
   a.first_step = si == 0 ? 1 : 0;
   const float ac_tr = h->ac[h->shp.trunc_timestep];
@@ -1151,6 +1167,7 @@ int forward_fused(ddh_handle* h, const float* ego, const float* agents, const vo
     a.B = B; a.A = A; a.Na = Na; a.P = P; a.spt = spt; a.n_tiles = n_tiles;
     a.anchors = h->anchors; a.noise = noise; a.img = h->img; a.pts = h->pts; a.q0t = h->q0t;
     a.modes = modes; a.scores = scores; a.smap = h->smap; a.dbg = nullptr;
+    a.logit_part = h->logits_hoisted ? h->logit_part : nullptr;
   };
   const bool reuse = h->conv_reuse && h->vkeep && conv_mode == 2 && S >= 2;
   if (reuse) CU_TRY(h, cudaMemsetAsync(h->new_count, 0, (size_t)S * L * 4, st));
@@ -1174,6 +1191,7 @@ int forward_fused(ddh_handle* h, const float* ego, const float* agents, const vo
         ru.vcap = h->vcap;
         vkeep_l = h->vkeep + (size_t)l * B * h->vcap * D;
       }
+      if (h->logits_hoisted) { ru.logit_part = h->logit_part; ru.logit_ld = CH_LOGITS; ru.logit_off = l * P; }
       { ProfSpan ps(h, ST_PLAN, st);
       launch_plan(h->q0t, pl.attw_w, pl.attw_b, h->pts, h->upix, h->nuniq, h->ent_slot, h->ent_w,
                   h->conv_rows + si * L + l, lazy ? h->need_seg : nullptr, h->done_seg, seg_shift,

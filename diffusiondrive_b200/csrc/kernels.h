@@ -43,6 +43,10 @@ struct PlanReuse {
   int2* new_list = nullptr;
   int* new_count = nullptr;               // rows in new_list (zeroed before the forward)
   int vcap = 0;                           // row capacity per scene
+  // independent of mode: attention-weight logits hoisted into the chain engine's encoder program
+  // (ChainArgs::logit_part; needs q0_spt > 0 and 8 poses): the layer's 8 logits start at logit_off of logit_ld
+  const float* logit_part = nullptr;
+  int logit_ld = 0, logit_off = 0;
 };
 void launch_plan(const float* q0, const float* attw_w, const float* attw_b, const float* pts,
                  int* upix, int* nuniq, int* ent_slot, float* ent_w, int* rows_total,

@@ -765,6 +765,13 @@ __global__ void __launch_bounds__(CH_NT, 1) chain_kernel(const __grid_constant__
           case CE_Q0: {
             const float* b0 = par + st.par[0] + cbase;
             float4* q0 = reinterpret_cast<float4*>(args.q0t) + ((size_t)tile * 64 + hf * 32) * 128 + r;
+            // hoisted attention-weight logits: this thread's half of the dot products of its row (fp32, the
+            // plan kernel adds the two halves and the bias)
+            const int nlog = args.logit_part ? (int)st.par[2] : 0;
+            const float* lw = par + st.par[1] + cbase;
+            float lacc[CH_LOGITS];
+#pragma unroll
+            for (int o = 0; o < CH_LOGITS; ++o) lacc[o] = 0.f;
 #pragma unroll 1
             for (int b = 0; b < 4; ++b) {
               float v[32];
@@ -773,6 +780,28 @@ __global__ void __launch_bounds__(CH_NT, 1) chain_kernel(const __grid_constant__
 #pragma unroll
               for (int i = 0; i < 8; ++i)
                 q0[(size_t)(b * 8 + i) * 128] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+              if (nlog) {
+#pragma unroll
+                for (int o = 0; o < CH_LOGITS; ++o) {
+                  if (o < nlog) {
+                    const float4* w4 = reinterpret_cast<const float4*>(lw + o * 256 + b * 32);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                      const float4 w = w4[i];
+                      lacc[o] = fmaf(v[4 * i], w.x, lacc[o]);
+                      lacc[o] = fmaf(v[4 * i + 1], w.y, lacc[o]);
+                      lacc[o] = fmaf(v[4 * i + 2], w.z, lacc[o]);
+                      lacc[o] = fmaf(v[4 * i + 3], w.w, lacc[o]);
+                    }
+                  }
+                }
+              }
+            }
+            if (nlog) {
+              float4* lp = reinterpret_cast<float4*>(args.logit_part + (((size_t)tile * 2 + hf) * 128 + r) * CH_LOGITS);
+#pragma unroll
+              for (int o = 0; o < CH_LOGITS / 4; ++o)
+                lp[o] = make_float4(lacc[4 * o], lacc[4 * o + 1], lacc[4 * o + 2], lacc[4 * o + 3]);
             }
           } break;
           default: break;

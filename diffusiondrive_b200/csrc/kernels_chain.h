@@ -13,6 +13,7 @@ constexpr int CH_MAX_MAPS = 14;
 constexpr int CH_MAX_OPS = 24;
 constexpr int CH_MAX_STEPS = 16;
 constexpr int CH_MAX_PAR = 28;
+constexpr int CH_LOGITS = 16;        // attention-weight logits per row the encoder program can hoist (layers x poses)
 constexpr int CH_PAR_FLOATS = 7168;   // staged per-column vectors (bias, LayerNorm, FiLM, ...)
 constexpr int CH_KV_LD = 520;         // bf16 elements per hoisted K|V row (512 + 8 pad: conflict-free ldmatrix)
 
@@ -67,6 +68,10 @@ struct ChainArgs {
   float* img;
   float* pts;
   float* q0t;                                  // [tile][64][128] float4: q0 tiled so that a row per lane is coalesced
+  // encoder mode, optional: the attention-weight logits of every decoder layer (blocks.py:110: Linear(D -> P)
+  // of the layer-invariant queries) as two partial dot products per row, one per column half of the CE_Q0
+  // epilogue: [tile][2][128][CH_LOGITS]; steps[].par[1] = staged weights [n][256], par[2] = n (0: off)
+  float* logit_part;
   const __nv_bfloat16* kv16;                   // [B * Na][CH_KV_LD] hoisted K|V of this layer
   const float* egov;                           // [B][256] collapsed ego attention of this layer
   float* modes;

@@ -617,10 +617,26 @@ __global__ void __launch_bounds__(256, 6) plan_kernel(const float* __restrict__ 
   // ---- attention weights: P (=8) logits per anchor, softmax over the poses; the 8 x 256 head is
   // staged in shared memory once per CTA
   __shared__ __align__(16) float ww[8 * D];
+  if (ru.logit_part) {
+    // the chain engine's encoder program left the logits as two partial sums per row (kernels_chain.h)
+    if (tid < A) {
+      const int tile = scene / q0_spt, r = (scene - tile * q0_spt) * A + tid;
+      const float* p0 = ru.logit_part + (((size_t)tile * 2) * 128 + r) * ru.logit_ld + ru.logit_off;
+      const float* p1 = p0 + (size_t)128 * ru.logit_ld;
+      float e[8], mx = -INFINITY, den = 0.f;
+#pragma unroll
+      for (int o = 0; o < 8; ++o) { e[o] = (p0[o] + p1[o]) + attw_b[o]; mx = fmaxf(mx, e[o]); }
+#pragma unroll
+      for (int o = 0; o < 8; ++o) { e[o] = expf(e[o] - mx); den += e[o]; }
+#pragma unroll
+      for (int o = 0; o < 8; ++o) aw[tid * P + o] = e[o] / den;
+    }
+  } else {
   for (int i = tid; i < 8 * D / 4; i += 256)
     reinterpret_cast<float4*>(ww)[i] = __ldg(reinterpret_cast<const float4*>(attw_w) + i);
   __syncthreads();
-  for (int a = warp; a < A; a += 8) {
+  }
+  for (int a = warp; a < A && !ru.logit_part; a += 8) {
     float qv[8];
     if (q0_spt > 0) {
       // chain engine layout (kernels_chain.cu): [tile][64 column groups][128 rows] float4
@@ -858,7 +874,7 @@ void launch_combine(const float* V, const int* ent_slot, const float* ent_w, flo
 // One CTA per scene, one warp per anchor (round robin), one lane per 8 channels: an entry is one 512-byte
 // row read by the whole warp (L1/L2 hits after the scene's first touch of a row); lane k holds entry k.
 // ===================================================================================
-__global__ void __launch_bounds__(256) combine_rows_kernel(const __nv_bfloat16* __restrict__ V,
+__global__ void __launch_bounds__(256, 4) combine_rows_kernel(const __nv_bfloat16* __restrict__ V,
                                                            const int* __restrict__ ent_slot,
                                                            const float* __restrict__ ent_w,
                                                            __nv_bfloat16* __restrict__ s16, int A,

@@ -1463,6 +1463,43 @@ tc_conv3_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap, in
             *reinterpret_cast<__nv_bfloat16*>(sm + C3_WC_OFF + (rr >> 6) * TC_A_TILE + a * 128 +
                                               ((((rr & 63) >> 3) ^ (a & 7)) << 4) + (rr & 7) * 2) = __float2bfloat16_rn(msum[i]);
         }
+        // ---- kept value rows (PlanReuse, p.vout): the pass's rows of V go out transposed back from the V^T
+        // operand, one 8-pixel group per warp: lane = channel octet, eight 16-byte reads (channel (i + lane) & 7
+        // of the octet at step i: the eight lanes of a quarter warp hit eight different swizzle units), a register
+        // rotation by lane, an 8 x 8 transpose of bf16 (PRMT), and per pixel ONE 512-byte row written by the warp.
+        // The SM pushes ~27 B/clk of stores (2-byte stores: 17 B/clk), i.e. ~4.6 k cycles per pass, of which the
+        // combine wait below hides 2.4 k.  (Storing each 32-pixel block as soon as it is drained was slower: the
+        // stores stall the issuing warps, which then hold up the drain barriers.)
+        const int vn = min(sp.rpp, nu - row_base);
+        uint4* vo = p.vout ? reinterpret_cast<uint4*>(p.vout + ((size_t)scene * p.vcap + row_base) * D) + lane : nullptr;
+        auto store_group = [&](int k8) {
+          const uint8_t* src = sm + (k8 >> 3) * C3_VT_CHUNK + lane * 1024;
+          uint4 v[8], w[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = (i + lane) & 7;
+            v[i] = *reinterpret_cast<const uint4*>(src + r * 128 + (((k8 & 7) ^ r) << 4));
+          }
+          // w[j] = channel j of the octet = v[(j - lane) & 7]
+#pragma unroll
+          for (int j = 0; j < 8; ++j) w[j] = (lane & 1) ? v[(j + 7) & 7] : v[j];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = (lane & 2) ? w[(j + 6) & 7] : w[j];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) w[j] = (lane & 4) ? v[(j + 4) & 7] : v[j];
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            uint4 o;
+            uint32_t* op = &o.x;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              const uint32_t* a0 = &w[2 * m].x;
+              const uint32_t* a1 = &w[2 * m + 1].x;
+              op[m] = __byte_perm(a0[r >> 1], a1[r >> 1], (r & 1) ? 0x7632 : 0x5410);
+            }
+            if (k8 * 8 + r < vn) vo[(size_t)(k8 * 8 + r) * (D / 8)] = o;
+          }
+        };
         // ---- drain: this thread's channel row of V^T, 32 pixel rows at a time
         const int nblk = (sp.rpp + 31) >> 5;     // (a last half block reads 16 stale columns: never used as K)
 #pragma unroll 1
@@ -1489,23 +1526,12 @@ tc_conv3_kernel(const GemmParams p, const __grid_constant__ CUtensorMap wmap, in
         fence_proxy_async();
         tc_fence_before();
         mbar_arrive(vt_ready);
-        if (p.vout) {
-          // kept value rows (PlanReuse): row r of the scene, channel c, read back from the V^T operand while
-          // the combine MMAs run (the stores hide in the wait below); a warp writes 64 contiguous bytes per row
-          __nv_bfloat16* vo = p.vout + ((size_t)scene * p.vcap + row_base) * D + c;
-          const int vn = min(sp.rpp, nu - row_base);
+        if (vo) {   // all eight warps have drained: warp = groups ew, ew + 8, ...
+          named_bar_sync(1, C2_EPI);
 #pragma unroll 1
-          for (int k8 = 0; k8 * 8 < vn; ++k8) {
-            const uint4 w = *reinterpret_cast<const uint4*>(sm + (k8 >> 3) * C3_VT_CHUNK + c * 128 + (((k8 & 7) ^ (c & 7)) << 4));
-            const uint32_t wp[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-            for (int h2 = 0; h2 < 4; ++h2) {
-              const __nv_bfloat162 hh = *reinterpret_cast<const __nv_bfloat162*>(&wp[h2]);
-              if (k8 * 8 + 2 * h2 < vn) vo[(size_t)(k8 * 8 + 2 * h2) * D] = hh.x;
-              if (k8 * 8 + 2 * h2 + 1 < vn) vo[(size_t)(k8 * 8 + 2 * h2 + 1) * D] = hh.y;
-            }
-          }
+          for (int k8 = ew; k8 * 8 < vn; k8 += 8) store_group(k8);
         }
+        C2_STAMP(sidx == 1 && pass == 0 && etid == 0, 36);
         // ---- S rows of this pass: anchor a = 16 q + lane (lanes 0-15 of quarter q), columns 128 mt .. + 127
         mbar_wait(comb_done, pi & 1u);
         tc_fence_after();

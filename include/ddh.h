@@ -277,6 +277,14 @@ DDH_API int ddh_set_concurrency(ddh_handle *h, int chunks, int min_chunk_scenes)
  *                           pack time like the engine options
  *   "conv_dynamic"       1  tc_conv3_kernel deals scenes to its persistent CTAs on demand (global counter) instead
  *                           of round-robin: removes the end-of-launch tail of unequal scenes
+ *   "conv_reuse"         1  chain engine, >= 2 denoise steps: value_proj(bev) of a layer (blocks.py:114) does not
+ *                           depend on the denoise step, so the value rows the first step evaluated are kept
+ *                           (bf16 [layers][B][min(H*W, steps * rows)][256], allocated only when it takes less
+ *                           than a third of the free device memory) and later steps evaluate only the pixels
+ *                           no earlier step sampled (cross-scene tc_conv_kernel<true>) and combine over the
+ *                           kept rows (combine_rows_kernel); exact up to the bf16 rounding of the combine
+ *                           weights; 0: every step runs the full on-demand conv.  Changing it frees the
+ *                           workspace (synchronises)
  *   "chain_timeline"    -1  index (step * layers + layer) of the chain launch that stamps clock64
  *                           into the "dbg" tap (CTA 0, second tile)
  *   "debug_taps"         0  keep fp32 copies of intermediate activations for ddh_debug_copy
@@ -287,7 +295,7 @@ DDH_API int ddh_set_option(ddh_handle *h, const char *name, int value);
  * on the caller's stream.  ddh_get_profile synchronises and returns the summed duration and
  * the number of timed spans of one stage of the LAST forward.  Stages: "bev_layout",
  * "hoist_kv_ego", "init", "embed_encode", "plan", "conv", "combine", "gemm_chain",
- * "attn_core", "reg_finish", "select". */
+ * "attn_core", "reg_finish", "select", "conv_new" (value rows of later denoise steps, conv_reuse). */
 DDH_API int ddh_set_profiling(ddh_handle *h, int on);
 DDH_API int ddh_get_profile(ddh_handle *h, const char *stage, float *total_ms, int *spans);
 
