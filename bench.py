@@ -349,6 +349,19 @@ def run_ours(args):
                 ms_off = e0.elapsed_time(e1) / args.steps
                 reuse["off_ms_per_step"] = ms_off
                 reuse["off_per_gpu_value"] = B / (ms_off * 1e-3)
+                # the conv kernel without the kept rows it otherwise writes (4 launches per step)
+                head.set_profiling(True)
+                head(ego, agents, bev, noise=noise)
+                prof_off = head.stage_profile()
+                rows_off = head.debug_tap("conv_rows", np.int32)
+                head.set_profiling(False)
+                n_off = max(prof_off["conv"]["spans"], 1)
+                ms_conv_off = prof_off["conv"]["ms"] / n_off
+                if ms_conv_off > 0:
+                    ach_off = float(rows_off.sum()) / n_off * FLOP_PER_CONV_ROW / (ms_conv_off * 1e-3) / 1e12
+                    reuse["off_conv"] = {"launch_ms": ms_conv_off, "launches_per_step": n_off, "achieved": ach_off,
+                                         "unit": "TFLOP/s", "frac": ach_off / peaks["bf16_tflops_sustained"],
+                                         "frac_burst": ach_off / peaks["bf16_tflops"]}
             except Exception as ex:
                 reuse["off_error"] = repr(ex)
             finally:
