@@ -325,6 +325,24 @@ def run_ours(args):
         }
         if reuse_on:
             roofline["kernel"] += "; runs in the first denoise step only, later steps reuse its value rows"
+    # ---- whole step on SURVEY 8(d)'s formula: scenes/s x FLOP per scene / peak, on the FLOPs this schedule
+    # executes and on the reference's own schedule at the same unique pixels (a value_proj conv in every call)
+    whole = None
+    if precision == "bf16" and conv_rows.size:
+        chain_flop = 0.195e9                      # decoder chain + encoder per scene
+        n_calls = int(conv_rows.size)
+        exec_per_scene = float(conv_rows.sum()) / B * FLOP_PER_CONV_ROW + chain_flop
+        first = float(conv_rows[:n_conv].sum()) / max(n_conv, 1) if reuse_on else float(conv_rows.sum()) / n_calls
+        sched_per_scene = first * n_calls / B * FLOP_PER_CONV_ROW + chain_flop
+        whole = {"executed_gflop_per_scene": exec_per_scene / 1e9,
+                 "executed_tflops": value / world * exec_per_scene / 1e12,
+                 "executed_frac_sustained": value / world * exec_per_scene / 1e12 / peaks["bf16_tflops_sustained"],
+                 "every_call_conv_gflop_per_scene": sched_per_scene / 1e9,
+                 "every_call_conv_equiv_tflops": value / world * sched_per_scene / 1e12,
+                 "every_call_conv_equiv_frac_sustained": value / world * sched_per_scene / 1e12 / peaks["bf16_tflops_sustained"],
+                 "note": "executed = rows of every conv call (kept rows are not evaluated again) x 2*2304*256 + 0.195 GFLOP "
+                         "of chain per scene; every_call_conv = the same unique pixels evaluated in every call as the "
+                         "reference does (an equivalent rate, not executed work)"}
     # ---- value-row reuse across denoise steps: what it skipped, and the same timed loop without it
     reuse = None
     if reuse_on:
@@ -736,7 +754,7 @@ def run_ours(args):
             "gpu_launches_per_step": launches_per_step,
             "roofline": roofline, "roofline_hbm_stage": hbm, "cpu_baseline": cpu,
             "latency_b1": lat, "latency_b1_host": lat_host, "parity": parity, "nhwc_bf16_input": nhwc,
-            "value_row_reuse": reuse,
+            "value_row_reuse": reuse, "whole_step": whole,
             "extra_configs": extra_cfg, "full_agent_b1": full_agent, "allgather_ms": allgather_ms, "numa_binding": numa, "comm_log_tail": _nccl_log_tail(),
             "stage_ms": {k: round(v["ms"], 4) for k, v in prof.items()},
         }
