@@ -351,8 +351,10 @@ def run_ours(args):
                  "conv_new_ms": prof["conv_new"]["ms"], "combine_ms": prof["combine"]["ms"],
                  "note": "value_proj(bev) of a layer (modules/blocks.py:114) does not depend on the denoise step: "
                          "the rows the first step evaluated are kept and later steps evaluate only pixels no "
-                         "earlier step sampled (exact; the overlap is data dependent: the synthetic scenes with "
-                         "random-init weights move little between steps)"}
+                         "earlier step sampled (exact).  The overlap is structural in the reference's schedule: "
+                         "scheduler.step(k=10) with set_timesteps(1000) returns 0.9475 * img + 0.0525 * x0_pred, so the "
+                         "second step samples within 5 % of the first step's refinement of the same noisy anchors; "
+                         "no_overlap_* = the same schedule when every later pixel counts as new (conv_reuse 2)"}
         if not args.quick:
             try:
                 head.set_option("conv_reuse", 0)
@@ -382,6 +384,37 @@ def run_ours(args):
                                          "frac_burst": ach_off / peaks["bf16_tflops"]}
             except Exception as ex:
                 reuse["off_error"] = repr(ex)
+            finally:
+                head.set_option("conv_reuse", 1)
+                head(ego, agents, bev, noise=noise)
+                torch.cuda.synchronize()
+            # worst case of the schedule: the later steps treat every sampled pixel as new (conv_reuse 2), i.e.
+            # what the step costs when the trajectories of the second step share no pixel with the first
+            try:
+                head.set_option("conv_reuse", 2)
+                for _ in range(3):
+                    head(ego, agents, bev, noise=noise)
+                torch.cuda.synchronize()
+                k_s = max(3, min(args.steps, 10))
+                e0.record()
+                for _ in range(k_s):
+                    head(ego, agents, bev, noise=noise)
+                e1.record()
+                torch.cuda.synchronize()
+                ms_w = e0.elapsed_time(e1) / k_s
+                head.set_profiling(True)
+                head(ego, agents, bev, noise=noise)
+                prof_w = head.stage_profile()
+                head.set_profiling(False)
+                reuse["no_overlap_ms_per_step"] = ms_w
+                reuse["no_overlap_per_gpu_value"] = B / (ms_w * 1e-3)
+                reuse["no_overlap_conv_new_ms"] = prof_w["conv_new"]["ms"]
+                reuse["break_even_new_rows_frac"] = None
+                if "off_ms_per_step" in reuse and ms_w > ms_per_step:
+                    # step time is close to linear in the share of new rows between the two measured ends
+                    reuse["break_even_new_rows_frac"] = (reuse["off_ms_per_step"] - ms_per_step) / (ms_w - ms_per_step)
+            except Exception as ex:
+                reuse["no_overlap_error"] = repr(ex)
             finally:
                 head.set_option("conv_reuse", 1)
                 head(ego, agents, bev, noise=noise)

@@ -1182,7 +1182,7 @@ int forward_fused(ddh_handle* h, const float* ego, const float* agents, const vo
       PlanReuse ru;
       __nv_bfloat16* vkeep_l = nullptr;
       if (reuse) {
-        ru.mode = si == 0 ? 1 : 2;
+        ru.mode = si == 0 ? 1 : (h->conv_reuse == 2 ? 3 : 2);
         ru.keep = si + 1 < S;
         ru.slot_tab = h->slot_tab + (size_t)l * B * HW;
         ru.slot_cnt = h->slot_cnt + (size_t)l * B;
@@ -1210,7 +1210,7 @@ int forward_fused(ddh_handle* h, const float* ego, const float* agents, const vo
       gp.H = s.bev_h; gp.W_ = s.bev_w; gp.C = s.bev_channels;
       gp.epi.bias = pl.conv.bias; gp.epi.relu = 1;
       gp.vout = vkeep_l; gp.vcap = h->vcap;
-      if (ru.mode != 2) {
+      if (ru.mode < 2) {
         ProfSpan ps(h, ST_CONV, st);
         gp.dbg = (h->conv_timeline == si * L + l) ? h->dbg + 256 : nullptr;
         gp.ent_slot = h->ent_slot; gp.ent_w = h->ent_w; gp.n_anchor = A; gp.ent_per_anchor = P * 4;
@@ -1918,8 +1918,9 @@ int ddh_set_option(ddh_handle* h, const char* name, int value) {
   else if (n == "conv_timeline") h->conv_timeline = value;
   else if (n == "conv_dynamic") h->conv_dynamic = value;
   else if (n == "conv_reuse") {
+    if (value < 0 || value > 2) return fail(h, DDH_ERR_BAD_ARG, "ddh_set_option: conv_reuse must be 0, 1 or 2");
     if ((h->conv_reuse != 0) != (value != 0)) { cudaDeviceSynchronize(); free_all(h->owned_ws); h->cap_B = 0; h->vkeep = nullptr; h->chain_prog.clear(); }
-    h->conv_reuse = value != 0;
+    h->conv_reuse = value;
   }
   else if (n == "fp32_tensor_conv") { repack = h->fp32_tensor_conv != value; h->fp32_tensor_conv = value; }
   else if (n == "host_zero_copy") h->host_zero_copy = value;

@@ -34,7 +34,9 @@ void launch_embed(const float* img, float* pts, float* emb32, __nv_bfloat16* emb
 // later step only evaluates the pixels that have no row yet.
 //   mode 0  off;  1  first step: the scene's unique pixels go to upix as before and the pixel -> slot
 //   table is saved;  2  later step: sampled pixels without a row are appended to the cross-scene list
-//   new_list (x = pixel index in the batch, y = value row it fills) and get the scene's next slots
+//   new_list (x = pixel index in the batch, y = value row it fills) and get the scene's next slots;
+//   3  as 2, but the saved table is ignored: every sampled pixel of the step is evaluated again (validation /
+//   worst case of the schedule: option conv_reuse = 2)
 struct PlanReuse {
   int mode = 0;
   int keep = 1;                           // write the slot table back (0 in the last step)

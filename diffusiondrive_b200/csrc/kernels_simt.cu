@@ -605,6 +605,7 @@ __global__ void __launch_bounds__(256, 6) plan_kernel(const float* __restrict__ 
   // call samples.  A later denoise step of the same layer (ru.mode == 2) starts from the table the
   // earlier steps left: value_proj(bev) does not depend on the step, so only pixels without a row
   // are handed to the conv.
+  const bool later = ru.mode >= 2;   // a denoise step after the first (3: its pixels all count as new)
   if (ru.mode == 2) {
     const uint4* src = reinterpret_cast<const uint4*>(ru.slot_tab + (size_t)scene * HW);
     for (int i = tid; i < HW / 8; i += 256) reinterpret_cast<uint4*>(table)[i] = __ldg(src + i);
@@ -719,7 +720,7 @@ __global__ void __launch_bounds__(256, 6) plan_kernel(const float* __restrict__ 
     const int total = base + cnt;
     total_s = total;
     int have = 0, gbase = 0;
-    if (ru.mode == 2) {
+    if (later) {
       have = ru.slot_cnt[scene];
       gbase = total ? atomicAdd(ru.new_count, total) : 0;
     }
@@ -727,8 +728,8 @@ __global__ void __launch_bounds__(256, 6) plan_kernel(const float* __restrict__ 
     reuse_s[0] = have;
     reuse_s[1] = gbase;
   }
-  if (ru.mode == 2) __syncthreads();
-  const int have = ru.mode == 2 ? reuse_s[0] : 0, gbase = ru.mode == 2 ? reuse_s[1] : 0;
+  if (later) __syncthreads();
+  const int have = later ? reuse_s[0] : 0, gbase = later ? reuse_s[1] : 0;
   // segments covering the 3x3 neighbourhood of every unique pixel; a thread's pixels are
   // consecutive, so it marks [xmin - 1, xmax + 1] of rows y - 1 .. y + 1 once per row it touches
   const int segs_per_row = W >> seg_shift;
@@ -747,7 +748,7 @@ __global__ void __launch_bounds__(256, 6) plan_kernel(const float* __restrict__ 
   };
   auto take = [&](int i) {
     const int yy = i / W, xx = i - yy * W;
-    if (ru.mode == 2) {   // row of the cross-scene list: (pixel of the batch, value row it fills)
+    if (later) {   // row of the cross-scene list: (pixel of the batch, value row it fills)
       DDH_ASSERT(have + base < ru.vcap);
       ru.new_list[gbase + base] = make_int2(scene * HW + i, scene * ru.vcap + have + base);
     } else {
@@ -768,7 +769,7 @@ __global__ void __launch_bounds__(256, 6) plan_kernel(const float* __restrict__ 
   flush();
   __syncthreads();
   if (tid == 0) {
-    if (ru.mode != 2) nuniq[scene] = total_s;
+    if (!later) nuniq[scene] = total_s;
     if (rows_total) atomicAdd(rows_total, total_s);
   }
   if (ru.mode && ru.keep) {   // slot table for the next denoise step

@@ -283,8 +283,9 @@ DDH_API int ddh_set_concurrency(ddh_handle *h, int chunks, int min_chunk_scenes)
  *                           than a third of the free device memory) and later steps evaluate only the pixels
  *                           no earlier step sampled (cross-scene tc_conv_kernel<true>) and combine over the
  *                           kept rows (combine_rows_kernel); exact up to the bf16 rounding of the combine
- *                           weights; 0: every step runs the full on-demand conv.  Changing it frees the
- *                           workspace (synchronises)
+ *                           weights; 0: every step runs the full on-demand conv; 2: validation / worst case:
+ *                           the later steps use the same kernels but treat every sampled pixel as new.
+ *                           Switching between 0 and non-zero frees the workspace (synchronises)
  *   "chain_timeline"    -1  index (step * layers + layer) of the chain launch that stamps clock64
  *                           into the "dbg" tap (CTA 0, second tile)
  *   "debug_taps"         0  keep fp32 copies of intermediate activations for ddh_debug_copy

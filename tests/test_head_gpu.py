@@ -497,50 +497,72 @@ def test_execution_options_do_not_change_results():
 def test_value_row_reuse_across_denoise_steps():
     """value_proj(bev) of a layer (modules/blocks.py:114) does not depend on the denoise step: the chain
     engine keeps the rows it evaluated and later steps evaluate only pixels no earlier step sampled
-    (option conv_reuse).  Checked against the fp32 oracle and against the engine without reuse, with
-    widened noise so that the second step samples many new pixels, and with three denoise steps."""
+    (option conv_reuse).  Checked against the fp32 oracle and against the engine without reuse; with
+    conv_reuse = 2 (every pixel of the later steps treated as new: the later steps' kernels do all the
+    work, several passes per CTA); with a regression head scaled x10 so that the trajectories move by
+    metres between calls (partial overlap); and with three denoise steps."""
     from oracle.head_oracle import forward_test
     B = 64
     ft = synth.make_features(B)
-    nz = synth.make_noise(B) * 6.0
+    nz = synth.make_noise(B)
     args = (ft["ego_query"].cuda(), ft["agents_query"].cuda(), ft["bev_feature"].cuda())
     head, sd = _make_head("bf16")
     a = {k: v.clone() for k, v in head(*args, noise=nz.cuda()).items()}
     rows = head.debug_tap("conv_rows", np.int32)
     assert rows.shape[0] == 4 and (rows[:2] > 100 * B).all()
-    assert (rows[2:] > 0).all() and (rows[2:] < rows[:2]).all(), rows   # new pixels only
+    assert (rows[2:] < rows[:2] // 10).all(), rows   # new pixels only
     a2 = head(*args, noise=nz.cuda())
     for k in a:
         assert torch.equal(a[k], a2[k]), ("rerun", k)
     head.set_option("conv_reuse", 0)
     b = head(*args, noise=nz.cuda())
     rows_off = head.debug_tap("conv_rows", np.int32)
-    assert (rows_off[2:] > rows[2:]).all()
+    assert (rows_off[2:] > 100 * B).all()
     ref = forward_test(sd, ft["ego_query"], ft["agents_query"], ft["bev_feature"], nz)
     for tag, o in (("reuse", a), ("no-reuse", b)):
-        rec = _report("bf16 wide noise B=64 " + tag + " vs oracle",
+        rec = _report("bf16 B=64 " + tag + " vs oracle",
                       {k: v.cpu().numpy() for k, v in o.items()}, {k: v.numpy() for k, v in ref.items()})
         assert rec["max_dxy_m"] <= TOL_BF16_M
-    d = (a["trajectory_modes"] - b["trajectory_modes"])[..., :2].abs().max().item()
-    assert d <= 1e-2, d
-    # default noise, ragged batch: nearly every pixel of the second step has a row already
+    assert (a["trajectory_modes"] - b["trajectory_modes"])[..., :2].abs().max().item() <= 1e-2
+    # every pixel of the second step evaluated again by the later steps' kernels: ~250 rows per scene
+    # and call through the cross-scene conv (two passes per CTA at 300 scenes) + the gather combine
     Bq = 300
     ftq = synth.make_features(Bq)
     nzq = synth.make_noise(Bq).cuda()
     argq = (ftq["ego_query"].cuda(), ftq["agents_query"].cuda(), ftq["bev_feature"].cuda())
     head.set_option("conv_reuse", 1)
     c = {k: v.clone() for k, v in head(*argq, noise=nzq).items()}
-    rows = head.debug_tap("conv_rows", np.int32)
-    assert (rows[2:] < rows[:2] // 10).all(), rows
+    rows1 = head.debug_tap("conv_rows", np.int32)
+    assert (rows1[2:] < rows1[:2] // 10).all(), rows1
+    head.set_option("conv_reuse", 2)
+    d = {k: v.clone() for k, v in head(*argq, noise=nzq).items()}
+    rows2 = head.debug_tap("conv_rows", np.int32)
+    assert (np.abs(rows2[2:] - rows2[:2]) < rows2[:2] // 20).all() and (rows2[2:] > 148 * 256).all(), rows2
     head.set_option("conv_reuse", 0)
     e = head(*argq, noise=nzq)
-    assert (c["trajectory_modes"] - e["trajectory_modes"])[..., :2].abs().max().item() <= 1e-2
-    assert (c["mode_idx"] == e["mode_idx"]).float().mean().item() >= 0.97
+    for tag, x, y in (("all-new vs reuse", d, c), ("all-new vs off", d, e), ("reuse vs off", c, e)):
+        dd = (x["trajectory_modes"] - y["trajectory_modes"])[..., :2].abs().max().item()
+        assert dd <= 1e-2, (tag, dd)
+        assert (x["mode_idx"] == y["mode_idx"]).float().mean().item() >= 0.97, tag
+    # trajectories that move by metres between calls: scaled regression head, partial overlap
+    sd10 = {k: (v * 10.0 if "plan_reg_branch.4" in k else v) for k, v in sd.items()}
+    head10, _ = _make_head("bf16")
+    head10.load_state_dict(sd10)
+    f = {k: v.clone() for k, v in head10(*args, noise=nz.cuda()).items()}
+    rows10 = head10.debug_tap("conv_rows", np.int32)
+    assert (rows10[2:] > rows[2:]).all() and (rows10[2:] < rows10[:2]).all(), rows10
+    head10.set_option("conv_reuse", 0)
+    g = head10(*args, noise=nz.cuda())
+    ref10 = forward_test(sd10, ft["ego_query"], ft["agents_query"], ft["bev_feature"], nz)
+    rec = _report("bf16 B=64 reg head x10, reuse vs oracle", {k: v.cpu().numpy() for k, v in f.items()},
+                  {k: v.numpy() for k, v in ref10.items()})
+    assert rec["max_dxy_m"] <= 10 * TOL_BF16_M       # the head's rounding errors scale with its output
+    assert (f["trajectory_modes"] - g["trajectory_modes"])[..., :2].abs().max().item() <= 5e-2
     # three denoise steps: rows accumulate over two later steps
     head3, sd3 = _make_head("bf16", step_num=3)
     B3 = 40
     ft3 = synth.make_features(B3)
-    nz3 = synth.make_noise(B3) * 4.0
+    nz3 = synth.make_noise(B3)
     arg3 = (ft3["ego_query"].cuda(), ft3["agents_query"].cuda(), ft3["bev_feature"].cuda())
     o3 = {k: v.clone() for k, v in head3(*arg3, noise=nz3.cuda()).items()}
     rows3 = head3.debug_tap("conv_rows", np.int32)
@@ -549,6 +571,9 @@ def test_value_row_reuse_across_denoise_steps():
     rec = _report("bf16 3 steps B=40 reuse vs oracle", {k: v.cpu().numpy() for k, v in o3.items()},
                   {k: v.numpy() for k, v in ref3.items()})
     assert rec["max_dxy_m"] <= TOL_BF16_M
+    head3.set_option("conv_reuse", 2)
+    p3 = head3(*arg3, noise=nz3.cuda())
+    assert (p3["trajectory_modes"] - o3["trajectory_modes"])[..., :2].abs().max().item() <= 1e-2
 
 
 def test_scene_independence_and_determinism_full_size():
