@@ -476,6 +476,7 @@ int ensure_ws(ddh_handle* h, int B) {
       size_t free_b = 0, total_b = 0;
       cudaMemGetInfo(&free_b, &total_b);
       if (h->conv_reuse && s.num_steps >= 2 && B > RES_MAX_B && h->vcap < 0x7fff && (HWs & 7) == 0 &&
+          h->persistent_conv >= 2 && s.num_anchors <= 64 && s.num_poses == 8 &&   // (the shapes tc_conv3_kernel serves)
           (size_t)B * HWs < ((size_t)1 << 31) && (size_t)B * h->vcap < ((size_t)1 << 31) &&
           keep_bytes <= free_b / 3) {
         WS(h->vkeep, (size_t)L * B * h->vcap * D);
@@ -1914,7 +1915,10 @@ int ddh_set_option(ddh_handle* h, const char* name, int value) {
     h->dense_max_b = value;
   }
   else if (n == "chain_timeline") h->chain_timeline = value;
-  else if (n == "persistent_conv") h->persistent_conv = value;
+  else if (n == "persistent_conv") {
+    if ((h->persistent_conv >= 2) != (value >= 2)) { cudaDeviceSynchronize(); free_all(h->owned_ws); h->cap_B = 0; h->vkeep = nullptr; h->chain_prog.clear(); }
+    h->persistent_conv = value;
+  }
   else if (n == "conv_timeline") h->conv_timeline = value;
   else if (n == "conv_dynamic") h->conv_dynamic = value;
   else if (n == "conv_reuse") {

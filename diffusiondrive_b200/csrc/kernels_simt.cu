@@ -633,11 +633,11 @@ __global__ void __launch_bounds__(256, 6) plan_kernel(const float* __restrict__ 
       for (int o = 0; o < 8; ++o) aw[tid * P + o] = e[o] / den;
     }
   } else {
-  for (int i = tid; i < 8 * D / 4; i += 256)
-    reinterpret_cast<float4*>(ww)[i] = __ldg(reinterpret_cast<const float4*>(attw_w) + i);
-  __syncthreads();
+    for (int i = tid; i < 8 * D / 4; i += 256)
+      reinterpret_cast<float4*>(ww)[i] = __ldg(reinterpret_cast<const float4*>(attw_w) + i);
+    __syncthreads();
   }
-  for (int a = warp; a < A && !ru.logit_part; a += 8) {
+  for (int a = warp; a < A && !ru.logit_part; a += 8) {   // (in-kernel logits: other engines, > 16 logits per row)
     float qv[8];
     if (q0_spt > 0) {
       // chain engine layout (kernels_chain.cu): [tile][64 column groups][128 rows] float4
